@@ -1,0 +1,242 @@
+/*
+ * qsparse_b200 — C-ABI of the B200-native quantize/prune hot path.
+ *
+ * This header is the drop-in boundary.  Every entry point is a
+ * stateless launcher: plain device pointers + sizes + a cudaStream_t (passed as
+ * void*), no torch types, no allocation, no host synchronisation.  The caller
+ * owns every buffer (inputs, outputs, workspace).  Scalars that the reference
+ * derives on the device (learned decimal / scale / lines / threshold) stay on
+ * the device and are passed as pointers.
+ *
+ * Tensor layout convention: a contiguous fp32 tensor is described as
+ * [outer, channels, inner] (row-major).  Per-tensor parameters use
+ * channels == 1 (outer == 1, inner == numel).  The channel of flat element e
+ * is (e / inner) % channels.
+ *
+ * Return value: 0 on success, a positive cudaError_t on a CUDA failure, a
+ * negative QSB_E_* code on an argument error.  qsb_error_string() names both.
+ *
+ * "ref:" comments cite the file:line of mlzxy/qsparse v2.0.1 that the entry
+ * point replaces.
+ */
+#ifndef QSPARSE_B200_H_
+#define QSPARSE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSB_ABI_VERSION 1
+
+/* argument errors */
+#define QSB_E_BADARG (-1)     /* null pointer / negative size / bad enum        */
+#define QSB_E_WORKSPACE (-2)  /* workspace too small (see *_workspace_bytes)    */
+#define QSB_E_ALIGN (-3)      /* pointer not 4-byte aligned                     */
+#define QSB_E_UNSUPPORTED (-4)
+
+/* mask_kind */
+#define QSB_MASK_NONE 0
+#define QSB_MASK_CHANNEL 1 /* uint8 mask[channels]  (structured prune)          */
+#define QSB_MASK_ELEMENT 2 /* uint8 mask[numel]     (unstructured prune)        */
+
+/* `what` bits of qsb_reduce_stats */
+#define QSB_STAT_ABSMAX 1 /* max |x|            -> float  absmax[channels]      */
+#define QSB_STAT_MINMAX 2 /* min x, max x       -> float  mn[channels], mx[..]  */
+#define QSB_STAT_ABSSUM 4 /* sum |x| (fp64)     -> double abssum[channels]      */
+#define QSB_STAT_NNZ 8    /* count(x != 0), min x (whole tensor, for l0 mode)   */
+
+int qsb_abi_version(void);
+const char *qsb_error_string(int code);
+/* SM count and L2 size of the current device. */
+int qsb_device_info(int *sm_count, int64_t *l2_bytes);
+/* Benchmark-only knobs; defaults are what the product uses.
+ *   key 0: CTAs per SM of the streaming kernels (0 = occupancy-derived
+ *          persistent grid, -1 = one CTA per tile, non persistent). */
+int qsb_set_tuning(int key, int value);
+
+/* ------------------------------------------------------------------------
+ * K1  fake-quant forward.  y may alias x.  An optional prune mask is applied
+ * first (y = Q(x * mask)): that is the fused prune->quantize of K7.
+ * ---------------------------------------------------------------------- */
+
+/* ref: DecimalQuantization.forward  qsparse/quantize.py:30-63
+ *   y = float(int32_rz(x * 2^d)) * 2^-d          (the clamp at :56-62 is dead)
+ * decimal_dev: device float[n_decimal] (n_decimal == 1 or == channels), or NULL
+ * to use the host scalar decimal_host. */
+int qsb_fq_pow2_fwd(const float *x, float *y, const float *decimal_dev,
+                    int64_t n_decimal, double decimal_host,
+                    const uint8_t *mask_dev, int mask_kind, int64_t outer,
+                    int64_t channels, int64_t inner, void *stream);
+
+/* ref: ScalerQuantization.forward  qsparse/quantize.py:86-117
+ *   y = float(int32_rz(rint(x / s))) * s          (IEEE division) */
+int qsb_fq_scaler_fwd(const float *x, float *y, const float *scaler_dev,
+                      int64_t n_scaler, float scaler_host,
+                      const uint8_t *mask_dev, int mask_kind, int64_t outer,
+                      int64_t channels, int64_t inner, void *stream);
+
+/* ref: LineQuantization.forward  qsparse/quantize.py:140-181
+ * lines_dev: device float[n_lines][2] = (lo, hi) rows (n_lines == 1 or
+ * channels), or NULL to use (lo_host, hi_host).
+ * float_zero_point != 0: training form (:168-181); == 0: eval form (:161-166). */
+int qsb_fq_line_fwd(const float *x, float *y, const float *lines_dev,
+                    int64_t n_lines, float lo_host, float hi_host, int bits,
+                    int float_zero_point, const uint8_t *mask_dev,
+                    int mask_kind, int64_t outer, int64_t channels,
+                    int64_t inner, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K2  straight-through-estimator backward (and the fused prune backward).
+ * ref: DecimalQuantization.backward qsparse/quantize.py:65-77,
+ *      ScalerQuantization.backward  qsparse/quantize.py:119-131
+ *   v = clamp(g, (-L+notch)*s, (L-1+notch)*s), NaN -> 0,  L = 2^(bits-1)
+ *   s = 2^-d when scale_is_decimal, else the scaler itself.
+ * g_clamped_out: where v is written; pass g itself for the reference's in-place
+ *   side effect (quantize.py:72), or NULL to skip it.
+ * gx_out: where v * mask is written (the autograd of `x * mask`,
+ *   sparse.py:66,116); NULL when mask_kind == QSB_MASK_NONE.
+ * ---------------------------------------------------------------------- */
+int qsb_ste_bwd(const float *g, float *g_clamped_out, float *gx_out,
+                const float *scale_dev, int64_t n_scale, double scale_host,
+                int scale_is_decimal, int bits, int notch,
+                const uint8_t *mask_dev, int mask_kind, int64_t outer,
+                int64_t channels, int64_t inner, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K6  prune mask apply, forward and backward (same arithmetic).
+ * ref: `x * mask`  qsparse/sparse.py:66,116,122,263  (fp32 multiply by 0.0/1.0,
+ * so the sign of zero and inf*0 = NaN are preserved). y may alias x.
+ * ---------------------------------------------------------------------- */
+int qsb_mask_apply(const float *x, float *y, const uint8_t *mask_dev,
+                   int mask_kind, int64_t outer, int64_t channels,
+                   int64_t inner, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K3  statistic reductions, one read of x for any combination of `what`.
+ * ref: DecimalQuantizer.optimize  qsparse/quantize.py:329-340 (abs-max)
+ *      AdaptiveQuantizer.optimize qsparse/quantize.py:396-418 (min / max)
+ *      squeeze_tensor_to_shape    qsparse/util.py:79-99       (mean |x|)
+ *      MagnitudePruningCallback.update_magnitude sparse.py:85-87 (l0: x != 0)
+ * Outputs are per channel; unused outputs may be NULL.
+ *   absmax/mn/mx : float[channels]
+ *   abssum       : double[channels]   (fp64 accumulation, fixed order)
+ *   nnz          : double[channels]   count of x != 0
+ *   tensor_min   : float[1]           min over the whole tensor (l0 gate)
+ * Deterministic: two-stage with a fixed combination order, no float atomics.
+ * ---------------------------------------------------------------------- */
+int64_t qsb_reduce_workspace_bytes(int64_t outer, int64_t channels,
+                                   int64_t inner);
+int qsb_reduce_stats(const float *x, int what, int64_t outer, int64_t channels,
+                     int64_t inner, float *absmax, float *mn, float *mx,
+                     double *abssum, double *nnz, float *tensor_min,
+                     void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K4  tiny on-device parameter updates (no host sync).
+ * ---------------------------------------------------------------------- */
+
+/* ref: DecimalQuantizer.optimize qsparse/quantize.py:340,344-348
+ *   new = absmax / 2^(bits-1);  t == 0: w = new;  else w = (t*w + new)/(t+1) */
+int qsb_scale_ema(float *weight, const float *absmax, int64_t n, int bits,
+                  int64_t t, void *stream);
+
+/* ref: DecimalQuantizer.quantize qsparse/quantize.py:316
+ *   d = round(log2(nan_to_num(1/s, posinf=1, neginf=1))) */
+int qsb_scale_to_decimal(const float *scale, float *decimal, int64_t n,
+                         void *stream);
+
+/* ref: AdaptiveQuantizer.optimize qsparse/quantize.py:412-430
+ *   lines[c] = (w[c]*(t-1) + (mn[c], mx[c])) / t       (t >= 1, after increment)
+ * The min-of-mins / max-of-maxes over the batch (:415-418) is already folded
+ * into qsb_reduce_stats by passing outer = batch. */
+int qsb_lines_ema(float *lines, const float *mn, const float *mx,
+                  int64_t channels, int64_t t, void *stream);
+
+/* ref: MagnitudePruningCallback.update_magnitude qsparse/sparse.py:82-89 with a
+ * reduced (structured) magnitude:  m = abssum / count  (or nnz / count when
+ * use_l0 and *tensor_min == 0);  mag = (t*mag + m) / (t+1) */
+int qsb_magnitude_ema_reduced(float *magnitude, const double *abssum,
+                              const double *nnz, const float *tensor_min,
+                              int use_l0, int64_t channels, double count,
+                              int64_t t, void *stream);
+
+/* Same, full-size (unstructured) magnitude, fused with |x|:
+ *   mag[i] = (t*mag[i] + |x[i]|) / (t+1)            12 B/elem.
+ * use_l0 and *tensor_min == 0: |x| is replaced by (x != 0). */
+int qsb_magnitude_ema_full(float *magnitude, const float *x,
+                           const float *tensor_min, int use_l0, int64_t n,
+                           int64_t t, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K5  exact k-th value (ascending, 0-based rank k) by radix select on the
+ * order-preserving uint32 key; NaNs order last (like torch.sort).
+ * ref: calculate_mask_given_importance qsparse/util.py:113-116
+ *      (values = sort(flat); threshold = values[idx + 1])
+ * ---------------------------------------------------------------------- */
+int64_t qsb_kth_workspace_bytes(int64_t n);
+/* take_abs != 0 selects on |v| (importance = x.abs() without materialising it,
+ * running_average=False, qsparse/sparse.py:63-64). */
+int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
+                  float *thr_out_dev, void *workspace, int64_t workspace_bytes,
+                  void *stream);
+
+/* ref: calculate_mask_given_importance qsparse/util.py:117  mask = imp >= thr */
+int qsb_mask_from_threshold(const float *importance, int take_abs,
+                            const float *thr_dev, uint8_t *mask_out, int64_t n,
+                            void *stream);
+
+/* Fused unstructured mask build + apply (13 B/elem; 9 when importance aliases
+ * x with take_abs, i.e. running_average=False):
+ *   mask = imp >= thr;  y = x * mask           ref: qsparse/sparse.py:65-66 */
+int qsb_mask_build_apply(const float *importance, int take_abs,
+                         const float *thr_dev, const float *x, float *y,
+                         uint8_t *mask_out, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Fused structured prune -> pow2 quantize parameter step: everything the
+ * reference does between "statistics are reduced" and "apply" for
+ *   Sequential(PruneLayer(dimensions={channel}), QuantizeLayer(channelwise=-1))
+ * in one tiny kernel, on device:
+ *   magnitude EMA (sparse.py:89) -> threshold = sorted(mag)[k] (util.py:113-116)
+ *   -> mask = mag >= thr (util.py:117) -> absmax of kept channels
+ *   (= max |x*mask|, quantize.py:329-340) -> scale EMA (quantize.py:344-348)
+ *   -> decimal (quantize.py:316).
+ * refresh_mask == 0 keeps the existing mask (sparse.py:115-116).
+ * update_scale == 0 skips the quantizer's optimize (eval / before timeout).
+ * ---------------------------------------------------------------------- */
+int qsb_prune_quant_params(float *magnitude, uint8_t *mask, float *scale,
+                           float *decimal_out, const double *abssum,
+                           const float *absmax, int64_t channels, double count,
+                           int64_t t_prune, int update_magnitude,
+                           int refresh_mask, int64_t k, int bits,
+                           int64_t t_quant, int update_scale, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Host-buffer entry points (what a host-side caller that keeps its tensors in
+ * CPU memory binds to).  They stage through pinned memory owned by a context,
+ * pipeline H2D / kernels / D2H over chunks on several streams, and return after
+ * the results are in the host buffers.
+ * ---------------------------------------------------------------------- */
+typedef struct qsb_host_ctx qsb_host_ctx;
+int qsb_host_ctx_create(qsb_host_ctx **out, int64_t max_elems_per_chunk,
+                        int n_slots);
+int qsb_host_ctx_destroy(qsb_host_ctx *ctx);
+
+/* One fused training step of prune(dimensions={channel}) -> pow2 quantize on
+ * host tensors (config 2 of BASELINE.json): forward y = Q(x*mask) with this
+ * step's statistics, backward gx = clamp(g)*mask.  State (magnitude, mask,
+ * scale) lives on the device in caller-provided buffers. */
+int qsb_host_prune_quant_step(qsb_host_ctx *ctx, const float *x_host,
+                              const float *g_host, float *y_host,
+                              float *gx_host, float *magnitude_dev,
+                              uint8_t *mask_dev, float *scale_dev,
+                              float *decimal_dev, int64_t outer,
+                              int64_t channels, int64_t inner, int64_t t_prune,
+                              int64_t k, int bits, int64_t t_quant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSPARSE_B200_H_ */

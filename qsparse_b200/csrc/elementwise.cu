@@ -1,0 +1,543 @@
+// K1 / K2 / K6 / K7 and the full-size EMA: every elementwise op of the
+// quantize/prune hot path, as Op functors over the streaming map kernel.
+//
+// Arithmetic is written with explicit round-to-nearest intrinsics so that no
+// FMA contraction can happen (the reference rounds after every ATen op).
+#include <math.h>
+
+#include "map_kernel.cuh"
+
+namespace qsb {
+
+MapTuning &map_tuning() {
+  static MapTuning t{0};
+  return t;
+}
+
+// mask multiply exactly like `x * mask.float()`
+__device__ __forceinline__ float mask_mul(float x, bool keep) {
+  return __fmul_rn(x, keep ? 1.0f : 0.0f);
+}
+
+// torch.clamp(v, min=Tensor, max=Tensor): a NaN bound makes the result NaN.
+__device__ __forceinline__ float clamp_torch_tensor(float v, float lo,
+                                                    float hi) {
+  if (lo != lo || hi != hi) return __uint_as_float(0x7fc00000u);
+  return clamp_torch(v, lo, hi);
+}
+
+// ---------------------------------------------------------------------------
+// K1a  pow2 fake-quant   ref qsparse/quantize.py:44-63
+// ---------------------------------------------------------------------------
+template <int MASK>
+struct Pow2Op {
+  static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
+                        kOut0 = true, kOut1 = false, kOutB = false,
+                        kCanSkip = (MASK == QSB_MASK_CHANNEL);
+  const float *dec;  // device decimals or nullptr
+  int dec_stride;    // 0: one decimal for the tensor, 1: per channel
+  float toi_host, tof_host;
+  const uint8_t *cmask;
+  struct P {
+    float toi, tof, m;
+  };
+  __device__ __forceinline__ P params(int32_t c) const {
+    P p;
+    if (dec) {
+      const float d = __ldg(dec + (int64_t)c * dec_stride);
+      p.toi = pow2f_exact(d);
+      p.tof = pow2f_exact(-d);
+    } else {
+      p.toi = toi_host;
+      p.tof = tof_host;
+    }
+    p.m = 1.0f;
+    if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
+    return p;
+  }
+  __device__ __forceinline__ bool skip(const P &p) const { return p.m == 0.0f; }
+  __device__ __forceinline__ void apply(float a, float, uint8_t mb, const P &p,
+                                        float &o0, float &, uint8_t &) const {
+    float t = a;
+    if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
+    if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
+    // (x * toi).int() : truncation toward zero (cvt.rzi.s32.f32);
+    // q.float() * tof : the int round trip also erases the sign of zero.
+    const int q = __float2int_rz(__fmul_rn(t, p.toi));
+    o0 = __fmul_rn(__int2float_rn(q), p.tof);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// K1b  float-scale fake-quant   ref qsparse/quantize.py:100-117
+// ---------------------------------------------------------------------------
+template <int MASK>
+struct ScalerOp {
+  static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
+                        kOut0 = true, kOut1 = false, kOutB = false,
+                        kCanSkip = (MASK == QSB_MASK_CHANNEL);
+  const float *scale;
+  int scale_stride;
+  float scale_host;
+  const uint8_t *cmask;
+  struct P {
+    float s, m;
+  };
+  __device__ __forceinline__ P params(int32_t c) const {
+    P p;
+    p.s = scale ? __ldg(scale + (int64_t)c * scale_stride) : scale_host;
+    p.m = 1.0f;
+    if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
+    return p;
+  }
+  __device__ __forceinline__ bool skip(const P &p) const { return p.m == 0.0f; }
+  __device__ __forceinline__ void apply(float a, float, uint8_t mb, const P &p,
+                                        float &o0, float &, uint8_t &) const {
+    float t = a;
+    if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
+    if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
+    // (x / s).round().int() : IEEE divide, round-half-even, truncating cast
+    const int q = __float2int_rz(rintf(__fdiv_rn(t, p.s)));
+    o0 = __fmul_rn(__int2float_rn(q), p.s);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// K1c  asymmetric ("line") fake-quant   ref qsparse/quantize.py:148-181
+// ---------------------------------------------------------------------------
+template <int MASK, bool FZP>
+struct LineOp {
+  static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
+                        kOut0 = true, kOut1 = false, kOutB = false,
+                        kCanSkip = false;  // output depends on lo even for x = 0
+  const float *lines;  // [n][2] or nullptr
+  int lines_stride;    // 0 or 1 (in rows)
+  float lo_host, hi_host;
+  float n_levels;  // float(2^bits)
+  float q_max;     // float(2^bits - 1)
+  const uint8_t *cmask;
+  struct P {
+    float lo, hi, step, qstart, m;
+  };
+  __device__ __forceinline__ P params(int32_t c) const {
+    P p;
+    if (lines) {
+      const float2 l =
+          __ldg(reinterpret_cast<const float2 *>(lines) + (int64_t)c * lines_stride);
+      p.lo = l.x;
+      p.hi = l.y;
+    } else {
+      p.lo = lo_host;
+      p.hi = hi_host;
+    }
+    // step = (end - start) / N ; step[step == 0] = 0.0001   (:159-160)
+    p.step = __fdiv_rn(__fsub_rn(p.hi, p.lo), n_levels);
+    if (p.step == 0.0f) p.step = 0.0001f;
+    p.qstart = FZP ? 0.0f : rintf(__fdiv_rn(p.lo, p.step));  // (:163)
+    p.m = 1.0f;
+    if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
+    return p;
+  }
+  __device__ __forceinline__ bool skip(const P &) const { return false; }
+  __device__ __forceinline__ void apply(float a, float, uint8_t mb, const P &p,
+                                        float &o0, float &, uint8_t &) const {
+    float t = a;
+    if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
+    if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
+    const float xc = clamp_torch_tensor(t, p.lo, p.hi);  // (:158)
+    if constexpr (FZP) {
+      float q = __fdiv_rn(__fsub_rn(xc, p.lo), p.step);      // (:176-177)
+      q = clamp_torch(rintf(q), 0.0f, q_max);                // (:178)
+      o0 = __fadd_rn(__fmul_rn(q, p.step), p.lo);            // (:179-180)
+    } else {
+      float q = rintf(__fdiv_rn(xc, p.step));                         // (:162)
+      q = clamp_torch(__fsub_rn(q, p.qstart), 0.0f, q_max);           // (:164)
+      o0 = __fmul_rn(__fadd_rn(q, p.qstart), p.step);                 // (:165)
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// K2  STE backward (+ fused prune backward)   ref qsparse/quantize.py:65-77
+// ---------------------------------------------------------------------------
+template <int MASK, bool WRITE_GC, bool WRITE_GX>
+struct SteOp {
+  static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
+                        kOut0 = WRITE_GC, kOut1 = WRITE_GX, kOutB = false,
+                        kCanSkip = false;  // v * 0 keeps the sign of v
+  const float *scale;
+  int scale_stride;
+  float scale_host;  // already 2^-d when the host decimal is used
+  bool is_decimal;   // device values are decimals: s = 2^-d
+  float n_lo, n_hi;  // (-L + notch), (L - 1 + notch) as fp32
+  const uint8_t *cmask;
+  struct P {
+    float lo, hi, m;
+  };
+  __device__ __forceinline__ P params(int32_t c) const {
+    float s = scale_host;
+    if (scale) {
+      s = __ldg(scale + (int64_t)c * scale_stride);
+      if (is_decimal) s = pow2f_exact(-s);
+    }
+    P p;
+    p.lo = __fmul_rn(n_lo, s);
+    p.hi = __fmul_rn(n_hi, s);
+    p.m = 1.0f;
+    if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
+    return p;
+  }
+  __device__ __forceinline__ bool skip(const P &) const { return false; }
+  __device__ __forceinline__ void apply(float g, float, uint8_t mb, const P &p,
+                                        float &o0, float &o1, uint8_t &) const {
+    float v = clamp_torch_tensor(g, p.lo, p.hi);  // (:72-75)
+    if (v != v) v = 0.0f;                         // (:76) fires only for NaN
+    o0 = v;
+    if constexpr (MASK == QSB_MASK_CHANNEL)
+      o1 = __fmul_rn(v, p.m);
+    else if constexpr (MASK == QSB_MASK_ELEMENT)
+      o1 = mask_mul(v, mb != 0);
+    else
+      o1 = v;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// K6  mask apply   ref qsparse/sparse.py:66,116,122,263
+// ---------------------------------------------------------------------------
+template <int MASK>
+struct MaskApplyOp {
+  static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
+                        kOut0 = true, kOut1 = false, kOutB = false,
+                        kCanSkip = false;  // x * 0 keeps the sign of x
+  const uint8_t *cmask;
+  struct P {
+    float m;
+  };
+  __device__ __forceinline__ P params(int32_t c) const {
+    P p;
+    p.m = 1.0f;
+    if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
+    return p;
+  }
+  __device__ __forceinline__ bool skip(const P &) const { return false; }
+  __device__ __forceinline__ void apply(float a, float, uint8_t mb, const P &p,
+                                        float &o0, float &, uint8_t &) const {
+    if constexpr (MASK == QSB_MASK_ELEMENT)
+      o0 = mask_mul(a, mb != 0);
+    else
+      o0 = __fmul_rn(a, p.m);
+  }
+};
+
+// mask = importance >= threshold (+ optional y = x * mask)
+// ref qsparse/util.py:117, qsparse/sparse.py:65-66
+template <bool APPLY>
+struct MaskBuildOp {
+  static constexpr bool kIn1 = APPLY, kInB = false, kOut0 = APPLY,
+                        kOut1 = false, kOutB = true, kCanSkip = false;
+  const float *thr;
+  bool take_abs;
+  struct P {
+    float thr;
+  };
+  __device__ __forceinline__ P params(int32_t) const {
+    P p;
+    p.thr = __ldg(thr);
+    return p;
+  }
+  __device__ __forceinline__ bool skip(const P &) const { return false; }
+  __device__ __forceinline__ void apply(float imp, float x, uint8_t, const P &p,
+                                        float &o0, float &, uint8_t &ob) const {
+    if (take_abs) imp = fabsf(imp);
+    const bool keep = imp >= p.thr;  // false for NaN on either side
+    ob = keep ? 1 : 0;
+    if constexpr (APPLY) o0 = mask_mul(x, keep);
+  }
+};
+
+// full-size magnitude EMA   ref qsparse/sparse.py:85-89
+//   mag = (t * mag + |x|) / (t + 1)
+struct EmaFullOp {
+  static constexpr bool kIn1 = true, kInB = false, kOut0 = true, kOut1 = false,
+                        kOutB = false, kCanSkip = false;
+  const float *tensor_min;  // device scalar, only read when use_l0
+  bool use_l0;
+  float t_f, t_plus_1_f;
+  struct P {
+    bool indicator;
+  };
+  __device__ __forceinline__ P params(int32_t) const {
+    P p;
+    p.indicator = use_l0 && (__ldg(tensor_min) == 0.0f);
+    return p;
+  }
+  __device__ __forceinline__ bool skip(const P &) const { return false; }
+  __device__ __forceinline__ void apply(float x, float mag, uint8_t, const P &p,
+                                        float &o0, float &, uint8_t &) const {
+    const float ax = p.indicator ? (x != 0.0f ? 1.0f : 0.0f) : fabsf(x);
+    o0 = __fdiv_rn(__fadd_rn(__fmul_rn(t_f, mag), ax), t_plus_1_f);
+  }
+};
+
+}  // namespace qsb
+
+// ===========================================================================
+// C-ABI
+// ===========================================================================
+using namespace qsb;
+
+namespace {
+
+int check_layout(int64_t outer, int64_t channels, int64_t inner) {
+  if (outer < 0 || channels < 0 || inner < 0) return QSB_E_BADARG;
+  return 0;
+}
+
+int check_mask(const uint8_t *mask, int kind) {
+  if (kind != QSB_MASK_NONE && kind != QSB_MASK_CHANNEL &&
+      kind != QSB_MASK_ELEMENT)
+    return QSB_E_BADARG;
+  if (kind != QSB_MASK_NONE && !mask) return QSB_E_BADARG;
+  return 0;
+}
+
+// An element mask addresses the tensor flat, so the op itself only needs the
+// channel structure when its own parameters are per channel.
+template <class F>
+int dispatch_mask(int kind, F &&f) {
+  switch (kind) {
+    case QSB_MASK_NONE:
+      return f(std::integral_constant<int, QSB_MASK_NONE>{});
+    case QSB_MASK_CHANNEL:
+      return f(std::integral_constant<int, QSB_MASK_CHANNEL>{});
+    default:
+      return f(std::integral_constant<int, QSB_MASK_ELEMENT>{});
+  }
+}
+
+// n_param must be 1 or `channels`; returns the stride (0 / 1) or -1.
+int param_stride(int64_t n_param, int64_t channels) {
+  if (n_param == 1) return 0;
+  if (n_param == channels) return 1;
+  return -1;
+}
+
+// When neither the parameters nor the mask are per channel the tensor is
+// processed flat (no channel arithmetic in the kernel).
+Layout effective_layout(int64_t outer, int64_t channels, int64_t inner,
+                        bool per_channel) {
+  if (per_channel) return Layout{outer, channels, inner};
+  return Layout{1, 1, outer * channels * inner};
+}
+
+}  // namespace
+
+extern "C" int qsb_fq_pow2_fwd(const float *x, float *y,
+                               const float *decimal_dev, int64_t n_decimal,
+                               double decimal_host, const uint8_t *mask_dev,
+                               int mask_kind, int64_t outer, int64_t channels,
+                               int64_t inner, void *stream) {
+  if (int e = check_layout(outer, channels, inner)) return e;
+  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (outer * channels * inner == 0) return 0;
+  if (!x || !y) return QSB_E_BADARG;
+  int stride = 0;
+  if (decimal_dev) {
+    stride = param_stride(n_decimal, channels);
+    if (stride < 0) return QSB_E_BADARG;
+  }
+  const bool per_channel = stride == 1 || mask_kind == QSB_MASK_CHANNEL;
+  const Layout L = effective_layout(outer, channels, inner, per_channel);
+  MapIO io{x, nullptr, mask_kind == QSB_MASK_ELEMENT ? mask_dev : nullptr,
+           y, nullptr, nullptr};
+  // Python: toi = 2.0**decimal (double) then cast to the tensor dtype.
+  const float toi = (float)pow(2.0, decimal_host);
+  const float tof = (float)pow(2.0, -decimal_host);
+  return dispatch_mask(mask_kind, [&](auto mk) {
+    Pow2Op<decltype(mk)::value> op{decimal_dev, stride, toi, tof, mask_dev};
+    return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+        op, io, L, (cudaStream_t)stream);
+  });
+}
+
+extern "C" int qsb_fq_scaler_fwd(const float *x, float *y,
+                                 const float *scaler_dev, int64_t n_scaler,
+                                 float scaler_host, const uint8_t *mask_dev,
+                                 int mask_kind, int64_t outer, int64_t channels,
+                                 int64_t inner, void *stream) {
+  if (int e = check_layout(outer, channels, inner)) return e;
+  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (outer * channels * inner == 0) return 0;
+  if (!x || !y) return QSB_E_BADARG;
+  int stride = 0;
+  if (scaler_dev) {
+    stride = param_stride(n_scaler, channels);
+    if (stride < 0) return QSB_E_BADARG;
+  }
+  const bool per_channel = stride == 1 || mask_kind == QSB_MASK_CHANNEL;
+  const Layout L = effective_layout(outer, channels, inner, per_channel);
+  MapIO io{x, nullptr, mask_kind == QSB_MASK_ELEMENT ? mask_dev : nullptr,
+           y, nullptr, nullptr};
+  return dispatch_mask(mask_kind, [&](auto mk) {
+    ScalerOp<decltype(mk)::value> op{scaler_dev, stride, scaler_host, mask_dev};
+    return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+        op, io, L, (cudaStream_t)stream);
+  });
+}
+
+extern "C" int qsb_fq_line_fwd(const float *x, float *y, const float *lines_dev,
+                               int64_t n_lines, float lo_host, float hi_host,
+                               int bits, int float_zero_point,
+                               const uint8_t *mask_dev, int mask_kind,
+                               int64_t outer, int64_t channels, int64_t inner,
+                               void *stream) {
+  if (int e = check_layout(outer, channels, inner)) return e;
+  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (bits < 0 || bits > 62) return QSB_E_BADARG;
+  if (outer * channels * inner == 0) return 0;
+  if (!x || !y) return QSB_E_BADARG;
+  int stride = 0;
+  if (lines_dev) {
+    stride = param_stride(n_lines, channels);
+    if (stride < 0) return QSB_E_BADARG;
+    if (!aligned_to(lines_dev, 8)) return QSB_E_ALIGN;
+  }
+  const bool per_channel = stride == 1 || mask_kind == QSB_MASK_CHANNEL;
+  const Layout L = effective_layout(outer, channels, inner, per_channel);
+  MapIO io{x, nullptr, mask_kind == QSB_MASK_ELEMENT ? mask_dev : nullptr,
+           y, nullptr, nullptr};
+  const double N = ldexp(1.0, bits);
+  const float n_levels = (float)N;
+  const float q_max = (float)(N - 1.0);
+  return dispatch_mask(mask_kind, [&](auto mk) {
+    constexpr int MK = decltype(mk)::value;
+    if (float_zero_point) {
+      LineOp<MK, true> op{lines_dev, stride, lo_host, hi_host,
+                          n_levels,  q_max,  mask_dev};
+      return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+          op, io, L, (cudaStream_t)stream);
+    } else {
+      LineOp<MK, false> op{lines_dev, stride, lo_host, hi_host,
+                           n_levels,  q_max,  mask_dev};
+      return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+          op, io, L, (cudaStream_t)stream);
+    }
+  });
+}
+
+extern "C" int qsb_ste_bwd(const float *g, float *g_clamped_out, float *gx_out,
+                           const float *scale_dev, int64_t n_scale,
+                           double scale_host, int scale_is_decimal, int bits,
+                           int notch, const uint8_t *mask_dev, int mask_kind,
+                           int64_t outer, int64_t channels, int64_t inner,
+                           void *stream) {
+  if (int e = check_layout(outer, channels, inner)) return e;
+  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (outer * channels * inner == 0) return 0;
+  if (!g) return QSB_E_BADARG;
+  if (!g_clamped_out && !gx_out) return QSB_E_BADARG;
+  int stride = 0;
+  if (scale_dev) {
+    stride = param_stride(n_scale, channels);
+    if (stride < 0) return QSB_E_BADARG;
+  }
+  const bool per_channel = stride == 1 || mask_kind == QSB_MASK_CHANNEL;
+  const Layout L = effective_layout(outer, channels, inner, per_channel);
+  // limit = torch.tensor(2.0 ** (bits - 1)) (fp32); the bounds are fp32 ops.
+  const float limit = (float)pow(2.0, (double)bits - 1.0);
+  const float n_lo = -limit + (float)notch;
+  volatile float lm1 = limit - 1.0f;
+  const float n_hi = lm1 + (float)notch;
+  float s_host = (float)scale_host;
+  if (scale_is_decimal) s_host = (float)pow(2.0, -scale_host);
+  MapIO io{g, nullptr, mask_kind == QSB_MASK_ELEMENT ? mask_dev : nullptr,
+           g_clamped_out, gx_out, nullptr};
+  const bool gc = g_clamped_out != nullptr, gx = gx_out != nullptr;
+  return dispatch_mask(mask_kind, [&](auto mk) {
+    constexpr int MK = decltype(mk)::value;
+    auto run = [&](auto op) {
+      return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+          op, io, L, (cudaStream_t)stream);
+    };
+    if (gc && gx)
+      return run(SteOp<MK, true, true>{scale_dev, stride, s_host,
+                                       scale_is_decimal != 0, n_lo, n_hi,
+                                       mask_dev});
+    if (gc)
+      return run(SteOp<MK, true, false>{scale_dev, stride, s_host,
+                                        scale_is_decimal != 0, n_lo, n_hi,
+                                        mask_dev});
+    return run(SteOp<MK, false, true>{scale_dev, stride, s_host,
+                                      scale_is_decimal != 0, n_lo, n_hi,
+                                      mask_dev});
+  });
+}
+
+extern "C" int qsb_mask_apply(const float *x, float *y, const uint8_t *mask_dev,
+                              int mask_kind, int64_t outer, int64_t channels,
+                              int64_t inner, void *stream) {
+  if (int e = check_layout(outer, channels, inner)) return e;
+  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (mask_kind == QSB_MASK_NONE) return QSB_E_BADARG;
+  if (outer * channels * inner == 0) return 0;
+  if (!x || !y) return QSB_E_BADARG;
+  const Layout L = effective_layout(outer, channels, inner,
+                                    mask_kind == QSB_MASK_CHANNEL);
+  MapIO io{x, nullptr, mask_kind == QSB_MASK_ELEMENT ? mask_dev : nullptr,
+           y, nullptr, nullptr};
+  if (mask_kind == QSB_MASK_CHANNEL) {
+    MaskApplyOp<QSB_MASK_CHANNEL> op{mask_dev};
+    return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+        op, io, L, (cudaStream_t)stream);
+  }
+  MaskApplyOp<QSB_MASK_ELEMENT> op{mask_dev};
+  return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+      op, io, L, (cudaStream_t)stream);
+}
+
+extern "C" int qsb_set_tuning(int key, int value) {
+  if (key == 0) {
+    map_tuning().ctas_per_sm = value;
+    return 0;
+  }
+  return QSB_E_BADARG;
+}
+
+extern "C" int qsb_mask_from_threshold(const float *importance, int take_abs,
+                                       const float *thr_dev, uint8_t *mask_out,
+                                       int64_t n, void *stream) {
+  if (n < 0) return QSB_E_BADARG;
+  if (n == 0) return 0;
+  if (!importance || !thr_dev || !mask_out) return QSB_E_BADARG;
+  MapIO io{importance, nullptr, nullptr, nullptr, nullptr, mask_out};
+  MaskBuildOp<false> op{thr_dev, take_abs != 0};
+  return launch_map<decltype(op), Hint::KEEP, Hint::KEEP>(
+      op, io, Layout{1, 1, n}, (cudaStream_t)stream);
+}
+
+extern "C" int qsb_mask_build_apply(const float *importance, int take_abs,
+                                    const float *thr_dev, const float *x,
+                                    float *y, uint8_t *mask_out, int64_t n,
+                                    void *stream) {
+  if (n < 0) return QSB_E_BADARG;
+  if (n == 0) return 0;
+  if (!importance || !thr_dev || !x || !y || !mask_out) return QSB_E_BADARG;
+  MapIO io{importance, x, nullptr, y, nullptr, mask_out};
+  MaskBuildOp<true> op{thr_dev, take_abs != 0};
+  return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+      op, io, Layout{1, 1, n}, (cudaStream_t)stream);
+}
+
+extern "C" int qsb_magnitude_ema_full(float *magnitude, const float *x,
+                                      const float *tensor_min, int use_l0,
+                                      int64_t n, int64_t t, void *stream) {
+  if (n < 0 || t < 0) return QSB_E_BADARG;
+  if (n == 0) return 0;
+  if (!magnitude || !x) return QSB_E_BADARG;
+  if (use_l0 && !tensor_min) return QSB_E_BADARG;
+  MapIO io{x, magnitude, nullptr, magnitude, nullptr, nullptr};
+  EmaFullOp op{tensor_min, use_l0 != 0, (float)t, (float)(t + 1)};
+  return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
+      op, io, Layout{1, 1, n}, (cudaStream_t)stream);
+}

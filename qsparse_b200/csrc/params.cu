@@ -1,0 +1,284 @@
+// K4  tiny on-device parameter updates (scale / lines / magnitude EMAs, the
+// scale -> decimal derivation, the fused structured prune->quantize parameter
+// step) plus library plumbing (device properties, error strings).
+//
+// These kernels touch a few hundred bytes; what matters is that they run on
+// the device, in stream order, so the training step never synchronises with
+// the host (the reference does 6-8 `.item()` round trips per layer-step,
+// SURVEY Q17).
+#include <math.h>
+
+#include <mutex>
+
+#include "qsb_common.cuh"
+
+namespace qsb {
+
+const DeviceProps &device_props() {
+  static DeviceProps props[64];
+  static bool init[64] = {false};
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!init[dev]) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!init[dev]) {
+      int sm = 148, l2 = 0;
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+      props[dev].sm_count = sm > 0 ? sm : 148;
+      props[dev].l2_bytes = l2;
+      init[dev] = true;
+    }
+  }
+  return props[dev];
+}
+
+// new = absmax / 2^(bits-1); EMA with a host step counter.
+// ref qsparse/quantize.py:340,344-348
+__device__ __forceinline__ float scale_ema_step(float w, float absmax,
+                                                float limit, int64_t t) {
+  const float nw = __fdiv_rn(absmax, limit);
+  if (t == 0) return nw;
+  return __fdiv_rn(__fadd_rn(__fmul_rn((float)t, w), nw), (float)(t + 1));
+}
+
+// d = round(log2(nan_to_num(1 / s, posinf=1, neginf=1)))
+// ref qsparse/quantize.py:316.  log2 is evaluated in fp64 and rounded to fp32,
+// i.e. the correctly rounded fp32 log2, then rint (half to even).
+__device__ __forceinline__ float scale_to_decimal(float s) {
+  float r = __fdiv_rn(1.0f, s);
+  if (r != r) r = 0.0f;
+  else if (isinf(r)) r = 1.0f;
+  const float l = (float)log2((double)r);
+  return rintf(l);
+}
+
+// mag = (t * mag + m) / (t + 1)      ref qsparse/sparse.py:89
+__device__ __forceinline__ float magnitude_ema_step(float mag, float m,
+                                                    int64_t t) {
+  return __fdiv_rn(__fadd_rn(__fmul_rn((float)t, mag), m), (float)(t + 1));
+}
+
+__global__ void scale_ema_kernel(float *w, const float *absmax, int64_t n,
+                                 float limit, int64_t t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] = scale_ema_step(w[i], absmax[i], limit, t);
+}
+
+__global__ void scale_to_decimal_kernel(const float *s, float *d, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = scale_to_decimal(s[i]);
+}
+
+// lines = (w * (t - 1) + new) / t     ref qsparse/quantize.py:428-430
+__global__ void lines_ema_kernel(float *lines, const float *mn, const float *mx,
+                                 int64_t channels, float tm1, float t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < channels) {
+    lines[2 * i] = __fdiv_rn(__fadd_rn(__fmul_rn(lines[2 * i], tm1), mn[i]), t);
+    lines[2 * i + 1] =
+        __fdiv_rn(__fadd_rn(__fmul_rn(lines[2 * i + 1], tm1), mx[i]), t);
+  }
+}
+
+__global__ void magnitude_ema_reduced_kernel(float *mag, const double *abssum,
+                                             const double *nnz,
+                                             const float *tensor_min,
+                                             int use_l0, int64_t channels,
+                                             double count, int64_t t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= channels) return;
+  const bool indicator = use_l0 && (*tensor_min == 0.0f);
+  const float m = (float)((indicator ? nnz[i] : abssum[i]) / count);
+  mag[i] = magnitude_ema_step(mag[i], m, t);
+}
+
+// ---------------------------------------------------------------------------
+// fused structured prune -> pow2 quantize parameter step (one CTA)
+// ---------------------------------------------------------------------------
+constexpr int kFusedMaxChannels = 4096;
+
+__global__ void __launch_bounds__(1024)
+    prune_quant_params_kernel(float *magnitude, uint8_t *mask, float *scale,
+                              float *decimal_out, const double *abssum,
+                              const float *absmax, int channels, double count,
+                              int64_t t_prune, int update_magnitude,
+                              int refresh_mask, int64_t k, float limit,
+                              int64_t t_quant, int update_scale) {
+  __shared__ float s_imp[kFusedMaxChannels];
+  __shared__ uint32_t s_key[kFusedMaxChannels];
+  __shared__ float s_thr;
+  __shared__ uint32_t s_amax[32];
+  const int tid = threadIdx.x;
+
+  // 1. importance: running-average magnitude (update_magnitude == 1), the
+  //    existing magnitude (0), or this step's mean |x| itself (2:
+  //    running_average=False, sparse.py:63-64).
+  for (int c = tid; c < channels; c += blockDim.x) {
+    float imp;
+    if (update_magnitude == 2) {
+      imp = (float)(abssum[c] / count);
+    } else {
+      imp = magnitude[c];
+      if (update_magnitude == 1) {
+        imp = magnitude_ema_step(imp, (float)(abssum[c] / count), t_prune);
+        magnitude[c] = imp;
+      }
+    }
+    s_imp[c] = imp;
+    s_key[c] = float_to_key(imp);
+  }
+  __syncthreads();
+
+  // 2. threshold = sorted(importance)[k]; mask = importance >= threshold
+  if (refresh_mask) {
+    for (int c = tid; c < channels; c += blockDim.x) {
+      const uint32_t kc = s_key[c];
+      int rank = 0;
+      for (int j = 0; j < channels; ++j) {
+        const uint32_t kj = s_key[j];
+        rank += (kj < kc) || (kj == kc && j < c);
+      }
+      if (rank == k) s_thr = s_imp[c];
+    }
+    __syncthreads();
+    const float thr = s_thr;
+    for (int c = tid; c < channels; c += blockDim.x)
+      mask[c] = (s_imp[c] >= thr) ? 1 : 0;
+    __syncthreads();
+  }
+
+  // 3. abs-max of the pruned tensor = max over kept channels (pruned ones
+  //    contribute |0| = 0), scale EMA, decimal.
+  uint32_t am = 0;
+  if (update_scale) {
+    for (int c = tid; c < channels; c += blockDim.x) {
+      if (mask[c]) {
+        uint32_t b = __float_as_uint(absmax[c]) & 0x7fffffffu;
+        am = b > am ? b : am;
+      }
+    }
+    am = warp_reduce(am, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
+    if ((tid & 31) == 0) s_amax[tid >> 5] = am;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = scale[0];
+    if (update_scale) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        am = s_amax[w] > am ? s_amax[w] : am;
+      s = scale_ema_step(s, __uint_as_float(am), limit, t_quant);
+      scale[0] = s;
+    }
+    if (decimal_out) decimal_out[0] = scale_to_decimal(s);
+  }
+}
+
+}  // namespace qsb
+
+using namespace qsb;
+
+extern "C" int qsb_abi_version(void) { return QSB_ABI_VERSION; }
+
+extern "C" const char *qsb_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case QSB_E_BADARG: return "qsparse_b200: bad argument";
+    case QSB_E_WORKSPACE: return "qsparse_b200: workspace too small";
+    case QSB_E_ALIGN: return "qsparse_b200: pointer not sufficiently aligned";
+    case QSB_E_UNSUPPORTED: return "qsparse_b200: unsupported configuration";
+    default:
+      if (code > 0) return cudaGetErrorString((cudaError_t)code);
+      return "qsparse_b200: unknown error";
+  }
+}
+
+extern "C" int qsb_device_info(int *sm_count, int64_t *l2_bytes) {
+  int dev = 0;
+  QSB_CUDA_TRY(cudaGetDevice(&dev));
+  const DeviceProps &p = device_props();
+  if (sm_count) *sm_count = p.sm_count;
+  if (l2_bytes) *l2_bytes = p.l2_bytes;
+  return 0;
+}
+
+static inline unsigned blocks_for(int64_t n, int threads) {
+  return (unsigned)((n + threads - 1) / threads);
+}
+
+extern "C" int qsb_scale_ema(float *weight, const float *absmax, int64_t n,
+                             int bits, int64_t t, void *stream) {
+  if (n < 0 || t < 0) return QSB_E_BADARG;
+  if (n == 0) return 0;
+  if (!weight || !absmax) return QSB_E_BADARG;
+  const float limit = (float)pow(2.0, (double)bits - 1.0);
+  scale_ema_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      weight, absmax, n, limit, t);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qsb_scale_to_decimal(const float *scale, float *decimal,
+                                    int64_t n, void *stream) {
+  if (n < 0) return QSB_E_BADARG;
+  if (n == 0) return 0;
+  if (!scale || !decimal) return QSB_E_BADARG;
+  scale_to_decimal_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      scale, decimal, n);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qsb_lines_ema(float *lines, const float *mn, const float *mx,
+                             int64_t channels, int64_t t, void *stream) {
+  if (channels < 0 || t < 1) return QSB_E_BADARG;
+  if (channels == 0) return 0;
+  if (!lines || !mn || !mx) return QSB_E_BADARG;
+  lines_ema_kernel<<<blocks_for(channels, 256), 256, 0, (cudaStream_t)stream>>>(
+      lines, mn, mx, channels, (float)(t - 1), (float)t);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qsb_magnitude_ema_reduced(float *magnitude, const double *abssum,
+                                         const double *nnz,
+                                         const float *tensor_min, int use_l0,
+                                         int64_t channels, double count,
+                                         int64_t t, void *stream) {
+  if (channels < 0 || t < 0 || !(count > 0)) return QSB_E_BADARG;
+  if (channels == 0) return 0;
+  if (!magnitude || !abssum) return QSB_E_BADARG;
+  if (use_l0 && (!nnz || !tensor_min)) return QSB_E_BADARG;
+  magnitude_ema_reduced_kernel<<<blocks_for(channels, 256), 256, 0,
+                                 (cudaStream_t)stream>>>(
+      magnitude, abssum, nnz, tensor_min, use_l0, channels, count, t);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qsb_prune_quant_params(float *magnitude, uint8_t *mask,
+                                      float *scale, float *decimal_out,
+                                      const double *abssum, const float *absmax,
+                                      int64_t channels, double count,
+                                      int64_t t_prune, int update_magnitude,
+                                      int refresh_mask, int64_t k, int bits,
+                                      int64_t t_quant, int update_scale,
+                                      void *stream) {
+  if (channels <= 0 || channels > kFusedMaxChannels) return QSB_E_UNSUPPORTED;
+  if (!mask || !scale) return QSB_E_BADARG;
+  if (update_magnitude < 0 || update_magnitude > 2) return QSB_E_BADARG;
+  if (update_magnitude != 2 && !magnitude) return QSB_E_BADARG;
+  if (update_magnitude && (!abssum || !(count > 0))) return QSB_E_BADARG;
+  if (update_scale && !absmax) return QSB_E_BADARG;
+  if (refresh_mask && (k < 0 || k >= channels)) return QSB_E_BADARG;
+  const float limit = (float)pow(2.0, (double)bits - 1.0);
+  int threads = 32;
+  while (threads < channels && threads < 1024) threads <<= 1;
+  prune_quant_params_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(
+      magnitude, mask, scale, decimal_out, abssum, absmax, (int)channels, count,
+      t_prune, update_magnitude, refresh_mask, k, limit, t_quant, update_scale);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,260 @@
+// Shared device/host helpers for the qsparse_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/qsparse_b200.h"
+
+#ifndef QSB_THREADS
+#define QSB_THREADS 256
+#endif
+
+namespace qsb {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+#define QSB_CUDA_TRY(expr)                      \
+  do {                                          \
+    cudaError_t _e = (expr);                    \
+    if (_e != cudaSuccess) return (int)_e;      \
+  } while (0)
+
+#define QSB_LAUNCH_CHECK()                      \
+  do {                                          \
+    cudaError_t _e = cudaPeekAtLastError();     \
+    if (_e != cudaSuccess) return (int)_e;      \
+  } while (0)
+
+struct DeviceProps {
+  int sm_count;
+  int64_t l2_bytes;
+};
+// Cached per device (queried once; never synchronises).
+const DeviceProps &device_props();
+
+inline bool aligned_to(const void *p, uintptr_t a) {
+  return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0;
+}
+
+// ---------------------------------------------------------------------------
+// vector global-memory access.  V floats per access: 8 -> one 256-bit
+// LDG/STG (new on sm_100), 4 -> 128-bit, 1 -> scalar.
+// Loads: L1::no_allocate (every element is touched once per kernel); not .nc,
+// because several ops run in place (STE backward, EMA) and the read-only path
+// must not be used on memory the same kernel writes.
+//   KEEP  : default L2 policy  (a following pass may hit L2)
+//   STREAM: L2::evict_first    (nothing re-reads it; PTX allows the L2 level
+//           qualifier on the 256-bit forms only, 128-bit accesses ignore it)
+// Stores: L1::no_allocate; STREAM adds L2::evict_first so a write-once output
+// does not push re-usable input lines out of the 126 MB L2.
+// ---------------------------------------------------------------------------
+enum class Hint { KEEP, STREAM };
+
+template <int V>
+struct VecF {
+  float v[V];
+};
+
+template <int V, Hint H>
+__device__ __forceinline__ VecF<V> ld_vec(const float *p) {
+  VecF<V> r;
+  if constexpr (V == 8) {
+    if constexpr (H == Hint::STREAM) {
+      asm volatile(
+          "ld.global.L1::no_allocate.L2::evict_first.v8.f32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]),
+            "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+          : "l"(p));
+    } else {
+      asm volatile(
+          "ld.global.L1::no_allocate.v8.f32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]),
+            "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+          : "l"(p));
+    }
+  } else if constexpr (V == 4) {
+    if constexpr (H == Hint::STREAM) {
+      asm volatile(
+          "ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+          : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+          : "l"(p));
+    } else {
+      asm volatile(
+          "ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+          : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+          : "l"(p));
+    }
+  } else {
+    static_assert(V == 1, "V must be 1, 4 or 8");
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+
+template <int V, Hint H>
+__device__ __forceinline__ void st_vec(float *p, const VecF<V> &r) {
+  if constexpr (V == 8) {
+    if constexpr (H == Hint::STREAM) {
+      asm volatile(
+          "st.global.L1::no_allocate.L2::evict_first.v8.f32 [%0], "
+          "{%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+          "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]),
+          "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+          : "memory");
+    } else {
+      asm volatile(
+          "st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+          "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]),
+          "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+          : "memory");
+    }
+  } else if constexpr (V == 4) {
+    if constexpr (H == Hint::STREAM) {
+      asm volatile(
+          "st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+          "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3])
+          : "memory");
+    } else {
+      asm volatile(
+          "st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+          "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3])
+          : "memory");
+    }
+  } else {
+    p[0] = r.v[0];
+  }
+}
+
+// V mask bytes (uint8 0/1) for V consecutive elements.
+template <int V>
+struct VecB {
+  uint8_t b[V];
+};
+
+template <int V>
+__device__ __forceinline__ VecB<V> ld_bytes(const uint8_t *p) {
+  VecB<V> r;
+  if constexpr (V == 8) {
+    uint2 w = __ldg(reinterpret_cast<const uint2 *>(p));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      r.b[j] = (w.x >> (8 * j)) & 0xff;
+      r.b[4 + j] = (w.y >> (8 * j)) & 0xff;
+    }
+  } else if constexpr (V == 4) {
+    uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.b[j] = (w >> (8 * j)) & 0xff;
+  } else {
+    r.b[0] = __ldg(p);
+  }
+  return r;
+}
+
+template <int V>
+__device__ __forceinline__ void st_bytes(uint8_t *p, const VecB<V> &r) {
+  if constexpr (V == 8) {
+    uint2 w;
+    w.x = r.b[0] | (r.b[1] << 8) | (r.b[2] << 16) | ((uint32_t)r.b[3] << 24);
+    w.y = r.b[4] | (r.b[5] << 8) | (r.b[6] << 16) | ((uint32_t)r.b[7] << 24);
+    *reinterpret_cast<uint2 *>(p) = w;
+  } else if constexpr (V == 4) {
+    uint32_t w =
+        r.b[0] | (r.b[1] << 8) | (r.b[2] << 16) | ((uint32_t)r.b[3] << 24);
+    *reinterpret_cast<uint32_t *>(p) = w;
+  } else {
+    p[0] = r.b[0];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// exact arithmetic helpers (every ATen op in the reference rounds separately:
+// no FMA contraction, IEEE division)
+// ---------------------------------------------------------------------------
+
+// 2^d for a float d the way torch.pow(2.0, d) gives it for integral d: exact,
+// including subnormal results and overflow to inf.  Non-integral d -> exp2f.
+__device__ __forceinline__ float pow2f_exact(float d) {
+  if (d == rintf(d) && fabsf(d) < 400.f) return ldexpf(1.0f, (int)d);
+  return exp2f(d);  // also +-inf and NaN
+}
+
+// torch.clamp(v, lo, hi) with scalar/tensor bounds: NaN in v propagates,
+// lo > hi gives hi (min(max(v, lo), hi)).
+__device__ __forceinline__ float clamp_torch(float v, float lo, float hi) {
+  float t = (v < lo) ? lo : v;
+  return (t > hi) ? hi : t;
+}
+
+// order-preserving float -> uint32 key; every NaN maps to the largest key so
+// NaNs order last like torch.sort.
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+  uint32_t b = __float_as_uint(f);
+  if ((b & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  if (k == 0xffffffffu) return __uint_as_float(0x7fc00000u);
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+// ---------------------------------------------------------------------------
+// flat element index -> (column in row, channel) without divisions in the loop
+// ---------------------------------------------------------------------------
+struct Layout {
+  int64_t outer, channels, inner;
+  __host__ __device__ int64_t numel() const { return outer * channels * inner; }
+};
+
+struct ChanPos {
+  int64_t col;  // position inside the current row, [0, inner)
+  int32_t c;    // channel, [0, channels)
+};
+
+__device__ __forceinline__ ChanPos chan_pos_of(int64_t e, const Layout &L) {
+  ChanPos p;
+  int64_t row = e / L.inner;
+  p.col = e - row * L.inner;
+  p.c = (int32_t)(row % L.channels);
+  return p;
+}
+
+// Constant advance of a ChanPos by `step` elements (step_rows = step / inner
+// reduced mod channels, step_cols = step % inner; both precomputed on the host).
+struct ChanStep {
+  int64_t cols;
+  int32_t chans;
+};
+inline ChanStep make_chan_step(int64_t step, const Layout &L) {
+  ChanStep s;
+  s.cols = step % L.inner;
+  s.chans = (int32_t)((step / L.inner) % L.channels);
+  return s;
+}
+__device__ __forceinline__ void advance(ChanPos &p, const ChanStep &s,
+                                        const Layout &L) {
+  p.col += s.cols;
+  p.c += s.chans;
+  if (p.col >= L.inner) {
+    p.col -= L.inner;
+    p.c += 1;
+  }
+  if (p.c >= (int32_t)L.channels) p.c -= (int32_t)L.channels;
+  if (p.c >= (int32_t)L.channels) p.c -= (int32_t)L.channels;
+}
+
+// ---------------------------------------------------------------------------
+// warp reductions
+// ---------------------------------------------------------------------------
+template <class T, class F>
+__device__ __forceinline__ T warp_reduce(T v, F f) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = f(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace qsb

@@ -1,0 +1,443 @@
+// K3  statistic reductions: abs-max, min/max, sum|x| (fp64) and count(x != 0),
+// per tensor or per channel of an [outer, channels, inner] tensor, in ONE read
+// of x (4 B/elem), deterministic (two stages, fixed combination order, no
+// floating-point atomics).
+//
+// Stage 1 has two shapes:
+//   row mode    (inner >= 64): one warp per (row, segment) work item, 256-bit
+//                loads with a scalar head/tail peel for rows that do not start
+//                on a 32-byte boundary;
+//   column mode (inner  < 64): the tensor is [outer, channels*inner]; one
+//                thread per column (or 4 columns) walks a chunk of rows, so a
+//                warp still reads contiguous 128/512-byte lines.
+// Stage 2 (finalize) combines the partials of each channel in a fixed order.
+#include <math.h>
+
+#include "qsb_common.cuh"
+
+namespace qsb {
+
+constexpr int kRowModeMinInner = 64;
+
+struct Partials {
+  uint32_t *amax;  // bits of max |x|  (NaN bit patterns order above inf)
+  float *mn;
+  float *mx;
+  double *asum;
+  double *nnz;
+};
+
+template <int WHAT>
+struct Acc {
+  uint32_t amax = 0;
+  float mn = INFINITY, mx = -INFINITY;
+  bool nan = false;
+  double asum = 0.0;
+  uint32_t nnz = 0;
+  __device__ __forceinline__ void add(float v) {
+    if constexpr (WHAT & QSB_STAT_ABSMAX) {
+      uint32_t b = __float_as_uint(v) & 0x7fffffffu;
+      amax = b > amax ? b : amax;
+    }
+    if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+      mn = fminf(mn, v);
+      nan |= (v != v);
+    }
+    if constexpr (WHAT & QSB_STAT_MINMAX) mx = fmaxf(mx, v);
+    if constexpr (WHAT & QSB_STAT_ABSSUM) asum += (double)fabsf(v);
+    if constexpr (WHAT & QSB_STAT_NNZ) nnz += (v != 0.0f) ? 1u : 0u;
+  }
+};
+
+__device__ __forceinline__ float nan_f() { return __uint_as_float(0x7fc00000u); }
+
+template <int WHAT>
+__device__ __forceinline__ void warp_store(const Acc<WHAT> &a_in, int lane,
+                                           const Partials &P, int64_t item) {
+  Acc<WHAT> a = a_in;
+  if constexpr (WHAT & QSB_STAT_ABSMAX) {
+    a.amax = warp_reduce(a.amax, [](uint32_t x, uint32_t y) { return x > y ? x : y; });
+    if (lane == 0) P.amax[item] = a.amax;
+  }
+  if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+    int nan = __any_sync(0xffffffffu, a.nan);
+    a.mn = warp_reduce(a.mn, [](float x, float y) { return fminf(x, y); });
+    if (lane == 0) P.mn[item] = nan ? nan_f() : a.mn;
+    if constexpr (WHAT & QSB_STAT_MINMAX) {
+      a.mx = warp_reduce(a.mx, [](float x, float y) { return fmaxf(x, y); });
+      if (lane == 0) P.mx[item] = nan ? nan_f() : a.mx;
+    }
+  }
+  if constexpr (WHAT & QSB_STAT_ABSSUM) {
+    a.asum = warp_reduce(a.asum, [](double x, double y) { return x + y; });
+    if (lane == 0) P.asum[item] = a.asum;
+  }
+  if constexpr (WHAT & QSB_STAT_NNZ) {
+    a.nnz = warp_reduce(a.nnz, [](uint32_t x, uint32_t y) { return x + y; });
+    if (lane == 0) P.nnz[item] = (double)a.nnz;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// stage 1, row mode
+// ---------------------------------------------------------------------------
+template <int WHAT>
+__global__ void __launch_bounds__(QSB_THREADS)
+    reduce_rows_kernel(const float *__restrict__ x, int64_t rows, int64_t inner,
+                       int64_t seg, int64_t segs_per_row, Partials P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (QSB_THREADS / 32);
+  const int64_t items = rows * segs_per_row;
+  for (int64_t item = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
+       item < items; item += warps_total) {
+    const int64_t row = item / segs_per_row;
+    const int64_t s = item - row * segs_per_row;
+    const int64_t c0 = s * seg;
+    const int64_t c1 = (c0 + seg < inner) ? c0 + seg : inner;
+    const float *p = x + row * inner + c0;
+    const int64_t len = c1 - c0;
+    Acc<WHAT> acc;
+    // head: scalars up to the first 32-byte boundary
+    int64_t head = ((32 - (reinterpret_cast<uintptr_t>(p) & 31)) & 31) >> 2;
+    if (head > len) head = len;
+    if (lane < head) acc.add(p[lane]);
+    const float *pv = p + head;
+    const int64_t nv = (len - head) >> 3;
+    // body: 256-bit loads, 4 in flight per lane
+    int64_t j = lane;
+    for (; j + 96 < nv; j += 128) {
+      VecF<8> v0 = ld_vec<8, Hint::KEEP>(pv + (j << 3));
+      VecF<8> v1 = ld_vec<8, Hint::KEEP>(pv + ((j + 32) << 3));
+      VecF<8> v2 = ld_vec<8, Hint::KEEP>(pv + ((j + 64) << 3));
+      VecF<8> v3 = ld_vec<8, Hint::KEEP>(pv + ((j + 96) << 3));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc.add(v0.v[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc.add(v1.v[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc.add(v2.v[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc.add(v3.v[k]);
+    }
+    for (; j < nv; j += 32) {
+      VecF<8> v0 = ld_vec<8, Hint::KEEP>(pv + (j << 3));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc.add(v0.v[k]);
+    }
+    // tail
+    const int64_t done = head + (nv << 3);
+    if (done + lane < len) acc.add(p[done + lane]);
+    warp_store<WHAT>(acc, lane, P, item);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// stage 1, column mode.  partial index = chunk * ncols + col
+// ---------------------------------------------------------------------------
+template <int WHAT, int V>
+__global__ void __launch_bounds__(QSB_THREADS)
+    reduce_cols_kernel(const float *__restrict__ x, int64_t nrows, int64_t ncols,
+                       int64_t rows_per_chunk, Partials P) {
+  const int64_t vcols = ncols / V;  // V == 4 requires ncols % 4 == 0
+  const int64_t vc = (int64_t)blockIdx.x * QSB_THREADS + threadIdx.x;
+  if (vc >= vcols) return;
+  const int64_t chunk = blockIdx.y;
+  const int64_t r0 = chunk * rows_per_chunk;
+  const int64_t r1 = (r0 + rows_per_chunk < nrows) ? r0 + rows_per_chunk : nrows;
+  Acc<WHAT> acc[V];
+  const float *p = x + vc * V;
+  int64_t r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    VecF<V> v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = ld_vec<V, Hint::KEEP>(p + (r + k) * ncols);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q].add(v[k].v[q]);
+  }
+  for (; r < r1; ++r) {
+    VecF<V> v = ld_vec<V, Hint::KEEP>(p + r * ncols);
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q].add(v.v[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < V; ++q) {
+    const int64_t idx = chunk * ncols + vc * V + q;
+    if constexpr (WHAT & QSB_STAT_ABSMAX) P.amax[idx] = acc[q].amax;
+    if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ))
+      P.mn[idx] = acc[q].nan ? nan_f() : acc[q].mn;
+    if constexpr (WHAT & QSB_STAT_MINMAX)
+      P.mx[idx] = acc[q].nan ? nan_f() : acc[q].mx;
+    if constexpr (WHAT & QSB_STAT_ABSSUM) P.asum[idx] = acc[q].asum;
+    if constexpr (WHAT & QSB_STAT_NNZ) P.nnz[idx] = (double)acc[q].nnz;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// stage 2: channel c combines entries j = 0..count-1 at
+//   idx(j) = (j / q) * (channels * q) + c * q + (j % q)
+// (q = segments per row in row mode, `inner` in column mode).
+// G threads per channel (32: a warp; 256: a CTA), fixed order.
+// ---------------------------------------------------------------------------
+struct FinalOut {
+  float *absmax, *mn, *mx;
+  double *abssum, *nnz;
+};
+
+template <int WHAT, int G>
+__global__ void __launch_bounds__(QSB_THREADS)
+    reduce_finalize_kernel(Partials P, FinalOut out, int64_t channels,
+                           int64_t count, int64_t q) {
+  constexpr int kGroupsPerBlock = QSB_THREADS / G;
+  const int g = threadIdx.x / G;
+  const int tg = threadIdx.x % G;
+  const int64_t c = (int64_t)blockIdx.x * kGroupsPerBlock + g;
+  const bool active = c < channels;
+
+  uint32_t amax = 0;
+  float mn = INFINITY, mx = -INFINITY;
+  bool nan = false;
+  double asum = 0.0, nnz = 0.0;
+  if (active) {
+    for (int64_t j = tg; j < count; j += G) {
+      const int64_t hi = j / q;
+      const int64_t idx = hi * (channels * q) + c * q + (j - hi * q);
+      if constexpr (WHAT & QSB_STAT_ABSMAX) {
+        uint32_t b = P.amax[idx];
+        amax = b > amax ? b : amax;
+      }
+      if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+        float v = P.mn[idx];
+        nan |= (v != v);
+        mn = fminf(mn, v);
+      }
+      if constexpr (WHAT & QSB_STAT_MINMAX) {
+        float v = P.mx[idx];
+        nan |= (v != v);
+        mx = fmaxf(mx, v);
+      }
+      if constexpr (WHAT & QSB_STAT_ABSSUM) asum += P.asum[idx];
+      if constexpr (WHAT & QSB_STAT_NNZ) nnz += P.nnz[idx];
+    }
+  }
+  // warp level
+  amax = warp_reduce(amax, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
+  mn = warp_reduce(mn, [](float a, float b) { return fminf(a, b); });
+  mx = warp_reduce(mx, [](float a, float b) { return fmaxf(a, b); });
+  nan = __any_sync(0xffffffffu, nan);
+  asum = warp_reduce(asum, [](double a, double b) { return a + b; });
+  nnz = warp_reduce(nnz, [](double a, double b) { return a + b; });
+  if constexpr (G > 32) {
+    __shared__ uint32_t s_amax[QSB_THREADS / 32];
+    __shared__ float s_mn[QSB_THREADS / 32], s_mx[QSB_THREADS / 32];
+    __shared__ int s_nan[QSB_THREADS / 32];
+    __shared__ double s_asum[QSB_THREADS / 32], s_nnz[QSB_THREADS / 32];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+      s_amax[w] = amax; s_mn[w] = mn; s_mx[w] = mx; s_nan[w] = nan;
+      s_asum[w] = asum; s_nnz[w] = nnz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < QSB_THREADS / 32; ++k) {
+        amax = s_amax[k] > amax ? s_amax[k] : amax;
+        mn = fminf(mn, s_mn[k]);
+        mx = fmaxf(mx, s_mx[k]);
+        nan = nan || s_nan[k];
+        asum += s_asum[k];
+        nnz += s_nnz[k];
+      }
+    }
+  }
+  if (active && tg == 0) {
+    if constexpr (WHAT & QSB_STAT_ABSMAX)
+      if (out.absmax) out.absmax[c] = __uint_as_float(amax);
+    if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ))
+      if (out.mn) out.mn[c] = nan ? nan_f() : mn;
+    if constexpr (WHAT & QSB_STAT_MINMAX)
+      if (out.mx) out.mx[c] = nan ? nan_f() : mx;
+    if constexpr (WHAT & QSB_STAT_ABSSUM)
+      if (out.abssum) out.abssum[c] = asum;
+    if constexpr (WHAT & QSB_STAT_NNZ)
+      if (out.nnz) out.nnz[c] = nnz;
+  }
+}
+
+// min over the per-channel minima (l0 gate, qsparse/sparse.py:85)
+__global__ void tensor_min_kernel(const float *mn, int64_t channels, float *out) {
+  float m = INFINITY;
+  bool nan = false;
+  for (int64_t j = threadIdx.x; j < channels; j += 32) {
+    float v = mn[j];
+    nan |= (v != v);
+    m = fminf(m, v);
+  }
+  m = warp_reduce(m, [](float a, float b) { return fminf(a, b); });
+  nan = __any_sync(0xffffffffu, nan);
+  if (threadIdx.x == 0) *out = nan ? nan_f() : m;
+}
+
+// ---------------------------------------------------------------------------
+// host-side planning
+// ---------------------------------------------------------------------------
+struct ReducePlan {
+  bool row_mode;
+  int64_t rows, seg, segs_per_row;     // row mode
+  int64_t nrows, ncols, chunks, rows_per_chunk;  // column mode
+  int vcol;
+  int64_t n_partials, fin_count, fin_q;
+};
+
+static ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
+                            const float *x) {
+  ReducePlan p{};
+  const int64_t target = (int64_t)device_props().sm_count * 64 * 2;
+  if (inner >= kRowModeMinInner) {
+    p.row_mode = true;
+    p.rows = outer * channels;
+    int64_t seg = 8192;
+    auto items = [&](int64_t s) { return p.rows * ((inner + s - 1) / s); };
+    while (seg > 512 && items(seg) < target) seg >>= 1;
+    p.seg = seg;
+    p.segs_per_row = (inner + seg - 1) / seg;
+    p.n_partials = p.rows * p.segs_per_row;
+    p.fin_count = outer * p.segs_per_row;
+    p.fin_q = p.segs_per_row;
+  } else {
+    p.row_mode = false;
+    p.nrows = outer;
+    p.ncols = channels * inner;
+    p.vcol = (p.ncols % 4 == 0 && (x == nullptr || aligned_to(x, 16))) ? 4 : 1;
+    const int64_t threads = p.ncols / p.vcol;
+    int64_t chunks = (target + threads - 1) / (threads > 0 ? threads : 1);
+    // at least 8 rows per chunk so the partial array stays small
+    const int64_t max_chunks = (outer + 7) / 8;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+    p.rows_per_chunk = (outer + chunks - 1) / chunks;
+    p.chunks = (outer + p.rows_per_chunk - 1) / p.rows_per_chunk;
+    if (p.chunks < 1) p.chunks = 1;
+    p.n_partials = p.chunks * p.ncols;
+    p.fin_count = p.chunks * inner;
+    p.fin_q = inner;
+  }
+  return p;
+}
+
+static int64_t partial_bytes(int64_t n) {
+  // amax(4) + mn(4) + mx(4) + pad(4) + asum(8) + nnz(8), each array 256-aligned
+  auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
+  return up(n * 4) * 3 + up(n * 8) * 2;
+}
+
+template <int WHAT>
+static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
+                      int64_t inner, const Partials &P, const FinalOut &out,
+                      cudaStream_t stream) {
+  if (pl.row_mode) {
+    static int occ = 0;
+    if (occ == 0) {
+      int o = 0;
+      QSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &o, reduce_rows_kernel<WHAT>, QSB_THREADS, 0));
+      occ = o > 0 ? o : 1;
+    }
+    constexpr int kWarps = QSB_THREADS / 32;
+    int64_t grid = (int64_t)device_props().sm_count * occ;
+    const int64_t need = (pl.n_partials + kWarps - 1) / kWarps;
+    if (grid > need) grid = need;
+    reduce_rows_kernel<WHAT><<<(unsigned)grid, QSB_THREADS, 0, stream>>>(
+        x, pl.rows, inner, pl.seg, pl.segs_per_row, P);
+  } else {
+    const int64_t threads = pl.ncols / pl.vcol;
+    dim3 grid((unsigned)((threads + QSB_THREADS - 1) / QSB_THREADS),
+              (unsigned)pl.chunks);
+    if (pl.vcol == 4)
+      reduce_cols_kernel<WHAT, 4><<<grid, QSB_THREADS, 0, stream>>>(
+          x, pl.nrows, pl.ncols, pl.rows_per_chunk, P);
+    else
+      reduce_cols_kernel<WHAT, 1><<<grid, QSB_THREADS, 0, stream>>>(
+          x, pl.nrows, pl.ncols, pl.rows_per_chunk, P);
+  }
+  QSB_LAUNCH_CHECK();
+  // few channels: a whole CTA per channel; many: a warp per channel
+  if (channels <= 2048) {
+    reduce_finalize_kernel<WHAT, QSB_THREADS>
+        <<<(unsigned)channels, QSB_THREADS, 0, stream>>>(P, out, channels,
+                                                         pl.fin_count, pl.fin_q);
+  } else {
+    constexpr int kPer = QSB_THREADS / 32;
+    reduce_finalize_kernel<WHAT, 32>
+        <<<(unsigned)((channels + kPer - 1) / kPer), QSB_THREADS, 0, stream>>>(
+            P, out, channels, pl.fin_count, pl.fin_q);
+  }
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace qsb
+
+using namespace qsb;
+
+extern "C" int64_t qsb_reduce_workspace_bytes(int64_t outer, int64_t channels,
+                                              int64_t inner) {
+  if (outer <= 0 || channels <= 0 || inner <= 0) return 256;
+  const ReducePlan pl = make_plan(outer, channels, inner, nullptr);
+  // column mode may fall back to scalar columns for an unaligned x: same size.
+  return partial_bytes(pl.n_partials) + 256;
+}
+
+extern "C" int qsb_reduce_stats(const float *x, int what, int64_t outer,
+                                int64_t channels, int64_t inner, float *absmax,
+                                float *mn, float *mx, double *abssum,
+                                double *nnz, float *tensor_min, void *workspace,
+                                int64_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (outer <= 0 || channels <= 0 || inner <= 0) return QSB_E_BADARG;
+  if (!x || !workspace) return QSB_E_BADARG;
+  if (!aligned_to(x, 4)) return QSB_E_ALIGN;
+  if ((what & ~(QSB_STAT_ABSMAX | QSB_STAT_MINMAX | QSB_STAT_ABSSUM |
+                QSB_STAT_NNZ)) || what == 0)
+    return QSB_E_BADARG;
+  if ((what & QSB_STAT_NNZ) && !(what & QSB_STAT_ABSSUM)) return QSB_E_BADARG;
+  const ReducePlan pl = make_plan(outer, channels, inner, x);
+  if (workspace_bytes < partial_bytes(pl.n_partials) + 256) return QSB_E_WORKSPACE;
+  auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
+  Partials P;
+  P.amax = reinterpret_cast<uint32_t *>(base); base += up(pl.n_partials * 4);
+  P.mn = reinterpret_cast<float *>(base);      base += up(pl.n_partials * 4);
+  P.mx = reinterpret_cast<float *>(base);      base += up(pl.n_partials * 4);
+  P.asum = reinterpret_cast<double *>(base);   base += up(pl.n_partials * 8);
+  P.nnz = reinterpret_cast<double *>(base);
+  FinalOut out{absmax, mn, mx, abssum, nnz};
+  int rc;
+  switch (what) {
+#define QSB_CASE(W) \
+  case W: rc = run_reduce<W>(x, pl, channels, inner, P, out, stream); break;
+    QSB_CASE(QSB_STAT_ABSMAX)
+    QSB_CASE(QSB_STAT_MINMAX)
+    QSB_CASE(QSB_STAT_ABSSUM)
+    QSB_CASE(QSB_STAT_ABSSUM | QSB_STAT_ABSMAX)
+    QSB_CASE(QSB_STAT_ABSSUM | QSB_STAT_NNZ)
+    QSB_CASE(QSB_STAT_ABSSUM | QSB_STAT_NNZ | QSB_STAT_ABSMAX)
+    QSB_CASE(QSB_STAT_ABSMAX | QSB_STAT_MINMAX)
+#undef QSB_CASE
+    default:
+      // any other combination: everything in one pass
+      rc = run_reduce<QSB_STAT_ABSMAX | QSB_STAT_MINMAX | QSB_STAT_ABSSUM |
+                      QSB_STAT_NNZ>(x, pl, channels, inner, P, out, stream);
+  }
+  if (rc) return rc;
+  if ((what & QSB_STAT_NNZ) && tensor_min) {
+    // the finalize wrote per-channel minima to `mn` if given, else we need a
+    // scratch: reuse the (now consumed) first partial array.
+    float *chan_min = mn;
+    if (!chan_min) return QSB_E_BADARG;
+    tensor_min_kernel<<<1, 32, 0, stream>>>(chan_min, channels, tensor_min);
+    QSB_LAUNCH_CHECK();
+  }
+  return 0;
+}

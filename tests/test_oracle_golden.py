@@ -1,0 +1,152 @@
+"""Pins the CPU oracle (oracle/) against golden vectors produced by the imported
+reference (oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.conftest import bits_equal, ulp_diff
+
+
+def test_pow2_forward(golden):
+    g = golden
+    x = g["pow2/x"]
+    for d in (5, 0, -2, 12):
+        assert bits_equal(orc.fq_pow2_fwd(x, d), g[f"pow2/y_d{d}"]), d
+    assert bits_equal(orc.fq_pow2_fwd(x, g["pow2/dec_ch1"], 1), g["pow2/y_ch1"])
+    assert bits_equal(orc.fq_pow2_fwd(x, g["pow2/dec_ch0"], 0), g["pow2/y_ch0"])
+    # bits / use_uint / flip_axis do not change the forward (dead clamp, quantize.py:56-62)
+    assert bits_equal(orc.fq_pow2_fwd(x, 5), g["pow2/y_d5_uint_flip_b4"])
+    assert bits_equal(orc.fq_pow2_fwd(g["pow2/x2"], g["pow2/dec2"], 1), g["pow2/y2_ch1"])
+
+
+def test_scaler_forward(golden):
+    g = golden
+    x = g["scaler/x"]
+    for name, s in (("0p1", 0.1), ("0p037", 0.037), ("0p5", 0.5), ("3", 3.0)):
+        assert bits_equal(orc.fq_scaler_fwd(x, np.float32(s)), g[f"scaler/y_s{name}"]), name
+    assert bits_equal(orc.fq_scaler_fwd(x, g["scaler/s_ch1"], 1), g["scaler/y_ch1"])
+
+
+def test_line_forward(golden):
+    g = golden
+    x = g["line/x"]
+    for bits in (8, 4):
+        for fzp in (True, False):
+            y = orc.fq_line_fwd(x, np.array([[-0.1, 0.9]], np.float32), bits, -1, fzp)
+            assert bits_equal(y, g[f"line/y_tuple_b{bits}_fzp{int(fzp)}"]), (bits, fzp)
+            y = orc.fq_line_fwd(x, g["line/lines_ch1"], bits, 1, fzp)
+            assert bits_equal(y, g[f"line/y_ch1_b{bits}_fzp{int(fzp)}"]), (bits, fzp)
+
+
+def test_ste_backward(golden):
+    g = golden
+    gr = g["bwd/g"]
+    for bits, d, flip in ((8, 5, False), (8, 5, True), (4, 3, False), (8, -1, False)):
+        gc, _ = orc.ste_bwd(gr, np.float32(d), bits, -1, True, flip)
+        assert bits_equal(gc, g[f"bwd/pow2_b{bits}_d{d}_f{int(flip)}_gx"])
+        # the reference clamps grad_output in place (quantize.py:72)
+        assert bits_equal(gc, g[f"bwd/pow2_b{bits}_d{d}_f{int(flip)}_go"])
+    gc, _ = orc.ste_bwd(gr, g["pow2/dec_ch1"], 8, 1, True, False)
+    assert bits_equal(gc, g["bwd/pow2_ch1_gx"])
+    assert bits_equal(gr, g["bwd/pow2_passthrough_gx"])
+    for name, s in (("0p1", 0.1), ("0p037", 0.037)):
+        gc, _ = orc.ste_bwd(gr, np.float32(s), 8, -1, False, False)
+        assert bits_equal(gc, g[f"bwd/scaler_s{name}_gx"])
+    gc, _ = orc.ste_bwd(gr, g["scaler/s_ch1"], 6, 1, False, True)
+    assert bits_equal(gc, g["bwd/scaler_ch1_b6_flip_gx"])
+
+
+def test_decimal_quantizer_optimize(golden):
+    g = golden
+    xs = g["dq/xs"]
+    for bits in (8, 4):
+        w = np.zeros(1, np.float32)
+        for t, x in enumerate(xs):
+            w = orc.scale_ema(w, orc.absmax(x, -1), bits, t)
+            assert bits_equal(w, g[f"dq/w_tensor_b{bits}"][t].reshape(-1)), (bits, t)
+    for ci, key in ((0, "dq/w_ch0"), (1, "dq/w_ch1")):
+        w = np.zeros(xs.shape[1 + ci], np.float32)
+        for t, x in enumerate(xs):
+            w = orc.scale_ema(w, orc.absmax(x, ci), 8, t)
+            assert bits_equal(w, g[key][t].reshape(-1)), (ci, t)
+
+
+def test_scale_to_decimal(golden):
+    g = golden
+    with np.errstate(all="ignore"):
+        d = orc.scale_to_decimal(g["dq/scales"])
+    assert bits_equal(d, g["dq/decimals"])
+    w = g["dq/w_tensor_b8"][0].reshape(-1)
+    y = orc.fq_pow2_fwd(g["dq/xs"][0], orc.scale_to_decimal(w))
+    assert bits_equal(y, g["dq/fwd_tensor"])
+
+
+def test_adaptive_optimize(golden):
+    g = golden
+    xs = g["dq/xs"]
+    for ci, batched, nch in ((1, True, 4), (0, False, 2), (-1, True, 1)):
+        lines = np.zeros((nch, 2), np.float32)
+        for t, x in enumerate(xs):
+            mn, mx = orc.minmax(x, ci)
+            lines = orc.lines_ema(lines, mn, mx, t + 1)
+            assert bits_equal(lines, g[f"aq/lines_ci{ci}_b{int(batched)}"][t]), (ci, t)
+
+
+def test_squeeze_mean_abs(golden):
+    g = golden
+    x = g["sq/x"]
+    for tgt in ((1, 8, 1, 1), (1, 8, 5, 7), (6, 1, 1, 1), (1, 8, 5, 1), (6, 8, 5, 7), (1, 1, 5, 7)):
+        ref = g["sq/" + "x".join(map(str, tgt))]
+        got = orc.squeeze_mean_abs(x, tgt)
+        assert got.shape == ref.shape
+        # torch's fp32 cascade summation is not restated: a few ulp
+        assert ulp_diff(got, ref).max() <= 4, tgt
+
+
+def test_mask_given_importance(golden):
+    g = golden
+    for s in (0.0, 0.47, 0.5, 0.75, 0.999):
+        m, _ = orc.mask_given_importance(g["mask/imp"], s)
+        assert np.array_equal(m, g[f"mask/m_{s}"]), s
+    assert 1 - orc.mask_given_importance(g["mask/imp"], 0.47)[0].mean() == 0.47  # tests/test_util.py:80-84
+    for s in (0.0, 0.25, 0.5, 0.75):
+        m, _ = orc.mask_given_importance(g["mask/tie_imp"], s)
+        assert np.array_equal(m, g[f"mask/tie_m_{s}"]), s
+    m, _ = orc.mask_given_importance(g["mask/neg_imp"], 0.3)
+    assert np.array_equal(m, g["mask/neg_m_0.3"])
+
+
+def _replay_callback(g, tag, mask_shape, sparsity=0.5, running_average=True, interval=1, stop=float("inf")):
+    xs, outs, masks, mags = g[f"cb/{tag}_x"], g[f"cb/{tag}_out"], g[f"cb/{tag}_mask"], g[f"cb/{tag}_mag"]
+    mask = np.ones(mask_shape, bool)
+    mag = np.zeros(mask_shape, np.float32)
+    structured = int(np.prod(mask_shape)) != xs[0].size
+    for t, x in enumerate(xs):
+        if t < stop and running_average:
+            mag = orc.magnitude_ema(mag, orc.squeeze_mean_abs(x, mask_shape), t)
+            assert ulp_diff(mag, mags[t]).max() <= 8, (tag, t)
+        if orc.refresh_gate(t, sparsity, interval, stop, running_average):
+            imp = mag if running_average else orc.squeeze_mean_abs(x, mask_shape)
+            mask, _ = orc.mask_given_importance(imp, sparsity)
+        assert np.array_equal(mask, masks[t]), (tag, t)
+        out = orc.mask_apply(x, mask.reshape(-1), 1 if structured else -1)
+        assert bits_equal(out, outs[t]), (tag, t)
+
+
+def test_magnitude_callback_sequences(golden):
+    _replay_callback(golden, "struct", (1, 8, 1, 1))
+    _replay_callback(golden, "unstruct", (2, 3, 6, 6))
+    _replay_callback(golden, "struct_norunavg", (1, 8, 1, 1), running_average=False)
+    _replay_callback(golden, "struct_refresh2", (1, 8, 1, 1), interval=2, stop=4)
+
+
+def test_prune_ramp(golden):
+    ref = golden["ramp/cur_sparsity"]
+    schedules, rampup_interval = orc.prune_schedule(200, 10, 4)
+    cur = 0.0
+    for step in range(241):
+        if step in schedules:
+            cur = orc.ramp_sparsity(step, 0.5, 200, 10, 4, rampup_interval)
+        assert cur == ref[step], step
+    # docs/tutorial.ipynb:224-228 : 0.29 / 0.44 / 0.49 / 0.50
+    assert [round(ref[s], 2) for s in (200, 210, 220, 230)] == [0.29, 0.44, 0.49, 0.5]
