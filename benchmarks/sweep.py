@@ -1,0 +1,144 @@
+"""Per-kernel bandwidth sweep on one B200 (development tool, not the graded bench).
+
+    python benchmarks/sweep.py [--out gpurun_out/sweep.jsonl] [--quick]
+
+Times every hot-path kernel with CUDA events on the launching stream; between timed
+launches a 512 MB buffer is rewritten to flush the 126 MB L2.  GB/s = algorithmic bytes
+ / time.  Also sweeps the grid policy knob (qsb_set_tuning key 0).
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from qsparse_b200 import ops  # noqa: E402
+
+PEAK = 6457.4  # MEASURED_PEAKS.json hbm_gbs (copy)
+
+
+def timeit(fn, iters=12, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1.0)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/sweep.jsonl")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+    out = open(args.out, "w")
+    dev = torch.device("cuda:0")
+    flush = torch.zeros(128 * 1024 * 1024, device=dev)  # 512 MB
+    torch.manual_seed(2)
+
+    def report(name, nbytes, fn, **extra):
+        med, best = timeit(fn, flush=flush)
+        rec = dict(kernel=name, us_median=round(med, 2), us_best=round(best, 2), gbs_median=round(nbytes / med / 1e3, 1),
+                   gbs_best=round(nbytes / best / 1e3, 1), frac_of_copy_peak=round(nbytes / med / 1e3 / PEAK, 3), **extra)
+        print(json.dumps(rec), flush=True)
+        out.write(json.dumps(rec) + "\n")
+        out.flush()
+
+    # ---------------- config 2: [256, 64, 56, 56]
+    shape, layout = (256, 64, 56, 56), (256, 64, 3136)
+    n = 256 * 64 * 3136
+    x = torch.relu(torch.randn(shape, device=dev))
+    g = torch.randn(shape, device=dev)
+    y = torch.empty_like(x)
+    gx = torch.empty_like(x)
+    dec1 = torch.tensor([5.0], device=dev)
+    decC = torch.full((64,), 5.0, device=dev)
+    mask75 = (torch.arange(64, device=dev) % 4 == 0)
+    mask0 = torch.ones(64, dtype=torch.bool, device=dev)
+    emask = torch.rand(shape, device=dev) > 0.5
+
+    report("torch_copy", 8 * n, lambda: y.copy_(x))
+    tunings = [0] if args.quick else [0, -1, 2, 3, 4, 6, 8]
+    for tune in tunings:
+        ops.set_tuning(0, tune)
+        report("fq_pow2_tensor", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, (1, 1, n), out=y), tune=tune)
+        report("fq_pow2_chdec", 8 * n, lambda: ops.fq_pow2_fwd(x, decC, layout, out=y), tune=tune)
+        report("fq_pow2_chmask0", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, layout, mask=mask0, out=y), tune=tune)
+        report("fq_pow2_chmask75", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, layout, mask=mask75, out=y), tune=tune,
+               note="dense-algorithmic bytes; 75% of reads skipped")
+        report("ste_bwd_inplace", 8 * n, lambda: ops.ste_bwd(g, dec1, True, 8, 0, (1, 1, n)), tune=tune)
+    ops.set_tuning(0, 0)
+    report("fq_pow2_emask", 9 * n, lambda: ops.fq_pow2_fwd(x, dec1, (1, 1, n), mask=emask, out=y))
+    report("fq_scaler_tensor", 8 * n, lambda: ops.fq_scaler_fwd(x, 0.037, (1, 1, n), out=y))
+    report("fq_line_ch", 8 * n, lambda: ops.fq_line_fwd(
+        x, torch.tensor([[-0.1, 0.9]] * 64, device=dev), 8, True, layout, out=y))
+
+    def bwd_fused():
+        lib_gx = ops.N.load_library()
+        from ctypes import c_double, c_int, c_int64
+        ops.N.check(lib_gx.qsb_ste_bwd(ops.N.ptr(g), ops.N.ptr(None), ops.N.ptr(gx), ops.N.ptr(dec1), c_int64(1),
+                                       c_double(0), c_int(1), c_int(8), c_int(0), ops.N.ptr(mask75), c_int(1),
+                                       c_int64(256), c_int64(64), c_int64(3136), ops.N.stream_ptr(dev)), "ste")
+    report("ste_bwd_fused_gx", 8 * n, bwd_fused)
+    report("mask_apply_ch", 8 * n, lambda: ops.mask_apply(x, mask75, layout, out=y))
+    report("reduce_abssum_absmax_ch", 4 * n, lambda: ops.reduce_stats(x, layout, abssum=True, absmax=True))
+    report("reduce_absmax_tensor", 4 * n, lambda: ops.reduce_stats(x, (1, 1, n), absmax=True))
+    report("reduce_minmax_ch", 4 * n, lambda: ops.reduce_stats(x, layout, minmax=True))
+    report("torch_absmax_tensor", 4 * n, lambda: x.abs().max())
+    report("torch_amax_ch", 4 * n, lambda: x.amax(dim=(0, 2, 3)))
+
+    # reduce -> params -> apply, then backward: the fused training step (20 B/elem)
+    mag = torch.zeros(64, device=dev)
+    mask = torch.ones(64, dtype=torch.bool, device=dev)
+    scale = torch.zeros(1, device=dev)
+    dec = torch.zeros(1, device=dev)
+    state = dict(t=0)
+
+    def step():
+        st = ops.reduce_stats(x, layout, abssum=True, absmax=True)
+        ops.prune_quant_params(mag, mask, scale, dec, st, 256 * 3136.0, state["t"], 1, state["t"] > 0, 48, 8,
+                               state["t"], True)
+        ops.fq_pow2_fwd(x, dec, layout, mask=mask, out=y)
+        bwd_fused()
+        state["t"] += 1
+    report("fused_train_step", 20 * n, step)
+
+    del emask, gx
+    # ---------------- config 3: [4096, 4096] channelwise=0
+    w = torch.randn(4096, 4096, device=dev) * 0.02
+    wy = torch.empty_like(w)
+    nw = w.numel()
+    lines = torch.zeros(4096, 2, device=dev)
+    report("c3_reduce_minmax", 4 * nw, lambda: ops.reduce_stats(w, (1, 4096, 4096), minmax=True))
+    st = ops.reduce_stats(w, (1, 4096, 4096), minmax=True)
+    ops.lines_ema_(lines, st["min"], st["max"], 1)
+    report("c3_line_fwd", 8 * nw, lambda: ops.fq_line_fwd(w, lines, 4, True, (1, 4096, 4096), out=wy))
+
+    # ---------------- config 4: 64 Mi unstructured
+    n4 = 1 << 26
+    wt = torch.randn(n4, device=dev) * 0.02
+    magf = wt.abs() * 0.9
+    yb = torch.empty_like(wt)
+    mk = torch.empty(n4, dtype=torch.bool, device=dev)
+    report("c4_ema_full", 12 * n4, lambda: ops.magnitude_ema_full_(magf, wt, 3))
+    report("c4_kth_value", 4 * n4, lambda: ops.kth_value(magf, n4 // 2), passes=3)
+    thr = ops.kth_value(magf, n4 // 2)
+    report("c4_mask_build_apply", 13 * n4, lambda: ops.mask_build_apply(magf, thr, wt, mk, out=yb))
+    report("c4_torch_sort", 4 * n4, lambda: torch.sort(magf))
+    out.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,286 @@
+"""Functional (non-autograd) wrappers of the C-ABI launchers.
+
+Every function takes CUDA tensors, enqueues one or two kernels on torch's
+current stream and returns without synchronising.  Argument conventions follow
+``include/qsparse_b200.h``; ``layout`` is ``(outer, channels, inner)``.
+"""
+from __future__ import annotations
+
+from ctypes import c_double, c_float, c_int, c_int64
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+Layout = Tuple[int, int, int]
+
+
+def _mask_kind(mask: Optional[torch.Tensor], numel: int, layout: Layout) -> int:
+    if mask is None:
+        return N.MASK_NONE
+    if mask.dtype not in (torch.bool, torch.uint8):
+        raise TypeError("mask must be a bool/uint8 tensor")
+    N.require_cuda(mask, "mask")
+    if not mask.is_contiguous():
+        raise ValueError("mask must be contiguous")
+    m = mask.numel()
+    if m == layout[1] and (m != numel or layout[0] * layout[2] == 1):
+        return N.MASK_CHANNEL
+    if m == numel:
+        return N.MASK_ELEMENT
+    raise ValueError(f"mask with {m} elements fits neither channels={layout[1]} nor numel={numel}")
+
+
+def _dev_param(p, what: str):
+    """(device tensor or None, n, host scalar)."""
+    if isinstance(p, torch.Tensor):
+        if p.is_cuda:
+            q = p.detach()
+            if q.dtype != torch.float32 or not q.is_contiguous():
+                q = q.float().contiguous()
+            return q, q.numel(), 0.0
+        if p.numel() == 1:
+            return None, 1, float(p)
+        raise RuntimeError(f"{what} is a multi-element CPU tensor; qsparse_b200 is CUDA-only")
+    return None, 1, float(p)
+
+
+def mask_layout(x_shape: Sequence[int], mask_shape: Sequence[int]) -> Tuple[str, Layout]:
+    """How a broadcastable prune mask maps onto x: ('element', (1,1,n)) for a
+    full-size mask, ('channel', (outer, C, inner)) when the kept axes form one
+    contiguous run (e.g. [1,C,1,1], [1,C,H,W], [Cout,1,1,1])."""
+    x_shape, mask_shape = list(x_shape), list(mask_shape)
+    if len(x_shape) != len(mask_shape):
+        raise RuntimeError(
+            f"The size of tensor a ({len(x_shape)} dims) must match the size of tensor b "
+            f"({len(mask_shape)} dims): prune mask and input ranks differ")
+    n = 1
+    for i, (sx, sm) in enumerate(zip(x_shape, mask_shape)):
+        if sm != 1 and sm != sx:
+            raise RuntimeError(
+                f"The size of tensor a ({sx}) must match the size of tensor b ({sm}) at non-singleton dimension {i}")
+        n *= sx
+    kept = [i for i, (sx, sm) in enumerate(zip(x_shape, mask_shape)) if sm != 1]
+    if not kept:
+        return "channel", (1, 1, n)
+    lo, hi = kept[0], kept[-1] + 1
+    for i in range(lo, hi):
+        if mask_shape[i] == 1 and x_shape[i] != 1:
+            raise NotImplementedError(
+                f"prune mask shape {tuple(mask_shape)} keeps non-adjacent axes of {tuple(x_shape)}; "
+                "only one contiguous run of kept axes is supported")
+    outer = 1
+    for s in x_shape[:lo]:
+        outer *= s
+    ch = 1
+    for s in x_shape[lo:hi]:
+        ch *= s
+    inner = 1
+    for s in x_shape[hi:]:
+        inner *= s
+    if outer == 1 and inner == 1:
+        return "element", (1, 1, n)
+    return "channel", (outer, ch, inner)
+
+
+# ----------------------------------------------------------------------------- K1
+def fq_pow2_fwd(x, decimal, layout: Layout, mask=None, out=None):
+    N.require_cuda(x, "input")
+    lib = N.load_library()
+    y = torch.empty_like(x) if out is None else out
+    dev, n, host = _dev_param(decimal, "decimal")
+    mk = _mask_kind(mask, x.numel(), layout)
+    N.check(lib.qsb_fq_pow2_fwd(N.ptr(x), N.ptr(y), N.ptr(dev), c_int64(n), c_double(host), N.ptr(mask), c_int(mk),
+                                c_int64(layout[0]), c_int64(layout[1]), c_int64(layout[2]), N.stream_ptr(x.device)),
+            "qsb_fq_pow2_fwd")
+    return y
+
+
+def fq_scaler_fwd(x, scaler, layout: Layout, mask=None, out=None):
+    N.require_cuda(x, "input")
+    lib = N.load_library()
+    y = torch.empty_like(x) if out is None else out
+    dev, n, host = _dev_param(scaler, "scaler")
+    mk = _mask_kind(mask, x.numel(), layout)
+    N.check(lib.qsb_fq_scaler_fwd(N.ptr(x), N.ptr(y), N.ptr(dev), c_int64(n), c_float(host), N.ptr(mask), c_int(mk),
+                                  c_int64(layout[0]), c_int64(layout[1]), c_int64(layout[2]), N.stream_ptr(x.device)),
+            "qsb_fq_scaler_fwd")
+    return y
+
+
+def fq_line_fwd(x, lines, bits: int, float_zero_point: bool, layout: Layout, mask=None, out=None):
+    """lines: CUDA float tensor [n, 2] (n == 1 or channels) or a (lo, hi) pair."""
+    N.require_cuda(x, "input")
+    lib = N.load_library()
+    y = torch.empty_like(x) if out is None else out
+    if isinstance(lines, torch.Tensor) and lines.is_cuda:
+        dev = lines.detach()
+        if dev.dtype != torch.float32 or not dev.is_contiguous():
+            dev = dev.float().contiguous()
+        n, lo, hi = dev.numel() // 2, 0.0, 0.0
+    else:
+        flat = torch.as_tensor(lines, dtype=torch.float32).reshape(-1)
+        if flat.numel() != 2:
+            raise RuntimeError("multi-row `lines` must be a CUDA tensor; qsparse_b200 is CUDA-only")
+        dev, n, lo, hi = None, 1, float(flat[0]), float(flat[1])
+    mk = _mask_kind(mask, x.numel(), layout)
+    N.check(lib.qsb_fq_line_fwd(N.ptr(x), N.ptr(y), N.ptr(dev), c_int64(n), c_float(lo), c_float(hi), c_int(bits),
+                                c_int(1 if float_zero_point else 0), N.ptr(mask), c_int(mk), c_int64(layout[0]),
+                                c_int64(layout[1]), c_int64(layout[2]), N.stream_ptr(x.device)),
+            "qsb_fq_line_fwd")
+    return y
+
+
+# ----------------------------------------------------------------------------- K2
+def ste_bwd(g, scale, is_decimal: bool, bits: int, notch: int, layout: Layout, mask=None, clamp_in_place=True,
+            want_gx=False):
+    """Returns (g_clamped or None, gx or None).  clamp_in_place reproduces the
+    reference's in-place `grad_output.clamp_` (quantize.py:72)."""
+    N.require_cuda(g, "grad_output")
+    lib = N.load_library()
+    dev, n, host = _dev_param(scale, "scale")
+    mk = _mask_kind(mask, g.numel(), layout)
+    gc = g if clamp_in_place else None
+    gx = torch.empty_like(g) if (want_gx or not clamp_in_place) else None
+    N.check(lib.qsb_ste_bwd(N.ptr(g), N.ptr(gc), N.ptr(gx), N.ptr(dev), c_int64(n), c_double(host),
+                            c_int(1 if is_decimal else 0), c_int(bits), c_int(notch), N.ptr(mask), c_int(mk),
+                            c_int64(layout[0]), c_int64(layout[1]), c_int64(layout[2]), N.stream_ptr(g.device)),
+            "qsb_ste_bwd")
+    return gc, gx
+
+
+# ----------------------------------------------------------------------------- K6
+def mask_apply(x, mask, layout: Layout, out=None):
+    N.require_cuda(x, "input")
+    lib = N.load_library()
+    y = torch.empty_like(x) if out is None else out
+    mk = _mask_kind(mask, x.numel(), layout)
+    N.check(lib.qsb_mask_apply(N.ptr(x), N.ptr(y), N.ptr(mask), c_int(mk), c_int64(layout[0]), c_int64(layout[1]),
+                               c_int64(layout[2]), N.stream_ptr(x.device)), "qsb_mask_apply")
+    return y
+
+
+# ----------------------------------------------------------------------------- K3
+def reduce_stats(x, layout: Layout, absmax=False, minmax=False, abssum=False, nnz=False):
+    """One read of x -> dict of per-channel statistics (device tensors)."""
+    N.require_cuda(x, "input")
+    lib = N.load_library()
+    outer, ch, inner = layout
+    what = (N.STAT_ABSMAX if absmax else 0) | (N.STAT_MINMAX if minmax else 0) | \
+           (N.STAT_ABSSUM if (abssum or nnz) else 0) | (N.STAT_NNZ if nnz else 0)
+    dev = x.device
+    res = {}
+    if absmax:
+        res["absmax"] = torch.empty(ch, dtype=torch.float32, device=dev)
+    if minmax or nnz:
+        res["min"] = torch.empty(ch, dtype=torch.float32, device=dev)
+    if minmax:
+        res["max"] = torch.empty(ch, dtype=torch.float32, device=dev)
+    if abssum or nnz:
+        res["abssum"] = torch.empty(ch, dtype=torch.float64, device=dev)
+    if nnz:
+        res["nnz"] = torch.empty(ch, dtype=torch.float64, device=dev)
+        res["tensor_min"] = torch.empty(1, dtype=torch.float32, device=dev)
+    nbytes = lib.qsb_reduce_workspace_bytes(c_int64(outer), c_int64(ch), c_int64(inner))
+    ws = N.workspace(dev, nbytes)
+    N.check(lib.qsb_reduce_stats(N.ptr(x), c_int(what), c_int64(outer), c_int64(ch), c_int64(inner),
+                                 N.ptr(res.get("absmax")), N.ptr(res.get("min")), N.ptr(res.get("max")),
+                                 N.ptr(res.get("abssum")), N.ptr(res.get("nnz")), N.ptr(res.get("tensor_min")),
+                                 N.ptr(ws), c_int64(ws.numel()), N.stream_ptr(dev)), "qsb_reduce_stats")
+    return res
+
+
+# ----------------------------------------------------------------------------- K4
+def scale_ema_(weight, absmax, bits: int, t: int):
+    lib = N.load_library()
+    N.require_cuda(weight, "weight")
+    N.check(lib.qsb_scale_ema(N.ptr(weight), N.ptr(absmax), c_int64(weight.numel()), c_int(bits), c_int64(t),
+                              N.stream_ptr(weight.device)), "qsb_scale_ema")
+    return weight
+
+
+def scale_to_decimal(scale):
+    lib = N.load_library()
+    N.require_cuda(scale, "scale")
+    s = scale.detach()
+    if s.dtype != torch.float32 or not s.is_contiguous():
+        s = s.float().contiguous()
+    d = torch.empty_like(s)
+    N.check(lib.qsb_scale_to_decimal(N.ptr(s), N.ptr(d), c_int64(s.numel()), N.stream_ptr(s.device)),
+            "qsb_scale_to_decimal")
+    return d
+
+
+def lines_ema_(lines, mn, mx, t: int):
+    lib = N.load_library()
+    N.require_cuda(lines, "lines")
+    N.check(lib.qsb_lines_ema(N.ptr(lines), N.ptr(mn), N.ptr(mx), c_int64(lines.numel() // 2), c_int64(t),
+                              N.stream_ptr(lines.device)), "qsb_lines_ema")
+    return lines
+
+
+def magnitude_ema_reduced_(magnitude, stats: dict, count: float, t: int, use_l0=False):
+    lib = N.load_library()
+    N.require_cuda(magnitude, "magnitude")
+    N.check(lib.qsb_magnitude_ema_reduced(N.ptr(magnitude), N.ptr(stats["abssum"]), N.ptr(stats.get("nnz")),
+                                          N.ptr(stats.get("tensor_min")), c_int(1 if use_l0 else 0),
+                                          c_int64(magnitude.numel()), c_double(count), c_int64(t),
+                                          N.stream_ptr(magnitude.device)), "qsb_magnitude_ema_reduced")
+    return magnitude
+
+
+def magnitude_ema_full_(magnitude, x, t: int, tensor_min=None, use_l0=False):
+    lib = N.load_library()
+    N.require_cuda(magnitude, "magnitude")
+    N.check(lib.qsb_magnitude_ema_full(N.ptr(magnitude), N.ptr(x), N.ptr(tensor_min), c_int(1 if use_l0 else 0),
+                                       c_int64(magnitude.numel()), c_int64(t), N.stream_ptr(magnitude.device)),
+            "qsb_magnitude_ema_full")
+    return magnitude
+
+
+# ----------------------------------------------------------------------------- K5 / K6
+def kth_value(v, k: int, take_abs=False):
+    """device scalar holding sorted(v)[k] (ascending, NaNs last)."""
+    lib = N.load_library()
+    N.require_cuda(v, "importance")
+    n = v.numel()
+    thr = torch.empty(1, dtype=torch.float32, device=v.device)
+    nbytes = lib.qsb_kth_workspace_bytes(c_int64(n))
+    ws = N.workspace(v.device, nbytes)
+    N.check(lib.qsb_kth_value(N.ptr(v), c_int64(n), c_int64(k), c_int(1 if take_abs else 0), N.ptr(thr), N.ptr(ws),
+                              c_int64(ws.numel()), N.stream_ptr(v.device)), "qsb_kth_value")
+    return thr
+
+
+def mask_from_threshold(importance, thr, mask_out, take_abs=False):
+    lib = N.load_library()
+    N.check(lib.qsb_mask_from_threshold(N.ptr(importance), c_int(1 if take_abs else 0), N.ptr(thr), N.ptr(mask_out),
+                                        c_int64(importance.numel()), N.stream_ptr(importance.device)),
+            "qsb_mask_from_threshold")
+    return mask_out
+
+
+def mask_build_apply(importance, thr, x, mask_out, take_abs=False, out=None):
+    lib = N.load_library()
+    y = torch.empty_like(x) if out is None else out
+    N.check(lib.qsb_mask_build_apply(N.ptr(importance), c_int(1 if take_abs else 0), N.ptr(thr), N.ptr(x), N.ptr(y),
+                                     N.ptr(mask_out), c_int64(x.numel()), N.stream_ptr(x.device)),
+            "qsb_mask_build_apply")
+    return y
+
+
+def prune_quant_params(magnitude, mask, scale, decimal_out, stats: dict, count: float, t_prune: int,
+                       update_magnitude: int, refresh_mask: bool, k: int, bits: int, t_quant: int,
+                       update_scale: bool):
+    lib = N.load_library()
+    N.check(lib.qsb_prune_quant_params(N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out),
+                                       N.ptr(stats.get("abssum")), N.ptr(stats.get("absmax")),
+                                       c_int64(mask.numel()), c_double(count), c_int64(t_prune),
+                                       c_int(update_magnitude), c_int(1 if refresh_mask else 0), c_int64(k),
+                                       c_int(bits), c_int64(t_quant), c_int(1 if update_scale else 0),
+                                       N.stream_ptr(mask.device)), "qsb_prune_quant_params")
+
+
+def set_tuning(key: int, value: int):
+    N.check(N.load_library().qsb_set_tuning(c_int(key), c_int(value)), "qsb_set_tuning")

@@ -1,0 +1,314 @@
+"""Magnitude pruning on sm_100a kernels, behind qsparse's own API.
+
+Mirrors ``qsparse/sparse.py`` of mlzxy/qsparse v2.0.1: ``prune()``, ``PruneLayer``,
+``MagnitudePruningCallback`` (+ its overridable ``initialize`` / ``receive_input`` /
+``update_magnitude`` / ``prune_and_update_mask``), ``UniformPruningCallback`` and
+``devise_layerwise_pruning_schedule`` with the same arguments, state_dict keys and
+error types.  The tensor work runs on the kernels of ``csrc/``:
+
+* running-average magnitude      -> K3 ``qsb_reduce_stats`` (+ ``qsb_magnitude_ema_*``)
+* k-th value threshold           -> K5 ``qsb_kth_value`` (exact radix select, no sort)
+* mask build / apply, fwd + bwd  -> K6 ``qsb_mask_from_threshold`` / ``qsb_mask_build_apply`` /
+                                    ``qsb_mask_apply``
+
+Step counters and the current sparsity are mirrored on the host (``HostMirror``), so a
+training forward never synchronises with the device (the reference does 6-8
+``.item()`` calls per step).
+"""
+from __future__ import annotations
+
+import copy
+from argparse import ArgumentError
+from typing import Callable, Iterable
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from . import ops
+from .imitation import imitate
+from .util import HostMirror, get_option, kth_rank, logging
+
+
+class _MaskApply(torch.autograd.Function):
+    """``x * mask`` (ref qsparse/sparse.py:66,116,122,263) and its gradient ``g * mask``.
+
+    ``precomputed`` lets the fused mask-build+apply kernel hand in the forward value."""
+
+    @staticmethod
+    def forward(ctx, x, mask, precomputed=None):
+        kind, layout = ops.mask_layout(x.shape, mask.shape)
+        ctx.layout = layout
+        ctx.mask = mask  # read at backward time, like the reference's saved Parameter
+        if precomputed is not None:
+            return precomputed
+        xs = N.as_f32_contiguous(x.detach())
+        return ops.mask_apply(xs, mask.detach(), layout)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        g = N.as_f32_contiguous(grad_output)
+        return ops.mask_apply(g, ctx.mask.detach(), ctx.layout), None, None
+
+
+def apply_mask(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    N.require_cuda(x, "x")
+    N.require_cuda(mask, "mask")
+    return _MaskApply.apply(x, mask)
+
+
+class MagnitudePruningCallback(nn.Module):
+    """Magnitude-based pruning, the default callback of ``prune`` (ref qsparse/sparse.py:18-122)."""
+
+    def __init__(self, mask_refresh_interval: int = -1, stop_mask_refresh: int = float("inf"),
+                 use_gradient: bool = False, running_average: bool = True, l0: bool = False,
+                 forward_hook: Callable[[torch.Tensor, str], None] = None):
+        super().__init__()
+        self.mask_refresh_interval = mask_refresh_interval
+        self.stop_mask_refresh = stop_mask_refresh
+        self.use_gradient = use_gradient
+        self.t = nn.Parameter(torch.full((1,), -1), requires_grad=False)
+        if use_gradient and not running_average:
+            raise ArgumentError(
+                None, "the combination of `use_gradient=True` and `running_average=False` is not supported")
+        self.running_average = running_average
+        self.prev_grad_hook = None
+        self.l0 = l0
+        self.forward_hook = forward_hook
+        self._t_mirror = HostMirror()
+
+    # ---- host-mirrored step counter -------------------------------------------------
+    def _t(self) -> int:
+        return int(self._t_mirror.get(self.t))
+
+    def _set_t(self, value: int):
+        self.t.data.fill_(value)
+        self._t_mirror.wrote(self.t, value)
+
+    @property
+    def initted(self) -> bool:
+        return self._t() != -1
+
+    # ---- overridable pieces, same names as the reference ----------------------------
+    def initialize(self, mask: torch.Tensor):
+        if self.running_average:
+            self.magnitude = nn.Parameter(torch.zeros(*mask.shape, device=mask.device, dtype=torch.float),
+                                          requires_grad=False)
+
+    def receive_input(self, x: torch.Tensor):
+        if self.use_gradient:
+            if self.prev_grad_hook is not None:
+                self.prev_grad_hook.remove()
+            if x.requires_grad:
+                self.prev_grad_hook = x.register_hook(lambda grad: self.update_magnitude(grad))
+            else:
+                logging.error("meeting no-grad tensor")
+                self.prev_grad_hook = None
+        else:
+            self.update_magnitude(x)
+
+    def update_magnitude(self, x):
+        """mag = (t * mag + mean|x|) / (t + 1)  (ref qsparse/sparse.py:82-89)."""
+        if not self.running_average:
+            return
+        with torch.no_grad():
+            N.require_cuda(x, "x")
+            xs = N.as_f32_contiguous(x.detach())
+            mag = self.magnitude.data
+            t = self._t()
+            kind, layout = ops.mask_layout(xs.shape, mag.shape)
+            if kind == "element":
+                tensor_min = None
+                if self.l0:  # `x.min() == 0` gate (sparse.py:85), evaluated on the device
+                    tensor_min = ops.reduce_stats(xs, (1, 1, xs.numel()), nnz=True)["tensor_min"]
+                ops.magnitude_ema_full_(mag, xs, t, tensor_min, self.l0)
+            else:
+                stats = ops.reduce_stats(xs, layout, abssum=True, nnz=self.l0)
+                ops.magnitude_ema_reduced_(mag, stats, float(layout[0] * layout[2]), t, self.l0)
+
+    def prune_and_update_mask(self, x: torch.Tensor, sparsity: float, mask: torch.Tensor) -> torch.Tensor:
+        """threshold = sorted(importance)[idx + 1]; mask = importance >= threshold; x * mask
+        (ref qsparse/sparse.py:58-66, qsparse/util.py:103-117)."""
+        N.require_cuda(x, "x")
+        with torch.no_grad():
+            xs = N.as_f32_contiguous(x.detach())
+            kind, layout = ops.mask_layout(xs.shape, mask.shape)
+            n = mask.numel()
+            k = kth_rank(sparsity, n)
+            if k >= n:
+                raise IndexError(f"index {k} is out of bounds for dimension 0 with size {n}")
+            take_abs = False
+            if self.running_average:
+                importance = self.magnitude.data
+            elif kind == "element":
+                importance, take_abs = xs, True  # importance = |x| itself, never materialised
+            else:
+                s = ops.reduce_stats(xs, layout, abssum=True)["abssum"]
+                importance = (s / float(layout[0] * layout[2])).float()
+            thr = ops.kth_value(importance, k, take_abs)
+            if kind == "element":
+                out = ops.mask_build_apply(importance, thr, xs, mask.data, take_abs)
+            else:
+                ops.mask_from_threshold(importance, thr, mask.data, take_abs)
+                out = None
+        return _MaskApply.apply(x, mask, out)
+
+    def forward(self, x: torch.Tensor, sparsity: float, mask: torch.Tensor, name=""):
+        if not self.training:
+            return apply_mask(x, mask)
+        if not self.initted:
+            self.initialize(mask)
+            self._set_t(0)
+            if self.mask_refresh_interval <= 0:
+                self.mask_refresh_interval = 1
+        t = self._t()
+        if t < self.stop_mask_refresh:
+            self.receive_input(x)
+        refresh = (sparsity >= 0 and (t % self.mask_refresh_interval == 0 and t <= self.stop_mask_refresh)
+                   and (t > 0 or not self.running_average))
+        out = self.prune_and_update_mask(x, sparsity, mask) if refresh else apply_mask(x, mask)
+        self.t += 1
+        self._t_mirror.wrote(self.t, t + 1)
+        if self.forward_hook is not None:
+            self.forward_hook(mask, name)
+        return out
+
+
+class UniformPruningCallback(MagnitudePruningCallback):
+    """Unstructured uniform random pruning; never re-activates pruned positions
+    (ref qsparse/sparse.py:125-152).  The random choice uses numpy's global RNG on the
+    host exactly like the reference (API compatibility; not a bandwidth path)."""
+
+    def initialize(self, mask: torch.Tensor):
+        pass
+
+    def receive_input(self, x: torch.Tensor):
+        pass
+
+    def prune_and_update_mask(self, x: torch.Tensor, sparsity: float, mask: torch.Tensor) -> torch.Tensor:
+        cur_sparsity = (~mask).sum().item() / mask.numel()
+        if cur_sparsity > sparsity:
+            logging.warning("sparsity is decreasing, which shall not happen")
+        budget = int(round((sparsity - cur_sparsity) * np.prod(mask.shape)))
+        slots = mask.nonzero(as_tuple=True)
+        chosen = np.random.choice(range(len(slots[0])), size=budget, replace=False)
+        mask.data[[slot[chosen] for slot in slots]] = False
+        return apply_mask(x, mask)
+
+
+class PruneLayer(nn.Module):
+    """Prune the input tensor on a schedule (ref qsparse/sparse.py:157-273).
+
+    ``state_dict`` keys as in the reference: ``mask`` (bool, input shape with the
+    non-pruned axes set to 1), ``_n_updates`` (int32 [1]), ``_cur_sparsity`` (fp32 [1]),
+    ``callback.t`` (int64 [1]), ``callback.magnitude`` (fp32, mask shape)."""
+
+    def __str__(self):
+        return (f"PruneLayer(sparsity={self.sparsity}, start={self.start}, interval={self.interval}, "
+                f"repetition={self.repetition}, dimensions={self.dimensions})")
+
+    def __repr__(self):
+        return str(self)
+
+    def __init__(self, sparsity: float = 0.5, dimensions: Iterable[int] = {1},
+                 callback: MagnitudePruningCallback = None, start: int = 1000, interval: int = 1000,
+                 repetition: int = 4, rampup: bool = False, name=""):
+        super().__init__()
+        if get_option("log_on_created"):
+            logging.warning(f"[Prune{name if name == '' else f' @ {name}'}] start = {start} interval = {interval} "
+                            f"repetition = {repetition} sparsity = {sparsity} dimensions = {dimensions}")
+        self.schedules = [start + interval * ((1 if rampup else 0) + i) for i in range(repetition)]
+        self.start = start
+        self.interval = interval
+        self.repetition = repetition
+        self.sparsity = sparsity
+        self.name = name
+        self.callback = callback if callback is not None else MagnitudePruningCallback()
+        self.rampup_interval = 0 if rampup else interval
+        self.dimensions = set(dimensions)
+        for key in ("mask", "_n_updates", "_cur_sparsity"):  # shape-less placeholders until the first forward
+            self.register_parameter(key, nn.Parameter(torch.tensor(-1, dtype=torch.int), requires_grad=False))
+        self._n_mirror = HostMirror()
+        self._s_mirror = HostMirror()
+
+    @property
+    def initted(self) -> bool:
+        return self._n_mirror.get(self._n_updates) != -1
+
+    def _allocate(self, x: torch.Tensor):
+        assert len(x.shape) > 1
+        N.require_cuda(x, "x")
+        mask_shape = [s if i in self.dimensions else 1 for i, s in enumerate(x.shape)]
+        self.mask = nn.Parameter(torch.ones(*mask_shape, dtype=torch.bool, device=x.device), requires_grad=False)
+        if self.mask.numel() == 1:
+            logging.warn(f"the mask shape of {self.name} is {tuple(self.mask.shape)}, which is not prunable")
+        self._n_updates = nn.Parameter(torch.zeros(1, dtype=torch.int, device=x.device), requires_grad=False)
+        self._cur_sparsity = nn.Parameter(torch.zeros(1, device=x.device), requires_grad=False)
+        self._n_mirror.wrote(self._n_updates, 0)
+        self._s_mirror.wrote(self._cur_sparsity, 0.0)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self.initted:
+            self._allocate(x)
+        n = self._n_mirror.get(self._n_updates)
+        if (n in self.schedules) and self.training:
+            # cubic ramp, stored in an fp32 parameter (ref qsparse/sparse.py:252-257)
+            ratio = (1.0 - (n - self.start + self.rampup_interval) / (self.interval * self.repetition)) ** 3
+            value = self.sparsity * (1 - ratio)
+            self._cur_sparsity[0] = value
+            self._s_mirror.wrote(self._cur_sparsity, float(np.float32(value)))
+            logging.warning(f"[Prune{self.name if self.name == '' else f' @ {self.name}'}] [Step {n}] "
+                            f"pruned {float(np.float32(value)):.02f}")
+        if not self.training or self.mask.numel() == 1:
+            return apply_mask(x, self.mask)
+        if n >= self.start:
+            if n == self.start:
+                logging.warning(f"Start pruning at {self.name} @ {n}")
+            out = self.callback(x, self._s_mirror.get(self._cur_sparsity), mask=self.mask, name=self.name)
+        else:
+            out = x
+        self._n_updates += 1
+        self._n_mirror.wrote(self._n_updates, n + 1)
+        return out
+
+
+def prune(inp: nn.Module = None, sparsity: float = 0.5, dimensions: Iterable[int] = {1},
+          callback: MagnitudePruningCallback = None, start: int = 1000, interval: int = 1000,
+          repetition: int = 4, rampup: bool = False, name="") -> nn.Module:
+    """Create a ``PruneLayer`` (no input module) or wrap the weight of ``inp`` with one
+    (ref qsparse/sparse.py:276-339)."""
+    callback = callback or MagnitudePruningCallback()
+    kwargs = dict(start=int(start), sparsity=sparsity, interval=int(interval), repetition=repetition,
+                  rampup=rampup, name=name, callback=callback, dimensions=dimensions)
+    if inp is None:
+        layer = PruneLayer(**kwargs)
+        setattr(layer, "_kwargs", kwargs)
+        return layer
+    if isinstance(inp, nn.Module):
+        return imitate(inp, "prune", PruneLayer(**kwargs))
+    raise ValueError(f"{inp} is not a valid argument for prune")
+
+
+def devise_layerwise_pruning_schedule(net: nn.Module, start: int = 1, interval: int = 10,
+                                      mask_refresh_interval: int = 1, inplace=False):
+    """Stagger the start of every PruneLayer, attribute for attribute as the reference
+    does (ref qsparse/sparse.py:343-359).  Note that the reference leaves
+    ``rampup_interval`` untouched, which makes the ramp formula overshoot afterwards
+    (SURVEY Q15); that behaviour is kept, not fixed."""
+    if not inplace:
+        net = copy.deepcopy(net)
+    layers = [m for m in net.modules() if isinstance(m, PruneLayer)]
+    weight_only = all(p.name.endswith(".prune") for p in layers)
+    for layer in layers:
+        layer.start = start
+        layer.interval = interval
+        layer.repetition = 1
+        layer.schedules = [start]
+        layer.callback.mask_refresh_interval = mask_refresh_interval
+        layer.callback.stop_mask_refresh = interval
+        if weight_only:
+            layer.callback.running_average = False
+        start += interval + 1
+    logging.danger(f"Pruning stops at iteration - {start}")
+    return net

@@ -1,0 +1,298 @@
+"""GPU parity, part 2: CUDA kernels (through the C-ABI) against the CPU oracle on seeded
+inputs — odd shapes, unaligned pointers, channels_last, element masks, big-ish sizes —
+and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests.conftest import bits_equal, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def rnd(shape, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(shape) * scale).astype(np.float32)
+    f = x.reshape(-1)
+    if f.size >= 16:
+        f[rng.choice(f.size, 8, replace=False)] = [0.0, -0.0, 0.5, -0.5, 1.5, 2.5, 1e-40, -3.0]
+    return x
+
+
+SHAPES = [
+    ((4, 6, 7, 7), 1),      # inner 49 (odd)
+    ((3, 5, 56, 56), 1),    # inner 3136, row mode, rows misaligned to 32 B? (3136*4 % 32 == 0)
+    ((2, 7, 9, 11), 1),     # inner 99
+    ((64, 130), 1),         # [N, C], inner 1 (column mode)
+    ((16, 4, 3, 3), 0),     # weights, channelwise=0, inner 36
+    ((5, 3, 33), 2),        # channel = last axis
+    ((2, 3, 1000), 1),      # inner 1000
+    ((1, 2, 70001), 1),     # long rows, odd length
+]
+
+
+@pytest.mark.parametrize("shape,ci", SHAPES)
+def test_fakequant_channelwise_vs_oracle(shape, ci):
+    from qsparse_b200.quantize import quantize_with_decimal, quantize_with_scaler, quantize_with_line
+    x = rnd(shape, 11, 2.0)
+    C = shape[ci]
+    rng = np.random.default_rng(5)
+    dec = rng.integers(-1, 9, C).astype(np.float32)
+    sc = rng.uniform(0.01, 0.7, C).astype(np.float32)
+    lines = np.stack([rng.uniform(-2, -0.1, C), rng.uniform(0.1, 2, C)], 1).astype(np.float32)
+    xc = cu(x)
+    assert bits_equal(npy(quantize_with_decimal(xc, 8, cu(dec), ci)), orc.fq_pow2_fwd(x, dec, ci))
+    assert bits_equal(npy(quantize_with_scaler(xc, 8, cu(sc), ci)), orc.fq_scaler_fwd(x, sc, ci))
+    for fzp in (True, False):
+        assert bits_equal(npy(quantize_with_line(xc, 5, cu(lines), ci, False, fzp)),
+                          orc.fq_line_fwd(x, lines, 5, ci, fzp))
+    # per tensor
+    assert bits_equal(npy(quantize_with_decimal(xc, 8, 4)), orc.fq_pow2_fwd(x, 4))
+    assert bits_equal(npy(quantize_with_scaler(xc, 8, 0.0371)), orc.fq_scaler_fwd(x, np.float32(0.0371)))
+
+
+@pytest.mark.parametrize("shape,ci", SHAPES)
+def test_ste_backward_vs_oracle(shape, ci):
+    from qsparse_b200 import ops
+    from qsparse_b200._native import channel_layout
+    g = rnd(shape, 12, 3.0)
+    g.reshape(-1)[::97] = np.nan
+    C = shape[ci]
+    rng = np.random.default_rng(6)
+    dec = rng.integers(2, 7, C).astype(np.float32)
+    sc = rng.uniform(0.001, 0.05, C).astype(np.float32)
+    for scale, is_dec in ((dec, True), (sc, False)):
+        gc = cu(g).clone()
+        ops.ste_bwd(gc, cu(scale), is_dec, 8, 1, channel_layout(shape, ci))
+        ref, _ = orc.ste_bwd(g, scale, 8, ci, is_dec, True)
+        assert bits_equal(npy(gc), ref), is_dec
+
+
+def test_unaligned_and_channels_last():
+    from qsparse_b200.quantize import quantize_with_decimal, quantize_with_scaler
+    base = rnd((1 + 4 * 6 * 10 * 10,), 3, 2.0)
+    xc = cu(base)[1:].view(4, 6, 10, 10)            # data pointer only 4-byte aligned
+    x = base[1:].reshape(4, 6, 10, 10)
+    dec = np.arange(6, dtype=np.float32)
+    assert bits_equal(npy(quantize_with_decimal(xc, 8, cu(dec), 1)), orc.fq_pow2_fwd(x, dec, 1))
+    assert bits_equal(npy(quantize_with_decimal(xc, 8, 3)), orc.fq_pow2_fwd(x, 3))
+    xcl = cu(x).contiguous(memory_format=torch.channels_last)
+    y = quantize_with_decimal(xcl, 8, cu(dec), 1)
+    assert y.is_contiguous(memory_format=torch.channels_last)   # memory format follows the input
+    assert bits_equal(npy(y), orc.fq_pow2_fwd(x, dec, 1))
+    y = quantize_with_scaler(xcl, 8, 0.05)
+    assert bits_equal(npy(y), orc.fq_scaler_fwd(x, np.float32(0.05)))
+    # non-fp32 input: converted, result fp32
+    y = quantize_with_decimal(cu(x).half(), 8, 3)
+    assert y.dtype == torch.float32
+    assert bits_equal(npy(y), orc.fq_pow2_fwd(x.astype(np.float16).astype(np.float32), 3))
+
+
+@pytest.mark.parametrize("shape,ci", SHAPES)
+def test_reductions_vs_oracle(shape, ci):
+    from qsparse_b200 import ops
+    from qsparse_b200._native import channel_layout
+    x = rnd(shape, 21, 1.5)
+    for layout_ci in (ci, -1):
+        st = ops.reduce_stats(cu(x), channel_layout(shape, layout_ci), absmax=True, minmax=True, abssum=True,
+                              nnz=True)
+        assert bits_equal(npy(st["absmax"]), orc.absmax(x, layout_ci))
+        mn, mx = orc.minmax(x, layout_ci)
+        assert np.array_equal(npy(st["min"]), mn) and np.array_equal(npy(st["max"]), mx)
+        o, c, i = orc.layout(shape, layout_ci)
+        xr = np.abs(x.astype(np.float64)).reshape(o, c, i)
+        assert np.allclose(npy(st["abssum"]), xr.sum(axis=(0, 2)), rtol=1e-12, atol=0)
+        assert np.array_equal(npy(st["nnz"]), (xr != 0).sum(axis=(0, 2)).astype(np.float64))
+        assert npy(st["tensor_min"])[0] == x.min()
+    # each single-statistic instantiation
+    st = ops.reduce_stats(cu(x), channel_layout(shape, ci), absmax=True)
+    assert bits_equal(npy(st["absmax"]), orc.absmax(x, ci))
+    st = ops.reduce_stats(cu(x), channel_layout(shape, ci), minmax=True)
+    assert np.array_equal(npy(st["min"]), orc.minmax(x, ci)[0])
+    st = ops.reduce_stats(cu(x), channel_layout(shape, ci), abssum=True, absmax=True)
+    assert bits_equal(npy(st["absmax"]), orc.absmax(x, ci))
+
+
+def test_reduction_nan_propagates():
+    from qsparse_b200 import ops
+    x = rnd((4, 8, 100), 2)
+    x[1, 3, 17] = np.nan
+    st = ops.reduce_stats(cu(x), (4, 8, 100), absmax=True, minmax=True)
+    am, mn = npy(st["absmax"]), npy(st["min"])
+    assert np.isnan(am[3]) and np.isnan(mn[3]) and not np.isnan(np.delete(am, 3)).any()
+
+
+@pytest.mark.parametrize("n", [2, 7, 64, 1000, 4097, 100003, 1 << 20, (1 << 22) + 5])
+def test_kth_value_vs_sort(n):
+    from qsparse_b200 import ops
+    rng = np.random.default_rng(n)
+    v = (rng.standard_normal(n) * rng.choice([1e-3, 1.0, 50.0], n)).astype(np.float32)
+    if n >= 64:
+        v[rng.choice(n, n // 8, replace=False)] = 0.25          # heavy ties
+        v[rng.choice(n, 3, replace=False)] = [np.inf, -np.inf, -0.0]
+    s = np.sort(v)
+    vc = cu(v)
+    for k in sorted({0, 1, n // 3, n // 2, n - 2, n - 1} & set(range(n))):
+        got = npy(ops.kth_value(vc, k))[0]
+        assert got == s[k], (n, k)
+        got = npy(ops.kth_value(vc, k, take_abs=True))[0]
+        assert got == np.sort(np.abs(v))[k], (n, k, "abs")
+    if n >= 64:  # NaNs order last, like torch.sort
+        v2 = v.copy()
+        v2[:5] = np.nan
+        assert np.isnan(npy(ops.kth_value(cu(v2), n - 1))[0])
+        assert npy(ops.kth_value(cu(v2), n - 6))[0] == np.sort(v2)[n - 6]
+    # unaligned base pointer
+    if n > 8:
+        got = npy(ops.kth_value(vc[1:], (n - 1) // 2))[0]
+        assert got == np.sort(v[1:])[(n - 1) // 2]
+
+
+@pytest.mark.parametrize("shape", [(8, 16, 3, 3), (37, 11), (3, 5, 7, 9)])
+@pytest.mark.parametrize("sparsity", [0.0, 0.3, 0.5, 0.9])
+def test_unstructured_mask_vs_oracle(shape, sparsity):
+    from qsparse_b200 import calculate_mask_given_importance, ops
+    imp = np.abs(rnd(shape, 31))
+    m_ref, thr_ref = orc.mask_given_importance(imp, sparsity)
+    assert np.array_equal(npy(calculate_mask_given_importance(cu(imp), sparsity)), m_ref)
+    # fused build + apply
+    x = rnd(shape, 32)
+    mask = torch.empty(shape, dtype=torch.bool, device="cuda")
+    thr = ops.kth_value(cu(imp), orc.kth_index(sparsity, imp.size))
+    assert npy(thr)[0] == thr_ref
+    y = ops.mask_build_apply(cu(imp), thr, cu(x), mask)
+    assert np.array_equal(npy(mask), m_ref)
+    assert bits_equal(npy(y), orc.mask_apply(x, m_ref.reshape(-1)))
+
+
+@pytest.mark.parametrize("shape,mshape", [((4, 8, 5, 5), (1, 8, 1, 1)), ((3, 6, 7), (1, 6, 7)), ((5, 4, 3, 3), (5, 1, 1, 1)),
+                                          ((2, 3, 6, 6), (2, 3, 6, 6)), ((6, 9), (1, 9))])
+def test_mask_apply_and_fused_quant_vs_oracle(shape, mshape):
+    from qsparse_b200 import ops
+    from qsparse_b200.sparse import apply_mask
+    x = rnd(shape, 41, 2.0)
+    rng = np.random.default_rng(8)
+    m = rng.random(mshape) > 0.4
+    kind, layout = ops.mask_layout(shape, mshape)
+    ci = {"element": -1}.get(kind, None)
+    if kind == "channel":
+        ci = [i for i, s in enumerate(mshape) if s != 1][0]
+        o, c, i = layout
+        ref = (x.reshape(o, c, i) * m.reshape(1, c, 1).astype(np.float32)).reshape(shape)
+    else:
+        ref = x * m.astype(np.float32)
+    xc = cu(x).requires_grad_(True)
+    y = apply_mask(xc, cu(m))
+    assert bits_equal(npy(y), ref)                          # sign of zero kept
+    g = rnd(shape, 42)
+    y.backward(cu(g))
+    gref = (g.reshape(layout) * m.reshape(1, layout[1], 1).astype(np.float32)).reshape(shape) if kind == "channel" \
+        else g * m.astype(np.float32)
+    assert bits_equal(npy(xc.grad), gref)
+    # fused prune -> quantize forward / backward equals the two-step oracle
+    mflat = cu(m.reshape(-1))
+    yq = ops.fq_pow2_fwd(cu(x), 5.0, layout, mask=mflat)
+    assert bits_equal(npy(yq), orc.fq_pow2_fwd(ref, 5))
+    ys = ops.fq_scaler_fwd(cu(x), 0.043, layout, mask=mflat)
+    assert bits_equal(npy(ys), orc.fq_scaler_fwd(ref, np.float32(0.043)))
+    gc = cu(g).clone()
+    _, gx = ops.ste_bwd(gc, 5.0, True, 8, 0, layout, mask=mflat, clamp_in_place=True, want_gx=True)
+    gcl, _ = orc.ste_bwd(g, np.float32(5), 8, -1, True, False)
+    assert bits_equal(npy(gc), gcl)
+    gxr = (gcl.reshape(layout) * m.reshape(1, layout[1], 1).astype(np.float32)).reshape(shape) if kind == "channel" \
+        else gcl * m.astype(np.float32)
+    assert bits_equal(npy(gx), gxr)
+
+
+def test_fused_param_step_vs_oracle():
+    """qsb_prune_quant_params == magnitude EMA -> mask -> abs-max of kept -> scale EMA -> decimal."""
+    from qsparse_b200 import ops
+    C, shape = 64, (8, 64, 14, 14)
+    mag = np.zeros(C, np.float32)
+    scale = np.zeros(1, np.float32)
+    mag_d = cu(mag)
+    mask_d = torch.ones(C, dtype=torch.bool, device="cuda")
+    scale_d = cu(scale)
+    dec_d = torch.zeros(1, device="cuda")
+    mask = np.ones(C, bool)
+    for t in range(5):
+        x = np.maximum(rnd(shape, 100 + t), 0) * np.linspace(0.2, 2.0, C, dtype=np.float32).reshape(1, C, 1, 1)
+        st = ops.reduce_stats(cu(x), (8, C, 196), abssum=True, absmax=True)
+        refresh = t > 0
+        k = orc.kth_index(0.75, C)
+        ops.prune_quant_params(mag_d, mask_d, scale_d, dec_d, st, 8 * 196.0, t, 1, refresh, k, 8, t, True)
+        mag = orc.magnitude_ema(mag, orc.squeeze_mean_abs(x, (1, C, 1, 1)).reshape(-1), t)
+        if refresh:
+            mask, _ = orc.mask_given_importance(mag, 0.75)
+        amax_kept = np.array([np.max(orc.absmax(x, 1) * mask)], np.float32)
+        scale = orc.scale_ema(scale, amax_kept, 8, t)
+        assert ulp_diff(npy(mag_d), mag).max() <= 8, t
+        assert np.array_equal(npy(mask_d), mask), t
+        assert bits_equal(npy(scale_d), scale), t
+        assert bits_equal(npy(dec_d), orc.scale_to_decimal(scale)), t
+        y = ops.fq_pow2_fwd(cu(x), dec_d, (8, C, 196), mask=mask_d)
+        assert bits_equal(npy(y), orc.fq_pow2_fwd(x, npy(dec_d), 1, mask=mask))
+
+
+def test_magnitude_ema_full_and_l0():
+    from qsparse_b200 import ops
+    x = rnd((3, 4, 50), 51)
+    x[x < 0.3] = 0
+    mag = np.abs(rnd((3, 4, 50), 52))
+    md = cu(mag).clone()
+    ops.magnitude_ema_full_(md, cu(x), 3)
+    assert bits_equal(npy(md), orc.magnitude_ema(mag, np.abs(x), 3))
+    md = cu(mag).clone()
+    tmin = ops.reduce_stats(cu(x), (1, 1, x.size), nnz=True)["tensor_min"]
+    ops.magnitude_ema_full_(md, cu(x), 3, tmin, True)     # min(x) == 0 -> indicator
+    assert bits_equal(npy(md), orc.magnitude_ema(mag, (x != 0).astype(np.float32), 3))
+
+
+# ------------------------------------------------------------------ properties at full size
+def test_full_size_properties_config2():
+    """[256,64,56,56] (BASELINE config 2): idempotence, integer grid, pruned channels zero,
+    agreement with the oracle on a sampled sub-block."""
+    from qsparse_b200 import ops
+    torch.manual_seed(2)
+    shape = (256, 64, 56, 56)
+    x = torch.relu(torch.randn(shape, device="cuda"))
+    layout = (256, 64, 3136)
+    mask = (torch.arange(64, device="cuda") % 4 == 0)           # 75 % of the channels pruned
+    dec = torch.tensor([5.0], device="cuda")
+    y = ops.fq_pow2_fwd(x, dec, layout, mask=mask)
+    assert torch.equal(ops.fq_pow2_fwd(y, dec, layout, mask=mask), y)          # idempotent
+    q = y * 32.0
+    assert torch.equal(q, q.round())                                           # on the 2^-5 grid
+    assert torch.count_nonzero(y[:, ~mask]).item() == 0
+    assert torch.equal(y[:, mask], ops.fq_pow2_fwd(x[:, mask].contiguous(), 5.0, (1, 1, 256 * 16 * 3136)))
+    xs = x[7:9].contiguous()
+    assert bits_equal(npy(ops.fq_pow2_fwd(xs, dec, (2, 64, 3136), mask=mask)),
+                      orc.fq_pow2_fwd(npy(xs), 5, 1, mask=npy(mask)))
+    st = ops.reduce_stats(x, layout, abssum=True, absmax=True)
+    assert torch.equal(st["absmax"], x.abs().amax(dim=(0, 2, 3)))
+    ref = x.double().abs().sum(dim=(0, 2, 3))
+    assert torch.allclose(st["abssum"], ref, rtol=1e-12, atol=0)
+
+
+def test_full_size_select_64M():
+    """64 Mi-element importance (BASELINE config 4): exact threshold == torch.sort's, mask count."""
+    from qsparse_b200 import calculate_mask_given_importance, ops
+    torch.manual_seed(4)
+    n = 1 << 26
+    imp = (torch.randn(n, device="cuda") * 0.02).abs()
+    for s in (0.5, 0.75):
+        k = max(int(s * n - 1), 0) + 1
+        thr = ops.kth_value(imp, k)
+        ref = torch.sort(imp).values[k]
+        assert thr.item() == ref.item()
+        m = calculate_mask_given_importance(imp, s)
+        assert int((~m).sum().item()) == k            # distinct values: exactly k pruned
