@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of BASELINE.json's north_star on config[1]:
+
+    [256, 64, 56, 56] fp32 activations, 8-bit pow2 fake-quant forward/backward
+    + 75 % structured channel prune, as ONE fused training step per "step":
+        reduce (sum|x|, max|x| per channel)      4 B/elem
+        parameters (EMA, k-th threshold, mask, scale, decimal)  ~0
+        y  = Q(x * mask)                         8 B/elem
+        gx = clamp(g) * mask                     8 B/elem     -> 20 B/elem algorithmic
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K ...   (CPU port of the reference)
+
+Prints ONE JSON line (rank 0).  `value` = algorithmic GB/s of the whole job with the
+inputs resident in HBM; `e2e` = the same metric through the C-ABI host-buffer entry
+point (pinned host x, g in; y, gx out; copies inside the timed region).
+Weak scaling: every rank owns its own [256,64,56,56] shard; only the 768-byte
+per-channel statistics row is all-gathered (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SHAPE = (256, 64, 56, 56)
+LAYOUT = (256, 64, 3136)
+SPARSITY, BITS = 0.75, 8
+BYTES_PER_ELEM = 20          # reduce 4 + apply 8 + backward 8
+METRIC = "quantize+prune fwd/bwd HBM GB/s"
+CONFIG = {
+    "workload": "config[1]: [256,64,56,56] fp32, 8-bit pow2 fake-quant fwd/bwd + 75% structured channel prune "
+                "(fused training step: reduce 4 + apply 8 + backward 8 = 20 B/elem)",
+    "shape_per_gpu": list(SHAPE), "bits": BITS, "sparsity": SPARSITY, "parallelism": "batch-sharded, stats all-gather",
+    "l2": "inputs (2 x 205.5 MB per step) exceed the 126 MB L2; no flush",
+}
+
+
+def peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path).read().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]            # the upper half = samples under load
+            out.update(sm_mhz=busy[len(busy) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------- CPU port (reference arm)
+def cpu_step_factory(batch: int, threads: int):
+    """The oracle (plain-C restatement of the reference) running the same fused step on the
+    host: per-thread batch slices, statistics combined like the reference's means."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+
+    C = SHAPE[1]
+    rng = np.random.default_rng(2)
+    x = np.maximum(rng.standard_normal((batch,) + SHAPE[1:], dtype=np.float32), 0)
+    g = rng.standard_normal(x.shape, dtype=np.float32)
+    threads = max(1, min(threads, batch))
+    slices = [slice(i * batch // threads, (i + 1) * batch // threads) for i in range(threads)]
+    pool = ThreadPoolExecutor(threads)
+    state = dict(t=0, mag=np.zeros(C, np.float32), mask=np.ones(C, bool), scale=np.zeros(1, np.float32))
+    k_sparsity = SPARSITY
+
+    def stats(sl):
+        xs = x[sl]
+        return orc.squeeze_mean_abs(xs, (1, C, 1, 1)).reshape(-1).astype(np.float64) * xs.shape[0], orc.absmax(xs, 1)
+
+    def step():
+        t = state["t"]
+        parts = list(pool.map(stats, slices))
+        mean = (sum(p[0] for p in parts) / batch).astype(np.float32)
+        amax = np.max(np.stack([p[1] for p in parts]), axis=0)
+        state["mag"] = orc.magnitude_ema(state["mag"], mean, t)
+        if t > 0:
+            state["mask"], _ = orc.mask_given_importance(state["mag"], k_sparsity)
+        state["scale"] = orc.scale_ema(state["scale"], np.array([np.max(amax * state["mask"])], np.float32), BITS, t)
+        dec = orc.scale_to_decimal(state["scale"])
+        mask = state["mask"]
+        list(pool.map(lambda sl: orc.fq_pow2_fwd(x[sl], dec, 1, mask=mask), slices))
+        list(pool.map(lambda sl: orc.ste_bwd(g[sl], dec, BITS, 1, True, False, mask=mask), slices))
+        state["t"] += 1
+
+    return step, x.size
+
+
+def time_cpu(batch: int, threads: int, steps: int, warmup: int):
+    step, n = cpu_step_factory(batch, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n * BYTES_PER_ELEM / dt / 1e9, n / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 64
+    gbs, eps, dt = time_cpu(batch, threads, max(args.steps, 1), min(max(args.warmup, 1), 3))
+    sample = f"[{batch},64,56,56] slice of the per-GPU tensor per step, {threads} host threads (batch-sliced)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "elems_per_s": round(eps, 1),
+        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is pure Python/PyTorch and does not exist on the GPU box; this is oracle/ (its plain-C "
+                "restatement, pinned to the reference's golden vectors) on the host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from qsparse_b200 import _native as N
+    from qsparse_b200 import ops
+    from qsparse_b200.parallel import StatExchange
+    from qsparse_b200.util import kth_rank
+    from ctypes import byref, c_double, c_int, c_int64, c_void_p
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = N.load_library()
+
+    n = SHAPE[0] * SHAPE[1] * SHAPE[2] * SHAPE[3]
+    C = SHAPE[1]
+    gen = torch.Generator(device=dev).manual_seed(2 + rank)
+    x = torch.relu(torch.randn(SHAPE, device=dev, generator=gen))
+    g = torch.randn(SHAPE, device=dev, generator=gen)
+    y = torch.empty_like(x)
+    gx = torch.empty_like(x)
+    mag = torch.zeros(C, device=dev)
+    mask = torch.ones(C, dtype=torch.bool, device=dev)
+    scale = torch.zeros(1, device=dev)
+    dec = torch.zeros(1, device=dev)
+    ex = StatExchange(C, dev)
+    k = kth_rank(SPARSITY, C)
+    state = {"t": 0}
+    stream = N.stream_ptr(dev)
+    ev_b0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_b1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def bwd():
+        # gx = clamp(g) * mask, dense read of g, dense write of gx (8 B/elem)
+        N.check(lib.qsb_ste_bwd(N.ptr(g), N.ptr(None), N.ptr(gx), N.ptr(dec), c_int64(1), c_double(0.0), c_int(1),
+                                c_int(BITS), c_int(0), N.ptr(mask), c_int(N.MASK_CHANNEL), c_int64(LAYOUT[0]),
+                                c_int64(LAYOUT[1]), c_int64(LAYOUT[2]), stream), "qsb_ste_bwd")
+
+    def step(i=None):
+        t = state["t"]
+        ops.reduce_stats(x, LAYOUT, abssum=True, absmax=True, out={"abssum": ex.row.abssum, "absmax": ex.row.absmax})
+        rows, n_rows, stride = ex.gather()
+        a0, m0 = ex.views(rows)
+        ops.prune_quant_params(mag, mask, scale, dec, {"abssum": a0, "absmax": m0},
+                               float(LAYOUT[0] * LAYOUT[2] * n_rows), t, 1, t > 0, k, BITS, t, True,
+                               n_rows=n_rows, row_stride_bytes=stride)
+        ops.fq_pow2_fwd(x, dec, LAYOUT, mask=mask, out=y)
+        if i is not None:
+            ev_b0[i].record()
+        bwd()
+        if i is not None:
+            ev_b1[i].record()
+        state["t"] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for i in range(args.steps):
+        step(i)
+    end.record()
+    barrier()
+    ms = start.elapsed_time(end)
+    bwd_ms = sum(a.elapsed_time(b) for a, b in zip(ev_b0, ev_b1)) / args.steps
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = tmax.item()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * n * BYTES_PER_ELEM / (ms_per_step * 1e-3) / 1e9
+    launches_per_step = 5      # reduce stage 1 + finalize, parameters, forward apply, backward
+
+    # ---- e2e: host buffers through the C-ABI (copies inside the timed region) ----
+    e2e_steps = max(3, min(args.steps, 10))
+    hx = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
+    hg = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
+    hy = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
+    hgx = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
+    hx.copy_(x)
+    hg.copy_(g)
+    ctx = c_void_p()
+    N.check(lib.qsb_host_ctx_create(byref(ctx), c_int64(n), c_int64(C), c_int(8)), "qsb_host_ctx_create")
+    e_state = dict(mag=torch.zeros(C, device=dev), mask=torch.ones(C, dtype=torch.bool, device=dev),
+                   scale=torch.zeros(1, device=dev), dec=torch.zeros(1, device=dev), t=0)
+
+    def e2e_step():
+        t = e_state["t"]
+        N.check(lib.qsb_host_prune_quant_step(ctx, N.ptr(hx), N.ptr(hg), N.ptr(hy), N.ptr(hgx), N.ptr(e_state["mag"]),
+                                              N.ptr(e_state["mask"]), N.ptr(e_state["scale"]), N.ptr(e_state["dec"]),
+                                              c_int64(LAYOUT[0]), c_int64(LAYOUT[1]), c_int64(LAYOUT[2]), c_int64(t),
+                                              c_int64(k), c_int(BITS), c_int64(t), stream),
+                "qsb_host_prune_quant_step")
+        e_state["t"] += 1
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = tmax.item()
+    e2e_value = world * n * BYTES_PER_ELEM / e2e_s / 1e9
+    # the host path and the resident path must agree bit for bit on the same inputs
+    same = None
+    if rank == 0:
+        chk = dict(mag=torch.zeros(C, device=dev), mask=torch.ones(C, dtype=torch.bool, device=dev),
+                   scale=torch.zeros(1, device=dev), dec=torch.zeros(1, device=dev))
+        if world == 1:
+            for t in range(2):
+                st = ops.reduce_stats(x, LAYOUT, abssum=True, absmax=True)
+                ops.prune_quant_params(chk["mag"], chk["mask"], chk["scale"], chk["dec"], st,
+                                       float(LAYOUT[0] * LAYOUT[2]), t, 1, t > 0, k, BITS, t, True)
+            yy = ops.fq_pow2_fwd(x, chk["dec"], LAYOUT, mask=chk["mask"])
+            e_chk = dict(mag=torch.zeros(C, device=dev), mask=torch.ones(C, dtype=torch.bool, device=dev),
+                         scale=torch.zeros(1, device=dev), dec=torch.zeros(1, device=dev))
+            for t in range(2):
+                N.check(lib.qsb_host_prune_quant_step(ctx, N.ptr(hx), N.ptr(hg), N.ptr(hy), N.ptr(hgx),
+                                                      N.ptr(e_chk["mag"]), N.ptr(e_chk["mask"]), N.ptr(e_chk["scale"]),
+                                                      N.ptr(e_chk["dec"]), c_int64(LAYOUT[0]), c_int64(LAYOUT[1]),
+                                                      c_int64(LAYOUT[2]), c_int64(t), c_int64(k), c_int(BITS),
+                                                      c_int64(t), stream), "host step")
+            same = bool(torch.equal(hy.to(dev), yy) and torch.equal(e_chk["mask"], chk["mask"]))
+    N.check(lib.qsb_host_ctx_destroy(ctx), "qsb_host_ctx_destroy")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peak_hbm()
+    bwd_gbs = n * 8 / (bwd_ms * 1e-3) / 1e9
+    traffic = None
+    prof = ROOT / "profiles" / "roofline_traffic.json"
+    if prof.exists():
+        try:
+            traffic = json.loads(prof.read_text()).get("ste_bwd_fused_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    # CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        gbs, eps, dt = time_cpu(64, threads, 5, 1)
+        cpu_baseline = {"value": round(gbs, 3), "unit": "GB/s", "cores": threads, "kind": "port",
+                        "sample": f"5 steps over a [64,64,56,56] slice (1/4 of the tensor), {dt*1e3:.0f} ms/step",
+                        "elems_per_s": round(eps, 1)}
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "elems_per_s": round(world * n / (ms_per_step * 1e-3), 1),
+        "frac_of_measured_hbm_peak": round(value / world / peak, 4),
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4 * world,
+                "d2h_bytes_per_step": 2 * n * 4 * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
+                "api": "qsb_host_prune_quant_step (C-ABI, pinned host buffers, 8 chunks, 3 streams)",
+                "matches_resident_path": same},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "map_chan_kernel<SteOp<CHANNEL,gx>> (fused STE backward, dense 8 B/elem)",
+                     "achieved": round(bwd_gbs, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": round(bwd_gbs / peak, 4), "traffic": traffic,
+                     "algorithmic_bytes_per_launch": n * 8, "avg_launch_us": round(bwd_ms * 1e3, 2)},
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

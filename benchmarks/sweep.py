@@ -70,18 +70,21 @@ def main():
     emask = torch.rand(shape, device=dev) > 0.5
 
     report("torch_copy", 8 * n, lambda: y.copy_(x))
-    tunings = [0] if args.quick else [0, -1, 2, 3, 4, 6, 8]
-    for tune in tunings:
+    for tune in ([0] if args.quick else [0, 4, 8]):      # per-tensor grid policy (key 0)
         ops.set_tuning(0, tune)
-        report("fq_pow2_tensor", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, (1, 1, n), out=y), tune=tune)
-        report("fq_pow2_chdec", 8 * n, lambda: ops.fq_pow2_fwd(x, decC, layout, out=y), tune=tune)
-        report("fq_pow2_chmask0", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, layout, mask=mask0, out=y), tune=tune)
-        report("fq_pow2_chmask75", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, layout, mask=mask75, out=y), tune=tune,
-               note="dense-algorithmic bytes; 75% of reads skipped")
-        report("ste_bwd_inplace", 8 * n, lambda: ops.ste_bwd(g, dec1, True, 8, 0, (1, 1, n)), tune=tune)
+        report("fq_pow2_tensor", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, (1, 1, n), out=y), tune0=tune)
+        report("ste_bwd_inplace", 8 * n, lambda: ops.ste_bwd(g, dec1, True, 8, 0, (1, 1, n)), tune0=tune)
     ops.set_tuning(0, 0)
+    for tune in ([0] if args.quick else [0, 2, 3, 4, 6, 8]):   # per-channel grid policy (key 1)
+        ops.set_tuning(1, tune)
+        report("fq_pow2_chdec", 8 * n, lambda: ops.fq_pow2_fwd(x, decC, layout, out=y), tune1=tune)
+        report("fq_pow2_chmask0", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, layout, mask=mask0, out=y), tune1=tune)
+        report("fq_pow2_chmask75", 8 * n, lambda: ops.fq_pow2_fwd(x, dec1, layout, mask=mask75, out=y), tune1=tune,
+               note="dense-algorithmic bytes; 75% of reads skipped")
+    ops.set_tuning(1, 0)
     report("fq_pow2_emask", 9 * n, lambda: ops.fq_pow2_fwd(x, dec1, (1, 1, n), mask=emask, out=y))
     report("fq_scaler_tensor", 8 * n, lambda: ops.fq_scaler_fwd(x, 0.037, (1, 1, n), out=y))
+    report("fq_line_tensor", 8 * n, lambda: ops.fq_line_fwd(x, (-0.1, 0.9), 8, True, (1, 1, n), out=y))
     report("fq_line_ch", 8 * n, lambda: ops.fq_line_fwd(
         x, torch.tensor([[-0.1, 0.9]] * 64, device=dev), 8, True, layout, out=y))
 
@@ -91,7 +94,10 @@ def main():
         ops.N.check(lib_gx.qsb_ste_bwd(ops.N.ptr(g), ops.N.ptr(None), ops.N.ptr(gx), ops.N.ptr(dec1), c_int64(1),
                                        c_double(0), c_int(1), c_int(8), c_int(0), ops.N.ptr(mask75), c_int(1),
                                        c_int64(256), c_int64(64), c_int64(3136), ops.N.stream_ptr(dev)), "ste")
-    report("ste_bwd_fused_gx", 8 * n, bwd_fused)
+    for tune in ([0] if args.quick else [0, 3, 4, 6, 8]):
+        ops.set_tuning(1, tune)
+        report("ste_bwd_fused_gx", 8 * n, bwd_fused, tune1=tune)
+    ops.set_tuning(1, 0)
     report("mask_apply_ch", 8 * n, lambda: ops.mask_apply(x, mask75, layout, out=y))
     report("reduce_abssum_absmax_ch", 4 * n, lambda: ops.reduce_stats(x, layout, abssum=True, absmax=True))
     report("reduce_absmax_tensor", 4 * n, lambda: ops.reduce_stats(x, (1, 1, n), absmax=True))
@@ -137,6 +143,19 @@ def main():
     thr = ops.kth_value(magf, n4 // 2)
     report("c4_mask_build_apply", 13 * n4, lambda: ops.mask_build_apply(magf, thr, wt, mk, out=yb))
     report("c4_torch_sort", 4 * n4, lambda: torch.sort(magf))
+    del wt, magf, yb, mk, x, g, y
+
+    # ---------------- config 5: flat sweep, fused prune(element mask) + pow2 quant fwd, bwd
+    for p in ([22, 26] if args.quick else [20, 22, 24, 26, 28, 30]):
+        n5 = 1 << p
+        x5 = torch.randn(n5, device=dev)
+        y5 = torch.empty_like(x5)
+        m5 = torch.rand(n5, device=dev) > 0.5
+        report("c5_fused_fwd", 9 * n5, lambda: ops.fq_pow2_fwd(x5, dec1, (1, 1, n5), mask=m5, out=y5), log2n=p)
+        report("c5_fused_bwd", 9 * n5, lambda: ops.ste_bwd(x5, dec1, True, 8, 0, (1, 1, n5), mask=m5,
+                                                           clamp_in_place=False, want_gx=True), log2n=p)
+        report("c5_plain_fwd", 8 * n5, lambda: ops.fq_pow2_fwd(x5, dec1, (1, 1, n5), out=y5), log2n=p)
+        del x5, y5, m5
     out.close()
 
 

@@ -52,9 +52,17 @@ const char *qsb_error_string(int code);
 /* SM count and L2 size of the current device. */
 int qsb_device_info(int *sm_count, int64_t *l2_bytes);
 /* Benchmark-only knobs; defaults are what the product uses.
- *   key 0: CTAs per SM of the streaming kernels (0 = occupancy-derived
- *          persistent grid, -1 = one CTA per tile, non persistent). */
+ *   key 0: per-tensor streaming kernels: 0 = one CTA per tile (default),
+ *          n > 0 = persistent grid of n CTAs per SM;
+ *   key 1: per-channel streaming kernels: 0 = occupancy-derived persistent
+ *          grid (default), n > 0 = n CTAs per SM. */
 int qsb_set_tuning(int key, int value);
+/* Test hook: compares the kernels' reciprocal-based exact division with
+ * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and
+ * adds the number of bit mismatches to *mismatches_dev (must be zeroed). */
+int qsb_selftest_fastdiv(int64_t n_threads, int64_t pairs_per_thread,
+                         uint64_t seed, unsigned long long *mismatches_dev,
+                         void *stream);
 
 /* ------------------------------------------------------------------------
  * K1  fake-quant forward.  y may alias x.  An optional prune mask is applied
@@ -205,10 +213,18 @@ int qsb_mask_build_apply(const float *importance, int take_abs,
  *   -> decimal (quantize.py:316).
  * refresh_mask == 0 keeps the existing mask (sparse.py:115-116).
  * update_scale == 0 skips the quantizer's optimize (eval / before timeout).
+ * update_magnitude: 0 keep, 1 running average, 2 importance = this step's
+ * mean |x| (running_average=False, sparse.py:63-64).
+ * The statistics may come as n_stat_rows rows (one per rank after an
+ * all-gather, or one per staged chunk of a host tensor), stat_row_stride_bytes
+ * apart; they are combined in row order: SUM for abssum, MAX for absmax.
+ * `count` is the number of elements per channel over ALL rows.
  * ---------------------------------------------------------------------- */
 int qsb_prune_quant_params(float *magnitude, uint8_t *mask, float *scale,
                            float *decimal_out, const double *abssum,
-                           const float *absmax, int64_t channels, double count,
+                           const float *absmax, int64_t n_stat_rows,
+                           int64_t stat_row_stride_bytes, int64_t channels,
+                           double count,
                            int64_t t_prune, int update_magnitude,
                            int refresh_mask, int64_t k, int bits,
                            int64_t t_quant, int update_scale, void *stream);
@@ -220,21 +236,30 @@ int qsb_prune_quant_params(float *magnitude, uint8_t *mask, float *scale,
  * the results are in the host buffers.
  * ---------------------------------------------------------------------- */
 typedef struct qsb_host_ctx qsb_host_ctx;
-int qsb_host_ctx_create(qsb_host_ctx **out, int64_t max_elems_per_chunk,
-                        int n_slots);
+/* The context owns device staging buffers for 4 tensors of max_elems floats,
+ * three streams (upload / compute / download) and per-chunk events. */
+int qsb_host_ctx_create(qsb_host_ctx **out, int64_t max_elems,
+                        int64_t max_channels, int n_chunks);
 int qsb_host_ctx_destroy(qsb_host_ctx *ctx);
 
 /* One fused training step of prune(dimensions={channel}) -> pow2 quantize on
- * host tensors (config 2 of BASELINE.json): forward y = Q(x*mask) with this
- * step's statistics, backward gx = clamp(g)*mask.  State (magnitude, mask,
- * scale) lives on the device in caller-provided buffers. */
+ * HOST tensors (config 2 of BASELINE.json): forward y = Q(x*mask) with this
+ * step's statistics (magnitude EMA at step t_prune, mask refresh when
+ * t_prune > 0 with threshold rank k, scale EMA at step t_quant), backward
+ * gx = clamp(g)*mask.  The layer state (magnitude[C], mask[C], scale[1],
+ * decimal[1]) lives on the device in caller-provided buffers.  Host buffers
+ * should be pinned.  Work is ordered after caller_stream; the call returns when
+ * y_host and gx_host are complete.
+ * ref: PruneLayer.forward sparse.py:215-273 -> QuantizeLayer.forward
+ * quantize.py:473-518 and their backward passes. */
 int qsb_host_prune_quant_step(qsb_host_ctx *ctx, const float *x_host,
                               const float *g_host, float *y_host,
                               float *gx_host, float *magnitude_dev,
                               uint8_t *mask_dev, float *scale_dev,
                               float *decimal_dev, int64_t outer,
                               int64_t channels, int64_t inner, int64_t t_prune,
-                              int64_t k, int bits, int64_t t_quant);
+                              int64_t k, int bits, int64_t t_quant,
+                              void *caller_stream);
 
 #ifdef __cplusplus
 }

@@ -44,9 +44,14 @@ _SIGNATURES = {
     "qsb_kth_value": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),
     "qsb_mask_from_threshold": (c_int, [_P, c_int, _P, _P, c_int64, _P]),
     "qsb_mask_build_apply": (c_int, [_P, c_int, _P, _P, _P, _P, c_int64, _P]),
-    "qsb_prune_quant_params": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_double, c_int64, c_int, c_int,
-                                       c_int64, c_int, c_int64, c_int, _P]),
+    "qsb_prune_quant_params": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_double, c_int64, c_int,
+                                       c_int, c_int64, c_int, c_int64, c_int, _P]),
+    "qsb_host_ctx_create": (c_int, [ctypes.POINTER(c_void_p), c_int64, c_int64, c_int]),
+    "qsb_host_ctx_destroy": (c_int, [_P]),
+    "qsb_host_prune_quant_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,
+                                          c_int64, c_int, c_int64, _P]),
     "qsb_set_tuning": (c_int, [c_int, c_int]),
+    "qsb_selftest_fastdiv": (c_int, [c_int64, c_int64, ctypes.c_uint64, _P, _P]),
 }
 
 _lib = None

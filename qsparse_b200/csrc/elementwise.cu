@@ -10,7 +10,7 @@
 namespace qsb {
 
 MapTuning &map_tuning() {
-  static MapTuning t{0};
+  static MapTuning t{0, 0};
   return t;
 }
 
@@ -81,11 +81,14 @@ struct ScalerOp {
   float scale_host;
   const uint8_t *cmask;
   struct P {
-    float s, m;
+    float s, r, m;
+    bool ok;
   };
   __device__ __forceinline__ P params(int32_t c) const {
     P p;
     p.s = scale ? __ldg(scale + (int64_t)c * scale_stride) : scale_host;
+    p.r = __frcp_rn(p.s);
+    p.ok = fastdiv_divisor_ok(p.s);
     p.m = 1.0f;
     if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
     return p;
@@ -96,8 +99,9 @@ struct ScalerOp {
     float t = a;
     if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
     if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
-    // (x / s).round().int() : IEEE divide, round-half-even, truncating cast
-    const int q = __float2int_rz(rintf(__fdiv_rn(t, p.s)));
+    // (x / s).round().int() : IEEE divide, then round-half-even + cast in one
+    // cvt.rni.s32.f32 (== trunc(rint(v)) including the saturating edge cases)
+    const int q = __float2int_rn(div_rn_by(t, p.s, p.r, p.ok));
     o0 = __fmul_rn(__int2float_rn(q), p.s);
   }
 };
@@ -117,7 +121,8 @@ struct LineOp {
   float q_max;     // float(2^bits - 1)
   const uint8_t *cmask;
   struct P {
-    float lo, hi, step, qstart, m;
+    float lo, hi, step, rstep, qstart, m;
+    bool ok;
   };
   __device__ __forceinline__ P params(int32_t c) const {
     P p;
@@ -133,6 +138,8 @@ struct LineOp {
     // step = (end - start) / N ; step[step == 0] = 0.0001   (:159-160)
     p.step = __fdiv_rn(__fsub_rn(p.hi, p.lo), n_levels);
     if (p.step == 0.0f) p.step = 0.0001f;
+    p.rstep = __frcp_rn(p.step);
+    p.ok = fastdiv_divisor_ok(p.step);
     p.qstart = FZP ? 0.0f : rintf(__fdiv_rn(p.lo, p.step));  // (:163)
     p.m = 1.0f;
     if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
@@ -146,11 +153,11 @@ struct LineOp {
     if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
     const float xc = clamp_torch_tensor(t, p.lo, p.hi);  // (:158)
     if constexpr (FZP) {
-      float q = __fdiv_rn(__fsub_rn(xc, p.lo), p.step);      // (:176-177)
+      float q = div_rn_by(__fsub_rn(xc, p.lo), p.step, p.rstep, p.ok);  // (:176-177)
       q = clamp_torch(rintf(q), 0.0f, q_max);                // (:178)
       o0 = __fadd_rn(__fmul_rn(q, p.step), p.lo);            // (:179-180)
     } else {
-      float q = rintf(__fdiv_rn(xc, p.step));                         // (:162)
+      float q = rintf(div_rn_by(xc, p.step, p.rstep, p.ok));          // (:162)
       q = clamp_torch(__fsub_rn(q, p.qstart), 0.0f, q_max);           // (:164)
       o0 = __fmul_rn(__fadd_rn(q, p.qstart), p.step);                 // (:165)
     }
@@ -263,7 +270,7 @@ struct EmaFullOp {
                         kOutB = false, kCanSkip = false;
   const float *tensor_min;  // device scalar, only read when use_l0
   bool use_l0;
-  float t_f, t_plus_1_f;
+  float t_f, t_plus_1_f, r_t_plus_1;  // r = RN(1 / (t + 1)), host computed
   struct P {
     bool indicator;
   };
@@ -276,7 +283,7 @@ struct EmaFullOp {
   __device__ __forceinline__ void apply(float x, float mag, uint8_t, const P &p,
                                         float &o0, float &, uint8_t &) const {
     const float ax = p.indicator ? (x != 0.0f ? 1.0f : 0.0f) : fabsf(x);
-    o0 = __fdiv_rn(__fadd_rn(__fmul_rn(t_f, mag), ax), t_plus_1_f);
+    o0 = div_rn_by(__fadd_rn(__fmul_rn(t_f, mag), ax), t_plus_1_f, r_t_plus_1, true);
   }
 };
 
@@ -501,7 +508,65 @@ extern "C" int qsb_set_tuning(int key, int value) {
     map_tuning().ctas_per_sm = value;
     return 0;
   }
+  if (key == 1) {
+    map_tuning().chan_ctas_per_sm = value;
+    return 0;
+  }
   return QSB_E_BADARG;
+}
+
+// ---- self test: div_rn_by == __fdiv_rn on pseudo-random operand pairs ----------
+namespace qsb {
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return (uint32_t)((z ^ (z >> 31)) >> 16);
+}
+__global__ void selftest_fastdiv_kernel(uint64_t pairs_per_thread, uint64_t seed,
+                                        unsigned long long *mismatches) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one divisor per thread (as in the kernels: shared by many elements)
+  uint32_t sb = mix32(seed * 0x9e3779b97f4a7c15ull + tid * 2 + 1);
+  const uint32_t mode = tid & 3;
+  uint32_t sexp = 87 + (mix32(seed + tid * 7919) % 80);        // inside the fast range
+  if (mode == 3) sexp = mix32(seed ^ (tid * 104729)) & 0xff;    // anywhere (slow path too)
+  const float s = __uint_as_float((sb & 0x807fffffu) | (sexp << 23));
+  const float r = __frcp_rn(s);
+  const bool ok = fastdiv_divisor_ok(s);
+  unsigned long long bad = 0;
+  for (uint64_t i = 0; i < pairs_per_thread; ++i) {
+    uint32_t xb = mix32((seed + 0x1234567ull) * (tid + 1) + i * 0x9e3779b97f4a7c15ull);
+    float x;
+    if ((i & 7) == 0) {
+      // near rounding boundaries of rint(x / s): x ~ (k + 0.5) * s
+      const float k = (float)((int)(xb & 0xffff) - 32768) + 0.5f;
+      x = __fmul_rn(k, s);
+      x = __uint_as_float(__float_as_uint(x) + ((xb >> 16) & 3) - 1);
+    } else if ((i & 7) == 1) {
+      x = __uint_as_float(xb);  // anything, incl. NaN / inf / subnormal
+    } else {
+      const uint32_t xexp = 100 + (mix32(xb) % 56);
+      x = __uint_as_float((xb & 0x807fffffu) | (xexp << 23));
+    }
+    const float a = div_rn_by(x, s, r, ok);
+    const float b = __fdiv_rn(x, s);
+    const bool same = (__float_as_uint(a) == __float_as_uint(b)) || (a != a && b != b);
+    bad += same ? 0 : 1;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace qsb
+
+extern "C" int qsb_selftest_fastdiv(int64_t n_threads, int64_t pairs_per_thread,
+                                    uint64_t seed,
+                                    unsigned long long *mismatches_dev,
+                                    void *stream) {
+  if (n_threads <= 0 || pairs_per_thread <= 0 || !mismatches_dev) return QSB_E_BADARG;
+  const unsigned blocks = (unsigned)((n_threads + 255) / 256);
+  selftest_fastdiv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      (uint64_t)pairs_per_thread, seed, mismatches_dev);
+  QSB_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int qsb_mask_from_threshold(const float *importance, int take_abs,
@@ -537,7 +602,9 @@ extern "C" int qsb_magnitude_ema_full(float *magnitude, const float *x,
   if (!magnitude || !x) return QSB_E_BADARG;
   if (use_l0 && !tensor_min) return QSB_E_BADARG;
   MapIO io{x, magnitude, nullptr, magnitude, nullptr, nullptr};
-  EmaFullOp op{tensor_min, use_l0 != 0, (float)t, (float)(t + 1)};
+  const float tp1 = (float)(t + 1);
+  volatile float rcp = 1.0f / tp1;  // IEEE round-to-nearest on the host
+  EmaFullOp op{tensor_min, use_l0 != 0, (float)t, tp1, rcp};
   return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
       op, io, Layout{1, 1, n}, (cudaStream_t)stream);
 }

@@ -1,14 +1,20 @@
-// Streaming elementwise "map" kernel shared by every fake-quant / STE / mask op.
+// Streaming elementwise "map" kernels shared by every fake-quant / STE / mask op.
 //
-// One persistent grid (SMs x resident CTAs), each thread moves U vectors of V
-// floats per iteration: all loads are issued first (U x 32 B in flight per
-// thread), then the arithmetic, then the stores.  HBM-bound: 4 B read + 4 B
-// written per element and per stream, nothing is staged in shared memory
-// because no element is touched twice.
+// HBM-bound: 4 B read + 4 B written per element and per stream; nothing is staged
+// in shared memory because no element is touched twice.  Each thread moves U
+// vectors of V floats per step: all loads are issued first (U x 32 B in flight
+// per thread), then the arithmetic, then the stores.
 //
-// Per-channel parameters are derived on the fly from the raw device-side
-// parameter arrays (decimal / scale / lines / channel mask) — no parameter
-// prep launch; the arrays are tiny and L1/L2 resident.
+//   map_kernel       per-tensor parameters.  One CTA per tile (measured on B200:
+//                    6.18 TB/s vs 5.65 TB/s for a persistent grid, profiles/).
+//   map_chan_kernel  per-channel parameters ([outer, C, inner]).  Persistent grid;
+//                    every CTA first derives the per-channel constants (2^d,
+//                    reciprocals, clamp bounds, mask) into a shared-memory table,
+//                    then streams with 32-bit (column, channel) bookkeeping that
+//                    is advanced by constants — no division in the loop.
+//                    MODE 0: inner % V == 0, a vector never straddles two rows;
+//                    MODE 1: inner >= V, a vector touches at most two channels;
+//                    MODE 2: inner <  V, walk the channels element by element.
 #pragma once
 #include "qsb_common.cuh"
 
@@ -31,120 +37,218 @@ struct MapIO {
 //   __device__ void apply(float a, float b, uint8_t mb, const P&,
 //                         float &o0, float &o1, uint8_t &ob) const;
 
-template <class Op, int V, Hint LH, Hint SH>
-struct MapVec {
-  VecF<V> a, b;
-  VecB<V> m;
-  bool loaded;
+struct MapTuning {
+  int ctas_per_sm;   // per-tensor kernel: 0 = one CTA per tile (default); >0 persistent
+  int chan_ctas_per_sm;  // channel kernel: 0 = occupancy-derived persistent grid
 };
+MapTuning &map_tuning();
 
-template <class Op, int V, int U, bool CHAN, Hint LH, Hint SH>
+// ---------------------------------------------------------------------------
+// per-tensor
+// ---------------------------------------------------------------------------
+template <class Op, int V, int U, Hint LH, Hint SH>
 __global__ void __launch_bounds__(QSB_THREADS)
-    map_kernel(Op op, MapIO io, int64_t n, Layout L, ChanStep step_u,
-               ChanStep step_iter) {
+    map_kernel(Op op, MapIO io, int64_t n) {
   using P = typename Op::P;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
+  constexpr int64_t kStrideU = (int64_t)QSB_THREADS * V;
   const int64_t n_main = (n / V) * V;
-  const int64_t stride_u = (int64_t)QSB_THREADS * V;
+  const P p = op.params(0);
 
-  P p_tensor;
-  if constexpr (!CHAN) p_tensor = op.params(0);
-
-  int64_t e_base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * V;
-  ChanPos pos_base;
-  if constexpr (CHAN) pos_base = chan_pos_of(e_base < n ? e_base : 0, L);
-
-  for (; e_base < n_main; e_base += (int64_t)gridDim.x * kTile) {
+  for (int64_t e_base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * V;
+       e_base < n_main; e_base += (int64_t)gridDim.x * kTile) {
     VecF<V> a[U], b[U];
     VecB<V> mb[U];
-    P p0[U], p1[U];
-    bool mixed[U], skipv[U];
-    ChanPos pos = pos_base;
-    // ---- phase 1: parameters + loads -----------------------------------
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t e = e_base + u * stride_u;
-      mixed[u] = false;
-      skipv[u] = false;
-      if constexpr (CHAN) {
-        if (e < n_main) {
-          if (L.inner >= V) {
-            p0[u] = op.params(pos.c);
-            mixed[u] = (pos.col + V > L.inner);
-            if (mixed[u]) {
-              int32_t c1 = pos.c + 1;
-              if (c1 >= (int32_t)L.channels) c1 = 0;
-              p1[u] = op.params(c1);
-            } else {
-              p1[u] = p0[u];
-            }
-            if constexpr (Op::kCanSkip)
-              skipv[u] = op.skip(p0[u]) && op.skip(p1[u]);
-          }
-        }
-        advance(pos, step_u, L);
-      }
+      const int64_t e = e_base + u * kStrideU;
       if (e < n_main) {
-        if (!skipv[u]) a[u] = ld_vec<V, LH>(io.in0 + e);
+        a[u] = ld_vec<V, LH>(io.in0 + e);
         if constexpr (Op::kIn1) b[u] = ld_vec<V, LH>(io.in1 + e);
         if constexpr (Op::kInB) mb[u] = ld_bytes<V>(io.inb + e);
       }
     }
-    // ---- phase 2: arithmetic + stores ----------------------------------
-    pos = pos_base;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t e = e_base + u * stride_u;
+      const int64_t e = e_base + u * kStrideU;
       if (e < n_main) {
         VecF<V> o0, o1;
         VecB<V> ob;
-        if (CHAN && L.inner < V) {
-          // rows shorter than one vector: walk the channels element by element
-          ChanPos q = pos;
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          op.apply(a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
+                   Op::kInB ? mb[u].b[j] : (uint8_t)1, p, o0.v[j], o1.v[j],
+                   ob.b[j]);
+        if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
+        if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
+        if constexpr (Op::kOutB) st_bytes<V>(io.outb + e, ob);
+      }
+    }
+  }
+  // tail: the last n % V elements, scalar, by block 0
+  if (blockIdx.x == 0) {
+    const int64_t e = n_main + threadIdx.x;
+    if (e < n) {
+      float o0, o1;
+      uint8_t ob;
+      op.apply(io.in0[e], Op::kIn1 ? io.in1[e] : 0.f,
+               Op::kInB ? io.inb[e] : (uint8_t)1, p, o0, o1, ob);
+      if constexpr (Op::kOut0) io.out0[e] = o0;
+      if constexpr (Op::kOut1) io.out1[e] = o1;
+      if constexpr (Op::kOutB) io.outb[e] = ob;
+    }
+  }
+}
+
+template <class Op, int V, int U, Hint LH, Hint SH>
+int launch_map_tensor(const Op &op, const MapIO &io, int64_t n,
+                      cudaStream_t stream) {
+  auto kern = map_kernel<Op, V, U, LH, SH>;
+  constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  int64_t grid = tiles;
+  const int per_sm = map_tuning().ctas_per_sm;
+  if (per_sm > 0) {
+    grid = (int64_t)device_props().sm_count * per_sm;
+    if (grid > tiles) grid = tiles;
+  }
+  if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;  // the kernel loops
+  kern<<<(unsigned)grid, QSB_THREADS, 0, stream>>>(op, io, n);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// per-channel
+// ---------------------------------------------------------------------------
+struct ChanGeom {
+  uint32_t inner, channels;
+  uint32_t su_cols, su_ch;  // advance by one vector stride (QSB_THREADS * V)
+  uint32_t si_cols, si_ch;  // advance by one grid stride
+  int use_table;
+};
+
+__device__ __forceinline__ void advance32(uint32_t &col, uint32_t &c,
+                                          uint32_t dcol, uint32_t dch,
+                                          const ChanGeom &G) {
+  col += dcol;
+  c += dch;
+  if (col >= G.inner) {
+    col -= G.inner;
+    c += 1;
+  }
+  if (c >= G.channels) c -= G.channels;
+}
+
+template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
+__global__ void __launch_bounds__(QSB_THREADS)
+    map_chan_kernel(Op op, MapIO io, int64_t n, ChanGeom G) {
+  using P = typename Op::P;
+  extern __shared__ __align__(16) unsigned char qsb_smem_raw[];
+  P *tab = reinterpret_cast<P *>(qsb_smem_raw);
+  if (G.use_table) {
+    for (uint32_t c = threadIdx.x; c < G.channels; c += QSB_THREADS)
+      tab[c] = op.params((int32_t)c);
+    __syncthreads();
+  }
+  auto param_of = [&](uint32_t c) -> P {
+    return G.use_table ? tab[c] : op.params((int32_t)c);
+  };
+
+  constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
+  constexpr int64_t kStrideU = (int64_t)QSB_THREADS * V;
+  const int64_t n_main = (n / V) * V;
+
+  int64_t e_base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * V;
+  uint32_t col0, c0;
+  {
+    const int64_t eb = e_base < n ? e_base : 0;
+    const int64_t row = eb / G.inner;  // the only division: once per thread
+    col0 = (uint32_t)(eb - row * G.inner);
+    c0 = (uint32_t)(row % G.channels);
+  }
+
+  for (; e_base < n_main; e_base += (int64_t)gridDim.x * kTile) {
+    VecF<V> a[U], b[U];
+    VecB<V> mb[U];
+    uint32_t cu[U], colu[U];
+    bool skipv[U];
+    uint32_t col = col0, c = c0;
+    // ---- phase 1: positions, skip decision, loads ------------------------
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e_base + u * kStrideU;
+      cu[u] = c;
+      colu[u] = col;
+      skipv[u] = false;
+      if (e < n_main) {
+        if constexpr (Op::kCanSkip && MODE != 2) {
+          bool s = op.skip(param_of(c));
+          if (MODE == 1 && s && col + V > G.inner) {
+            const uint32_t c1 = (c + 1 >= G.channels) ? 0 : c + 1;
+            s = op.skip(param_of(c1));
+          }
+          skipv[u] = s;
+        }
+        if (!skipv[u]) a[u] = ld_vec<V, LH>(io.in0 + e);
+        if constexpr (Op::kIn1) b[u] = ld_vec<V, LH>(io.in1 + e);
+        if constexpr (Op::kInB) mb[u] = ld_bytes<V>(io.inb + e);
+      }
+      advance32(col, c, G.su_cols, G.su_ch, G);
+    }
+    // ---- phase 2: arithmetic + stores ------------------------------------
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e_base + u * kStrideU;
+      if (e < n_main) {
+        VecF<V> o0, o1;
+        VecB<V> ob;
+        if constexpr (MODE == 2) {
+          uint32_t qc = cu[u], qcol = colu[u];
 #pragma unroll
           for (int j = 0; j < V; ++j) {
-            P pj = op.params(q.c);
+            const P pj = param_of(qc);
             op.apply(a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
                      Op::kInB ? mb[u].b[j] : (uint8_t)1, pj, o0.v[j], o1.v[j],
                      ob.b[j]);
-            q.col += 1;
-            if (q.col >= L.inner) {
-              q.col = 0;
-              q.c += 1;
-              if (q.c >= (int32_t)L.channels) q.c = 0;
+            if (++qcol >= G.inner) {
+              qcol = 0;
+              if (++qc >= G.channels) qc = 0;
             }
           }
         } else {
-          const int64_t left = CHAN ? (L.inner - pos.col) : (int64_t)V;
+          const P p0 = param_of(cu[u]);
+          const uint32_t left = G.inner - colu[u];  // elements left in this row
+          if (MODE == 0 || left >= (uint32_t)V) {
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            const P &pj = CHAN ? ((mixed[u] && j >= left) ? p1[u] : p0[u])
-                               : p_tensor;
-            float av = a[u].v[j];
-            if (Op::kCanSkip && CHAN && skipv[u]) av = 0.f;
-            op.apply(av, Op::kIn1 ? b[u].v[j] : 0.f,
-                     Op::kInB ? mb[u].b[j] : (uint8_t)1, pj, o0.v[j], o1.v[j],
-                     ob.b[j]);
+            for (int j = 0; j < V; ++j)
+              op.apply(skipv[u] ? 0.f : a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
+                       Op::kInB ? mb[u].b[j] : (uint8_t)1, p0, o0.v[j], o1.v[j],
+                       ob.b[j]);
+          } else {
+            const uint32_t c1 = (cu[u] + 1 >= G.channels) ? 0 : cu[u] + 1;
+            const P p1 = param_of(c1);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              op.apply(skipv[u] ? 0.f : a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
+                       Op::kInB ? mb[u].b[j] : (uint8_t)1,
+                       ((uint32_t)j < left) ? p0 : p1, o0.v[j], o1.v[j], ob.b[j]);
           }
         }
         if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
         if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
         if constexpr (Op::kOutB) st_bytes<V>(io.outb + e, ob);
       }
-      if constexpr (CHAN) advance(pos, step_u, L);
     }
-    if constexpr (CHAN) advance(pos_base, step_iter, L);
+    advance32(col0, c0, G.si_cols, G.si_ch, G);
   }
 
-  // ---- tail: the last n % V elements, scalar, by block 0 -----------------
+  // tail: the last n % V elements, scalar, by block 0
   if (blockIdx.x == 0) {
     const int64_t e = n_main + threadIdx.x;
     if (e < n) {
-      P pj;
-      if constexpr (CHAN)
-        pj = op.params(chan_pos_of(e, L).c);
-      else
-        pj = p_tensor;
+      const int64_t row = e / G.inner;
+      const P pj = param_of((uint32_t)(row % G.channels));
       float o0, o1;
       uint8_t ob;
       op.apply(io.in0[e], Op::kIn1 ? io.in1[e] : 0.f,
@@ -156,44 +260,41 @@ __global__ void __launch_bounds__(QSB_THREADS)
   }
 }
 
-// Tuning knobs (benchmark use; defaults are what the product uses).
-struct MapTuning {
-  int ctas_per_sm;  // 0: occupancy-derived persistent grid; -1: one CTA per tile
-};
-MapTuning &map_tuning();
-
-template <class Op, int V, int U, bool CHAN, Hint LH, Hint SH>
-int launch_map_variant(const Op &op, const MapIO &io, int64_t n,
-                       const Layout &L, cudaStream_t stream) {
-  if (n <= 0) return 0;
-  auto kern = map_kernel<Op, V, U, CHAN, LH, SH>;
+template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
+int launch_map_chan_variant(const Op &op, const MapIO &io, int64_t n,
+                            const Layout &L, cudaStream_t stream) {
+  using P = typename Op::P;
+  auto kern = map_chan_kernel<Op, V, U, MODE, LH, SH>;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
-  static int occ = 0;  // per instantiation
-  if (occ == 0) {
-    int o = 0;
-    QSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern,
-                                                               QSB_THREADS, 0));
-    occ = o > 0 ? o : 1;
-  }
+  ChanGeom G;
+  G.inner = (uint32_t)L.inner;
+  G.channels = (uint32_t)L.channels;
+  const size_t tab_bytes = (size_t)L.channels * sizeof(P);
+  G.use_table = tab_bytes <= 48 * 1024;
+  const size_t smem = G.use_table ? tab_bytes : 0;
+  int occ = 0;
+  QSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern,
+                                                             QSB_THREADS, smem));
+  if (occ < 1) occ = 1;
+  const int per_sm = map_tuning().chan_ctas_per_sm;
   const int64_t tiles = (n + kTile - 1) / kTile;
-  int per_sm = map_tuning().ctas_per_sm;
-  int64_t grid;
-  if (per_sm < 0)
-    grid = tiles;
-  else
-    grid = (int64_t)device_props().sm_count * (per_sm > 0 ? per_sm : occ);
+  int64_t grid = (int64_t)device_props().sm_count * (per_sm > 0 ? per_sm : occ);
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
-  ChanStep su = make_chan_step((int64_t)QSB_THREADS * V, L);
-  ChanStep si = make_chan_step(grid * kTile, L);
-  kern<<<(unsigned)grid, QSB_THREADS, 0, stream>>>(op, io, n, L, su, si);
+  const int64_t su = (int64_t)QSB_THREADS * V, si = grid * kTile;
+  G.su_cols = (uint32_t)(su % L.inner);
+  G.su_ch = (uint32_t)((su / L.inner) % L.channels);
+  G.si_cols = (uint32_t)(si % L.inner);
+  G.si_ch = (uint32_t)((si / L.inner) % L.channels);
+  kern<<<(unsigned)grid, QSB_THREADS, smem, stream>>>(op, io, n, G);
   QSB_LAUNCH_CHECK();
   return 0;
 }
 
-// Picks the widest vector the pointers allow (32 B -> V=8, 16 B -> V=4, else
-// scalar) and per-tensor vs per-channel addressing.
-template <class Op, Hint LH = Hint::KEEP, Hint SH = Hint::STREAM>
+// Picks per-tensor vs per-channel addressing and the widest vector the pointers
+// allow (32 B -> V = 8; otherwise scalar for the channel kernel, 16 B -> V = 4
+// for the per-tensor kernel).
+template <class Op, Hint LH = Hint::STREAM, Hint SH = Hint::KEEP>
 int launch_map(const Op &op, const MapIO &io, const Layout &L,
                cudaStream_t stream) {
   const int64_t n = L.numel();
@@ -211,16 +312,18 @@ int launch_map(const Op &op, const MapIO &io, const Layout &L,
   if (Op::kInB) acc(io.inb, 4);
   if (Op::kOutB) acc(io.outb, 4);
   if (bits & 3) return QSB_E_ALIGN;
-  const bool chan = L.channels > 1;
-  if ((bits & 31) == 0) {
-    return chan ? launch_map_variant<Op, 8, 2, true, LH, SH>(op, io, n, L, stream)
-                : launch_map_variant<Op, 8, 2, false, LH, SH>(op, io, n, L, stream);
-  } else if ((bits & 15) == 0) {
-    return chan ? launch_map_variant<Op, 4, 4, true, LH, SH>(op, io, n, L, stream)
-                : launch_map_variant<Op, 4, 4, false, LH, SH>(op, io, n, L, stream);
+  if (L.channels <= 1) {
+    if ((bits & 31) == 0) return launch_map_tensor<Op, 8, 2, LH, SH>(op, io, n, stream);
+    if ((bits & 15) == 0) return launch_map_tensor<Op, 4, 4, LH, SH>(op, io, n, stream);
+    return launch_map_tensor<Op, 1, 4, LH, SH>(op, io, n, stream);
   }
-  return chan ? launch_map_variant<Op, 1, 4, true, LH, SH>(op, io, n, L, stream)
-              : launch_map_variant<Op, 1, 4, false, LH, SH>(op, io, n, L, stream);
+  if (L.inner >= (1LL << 31) || L.channels >= (1LL << 31)) return QSB_E_UNSUPPORTED;
+  if ((bits & 31) == 0) {
+    if (L.inner % 8 == 0) return launch_map_chan_variant<Op, 8, 2, 0, LH, SH>(op, io, n, L, stream);
+    if (L.inner >= 8) return launch_map_chan_variant<Op, 8, 2, 1, LH, SH>(op, io, n, L, stream);
+    return launch_map_chan_variant<Op, 8, 2, 2, LH, SH>(op, io, n, L, stream);
+  }
+  return launch_map_chan_variant<Op, 1, 4, 0, LH, SH>(op, io, n, L, stream);
 }
 
 }  // namespace qsb

@@ -103,15 +103,36 @@ constexpr int kFusedMaxChannels = 4096;
 __global__ void __launch_bounds__(1024)
     prune_quant_params_kernel(float *magnitude, uint8_t *mask, float *scale,
                               float *decimal_out, const double *abssum,
-                              const float *absmax, int channels, double count,
-                              int64_t t_prune, int update_magnitude,
-                              int refresh_mask, int64_t k, float limit,
-                              int64_t t_quant, int update_scale) {
+                              const float *absmax, int n_rows,
+                              int64_t row_stride_bytes, int channels,
+                              double count, int64_t t_prune,
+                              int update_magnitude, int refresh_mask, int64_t k,
+                              float limit, int64_t t_quant, int update_scale) {
   __shared__ float s_imp[kFusedMaxChannels];
   __shared__ uint32_t s_key[kFusedMaxChannels];
   __shared__ float s_thr;
   __shared__ uint32_t s_amax[32];
   const int tid = threadIdx.x;
+  // statistics may arrive as several rows (one per rank / per staged chunk), each
+  // row_stride_bytes apart; they are combined here in row order (fixed order ->
+  // every rank computes bit-identical parameters).
+  auto sum_of = [&](int c) {
+    double sacc = 0.0;
+    for (int r = 0; r < n_rows; ++r)
+      sacc += *reinterpret_cast<const double *>(
+          reinterpret_cast<const char *>(abssum + c) + (int64_t)r * row_stride_bytes);
+    return sacc;
+  };
+  auto max_bits_of = [&](int c) {
+    uint32_t mb = 0;
+    for (int r = 0; r < n_rows; ++r) {
+      const float v = *reinterpret_cast<const float *>(
+          reinterpret_cast<const char *>(absmax + c) + (int64_t)r * row_stride_bytes);
+      const uint32_t b = __float_as_uint(v) & 0x7fffffffu;
+      mb = b > mb ? b : mb;
+    }
+    return mb;
+  };
 
   // 1. importance: running-average magnitude (update_magnitude == 1), the
   //    existing magnitude (0), or this step's mean |x| itself (2:
@@ -119,11 +140,11 @@ __global__ void __launch_bounds__(1024)
   for (int c = tid; c < channels; c += blockDim.x) {
     float imp;
     if (update_magnitude == 2) {
-      imp = (float)(abssum[c] / count);
+      imp = (float)(sum_of(c) / count);
     } else {
       imp = magnitude[c];
       if (update_magnitude == 1) {
-        imp = magnitude_ema_step(imp, (float)(abssum[c] / count), t_prune);
+        imp = magnitude_ema_step(imp, (float)(sum_of(c) / count), t_prune);
         magnitude[c] = imp;
       }
     }
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(1024)
   if (update_scale) {
     for (int c = tid; c < channels; c += blockDim.x) {
       if (mask[c]) {
-        uint32_t b = __float_as_uint(absmax[c]) & 0x7fffffffu;
+        const uint32_t b = max_bits_of(c);
         am = b > am ? b : am;
       }
     }
@@ -261,6 +282,8 @@ extern "C" int qsb_magnitude_ema_reduced(float *magnitude, const double *abssum,
 extern "C" int qsb_prune_quant_params(float *magnitude, uint8_t *mask,
                                       float *scale, float *decimal_out,
                                       const double *abssum, const float *absmax,
+                                      int64_t n_stat_rows,
+                                      int64_t stat_row_stride_bytes,
                                       int64_t channels, double count,
                                       int64_t t_prune, int update_magnitude,
                                       int refresh_mask, int64_t k, int bits,
@@ -273,12 +296,14 @@ extern "C" int qsb_prune_quant_params(float *magnitude, uint8_t *mask,
   if (update_magnitude && (!abssum || !(count > 0))) return QSB_E_BADARG;
   if (update_scale && !absmax) return QSB_E_BADARG;
   if (refresh_mask && (k < 0 || k >= channels)) return QSB_E_BADARG;
+  if (n_stat_rows < 1 || n_stat_rows > 4096) return QSB_E_BADARG;
   const float limit = (float)pow(2.0, (double)bits - 1.0);
   int threads = 32;
   while (threads < channels && threads < 1024) threads <<= 1;
   prune_quant_params_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(
-      magnitude, mask, scale, decimal_out, abssum, absmax, (int)channels, count,
-      t_prune, update_magnitude, refresh_mask, k, limit, t_quant, update_scale);
+      magnitude, mask, scale, decimal_out, abssum, absmax, (int)n_stat_rows,
+      stat_row_stride_bytes, (int)channels, count, t_prune, update_magnitude,
+      refresh_mask, k, limit, t_quant, update_scale);
   QSB_LAUNCH_CHECK();
   return 0;
 }

@@ -189,6 +189,31 @@ __device__ __forceinline__ float clamp_torch(float v, float lo, float hi) {
   return (t > hi) ? hi : t;
 }
 
+// x / s, correctly rounded (== __fdiv_rn), for a divisor that is shared by many
+// elements: r = RN(1/s) is computed once per channel (__frcp_rn) and the quotient
+// is refined with two exact-residual FMA steps (Markstein: with a correctly
+// rounded reciprocal and a faithful quotient estimate, q + (x - s*q)*r rounds to
+// RN(x/s)).  No MUFU / FCHK per element.  The fast path is taken when no
+// intermediate can overflow or lose bits to underflow: s_ok <=> |s| in
+// [2^-40, 2^40] (checked once per channel), |x| in [2^-64, 2^64) or x == 0;
+// everything else goes through __fdiv_rn.  tests: qsb_selftest_fastdiv.
+__device__ __forceinline__ bool fastdiv_divisor_ok(float s) {
+  const uint32_t as = __float_as_uint(s) & 0x7fffffffu;
+  return (as - 0x2b800000u) < 0x28000000u;  // exponent field in [87, 167)
+}
+__device__ __forceinline__ float div_rn_by(float x, float s, float r, bool s_ok) {
+  const uint32_t ax = __float_as_uint(x) & 0x7fffffffu;
+  if (s_ok && (((ax - 0x1f800000u) < 0x40000000u) || ax == 0u)) {
+    const float q0 = __fmul_rn(x, r);
+    float e = __fmaf_rn(-s, q0, x);
+    float q = __fmaf_rn(e, r, q0);
+    e = __fmaf_rn(-s, q, x);
+    q = __fmaf_rn(e, r, q);
+    return ax == 0u ? q0 : q;  // keeps the sign of a zero quotient
+  }
+  return __fdiv_rn(x, s);
+}
+
 // order-preserving float -> uint32 key; every NaN maps to the largest key so
 // NaNs order last like torch.sort.
 __device__ __forceinline__ uint32_t float_to_key(float f) {

@@ -4,9 +4,13 @@
 // floating-point atomics).
 //
 // Stage 1 has two shapes:
-//   row mode    (inner >= 64): one warp per (row, segment) work item, 256-bit
-//                loads with a scalar head/tail peel for rows that do not start
-//                on a 32-byte boundary;
+//   row mode    (inner >= 64): work items are (row, segment) pieces; a "virtual
+//                warp" v owns items v, v + W, v + 2W, ... where W is a multiple of
+//                channels * segments_per_row, so all its items belong to ONE
+//                channel: it accumulates them in registers and writes a single
+//                partial at the end (W partials in total instead of one per item).
+//                256-bit loads, 4 in flight per lane, scalar head/tail peel for
+//                pieces that do not start on a 32-byte boundary;
 //   column mode (inner  < 64): the tensor is [outer, channels*inner]; one
 //                thread per column (or 4 columns) walks a chunk of rows, so a
 //                warp still reads contiguous 128/512-byte lines.
@@ -18,6 +22,7 @@
 namespace qsb {
 
 constexpr int kRowModeMinInner = 64;
+constexpr int kRowCtasPerSm = 4;  // matches __launch_bounds__ of reduce_rows_kernel
 
 struct Partials {
   uint32_t *amax;  // bits of max |x|  (NaN bit patterns order above inf)
@@ -82,52 +87,58 @@ __device__ __forceinline__ void warp_store(const Acc<WHAT> &a_in, int lane,
 // stage 1, row mode
 // ---------------------------------------------------------------------------
 template <int WHAT>
-__global__ void __launch_bounds__(QSB_THREADS)
+__global__ void __launch_bounds__(QSB_THREADS, 4)
     reduce_rows_kernel(const float *__restrict__ x, int64_t rows, int64_t inner,
-                       int64_t seg, int64_t segs_per_row, Partials P) {
+                       int64_t seg, int64_t segs_per_row, int64_t vwarps,
+                       Partials P) {
   const int lane = threadIdx.x & 31;
-  const int64_t warps_total = (int64_t)gridDim.x * (QSB_THREADS / 32);
+  const int64_t warps_phys = (int64_t)gridDim.x * (QSB_THREADS / 32);
   const int64_t items = rows * segs_per_row;
-  for (int64_t item = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
-       item < items; item += warps_total) {
-    const int64_t row = item / segs_per_row;
-    const int64_t s = item - row * segs_per_row;
-    const int64_t c0 = s * seg;
-    const int64_t c1 = (c0 + seg < inner) ? c0 + seg : inner;
-    const float *p = x + row * inner + c0;
-    const int64_t len = c1 - c0;
+  for (int64_t vw = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
+       vw < vwarps; vw += warps_phys) {
     Acc<WHAT> acc;
-    // head: scalars up to the first 32-byte boundary
-    int64_t head = ((32 - (reinterpret_cast<uintptr_t>(p) & 31)) & 31) >> 2;
-    if (head > len) head = len;
-    if (lane < head) acc.add(p[lane]);
-    const float *pv = p + head;
-    const int64_t nv = (len - head) >> 3;
-    // body: 256-bit loads, 4 in flight per lane
-    int64_t j = lane;
-    for (; j + 96 < nv; j += 128) {
-      VecF<8> v0 = ld_vec<8, Hint::KEEP>(pv + (j << 3));
-      VecF<8> v1 = ld_vec<8, Hint::KEEP>(pv + ((j + 32) << 3));
-      VecF<8> v2 = ld_vec<8, Hint::KEEP>(pv + ((j + 64) << 3));
-      VecF<8> v3 = ld_vec<8, Hint::KEEP>(pv + ((j + 96) << 3));
+    for (int64_t item = vw; item < items; item += vwarps) {
+      const int64_t row = item / segs_per_row;
+      const int64_t s = item - row * segs_per_row;
+      const int64_t c0 = s * seg;
+      const int64_t c1 = (c0 + seg < inner) ? c0 + seg : inner;
+      const float *p = x + row * inner + c0;
+      const int64_t len = c1 - c0;
+      // head: scalars up to the first 32-byte boundary
+      int64_t head = ((32 - (reinterpret_cast<uintptr_t>(p) & 31)) & 31) >> 2;
+      if (head > len) head = len;
+      if (lane < head) acc.add(p[lane]);
+      const float *pv = p + head;
+      const int64_t nv = (len - head) >> 3;
+      // body: 256-bit loads, up to 4 in flight per lane (predicated, so short
+      // pieces do not fall back to one load per round trip)
+      for (int64_t j = lane; j < nv; j += 128) {
+        const bool b1 = j + 32 < nv, b2 = j + 64 < nv, b3 = j + 96 < nv;
+        VecF<8> v0, v1, v2, v3;
+        v0 = ld_vec<8, Hint::KEEP>(pv + (j << 3));
+        if (b1) v1 = ld_vec<8, Hint::KEEP>(pv + ((j + 32) << 3));
+        if (b2) v2 = ld_vec<8, Hint::KEEP>(pv + ((j + 64) << 3));
+        if (b3) v3 = ld_vec<8, Hint::KEEP>(pv + ((j + 96) << 3));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc.add(v0.v[k]);
+        for (int k = 0; k < 8; ++k) acc.add(v0.v[k]);
+        if (b1) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc.add(v1.v[k]);
+          for (int k = 0; k < 8; ++k) acc.add(v1.v[k]);
+        }
+        if (b2) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc.add(v2.v[k]);
+          for (int k = 0; k < 8; ++k) acc.add(v2.v[k]);
+        }
+        if (b3) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc.add(v3.v[k]);
+          for (int k = 0; k < 8; ++k) acc.add(v3.v[k]);
+        }
+      }
+      // tail
+      const int64_t done = head + (nv << 3);
+      if (done + lane < len) acc.add(p[done + lane]);
     }
-    for (; j < nv; j += 32) {
-      VecF<8> v0 = ld_vec<8, Hint::KEEP>(pv + (j << 3));
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc.add(v0.v[k]);
-    }
-    // tail
-    const int64_t done = head + (nv << 3);
-    if (done + lane < len) acc.add(p[done + lane]);
-    warp_store<WHAT>(acc, lane, P, item);
+    warp_store<WHAT>(acc, lane, P, vw);
   }
 }
 
@@ -200,25 +211,59 @@ __global__ void __launch_bounds__(QSB_THREADS)
   bool nan = false;
   double asum = 0.0, nnz = 0.0;
   if (active) {
-    for (int64_t j = tg; j < count; j += G) {
+    auto index_of = [&](int64_t j) {
       const int64_t hi = j / q;
-      const int64_t idx = hi * (channels * q) + c * q + (j - hi * q);
+      return hi * (channels * q) + c * q + (j - hi * q);
+    };
+    for (int64_t j0 = tg; j0 < count; j0 += 4 * G) {
+      int64_t idx[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ok[u] = j0 + (int64_t)u * G < count;
+        idx[u] = ok[u] ? index_of(j0 + (int64_t)u * G) : 0;
+      }
       if constexpr (WHAT & QSB_STAT_ABSMAX) {
-        uint32_t b = P.amax[idx];
-        amax = b > amax ? b : amax;
+        uint32_t b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) b[u] = ok[u] ? P.amax[idx[u]] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) amax = b[u] > amax ? b[u] : amax;
       }
       if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
-        float v = P.mn[idx];
-        nan |= (v != v);
-        mn = fminf(mn, v);
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.mn[idx[u]] : INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          nan |= (v[u] != v[u]);
+          mn = fminf(mn, v[u]);
+        }
       }
       if constexpr (WHAT & QSB_STAT_MINMAX) {
-        float v = P.mx[idx];
-        nan |= (v != v);
-        mx = fmaxf(mx, v);
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.mx[idx[u]] : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          nan |= (v[u] != v[u]);
+          mx = fmaxf(mx, v[u]);
+        }
       }
-      if constexpr (WHAT & QSB_STAT_ABSSUM) asum += P.asum[idx];
-      if constexpr (WHAT & QSB_STAT_NNZ) nnz += P.nnz[idx];
+      if constexpr (WHAT & QSB_STAT_ABSSUM) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.asum[idx[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) asum += v[u];
+      }
+      if constexpr (WHAT & QSB_STAT_NNZ) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.nnz[idx[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nnz += v[u];
+      }
     }
   }
   // warp level
@@ -283,28 +328,57 @@ __global__ void tensor_min_kernel(const float *mn, int64_t channels, float *out)
 // ---------------------------------------------------------------------------
 struct ReducePlan {
   bool row_mode;
-  int64_t rows, seg, segs_per_row;     // row mode
+  int64_t rows, seg, segs_per_row, vwarps;       // row mode
   int64_t nrows, ncols, chunks, rows_per_chunk;  // column mode
   int vcol;
   int64_t n_partials, fin_count, fin_q;
 };
 
+// Physical warps of the row kernel: SMs x resident CTAs x 8.  The CTA count per
+// SM is fixed (not queried per instantiation) so that the plan — and with it the
+// summation order — only depends on the device, never on which statistics run.
 static ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
                             const float *x) {
   ReducePlan p{};
-  const int64_t target = (int64_t)device_props().sm_count * 64 * 2;
+  const int64_t warps_phys =
+      (int64_t)device_props().sm_count * kRowCtasPerSm * (QSB_THREADS / 32);
   if (inner >= kRowModeMinInner) {
     p.row_mode = true;
     p.rows = outer * channels;
-    int64_t seg = 8192;
-    auto items = [&](int64_t s) { return p.rows * ((inner + s - 1) / s); };
-    while (seg > 512 && items(seg) < target) seg >>= 1;
+    // balanced segments, >= 6 items per physical warp where the rows allow it,
+    // at least 512 elements per segment
+    int64_t spr = (6 * warps_phys + p.rows - 1) / p.rows;
+    const int64_t spr_max = inner / 512 > 0 ? inner / 512 : 1;
+    if (spr > spr_max) spr = spr_max;
+    if (spr < 1) spr = 1;
+    int64_t seg = (inner + spr - 1) / spr;
+    seg = (seg + 7) / 8 * 8;
+    spr = (inner + seg - 1) / seg;
     p.seg = seg;
-    p.segs_per_row = (inner + seg - 1) / seg;
-    p.n_partials = p.rows * p.segs_per_row;
-    p.fin_count = outer * p.segs_per_row;
-    p.fin_q = p.segs_per_row;
+    p.segs_per_row = spr;
+    const int64_t items = p.rows * spr;
+    const int64_t period = channels * spr;  // items with the same (channel, segment)
+    int64_t m;                              // virtual warps = m * period
+    if (channels == 1) {
+      // one channel: any assignment works; one virtual warp per physical warp
+      p.vwarps = items < warps_phys ? items : warps_phys;
+      p.fin_count = p.vwarps;
+      p.fin_q = 1;
+    } else {
+      const int64_t m_max = outer;
+      if (period * 4 <= warps_phys)
+        m = warps_phys / period;
+      else
+        m = (4 * warps_phys + period - 1) / period;
+      if (m > m_max) m = m_max;
+      if (m < 1) m = 1;
+      p.vwarps = m * period;
+      p.fin_count = m * spr;
+      p.fin_q = spr;
+    }
+    p.n_partials = p.vwarps;
   } else {
+    const int64_t target = warps_phys * 32;
     p.row_mode = false;
     p.nrows = outer;
     p.ncols = channels * inner;
@@ -337,19 +411,12 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
                       int64_t inner, const Partials &P, const FinalOut &out,
                       cudaStream_t stream) {
   if (pl.row_mode) {
-    static int occ = 0;
-    if (occ == 0) {
-      int o = 0;
-      QSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &o, reduce_rows_kernel<WHAT>, QSB_THREADS, 0));
-      occ = o > 0 ? o : 1;
-    }
     constexpr int kWarps = QSB_THREADS / 32;
-    int64_t grid = (int64_t)device_props().sm_count * occ;
-    const int64_t need = (pl.n_partials + kWarps - 1) / kWarps;
+    int64_t grid = (int64_t)device_props().sm_count * kRowCtasPerSm;
+    const int64_t need = (pl.vwarps + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
     reduce_rows_kernel<WHAT><<<(unsigned)grid, QSB_THREADS, 0, stream>>>(
-        x, pl.rows, inner, pl.seg, pl.segs_per_row, P);
+        x, pl.rows, inner, pl.seg, pl.segs_per_row, pl.vwarps, P);
   } else {
     const int64_t threads = pl.ncols / pl.vcol;
     dim3 grid((unsigned)((threads + QSB_THREADS - 1) / QSB_THREADS),
@@ -363,7 +430,7 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
   }
   QSB_LAUNCH_CHECK();
   // few channels: a whole CTA per channel; many: a warp per channel
-  if (channels <= 2048) {
+  if (pl.fin_count > 1024) {
     reduce_finalize_kernel<WHAT, QSB_THREADS>
         <<<(unsigned)channels, QSB_THREADS, 0, stream>>>(P, out, channels,
                                                          pl.fin_count, pl.fin_q);

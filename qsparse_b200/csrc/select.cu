@@ -74,15 +74,45 @@ __device__ void find_bin(const unsigned long long *hist, unsigned long long k,
   __syncthreads();
 }
 
-template <int PASS>
-__device__ __forceinline__ void count_key(uint32_t key, uint32_t prefix,
-                                          uint32_t *s_hist, int lane) {
-  if constexpr (PASS == 0) {
-    atomicAdd(&s_hist[(key >> 24) * 32 + lane], 1u);
-  } else if constexpr (PASS == 1) {
-    if ((key >> 24) == prefix) atomicAdd(&s_hist[(key >> 12) & 0xfffu], 1u);
+// The prefix tests run on the raw IEEE bits instead of the converted key: inside
+// one 8-bit key bucket every value has the same sign, so "top bits of the key ==
+// prefix" is "top bits of the raw word == a per-launch constant", and the next
+// digit is the raw field XOR a per-launch constant.  Only negative NaNs need a fix
+// up front (they must order last, like every NaN): they are remapped to 0x7fffffff.
+struct PassConst {
+  uint32_t raw_prefix;  // PASS 1: wanted raw bits >> 24; PASS 2: wanted raw bits >> 12
+  uint32_t flip;        // 0xfff for a negative bucket (key = ~bits), else 0
+};
+
+__device__ __forceinline__ PassConst make_pass_const(int pass, uint32_t key_prefix) {
+  PassConst pc;
+  if (pass == 1) {
+    const bool neg = (key_prefix & 0x80u) == 0;          // key top bit clear <=> negative
+    pc.raw_prefix = neg ? (key_prefix ^ 0xffu) : (key_prefix ^ 0x80u);
+    pc.flip = neg ? 0xfffu : 0u;
   } else {
-    if ((key >> 12) == prefix) atomicAdd(&s_hist[key & 0xfffu], 1u);
+    const bool neg = (key_prefix & 0x80000u) == 0;
+    pc.raw_prefix = neg ? (~key_prefix & 0xfffffu) : (key_prefix ^ 0x80000u);
+    pc.flip = neg ? 0xfffu : 0u;
+  }
+  return pc;
+}
+
+template <int PASS, bool ABS>
+__device__ __forceinline__ void count_value(float f, const PassConst &pc,
+                                            uint32_t *s_hist, int lane) {
+  uint32_t b = __float_as_uint(f);
+  if constexpr (ABS) b &= 0x7fffffffu;
+  else b = (b > 0xff800000u) ? 0x7fffffffu : b;
+  if constexpr (PASS == 0) {
+    const uint32_t t = b >> 24;
+    const uint32_t digit = ((int32_t)b < 0) ? (t ^ 0xffu) : (t | 0x80u);
+    atomicAdd(&s_hist[digit * 32 + lane], 1u);
+  } else if constexpr (PASS == 1) {
+    if ((b >> 24) == pc.raw_prefix)
+      atomicAdd(&s_hist[((b >> 12) & 0xfffu) ^ pc.flip], 1u);
+  } else {
+    if ((b >> 12) == pc.raw_prefix) atomicAdd(&s_hist[(b & 0xfffu) ^ pc.flip], 1u);
   }
 }
 
@@ -95,17 +125,18 @@ __global__ void __launch_bounds__(QSB_THREADS)
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < kSmemWords; i += QSB_THREADS) s_hist[i] = 0;
 
-  uint32_t prefix = 0;
+  PassConst pc{0, 0};
   if constexpr (PASS >= 1) {
     unsigned long long kk;
     uint32_t b0;
     find_bin<kBins0>(ws.hist0, (unsigned long long)k, &b0, &kk);
-    prefix = b0;
+    uint32_t prefix = b0;
     if constexpr (PASS == 2) {
       uint32_t b1;
       find_bin<kBins1>(ws.hist1, kk, &b1, &kk);
       prefix = (b0 << 12) | b1;
     }
+    pc = make_pass_const(PASS, prefix);
   }
   __syncthreads();
 
@@ -126,15 +157,13 @@ __global__ void __launch_bounds__(QSB_THREADS)
       if (e < n_main) {
 #pragma unroll
         for (int j = 0; j < V; ++j)
-          count_key<PASS>(float_to_key(ABS ? fabsf(x[u].v[j]) : x[u].v[j]), prefix,
-                          s_hist, lane);
+          count_value<PASS, ABS>(x[u].v[j], pc, s_hist, lane);
       }
     }
   }
   if (blockIdx.x == 0) {
     const int64_t e = n_main + tid;
-    if (e < n)
-      count_key<PASS>(float_to_key(ABS ? fabsf(v[e]) : v[e]), prefix, s_hist, lane);
+    if (e < n) count_value<PASS, ABS>(v[e], pc, s_hist, lane);
   }
   __syncthreads();
 

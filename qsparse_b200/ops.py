@@ -162,22 +162,24 @@ def mask_apply(x, mask, layout: Layout, out=None):
 
 
 # ----------------------------------------------------------------------------- K3
-def reduce_stats(x, layout: Layout, absmax=False, minmax=False, abssum=False, nnz=False):
-    """One read of x -> dict of per-channel statistics (device tensors)."""
+def reduce_stats(x, layout: Layout, absmax=False, minmax=False, abssum=False, nnz=False, out=None):
+    """One read of x -> dict of per-channel statistics (device tensors).  ``out`` may
+    supply pre-allocated result tensors (e.g. views into a statistics row that is
+    all-gathered afterwards)."""
     N.require_cuda(x, "input")
     lib = N.load_library()
     outer, ch, inner = layout
     what = (N.STAT_ABSMAX if absmax else 0) | (N.STAT_MINMAX if minmax else 0) | \
            (N.STAT_ABSSUM if (abssum or nnz) else 0) | (N.STAT_NNZ if nnz else 0)
     dev = x.device
-    res = {}
-    if absmax:
+    res = dict(out) if out else {}
+    if absmax and "absmax" not in res:
         res["absmax"] = torch.empty(ch, dtype=torch.float32, device=dev)
-    if minmax or nnz:
+    if (minmax or nnz) and "min" not in res:
         res["min"] = torch.empty(ch, dtype=torch.float32, device=dev)
-    if minmax:
+    if minmax and "max" not in res:
         res["max"] = torch.empty(ch, dtype=torch.float32, device=dev)
-    if abssum or nnz:
+    if (abssum or nnz) and "abssum" not in res:
         res["abssum"] = torch.empty(ch, dtype=torch.float64, device=dev)
     if nnz:
         res["nnz"] = torch.empty(ch, dtype=torch.float64, device=dev)
@@ -272,10 +274,13 @@ def mask_build_apply(importance, thr, x, mask_out, take_abs=False, out=None):
 
 def prune_quant_params(magnitude, mask, scale, decimal_out, stats: dict, count: float, t_prune: int,
                        update_magnitude: int, refresh_mask: bool, k: int, bits: int, t_quant: int,
-                       update_scale: bool):
+                       update_scale: bool, n_rows: int = 1, row_stride_bytes: int = 0):
+    """stats["abssum"] / stats["absmax"] point at row 0; further rows (ranks / chunks) follow
+    every row_stride_bytes and are combined inside the kernel in row order."""
     lib = N.load_library()
     N.check(lib.qsb_prune_quant_params(N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out),
                                        N.ptr(stats.get("abssum")), N.ptr(stats.get("absmax")),
+                                       c_int64(n_rows), c_int64(row_stride_bytes),
                                        c_int64(mask.numel()), c_double(count), c_int64(t_prune),
                                        c_int(update_magnitude), c_int(1 if refresh_mask else 0), c_int64(k),
                                        c_int(bits), c_int64(t_quant), c_int(1 if update_scale else 0),

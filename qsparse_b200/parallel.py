@@ -1,0 +1,73 @@
+"""Multi-GPU plumbing of the quantize/prune path.
+
+The path shards along the batch: every GPU reduces, applies and back-propagates its own
+activation shard; the only exchange is the tiny per-channel statistics row
+``[C x fp64 sum|x|  |  C x fp32 max|x|]`` (768 B for 64 channels).  One
+``all_gather`` moves the rows; the parameter kernel then combines them in rank order
+(SUM / MAX), so every rank derives bit-identical magnitudes, masks and scales — equal
+to a single process running on the concatenated batch (MAX exactly; SUM to the
+last fp64 bit of a fixed-order sum).  The bulk tensors never cross NVLink.
+
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the transport.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def stat_row_bytes(channels: int) -> int:
+    """bytes of one rank's statistics row, padded to 256 B"""
+    return (channels * 12 + 255) // 256 * 256
+
+
+class StatRow:
+    """A rank-local statistics row plus typed views into it.  The reduction kernel
+    writes its results straight into these views (no packing launch)."""
+
+    def __init__(self, channels: int, device):
+        self.channels = channels
+        self.nbytes = stat_row_bytes(channels)
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.abssum = self.buf[: 8 * channels].view(torch.float64)
+        self.absmax = self.buf[8 * channels: 12 * channels].view(torch.float32)
+
+
+class StatExchange:
+    """all-gather of statistics rows over a process group (None = default group).
+
+    ``gather(row)`` returns ``(rows_buffer, n_rows, row_stride_bytes)``; with a single
+    process it is the row itself and no collective runs."""
+
+    def __init__(self, channels: int, device, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.row = StatRow(channels, device)
+        self.gathered = (torch.zeros(self.world * self.row.nbytes, dtype=torch.uint8, device=device)
+                         if self.world > 1 else self.row.buf)
+
+    def gather(self) -> Tuple[torch.Tensor, int, int]:
+        if self.world == 1:
+            return self.row.buf, 1, self.row.nbytes
+        dist.all_gather_into_tensor(self.gathered, self.row.buf, group=self.group)
+        return self.gathered, self.world, self.row.nbytes
+
+    def views(self, buf: torch.Tensor):
+        """(abssum row 0, absmax row 0) views of a gathered buffer, as the kernel wants them"""
+        c = self.row.channels
+        return buf[: 8 * c].view(torch.float64), buf[8 * c: 12 * c].view(torch.float32)
+
+
+def combine_rows_host(gathered: torch.Tensor, n_rows: int, row_bytes: int, channels: int):
+    """Host restatement of how the parameter kernel combines rows (rank order: SUM of the
+    fp64 sums, MAX of the maxima).  Used by the CPU (gloo) tests of the exchange."""
+    total = torch.zeros(channels, dtype=torch.float64)
+    amax = torch.zeros(channels, dtype=torch.float32)
+    g = gathered.cpu()
+    for r in range(n_rows):
+        row = g[r * row_bytes: (r + 1) * row_bytes]
+        total = total + row[: 8 * channels].view(torch.float64)
+        amax = torch.maximum(amax, row[8 * channels: 12 * channels].view(torch.float32).abs())
+    return total, amax

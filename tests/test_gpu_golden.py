@@ -23,10 +23,12 @@ def npy(t):
 
 @pytest.fixture(scope="module")
 def q():
+    import importlib
     import qsparse_b200
-    import qsparse_b200.quantize as Q
     qsparse_b200.set_qsparse_options(log_on_created=False)
-    return Q
+    # `qsparse_b200.quantize` the attribute is the quantize() function (as in the
+    # reference's __init__), so fetch the submodule explicitly
+    return importlib.import_module("qsparse_b200.quantize")
 
 
 def test_pow2_forward(golden, q):

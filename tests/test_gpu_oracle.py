@@ -295,4 +295,34 @@ def test_full_size_select_64M():
         ref = torch.sort(imp).values[k]
         assert thr.item() == ref.item()
         m = calculate_mask_given_importance(imp, s)
-        assert int((~m).sum().item()) == k            # distinct values: exactly k pruned
+        assert torch.equal(m, imp >= ref)             # ties with the threshold are kept
+        assert int((~m).sum().item()) <= k
+
+
+def test_fast_division_is_exact():
+    """The reciprocal-based division used by the scaler / line / EMA kernels must equal
+    IEEE division bit for bit (2^31 operand pairs incl. rounding-boundary neighbours)."""
+    from ctypes import c_int64, c_uint64
+    from qsparse_b200 import _native as N
+    lib = N.load_library()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed in (1, 2, 3, 4):
+        N.check(lib.qsb_selftest_fastdiv(c_int64(1 << 19), c_int64(1 << 10), c_uint64(seed), N.ptr(bad),
+                                         N.stream_ptr(bad.device)), "selftest")
+    assert bad.item() == 0
+
+
+def test_scaler_line_dense_rounding_boundaries():
+    """x placed on and next to every (k + 0.5) * s boundary: division + rint must agree with the oracle."""
+    from qsparse_b200.quantize import quantize_with_scaler, quantize_with_line
+    rng = np.random.default_rng(77)
+    for s in (0.1, 0.037, 0.0123456, 1.7):
+        k = np.arange(-300, 300, dtype=np.float32) + 0.5
+        x = (k * np.float32(s)).astype(np.float32)
+        xs = np.concatenate([x, np.nextafter(x, np.float32(10)), np.nextafter(x, np.float32(-10)),
+                             rng.standard_normal(4096).astype(np.float32)])
+        assert bits_equal(npy(quantize_with_scaler(cu(xs), 8, s)), orc.fq_scaler_fwd(xs, np.float32(s)))
+        lines = np.array([[-3 * s, 250 * s]], np.float32)
+        for fzp in (True, False):
+            assert bits_equal(npy(quantize_with_line(cu(xs), 8, (float(lines[0, 0]), float(lines[0, 1])), -1, False, fzp)),
+                              orc.fq_line_fwd(xs, lines, 8, -1, fzp))
