@@ -122,7 +122,9 @@ struct LineOp {
   const uint8_t *cmask;
   struct P {
     float lo, hi, step, rstep, qstart, m;
-    bool ok;
+    bool ok;         // step is in the fast-division range
+    bool nan_bound;  // torch.clamp with a NaN bound returns NaN
+    bool magic;      // |quotient| < 2^22 guaranteed: rint via the 1.5*2^23 trick
   };
   __device__ __forceinline__ P params(int32_t c) const {
     P p;
@@ -141,6 +143,14 @@ struct LineOp {
     p.rstep = __frcp_rn(p.step);
     p.ok = fastdiv_divisor_ok(p.step);
     p.qstart = FZP ? 0.0f : rintf(__fdiv_rn(p.lo, p.step));  // (:163)
+    p.nan_bound = (p.lo != p.lo) || (p.hi != p.hi);
+    // after the clamp |x| <= max(|lo|, |hi|): when that bound / step (and the float
+    // zero-point form's (hi - lo) / step) stays below 2^22, (q + 1.5*2^23) - 1.5*2^23
+    // is exactly rint(q) (round half to even) — two FADDs instead of an XU-pipe FRND
+    {
+      const float span = FZP ? fabsf(__fsub_rn(p.hi, p.lo)) : fmaxf(fabsf(p.lo), fabsf(p.hi));
+      p.magic = (span * fabsf(p.rstep)) < 2097152.0f;  // 2^21: a 2x margin
+    }
     p.m = 1.0f;
     if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
     return p;
@@ -151,13 +161,18 @@ struct LineOp {
     float t = a;
     if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
     if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
-    const float xc = clamp_torch_tensor(t, p.lo, p.hi);  // (:158)
+    const float xc = p.nan_bound ? __uint_as_float(0x7fc00000u)
+                                 : clamp_torch(t, p.lo, p.hi);  // (:158)
+    auto round_even = [&](float v) {
+      const float kMagic = 12582912.0f;  // 1.5 * 2^23
+      return p.magic ? __fsub_rn(__fadd_rn(v, kMagic), kMagic) : rintf(v);
+    };
     if constexpr (FZP) {
       float q = div_rn_by(__fsub_rn(xc, p.lo), p.step, p.rstep, p.ok);  // (:176-177)
-      q = clamp_torch(rintf(q), 0.0f, q_max);                // (:178)
+      q = clamp_torch(round_even(q), 0.0f, q_max);           // (:178)
       o0 = __fadd_rn(__fmul_rn(q, p.step), p.lo);            // (:179-180)
     } else {
-      float q = rintf(div_rn_by(xc, p.step, p.rstep, p.ok));          // (:162)
+      float q = round_even(div_rn_by(xc, p.step, p.rstep, p.ok));     // (:162)
       q = clamp_torch(__fsub_rn(q, p.qstart), 0.0f, q_max);           // (:164)
       o0 = __fmul_rn(__fadd_rn(q, p.qstart), p.step);                 // (:165)
     }

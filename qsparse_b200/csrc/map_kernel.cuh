@@ -7,14 +7,21 @@
 //
 //   map_kernel       per-tensor parameters.  One CTA per tile (measured on B200:
 //                    6.18 TB/s vs 5.65 TB/s for a persistent grid, profiles/).
-//   map_chan_kernel  per-channel parameters ([outer, C, inner]).  Persistent grid;
-//                    every CTA first derives the per-channel constants (2^d,
-//                    reciprocals, clamp bounds, mask) into a shared-memory table,
-//                    then streams with 32-bit (column, channel) bookkeeping that
-//                    is advanced by constants — no division in the loop.
+//   map_chan_win_kernel  per-channel parameters ([outer, C, inner]), inner >= V.
+//                    One CTA per tile, like the per-tensor kernel (persistent
+//                    grids run their warps in lock-step load/compute phases and
+//                    measured 4-9 % slower, profiles/).  The CTA derives the
+//                    per-channel constants (2^d, reciprocals, clamp bounds, mask)
+//                    only for the rows its tile touches — a "window" table of
+//                    tile/inner + 2 entries in shared memory, independent of C —
+//                    then every vector needs one 32-bit division to find its row.
 //                    MODE 0: inner % V == 0, a vector never straddles two rows;
-//                    MODE 1: inner >= V, a vector touches at most two channels;
-//                    MODE 2: inner <  V, walk the channels element by element.
+//                    MODE 1: a vector touches at most two channels.
+//   map_chan_kernel  rows shorter than a vector (inner < V, MODE 2: walk the
+//                    channels element by element) and unaligned pointers.
+//                    Persistent grid, full per-channel table in shared memory
+//                    when it fits, 32-bit (column, channel) bookkeeping advanced
+//                    by constants — no division in the loop.
 #pragma once
 #include "qsb_common.cuh"
 
@@ -260,6 +267,111 @@ __global__ void __launch_bounds__(QSB_THREADS)
   }
 }
 
+// ---------------------------------------------------------------------------
+// per-channel, one CTA per tile, window table (inner >= V)
+// ---------------------------------------------------------------------------
+template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
+__global__ void __launch_bounds__(QSB_THREADS)
+    map_chan_win_kernel(Op op, MapIO io, int64_t n, uint32_t inner,
+                        uint32_t channels) {
+  using P = typename Op::P;
+  static_assert(MODE == 0 || MODE == 1, "window kernel needs inner >= V");
+  extern __shared__ __align__(16) unsigned char qsb_smem_raw[];
+  P *tab = reinterpret_cast<P *>(qsb_smem_raw);
+  constexpr uint32_t kTile = QSB_THREADS * V * U;
+  constexpr uint32_t kStrideU = QSB_THREADS * V;
+  const int64_t n_main = (n / V) * V;
+  const int64_t t0 = (int64_t)blockIdx.x * kTile;
+  // first row / column / channel of the tile (uniform across the CTA)
+  const int64_t row0 = t0 / inner;
+  const uint32_t col0 = (uint32_t)(t0 - row0 * inner);
+  const uint32_t c0 = (uint32_t)(row0 % channels);
+  const uint32_t rows = (col0 + kTile - 1) / inner + 1;
+  for (uint32_t k = threadIdx.x; k < rows; k += QSB_THREADS)
+    tab[k] = op.params((int32_t)((c0 + k) % channels));
+  __syncthreads();
+
+  VecF<V> a[U], b[U];
+  VecB<V> mb[U];
+  uint32_t ru[U], leftu[U];
+  bool skipv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t o = threadIdx.x * V + u * kStrideU;
+    const int64_t e = t0 + o;
+    const uint32_t pos = col0 + o;
+    ru[u] = pos / inner;
+    leftu[u] = inner - (pos - ru[u] * inner);  // elements left in this row
+    skipv[u] = false;
+    if (e < n_main) {
+      if constexpr (Op::kCanSkip) {
+        bool s = op.skip(tab[ru[u]]);
+        if (MODE == 1 && s && leftu[u] < (uint32_t)V) s = op.skip(tab[ru[u] + 1]);
+        skipv[u] = s;
+      }
+      if (!skipv[u]) a[u] = ld_vec<V, LH>(io.in0 + e);
+      if constexpr (Op::kIn1) b[u] = ld_vec<V, LH>(io.in1 + e);
+      if constexpr (Op::kInB) mb[u] = ld_bytes<V>(io.inb + e);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t e = t0 + threadIdx.x * V + u * kStrideU;
+    if (e < n_main) {
+      VecF<V> o0, o1;
+      VecB<V> ob;
+      const P p0 = tab[ru[u]];
+      if (MODE == 0 || leftu[u] >= (uint32_t)V) {
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          op.apply(skipv[u] ? 0.f : a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
+                   Op::kInB ? mb[u].b[j] : (uint8_t)1, p0, o0.v[j], o1.v[j],
+                   ob.b[j]);
+      } else {
+        const P p1 = tab[ru[u] + 1];
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          op.apply(skipv[u] ? 0.f : a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
+                   Op::kInB ? mb[u].b[j] : (uint8_t)1,
+                   ((uint32_t)j < leftu[u]) ? p0 : p1, o0.v[j], o1.v[j], ob.b[j]);
+      }
+      if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
+      if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
+      if constexpr (Op::kOutB) st_bytes<V>(io.outb + e, ob);
+    }
+  }
+  // tail: the last n % V elements, scalar, by the CTA that owns them
+  if (t0 <= n_main && n_main < t0 + kTile) {
+    const int64_t e = n_main + threadIdx.x;
+    if (e < n) {
+      const P pj = tab[(uint32_t)((col0 + (uint32_t)(e - t0)) / inner)];
+      float o0, o1;
+      uint8_t ob;
+      op.apply(io.in0[e], Op::kIn1 ? io.in1[e] : 0.f,
+               Op::kInB ? io.inb[e] : (uint8_t)1, pj, o0, o1, ob);
+      if constexpr (Op::kOut0) io.out0[e] = o0;
+      if constexpr (Op::kOut1) io.out1[e] = o1;
+      if constexpr (Op::kOutB) io.outb[e] = ob;
+    }
+  }
+}
+
+template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
+int launch_map_chan_win(const Op &op, const MapIO &io, int64_t n,
+                        const Layout &L, cudaStream_t stream) {
+  using P = typename Op::P;
+  auto kern = map_chan_win_kernel<Op, V, U, MODE, LH, SH>;
+  constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  const size_t rows_max = (size_t)((L.inner - 1 + kTile - 1) / L.inner + 2);
+  const size_t smem = rows_max * sizeof(P);
+  if (tiles > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
+  kern<<<(unsigned)tiles, QSB_THREADS, smem, stream>>>(op, io, n, (uint32_t)L.inner,
+                                                       (uint32_t)L.channels);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
 int launch_map_chan_variant(const Op &op, const MapIO &io, int64_t n,
                             const Layout &L, cudaStream_t stream) {
@@ -279,8 +391,10 @@ int launch_map_chan_variant(const Op &op, const MapIO &io, int64_t n,
   const int per_sm = map_tuning().chan_ctas_per_sm;
   const int64_t tiles = (n + kTile - 1) / kTile;
   int64_t grid = (int64_t)device_props().sm_count * (per_sm > 0 ? per_sm : occ);
+  if (per_sm < 0) grid = tiles;  // one CTA per tile
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
+  if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
   const int64_t su = (int64_t)QSB_THREADS * V, si = grid * kTile;
   G.su_cols = (uint32_t)(su % L.inner);
   G.su_ch = (uint32_t)((su / L.inner) % L.channels);
@@ -319,8 +433,13 @@ int launch_map(const Op &op, const MapIO &io, const Layout &L,
   }
   if (L.inner >= (1LL << 31) || L.channels >= (1LL << 31)) return QSB_E_UNSUPPORTED;
   if ((bits & 31) == 0) {
-    if (L.inner % 8 == 0) return launch_map_chan_variant<Op, 8, 2, 0, LH, SH>(op, io, n, L, stream);
-    if (L.inner >= 8) return launch_map_chan_variant<Op, 8, 2, 1, LH, SH>(op, io, n, L, stream);
+    if (map_tuning().chan_ctas_per_sm == 0) {
+      if (L.inner % 8 == 0) return launch_map_chan_win<Op, 8, 2, 0, LH, SH>(op, io, n, L, stream);
+      if (L.inner >= 8) return launch_map_chan_win<Op, 8, 2, 1, LH, SH>(op, io, n, L, stream);
+    } else {  // benchmark knob: the persistent full-table kernel for every shape
+      if (L.inner % 8 == 0) return launch_map_chan_variant<Op, 8, 2, 0, LH, SH>(op, io, n, L, stream);
+      if (L.inner >= 8) return launch_map_chan_variant<Op, 8, 2, 1, LH, SH>(op, io, n, L, stream);
+    }
     return launch_map_chan_variant<Op, 8, 2, 2, LH, SH>(op, io, n, L, stream);
   }
   return launch_map_chan_variant<Op, 1, 4, 0, LH, SH>(op, io, n, L, stream);

@@ -15,6 +15,14 @@
 //                thread per column (or 4 columns) walks a chunk of rows, so a
 //                warp still reads contiguous 128/512-byte lines.
 // Stage 2 (finalize) combines the partials of each channel in a fixed order.
+//
+// sum|x|: the 8 values of one 256-bit vector are first added pairwise in fp32
+// (3 levels, |x| >= 0 so there is no cancellation), the vector sum is then
+// accumulated in fp64.  That keeps the fp32->fp64 conversions (XU pipe, quarter
+// rate) at one per 8 elements; accumulating every element in fp64 left the kernel
+// XU-bound at 47 % pipe utilisation (profiles/).  The result is within ~1e-7
+// relative of the exact sum — an order of magnitude closer than the reference's
+// own fp32 cascade sums.
 #include <math.h>
 
 #include "qsb_common.cuh"
@@ -51,6 +59,34 @@ struct Acc {
     if constexpr (WHAT & QSB_STAT_MINMAX) mx = fmaxf(mx, v);
     if constexpr (WHAT & QSB_STAT_ABSSUM) asum += (double)fabsf(v);
     if constexpr (WHAT & QSB_STAT_NNZ) nnz += (v != 0.0f) ? 1u : 0u;
+  }
+  // N values at once (N = 8: one vector; N = 4: four rows of one column)
+  template <int N>
+  __device__ __forceinline__ void add_n(const float *v) {
+    if constexpr (WHAT & QSB_STAT_ABSSUM) {
+      float t[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) t[k] = fabsf(v[k]);
+#pragma unroll
+      for (int w = N / 2; w >= 1; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) t[k] = __fadd_rn(t[k], t[k + w]);
+      asum += (double)t[0];
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float x = v[k];
+      if constexpr (WHAT & QSB_STAT_ABSMAX) {
+        uint32_t b = __float_as_uint(x) & 0x7fffffffu;
+        amax = b > amax ? b : amax;
+      }
+      if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+        mn = fminf(mn, x);
+        nan |= (x != x);
+      }
+      if constexpr (WHAT & QSB_STAT_MINMAX) mx = fmaxf(mx, x);
+      if constexpr (WHAT & QSB_STAT_NNZ) nnz += (x != 0.0f) ? 1u : 0u;
+    }
   }
 };
 
@@ -119,20 +155,10 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
         if (b1) v1 = ld_vec<8, Hint::KEEP>(pv + ((j + 32) << 3));
         if (b2) v2 = ld_vec<8, Hint::KEEP>(pv + ((j + 64) << 3));
         if (b3) v3 = ld_vec<8, Hint::KEEP>(pv + ((j + 96) << 3));
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc.add(v0.v[k]);
-        if (b1) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc.add(v1.v[k]);
-        }
-        if (b2) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc.add(v2.v[k]);
-        }
-        if (b3) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc.add(v3.v[k]);
-        }
+        acc.template add_n<8>(v0.v);
+        if (b1) acc.template add_n<8>(v1.v);
+        if (b2) acc.template add_n<8>(v2.v);
+        if (b3) acc.template add_n<8>(v3.v);
       }
       // tail
       const int64_t done = head + (nv << 3);
@@ -163,9 +189,10 @@ __global__ void __launch_bounds__(QSB_THREADS)
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = ld_vec<V, Hint::KEEP>(p + (r + k) * ncols);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int q = 0; q < V; ++q) acc[q].add(v[k].v[q]);
+    for (int q = 0; q < V; ++q) {
+      const float col4[4] = {v[0].v[q], v[1].v[q], v[2].v[q], v[3].v[q]};
+      acc[q].template add_n<4>(col4);
+    }
   }
   for (; r < r1; ++r) {
     VecF<V> v = ld_vec<V, Hint::KEEP>(p + r * ncols);
