@@ -303,6 +303,17 @@ def run_ours(args):
     for _ in range(2):
         e2e_step()
     barrier()
+    # the PCIe link this box gives us (context for the e2e number): one pinned 205 MB copy each way
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ev0.record()
+    y.copy_(hx, non_blocking=True)
+    ev1.record()
+    hy.copy_(y, non_blocking=True)
+    ev2.record()
+    torch.cuda.synchronize()
+    pcie_h2d = n * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    pcie_d2h = n * 4 / (ev1.elapsed_time(ev2) * 1e-3) / 1e9
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -367,6 +378,8 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4 * world,
                 "d2h_bytes_per_step": 2 * n * 4 * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
                 "api": "qsb_host_prune_quant_step (C-ABI, pinned host buffers, 8 chunks, 3 streams)",
+                "pcie_h2d_gbs": round(pcie_h2d, 1), "pcie_d2h_gbs": round(pcie_d2h, 1),
+                "bound": "PCIe: upload(x) -> [download(y) || upload(g)] -> download(gx) = 3 x 205.5 MB serial",
                 "matches_resident_path": same},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "map_chan_kernel<SteOp<CHANNEL,gx>> (fused STE backward, dense 8 B/elem)",

@@ -33,7 +33,8 @@ template <int MASK>
 struct Pow2Op {
   static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
                         kOut0 = true, kOut1 = false, kOutB = false,
-                        kCanSkip = (MASK == QSB_MASK_CHANNEL);
+                        kCanSkip = (MASK == QSB_MASK_CHANNEL),
+                        kHasFast = false;
   const float *dec;  // device decimals or nullptr
   int dec_stride;    // 0: one decimal for the tensor, 1: per channel
   float toi_host, tof_host;
@@ -75,7 +76,8 @@ template <int MASK>
 struct ScalerOp {
   static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
                         kOut0 = true, kOut1 = false, kOutB = false,
-                        kCanSkip = (MASK == QSB_MASK_CHANNEL);
+                        kCanSkip = (MASK == QSB_MASK_CHANNEL),
+                        kHasFast = true;
   const float *scale;
   int scale_stride;
   float scale_host;
@@ -101,7 +103,24 @@ struct ScalerOp {
     if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
     // (x / s).round().int() : IEEE divide, then round-half-even + cast in one
     // cvt.rni.s32.f32 (== trunc(rint(v)) including the saturating edge cases)
-    const int q = __float2int_rn(div_rn_by(t, p.s, p.r, p.ok));
+    const int q = __float2int_rn(__fdiv_rn(t, p.s));
+    o0 = __fmul_rn(__int2float_rn(q), p.s);
+  }
+  // fast path: the scale is in the reciprocal-division range and every |x| of the
+  // vector is below 2^64 (NaNs pass the max and end as q = 0 on both paths)
+  template <int V>
+  __device__ __forceinline__ bool fast(const P &p, const float *a) const {
+    float m = fabsf(a[0]);
+#pragma unroll
+    for (int j = 1; j < V; ++j) m = fmaxf(m, fabsf(a[j]));
+    return p.ok && m < 1.8446744e19f;
+  }
+  __device__ __forceinline__ void apply_fast(float a, float, uint8_t mb, const P &p,
+                                             float &o0, float &, uint8_t &) const {
+    float t = a;
+    if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
+    if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
+    const int q = __float2int_rn(div_rn_by_unchecked(t, p.s, p.r));
     o0 = __fmul_rn(__int2float_rn(q), p.s);
   }
 };
@@ -113,7 +132,8 @@ template <int MASK, bool FZP>
 struct LineOp {
   static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
                         kOut0 = true, kOut1 = false, kOutB = false,
-                        kCanSkip = false;  // output depends on lo even for x = 0
+                        kCanSkip = false,  // output depends on lo even for x = 0
+                        kHasFast = true;
   const float *lines;  // [n][2] or nullptr
   int lines_stride;    // 0 or 1 (in rows)
   float lo_host, hi_host;
@@ -122,9 +142,10 @@ struct LineOp {
   const uint8_t *cmask;
   struct P {
     float lo, hi, step, rstep, qstart, m;
-    bool ok;         // step is in the fast-division range
-    bool nan_bound;  // torch.clamp with a NaN bound returns NaN
-    bool magic;      // |quotient| < 2^22 guaranteed: rint via the 1.5*2^23 trick
+    // fast: step is in the fast-division range, the bounds are finite, every
+    // quotient is below 2^21 in magnitude -> unchecked reciprocal division and
+    // rint via the 1.5*2^23 trick; otherwise the generic IEEE path.
+    bool fast;
   };
   __device__ __forceinline__ P params(int32_t c) const {
     P p;
@@ -141,15 +162,16 @@ struct LineOp {
     p.step = __fdiv_rn(__fsub_rn(p.hi, p.lo), n_levels);
     if (p.step == 0.0f) p.step = 0.0001f;
     p.rstep = __frcp_rn(p.step);
-    p.ok = fastdiv_divisor_ok(p.step);
     p.qstart = FZP ? 0.0f : rintf(__fdiv_rn(p.lo, p.step));  // (:163)
-    p.nan_bound = (p.lo != p.lo) || (p.hi != p.hi);
-    // after the clamp |x| <= max(|lo|, |hi|): when that bound / step (and the float
-    // zero-point form's (hi - lo) / step) stays below 2^22, (q + 1.5*2^23) - 1.5*2^23
-    // is exactly rint(q) (round half to even) — two FADDs instead of an XU-pipe FRND
+    // after the clamp |x| <= max(|lo|, |hi|) (and x - lo in [0, hi - lo]): when that
+    // bound / step stays below 2^21, every quotient is in the range where the
+    // reciprocal division needs no guard and (q + 1.5*2^23) - 1.5*2^23 == rint(q)
+    // (round half to even) — two FADDs instead of an XU-pipe FRND.  NaN / inf
+    // bounds fail the comparison and take the generic path.
     {
       const float span = FZP ? fabsf(__fsub_rn(p.hi, p.lo)) : fmaxf(fabsf(p.lo), fabsf(p.hi));
-      p.magic = (span * fabsf(p.rstep)) < 2097152.0f;  // 2^21: a 2x margin
+      p.fast = fastdiv_divisor_ok(p.step) && (__fmul_rn(span, fabsf(p.rstep)) < 2097152.0f) &&
+               (fabsf(p.lo) < 1.8446744e19f) && (fabsf(p.hi) < 1.8446744e19f);
     }
     p.m = 1.0f;
     if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
@@ -161,20 +183,38 @@ struct LineOp {
     float t = a;
     if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
     if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
-    const float xc = p.nan_bound ? __uint_as_float(0x7fc00000u)
-                                 : clamp_torch(t, p.lo, p.hi);  // (:158)
-    auto round_even = [&](float v) {
-      const float kMagic = 12582912.0f;  // 1.5 * 2^23
-      return p.magic ? __fsub_rn(__fadd_rn(v, kMagic), kMagic) : rintf(v);
-    };
+    const float xc = clamp_torch_tensor(t, p.lo, p.hi);  // (:158)
     if constexpr (FZP) {
-      float q = div_rn_by(__fsub_rn(xc, p.lo), p.step, p.rstep, p.ok);  // (:176-177)
-      q = clamp_torch(round_even(q), 0.0f, q_max);           // (:178)
+      float q = __fdiv_rn(__fsub_rn(xc, p.lo), p.step);      // (:176-177)
+      q = clamp_torch(rintf(q), 0.0f, q_max);                // (:178)
       o0 = __fadd_rn(__fmul_rn(q, p.step), p.lo);            // (:179-180)
     } else {
-      float q = round_even(div_rn_by(xc, p.step, p.rstep, p.ok));     // (:162)
+      float q = rintf(__fdiv_rn(xc, p.step));                         // (:162)
       q = clamp_torch(__fsub_rn(q, p.qstart), 0.0f, q_max);           // (:164)
       o0 = __fmul_rn(__fadd_rn(q, p.qstart), p.step);                 // (:165)
+    }
+  }
+  template <int V>
+  __device__ __forceinline__ bool fast(const P &p, const float *) const {
+    return p.fast;
+  }
+  __device__ __forceinline__ void apply_fast(float a, float, uint8_t mb, const P &p,
+                                             float &o0, float &, uint8_t &) const {
+    float t = a;
+    if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
+    if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
+    const float kMagic = 12582912.0f;             // 1.5 * 2^23
+    const float xc = clamp_torch(t, p.lo, p.hi);  // (:158) bounds are finite here
+    if constexpr (FZP) {
+      float q = div_rn_by_unchecked(__fsub_rn(xc, p.lo), p.step, p.rstep);  // (:176-177)
+      q = __fsub_rn(__fadd_rn(q, kMagic), kMagic);                            // round_ (:178)
+      q = clamp_torch(q, 0.0f, q_max);
+      o0 = __fadd_rn(__fmul_rn(q, p.step), p.lo);                             // (:179-180)
+    } else {
+      float q = div_rn_by_unchecked(xc, p.step, p.rstep);
+      q = __fsub_rn(__fadd_rn(q, kMagic), kMagic);                            // (:162)
+      q = clamp_torch(__fsub_rn(q, p.qstart), 0.0f, q_max);                   // (:164)
+      o0 = __fmul_rn(__fadd_rn(q, p.qstart), p.step);                         // (:165)
     }
   }
 };
@@ -186,7 +226,8 @@ template <int MASK, bool WRITE_GC, bool WRITE_GX>
 struct SteOp {
   static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
                         kOut0 = WRITE_GC, kOut1 = WRITE_GX, kOutB = false,
-                        kCanSkip = false;  // v * 0 keeps the sign of v
+                        kCanSkip = false,
+                        kHasFast = false;  // v * 0 keeps the sign of v
   const float *scale;
   int scale_stride;
   float scale_host;  // already 2^-d when the host decimal is used
@@ -231,7 +272,8 @@ template <int MASK>
 struct MaskApplyOp {
   static constexpr bool kIn1 = false, kInB = (MASK == QSB_MASK_ELEMENT),
                         kOut0 = true, kOut1 = false, kOutB = false,
-                        kCanSkip = false;  // x * 0 keeps the sign of x
+                        kCanSkip = false,
+                        kHasFast = false;  // x * 0 keeps the sign of x
   const uint8_t *cmask;
   struct P {
     float m;
@@ -257,7 +299,8 @@ struct MaskApplyOp {
 template <bool APPLY>
 struct MaskBuildOp {
   static constexpr bool kIn1 = APPLY, kInB = false, kOut0 = APPLY,
-                        kOut1 = false, kOutB = true, kCanSkip = false;
+                        kOut1 = false, kOutB = true, kCanSkip = false,
+                        kHasFast = false;
   const float *thr;
   bool take_abs;
   struct P {
@@ -282,7 +325,8 @@ struct MaskBuildOp {
 //   mag = (t * mag + |x|) / (t + 1)
 struct EmaFullOp {
   static constexpr bool kIn1 = true, kInB = false, kOut0 = true, kOut1 = false,
-                        kOutB = false, kCanSkip = false;
+                        kOutB = false, kCanSkip = false,
+                        kHasFast = false;
   const float *tensor_min;  // device scalar, only read when use_l0
   bool use_l0;
   float t_f, t_plus_1_f, r_t_plus_1;  // r = RN(1 / (t + 1)), host computed

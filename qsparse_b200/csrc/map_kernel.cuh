@@ -38,11 +38,35 @@ struct MapIO {
 
 // Op requirements:
 //   struct P;                                  per-channel derived constants
-//   static constexpr bool kIn1, kInB, kOut0, kOut1, kOutB, kCanSkip;
+//   static constexpr bool kIn1, kInB, kOut0, kOut1, kOutB, kCanSkip, kHasFast;
 //   __device__ P params(int32_t c) const;
 //   __device__ bool skip(const P&) const;      (kCanSkip) output independent of in0
 //   __device__ void apply(float a, float b, uint8_t mb, const P&,
 //                         float &o0, float &o1, uint8_t &ob) const;
+
+// One vector of V elements that all use the same per-channel constants.  Ops with
+// a cheaper arithmetic path that is only valid on part of the input domain expose
+// it as apply_fast() and decide ONCE per vector (fast()), so the generic IEEE path
+// is not inlined behind a branch for every element.
+template <class Op, int V>
+__device__ __forceinline__ void apply_vec(const Op &op, const VecF<V> &a,
+                                          const VecF<V> &b, const VecB<V> &mb,
+                                          bool skip, const typename Op::P &p,
+                                          VecF<V> &o0, VecF<V> &o1, VecB<V> &ob) {
+  if constexpr (Op::kHasFast) {
+    if (op.template fast<V>(p, a.v)) {
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        op.apply_fast(skip ? 0.f : a.v[j], Op::kIn1 ? b.v[j] : 0.f,
+                      Op::kInB ? mb.b[j] : (uint8_t)1, p, o0.v[j], o1.v[j], ob.b[j]);
+      return;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j)
+    op.apply(skip ? 0.f : a.v[j], Op::kIn1 ? b.v[j] : 0.f,
+             Op::kInB ? mb.b[j] : (uint8_t)1, p, o0.v[j], o1.v[j], ob.b[j]);
+}
 
 struct MapTuning {
   int ctas_per_sm;   // per-tensor kernel: 0 = one CTA per tile (default); >0 persistent
@@ -81,11 +105,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
       if (e < n_main) {
         VecF<V> o0, o1;
         VecB<V> ob;
-#pragma unroll
-        for (int j = 0; j < V; ++j)
-          op.apply(a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
-                   Op::kInB ? mb[u].b[j] : (uint8_t)1, p, o0.v[j], o1.v[j],
-                   ob.b[j]);
+        apply_vec<Op, V>(op, a[u], b[u], mb[u], false, p, o0, o1, ob);
         if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
         if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
         if constexpr (Op::kOutB) st_bytes<V>(io.outb + e, ob);
@@ -227,11 +247,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
           const P p0 = param_of(cu[u]);
           const uint32_t left = G.inner - colu[u];  // elements left in this row
           if (MODE == 0 || left >= (uint32_t)V) {
-#pragma unroll
-            for (int j = 0; j < V; ++j)
-              op.apply(skipv[u] ? 0.f : a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
-                       Op::kInB ? mb[u].b[j] : (uint8_t)1, p0, o0.v[j], o1.v[j],
-                       ob.b[j]);
+            apply_vec<Op, V>(op, a[u], b[u], mb[u], skipv[u], p0, o0, o1, ob);
           } else {
             const uint32_t c1 = (cu[u] + 1 >= G.channels) ? 0 : cu[u] + 1;
             const P p1 = param_of(c1);
@@ -322,11 +338,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
       VecB<V> ob;
       const P p0 = tab[ru[u]];
       if (MODE == 0 || leftu[u] >= (uint32_t)V) {
-#pragma unroll
-        for (int j = 0; j < V; ++j)
-          op.apply(skipv[u] ? 0.f : a[u].v[j], Op::kIn1 ? b[u].v[j] : 0.f,
-                   Op::kInB ? mb[u].b[j] : (uint8_t)1, p0, o0.v[j], o1.v[j],
-                   ob.b[j]);
+        apply_vec<Op, V>(op, a[u], b[u], mb[u], skipv[u], p0, o0, o1, ob);
       } else {
         const P p1 = tab[ru[u] + 1];
 #pragma unroll

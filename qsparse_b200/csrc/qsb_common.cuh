@@ -214,6 +214,25 @@ __device__ __forceinline__ float div_rn_by(float x, float s, float r, bool s_ok)
   return __fdiv_rn(x, s);
 }
 
+// The same refinement without any range check: the caller guarantees s_ok and
+// |x| < 2^64.  Tiny x needs no guard when the quotient only feeds a rounding to
+// integer: a residual that underflows leaves q ~ q0, |q| << 0.5, which rounds to 0
+// exactly like the true quotient.
+__device__ __forceinline__ float div_rn_by_unchecked(float x, float s, float r) {
+  const float q0 = __fmul_rn(x, r);
+  float e = __fmaf_rn(-s, q0, x);
+  float q = __fmaf_rn(e, r, q0);
+  e = __fmaf_rn(-s, q, x);
+  q = __fmaf_rn(e, r, q);
+  return (x == 0.0f) ? q0 : q;
+}
+// For quotients that are rounded to an integer next: one upper-bound compare.
+__device__ __forceinline__ float div_rn_by_q(float x, float s, float r, bool s_ok) {
+  if (s_ok && fabsf(x) < 1.8446744e19f)  // 2^64; false for NaN / inf
+    return div_rn_by_unchecked(x, s, r);
+  return __fdiv_rn(x, s);
+}
+
 // order-preserving float -> uint32 key; every NaN maps to the largest key so
 // NaNs order last like torch.sort.
 __device__ __forceinline__ uint32_t float_to_key(float f) {

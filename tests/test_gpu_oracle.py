@@ -110,7 +110,8 @@ def test_reductions_vs_oracle(shape, ci):
         assert np.array_equal(npy(st["min"]), mn) and np.array_equal(npy(st["max"]), mx)
         o, c, i = orc.layout(shape, layout_ci)
         xr = np.abs(x.astype(np.float64)).reshape(o, c, i)
-        assert np.allclose(npy(st["abssum"]), xr.sum(axis=(0, 2)), rtol=1e-12, atol=0)
+        # 8-element fp32 pre-sums, then fp64: ~1e-7 relative of the exact sum (reduce.cu header)
+        assert np.allclose(npy(st["abssum"]), xr.sum(axis=(0, 2)), rtol=3e-7, atol=0)
         assert np.array_equal(npy(st["nnz"]), (xr != 0).sum(axis=(0, 2)).astype(np.float64))
         assert npy(st["tensor_min"])[0] == x.min()
     # each single-statistic instantiation
@@ -280,7 +281,9 @@ def test_full_size_properties_config2():
     st = ops.reduce_stats(x, layout, abssum=True, absmax=True)
     assert torch.equal(st["absmax"], x.abs().amax(dim=(0, 2, 3)))
     ref = x.double().abs().sum(dim=(0, 2, 3))
-    assert torch.allclose(st["abssum"], ref, rtol=1e-12, atol=0)
+    assert torch.allclose(st["abssum"], ref, rtol=3e-7, atol=0)
+    again = ops.reduce_stats(x, layout, abssum=True, absmax=True)
+    assert torch.equal(again["abssum"], st["abssum"])        # deterministic: fixed summation order
 
 
 def test_full_size_select_64M():
