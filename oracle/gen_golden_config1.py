@@ -64,6 +64,7 @@ def run(qs, callback_factory, device="cpu", record=None):
     model.train()
     opt = torch.optim.Adadelta(model.parameters(), lr=1.0)
     losses, sparsities = [], []
+    trace = {"mag0": [], "mask0": [], "mag1": [], "mask1": [], "qw": []}
     with contextlib.redirect_stdout(io.StringIO()):
         for step in range(STEPS):
             x, y = data(step)
@@ -73,9 +74,21 @@ def run(qs, callback_factory, device="cpu", record=None):
             loss.backward()
             opt.step()
             losses.append(loss.item())
+            players = from_layers(model, "PruneLayer")
             sparsities.append([float((~m.mask).float().mean().item()) if m.mask.dim() > 0 else 0.0
-                               for _, m in from_layers(model, "PruneLayer")])
+                               for _, m in players])
+            for i, (_, m) in enumerate(players):
+                has = hasattr(m.callback, "magnitude")
+                trace[f"mag{i}"].append(m.callback.magnitude.detach().cpu().numpy().reshape(-1).copy() if has
+                                        else np.zeros(m.mask.numel() if m.mask.dim() else 1, np.float32))
+                trace[f"mask{i}"].append(m.mask.detach().cpu().numpy().reshape(-1).copy() if m.mask.dim()
+                                         else np.ones(1, bool))
+            trace["qw"].append(np.array([m.weight.detach().cpu().numpy().reshape(-1)[0] if hasattr(m, "weight")
+                                         else 0.0 for _, m in from_layers(model, "QuantizeLayer")], np.float32))
     out = {"loss": np.array(losses, np.float64), "sparsity": np.array(sparsities, np.float64)}
+    for k, v in trace.items():
+        n = max(len(a) for a in v)
+        out["trace_" + k] = np.stack([np.resize(a, n) if len(a) != n else a for a in v])
     for i, (n, m) in enumerate(from_layers(model, "PruneLayer")):
         out[f"prune{i}_mask"] = m.mask.detach().cpu().numpy()
         out[f"prune{i}_magnitude"] = m.callback.magnitude.detach().cpu().numpy()

@@ -150,3 +150,20 @@ def test_prune_ramp(golden):
         assert cur == ref[step], step
     # docs/tutorial.ipynb:224-228 : 0.29 / 0.44 / 0.49 / 0.50
     assert [round(ref[s], 2) for s in (200, 210, 220, 230)] == [0.29, 0.44, 0.49, 0.5]
+
+
+def test_oracle_layer_emulators_match_reference_layers(golden):
+    """tests/oracle_layers.py (host control flow of QuantizeLayer / PruneLayer over the oracle) against the
+    reference's recorded layer flows — pins the emulators used for the teacher-forced end-to-end GPU test."""
+    from tests.oracle_layers import OraclePrune, OracleQuantize
+    g = golden
+    x = g["layer/x"]
+    for kind, key in (("decimal", "layer/q_dec"), ("scaler", "layer/q_scl")):
+        em = OracleQuantize(8, 3, kind)
+        outs = np.stack([em.forward(x) for _ in range(6)])
+        assert bits_equal(outs, g[key + "_out"]) and bits_equal(em.weight, g[key + "_weight"].reshape(-1))
+    em = OraclePrune(0.5, 2, 2, 3)
+    for t in range(12):
+        out = em.forward(g["layer/px"])
+        assert bits_equal(out, g["layer/p_out"][t]), t
+        assert np.array_equal(em.mask, g["layer/p_mask"][t]), t
