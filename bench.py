@@ -39,7 +39,7 @@ METRIC = "quantize+prune fwd/bwd HBM GB/s"
 CONFIG = {
     "workload": "config[1]: [256,64,56,56] fp32, 8-bit pow2 fake-quant fwd/bwd + 75% structured channel prune "
                 "(fused training step: reduce 4 + apply 8 + backward 8 = 20 B/elem)",
-    "shape_per_gpu": list(SHAPE), "bits": BITS, "sparsity": SPARSITY, "parallelism": "batch-sharded, stats all-gather",
+    "shape_per_gpu": list(SHAPE), "bits": BITS, "sparsity": SPARSITY, "parallelism": "batch-sharded; 768-byte statistics row exchanged over peer memory inside the parameter kernel",
     "l2": "inputs (2 x 205.5 MB per step) exceed the 126 MB L2; no flush",
 }
 
@@ -183,7 +183,7 @@ def run_ours(args):
 
     from qsparse_b200 import _native as N
     from qsparse_b200 import ops
-    from qsparse_b200.parallel import StatExchange
+    from qsparse_b200.parallel import StatExchange, make_exchange
     from qsparse_b200.util import kth_rank
     from ctypes import byref, c_double, c_int, c_int64, c_void_p
 
@@ -209,7 +209,8 @@ def run_ours(args):
     mask = torch.ones(C, dtype=torch.bool, device=dev)
     scale = torch.zeros(1, device=dev)
     dec = torch.zeros(1, device=dev)
-    ex = StatExchange(C, dev)
+    p2p = make_exchange(C, dev)                      # peer-memory exchange fused into the parameter kernel
+    ex = StatExchange(C, dev) if (world > 1 and p2p is None) else None   # NCCL all-gather fallback
     k = kth_rank(SPARSITY, C)
     state = {"t": 0}
     stream = N.stream_ptr(dev)
@@ -224,12 +225,19 @@ def run_ours(args):
 
     def step(i=None):
         t = state["t"]
-        ops.reduce_stats(x, LAYOUT, abssum=True, absmax=True, out={"abssum": ex.row.abssum, "absmax": ex.row.absmax})
-        rows, n_rows, stride = ex.gather()
-        a0, m0 = ex.views(rows)
-        ops.prune_quant_params(mag, mask, scale, dec, {"abssum": a0, "absmax": m0},
-                               float(LAYOUT[0] * LAYOUT[2] * n_rows), t, 1, t > 0, k, BITS, t, True,
-                               n_rows=n_rows, row_stride_bytes=stride)
+        if ex is None:
+            ws = ops.reduce_partials(x, LAYOUT)
+            ops.prune_quant_step_params(mag, mask, scale, dec, ws, LAYOUT, float(LAYOUT[0] * LAYOUT[2] * world), t, 1,
+                                        t > 0, k, BITS, t, True, group=p2p.handle if p2p else None,
+                                        step_stamp=p2p.next_stamp() if p2p else 1)
+        else:
+            ops.reduce_stats(x, LAYOUT, abssum=True, absmax=True,
+                             out={"abssum": ex.row.abssum, "absmax": ex.row.absmax})
+            rows, n_rows, stride = ex.gather()
+            a0, m0 = ex.views(rows)
+            ops.prune_quant_params(mag, mask, scale, dec, {"abssum": a0, "absmax": m0},
+                                   float(LAYOUT[0] * LAYOUT[2] * n_rows), t, 1, t > 0, k, BITS, t, True,
+                                   n_rows=n_rows, row_stride_bytes=stride)
         ops.fq_pow2_fwd(x, dec, LAYOUT, mask=mask, out=y)
         if i is not None:
             ev_b0[i].record()
@@ -276,7 +284,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * n * BYTES_PER_ELEM / (ms_per_step * 1e-3) / 1e9
-    launches_per_step = 5      # reduce stage 1 + finalize, parameters, forward apply, backward
+    # reduce stage 1, fused finalize+exchange+parameters, forward apply, backward  (+ finalize on the NCCL path)
+    launches_per_step = 4 if ex is None else 5
 
     # ---- e2e: host buffers through the C-ABI (copies inside the timed region) ----
     e2e_steps = max(3, min(args.steps, 10))
@@ -375,6 +384,9 @@ def run_ours(args):
         "elems_per_s": round(world * n / (ms_per_step * 1e-3), 1),
         "frac_of_measured_hbm_peak": round(value / world / peak, 4),
         "clocks": clocks,
+        "exchange": ("none (1 GPU)" if world == 1 else ("peer-memory (CUDA IPC over NVLink), fused into the parameter kernel"
+                                                         if p2p else "NCCL all_gather_into_tensor")),
+        "exchange_error": (p2p.error() if p2p else 0),
         "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4 * world,
                 "d2h_bytes_per_step": 2 * n * 4 * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
                 "api": "qsb_host_prune_quant_step (C-ABI, pinned host buffers, 8 chunks, 3 streams)",

@@ -230,6 +230,52 @@ int qsb_prune_quant_params(float *magnitude, uint8_t *mask, float *scale,
                            int64_t t_quant, int update_scale, void *stream);
 
 /* ------------------------------------------------------------------------
+ * The same parameter step as ONE kernel that also finalizes the reduction and,
+ * across GPUs, exchanges the statistics row over peer memory (NVLink) — the
+ * fused compute + collective form of the training step:
+ *   qsb_reduce_partials(x)           stage 1 only, partials stay in the workspace
+ *   qsb_prune_quant_step_params(...) finalize -> push my [C x fp64 sum | C x max]
+ *       row into every peer's exchange buffer + stamp -> wait for all stamps ->
+ *       combine in rank order -> EMA / threshold / mask / scale / decimal
+ *   qsb_fq_pow2_fwd(mask), qsb_ste_bwd(mask)
+ * group == NULL: single GPU.  step_stamp must be > 0, equal on all ranks and
+ * increase by one per step (two slots are used alternately).  `count` is the
+ * number of elements per channel over ALL ranks.  abssum_out / absmax_out
+ * (optional, both or neither) receive the combined statistics.
+ * Requires channels <= 2048 and the same (outer, channels, inner) that was
+ * passed to qsb_reduce_partials.
+ * ---------------------------------------------------------------------- */
+int qsb_reduce_partials(const float *x, int64_t outer, int64_t channels,
+                        int64_t inner, void *workspace, int64_t workspace_bytes,
+                        void *stream);
+
+typedef struct qsb_p2p_group qsb_p2p_group;
+/* exchange-buffer size for `world` ranks (<= 16) and `channels` channels */
+int64_t qsb_p2p_group_bytes(int world, int64_t channels);
+/* cudaMalloc'ed, zeroed buffer + its 64-byte CUDA IPC handle (send it to the peers) */
+int qsb_p2p_alloc(int64_t bytes, void **dev_ptr, unsigned char *handle64);
+int qsb_p2p_open(const unsigned char *handle64, void **peer_ptr);
+int qsb_p2p_close(void *peer_ptr);
+int qsb_p2p_free(void *dev_ptr);
+/* bufs[r] = rank r's exchange buffer as mapped in THIS process (bufs[rank] local) */
+int qsb_p2p_group_create(qsb_p2p_group **out, int rank, int world,
+                         int64_t channels, void *const *bufs);
+/* *error_out != 0 if a peer's stamp did not arrive within 4 s (synchronises) */
+int qsb_p2p_group_error(qsb_p2p_group *group, int *error_out);
+int qsb_p2p_group_destroy(qsb_p2p_group *group);
+
+int qsb_prune_quant_step_params(float *magnitude, uint8_t *mask, float *scale,
+                                float *decimal_out, void *reduce_workspace,
+                                int64_t workspace_bytes, int64_t outer,
+                                int64_t channels, int64_t inner,
+                                qsb_p2p_group *group, int64_t step_stamp,
+                                double count, int64_t t_prune,
+                                int update_magnitude, int refresh_mask,
+                                int64_t k, int bits, int64_t t_quant,
+                                int update_scale, double *abssum_out,
+                                float *absmax_out, void *stream);
+
+/* ------------------------------------------------------------------------
  * Host-buffer entry points (what a host-side caller that keeps its tensors in
  * CPU memory binds to).  They stage through pinned memory owned by a context,
  * pipeline H2D / kernels / D2H over chunks on several streams, and return after

@@ -46,6 +46,18 @@ _SIGNATURES = {
     "qsb_mask_build_apply": (c_int, [_P, c_int, _P, _P, _P, _P, c_int64, _P]),
     "qsb_prune_quant_params": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_double, c_int64, c_int,
                                        c_int, c_int64, c_int, c_int64, c_int, _P]),
+    "qsb_reduce_partials": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, _P]),
+    "qsb_p2p_group_bytes": (c_int64, [c_int, c_int64]),
+    "qsb_p2p_alloc": (c_int, [c_int64, ctypes.POINTER(c_void_p), ctypes.c_char_p]),
+    "qsb_p2p_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "qsb_p2p_close": (c_int, [_P]),
+    "qsb_p2p_free": (c_int, [_P]),
+    "qsb_p2p_group_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int64, ctypes.POINTER(c_void_p)]),
+    "qsb_p2p_group_error": (c_int, [_P, ctypes.POINTER(c_int)]),
+    "qsb_p2p_group_destroy": (c_int, [_P]),
+    "qsb_prune_quant_step_params": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64,
+                                            c_double, c_int64, c_int, c_int, c_int64, c_int, c_int64, c_int, _P, _P,
+                                            _P]),
     "qsb_host_ctx_create": (c_int, [ctypes.POINTER(c_void_p), c_int64, c_int64, c_int]),
     "qsb_host_ctx_destroy": (c_int, [_P]),
     "qsb_host_prune_quant_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,

@@ -10,7 +10,9 @@
 
 #include <mutex>
 
+#include "p2p_internal.cuh"
 #include "qsb_common.cuh"
+#include "reduce_internal.cuh"
 
 namespace qsb {
 
@@ -197,6 +199,168 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// ONE kernel between "stage-1 partials are written" and "apply":
+//   finalize the reduction  ->  exchange the statistics row with every peer GPU
+//   over NVLink (peer stores + stamp, no NCCL launch)  ->  combine in rank order
+//   ->  magnitude EMA, k-th threshold, mask, abs-max of kept, scale EMA, decimal.
+// One CTA of 1024 threads.
+// ---------------------------------------------------------------------------
+constexpr int kStepMaxChannels = 2048;
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(1024)
+    prune_quant_step_kernel(float *magnitude, uint8_t *mask, float *scale,
+                            float *decimal_out, Partials P, int64_t fin_count,
+                            int64_t fin_q, int channels, P2PDev px,
+                            unsigned long long stamp, double count,
+                            int64_t t_prune, int update_magnitude,
+                            int refresh_mask, int64_t k, float limit,
+                            int64_t t_quant, int update_scale,
+                            double *abssum_out, float *absmax_out) {
+  __shared__ double s_sum[kStepMaxChannels];
+  __shared__ uint32_t s_max[kStepMaxChannels];
+  __shared__ float s_imp[kStepMaxChannels];
+  __shared__ uint32_t s_key[kStepMaxChannels];
+  __shared__ float s_thr;
+  __shared__ uint32_t s_amax[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+
+  // ---- 1. finalize this GPU's partials: a warp per channel, fixed order --------
+  for (int c = warp; c < channels; c += nwarps) {
+    double sum = 0.0;
+    uint32_t mx = 0;
+    for (int64_t j = lane; j < fin_count; j += 32) {
+      const int64_t hi = j / fin_q;
+      const int64_t idx = hi * ((int64_t)channels * fin_q) + (int64_t)c * fin_q + (j - hi * fin_q);
+      sum += P.asum[idx];
+      const uint32_t b = P.amax[idx];
+      mx = b > mx ? b : mx;
+    }
+    sum = warp_reduce(sum, [](double a, double b) { return a + b; });
+    mx = warp_reduce(mx, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
+    if (lane == 0) {
+      s_sum[c] = sum;
+      s_max[c] = mx;
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. exchange with the peers (weak scaling over the batch) ----------------
+  if (px.world > 1) {
+    const int parity = (int)(stamp & 1ull);
+    // push my row into slot [parity][rank] of EVERY rank's buffer (mine included)
+    for (int i = tid; i < channels * px.world; i += blockDim.x) {
+      const int r = i / channels, c = i - r * channels;
+      unsigned char *slot = px.bufs[r] + p2p_slot_offset(px, parity, px.rank);
+      reinterpret_cast<double *>(slot)[c] = s_sum[c];
+      reinterpret_cast<uint32_t *>(slot + (int64_t)channels * 8)[c] = s_max[c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < px.world) {
+      st_flag(reinterpret_cast<unsigned long long *>(px.bufs[tid] +
+                                                    p2p_flag_offset(px, parity, px.rank)),
+              stamp);
+      // wait for rank `tid`'s stamp in MY buffer (bounded: never hang the GPU)
+      const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(
+          px.bufs[px.rank] + p2p_flag_offset(px, parity, tid));
+      const unsigned long long t0 = global_ns();
+      while (ld_flag(flag) != stamp) {
+        __nanosleep(200);
+        if (global_ns() - t0 > 4000000000ull) {  // 4 s
+          *px.error = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    // combine in rank order (SUM of sums, MAX of maxima): identical on every rank
+    for (int c = tid; c < channels; c += blockDim.x) {
+      double sum = 0.0;
+      uint32_t mx = 0;
+      for (int r = 0; r < px.world; ++r) {
+        const unsigned char *slot = px.bufs[px.rank] + p2p_slot_offset(px, parity, r);
+        sum += __ldcg(reinterpret_cast<const double *>(slot) + c);
+        const uint32_t b = __ldcg(reinterpret_cast<const uint32_t *>(slot + (int64_t)channels * 8) + c);
+        mx = b > mx ? b : mx;
+      }
+      s_sum[c] = sum;
+      s_max[c] = mx;
+    }
+    __syncthreads();
+  }
+  if (abssum_out)
+    for (int c = tid; c < channels; c += blockDim.x) {
+      abssum_out[c] = s_sum[c];
+      absmax_out[c] = __uint_as_float(s_max[c]);
+    }
+
+  // ---- 3. parameters (same arithmetic as prune_quant_params_kernel) --------------
+  for (int c = tid; c < channels; c += blockDim.x) {
+    float imp;
+    if (update_magnitude == 2) {
+      imp = (float)(s_sum[c] / count);
+    } else {
+      imp = magnitude[c];
+      if (update_magnitude == 1) {
+        imp = magnitude_ema_step(imp, (float)(s_sum[c] / count), t_prune);
+        magnitude[c] = imp;
+      }
+    }
+    s_imp[c] = imp;
+    s_key[c] = float_to_key(imp);
+  }
+  __syncthreads();
+  if (refresh_mask) {
+    for (int c = tid; c < channels; c += blockDim.x) {
+      const uint32_t kc = s_key[c];
+      int rank = 0;
+      for (int j = 0; j < channels; ++j) {
+        const uint32_t kj = s_key[j];
+        rank += (kj < kc) || (kj == kc && j < c);
+      }
+      if (rank == k) s_thr = s_imp[c];
+    }
+    __syncthreads();
+    const float thr = s_thr;
+    for (int c = tid; c < channels; c += blockDim.x) mask[c] = (s_imp[c] >= thr) ? 1 : 0;
+    __syncthreads();
+  }
+  uint32_t am = 0;
+  if (update_scale) {
+    for (int c = tid; c < channels; c += blockDim.x)
+      if (mask[c]) am = s_max[c] > am ? s_max[c] : am;
+    am = warp_reduce(am, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
+    if (lane == 0) s_amax[warp] = am;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = scale[0];
+    if (update_scale) {
+      for (int w = 1; w < nwarps; ++w) am = s_amax[w] > am ? s_amax[w] : am;
+      s = scale_ema_step(s, __uint_as_float(am), limit, t_quant);
+      scale[0] = s;
+    }
+    if (decimal_out) decimal_out[0] = scale_to_decimal(s);
+  }
+}
+
 }  // namespace qsb
 
 using namespace qsb;
@@ -304,6 +468,37 @@ extern "C" int qsb_prune_quant_params(float *magnitude, uint8_t *mask,
       magnitude, mask, scale, decimal_out, abssum, absmax, (int)n_stat_rows,
       stat_row_stride_bytes, (int)channels, count, t_prune, update_magnitude,
       refresh_mask, k, limit, t_quant, update_scale);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qsb_prune_quant_step_params(
+    float *magnitude, uint8_t *mask, float *scale, float *decimal_out,
+    void *reduce_workspace, int64_t workspace_bytes, int64_t outer,
+    int64_t channels, int64_t inner, qsb_p2p_group *group, int64_t step_stamp,
+    double count, int64_t t_prune, int update_magnitude, int refresh_mask,
+    int64_t k, int bits, int64_t t_quant, int update_scale, double *abssum_out,
+    float *absmax_out, void *stream) {
+  if (channels <= 0 || channels > kStepMaxChannels) return QSB_E_UNSUPPORTED;
+  if (outer <= 0 || inner <= 0 || !reduce_workspace) return QSB_E_BADARG;
+  if (!mask || !scale) return QSB_E_BADARG;
+  if (update_magnitude < 0 || update_magnitude > 2) return QSB_E_BADARG;
+  if (update_magnitude != 2 && !magnitude) return QSB_E_BADARG;
+  if (!(count > 0)) return QSB_E_BADARG;
+  if (refresh_mask && (k < 0 || k >= channels)) return QSB_E_BADARG;
+  if ((abssum_out == nullptr) != (absmax_out == nullptr)) return QSB_E_BADARG;
+  if (group && (group->channels != channels || step_stamp <= 0)) return QSB_E_BADARG;
+  const ReducePlan pl = make_plan(outer, channels, inner, nullptr);
+  if (workspace_bytes < partial_bytes(pl.n_partials) + 256) return QSB_E_WORKSPACE;
+  const Partials P = partials_from_workspace(reduce_workspace, pl.n_partials);
+  P2PDev px{};
+  px.world = 1;
+  if (group) px = group->dev;
+  const float limit = (float)pow(2.0, (double)bits - 1.0);
+  prune_quant_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      magnitude, mask, scale, decimal_out, P, pl.fin_count, pl.fin_q, (int)channels,
+      px, (unsigned long long)step_stamp, count, t_prune, update_magnitude,
+      refresh_mask, k, limit, t_quant, update_scale, abssum_out, absmax_out);
   QSB_LAUNCH_CHECK();
   return 0;
 }

@@ -26,19 +26,12 @@
 #include <math.h>
 
 #include "qsb_common.cuh"
+#include "reduce_internal.cuh"
 
 namespace qsb {
 
 constexpr int kRowModeMinInner = 64;
 constexpr int kRowCtasPerSm = 4;  // matches __launch_bounds__ of reduce_rows_kernel
-
-struct Partials {
-  uint32_t *amax;  // bits of max |x|  (NaN bit patterns order above inf)
-  float *mn;
-  float *mx;
-  double *asum;
-  double *nnz;
-};
 
 template <int WHAT>
 struct Acc {
@@ -353,18 +346,10 @@ __global__ void tensor_min_kernel(const float *mn, int64_t channels, float *out)
 // ---------------------------------------------------------------------------
 // host-side planning
 // ---------------------------------------------------------------------------
-struct ReducePlan {
-  bool row_mode;
-  int64_t rows, seg, segs_per_row, vwarps;       // row mode
-  int64_t nrows, ncols, chunks, rows_per_chunk;  // column mode
-  int vcol;
-  int64_t n_partials, fin_count, fin_q;
-};
-
 // Physical warps of the row kernel: SMs x resident CTAs x 8.  The CTA count per
 // SM is fixed (not queried per instantiation) so that the plan — and with it the
 // summation order — only depends on the device, never on which statistics run.
-static ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
+ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
                             const float *x) {
   ReducePlan p{};
   const int64_t warps_phys =
@@ -427,16 +412,28 @@ static ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
   return p;
 }
 
-static int64_t partial_bytes(int64_t n) {
+int64_t partial_bytes(int64_t n) {
   // amax(4) + mn(4) + mx(4) + pad(4) + asum(8) + nnz(8), each array 256-aligned
   auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
   return up(n * 4) * 3 + up(n * 8) * 2;
 }
 
+Partials partials_from_workspace(void *workspace, int64_t n_partials) {
+  auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
+  Partials P;
+  P.amax = reinterpret_cast<uint32_t *>(base); base += up(n_partials * 4);
+  P.mn = reinterpret_cast<float *>(base);      base += up(n_partials * 4);
+  P.mx = reinterpret_cast<float *>(base);      base += up(n_partials * 4);
+  P.asum = reinterpret_cast<double *>(base);   base += up(n_partials * 8);
+  P.nnz = reinterpret_cast<double *>(base);
+  return P;
+}
+
 template <int WHAT>
 static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
                       int64_t inner, const Partials &P, const FinalOut &out,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool finalize = true) {
   if (pl.row_mode) {
     constexpr int kWarps = QSB_THREADS / 32;
     int64_t grid = (int64_t)device_props().sm_count * kRowCtasPerSm;
@@ -456,6 +453,7 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
           x, pl.nrows, pl.ncols, pl.rows_per_chunk, P);
   }
   QSB_LAUNCH_CHECK();
+  if (!finalize) return 0;
   // few channels: a whole CTA per channel; many: a warp per channel
   if (pl.fin_count > 1024) {
     reduce_finalize_kernel<WHAT, QSB_THREADS>
@@ -498,14 +496,7 @@ extern "C" int qsb_reduce_stats(const float *x, int what, int64_t outer,
   if ((what & QSB_STAT_NNZ) && !(what & QSB_STAT_ABSSUM)) return QSB_E_BADARG;
   const ReducePlan pl = make_plan(outer, channels, inner, x);
   if (workspace_bytes < partial_bytes(pl.n_partials) + 256) return QSB_E_WORKSPACE;
-  auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
-  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
-  Partials P;
-  P.amax = reinterpret_cast<uint32_t *>(base); base += up(pl.n_partials * 4);
-  P.mn = reinterpret_cast<float *>(base);      base += up(pl.n_partials * 4);
-  P.mx = reinterpret_cast<float *>(base);      base += up(pl.n_partials * 4);
-  P.asum = reinterpret_cast<double *>(base);   base += up(pl.n_partials * 8);
-  P.nnz = reinterpret_cast<double *>(base);
+  const Partials P = partials_from_workspace(workspace, pl.n_partials);
   FinalOut out{absmax, mn, mx, abssum, nnz};
   int rc;
   switch (what) {
@@ -534,4 +525,21 @@ extern "C" int qsb_reduce_stats(const float *x, int what, int64_t outer,
     QSB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+// Stage 1 only: leaves the per-virtual-warp partials of sum|x| and max|x| in the
+// workspace for qsb_prune_quant_step_params, which finalizes them itself.
+extern "C" int qsb_reduce_partials(const float *x, int64_t outer, int64_t channels,
+                                   int64_t inner, void *workspace,
+                                   int64_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (outer <= 0 || channels <= 0 || inner <= 0) return QSB_E_BADARG;
+  if (!x || !workspace) return QSB_E_BADARG;
+  if (!aligned_to(x, 4)) return QSB_E_ALIGN;
+  const ReducePlan pl = make_plan(outer, channels, inner, x);
+  if (workspace_bytes < partial_bytes(pl.n_partials) + 256) return QSB_E_WORKSPACE;
+  const Partials P = partials_from_workspace(workspace, pl.n_partials);
+  FinalOut out{nullptr, nullptr, nullptr, nullptr, nullptr};
+  return run_reduce<QSB_STAT_ABSSUM | QSB_STAT_ABSMAX>(x, pl, channels, inner, P, out,
+                                                      stream, /*finalize=*/false);
 }

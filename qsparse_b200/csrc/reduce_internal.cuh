@@ -1,0 +1,31 @@
+// Internals of the two-stage reductions shared between reduce.cu (stage 1 + the
+// stand-alone finalize) and params.cu (the fused finalize + exchange + parameter kernel).
+#pragma once
+#include "qsb_common.cuh"
+
+namespace qsb {
+
+struct Partials {
+  uint32_t *amax;  // bits of max |x|  (NaN bit patterns order above inf)
+  float *mn;
+  float *mx;
+  double *asum;
+  double *nnz;
+};
+
+struct ReducePlan {
+  bool row_mode;
+  int64_t rows, seg, segs_per_row, vwarps;       // row mode
+  int64_t nrows, ncols, chunks, rows_per_chunk;  // column mode
+  int vcol;
+  // channel c combines entries j = 0..fin_count-1 at
+  //   idx(j) = (j / fin_q) * (channels * fin_q) + c * fin_q + (j % fin_q)
+  int64_t n_partials, fin_count, fin_q;
+};
+
+ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner, const float *x);
+int64_t partial_bytes(int64_t n);
+// carve the five partial arrays out of a caller workspace (256-byte aligned)
+Partials partials_from_workspace(void *workspace, int64_t n_partials);
+
+}  // namespace qsb

@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from . import _native as N
 from . import ops
-from .parallel import StatExchange
+from .parallel import StatExchange, make_exchange
 from .util import kth_rank
 
 
@@ -66,7 +66,12 @@ class PruneQuantize(nn.Module):
         self.mask = nn.Parameter(torch.ones(channels, dtype=torch.bool, device=dev), requires_grad=False)
         self.scale = nn.Parameter(torch.zeros(1, 1, device=dev), requires_grad=False)
         self.decimal = torch.zeros(1, device=dev)
-        self._exchange = StatExchange(channels, dev, self.group)
+        self._p2p = make_exchange(channels, dev, self.group) if channels <= 2048 else None
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        # NCCL all-gather path only when peer memory is unavailable (or > 2048 channels)
+        self._exchange = StatExchange(channels, dev, self.group) if (multi and self._p2p is None) or channels > 2048 \
+            else True
 
     def _forward_impl(self, x, layout):
         outer, ch, inner = layout
@@ -74,17 +79,30 @@ class PruneQuantize(nn.Module):
         if self._exchange is None:
             self._allocate(xs, ch)
         if self.training:
-            ex = self._exchange
-            ops.reduce_stats(xs, layout, abssum=True, absmax=True,
-                             out={"abssum": ex.row.abssum, "absmax": ex.row.absmax})
-            rows, n_rows, stride = ex.gather()
-            abssum0, absmax0 = ex.views(rows)
             t = self.t_prune
             refresh = (t % self.mask_refresh_interval == 0) and (t > 0 or not self.running_average)
-            ops.prune_quant_params(self.magnitude.data, self.mask.data, self.scale.data, self.decimal,
-                                   {"abssum": abssum0, "absmax": absmax0}, float(outer * inner * n_rows), t,
-                                   1 if self.running_average else 2, refresh, kth_rank(self.sparsity, ch),
-                                   self.bits, self.t_quant, True, n_rows=n_rows, row_stride_bytes=stride)
+            mode = 1 if self.running_average else 2
+            k = kth_rank(self.sparsity, ch)
+            if isinstance(self._exchange, StatExchange):
+                # NCCL fallback: finalize into the row, all-gather, combine rows in the kernel
+                ex = self._exchange
+                ops.reduce_stats(xs, layout, abssum=True, absmax=True,
+                                 out={"abssum": ex.row.abssum, "absmax": ex.row.absmax})
+                rows, n_rows, stride = ex.gather()
+                abssum0, absmax0 = ex.views(rows)
+                ops.prune_quant_params(self.magnitude.data, self.mask.data, self.scale.data, self.decimal,
+                                       {"abssum": abssum0, "absmax": absmax0}, float(outer * inner * n_rows), t,
+                                       mode, refresh, k, self.bits, self.t_quant, True, n_rows=n_rows,
+                                       row_stride_bytes=stride)
+            else:
+                # one kernel: finalize + peer-memory exchange + parameters
+                ws = ops.reduce_partials(xs, layout)
+                world = self._p2p.world if self._p2p is not None else 1
+                ops.prune_quant_step_params(self.magnitude.data, self.mask.data, self.scale.data, self.decimal, ws,
+                                            layout, float(outer * inner * world), t, mode, refresh, k, self.bits,
+                                            self.t_quant, True,
+                                            group=self._p2p.handle if self._p2p is not None else None,
+                                            step_stamp=self._p2p.next_stamp() if self._p2p is not None else 1)
             self.t_prune += 1
             self.t_quant += 1
         return ops.fq_pow2_fwd(xs, self.decimal, layout, mask=self.mask.data)

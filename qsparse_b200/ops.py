@@ -287,5 +287,34 @@ def prune_quant_params(magnitude, mask, scale, decimal_out, stats: dict, count: 
                                        N.stream_ptr(mask.device)), "qsb_prune_quant_params")
 
 
+def reduce_partials(x, layout: Layout):
+    """Stage 1 of the sum|x| / max|x| reduction only; the partials stay in the returned
+    workspace for prune_quant_step_params (which finalizes them in its own kernel)."""
+    N.require_cuda(x, "input")
+    lib = N.load_library()
+    outer, ch, inner = layout
+    nbytes = lib.qsb_reduce_workspace_bytes(c_int64(outer), c_int64(ch), c_int64(inner))
+    ws = N.workspace(x.device, nbytes)
+    N.check(lib.qsb_reduce_partials(N.ptr(x), c_int64(outer), c_int64(ch), c_int64(inner), N.ptr(ws),
+                                    c_int64(ws.numel()), N.stream_ptr(x.device)), "qsb_reduce_partials")
+    return ws
+
+
+def prune_quant_step_params(magnitude, mask, scale, decimal_out, workspace, layout: Layout, count: float,
+                            t_prune: int, update_magnitude: int, refresh_mask: bool, k: int, bits: int,
+                            t_quant: int, update_scale: bool, group=None, step_stamp: int = 1,
+                            abssum_out=None, absmax_out=None):
+    """finalize + (peer-memory exchange) + parameter update in ONE kernel.  `group` is a
+    parallel.P2PExchange handle (ctypes pointer) or None for a single GPU."""
+    lib = N.load_library()
+    outer, ch, inner = layout
+    N.check(lib.qsb_prune_quant_step_params(
+        N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out), N.ptr(workspace),
+        c_int64(workspace.numel()), c_int64(outer), c_int64(ch), c_int64(inner), group, c_int64(step_stamp),
+        c_double(count), c_int64(t_prune), c_int(update_magnitude), c_int(1 if refresh_mask else 0), c_int64(k),
+        c_int(bits), c_int64(t_quant), c_int(1 if update_scale else 0), N.ptr(abssum_out), N.ptr(absmax_out),
+        N.stream_ptr(mask.device)), "qsb_prune_quant_step_params")
+
+
 def set_tuning(key: int, value: int):
     N.check(N.load_library().qsb_set_tuning(c_int(key), c_int(value)), "qsb_set_tuning")

@@ -60,6 +60,87 @@ class StatExchange:
         return buf[: 8 * c].view(torch.float64), buf[8 * c: 12 * c].view(torch.float32)
 
 
+class P2PExchange:
+    """Peer-memory statistics exchange: every rank maps every other rank's small exchange
+    buffer through CUDA IPC (same node, NVLink / NVSwitch); the parameter kernel then
+    pushes its row to all peers, publishes a step stamp and combines the rows in rank
+    order — no collective launch on the critical path.  ``handle`` is what
+    ``ops.prune_quant_step_params(group=...)`` takes."""
+
+    def __init__(self, channels: int, device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+        from ctypes import byref, c_int, c_int64, c_void_p
+
+        from . import _native as N
+
+        self._N = N
+        self.lib = N.load_library()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 16:
+            raise RuntimeError("P2PExchange supports up to 16 ranks of one node")
+        nbytes = self.lib.qsb_p2p_group_bytes(c_int(self.world), c_int64(channels))
+        self.local = c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            N.check(self.lib.qsb_p2p_alloc(c_int64(nbytes), byref(self.local), handle), "qsb_p2p_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.peers = []
+            bufs = (c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    bufs[r] = self.local
+                    continue
+                p = c_void_p()
+                N.check(self.lib.qsb_p2p_open(ctypes.create_string_buffer(handles[r], 64), byref(p)), "qsb_p2p_open")
+                self.peers.append(p)
+                bufs[r] = p
+            self.handle = c_void_p()
+            N.check(self.lib.qsb_p2p_group_create(byref(self.handle), c_int(self.rank), c_int(self.world),
+                                                  c_int64(channels), bufs), "qsb_p2p_group_create")
+        dist.barrier(group=group)      # every peer has mapped every buffer before the first kernel
+        self.stamp = 0
+
+    def next_stamp(self) -> int:
+        self.stamp += 1
+        return self.stamp
+
+    def error(self) -> int:
+        from ctypes import byref, c_int
+        e = c_int(0)
+        self._N.check(self.lib.qsb_p2p_group_error(self.handle, byref(e)), "qsb_p2p_group_error")
+        return e.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.qsb_p2p_group_destroy(self.handle)
+            self.handle = None
+            for p in self.peers:
+                self.lib.qsb_p2p_close(p)
+            self.lib.qsb_p2p_free(self.local)
+
+
+def make_exchange(channels: int, device, group=None):
+    """P2PExchange when a multi-rank group is initialised and peer mapping works, else None
+    (single process, or the caller falls back to StatExchange / NCCL)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    ok = torch.ones(1, device=device)
+    ex = None
+    try:
+        ex = P2PExchange(channels, device, group)
+    except Exception as exc:  # pragma: no cover - depends on the box
+        print(f"[qsparse_b200] peer-memory exchange unavailable ({exc}); using NCCL all-gather")
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # all ranks take the same path
+    if ok.item() == 0:
+        if ex is not None:
+            ex.close()
+        return None
+    return ex
+
+
 def combine_rows_host(gathered: torch.Tensor, n_rows: int, row_bytes: int, channels: int):
     """Host restatement of how the parameter kernel combines rows (rank order: SUM of the
     fp64 sums, MAX of the maxima).  Used by the CPU (gloo) tests of the exchange."""

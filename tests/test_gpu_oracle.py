@@ -329,3 +329,31 @@ def test_scaler_line_dense_rounding_boundaries():
         for fzp in (True, False):
             assert bits_equal(npy(quantize_with_line(cu(xs), 8, (float(lines[0, 0]), float(lines[0, 1])), -1, False, fzp)),
                               orc.fq_line_fwd(xs, lines, 8, -1, fzp))
+
+
+@pytest.mark.parametrize("shape,C", [((8, 64, 14, 14), 64), ((4, 200, 9, 9), 200), ((16, 7, 70), 7), ((32, 48), 48)])
+def test_fused_step_kernel_equals_separate_kernels(shape, C):
+    """reduce_partials + prune_quant_step_params (finalize folded into the parameter kernel)
+    must be bit-identical to reduce_stats + prune_quant_params."""
+    from qsparse_b200 import ops
+    from qsparse_b200._native import channel_layout
+    layout = channel_layout(shape, 1)
+    count = float(layout[0] * layout[2])
+    st_a = dict(mag=torch.zeros(C, device="cuda"), mask=torch.ones(C, dtype=torch.bool, device="cuda"),
+                scale=torch.zeros(1, device="cuda"), dec=torch.zeros(1, device="cuda"))
+    st_b = {k: v.clone() for k, v in st_a.items()}
+    k = orc.kth_index(0.5, C)
+    for t in range(4):
+        x = cu(np.maximum(rnd(shape, 300 + t), 0) * np.linspace(0.3, 1.7, C, dtype=np.float32).reshape(
+            (1, C) + (1,) * (len(shape) - 2)))
+        st = ops.reduce_stats(x, layout, abssum=True, absmax=True)
+        ops.prune_quant_params(st_a["mag"], st_a["mask"], st_a["scale"], st_a["dec"], st, count, t, 1, t > 0, k, 8, t,
+                               True)
+        ws = ops.reduce_partials(x, layout)
+        asum = torch.empty(C, dtype=torch.float64, device="cuda")
+        amax = torch.empty(C, dtype=torch.float32, device="cuda")
+        ops.prune_quant_step_params(st_b["mag"], st_b["mask"], st_b["scale"], st_b["dec"], ws, layout, count, t, 1,
+                                    t > 0, k, 8, t, True, abssum_out=asum, absmax_out=amax)
+        assert torch.equal(asum, st["abssum"]) and torch.equal(amax, st["absmax"]), t
+        for key in st_a:
+            assert torch.equal(st_a[key], st_b[key]), (key, t)
