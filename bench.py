@@ -191,6 +191,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so
+    # everything but the final line goes to stderr.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -213,6 +218,7 @@ def run_ours(args):
     ex = StatExchange(C, dev) if (world > 1 and p2p is None) else None   # NCCL all-gather fallback
     k = kth_rank(SPARSITY, C)
     state = {"t": 0}
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)      # device-side step index (graph mode)
     stream = N.stream_ptr(dev)
     ev_b0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev_b1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -223,7 +229,25 @@ def run_ours(args):
                                 c_int(BITS), c_int(0), N.ptr(mask), c_int(N.MASK_CHANNEL), c_int64(LAYOUT[0]),
                                 c_int64(LAYOUT[1]), c_int64(LAYOUT[2]), stream), "qsb_ste_bwd")
 
+    def fwd_graphable():
+        # reduce stage 1 -> ONE kernel (finalize + peer exchange + parameters) -> forward apply;
+        # the step index is read from / advanced on the device, so the launch arguments are constant
+        ws = ops.reduce_partials(x, LAYOUT)
+        ops.prune_quant_step_params(mag, mask, scale, dec, ws, LAYOUT, float(LAYOUT[0] * LAYOUT[2] * world), 0, 1,
+                                    1, k, BITS, 0, True, group=p2p.handle if p2p else None, step_counter=counter)
+        ops.fq_pow2_fwd(x, dec, LAYOUT, mask=mask, out=y)
+
+    graph = None
+
     def step(i=None):
+        if graph is not None:
+            graph.replay()
+            if i is not None:
+                ev_b0[i].record()
+            bwd()
+            if i is not None:
+                ev_b1[i].record()
+            return
         t = state["t"]
         if ex is None:
             ws = ops.reduce_partials(x, LAYOUT)
@@ -255,6 +279,21 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.2)
+    for _ in range(3):
+        step()                      # eager steps: first-use initialisation outside any capture
+    use_graph = args.mode == "graph" and ex is None
+    if use_graph:
+        counter.fill_(state["t"])
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fwd_graphable()
+            bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            fwd_graphable()
+        graph = g_
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -286,6 +325,8 @@ def run_ours(args):
     value = world * n * BYTES_PER_ELEM / (ms_per_step * 1e-3) / 1e9
     # reduce stage 1, fused finalize+exchange+parameters, forward apply, backward  (+ finalize on the NCCL path)
     launches_per_step = 4 if ex is None else 5
+    launch_mode = ("CUDA graph [reduce, finalize+exchange+params, forward] + backward kernel" if graph is not None
+                   else "eager launches")
 
     # ---- e2e: host buffers through the C-ABI (copies inside the timed region) ----
     e2e_steps = max(3, min(args.steps, 10))
@@ -355,9 +396,11 @@ def run_ours(args):
             same = bool(torch.equal(hy.to(dev), yy) and torch.equal(e_chk["mask"], chk["mask"]))
     N.check(lib.qsb_host_ctx_destroy(ctx), "qsb_host_ctx_destroy")
 
+    exchange_error = p2p.error() if p2p else 0
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     peak, peak_src = peak_hbm()
@@ -386,7 +429,8 @@ def run_ours(args):
         "clocks": clocks,
         "exchange": ("none (1 GPU)" if world == 1 else ("peer-memory (CUDA IPC over NVLink), fused into the parameter kernel"
                                                          if p2p else "NCCL all_gather_into_tensor")),
-        "exchange_error": (p2p.error() if p2p else 0),
+        "exchange_error": exchange_error,
+        "launch_mode": launch_mode,
         "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4 * world,
                 "d2h_bytes_per_step": 2 * n * 4 * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
                 "api": "qsb_host_prune_quant_step (C-ABI, pinned host buffers, 8 chunks, 3 streams)",
@@ -400,9 +444,9 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": n * 8, "avg_launch_us": round(bwd_ms * 1e3, 2)},
         "cpu_baseline": cpu_baseline,
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -412,6 +456,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph: the forward half of the step is one captured CUDA graph (default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -55,7 +55,10 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *   key 0: per-tensor streaming kernels: 0 = one CTA per tile (default),
  *          n > 0 = persistent grid of n CTAs per SM;
  *   key 1: per-channel streaming kernels: 0 = occupancy-derived persistent
- *          grid (default), n > 0 = n CTAs per SM. */
+ *          grid (default), n > 0 = n CTAs per SM;
+ *   key 2: tile order of the one-CTA-per-tile kernels: 1 = last tile first
+ *          (default; re-reads the L2-resident tail of a just-touched tensor),
+ *          0 = first tile first. */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and
@@ -244,6 +247,11 @@ int qsb_prune_quant_params(float *magnitude, uint8_t *mask, float *scale,
  * (optional, both or neither) receive the combined statistics.
  * Requires channels <= 2048 and the same (outer, channels, inner) that was
  * passed to qsb_reduce_partials.
+ * step_counter_dev (optional): a device int64 step index for CUDA-graph capture
+ * (launch arguments of a captured graph are frozen).  When given, the kernel uses
+ * t_prune = t_quant = *step_counter_dev, step_stamp = t + 1, treats refresh_mask
+ * as the refresh INTERVAL (refresh when t % interval == 0 and (t > 0 or
+ * update_magnitude == 2)) and increments the counter at the end.
  * ---------------------------------------------------------------------- */
 int qsb_reduce_partials(const float *x, int64_t outer, int64_t channels,
                         int64_t inner, void *workspace, int64_t workspace_bytes,
@@ -273,7 +281,8 @@ int qsb_prune_quant_step_params(float *magnitude, uint8_t *mask, float *scale,
                                 int update_magnitude, int refresh_mask,
                                 int64_t k, int bits, int64_t t_quant,
                                 int update_scale, double *abssum_out,
-                                float *absmax_out, void *stream);
+                                float *absmax_out, int64_t *step_counter_dev,
+                                void *stream);
 
 /* ------------------------------------------------------------------------
  * Host-buffer entry points (what a host-side caller that keeps its tensors in

@@ -57,7 +57,7 @@ _SIGNATURES = {
     "qsb_p2p_group_destroy": (c_int, [_P]),
     "qsb_prune_quant_step_params": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64,
                                             c_double, c_int64, c_int, c_int, c_int64, c_int, c_int64, c_int, _P, _P,
-                                            _P]),
+                                            _P, _P]),
     "qsb_host_ctx_create": (c_int, [ctypes.POINTER(c_void_p), c_int64, c_int64, c_int]),
     "qsb_host_ctx_destroy": (c_int, [_P]),
     "qsb_host_prune_quant_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,

@@ -10,7 +10,7 @@
 namespace qsb {
 
 MapTuning &map_tuning() {
-  static MapTuning t{0, 0};
+  static MapTuning t{0, 0, 1};
   return t;
 }
 
@@ -569,6 +569,10 @@ extern "C" int qsb_set_tuning(int key, int value) {
   }
   if (key == 1) {
     map_tuning().chan_ctas_per_sm = value;
+    return 0;
+  }
+  if (key == 2) {
+    map_tuning().reverse_tiles = value;
     return 0;
   }
   return QSB_E_BADARG;

@@ -71,6 +71,11 @@ __device__ __forceinline__ void apply_vec(const Op &op, const VecF<V> &a,
 struct MapTuning {
   int ctas_per_sm;   // per-tensor kernel: 0 = one CTA per tile (default); >0 persistent
   int chan_ctas_per_sm;  // channel kernel: 0 = occupancy-derived persistent grid
+  // Tile order of the one-CTA-per-tile kernels.  1 (default): last tile first.  The
+  // tensor a streaming kernel reads was normally just produced / reduced front to
+  // back, so its TAIL is what still sits in the 126 MB L2; walking backwards turns
+  // up to ~100 MB of the second pass into L2 hits instead of HBM reads.
+  int reverse_tiles;
 };
 MapTuning &map_tuning();
 
@@ -79,14 +84,16 @@ MapTuning &map_tuning();
 // ---------------------------------------------------------------------------
 template <class Op, int V, int U, Hint LH, Hint SH>
 __global__ void __launch_bounds__(QSB_THREADS)
-    map_kernel(Op op, MapIO io, int64_t n) {
+    map_kernel(Op op, MapIO io, int64_t n, int reverse) {
   using P = typename Op::P;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
   constexpr int64_t kStrideU = (int64_t)QSB_THREADS * V;
   const int64_t n_main = (n / V) * V;
   const P p = op.params(0);
+  // reverse is only set for one-CTA-per-tile launches (the loop then runs once)
+  const int64_t first_tile = reverse ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
 
-  for (int64_t e_base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * V;
+  for (int64_t e_base = first_tile * kTile + (int64_t)threadIdx.x * V;
        e_base < n_main; e_base += (int64_t)gridDim.x * kTile) {
     VecF<V> a[U], b[U];
     VecB<V> mb[U];
@@ -140,7 +147,8 @@ int launch_map_tensor(const Op &op, const MapIO &io, int64_t n,
     if (grid > tiles) grid = tiles;
   }
   if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;  // the kernel loops
-  kern<<<(unsigned)grid, QSB_THREADS, 0, stream>>>(op, io, n);
+  const int reverse = (grid == tiles && map_tuning().reverse_tiles) ? 1 : 0;
+  kern<<<(unsigned)grid, QSB_THREADS, 0, stream>>>(op, io, n, reverse);
   QSB_LAUNCH_CHECK();
   return 0;
 }
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
 template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
 __global__ void __launch_bounds__(QSB_THREADS)
     map_chan_win_kernel(Op op, MapIO io, int64_t n, uint32_t inner,
-                        uint32_t channels) {
+                        uint32_t channels, int reverse) {
   using P = typename Op::P;
   static_assert(MODE == 0 || MODE == 1, "window kernel needs inner >= V");
   extern __shared__ __align__(16) unsigned char qsb_smem_raw[];
@@ -297,7 +305,8 @@ __global__ void __launch_bounds__(QSB_THREADS)
   constexpr uint32_t kTile = QSB_THREADS * V * U;
   constexpr uint32_t kStrideU = QSB_THREADS * V;
   const int64_t n_main = (n / V) * V;
-  const int64_t t0 = (int64_t)blockIdx.x * kTile;
+  const int64_t t0 =
+      (int64_t)(reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * kTile;
   // first row / column / channel of the tile (uniform across the CTA)
   const int64_t row0 = t0 / inner;
   const uint32_t col0 = (uint32_t)(t0 - row0 * inner);
@@ -378,8 +387,8 @@ int launch_map_chan_win(const Op &op, const MapIO &io, int64_t n,
   const size_t rows_max = (size_t)((L.inner - 1 + kTile - 1) / L.inner + 2);
   const size_t smem = rows_max * sizeof(P);
   if (tiles > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
-  kern<<<(unsigned)tiles, QSB_THREADS, smem, stream>>>(op, io, n, (uint32_t)L.inner,
-                                                       (uint32_t)L.channels);
+  kern<<<(unsigned)tiles, QSB_THREADS, smem, stream>>>(
+      op, io, n, (uint32_t)L.inner, (uint32_t)L.channels, map_tuning().reverse_tiles ? 1 : 0);
   QSB_LAUNCH_CHECK();
   return 0;
 }

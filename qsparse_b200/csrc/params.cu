@@ -231,7 +231,19 @@ __global__ void __launch_bounds__(1024)
                             int64_t t_prune, int update_magnitude,
                             int refresh_mask, int64_t k, float limit,
                             int64_t t_quant, int update_scale,
-                            double *abssum_out, float *absmax_out) {
+                            double *abssum_out, float *absmax_out,
+                            long long *step_counter) {
+  // graph mode: the step index lives on the device (the launch arguments of a captured
+  // CUDA graph are frozen), the kernel reads it, derives t / stamp / refresh itself
+  // and increments it at the end.  `refresh_mask` then carries the refresh interval.
+  if (step_counter) {
+    const long long t = *step_counter;
+    t_prune = t;
+    t_quant = t;
+    stamp = (unsigned long long)(t + 1);
+    const int interval = refresh_mask > 0 ? refresh_mask : 1;
+    refresh_mask = (t % interval == 0) && (t > 0 || update_magnitude == 2);
+  }
   __shared__ double s_sum[kStepMaxChannels];
   __shared__ uint32_t s_max[kStepMaxChannels];
   __shared__ float s_imp[kStepMaxChannels];
@@ -358,6 +370,7 @@ __global__ void __launch_bounds__(1024)
       scale[0] = s;
     }
     if (decimal_out) decimal_out[0] = scale_to_decimal(s);
+    if (step_counter) *step_counter = t_prune + 1;
   }
 }
 
@@ -478,7 +491,7 @@ extern "C" int qsb_prune_quant_step_params(
     int64_t channels, int64_t inner, qsb_p2p_group *group, int64_t step_stamp,
     double count, int64_t t_prune, int update_magnitude, int refresh_mask,
     int64_t k, int bits, int64_t t_quant, int update_scale, double *abssum_out,
-    float *absmax_out, void *stream) {
+    float *absmax_out, int64_t *step_counter_dev, void *stream) {
   if (channels <= 0 || channels > kStepMaxChannels) return QSB_E_UNSUPPORTED;
   if (outer <= 0 || inner <= 0 || !reduce_workspace) return QSB_E_BADARG;
   if (!mask || !scale) return QSB_E_BADARG;
@@ -487,7 +500,8 @@ extern "C" int qsb_prune_quant_step_params(
   if (!(count > 0)) return QSB_E_BADARG;
   if (refresh_mask && (k < 0 || k >= channels)) return QSB_E_BADARG;
   if ((abssum_out == nullptr) != (absmax_out == nullptr)) return QSB_E_BADARG;
-  if (group && (group->channels != channels || step_stamp <= 0)) return QSB_E_BADARG;
+  if (group && (group->channels != channels || (!step_counter_dev && step_stamp <= 0)))
+    return QSB_E_BADARG;
   const ReducePlan pl = make_plan(outer, channels, inner, nullptr);
   if (workspace_bytes < partial_bytes(pl.n_partials) + 256) return QSB_E_WORKSPACE;
   const Partials P = partials_from_workspace(reduce_workspace, pl.n_partials);
@@ -498,7 +512,8 @@ extern "C" int qsb_prune_quant_step_params(
   prune_quant_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
       magnitude, mask, scale, decimal_out, P, pl.fin_count, pl.fin_q, (int)channels,
       px, (unsigned long long)step_stamp, count, t_prune, update_magnitude,
-      refresh_mask, k, limit, t_quant, update_scale, abssum_out, absmax_out);
+      refresh_mask, k, limit, t_quant, update_scale, abssum_out, absmax_out,
+      reinterpret_cast<long long *>(step_counter_dev));
   QSB_LAUNCH_CHECK();
   return 0;
 }

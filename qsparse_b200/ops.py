@@ -303,7 +303,7 @@ def reduce_partials(x, layout: Layout):
 def prune_quant_step_params(magnitude, mask, scale, decimal_out, workspace, layout: Layout, count: float,
                             t_prune: int, update_magnitude: int, refresh_mask: bool, k: int, bits: int,
                             t_quant: int, update_scale: bool, group=None, step_stamp: int = 1,
-                            abssum_out=None, absmax_out=None):
+                            abssum_out=None, absmax_out=None, step_counter=None):
     """finalize + (peer-memory exchange) + parameter update in ONE kernel.  `group` is a
     parallel.P2PExchange handle (ctypes pointer) or None for a single GPU."""
     lib = N.load_library()
@@ -311,9 +311,9 @@ def prune_quant_step_params(magnitude, mask, scale, decimal_out, workspace, layo
     N.check(lib.qsb_prune_quant_step_params(
         N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out), N.ptr(workspace),
         c_int64(workspace.numel()), c_int64(outer), c_int64(ch), c_int64(inner), group, c_int64(step_stamp),
-        c_double(count), c_int64(t_prune), c_int(update_magnitude), c_int(1 if refresh_mask else 0), c_int64(k),
+        c_double(count), c_int64(t_prune), c_int(update_magnitude), c_int(int(refresh_mask)), c_int64(k),
         c_int(bits), c_int64(t_quant), c_int(1 if update_scale else 0), N.ptr(abssum_out), N.ptr(absmax_out),
-        N.stream_ptr(mask.device)), "qsb_prune_quant_step_params")
+        N.ptr(step_counter), N.stream_ptr(mask.device)), "qsb_prune_quant_step_params")
 
 
 def set_tuning(key: int, value: int):

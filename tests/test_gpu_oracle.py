@@ -342,6 +342,8 @@ def test_fused_step_kernel_equals_separate_kernels(shape, C):
     st_a = dict(mag=torch.zeros(C, device="cuda"), mask=torch.ones(C, dtype=torch.bool, device="cuda"),
                 scale=torch.zeros(1, device="cuda"), dec=torch.zeros(1, device="cuda"))
     st_b = {k: v.clone() for k, v in st_a.items()}
+    st_c = {k: v.clone() for k, v in st_a.items()}          # graph mode: step index on the device
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
     k = orc.kth_index(0.5, C)
     for t in range(4):
         x = cu(np.maximum(rnd(shape, 300 + t), 0) * np.linspace(0.3, 1.7, C, dtype=np.float32).reshape(
@@ -355,5 +357,10 @@ def test_fused_step_kernel_equals_separate_kernels(shape, C):
         ops.prune_quant_step_params(st_b["mag"], st_b["mask"], st_b["scale"], st_b["dec"], ws, layout, count, t, 1,
                                     t > 0, k, 8, t, True, abssum_out=asum, absmax_out=amax)
         assert torch.equal(asum, st["abssum"]) and torch.equal(amax, st["absmax"]), t
+        ws = ops.reduce_partials(x, layout)
+        ops.prune_quant_step_params(st_c["mag"], st_c["mask"], st_c["scale"], st_c["dec"], ws, layout, count, 0, 1,
+                                    1, k, 8, 0, True, step_counter=counter)
+        assert counter.item() == t + 1
         for key in st_a:
             assert torch.equal(st_a[key], st_b[key]), (key, t)
+            assert torch.equal(st_a[key], st_c[key]), (key, t, "graph mode")
