@@ -20,8 +20,8 @@ scale = torch.zeros(1, device=dev)
 dec = torch.zeros(1, device=dev)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 for t in range(steps):
-    st = ops.reduce_stats(x, layout, abssum=True, absmax=True)
-    ops.prune_quant_params(mag, mask, scale, dec, st, 256 * 3136.0, t, 1, t > 0, 48, 8, t, True)
+    ws = ops.reduce_partials(x, layout)
+    ops.prune_quant_step_params(mag, mask, scale, dec, ws, layout, 256 * 3136.0, t, 1, t > 0, 48, 8, t, True)
     ops.fq_pow2_fwd(x, dec, layout, mask=mask, out=y)
     gc = g.clone()
     ops.ste_bwd(gc, dec, True, 8, 0, layout, mask=mask, clamp_in_place=False, want_gx=True)

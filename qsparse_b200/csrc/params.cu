@@ -225,8 +225,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 __global__ void __launch_bounds__(1024)
     prune_quant_step_kernel(float *magnitude, uint8_t *mask, float *scale,
-                            float *decimal_out, Partials P, int64_t fin_count,
-                            int64_t fin_q, int channels, P2PDev px,
+                            float *decimal_out, Partials P, int fin_count,
+                            int fin_q, int channels, int group, P2PDev px,
                             unsigned long long stamp, double count,
                             int64_t t_prune, int update_magnitude,
                             int refresh_mask, int64_t k, float limit,
@@ -251,24 +251,49 @@ __global__ void __launch_bounds__(1024)
   __shared__ float s_thr;
   __shared__ uint32_t s_amax[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nwarps = blockDim.x >> 5;
+  // `group` threads (a power of two <= 32, inside one warp) share a channel, so the few
+  // thousand partials are fetched with independent loads by all 1024 threads; the
+  // kernel is a chain of dependent round trips, everything is laid out to keep it short.
+  const int gl = tid % group, gc = tid / group, cpp = 1024 / group;
+  const float scale_old = (tid == 0) ? scale[0] : 0.0f;  // prefetch
 
-  // ---- 1. finalize this GPU's partials: a warp per channel, fixed order --------
-  for (int c = warp; c < channels; c += nwarps) {
+  // ---- 1. finalize this GPU's partials (fixed order: strided per thread, xor tree) ----
+  for (int base = 0; base < channels; base += cpp) {
+    const int c = base + gc;
+    const bool act = c < channels;
+    float mag_old = 0.0f;
+    if (act && gl == 0 && update_magnitude != 2) mag_old = magnitude[c];  // prefetch
     double sum = 0.0;
     uint32_t mx = 0;
-    for (int64_t j = lane; j < fin_count; j += 32) {
-      const int64_t hi = j / fin_q;
-      const int64_t idx = hi * ((int64_t)channels * fin_q) + (int64_t)c * fin_q + (j - hi * fin_q);
-      sum += P.asum[idx];
-      const uint32_t b = P.amax[idx];
-      mx = b > mx ? b : mx;
+    if (act) {
+      for (int j0 = gl; j0 < fin_count; j0 += 4 * group) {
+        double v[4];
+        uint32_t b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u * group;
+          const bool ok = j < fin_count;
+          const int hi = ok ? j / fin_q : 0;
+          const int64_t idx = (int64_t)hi * ((int64_t)channels * fin_q) + (int64_t)c * fin_q + (ok ? j - hi * fin_q : 0);
+          v[u] = ok ? P.asum[idx] : 0.0;
+          b[u] = ok ? P.amax[idx] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sum += v[u];
+          mx = b[u] > mx ? b[u] : mx;
+        }
+      }
     }
-    sum = warp_reduce(sum, [](double a, double b) { return a + b; });
-    mx = warp_reduce(mx, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
-    if (lane == 0) {
+    for (int o = group >> 1; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, mx, o);
+      mx = other > mx ? other : mx;
+    }
+    if (act && gl == 0) {
       s_sum[c] = sum;
       s_max[c] = mx;
+      s_imp[c] = mag_old;
     }
   }
   __syncthreads();
@@ -294,7 +319,7 @@ __global__ void __launch_bounds__(1024)
           px.bufs[px.rank] + p2p_flag_offset(px, parity, tid));
       const unsigned long long t0 = global_ns();
       while (ld_flag(flag) != stamp) {
-        __nanosleep(200);
+        __nanosleep(100);
         if (global_ns() - t0 > 4000000000ull) {  // 4 s
           *px.error = 1;
           break;
@@ -317,21 +342,21 @@ __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
   }
-  if (abssum_out)
-    for (int c = tid; c < channels; c += blockDim.x) {
+
+  // ---- 3. importance (magnitude EMA) --------------------------------------------
+  for (int c = tid; c < channels; c += blockDim.x) {
+    if (abssum_out) {
       abssum_out[c] = s_sum[c];
       absmax_out[c] = __uint_as_float(s_max[c]);
     }
-
-  // ---- 3. parameters (same arithmetic as prune_quant_params_kernel) --------------
-  for (int c = tid; c < channels; c += blockDim.x) {
+    const float m = (float)(s_sum[c] / count);
     float imp;
     if (update_magnitude == 2) {
-      imp = (float)(s_sum[c] / count);
+      imp = m;
     } else {
-      imp = magnitude[c];
+      imp = s_imp[c];  // the prefetched old magnitude
       if (update_magnitude == 1) {
-        imp = magnitude_ema_step(imp, (float)(s_sum[c] / count), t_prune);
+        imp = magnitude_ema_step(imp, m, t_prune);
         magnitude[c] = imp;
       }
     }
@@ -339,33 +364,45 @@ __global__ void __launch_bounds__(1024)
     s_key[c] = float_to_key(imp);
   }
   __syncthreads();
+
+  // ---- 4. threshold = sorted(importance)[k] by rank counting, `group` threads/channel --
   if (refresh_mask) {
-    for (int c = tid; c < channels; c += blockDim.x) {
-      const uint32_t kc = s_key[c];
-      int rank = 0;
-      for (int j = 0; j < channels; ++j) {
-        const uint32_t kj = s_key[j];
-        rank += (kj < kc) || (kj == kc && j < c);
-      }
-      if (rank == k) s_thr = s_imp[c];
+    for (int base = 0; base < channels; base += cpp) {
+      const int c = base + gc;
+      const bool act = c < channels;
+      const uint32_t kc = act ? s_key[c] : 0u;
+      int cnt = 0;
+      if (act)
+        for (int j = gl; j < channels; j += group) {
+          const uint32_t kj = s_key[j];
+          cnt += (kj < kc) || (kj == kc && j < c);
+        }
+      for (int o = group >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (act && gl == 0 && cnt == k) s_thr = s_imp[c];
     }
     __syncthreads();
-    const float thr = s_thr;
-    for (int c = tid; c < channels; c += blockDim.x) mask[c] = (s_imp[c] >= thr) ? 1 : 0;
-    __syncthreads();
   }
+
+  // ---- 5. mask, abs-max of the kept channels, scale EMA, decimal ------------------
+  const float thr = refresh_mask ? s_thr : 0.0f;
   uint32_t am = 0;
-  if (update_scale) {
-    for (int c = tid; c < channels; c += blockDim.x)
-      if (mask[c]) am = s_max[c] > am ? s_max[c] : am;
-    am = warp_reduce(am, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
-    if (lane == 0) s_amax[warp] = am;
+  for (int c = tid; c < channels; c += blockDim.x) {
+    bool keep;
+    if (refresh_mask) {
+      keep = s_imp[c] >= thr;
+      mask[c] = keep ? 1 : 0;
+    } else {
+      keep = mask[c] != 0;
+    }
+    if (keep && update_scale) am = s_max[c] > am ? s_max[c] : am;
   }
+  am = warp_reduce(am, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
+  if (lane == 0) s_amax[warp] = am;
   __syncthreads();
   if (tid == 0) {
-    float s = scale[0];
+    float s = scale_old;
     if (update_scale) {
-      for (int w = 1; w < nwarps; ++w) am = s_amax[w] > am ? s_amax[w] : am;
+      for (int w = 1; w < 32; ++w) am = s_amax[w] > am ? s_amax[w] : am;
       s = scale_ema_step(s, __uint_as_float(am), limit, t_quant);
       scale[0] = s;
     }
@@ -509,9 +546,13 @@ extern "C" int qsb_prune_quant_step_params(
   px.world = 1;
   if (group) px = group->dev;
   const float limit = (float)pow(2.0, (double)bits - 1.0);
+  if (pl.fin_count > 0x7fffffffLL || pl.fin_q > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
+  int tpc = 32;  // threads per channel: largest power of two <= min(32, 1024 / channels)
+  while (tpc > 1 && (int64_t)tpc * channels > 1024) tpc >>= 1;
   prune_quant_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
-      magnitude, mask, scale, decimal_out, P, pl.fin_count, pl.fin_q, (int)channels,
-      px, (unsigned long long)step_stamp, count, t_prune, update_magnitude,
+      magnitude, mask, scale, decimal_out, P, (int)pl.fin_count, (int)pl.fin_q,
+      (int)channels, tpc, px, (unsigned long long)step_stamp, count, t_prune,
+      update_magnitude,
       refresh_mask, k, limit, t_quant, update_scale, abssum_out, absmax_out,
       reinterpret_cast<long long *>(step_counter_dev));
   QSB_LAUNCH_CHECK();

@@ -356,7 +356,8 @@ def test_fused_step_kernel_equals_separate_kernels(shape, C):
         amax = torch.empty(C, dtype=torch.float32, device="cuda")
         ops.prune_quant_step_params(st_b["mag"], st_b["mask"], st_b["scale"], st_b["dec"], ws, layout, count, t, 1,
                                     t > 0, k, 8, t, True, abssum_out=asum, absmax_out=amax)
-        assert torch.equal(asum, st["abssum"]) and torch.equal(amax, st["absmax"]), t
+        # the two kernels add the same partials in different (each fixed) orders: fp64 rounding only
+        assert torch.allclose(asum, st["abssum"], rtol=1e-14, atol=0) and torch.equal(amax, st["absmax"]), t
         ws = ops.reduce_partials(x, layout)
         ops.prune_quant_step_params(st_c["mag"], st_c["mask"], st_c["scale"], st_c["dec"], ws, layout, count, 0, 1,
                                     1, k, 8, 0, True, step_counter=counter)
