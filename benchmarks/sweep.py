@@ -128,7 +128,7 @@ def main():
         state["t"] += 1
     report("fused_train_step", 20 * n, step)
 
-    del emask, gx
+    del emask
     # ---------------- config 3: [4096, 4096] channelwise=0
     w = torch.randn(4096, 4096, device=dev) * 0.02
     wy = torch.empty_like(w)
@@ -138,6 +138,17 @@ def main():
     st = ops.reduce_stats(w, (1, 4096, 4096), minmax=True)
     ops.lines_ema_(lines, st["min"], st["max"], 1)
     report("c3_line_fwd", 8 * nw, lambda: ops.fq_line_fwd(w, lines, 4, True, (1, 4096, 4096), out=wy))
+    for seg in (512, 1024, 2048, 4096):
+        ops.set_tuning(3, seg)
+        report("c3_reduce_minmax", 4 * nw, lambda: ops.reduce_stats(w, (1, 4096, 4096), minmax=True), seg_min=seg)
+        report("reduce_abssum_absmax_ch", 4 * n, lambda: ops.reduce_stats(x, layout, abssum=True, absmax=True), seg_min=seg)
+    ops.set_tuning(3, 1024)
+
+    def c3_access():      # the real weight access: reduce -> EMA -> line quant, back to back (W stays in L2)
+        st_ = ops.reduce_stats(w, (1, 4096, 4096), minmax=True)
+        ops.lines_ema_(lines, st_["min"], st_["max"], 2)
+        ops.fq_line_fwd(w, lines, 4, True, (1, 4096, 4096), out=wy)
+    report("c3_weight_access", 12 * nw, c3_access)
 
     # ---------------- config 4: 64 Mi unstructured
     n4 = 1 << 26
@@ -146,7 +157,10 @@ def main():
     yb = torch.empty_like(wt)
     mk = torch.empty(n4, dtype=torch.bool, device=dev)
     report("c4_ema_full", 12 * n4, lambda: ops.magnitude_ema_full_(magf, wt, 3))
-    report("c4_kth_value", 4 * n4, lambda: ops.kth_value(magf, n4 // 2), passes=3)
+    report("c4_kth_value", 4 * n4, lambda: ops.kth_value(magf, n4 // 2), route="sampled pivots, ~1 pass")
+    ops.set_tuning(4, 0)
+    report("c4_kth_value_3pass", 4 * n4, lambda: ops.kth_value(magf, n4 // 2), route="3-pass radix select")
+    ops.set_tuning(4, 1)
     thr = ops.kth_value(magf, n4 // 2)
     report("c4_mask_build_apply", 13 * n4, lambda: ops.mask_build_apply(magf, thr, wt, mk, out=yb))
     report("c4_torch_sort", 4 * n4, lambda: torch.sort(magf))

@@ -58,7 +58,10 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *          grid (default), n > 0 = n CTAs per SM;
  *   key 2: tile order of the one-CTA-per-tile kernels: 1 = last tile first
  *          (default; re-reads the L2-resident tail of a just-touched tensor),
- *          0 = first tile first. */
+ *          0 = first tile first;
+ *   key 3: minimum segment length (elements) of the row reductions (default 1024);
+ *   key 4: 1 = sampled-pivot ~1-pass route of qsb_kth_value for n >= 2^22
+ *          (default), 0 = always the 3-pass radix select. */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and

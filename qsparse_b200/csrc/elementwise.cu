@@ -6,6 +6,10 @@
 #include <math.h>
 
 #include "map_kernel.cuh"
+#include "reduce_internal.cuh"
+namespace qsb {
+void set_select_fast(int v);
+}
 
 namespace qsb {
 
@@ -573,6 +577,14 @@ extern "C" int qsb_set_tuning(int key, int value) {
   }
   if (key == 2) {
     map_tuning().reverse_tiles = value;
+    return 0;
+  }
+  if (key == 3) {
+    set_reduce_seg_min(value);
+    return 0;
+  }
+  if (key == 4) {
+    set_select_fast(value);
     return 0;
   }
   return QSB_E_BADARG;

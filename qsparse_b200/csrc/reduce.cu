@@ -349,6 +349,10 @@ __global__ void tensor_min_kernel(const float *mn, int64_t channels, float *out)
 // Physical warps of the row kernel: SMs x resident CTAs x 8.  The CTA count per
 // SM is fixed (not queried per instantiation) so that the plan — and with it the
 // summation order — only depends on the device, never on which statistics run.
+static int g_reduce_seg_min = 1024;
+int64_t reduce_seg_min() { return g_reduce_seg_min; }
+void set_reduce_seg_min(int v) { g_reduce_seg_min = v >= 256 ? v : 256; }
+
 ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
                             const float *x) {
   ReducePlan p{};
@@ -357,12 +361,19 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
   if (inner >= kRowModeMinInner) {
     p.row_mode = true;
     p.rows = outer * channels;
-    // balanced segments, >= 6 items per physical warp where the rows allow it,
-    // at least 512 elements per segment
+    // balanced segments: aim for >= 6 work items per physical warp, but keep every
+    // segment >= seg_min elements (two rounds of 4 x 256-bit loads per lane) unless the
+    // machine could not be filled otherwise
+    const int64_t seg_min = reduce_seg_min();
+    int64_t spr_max = inner / seg_min > 0 ? inner / seg_min : 1;
     int64_t spr = (6 * warps_phys + p.rows - 1) / p.rows;
-    const int64_t spr_max = inner / 512 > 0 ? inner / 512 : 1;
     if (spr > spr_max) spr = spr_max;
     if (spr < 1) spr = 1;
+    if (p.rows * spr < warps_phys) {
+      spr_max = inner / 512 > 0 ? inner / 512 : 1;
+      spr = (warps_phys + p.rows - 1) / p.rows;
+      if (spr > spr_max) spr = spr_max;
+    }
     int64_t seg = (inner + spr - 1) / spr;
     seg = (seg + 7) / 8 * 8;
     spr = (inner + seg - 1) / seg;

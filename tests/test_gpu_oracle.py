@@ -365,3 +365,37 @@ def test_fused_step_kernel_equals_separate_kernels(shape, C):
         for key in st_a:
             assert torch.equal(st_a[key], st_b[key]), (key, t)
             assert torch.equal(st_a[key], st_c[key]), (key, t, "graph mode")
+
+
+@pytest.mark.parametrize("kind", ["normal", "all_equal", "half_zeros", "two_values", "with_nan"])
+def test_kth_value_fast_route_and_fallback(kind):
+    """n >= 2^22 takes the sampled-pivot route; data with heavy ties overflows the candidate buffer and
+    must fall back to the full radix select on the device.  Both must equal torch.sort bit for bit."""
+    from qsparse_b200 import ops
+    n = (1 << 23) + 77
+    g = torch.Generator(device="cuda").manual_seed(5)
+    v = torch.randn(n, device="cuda", generator=g)
+    if kind == "all_equal":
+        v.fill_(0.125)
+    elif kind == "half_zeros":
+        v = torch.relu(v)
+    elif kind == "two_values":
+        v = (v > 0.3).float() * 2 - 0.5
+    elif kind == "with_nan":
+        v[::1000003] = float("nan")
+    ref = torch.sort(v).values
+    ref_abs = torch.sort(v.abs()).values
+    for k in (0, 1, n // 7, n // 2, (3 * n) // 4, n - 2, n - 1):
+        got = ops.kth_value(v, k)
+        assert torch.equal(got.view(torch.int32), ref[k:k + 1].view(torch.int32)) or \
+            (torch.isnan(got).item() and torch.isnan(ref[k]).item()), (kind, k)
+        got = ops.kth_value(v, k, take_abs=True)
+        assert torch.equal(got, ref_abs[k:k + 1]) or (torch.isnan(got).item() and torch.isnan(ref_abs[k]).item()), \
+            (kind, k, "abs")
+    ops.set_tuning(4, 0)          # 3-pass route only: same answers
+    try:
+        for k in (n // 2, n - 1):
+            a = ops.kth_value(v, k)
+            assert torch.equal(a.view(torch.int32), ref[k:k + 1].view(torch.int32)) or torch.isnan(a).item()
+    finally:
+        ops.set_tuning(4, 1)
