@@ -42,8 +42,9 @@ struct SelectWs {
 // fast-route state (device memory, zeroed before every call)
 struct SelState {
   unsigned long long count_lt;  // keys < lo
-  unsigned long long n_cand;    // keys in [lo, hi] (attempted appends, may exceed cap)
+  unsigned long long n_cand;    // keys in [lo, hi]
   uint32_t lo_key, hi_key;
+  uint32_t overflow;            // some tile had more candidates than its region holds
 };
 
 enum { kModePlain = 0, kModeCandidates = 1, kModeFallback = 2 };
@@ -57,7 +58,8 @@ __device__ __forceinline__ bool sel_fast_valid(const SelState *st, unsigned long
   const unsigned long long lt = st->count_lt, nc = st->n_cand;
   *k_in_cand = k - lt;
   *n_cand = nc;
-  return nc <= cap && k >= lt && (k - lt) < nc;
+  (void)cap;
+  return st->overflow == 0 && k >= lt && (k - lt) < nc;
 }
 
 // Find the bin where the running count first exceeds k.  All threads of the CTA
@@ -67,10 +69,10 @@ template <int BINS>
 __device__ void find_bin(const unsigned long long *hist, unsigned long long k,
                          uint32_t *bin_out, unsigned long long *k_out) {
   constexpr int PER = (BINS + QSB_THREADS - 1) / QSB_THREADS;
-  __shared__ unsigned long long s_part[QSB_THREADS];
+  __shared__ unsigned long long s_warp[QSB_THREADS / 32];
   __shared__ uint32_t s_bin;
   __shared__ unsigned long long s_k;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned long long local[PER];
   unsigned long long sum = 0;
 #pragma unroll
@@ -79,15 +81,21 @@ __device__ void find_bin(const unsigned long long *hist, unsigned long long k,
     local[i] = (b < BINS) ? hist[b] : 0ull;
     sum += local[i];
   }
-  s_part[tid] = sum;
+  // block-wide exclusive scan of the per-thread sums (warp shuffles + one smem hop)
+  unsigned long long incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
   if (tid == 0) {
     s_bin = BINS - 1;
     s_k = 0;
   }
   __syncthreads();
-  // exclusive prefix of this thread's chunk (256 sequential adds: negligible)
-  unsigned long long before = 0;
-  for (int j = 0; j < tid; ++j) before += s_part[j];
+  unsigned long long before = incl - sum;
+  for (int w = 0; w < warp; ++w) before += s_warp[w];
   if (k >= before && k < before + sum) {
     unsigned long long run = before;
 #pragma unroll
@@ -266,96 +274,64 @@ static int launch_hist(const float *v, int64_t n, int64_t k, const SelectWs &ws,
 }
 
 // ---------------------------------------------------------------------------
-// fast route, step 1: pivots from a sample (one CTA, 1024 threads, 64 KB of keys)
+// fast route, step 1: pivots from a sample (one CTA, 1024 threads): 16384 evenly
+// spaced keys, bitonic sort in 64 KB of shared memory, pivots = two order statistics
 // ---------------------------------------------------------------------------
 constexpr int kSampleSize = 16384;
-
-__device__ __forceinline__ uint32_t sel_key(float f, bool take_abs) {
-  return float_to_key(take_abs ? fabsf(f) : f);
-}
-
-// rank-r key (0-based) of keys[0..m) in shared memory; all 1024 threads call it
-__device__ uint32_t smem_select(const uint32_t *keys, int m, int r, uint32_t *hist,
-                                uint32_t *bcast) {
-  uint32_t prefix = 0, mask_hi = 0;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      const uint32_t key = keys[i];
-      if ((key & mask_hi) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t local[8], sum = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        local[b] = hist[threadIdx.x * 8 + b];
-        sum += local[b];
-      }
-      uint32_t incl = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)threadIdx.x >= o) incl += t;
-      }
-      uint32_t run = incl - sum;  // keys in the bins before this lane's
-      if ((uint32_t)r >= run && (uint32_t)r < incl) {
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if ((uint32_t)r < run + local[b]) {
-            bcast[0] = threadIdx.x * 8 + b;
-            bcast[1] = (uint32_t)r - run;
-            break;
-          }
-          run += local[b];
-        }
-      }
-    }
-    __syncthreads();
-    prefix |= bcast[0] << shift;
-    mask_hi |= 0xffu << shift;
-    r = (int)bcast[1];
-    __syncthreads();
-  }
-  return prefix;
-}
 
 __global__ void __launch_bounds__(1024)
     select_sample_kernel(const float *__restrict__ v, int64_t n, int take_abs, int r_lo,
                          int r_hi, SelState *st) {
   extern __shared__ uint32_t s_keys[];  // kSampleSize keys
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_bcast[2];
   const int64_t stride = n / kSampleSize;
-  for (int i = threadIdx.x; i < kSampleSize; i += blockDim.x)
-    s_keys[i] = sel_key(v[(int64_t)i * stride + (stride >> 1)], take_abs != 0);
+  for (int i = threadIdx.x; i < kSampleSize; i += blockDim.x) {
+    const float f = v[(int64_t)i * stride + (stride >> 1)];
+    s_keys[i] = float_to_key(take_abs ? fabsf(f) : f);
+  }
   __syncthreads();
-  const uint32_t lo = (r_lo < 0) ? 0u : smem_select(s_keys, kSampleSize, r_lo, s_hist, s_bcast);
-  const uint32_t hi =
-      (r_hi >= kSampleSize) ? 0xffffffffu : smem_select(s_keys, kSampleSize, r_hi, s_hist, s_bcast);
+  for (int size = 2; size <= kSampleSize; size <<= 1) {
+    for (int step = size >> 1; step > 0; step >>= 1) {
+      for (int t = threadIdx.x; t < kSampleSize / 2; t += blockDim.x) {
+        const int i = ((t / step) * step * 2) + (t % step);  // lower index of the pair
+        const int j = i + step;
+        const bool up = ((i & size) == 0);
+        const uint32_t a = s_keys[i], b = s_keys[j];
+        if ((a > b) == up) {
+          s_keys[i] = b;
+          s_keys[j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
   if (threadIdx.x == 0) {
-    st->lo_key = lo;
-    st->hi_key = hi;
+    st->lo_key = (r_lo < 0) ? 0u : s_keys[r_lo];
+    st->hi_key = (r_hi >= kSampleSize) ? 0xffffffffu : s_keys[r_hi];
   }
 }
 
 // ---------------------------------------------------------------------------
-// fast route, step 2: count keys < lo, compact keys in [lo, hi].  One CTA per tile.
-// The candidates are stored as values (|v| already applied), so the candidate select
-// runs on plain floats.
+// fast route, step 2: ONE streaming pass.  Each CTA owns a tile of 4096 elements and
+// a private region of kRegion candidate slots: it counts its keys < lo and compacts
+// its keys in [lo, hi] into the region — no atomics, no ordering between CTAs.
+// The candidates are stored as values (|v| already applied).
 // ---------------------------------------------------------------------------
+constexpr int kRegion = 512;  // candidate slots per 4096-element tile (12.5 %; ~4 % expected)
+
 template <int V, bool ABS>
 __global__ void __launch_bounds__(QSB_THREADS)
-    select_partition_kernel(const float *__restrict__ v, int64_t n, SelState *st,
-                            float *__restrict__ cand, int64_t cap) {
+    select_partition_kernel(const float *__restrict__ v, int64_t n, const SelState *st,
+                            float *__restrict__ cand, uint32_t *__restrict__ cnt,
+                            uint32_t *__restrict__ lt_arr) {
   constexpr int U = 2;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
-  __shared__ unsigned long long s_lt[QSB_THREADS / 32];
+  static_assert(kTile == 4096, "region bookkeeping assumes 4096-element tiles");
+  __shared__ uint32_t s_nc[QSB_THREADS / 32], s_lt[QSB_THREADS / 32];
   const uint32_t lo = st->lo_key, span = st->hi_key - st->lo_key;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_main = (n / V) * V;
-  const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)tid * V;
+  const int64_t t0 = (int64_t)blockIdx.x * kTile;
+  const int64_t base = t0 + (int64_t)tid * V;
   VecF<V> x[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -381,7 +357,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
   // the last n % V elements: the owning CTA's first threads, scalar
   float tail_val = 0.f;
   bool tail_c = false;
-  if (base - (int64_t)tid * V <= n_main && n_main < base - (int64_t)tid * V + kTile) {
+  if (t0 <= n_main && n_main < t0 + kTile) {
     const int64_t e = n_main + tid;
     if (e < n) {
       tail_val = ABS ? fabsf(v[e]) : v[e];
@@ -391,40 +367,122 @@ __global__ void __launch_bounds__(QSB_THREADS)
       nc += tail_c;
     }
   }
-  // warp-aggregated append: one atomic per warp that has candidates
+  // CTA-wide exclusive scan of the candidate counts
   uint32_t incl = nc;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total) {
-    unsigned long long wbase = 0;
-    if (lane == 31) wbase = atomicAdd(&st->n_cand, (unsigned long long)total);
-    wbase = __shfl_sync(0xffffffffu, wbase, 31);
-    unsigned long long pos = wbase + (incl - nc);
-    if (nc) {
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < V; ++j)
-          if (cmask & (1u << (u * V + j))) {
-            if (pos < (unsigned long long)cap) cand[pos] = ABS ? fabsf(x[u].v[j]) : x[u].v[j];
-            ++pos;
-          }
-      if (tail_c && pos < (unsigned long long)cap) cand[pos] = tail_val;
-    }
-  }
-  // keys < lo: one atomic per CTA
-  unsigned long long wl = warp_reduce((unsigned long long)lt,
-                                      [](unsigned long long a, unsigned long long b) { return a + b; });
-  if (lane == 0) s_lt[tid >> 5] = wl;
+  const uint32_t wlt = warp_reduce(lt, [](uint32_t a, uint32_t b) { return a + b; });
+  if (lane == 31) s_nc[warp] = incl;
+  if (lane == 0) s_lt[warp] = wlt;
   __syncthreads();
+  uint32_t pos = incl - nc;
+  for (int w = 0; w < warp; ++w) pos += s_nc[w];
   if (tid == 0) {
-    unsigned long long t = 0;
-    for (int w = 0; w < QSB_THREADS / 32; ++w) t += s_lt[w];
-    if (t) atomicAdd(&st->count_lt, t);
+    uint32_t total = 0, tlt = 0;
+    for (int w = 0; w < QSB_THREADS / 32; ++w) {
+      total += s_nc[w];
+      tlt += s_lt[w];
+    }
+    cnt[blockIdx.x] = total;  // > kRegion marks an overflow
+    lt_arr[blockIdx.x] = tlt;
+  }
+  if (nc) {
+    float *region = cand + (int64_t)blockIdx.x * kRegion;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (cmask & (1u << (u * V + j))) {
+          if (pos < (uint32_t)kRegion) region[pos] = ABS ? fabsf(x[u].v[j]) : x[u].v[j];
+          ++pos;
+        }
+    if (tail_c && pos < (uint32_t)kRegion) region[pos] = tail_val;
+  }
+}
+
+// step 3: totals (one CTA): count_lt, n_cand, overflow
+__global__ void __launch_bounds__(1024)
+    select_decide_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ lt_arr,
+                         int64_t tiles, SelState *st) {
+  __shared__ unsigned long long s_a[32], s_b[32];
+  __shared__ uint32_t s_o[32];
+  unsigned long long a = 0, b = 0;
+  uint32_t o = 0;
+  for (int64_t i = threadIdx.x; i < tiles; i += blockDim.x) {
+    const uint32_t c = cnt[i];
+    a += lt_arr[i];
+    b += c;
+    o |= (c > (uint32_t)kRegion);
+  }
+  a = warp_reduce(a, [](unsigned long long x, unsigned long long y) { return x + y; });
+  b = warp_reduce(b, [](unsigned long long x, unsigned long long y) { return x + y; });
+  o = __any_sync(0xffffffffu, o);
+  if ((threadIdx.x & 31) == 0) {
+    s_a[threadIdx.x >> 5] = a;
+    s_b[threadIdx.x >> 5] = b;
+    s_o[threadIdx.x >> 5] = o;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = b = 0;
+    o = 0;
+    for (int w = 0; w < 32; ++w) {
+      a += s_a[w];
+      b += s_b[w];
+      o |= s_o[w];
+    }
+    st->count_lt = a;
+    st->n_cand = b;
+    st->overflow = o;
+  }
+}
+
+// step 4: radix-select histogram passes over the candidate regions, a warp per region
+template <int PASS>
+__global__ void __launch_bounds__(QSB_THREADS)
+    select_hist_regions_kernel(const float *__restrict__ cand, const uint32_t *__restrict__ cnt,
+                               int64_t tiles, int64_t k, SelectWs ws, const SelState *st) {
+  unsigned long long kc, nc;
+  if (!sel_fast_valid(st, (unsigned long long)k, 0, &kc, &nc)) return;
+  constexpr int kSmemWords = (PASS == 0) ? kBins0 * 32 : kBins1;
+  __shared__ uint32_t s_hist[kSmemWords];
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < kSmemWords; i += QSB_THREADS) s_hist[i] = 0;
+  PassConst pc{0, 0};
+  if constexpr (PASS >= 1) {
+    unsigned long long kk;
+    uint32_t b0;
+    find_bin<kBins0>(ws.hist0, kc, &b0, &kk);
+    uint32_t prefix = b0;
+    if constexpr (PASS == 2) {
+      uint32_t b1;
+      find_bin<kBins1>(ws.hist1, kk, &b1, &kk);
+      prefix = (b0 << 12) | b1;
+    }
+    pc = make_pass_const(PASS, prefix);
+  }
+  __syncthreads();
+  const int64_t warps_total = (int64_t)gridDim.x * (QSB_THREADS / 32);
+  for (int64_t r = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (tid >> 5); r < tiles; r += warps_total) {
+    const uint32_t c = cnt[r];
+    const float *region = cand + r * kRegion;
+    for (uint32_t i = lane; i < c; i += 32) count_value<PASS, false>(region[i], pc, s_hist, lane);
+  }
+  __syncthreads();
+  if constexpr (PASS == 0) {
+    unsigned long long sum = 0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) sum += s_hist[tid * 32 + ((l + tid) & 31)];
+    if (sum) atomicAdd(&ws.hist0[tid], sum);
+  } else {
+    unsigned long long *g = (PASS == 1) ? ws.hist1 : ws.hist2;
+    for (int b = tid; b < kBins1; b += QSB_THREADS) {
+      const uint32_t c = s_hist[b];
+      if (c) atomicAdd(&g[b], (unsigned long long)c);
+    }
   }
 }
 
@@ -435,7 +493,7 @@ constexpr int64_t kSelectHeaderBytes = 2 * kHistBytes + 256;
 constexpr int64_t kFastMinN = 1 << 22;
 static int g_select_fast = 1;  // tuning key 4
 
-static int64_t select_cap(int64_t n) { return n >= kFastMinN ? n / 8 + 4096 : 0; }
+static int64_t select_tiles(int64_t n) { return n >= kFastMinN ? (n + 4095) / 4096 : 0; }
 
 void set_select_fast(int v) { g_select_fast = v; }
 
@@ -444,7 +502,9 @@ void set_select_fast(int v) { g_select_fast = v; }
 using namespace qsb;
 
 extern "C" int64_t qsb_kth_workspace_bytes(int64_t n) {
-  return kSelectHeaderBytes + 256 + select_cap(n) * (int64_t)sizeof(float) + 32;
+  // header | cnt[tiles] | lt[tiles] | candidate regions [tiles][512]
+  const int64_t tiles = select_tiles(n);
+  return kSelectHeaderBytes + 256 + tiles * 8 + 64 + tiles * kRegion * (int64_t)sizeof(float) + 32;
 }
 
 template <int V, bool ABS>
@@ -474,13 +534,16 @@ extern "C" int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
   wc.hist1 = wc.hist0 + kBins0;
   wc.hist2 = wc.hist1 + kBins1;
   SelState *st = reinterpret_cast<SelState *>(wc.hist2 + kBins2);
-  float *cand = reinterpret_cast<float *>((base + kSelectHeaderBytes + 31) / 32 * 32);
+  const int64_t tiles = select_tiles(n);
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(base + kSelectHeaderBytes);
+  uint32_t *lt_arr = cnt + tiles;
+  float *cand = reinterpret_cast<float *>(
+      (reinterpret_cast<uintptr_t>(lt_arr + tiles) + 31) / 32 * 32);
   QSB_CUDA_TRY(cudaMemsetAsync(ws.hist0, 0, kSelectHeaderBytes, stream));
   const bool v32 = aligned_to(v, 32);
   const bool fast = g_select_fast && n >= kFastMinN && v32;
   int rc;
   if (fast) {
-    const int64_t cap = select_cap(n);
     // sample ranks bracketing k: +-5 sigma of the binomial rank error, +3
     const double m = (double)kSampleSize, p = (double)k / (double)n;
     const double delta = 5.0 * sqrt(m * p * (1.0 - p)) + 3.0;
@@ -495,20 +558,28 @@ extern "C" int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
     select_sample_kernel<<<1, 1024, kSampleSize * sizeof(uint32_t), stream>>>(
         v, n, take_abs, r_lo, r_hi, st);
     QSB_LAUNCH_CHECK();
-    constexpr int64_t kTile = (int64_t)QSB_THREADS * 8 * 2;
-    const int64_t tiles = (n + kTile - 1) / kTile;
     if (take_abs)
-      select_partition_kernel<8, true><<<(unsigned)tiles, QSB_THREADS, 0, stream>>>(v, n, st, cand, cap);
+      select_partition_kernel<8, true><<<(unsigned)tiles, QSB_THREADS, 0, stream>>>(v, n, st, cand, cnt, lt_arr);
     else
-      select_partition_kernel<8, false><<<(unsigned)tiles, QSB_THREADS, 0, stream>>>(v, n, st, cand, cap);
+      select_partition_kernel<8, false><<<(unsigned)tiles, QSB_THREADS, 0, stream>>>(v, n, st, cand, cnt, lt_arr);
     QSB_LAUNCH_CHECK();
-    // continuation A: exact select on the candidates (runs only if rank k is inside)
-    if ((rc = run_passes<8, false>(cand, cap, k, wc, stream, st, kModeCandidates, cap))) return rc;
+    select_decide_kernel<<<1, 1024, 0, stream>>>(cnt, lt_arr, tiles, st);
+    QSB_LAUNCH_CHECK();
+    // continuation A: exact select on the candidate regions (runs only if rank k is inside)
+    {
+      int64_t grid = (int64_t)device_props().sm_count * 4;
+      const int64_t need = (tiles + QSB_THREADS / 32 - 1) / (QSB_THREADS / 32);
+      if (grid > need) grid = need;
+      select_hist_regions_kernel<0><<<(unsigned)grid, QSB_THREADS, 0, stream>>>(cand, cnt, tiles, k, wc, st);
+      select_hist_regions_kernel<1><<<(unsigned)grid, QSB_THREADS, 0, stream>>>(cand, cnt, tiles, k, wc, st);
+      select_hist_regions_kernel<2><<<(unsigned)grid, QSB_THREADS, 0, stream>>>(cand, cnt, tiles, k, wc, st);
+      QSB_LAUNCH_CHECK();
+    }
     // continuation B: the full select (runs only if A is not valid)
-    rc = take_abs ? run_passes<8, true>(v, n, k, ws, stream, st, kModeFallback, cap)
-                  : run_passes<8, false>(v, n, k, ws, stream, st, kModeFallback, cap);
+    rc = take_abs ? run_passes<8, true>(v, n, k, ws, stream, st, kModeFallback, 0)
+                  : run_passes<8, false>(v, n, k, ws, stream, st, kModeFallback, 0);
     if (rc) return rc;
-    select_final_kernel<<<1, QSB_THREADS, 0, stream>>>(k, ws, wc, st, cap, thr_out_dev);
+    select_final_kernel<<<1, QSB_THREADS, 0, stream>>>(k, ws, wc, st, 0, thr_out_dev);
     QSB_LAUNCH_CHECK();
     return 0;
   }
