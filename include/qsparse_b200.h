@@ -61,7 +61,13 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *          0 = first tile first;
  *   key 3: minimum segment length (elements) of the row reductions (default 1024);
  *   key 4: 1 = sampled-pivot ~1-pass route of qsb_kth_value for n >= 2^22
- *          (default), 0 = always the 3-pass radix select. */
+ *          (default), 0 = always the 3-pass radix select;
+ *   key 6: 256-bit loads in flight per thread in the select's partition pass
+ *          (2, 4 = default);
+ *   key 7: samples per sampler thread of the select (1, 2 = default, 4 ->
+ *          8 Ki, 16 Ki, 32 Ki samples);
+ *   key 8: 1 = the kernels of one select are chained by programmatic dependent
+ *          launch (default), 0 = ordinary stream order. */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and

@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC,-O2,-fno-fast-math",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("QSB_EXTRA_NVCC_FLAGS", "").split()   # development only (e.g. -DQSB_SELECT_TIMING)
 
 
 def find_nvcc() -> str:

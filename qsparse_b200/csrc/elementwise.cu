@@ -9,6 +9,9 @@
 #include "reduce_internal.cuh"
 namespace qsb {
 void set_select_fast(int v);
+void set_select_partition_u(int v);
+void set_select_sample_per(int v);
+void set_select_pdl(int v);
 }
 
 namespace qsb {
@@ -585,6 +588,18 @@ extern "C" int qsb_set_tuning(int key, int value) {
   }
   if (key == 4) {
     set_select_fast(value);
+    return 0;
+  }
+  if (key == 6) {
+    set_select_partition_u(value);
+    return 0;
+  }
+  if (key == 7) {
+    set_select_sample_per(value);
+    return 0;
+  }
+  if (key == 8) {
+    set_select_pdl(value);
     return 0;
   }
   return QSB_E_BADARG;

@@ -38,6 +38,35 @@ inline bool aligned_to(const void *p, uintptr_t a) {
 }
 
 // ---------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become
+// resident while its predecessor in the stream is still running; it must execute
+// pdl_wait() before it touches anything the predecessor writes (the wait returns when the
+// predecessor grid has completed and its writes are visible).  A predecessor calls
+// pdl_trigger() once it no longer minds the successor's CTAs occupying free SM resources.
+// Both are no-ops in a kernel launched the ordinary way.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // vector global-memory access.  V floats per access: 8 -> one 256-bit
 // LDG/STG (new on sm_100), 4 -> 128-bit, 1 -> scalar.
 // Loads: L1::no_allocate (every element is touched once per kernel); not .nc,

@@ -17,20 +17,30 @@
 // answer, so a select is memset + 3 launches.  Counters are 64-bit (n may exceed 2^32).
 //
 // Large inputs (n >= 2^22) first try a ~1-pass route:
-//   sample    4096 evenly spaced values; their exact ranks inside the sample are
-//             counted by 128 CTAs; two pivots lo <= hi = the order statistics +-5 sigma
-//             (binomial rank error) around rank k * 4096 / n;
-//   partition ONE streaming pass over v: every CTA counts its values < lo and compacts
-//             its values in [lo, hi] (~8 %) into a private 512-slot region of the
-//             candidate buffer — no atomics on the critical path, totals by RED;
-//   passes    the same 3 radix passes, but over the candidate regions (a warp per
-//             region) with rank k - count_lt.
-// If rank k is not inside [lo, hi] or a region overflows (heavy ties), the 3 passes run
-// over v itself.  The route is chosen ON THE DEVICE in the prologue of each pass from
-// the counters — one launch per pass either way, no host synchronisation.
+//   sample    ONE CTA gathers 8192 evenly spaced values into shared memory and radix-
+//             selects (top 22 key bits, in shared memory) the two order statistics
+//             +-4.5 sigma (binomial rank error) around rank k * 8192 / n -> pivots
+//             lo <= hi (floor / ceiling of the 22-bit prefixes).  The same CTA zeroes
+//             the workspace header while its gathers are in flight (no memset node).
+//   partition ONE streaming pass over v: every CTA counts its values < lo and appends
+//             its values in [lo, hi] (~5 %) to a dense candidate array (one cursor
+//             atomic per CTA; totals by fire-and-forget RED).
+//   passes    radix select over the candidates on the RANGE-RELATIVE key
+//             rel = key - key(lo) < 2^W, W = bits of key(hi) - key(lo) (~20): digits of
+//             11 bits from bit W down, so two passes over the (L2-resident) candidates
+//             finish W <= 22 and a third finishes any W.  Exact for any data: ties,
+//             +-0 (canonicalised to +0), infinities.
+// If rank k is not inside [lo, hi] (adversarial order) or the candidates do not fit
+// (n/8 slots), the 3 generic passes run over v itself.  Fast and generic passes share
+// the same three launches: the route is chosen ON THE DEVICE in the prologue of each
+// pass from the counters — no host synchronisation, no extra launches.
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stddef.h>
 
 #include "qsb_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace qsb {
 
@@ -38,10 +48,18 @@ constexpr int kBits0 = 8, kBits1 = 12, kBits2 = 12;
 constexpr int kBins0 = 1 << kBits0, kBins1 = 1 << kBits1, kBins2 = 1 << kBits2;
 static_assert(kBins0 == QSB_THREADS, "pass-0 merge maps one thread to one bin");
 
-constexpr int kSampleSize = 4096;
-constexpr int kSampleParts = 8;    // threads that share the rank count of one sample
-constexpr int kRegion = 512;       // candidate slots per 4096-element tile (12.5 %)
+// fast route
+constexpr int kSampleThreads = 1024;
+constexpr int kSampleCtas = 8;  // one thread-block cluster; PER samples per thread
+constexpr int kFastBits = 11, kFastBins = 1 << kFastBits;
+constexpr int kCandShift = 3;      // candidate slots = n >> 3 (12.5 %)
+constexpr int kSegs = 32;          // independent candidate segments (one packed counter each)
+constexpr int kCtasPerSeg = 18;
+constexpr int kFastCtas = kSegs * kCtasPerSeg;  // CTAs of a pass that work on the candidates
+constexpr int kSegStride = 16;     // counters are 128 B apart: same-line atomics serialise in L2
 constexpr int64_t kFastMinN = 1 << 22;
+constexpr uint32_t kKeyNegInf = 0x007fffffu, kKeyPosInf = 0xff800000u;
+constexpr uint32_t kKeyNegZero = 0x7fffffffu, kKeyPosZero = 0x80000000u;
 
 struct SelectWs {
   unsigned long long *hist0;  // [256]
@@ -49,28 +67,96 @@ struct SelectWs {
   unsigned long long *hist2;  // [4096]
 };
 
-// device-side state of one select call (zeroed by the memset that starts it)
+// device-side state of one select call (zeroed at its start)
 struct SelState {
-  unsigned long long count_lt;  // values < lo            (fast route)
-  unsigned long long n_cand;    // values in [lo, hi]     (fast route)
   float lo, hi;                 // pivots
-  uint32_t overflow;            // a tile had more candidates than its region holds
-  uint32_t done;                // CTAs of pass 2 that have finished (ticket)
+  uint32_t lo_key;              // key(lo); candidates have key - lo_key < 2^width
+  uint32_t shift_a;             // digit A = rel >> shift_a
+  uint32_t shift_b;             // digit B = (rel >> shift_b) & ..
+  uint32_t width;               // W
+  uint32_t tie_lo;              // values == lo are counted, not stored (heavy ties at lo, or lo == hi)
+  uint32_t route;               // first pass's verdict: 1 = radix passes over the candidates,
+                                // 2 = generic passes over v, 3 = the answer is lo (written)
+  unsigned long long count_below;  // values < lo plus (ties) values == lo   (written by the first pass)
+  uint32_t done;                // generic pass 2 ticket
+  uint32_t done_b, done_c;      // fast pass tickets
+};
+static_assert(offsetof(SelState, lo) == 0 && offsetof(SelState, hi) == 4, "the partition kernel loads both pivots at once");
+
+#ifdef QSB_SELECT_TIMING
+#define QSB_TICK(st, slot)                                                      \
+  do {                                                                          \
+    if (threadIdx.x == 0 && blockIdx.x == 0)                                    \
+      reinterpret_cast<long long *>(st)[16 + (slot)] = clock64();               \
+  } while (0)
+#else
+#define QSB_TICK(st, slot) do {} while (0)
+#endif
+
+// Candidates live in kSegs dense segments.  Segment s has ONE packed 64-bit counter
+// (segctr[s * kSegStride]): low 32 bits = candidates appended (also the append cursor),
+// high 32 bits = values < lo seen by the CTAs that use the segment — a partition CTA
+// issues a single atomic, and the kSegs counters sit in different 128-byte lines.  The
+// next word of the line counts the values == lo when those are not stored (tie_lo).
+struct FastBufs {
+  const SelState *st;              // nullptr: there is no fast route (small n)
+  const float *cand;               // [kSegs][seg_cap], 32-byte aligned, |.| already applied
+  const unsigned long long *segctr;
+  uint32_t *fh;                    // [3][kFastBins] histograms of the range-relative digits
+  uint32_t seg_cap;                // slots per segment (multiple of 8)
 };
 
-// Is rank k inside the candidate set, and did every candidate fit?  Evaluated by every
-// CTA of every pass from the same counters, so they always agree.
-__device__ __forceinline__ bool fast_route_valid(const SelState *st, unsigned long long k,
-                                                 unsigned long long *k_in_cand) {
-  const unsigned long long lt = st->count_lt, nc = st->n_cand;
-  *k_in_cand = k - lt;
-  return st->overflow == 0 && k >= lt && (k - lt) < nc;
+// Totals of the packed counters -> where is rank k?  Pass 0: every CTA derives the route
+// from the counters (CTA 0 also records it, and writes the answer when it is lo itself);
+// later passes read the record.  Returns the route; *k_in_cand = rank among the candidates.
+__device__ uint32_t fast_route(const FastBufs &fb, SelState *st_rw, int pass,
+                               unsigned long long k, unsigned long long *k_in_cand,
+                               float *thr_out) {
+  __shared__ unsigned long long s_below;
+  __shared__ uint32_t s_route;
+  if (pass > 0) {
+    *k_in_cand = k - fb.st->count_below;
+    return fb.st->route;
+  }
+  if (threadIdx.x < 32) {
+    static_assert(kSegs == 32, "one lane per segment");
+    const ulonglong2 c2 =
+        __ldcg(reinterpret_cast<const ulonglong2 *>(fb.segctr + threadIdx.x * kSegStride));
+    const uint32_t cand = (uint32_t)c2.x;
+    unsigned long long lt = c2.x >> 32, eq = c2.y, nc = cand;
+    int over = cand > fb.seg_cap;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lt += __shfl_xor_sync(0xffffffffu, lt, o);
+      eq += __shfl_xor_sync(0xffffffffu, eq, o);
+      nc += __shfl_xor_sync(0xffffffffu, nc, o);
+      over |= __shfl_xor_sync(0xffffffffu, over, o);
+    }
+    if (threadIdx.x == 0) {
+      uint32_t route = 2;
+      if (k >= lt) {
+        if (k - lt < eq) route = 3;
+        else if (!over && k - lt - eq < nc) route = 1;
+      }
+      s_below = lt + eq;
+      s_route = route;
+      if (blockIdx.x == 0) {
+        st_rw->count_below = lt + eq;
+        st_rw->route = route;
+        if (route == 3) *thr_out = fb.st->lo;
+      }
+    }
+  }
+  __syncthreads();
+  *k_in_cand = k - s_below;
+  return s_route;
 }
 
 // Find the bin where the running count first exceeds k; result broadcast to the CTA.
-template <int BINS>
-__device__ void find_bin(const unsigned long long *hist, unsigned long long k,
-                         uint32_t *bin_out, unsigned long long *k_out) {
+// REPS > 1: the histogram is the sum of REPS replicas, BINS apart.
+template <int BINS, int REPS = 1, class T>
+__device__ void find_bin(const T *hist, unsigned long long k, uint32_t *bin_out,
+                         unsigned long long *k_out) {
   constexpr int PER = (BINS + QSB_THREADS - 1) / QSB_THREADS;
   __shared__ unsigned long long s_warp[QSB_THREADS / 32];
   __shared__ uint32_t s_bin;
@@ -78,12 +164,33 @@ __device__ void find_bin(const unsigned long long *hist, unsigned long long k,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned long long local[PER];
   unsigned long long sum = 0;
+  // L2 loads (__ldcg): the counters were written by other CTAs' atomics.  Every CTA of a
+  // pass reads the same few lines, so use the widest loads (fewest requests per line).
+  if constexpr (sizeof(T) == 4 && PER % 4 == 0) {
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int b = tid * PER + i;
-    local[i] = (b < BINS) ? __ldcg(hist + b) : 0ull;  // L2: written by other CTAs' atomics
-    sum += local[i];
+    for (int i = 0; i < PER; i += 4) {
+      local[i] = local[i + 1] = local[i + 2] = local[i + 3] = 0;
+#pragma unroll
+      for (int r = 0; r < REPS; ++r) {
+        const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(hist + r * BINS + tid * PER + i));
+        local[i] += q.x, local[i + 1] += q.y, local[i + 2] += q.z, local[i + 3] += q.w;
+      }
+    }
+  } else if constexpr (sizeof(T) == 8 && PER % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < PER; i += 2) {
+      const ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(hist + tid * PER + i));
+      local[i] = q.x, local[i + 1] = q.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int b = tid * PER + i;
+      local[i] = (b < BINS) ? (unsigned long long)__ldcg(hist + b) : 0ull;
+    }
   }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) sum += local[i];
   unsigned long long incl = sum;  // block-wide exclusive scan: shuffles + one smem hop
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -155,36 +262,143 @@ __device__ __forceinline__ void count_value(float f, const PassConst &pc,
 }
 
 // ---------------------------------------------------------------------------
+// fast route: passes over the candidate segments
+// ---------------------------------------------------------------------------
+// key of a candidate; -0.0 was never stored as such but be safe: x + 0 canonicalises it
+__device__ __forceinline__ uint32_t cand_rel(float f, uint32_t lo_key) {
+  const uint32_t b = __float_as_uint(f + 0.0f);
+  const uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return key - lo_key;
+}
+
+// STAGE 0: digit A of every candidate.  STAGE 1: digit B of those whose digit A is the
+// selected one.  STAGE 2: the low bits of those whose digits A and B are selected.
+// (Counting digit A inside the partition kernel was tried twice and lost: atomic
+// transactions to one 128-byte line serialise at ~2.6 ns in L2, so one RED per candidate
+// (2.4 M on 64 lines) cost +100 us, and a per-CTA shared-memory histogram flushed with
+// line-coalesced REDs (8192 CTAs x 32 lines) cost +15 us against the 10 us pass it saves.)
+template <int STAGE>
+__device__ __forceinline__ void fast_count(float f, uint32_t lo_key, uint32_t shift,
+                                           uint32_t want_shift, uint32_t want,
+                                           uint32_t mask, uint32_t *s_hist) {
+  const uint32_t rel = cand_rel(f, lo_key);
+  if constexpr (STAGE == 0) {
+    atomicAdd(&s_hist[rel >> shift], 1u);
+  } else {
+    if ((rel >> want_shift) == want) atomicAdd(&s_hist[(rel >> shift) & mask], 1u);
+  }
+}
+
+template <int STAGE>
+__device__ void fast_pass(const FastBufs &fb, unsigned long long kc, SelState *st_rw,
+                          float *thr_out, uint32_t *s_hist, int *s_last) {
+  const SelState *st = fb.st;
+  const int tid = threadIdx.x;
+  QSB_TICK(st_rw, 8 + STAGE * 8 + 1);
+  const uint32_t lo_key = st->lo_key, shift_a = st->shift_a, shift_b = st->shift_b;
+  if (STAGE == 2 && shift_b == 0) return;  // stage 1 already wrote the answer
+  // a multiple of kSegs CTAs works on the candidates (the grid has >= kSegs CTAs: n >= 2^22)
+  const unsigned nctas = gridDim.x < (unsigned)kFastCtas ? gridDim.x / kSegs * kSegs : (unsigned)kFastCtas;
+  if (blockIdx.x >= nctas) return;
+  uint32_t b0 = 0, b1 = 0;
+  unsigned long long k1 = kc, k2 = 0;
+  if constexpr (STAGE >= 1) {
+    find_bin<kFastBins>(fb.fh, kc, &b0, &k1);
+    if (shift_a == 0) {  // the whole range fitted digit A
+      if (STAGE == 1 && blockIdx.x == 0 && tid == 0) *thr_out = key_to_float(lo_key + b0);
+      return;
+    }
+  }
+  if constexpr (STAGE == 2) find_bin<kFastBins>(fb.fh + kFastBins, k1, &b1, &k2);
+  const uint32_t bits_b = shift_a - shift_b;
+  uint32_t shift, want_shift = 0, want = 0, mask = 0;
+  if constexpr (STAGE == 0) {
+    shift = shift_a;
+  } else if constexpr (STAGE == 1) {
+    shift = shift_b, want_shift = shift_a, want = b0, mask = (1u << bits_b) - 1u;
+  } else {
+    shift = 0, want_shift = shift_b, want = (b0 << bits_b) | b1, mask = (1u << shift_b) - 1u;
+  }
+  QSB_TICK(st_rw, 8 + STAGE * 8 + 2);
+  for (int i = tid; i < kFastBins; i += QSB_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  // kCtasPerSeg CTAs share one segment
+  const int seg = blockIdx.x % kSegs, part = blockIdx.x / kSegs, parts = nctas / kSegs;
+  const uint32_t nc = (uint32_t)__ldcg(fb.segctr + seg * kSegStride), n4 = nc >> 2;
+  const float *cseg = fb.cand + (size_t)seg * fb.seg_cap;
+  const float4 *c4 = reinterpret_cast<const float4 *>(cseg);
+  const uint32_t step = (uint32_t)parts * QSB_THREADS;
+  uint32_t i = (uint32_t)part * QSB_THREADS + tid;
+  for (; i < n4; i += 4 * step) {  // four 128-bit loads in flight
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * step < n4) q[u] = c4[i + u * step];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * step < n4) {
+        fast_count<STAGE>(q[u].x, lo_key, shift, want_shift, want, mask, s_hist);
+        fast_count<STAGE>(q[u].y, lo_key, shift, want_shift, want, mask, s_hist);
+        fast_count<STAGE>(q[u].z, lo_key, shift, want_shift, want, mask, s_hist);
+        fast_count<STAGE>(q[u].w, lo_key, shift, want_shift, want, mask, s_hist);
+      }
+  }
+  if (part == 0 && tid < (int)(nc & 3))
+    fast_count<STAGE>(cseg[(n4 << 2) + tid], lo_key, shift, want_shift, want, mask, s_hist);
+  __syncthreads();
+  QSB_TICK(st_rw, 8 + STAGE * 8 + 3);
+  uint32_t *g = fb.fh + STAGE * kFastBins;
+  for (int b = tid; b < kFastBins; b += QSB_THREADS) {
+    const uint32_t c = s_hist[b];
+    if (c) atomicAdd(&g[b], c);  // result unused: RED
+  }
+  QSB_TICK(st_rw, 8 + STAGE * 8 + 4);
+  const bool finishes = (STAGE == 1 && shift_b == 0) || STAGE == 2;
+  if (!finishes) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0)
+    *s_last = (atomicAdd(STAGE == 1 ? &st_rw->done_b : &st_rw->done_c, 1u) == nctas - 1);
+  __syncthreads();
+  if (!*s_last) return;
+  if constexpr (STAGE == 1) {
+    find_bin<kFastBins>(fb.fh + kFastBins, k1, &b1, &k2);
+    if (tid == 0) *thr_out = key_to_float(lo_key + (b0 << shift_a) + b1);
+  } else if constexpr (STAGE == 2) {
+    uint32_t b2;
+    unsigned long long k3;
+    find_bin<kFastBins>(fb.fh + 2 * kFastBins, k2, &b2, &k3);
+    if (tid == 0)
+      *thr_out = key_to_float(lo_key + (b0 << shift_a) + (b1 << shift_b) + b2);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // one radix pass; route chosen on the device
 // ---------------------------------------------------------------------------
-struct FastBufs {
-  const SelState *st;     // nullptr: there is no fast route (small n)
-  const float *cand;      // [tiles][kRegion]
-  const uint32_t *cnt;    // [tiles]
-  int64_t tiles;
-  SelectWs ws_cand;
-};
-
 template <int PASS, int V, bool ABS>
 __global__ void __launch_bounds__(QSB_THREADS)
     select_pass_kernel(const float *__restrict__ v, int64_t n, int64_t k, SelectWs ws,
                        FastBufs fb, SelState *st_rw, float *thr_out) {
   constexpr int kSmemWords = (PASS == 0) ? kBins0 * 32 : kBins1;
+  static_assert(kSmemWords >= kFastBins, "the fast passes reuse the histogram");
   __shared__ uint32_t s_hist[kSmemWords];
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < kSmemWords; i += QSB_THREADS) s_hist[i] = 0;
-
-  bool on_candidates = false;
-  unsigned long long kk = (unsigned long long)k;
+  const unsigned long long kk = (unsigned long long)k;
+  pdl_wait();     // everything below reads what the previous launch of the chain wrote
+  pdl_trigger();  // the next launch may take the SM resources this grid leaves free
+  if (fb.st) QSB_TICK(st_rw, 8 + PASS * 8 + 0);
   if (fb.st) {
     unsigned long long kc;
-    if (fast_route_valid(fb.st, kk, &kc)) {
-      on_candidates = true;
-      kk = kc;
-      ws = fb.ws_cand;
+    const uint32_t route = fast_route(fb, st_rw, PASS, kk, &kc, thr_out);
+    if (route == 3) return;  // the answer was lo
+    if (route == 1) {
+      fast_pass<PASS>(fb, kc, st_rw, thr_out, s_hist, &s_last);
+      return;
     }
   }
+  for (int i = tid; i < kSmemWords; i += QSB_THREADS) s_hist[i] = 0;
   PassConst pc{0, 0};
   if constexpr (PASS >= 1) {
     unsigned long long k1;
@@ -200,17 +414,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
   }
   __syncthreads();
 
-  if (on_candidates) {
-    // candidate regions hold values with |.| already applied: a warp per region
-    const int64_t warps_total = (int64_t)gridDim.x * (QSB_THREADS / 32);
-    for (int64_t r = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (tid >> 5); r < fb.tiles;
-         r += warps_total) {
-      const uint32_t c = fb.cnt[r];
-      const float *region = fb.cand + r * kRegion;
-      for (uint32_t i = lane; i < c; i += 32)
-        count_value<PASS, false>(region[i], pc, s_hist, lane);
-    }
-  } else {
+  {
     constexpr int U = (V == 8) ? 2 : 4;
     constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
     const int64_t n_main = (n / V) * V;
@@ -270,65 +474,219 @@ __global__ void __launch_bounds__(QSB_THREADS)
 }
 
 // ---------------------------------------------------------------------------
-// fast route, step 1: pivots.  kSampleSize evenly spaced values; 128 CTAs count the
-// exact rank range [#less, #less-or-equal) of every sample inside the sample
-// (kSampleParts threads per sample, each scanning 1/8 of the keys from shared memory);
-// the samples whose range contains r_lo / r_hi are the pivots.
+// fast route, step 1: pivots.  ONE cluster of 8 CTAs x 1024 threads, one sample per
+// thread (a single SM cannot issue 8192 scattered sector requests in less than ~8 us;
+// eight SMs can).  The CTAs zero the workspace header while the gathers fly, histogram
+// their keys' top 11 bits in their own shared memory, and CTA 0 adds the eight
+// histograms through distributed shared memory and finds the bins of the sample ranks
+// r_lo and r_hi; a second round does the same for the next 11 bits under those two
+// prefixes.  lo = floor, hi = ceiling of the selected 22-bit prefixes.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(QSB_THREADS)
-    select_sample_kernel(const float *__restrict__ v, int64_t n, int take_abs, int r_lo,
-                         int r_hi, SelState *st) {
-  __shared__ __align__(16) uint32_t s_keys[kSampleSize];
-  const int64_t stride = n / kSampleSize;
-  for (int i = threadIdx.x; i < kSampleSize; i += QSB_THREADS) {
-    const float f = v[(int64_t)i * stride + (stride >> 1)];
-    s_keys[i] = float_to_key(take_abs ? fabsf(f) : f);
+// bins where the running count first exceeds rank r_a in hist_a and r_b in hist_b (the
+// two may be the same array): ONE block scan for both (1024 threads, 2 bins each).
+// out[0..2] = bin, rank inside the bin, count of the bin for a; out[3..5] for b.
+__device__ void sample_find2(const uint32_t *hist_a, int r_a, const uint32_t *hist_b, int r_b,
+                             uint32_t *s_scan, uint32_t *out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint2 ca = reinterpret_cast<const uint2 *>(hist_a)[tid];
+  const uint2 cb = reinterpret_cast<const uint2 *>(hist_b)[tid];
+  const uint32_t sum_a = ca.x + ca.y, sum_b = cb.x + cb.y;
+  uint32_t ia = sum_a, ib = sum_b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o);
+    const uint32_t tb = __shfl_up_sync(0xffffffffu, ib, o);
+    if (lane >= o) ia += ta, ib += tb;
+  }
+  if (lane == 31) s_scan[warp] = ia, s_scan[32 + warp] = ib;
+  __syncthreads();
+  if (warp < 2) {
+    const uint32_t w = s_scan[warp * 32 + lane];
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_scan[64 + warp * 32 + lane] = wi - w;  // exclusive warp offsets
   }
   __syncthreads();
-  constexpr int kPerCta = QSB_THREADS / kSampleParts;  // samples ranked by one CTA
-  const int part = threadIdx.x % kSampleParts;
-  const int i = blockIdx.x * kPerCta + threadIdx.x / kSampleParts;
-  const uint32_t ki = s_keys[i];
-  const uint4 *k4 = reinterpret_cast<const uint4 *>(s_keys);
-  constexpr int kVecPerPart = kSampleSize / 4 / kSampleParts;
-  int lt = 0, le = 0;
-#pragma unroll 4
-  for (int j = 0; j < kVecPerPart; ++j) {
-    const uint4 q = k4[part * kVecPerPart + j];
-    lt += (q.x < ki) + (q.y < ki) + (q.z < ki) + (q.w < ki);
-    le += (q.x <= ki) + (q.y <= ki) + (q.z <= ki) + (q.w <= ki);
+  const uint32_t before_a = s_scan[64 + warp] + ia - sum_a, before_b = s_scan[96 + warp] + ib - sum_b;
+  const uint32_t ua = (uint32_t)r_a, ub = (uint32_t)r_b;
+  if (ua >= before_a && ua < before_a + sum_a) {
+    const bool first = ua < before_a + ca.x;
+    out[0] = 2 * tid + (first ? 0 : 1);
+    out[1] = ua - before_a - (first ? 0 : ca.x);
+    out[2] = first ? ca.x : ca.y;
   }
+  if (ub >= before_b && ub < before_b + sum_b) {
+    const bool first = ub < before_b + cb.x;
+    out[3] = 2 * tid + (first ? 0 : 1);
+    out[4] = ub - before_b - (first ? 0 : cb.x);
+    out[5] = first ? cb.x : cb.y;
+  }
+  __syncthreads();
+}
+
+// CTA 0 of the cluster: h[b] += the same bin of the other CTAs' histograms
+__device__ __forceinline__ void cluster_sum_hist(cg::cluster_group &cluster, uint32_t *h) {
+  uint2 acc = reinterpret_cast<uint2 *>(h)[threadIdx.x];
 #pragma unroll
-  for (int o = kSampleParts >> 1; o > 0; o >>= 1) {
-    lt += __shfl_xor_sync(0xffffffffu, lt, o);
-    le += __shfl_xor_sync(0xffffffffu, le, o);
+  for (int r = 1; r < kSampleCtas; ++r) {
+    const uint2 q = reinterpret_cast<const uint2 *>(cluster.map_shared_rank(h, r))[threadIdx.x];
+    acc.x += q.x;
+    acc.y += q.y;
   }
-  if (part == 0) {
-    // the r-th order statistic equals this key iff lt <= r < le (ties write the same value)
-    if (r_lo >= 0 && lt <= r_lo && r_lo < le) st->lo = key_to_float(ki);
-    if (r_hi < kSampleSize && lt <= r_hi && r_hi < le) st->hi = key_to_float(ki);
-    if (i == 0) {
-      if (r_lo < 0) st->lo = -INFINITY;
-      if (r_hi >= kSampleSize) st->hi = INFINITY;
+  reinterpret_cast<uint2 *>(h)[threadIdx.x] = acc;
+}
+
+template <int PER>
+__global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThreads)
+    select_sample_kernel(const float *__restrict__ v, int64_t n, int take_abs, int r_lo,
+                         int r_hi, SelState *st, uint4 *zero_base, int zero_vecs) {
+  static_assert(kFastBins == 2 * kSampleThreads, "two bins per thread");
+  constexpr int kSampleSize = kSampleThreads * kSampleCtas * PER;
+  constexpr int kTieMinCount = kSampleSize / 50;  // >= 2 % of the sample in lo's bucket: ties at lo
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ __align__(16) uint32_t h0[kFastBins];  // top 11 bits
+  __shared__ __align__(16) uint32_t ha[kFastBins];  // next 11 bits under r_lo's prefix
+  __shared__ __align__(16) uint32_t hb[kFastBins];  // next 11 bits under r_hi's prefix
+  __shared__ uint32_t s_scan[128];
+  __shared__ uint32_t s_res[12];  // [0..5] first digit (bin, rank, count) x (lo, hi); [6..11] second
+  const int tid = threadIdx.x;
+  const unsigned rank = cluster.block_rank();
+  const int i = (int)rank * kSampleThreads + tid;
+  const int64_t stride = n / kSampleSize;
+#ifdef QSB_SELECT_TIMING
+  const long long t_start = clock64();
+#endif
+  pdl_trigger();  // the partition kernel may start loading v on the other SMs right away
+  float f[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+    f[q] = v[(int64_t)(q * kSampleThreads * kSampleCtas + i) * stride + (stride >> 1)];
+  for (int j = i; j < zero_vecs; j += kSampleThreads * kSampleCtas) zero_base[j] = make_uint4(0, 0, 0, 0);
+  reinterpret_cast<uint2 *>(h0)[tid] = make_uint2(0, 0);
+  reinterpret_cast<uint2 *>(ha)[tid] = make_uint2(0, 0);
+  reinterpret_cast<uint2 *>(hb)[tid] = make_uint2(0, 0);
+  if (tid < 12) s_res[tid] = 0;
+  __syncthreads();
+  uint32_t key[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    key[q] = float_to_key((take_abs ? fabsf(f[q]) : f[q]) + 0.0f);  // -0 -> +0
+    atomicAdd(&h0[key[q] >> 21], 1u);
+  }
+  cluster.sync();
+  QSB_TICK(st, 1);
+  if (rank == 0) {
+    cluster_sum_hist(cluster, h0);
+    __syncthreads();
+    // r_hi >= kSampleSize: hi = +inf.  r_lo < 0: lo = -inf, unless the smallest sample's
+    // bucket is a heavy tie (the zeros of a ReLU output) — then that value is lo.
+    sample_find2(h0, r_lo >= 0 ? r_lo : 0, h0, r_hi < kSampleSize ? r_hi : kSampleSize - 1, s_scan, s_res);
+  }
+  cluster.sync();
+  QSB_TICK(st, 2);
+  const uint32_t *res0 = cluster.map_shared_rank(s_res, 0);
+  const uint32_t p_lo = res0[0], p_hi = res0[3];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const uint32_t top = key[q] >> 21, mid = (key[q] >> 10) & (kFastBins - 1);
+    if (top == p_lo) atomicAdd(&ha[mid], 1u);
+    if (top == p_hi) atomicAdd(&hb[mid], 1u);
+  }
+  cluster.sync();
+  QSB_TICK(st, 3);
+  if (rank == 0) {
+    cluster_sum_hist(cluster, ha);
+    cluster_sum_hist(cluster, hb);
+    __syncthreads();
+    sample_find2(ha, (int)s_res[1], hb, (int)s_res[4], s_scan, s_res + 6);
+    QSB_TICK(st, 4);
+    if (tid == 0) {
+      const bool lo_tie = s_res[8] >= (uint32_t)kTieMinCount;
+      uint32_t lo_key = (r_lo >= 0 || lo_tie) ? ((p_lo << 21) | (s_res[6] << 10)) : kKeyNegInf;
+      uint32_t hi_key = (r_hi < kSampleSize) ? ((p_hi << 21) | (s_res[9] << 10) | 0x3ffu) : kKeyPosInf;
+      // keep both pivots ordinary floats whose compare order equals the (canonical) key order
+      if (lo_key < kKeyNegInf) lo_key = kKeyNegInf;
+      if (hi_key > kKeyPosInf) hi_key = kKeyPosInf;
+      if (hi_key == kKeyNegZero) hi_key = kKeyPosZero;  // a <= -0.0 also admits +0.0
+      if (hi_key < lo_key) hi_key = lo_key;
+      const uint32_t span = hi_key - lo_key;
+      const uint32_t width = span ? 32u - (uint32_t)__clz(span) : 0u;
+      st->lo = key_to_float(lo_key);
+      st->hi = key_to_float(hi_key);
+      st->lo_key = lo_key;
+      st->width = width;
+      st->shift_a = width > (uint32_t)kFastBits ? width - kFastBits : 0u;
+      st->shift_b = width > 2u * kFastBits ? width - 2u * kFastBits : 0u;
+      // many samples in lo's 22-bit bucket (zeros of a ReLU output, a value of a quantisation
+      // grid): count the values == lo instead of storing them.  Also when lo == hi.
+      st->tie_lo = (span == 0u) || lo_tie;
     }
   }
+  cluster.sync();  // the other CTAs' shared memory must outlive CTA 0's reads
+  QSB_TICK(st, 5);
+#ifdef QSB_SELECT_TIMING
+  if (tid == 0 && rank == 0) reinterpret_cast<long long *>(st)[16] = t_start;
+#endif
 }
 
 // ---------------------------------------------------------------------------
 // fast route, step 2: ONE streaming pass.  Plain float compares against the pivots
-// (NaNs compare false and so count as "above hi"); each CTA owns a 4096-element tile
-// and a private region of kRegion candidate slots; totals by fire-and-forget RED.
+// (NaNs compare false and so count as "above hi"); every CTA owns a tile of
+// 256 * 8 * U elements, appends its candidates to the dense array behind one cursor
+// atomic, and adds its totals by fire-and-forget RED.
 // ---------------------------------------------------------------------------
-template <int V, bool ABS>
-__global__ void __launch_bounds__(QSB_THREADS)
-    select_partition_kernel(const float *__restrict__ v, int64_t n, SelState *st,
-                            float *__restrict__ cand, uint32_t *__restrict__ cnt) {
-  constexpr int U = 2;
+// 1.0f / 0.0f compare results (one FSET.BF each, no predicate round trip); NaN -> 0
+__device__ __forceinline__ float setf_lt(float a, float b) {
+  float m;
+  asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+  return m;
+}
+__device__ __forceinline__ float setf_le(float a, float b) {
+  float m;
+  asm("set.le.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+  return m;
+}
+__device__ __forceinline__ float setf_eq(float a, float b) {
+  float m;
+  asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+  return m;
+}
+
+// Classify the 8 elements of one vector against the pivots: a base-4 digit per element,
+// 3 = below lo, 2 = equal to lo (TIE only), 1 = candidate (lo <= a <= hi), 0 = above hi or
+// NaN, accumulated EXACTLY in one float (16 bits) by FSET.BF + FFMA — 4 instructions per
+// element instead of 6 through predicates.  Returns the digits as an integer.
+template <bool ABS, bool TIE>
+__device__ __forceinline__ uint32_t classify8(const VecF<8> &x, float lo, float hi) {
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a = ABS ? fabsf(x.v[j]) : x.v[j];
+    const float w = (float)(1u << (2 * j));
+    acc = __fmaf_rn(setf_lt(a, lo), 2.0f * w, acc);
+    acc = __fmaf_rn(setf_le(a, hi), w, acc);
+    if constexpr (TIE) acc = __fmaf_rn(setf_eq(a, lo), w, acc);
+  }
+  return (uint32_t)__float2int_rz(acc);
+}
+
+template <int U, bool ABS>
+__global__ void __launch_bounds__(QSB_THREADS, U == 2 ? 8 : 5)
+    select_partition_kernel(const float *__restrict__ v, int64_t n, const SelState *st,
+                            unsigned long long *segctr, float *__restrict__ cand,
+                            uint32_t seg_cap) {
+  constexpr int V = 8;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
-  static_assert(kTile == 4096, "region bookkeeping assumes 4096-element tiles");
-  __shared__ uint32_t s_nc[QSB_THREADS / 32], s_lt[QSB_THREADS / 32];
-  const float lo = st->lo, hi = st->hi;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // every thread parks its own elements here so that the (rare) candidates can be picked
+  // by index: [u][half][tid] float4 — conflict-free 128-bit stores, read back by the owner only
+  __shared__ float4 s_x[U * 2 * QSB_THREADS];
+  __shared__ uint32_t s_nc, s_lt, s_eq;
+  __shared__ long long s_gbase;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int64_t n_main = (n / V) * V;
   const int64_t t0 = (int64_t)blockIdx.x * kTile;
   const int64_t base = t0 + (int64_t)tid * V;
@@ -338,85 +696,139 @@ __global__ void __launch_bounds__(QSB_THREADS)
     const int64_t e = base + (int64_t)u * QSB_THREADS * V;
     if (e < n_main) x[u] = ld_vec<V, Hint::KEEP>(v + e);
   }
-  uint32_t lt = 0, nc = 0, cmask = 0;  // cmask bit (u * V + j): element is a candidate
+  const bool tail_owner = (t0 <= n_main && n_main < t0 + kTile);
+  float tail_val = 0.f;
+  const bool has_tail = tail_owner && (n_main + tid < n);
+  if (has_tail) tail_val = v[n_main + tid];
+  pdl_wait();     // the loads above are in flight; the pivots come from the sampler
+  pdl_trigger();
+  const float2 piv = *reinterpret_cast<const float2 *>(st);
+  const float lo = piv.x, hi = piv.y;
+  const bool tie = st->tie_lo != 0;
+  if (tid == 0) {
+    s_nc = 0;
+    s_lt = 0;
+    s_eq = 0;
+  }
+  __syncthreads();
+  // digits of vectors (2w, 2w + 1) in word w: bit0 of a digit = candidate-or-below, bit1 = ..
+  constexpr int W = (U + 1) / 2;
+  uint32_t dig[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) dig[w] = 0;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int64_t e = base + (int64_t)u * QSB_THREADS * V;
     if (e < n_main) {
+      const uint32_t d = tie ? classify8<ABS, true>(x[u], lo, hi) : classify8<ABS, false>(x[u], lo, hi);
+      dig[u >> 1] |= d << (16 * (u & 1));
+    }
+  }
+  uint32_t lt = 0, eq = 0, nc = 0;
+  uint32_t cbits[W];  // bit 2j (+16 for the odd vector) set: element j is a candidate
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float a = ABS ? fabsf(x[u].v[j]) : x[u].v[j];
-        lt += a < lo;
-        const bool c = (a >= lo) && (a <= hi);
-        nc += c;
-        cmask |= (uint32_t)c << (u * V + j);
-      }
-    }
+  for (int w = 0; w < W; ++w) {
+    const uint32_t b0 = dig[w] & 0x55555555u, b1 = (dig[w] >> 1) & 0x55555555u;
+    cbits[w] = b0 & ~b1;
+    lt += __popc(b0 & b1);
+    eq += __popc(b1 & ~b0);
+    nc += __popc(cbits[w]);
   }
-  float tail_val = 0.f;  // the last n % V elements: the owning CTA's first threads
   bool tail_c = false;
-  if (t0 <= n_main && n_main < t0 + kTile) {
-    const int64_t e = n_main + tid;
-    if (e < n) {
-      tail_val = ABS ? fabsf(v[e]) : v[e];
-      lt += tail_val < lo;
-      tail_c = (tail_val >= lo) && (tail_val <= hi);
-      nc += tail_c;
+  if (has_tail) {
+    tail_val = ABS ? fabsf(tail_val) : tail_val;
+    if (tail_val < lo) ++lt;
+    else if (tie && tail_val == lo) ++eq;
+    else if (tail_val <= hi) tail_c = true, ++nc;
+  }
+  if (nc) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      s_x[(u * 2 + 0) * QSB_THREADS + tid] = make_float4(x[u].v[0], x[u].v[1], x[u].v[2], x[u].v[3]);
+      s_x[(u * 2 + 1) * QSB_THREADS + tid] = make_float4(x[u].v[4], x[u].v[5], x[u].v[6], x[u].v[7]);
     }
   }
-  uint32_t incl = nc;  // CTA-wide exclusive scan of the candidate counts
+  uint32_t incl = nc;  // warp scan, then one shared-memory atomic per warp
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  const uint32_t wlt = warp_reduce(lt, [](uint32_t a, uint32_t b) { return a + b; });
-  if (lane == 31) s_nc[warp] = incl;
-  if (lane == 0) s_lt[warp] = wlt;
+  const uint32_t wlt = __reduce_add_sync(0xffffffffu, lt);
+  const uint32_t weq = tie ? __reduce_add_sync(0xffffffffu, eq) : 0u;
+  uint32_t wbase = 0;
+  if (lane == 31) {
+    if (incl) wbase = atomicAdd(&s_nc, incl);
+    if (wlt) atomicAdd(&s_lt, wlt);
+    if (weq) atomicAdd(&s_eq, weq);
+  }
+  wbase = __shfl_sync(0xffffffffu, wbase, 31);
   __syncthreads();
-  uint32_t pos = incl - nc;
-  for (int w = 0; w < warp; ++w) pos += s_nc[w];
+  const int seg = blockIdx.x % kSegs;
   if (tid == 0) {
-    uint32_t total = 0, tlt = 0;
-    for (int w = 0; w < QSB_THREADS / 32; ++w) {
-      total += s_nc[w];
-      tlt += s_lt[w];
+    const uint32_t total = s_nc, tlt = s_lt, teq = s_eq;
+    long long g = -1;
+    if (teq) atomicAdd(segctr + seg * kSegStride + 1, (unsigned long long)teq);  // unused result: RED
+    if (total | tlt) {
+      // ONE atomic per CTA: candidates in the low word (the append cursor), "< lo" in the high
+      const unsigned long long old = atomicAdd(
+          segctr + seg * kSegStride, ((unsigned long long)tlt << 32) | (unsigned long long)total);
+      const uint32_t at = (uint32_t)old;
+      if (total && at <= seg_cap && total <= seg_cap - at) g = at;  // else: overflow, seen in
+    }                                                               // the counter by the passes
+    s_gbase = g;
+  }
+  __syncthreads();
+  const long long g = s_gbase;
+  if (nc == 0 || g < 0) return;  // nothing to store, or the segment is full
+  float *out = cand + (size_t)seg * seg_cap + (uint32_t)g;
+  uint32_t pos = wbase + (incl - nc);
+  const float *sx = reinterpret_cast<const float *>(s_x);
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    uint32_t m = cbits[w];
+    while (m) {
+      const int b = __ffs(m) - 1;  // vector u = 2w + b / 16, element j = (b % 16) / 2
+      m &= m - 1;
+      const int q = 4 * w + (b >> 3);  // float4 row of s_x: u * 2 + j / 4
+      const float a = sx[((q * QSB_THREADS) + tid) * 4 + ((b >> 1) & 3)];
+      out[pos++] = (ABS ? fabsf(a) : a) + 0.0f;  // -0 -> +0
     }
-    cnt[blockIdx.x] = total < (uint32_t)kRegion ? total : (uint32_t)kRegion;
-    if (total > (uint32_t)kRegion) st->overflow = 1;
-    if (tlt) atomicAdd(&st->count_lt, (unsigned long long)tlt);    // result unused: RED
-    if (total) atomicAdd(&st->n_cand, (unsigned long long)total);  // result unused: RED
   }
-  if (nc) {
-    float *region = cand + (int64_t)blockIdx.x * kRegion;
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int j = 0; j < V; ++j)
-        if (cmask & (1u << (u * V + j))) {
-          if (pos < (uint32_t)kRegion) region[pos] = ABS ? fabsf(x[u].v[j]) : x[u].v[j];
-          ++pos;
-        }
-    if (tail_c && pos < (uint32_t)kRegion) region[pos] = tail_val;
-  }
+  if (tail_c) out[pos] = tail_val + 0.0f;
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 constexpr int64_t kHistBytes = (int64_t)(kBins0 + kBins1 + kBins2) * sizeof(unsigned long long);
-// [hist x3 | candidate hist x3 | SelState | pad] | cnt[tiles] | candidate regions
-constexpr int64_t kSelectHeaderBytes = 2 * kHistBytes + 256;
+constexpr int64_t kFastHistBytes = 3 * (int64_t)kFastBins * sizeof(uint32_t);
+constexpr int64_t kSegCtrBytes = (int64_t)kSegs * kSegStride * sizeof(unsigned long long);
+// [hist x3 | fast hist x3 | segment counters | SelState | pad] | candidate segments
+constexpr int64_t kSelectHeaderBytes = kHistBytes + kFastHistBytes + kSegCtrBytes + 1024;
+static_assert(kSelectHeaderBytes % 16 == 0, "the sampler zeroes the header with 128-bit stores");
+static_assert(sizeof(SelState) <= 128, "SelState must fit the header pad (timing slots follow it)");
 static int g_select_fast = 1;  // tuning key 4
+static int g_select_pdl = 1;   // tuning key 8: programmatic dependent launch inside a select
+static int g_partition_u = 4;  // tuning key 6: 256-bit loads in flight per thread (2 or 4)
+static int g_sample_per = 2;   // tuning key 7: samples per sampler thread (1, 2, 4 -> 8K, 16K, 32K samples)
 
-static int64_t select_tiles(int64_t n) { return n >= kFastMinN ? (n + 4095) / 4096 : 0; }
+// slots per segment: n/8 in total, a multiple of 8 per segment, < 2^32
+static int64_t seg_slots(int64_t n) {
+  if (n < kFastMinN) return 0;
+  int64_t c = ((n >> kCandShift) / kSegs) & ~(int64_t)7;
+  return c > 0xfffffff8ll ? 0xfffffff8ll : c;
+}
 
 void set_select_fast(int v) { g_select_fast = v; }
+void set_select_pdl(int v) { g_select_pdl = v != 0; }
+void set_select_partition_u(int v) { g_partition_u = (v == 2) ? 2 : 4; }
+void set_select_sample_per(int v) { g_sample_per = (v == 1 || v == 4) ? v : 2; }
 
 template <int PASS, int V, bool ABS>
 static int launch_pass(const float *v, int64_t n, int64_t k, const SelectWs &ws,
                        const FastBufs &fb, SelState *st, float *thr_out,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, bool after_kernel) {
   static int occ = 0;
   if (occ == 0) {
     int o = 0;
@@ -430,6 +842,11 @@ static int launch_pass(const float *v, int64_t n, int64_t k, const SelectWs &ws,
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
+  if (g_select_pdl && after_kernel) {  // the previous kernel of this select is the dependency
+    QSB_CUDA_TRY(launch_pdl(select_pass_kernel<PASS, V, ABS>, dim3((unsigned)grid), dim3(QSB_THREADS), 0,
+                            stream, v, n, k, ws, fb, st, thr_out));
+    return 0;
+  }
   select_pass_kernel<PASS, V, ABS>
       <<<(unsigned)grid, QSB_THREADS, 0, stream>>>(v, n, k, ws, fb, st, thr_out);
   QSB_LAUNCH_CHECK();
@@ -441,9 +858,27 @@ static int run_passes(const float *v, int64_t n, int64_t k, const SelectWs &ws,
                       const FastBufs &fb, SelState *st, float *thr_out,
                       cudaStream_t stream) {
   int rc;
-  if ((rc = launch_pass<0, V, ABS>(v, n, k, ws, fb, st, thr_out, stream))) return rc;
-  if ((rc = launch_pass<1, V, ABS>(v, n, k, ws, fb, st, thr_out, stream))) return rc;
-  return launch_pass<2, V, ABS>(v, n, k, ws, fb, st, thr_out, stream);
+  // without the fast route the first pass follows a memset, not a kernel of ours
+  if ((rc = launch_pass<0, V, ABS>(v, n, k, ws, fb, st, thr_out, stream, fb.st != nullptr))) return rc;
+  if ((rc = launch_pass<1, V, ABS>(v, n, k, ws, fb, st, thr_out, stream, true))) return rc;
+  return launch_pass<2, V, ABS>(v, n, k, ws, fb, st, thr_out, stream, true);
+}
+
+template <int U, bool ABS>
+static int launch_partition(const float *v, int64_t n, const SelState *st,
+                            unsigned long long *segctr, float *cand, uint32_t seg_cap,
+                            cudaStream_t stream) {
+  constexpr int64_t kTile = (int64_t)QSB_THREADS * 8 * U;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (g_select_pdl) {
+    QSB_CUDA_TRY(launch_pdl(select_partition_kernel<U, ABS>, dim3((unsigned)tiles), dim3(QSB_THREADS), 0,
+                            stream, v, n, st, segctr, cand, seg_cap));
+    return 0;
+  }
+  select_partition_kernel<U, ABS>
+      <<<(unsigned)tiles, QSB_THREADS, 0, stream>>>(v, n, st, segctr, cand, seg_cap);
+  QSB_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace qsb
@@ -451,8 +886,7 @@ static int run_passes(const float *v, int64_t n, int64_t k, const SelectWs &ws,
 using namespace qsb;
 
 extern "C" int64_t qsb_kth_workspace_bytes(int64_t n) {
-  const int64_t tiles = select_tiles(n);
-  return kSelectHeaderBytes + 256 + tiles * 4 + 64 + tiles * kRegion * (int64_t)sizeof(float) + 32;
+  return 256 + kSelectHeaderBytes + 32 + kSegs * seg_slots(n) * (int64_t)sizeof(float) + 32;
 }
 
 extern "C" int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
@@ -464,37 +898,43 @@ extern "C" int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
   if (!aligned_to(v, 4)) return QSB_E_ALIGN;
   if (workspace_bytes < qsb_kth_workspace_bytes(n)) return QSB_E_WORKSPACE;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
-  SelectWs ws, wc;
+  SelectWs ws;
   ws.hist0 = reinterpret_cast<unsigned long long *>(base);
   ws.hist1 = ws.hist0 + kBins0;
   ws.hist2 = ws.hist1 + kBins1;
-  wc.hist0 = ws.hist2 + kBins2;
-  wc.hist1 = wc.hist0 + kBins0;
-  wc.hist2 = wc.hist1 + kBins1;
-  SelState *st = reinterpret_cast<SelState *>(wc.hist2 + kBins2);
-  static_assert(sizeof(SelState) <= 256, "SelState must fit the header pad");
-  QSB_CUDA_TRY(cudaMemsetAsync(ws.hist0, 0, kSelectHeaderBytes, stream));
+  uint32_t *fh = reinterpret_cast<uint32_t *>(ws.hist2 + kBins2);
+  unsigned long long *segctr = reinterpret_cast<unsigned long long *>(fh + 3 * kFastBins);
+  SelState *st = reinterpret_cast<SelState *>(segctr + kSegs * kSegStride);
 
   const bool v32 = aligned_to(v, 32);
-  FastBufs fb{nullptr, nullptr, nullptr, 0, wc};
+  FastBufs fb{nullptr, nullptr, nullptr, nullptr, 0};
   if (g_select_fast && n >= kFastMinN && v32) {
-    const int64_t tiles = select_tiles(n);
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(base + kSelectHeaderBytes);
-    float *cand = reinterpret_cast<float *>(
-        (reinterpret_cast<uintptr_t>(cnt + tiles) + 31) / 32 * 32);
-    // sample ranks bracketing k: +-5 sigma of the binomial rank error, +3
-    const double m = (double)kSampleSize, p = (double)k / (double)n;
-    const double delta = 5.0 * sqrt(m * p * (1.0 - p)) + 3.0;
+    float *cand = reinterpret_cast<float *>((base + kSelectHeaderBytes + 31) / 32 * 32);
+    const uint32_t cap = (uint32_t)seg_slots(n);
+    // sample ranks bracketing k: +-4.5 sigma of the binomial rank error, +3
+    const double m = (double)(kSampleThreads * kSampleCtas * g_sample_per), p = (double)k / (double)n;
+    const double delta = 4.5 * sqrt(m * p * (1.0 - p)) + 3.0;
     const int r_lo = (int)floor(p * m - delta), r_hi = (int)ceil(p * m + delta);
-    select_sample_kernel<<<kSampleSize / (QSB_THREADS / kSampleParts), QSB_THREADS, 0, stream>>>(
-        v, n, take_abs, r_lo, r_hi, st);
-    QSB_LAUNCH_CHECK();
-    if (take_abs)
-      select_partition_kernel<8, true><<<(unsigned)tiles, QSB_THREADS, 0, stream>>>(v, n, st, cand, cnt);
+    uint4 *zb = reinterpret_cast<uint4 *>(base);
+    const int zv = (int)(kSelectHeaderBytes / 16);
+    if (g_sample_per == 1)
+      select_sample_kernel<1><<<kSampleCtas, kSampleThreads, 0, stream>>>(v, n, take_abs, r_lo, r_hi, st, zb, zv);
+    else if (g_sample_per == 4)
+      select_sample_kernel<4><<<kSampleCtas, kSampleThreads, 0, stream>>>(v, n, take_abs, r_lo, r_hi, st, zb, zv);
     else
-      select_partition_kernel<8, false><<<(unsigned)tiles, QSB_THREADS, 0, stream>>>(v, n, st, cand, cnt);
+      select_sample_kernel<2><<<kSampleCtas, kSampleThreads, 0, stream>>>(v, n, take_abs, r_lo, r_hi, st, zb, zv);
     QSB_LAUNCH_CHECK();
-    fb = FastBufs{st, cand, cnt, tiles, wc};
+    int rc;
+    if (g_partition_u == 4)
+      rc = take_abs ? launch_partition<4, true>(v, n, st, segctr, cand, cap, stream)
+                    : launch_partition<4, false>(v, n, st, segctr, cand, cap, stream);
+    else
+      rc = take_abs ? launch_partition<2, true>(v, n, st, segctr, cand, cap, stream)
+                    : launch_partition<2, false>(v, n, st, segctr, cand, cap, stream);
+    if (rc) return rc;
+    fb = FastBufs{st, cand, segctr, fh, cap};
+  } else {
+    QSB_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<void *>(base), 0, kSelectHeaderBytes, stream));
   }
   if (v32)
     return take_abs ? run_passes<8, true>(v, n, k, ws, fb, st, thr_out_dev, stream)
