@@ -149,6 +149,25 @@ def main():
         ops.lines_ema_(lines, st_["min"], st_["max"], 2)
         ops.fq_line_fwd(w, lines, 4, True, (1, 4096, 4096), out=wy)
     report("c3_weight_access", 12 * nw, c3_access)
+    # the same access through the row-resident fused kernel: one launch, 8 B/elem of traffic.  Reported
+    # against the 12 B/elem of the reference's algorithm too (what the two-launch path is measured on).
+    lines2 = torch.zeros(4096, 2, device=dev)
+    report("c3_weight_access_fused", 8 * nw, lambda: ops.row_quant_fused_(w, lines2, ops.ROW_LINE, 4, 2, True),
+           note="8 B/elem actual traffic")
+    report("c3_weight_access_fused_alg12", 12 * nw,
+           lambda: ops.row_quant_fused_(w, lines2, ops.ROW_LINE, 4, 2, True), note="12 B/elem dense-algorithmic")
+    ops.set_tuning(9, 1)
+    for per_sm, stages in ((3, 4), (6, 2)):
+        ops.set_tuning(10, per_sm)
+        ops.set_tuning(11, stages)
+        report("c3_weight_access_fused", 8 * nw, lambda: ops.row_quant_fused_(w, lines2, ops.ROW_LINE, 4, 2, True),
+               variant="TMA-pipelined persistent", ctas_per_sm=per_sm, stages=stages)
+    ops.set_tuning(10, 0)
+    ops.set_tuning(11, 0)
+    ops.set_tuning(9, 0)
+    sc2 = torch.zeros(4096, 1, device=dev)
+    report("c3_weight_access_fused_scaler", 8 * nw, lambda: ops.row_quant_fused_(w, sc2, ops.ROW_SCALER, 4, 1))
+    report("c3_weight_access_fused_decimal", 8 * nw, lambda: ops.row_quant_fused_(w, sc2, ops.ROW_DECIMAL, 4, 1))
 
     # ---------------- config 4: 64 Mi unstructured
     n4 = 1 << 26

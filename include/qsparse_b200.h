@@ -67,7 +67,10 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *   key 7: samples per sampler thread of the select (1, 2 = default, 4 ->
  *          8 Ki, 16 Ki, 32 Ki samples);
  *   key 8: 1 = the kernels of one select are chained by programmatic dependent
- *          launch (default), 0 = ordinary stream order. */
+ *          launch (default), 0 = ordinary stream order;
+ *   key 9: qsb_row_quant_fused on rows of 1 Ki .. 16 Ki elements: 0 = register-
+ *          resident one-CTA-per-row kernel (default), 1 = TMA-pipelined persistent kernel;
+ *   key 10 / 11: persistent CTAs per SM (0 = up to 3) / ring stages (0 = auto) of the latter. */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and
@@ -173,6 +176,30 @@ int qsb_scale_to_decimal(const float *scale, float *decimal, int64_t n,
  * into qsb_reduce_stats by passing outer = batch. */
 int qsb_lines_ema(float *lines, const float *mn, const float *mx,
                   int64_t channels, int64_t t, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K8  row-resident fused estimate + quantize for tensors quantized along their
+ * LEADING axis (x is [rows][inner] contiguous, one parameter row per x row —
+ * the `channelwise=0` weight case).  One launch, 8 B/elem, replaces
+ *   QuantizeLayer.forward -> callback.optimize + callback.forward
+ *   (qsparse/quantize.py:501-508) =
+ *     kind 0 (Decimal): abs-max (:329-340) -> scale EMA (:344-348) ->
+ *            decimal = round(log2(1/s)) (:316) -> pow2 fake-quant (:44-63)
+ *     kind 1 (Scaler) : abs-max -> scale EMA -> scaler fake-quant (:100-117)
+ *     kind 2 (Adaptive): min / max (:396-411) -> lines EMA (:428-430) ->
+ *            line fake-quant (:148-181; float_zero_point as in qsb_fq_line_fwd)
+ * param: float[rows][1] (scale) or float[rows][2] (lo, hi), updated IN PLACE
+ * exactly like qsb_scale_ema / qsb_lines_ema would (t has the same meaning as
+ * in those calls: 0-based for kinds 0/1, 1-based for kind 2).
+ * decimal_out: float[rows] or NULL, kind 0 only (what the STE backward needs).
+ * Results are bit-identical to qsb_reduce_stats + qsb_*_ema + qsb_fq_*_fwd.
+ * Returns QSB_E_UNSUPPORTED when a row is not a whole number of 32-byte
+ * vectors (inner % 8, pointer alignment) or longer than 16384 elements; the
+ * caller then uses the three-kernel sequence above. */
+int qsb_row_quant_fused(const float *x, float *y, float *param,
+                        float *decimal_out, int kind, int bits,
+                        int float_zero_point, int64_t rows, int64_t inner,
+                        int64_t t, void *stream);
 
 /* ref: MagnitudePruningCallback.update_magnitude qsparse/sparse.py:82-89 with a
  * reduced (structured) magnitude:  m = abssum / count  (or nnz / count when

@@ -11,6 +11,7 @@
 #include <mutex>
 
 #include "p2p_internal.cuh"
+#include "param_math.cuh"
 #include "qsb_common.cuh"
 #include "reduce_internal.cuh"
 
@@ -37,32 +38,6 @@ const DeviceProps &device_props() {
   return props[dev];
 }
 
-// new = absmax / 2^(bits-1); EMA with a host step counter.
-// ref qsparse/quantize.py:340,344-348
-__device__ __forceinline__ float scale_ema_step(float w, float absmax,
-                                                float limit, int64_t t) {
-  const float nw = __fdiv_rn(absmax, limit);
-  if (t == 0) return nw;
-  return __fdiv_rn(__fadd_rn(__fmul_rn((float)t, w), nw), (float)(t + 1));
-}
-
-// d = round(log2(nan_to_num(1 / s, posinf=1, neginf=1)))
-// ref qsparse/quantize.py:316.  log2 is evaluated in fp64 and rounded to fp32,
-// i.e. the correctly rounded fp32 log2, then rint (half to even).
-__device__ __forceinline__ float scale_to_decimal(float s) {
-  float r = __fdiv_rn(1.0f, s);
-  if (r != r) r = 0.0f;
-  else if (isinf(r)) r = 1.0f;
-  const float l = (float)log2((double)r);
-  return rintf(l);
-}
-
-// mag = (t * mag + m) / (t + 1)      ref qsparse/sparse.py:89
-__device__ __forceinline__ float magnitude_ema_step(float mag, float m,
-                                                    int64_t t) {
-  return __fdiv_rn(__fadd_rn(__fmul_rn((float)t, mag), m), (float)(t + 1));
-}
-
 __global__ void scale_ema_kernel(float *w, const float *absmax, int64_t n,
                                  float limit, int64_t t) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,9 +54,8 @@ __global__ void lines_ema_kernel(float *lines, const float *mn, const float *mx,
                                  int64_t channels, float tm1, float t) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < channels) {
-    lines[2 * i] = __fdiv_rn(__fadd_rn(__fmul_rn(lines[2 * i], tm1), mn[i]), t);
-    lines[2 * i + 1] =
-        __fdiv_rn(__fadd_rn(__fmul_rn(lines[2 * i + 1], tm1), mx[i]), t);
+    lines[2 * i] = lines_ema_step(lines[2 * i], mn[i], tm1, t);
+    lines[2 * i + 1] = lines_ema_step(lines[2 * i + 1], mx[i], tm1, t);
   }
 }
 

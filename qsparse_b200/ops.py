@@ -222,6 +222,35 @@ def lines_ema_(lines, mn, mx, t: int):
     return lines
 
 
+ROW_DECIMAL, ROW_SCALER, ROW_LINE = 0, 1, 2
+
+
+def row_quant_supported(x, rows: int) -> bool:
+    """Can ``qsb_row_quant_fused`` take this [rows, inner] fp32 contiguous tensor?"""
+    n = x.numel()
+    if rows <= 0 or n == 0 or n % rows:
+        return False
+    inner = n // rows
+    return inner % 8 == 0 and inner <= 16384 and x.data_ptr() % 32 == 0
+
+
+def row_quant_fused_(x, param, kind: int, bits: int, t: int, float_zero_point=True):
+    """K8: per-row estimate (abs-max or min/max) -> EMA into ``param`` (in place) -> fake-quantize, one launch.
+    x: [rows, ...] fp32 contiguous; param: [rows, 1] (scale) or [rows, 2] (lines).
+    Returns (y, decimal or None)."""
+    lib = N.load_library()
+    N.require_cuda(x, "x")
+    N.require_cuda(param, "weight")
+    rows = param.shape[0]
+    inner = x.numel() // rows
+    y = torch.empty_like(x)
+    dec = torch.empty(rows, dtype=torch.float32, device=x.device) if kind == ROW_DECIMAL else None
+    N.check(lib.qsb_row_quant_fused(N.ptr(x), N.ptr(y), N.ptr(param), N.ptr(dec), c_int(kind), c_int(bits),
+                                    c_int(1 if float_zero_point else 0), c_int64(rows), c_int64(inner), c_int64(t),
+                                    N.stream_ptr(x.device)), "qsb_row_quant_fused")
+    return y, dec
+
+
 def magnitude_ema_reduced_(magnitude, stats: dict, count: float, t: int, use_l0=False):
     lib = N.load_library()
     N.require_cuda(magnitude, "magnitude")

@@ -32,6 +32,11 @@ from .imitation import imitate
 from .util import HostMirror, get_option, logging
 
 
+# Route `channelwise=0` weight layers through the one-launch row kernel (K8).  False keeps the
+# reduce -> EMA -> quantize sequence (same results; used by the tests to compare the two).
+FUSE_ROW_QUANTIZE = True
+
+
 # --------------------------------------------------------------------------- helpers
 def _physical_layout(x: torch.Tensor, channel_index: int, channelwise: bool):
     """(tensor whose memory the kernel walks, (outer, C, inner)).
@@ -189,6 +194,62 @@ class LineQuantization(torch.autograd.Function):
         return (grad_output,) + (None,) * 5
 
 
+class _RowFusedSte(torch.autograd.Function):
+    """K8 for the symmetric quantizers on a `channelwise=0` tensor: per-row abs-max -> scale EMA (into
+    ``weight``, in place) -> [decimal] -> fake-quantize in ONE launch (``qsb_row_quant_fused``); the backward
+    is the ordinary STE kernel with the row's decimal / scale.  Same results as
+    ``DecimalQuantizer.optimize`` + ``DecimalQuantization`` / ``ScalerQuantization`` (ref quantize.py:327-349,
+    :24-131)."""
+
+    @staticmethod
+    def forward(ctx, input, quantizer, bits, weight, xs):
+        is_decimal = not quantizer.use_float_scaler
+        y, dec = ops.row_quant_fused_(xs, weight.data, ops.ROW_DECIMAL if is_decimal else ops.ROW_SCALER, bits,
+                                      quantizer.t)
+        quantizer.t += 1
+        ctx.backward_passthrough = quantizer.backward_passthrough
+        ctx.notch = 1 if quantizer.flip_axis else 0
+        ctx.bits = bits
+        ctx.is_decimal = is_decimal
+        ctx.channelwise = True
+        ctx.channel_index = 0
+        ctx.param_is_tensor = True
+        ctx.param_host = None
+        ctx.save_for_backward(dec if is_decimal else weight.data.view(-1))
+        return y.view(input.shape)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return (_ste_backward(ctx, grad_output),) + (None,) * 4
+
+
+class _RowFusedLine(torch.autograd.Function):
+    """K8 for the asymmetric quantizer: per-row min / max -> lines EMA (in place) -> line fake-quantize in
+    ONE launch; identity backward (ref quantize.py:393-430, :134-185)."""
+
+    @staticmethod
+    def forward(ctx, input, bits, weight, xs, t, float_zero_point):
+        y, _ = ops.row_quant_fused_(xs, weight.data, ops.ROW_LINE, bits, t, float_zero_point)
+        return y.view(input.shape)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return (grad_output,) + (None,) * 5
+
+
+def _row_fusable(quantizer, exact_type, x, weight, channel_index):
+    """The fused row kernel replaces optimize() + forward() only for the stock callbacks (a subclass may
+    override either), on a CUDA tensor quantized along its leading axis, without channel grouping."""
+    if type(quantizer) is not exact_type or channel_index != 0 or quantizer.group_num > 0:
+        return None
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() >= 2 and isinstance(weight, nn.Parameter)):
+        return None
+    if tuple(weight.shape) != (x.shape[0], quantizer.weight_size) or not weight.is_contiguous():
+        return None
+    xs = N.as_f32_contiguous(x.detach())
+    return xs if ops.row_quant_supported(xs, x.shape[0]) else None
+
+
 def quantize_with_decimal(input: torch.Tensor, bits: int = 8, decimal: TensorOrInt = 5, channel_index: int = -1,
                           use_uint: bool = False, backward_passthrough: bool = False,
                           flip_axis: bool = False) -> torch.Tensor:
@@ -276,6 +337,14 @@ class DecimalQuantizer(BaseQuantizer):
         self.t += 1
         return weight
 
+    def optimize_and_forward(self, x, bits, weight, channel_index=-1, **kwargs):
+        """optimize() followed by forward() as one kernel when the tensor allows it (K8); None otherwise."""
+        xs = _row_fusable(self, ScalerQuantizer if self.use_float_scaler else DecimalQuantizer, x, weight,
+                          channel_index)
+        if xs is None:
+            return None
+        return _RowFusedSte.apply(x, self, bits, weight, xs)
+
     def _group(self, scaler):
         if self.groups is None:
             from sklearn.cluster import AgglomerativeClustering  # one-shot, host side (quantize.py:355-359)
@@ -321,6 +390,23 @@ class AdaptiveQuantizer(DecimalQuantizer):
         # float zero-point while training, integer zero-point in eval (quantize.py:390-391)
         return self.function(tensor, bits, lines, channel_index, kwargs.get("inplace", False), self.training)
 
+    def _next_t(self) -> int:
+        """advance the call counter the way optimize() does for an existing weight (quantize.py:426-427)"""
+        if isinstance(self.t, torch.Tensor):
+            self.t += 1
+            self._t_host = getattr(self, "_t_host", 0) + 1
+            return self._t_host
+        self.t += 1
+        return self.t
+
+    def optimize_and_forward(self, x, bits, weight, channel_index=-1, **kwargs):
+        xs = _row_fusable(self, AdaptiveQuantizer, x, weight, channel_index)
+        if xs is None:
+            return None
+        with torch.no_grad():
+            t = self._next_t()
+        return _RowFusedLine.apply(x, bits, weight, xs, t, self.training)
+
     def optimize(self, x, bits, weight=None, channel_index=-1, batched=False, **kwargs):
         N.require_cuda(x, "x")
         if batched and channel_index == 0:
@@ -339,13 +425,7 @@ class AdaptiveQuantizer(DecimalQuantizer):
                 self._t_host = 1
                 return torch.stack([st["min"], st["max"]], dim=1).view(nch, 2)
             assert (nch, 2) == tuple(weight.shape)
-            if isinstance(self.t, torch.Tensor):
-                self.t += 1
-                self._t_host = getattr(self, "_t_host", 0) + 1
-                t = self._t_host
-            else:
-                self.t += 1
-                t = self.t
+            t = self._next_t()
             target = weight.data if isinstance(weight, nn.Parameter) else weight
             ops.lines_ema_(target, st["min"], st["max"], t)
         return weight
@@ -405,12 +485,21 @@ class QuantizeLayer(nn.Module):
             if self.training:
                 if t == self.timeout:
                     logging.warn(f"quantizing {self.name} with {self.bits} bits")
-                new_weight = self.callback.optimize(x, self.bits, self.weight, batched=self.batch_dimension == 0,
-                                                    channel_index=self.channelwise)
-                if new_weight is not None and new_weight is not self.weight:
-                    self.weight.data[:] = new_weight
+                fused = None
+                if self.channelwise == 0 and self.batch_dimension != 0 and FUSE_ROW_QUANTIZE:
+                    # weights quantized along their leading axis: estimate + quantize in one launch (K8)
+                    fuse = getattr(self.callback, "optimize_and_forward", None)
+                    fused = fuse(x, self.bits, self.weight, channel_index=0) if fuse is not None else None
+                if fused is None:
+                    new_weight = self.callback.optimize(x, self.bits, self.weight,
+                                                        batched=self.batch_dimension == 0,
+                                                        channel_index=self.channelwise)
+                    if new_weight is not None and new_weight is not self.weight:
+                        self.weight.data[:] = new_weight
                 self._quantized = True
-            if self._quantized:
+                if fused is not None:
+                    out = fused
+            if self._quantized and out is x:
                 out = self.callback(x, self.bits, self.weight, channel_index=self.channelwise,
                                     inplace=self.batch_dimension == 0)
         if self.training:

@@ -399,3 +399,121 @@ def test_kth_value_fast_route_and_fallback(kind):
             assert torch.equal(a.view(torch.int32), ref[k:k + 1].view(torch.int32)) or torch.isnan(a).item()
     finally:
         ops.set_tuning(4, 1)
+
+
+# ----------------------------------------------------------------------------- K8 row-resident fused kernel
+ROW_SHAPES = [(33, 8), (64, 288), (7, 1000), (130, 1024), (5, 2048), (48, 4096), (3, 8200), (2, 16384),
+              (9, 4, 6, 12)]
+
+
+@pytest.fixture(params=[0, 1], ids=["registers", "tma"])
+def row_variant(request):
+    """both kernels for rows of 1 Ki .. 16 Ki elements: register-resident (default) and TMA-pipelined"""
+    from qsparse_b200 import ops
+    ops.set_tuning(9, request.param)
+    yield request.param
+    ops.set_tuning(9, 0)
+
+
+@pytest.mark.parametrize("shape", ROW_SHAPES)
+@pytest.mark.parametrize("kind", ["decimal", "scaler", "line"])
+def test_row_quant_fused_vs_oracle_and_unfused(shape, kind, row_variant):
+    """qsb_row_quant_fused == reduce -> EMA -> fake-quant (oracle, and our own three-kernel sequence), bit for
+    bit, over several EMA steps; rows of every dispatch width (a warp per row, a CTA per row)."""
+    from qsparse_b200 import ops
+    rows = shape[0]
+    bits = 4
+    w_unf = None
+    if kind == "line":
+        w_fused = torch.zeros(rows, 2, device="cuda")
+        w_orc = np.zeros((rows, 2), np.float32)
+    else:
+        w_fused = torch.zeros(rows, 1, device="cuda")
+        w_orc = np.zeros((rows, 1), np.float32)
+    w_unf = w_fused.clone()
+    for step in range(3):
+        x = rnd(shape, 100 + step, 0.02 * (step + 1))
+        if step == 1:
+            x.reshape(rows, -1)[0, :] = 0.0           # an all-zero row: scale 0 / step 0 -> 1e-4 paths
+        xc = cu(x)
+        assert ops.row_quant_supported(xc, rows)
+        if kind == "line":
+            t = step + 1
+            y, _ = ops.row_quant_fused_(xc, w_fused, ops.ROW_LINE, bits, t, True)
+            mn, mx = orc.minmax(x, 0)
+            w_orc = orc.lines_ema(w_orc, mn, mx, t)
+            y_orc = orc.fq_line_fwd(x, w_orc, bits, 0, True)
+            st = ops.reduce_stats(xc, (1, rows, x.size // rows), minmax=True)
+            ops.lines_ema_(w_unf, st["min"], st["max"], t)
+            y_unf = ops.fq_line_fwd(xc, w_unf, bits, True, (1, rows, x.size // rows))
+        else:
+            t = step
+            k = ops.ROW_DECIMAL if kind == "decimal" else ops.ROW_SCALER
+            y, dec = ops.row_quant_fused_(xc, w_fused, k, bits, t)
+            w_orc = orc.scale_ema(w_orc.reshape(-1), orc.absmax(x, 0), bits, t).reshape(rows, 1)
+            st = ops.reduce_stats(xc, (1, rows, x.size // rows), absmax=True)
+            ops.scale_ema_(w_unf, st["absmax"], bits, t)
+            if kind == "decimal":
+                d_orc = orc.scale_to_decimal(w_orc.reshape(-1))
+                assert bits_equal(npy(dec), d_orc), step
+                y_orc = orc.fq_pow2_fwd(x, d_orc, 0)
+                y_unf = ops.fq_pow2_fwd(xc, ops.scale_to_decimal(w_unf).view(-1), (1, rows, x.size // rows))
+            else:
+                y_orc = orc.fq_scaler_fwd(x, w_orc.reshape(-1), 0)
+                y_unf = ops.fq_scaler_fwd(xc, w_unf.view(-1), (1, rows, x.size // rows))
+        assert bits_equal(npy(w_fused), w_orc), (kind, step, "param vs oracle")
+        assert torch.equal(w_fused.view(torch.int32), w_unf.view(torch.int32)), (kind, step, "param vs unfused")
+        assert bits_equal(npy(y), y_orc), (kind, step, "y vs oracle")
+        assert torch.equal(y.view(torch.int32), y_unf.view(torch.int32)), (kind, step, "y vs unfused")
+
+
+def test_row_quant_fused_nan_and_unsupported():
+    from qsparse_b200 import ops
+    x = rnd((4, 512), 3)
+    x[2, 77] = np.nan
+    xc = cu(x)
+    w = torch.zeros(4, 2, device="cuda")
+    ops.row_quant_fused_(xc, w, ops.ROW_LINE, 8, 1, True)
+    wn = npy(w)
+    assert np.isnan(wn[2]).all() and not np.isnan(np.delete(wn, 2, 0)).any()
+    assert not ops.row_quant_supported(cu(rnd((4, 9), 1)), 4)         # rows are not whole vectors
+    assert not ops.row_quant_supported(cu(rnd((2, 16392), 1)), 2)     # longer than 16 Ki
+    with pytest.raises(RuntimeError):
+        ops.row_quant_fused_(cu(rnd((4, 12), 1)), torch.zeros(4, 1, device="cuda"), ops.ROW_SCALER, 8, 0)
+
+
+@pytest.mark.parametrize("cb_name", ["DecimalQuantizer", "ScalerQuantizer", "AdaptiveQuantizer"])
+def test_weight_layer_fused_equals_unfused(cb_name):
+    """quantize(nn.Linear, channelwise=0): the layer routed through K8 gives the same outputs, weights of the
+    quantizer, gradients and counters as the reduce -> EMA -> quantize sequence (config 3 shape, 4 bits)."""
+    import importlib
+    import qsparse_b200 as q
+    qz = importlib.import_module("qsparse_b200.quantize")   # the package attribute is the function
+    outs = {}
+    for fuse in (True, False):
+        qz.FUSE_ROW_QUANTIZE = fuse
+        try:
+            torch.manual_seed(3)
+            lin = torch.nn.Linear(512, 256).cuda()
+            raw = lin.weight            # the leaf Parameter (lin.weight becomes a property below)
+            layer = q.quantize(lin, bits=4, channelwise=0, timeout=1, callback=getattr(qz, cb_name)())
+            layer.train()
+            rec = []
+            for step in range(4):
+                xin = torch.randn(8, 512, device="cuda", generator=torch.Generator("cuda").manual_seed(step))
+                with torch.no_grad():
+                    raw.mul_(1.0 + 0.1 * step)
+                y = layer(xin)
+                y.square().mean().backward()
+                rec.append((y.detach().clone(), raw.grad.detach().clone()))
+                raw.grad = None
+            sd = {k: v.detach().clone() for k, v in layer.state_dict().items()}
+            outs[fuse] = (rec, sd)
+        finally:
+            qz.FUSE_ROW_QUANTIZE = True
+    (ra, sa), (rb, sb) = outs[True], outs[False]
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    for (ya, ga), (yb, gb) in zip(ra, rb):
+        assert torch.equal(ya, yb) and torch.equal(ga, gb)
