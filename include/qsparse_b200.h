@@ -70,7 +70,10 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *          launch (default), 0 = ordinary stream order;
  *   key 9: qsb_row_quant_fused on rows of 1 Ki .. 16 Ki elements: 0 = register-
  *          resident one-CTA-per-row kernel (default), 1 = TMA-pipelined persistent kernel;
- *   key 10 / 11: persistent CTAs per SM (0 = up to 3) / ring stages (0 = auto) of the latter. */
+ *   key 10 / 11: persistent CTAs per SM (0 = up to 3) / ring stages (0 = auto) of the latter;
+ *   key 12: 1 = the streaming, reduction and fused-parameter kernels are launched with
+ *          programmatic stream serialization (each begins with griddepcontrol.wait, so
+ *          stream order is unchanged; launch latency overlaps the predecessor's tail). */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and
@@ -327,8 +330,8 @@ int qsb_prune_quant_step_params(float *magnitude, uint8_t *mask, float *scale,
  * the results are in the host buffers.
  * ---------------------------------------------------------------------- */
 typedef struct qsb_host_ctx qsb_host_ctx;
-/* The context owns device staging buffers for 4 tensors of max_elems floats,
- * three streams (upload / compute / download) and per-chunk events. */
+/* The context owns two slots of device staging buffers (4 tensors of max_elems
+ * floats each), three streams (upload / compute / download) and per-chunk events. */
 int qsb_host_ctx_create(qsb_host_ctx **out, int64_t max_elems,
                         int64_t max_channels, int n_chunks);
 int qsb_host_ctx_destroy(qsb_host_ctx *ctx);
@@ -351,6 +354,24 @@ int qsb_host_prune_quant_step(qsb_host_ctx *ctx, const float *x_host,
                               int64_t channels, int64_t inner, int64_t t_prune,
                               int64_t k, int bits, int64_t t_quant,
                               void *caller_stream);
+
+/* The same step, asynchronous: enqueue everything for `slot` (0 or 1) and return.
+ * Two steps may be in flight, one per slot — the upload of step t+1 then overlaps
+ * the download of step t (PCIe is full duplex), and the steady state costs 2
+ * transfers per direction per step instead of 3 serial ones.  Steps are applied to
+ * the layer state in submission order.  Each slot needs its own four host buffers;
+ * qsb_host_ctx_wait(ctx, slot) returns when that slot's y_host / gx_host are
+ * complete (submitting to a busy slot waits for it first). */
+int qsb_host_prune_quant_step_submit(qsb_host_ctx *ctx, int slot,
+                                     const float *x_host, const float *g_host,
+                                     float *y_host, float *gx_host,
+                                     float *magnitude_dev, uint8_t *mask_dev,
+                                     float *scale_dev, float *decimal_dev,
+                                     int64_t outer, int64_t channels,
+                                     int64_t inner, int64_t t_prune, int64_t k,
+                                     int bits, int64_t t_quant,
+                                     void *caller_stream);
+int qsb_host_ctx_wait(qsb_host_ctx *ctx, int slot);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,9 @@ _SIGNATURES = {
     "qsb_host_ctx_destroy": (c_int, [_P]),
     "qsb_host_prune_quant_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,
                                           c_int64, c_int, c_int64, _P]),
+    "qsb_host_prune_quant_step_submit": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64,
+                                                 c_int64, c_int64, c_int, c_int64, _P]),
+    "qsb_host_ctx_wait": (c_int, [_P, c_int]),
     "qsb_set_tuning": (c_int, [c_int, c_int]),
     "qsb_selftest_fastdiv": (c_int, [c_int64, c_int64, ctypes.c_uint64, _P, _P]),
 }

@@ -413,6 +413,10 @@ extern "C" int qsb_set_tuning(int key, int value) {
     set_row_stages(value);
     return 0;
   }
+  if (key == 12) {
+    set_pdl_enabled(value);
+    return 0;
+  }
   return QSB_E_BADARG;
 }
 

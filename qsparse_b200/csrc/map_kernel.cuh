@@ -85,6 +85,8 @@ MapTuning &map_tuning();
 template <class Op, int V, int U, Hint LH, Hint SH>
 __global__ void __launch_bounds__(QSB_THREADS)
     map_kernel(Op op, MapIO io, int64_t n, int reverse) {
+  pdl_wait();
+  pdl_trigger();
   using P = typename Op::P;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
   constexpr int64_t kStrideU = (int64_t)QSB_THREADS * V;
@@ -148,8 +150,7 @@ int launch_map_tensor(const Op &op, const MapIO &io, int64_t n,
   }
   if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;  // the kernel loops
   const int reverse = (grid == tiles && map_tuning().reverse_tiles) ? 1 : 0;
-  kern<<<(unsigned)grid, QSB_THREADS, 0, stream>>>(op, io, n, reverse);
-  QSB_LAUNCH_CHECK();
+  QSB_CUDA_TRY(launch_k(kern, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, op, io, n, reverse));
   return 0;
 }
 
@@ -178,6 +179,8 @@ __device__ __forceinline__ void advance32(uint32_t &col, uint32_t &c,
 template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
 __global__ void __launch_bounds__(QSB_THREADS)
     map_chan_kernel(Op op, MapIO io, int64_t n, ChanGeom G) {
+  pdl_wait();
+  pdl_trigger();
   using P = typename Op::P;
   extern __shared__ __align__(16) unsigned char qsb_smem_raw[];
   P *tab = reinterpret_cast<P *>(qsb_smem_raw);
@@ -298,6 +301,8 @@ template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
 __global__ void __launch_bounds__(QSB_THREADS)
     map_chan_win_kernel(Op op, MapIO io, int64_t n, uint32_t inner,
                         uint32_t channels, int reverse) {
+  pdl_wait();
+  pdl_trigger();
   using P = typename Op::P;
   static_assert(MODE == 0 || MODE == 1, "window kernel needs inner >= V");
   extern __shared__ __align__(16) unsigned char qsb_smem_raw[];
@@ -387,9 +392,8 @@ int launch_map_chan_win(const Op &op, const MapIO &io, int64_t n,
   const size_t rows_max = (size_t)((L.inner - 1 + kTile - 1) / L.inner + 2);
   const size_t smem = rows_max * sizeof(P);
   if (tiles > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
-  kern<<<(unsigned)tiles, QSB_THREADS, smem, stream>>>(
-      op, io, n, (uint32_t)L.inner, (uint32_t)L.channels, map_tuning().reverse_tiles ? 1 : 0);
-  QSB_LAUNCH_CHECK();
+  QSB_CUDA_TRY(launch_k(kern, dim3((unsigned)tiles), dim3(QSB_THREADS), smem, stream, op, io, n,
+                        (uint32_t)L.inner, (uint32_t)L.channels, map_tuning().reverse_tiles ? 1 : 0));
   return 0;
 }
 
@@ -421,8 +425,7 @@ int launch_map_chan_variant(const Op &op, const MapIO &io, int64_t n,
   G.su_ch = (uint32_t)((su / L.inner) % L.channels);
   G.si_cols = (uint32_t)(si % L.inner);
   G.si_ch = (uint32_t)((si / L.inner) % L.channels);
-  kern<<<(unsigned)grid, QSB_THREADS, smem, stream>>>(op, io, n, G);
-  QSB_LAUNCH_CHECK();
+  QSB_CUDA_TRY(launch_k(kern, dim3((unsigned)grid), dim3(QSB_THREADS), smem, stream, op, io, n, G));
   return 0;
 }
 

@@ -17,6 +17,10 @@
 
 namespace qsb {
 
+static int g_pdl_enabled = 1;  // tuning key 12 (default on: eager step 168.6 -> 165.1 us, = the CUDA-graph time)
+bool pdl_enabled() { return g_pdl_enabled != 0; }
+void set_pdl_enabled(int v) { g_pdl_enabled = v != 0; }
+
 const DeviceProps &device_props() {
   static DeviceProps props[64];
   static bool init[64] = {false};
@@ -210,6 +214,8 @@ __global__ void __launch_bounds__(1024)
   // graph mode: the step index lives on the device (the launch arguments of a captured
   // CUDA graph are frozen), the kernel reads it, derives t / stamp / refresh itself
   // and increments it at the end.  `refresh_mask` then carries the refresh interval.
+  pdl_wait();     // the partials come from the reduction launched just before
+  pdl_trigger();  // the forward kernel's CTAs may queue up behind this single CTA
   if (step_counter) {
     const long long t = *step_counter;
     t_prune = t;
@@ -523,12 +529,10 @@ extern "C" int qsb_prune_quant_step_params(
   if (pl.fin_count > 0x7fffffffLL || pl.fin_q > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
   int tpc = 32;  // threads per channel: largest power of two <= min(32, 1024 / channels)
   while (tpc > 1 && (int64_t)tpc * channels > 1024) tpc >>= 1;
-  prune_quant_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
-      magnitude, mask, scale, decimal_out, P, (int)pl.fin_count, (int)pl.fin_q,
-      (int)channels, tpc, px, (unsigned long long)step_stamp, count, t_prune,
-      update_magnitude,
-      refresh_mask, k, limit, t_quant, update_scale, abssum_out, absmax_out,
-      reinterpret_cast<long long *>(step_counter_dev));
-  QSB_LAUNCH_CHECK();
+  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, magnitude, mask,
+                        scale, decimal_out, P, (int)pl.fin_count, (int)pl.fin_q, (int)channels, tpc, px,
+                        (unsigned long long)step_stamp, count, t_prune, update_magnitude, refresh_mask, k,
+                        limit, t_quant, update_scale, abssum_out, absmax_out,
+                        reinterpret_cast<long long *>(step_counter_dev)));
   return 0;
 }

@@ -66,6 +66,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Launch policy of the streaming / reduction / parameter kernels (tuning key 12): with PDL
+// every such kernel starts with pdl_wait(), so it is ordered after ANY predecessor in the
+// stream exactly like an ordinary launch, but its launch latency and CTA ramp-up overlap
+// the predecessor's tail.
+bool pdl_enabled();
+void set_pdl_enabled(int v);
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t stream, Args... args) {
+  if (pdl_enabled()) return launch_pdl(kernel, grid, block, smem, stream, args...);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------------------
 // vector global-memory access.  V floats per access: 8 -> one 256-bit
 // LDG/STG (new on sm_100), 4 -> 128-bit, 1 -> scalar.

@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
     reduce_rows_kernel(const float *__restrict__ x, int64_t rows, int64_t inner,
                        int64_t seg, int64_t segs_per_row, int64_t vwarps,
                        Partials P) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps_phys = (int64_t)gridDim.x * (QSB_THREADS / 32);
   const int64_t items = rows * segs_per_row;
@@ -220,6 +222,8 @@ template <int WHAT, int G>
 __global__ void __launch_bounds__(QSB_THREADS)
     reduce_finalize_kernel(Partials P, FinalOut out, int64_t channels,
                            int64_t count, int64_t q) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int kGroupsPerBlock = QSB_THREADS / G;
   const int g = threadIdx.x / G;
   const int tg = threadIdx.x % G;
@@ -450,8 +454,8 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
     int64_t grid = (int64_t)device_props().sm_count * kRowCtasPerSm;
     const int64_t need = (pl.vwarps + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
-    reduce_rows_kernel<WHAT><<<(unsigned)grid, QSB_THREADS, 0, stream>>>(
-        x, pl.rows, inner, pl.seg, pl.segs_per_row, pl.vwarps, P);
+    QSB_CUDA_TRY(launch_k(reduce_rows_kernel<WHAT>, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, x,
+                          pl.rows, inner, pl.seg, pl.segs_per_row, pl.vwarps, P));
   } else {
     const int64_t threads = pl.ncols / pl.vcol;
     dim3 grid((unsigned)((threads + QSB_THREADS - 1) / QSB_THREADS),
@@ -467,14 +471,12 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
   if (!finalize) return 0;
   // few channels: a whole CTA per channel; many: a warp per channel
   if (pl.fin_count > 1024) {
-    reduce_finalize_kernel<WHAT, QSB_THREADS>
-        <<<(unsigned)channels, QSB_THREADS, 0, stream>>>(P, out, channels,
-                                                         pl.fin_count, pl.fin_q);
+    QSB_CUDA_TRY(launch_k(reduce_finalize_kernel<WHAT, QSB_THREADS>, dim3((unsigned)channels),
+                          dim3(QSB_THREADS), 0, stream, P, out, channels, pl.fin_count, pl.fin_q));
   } else {
     constexpr int kPer = QSB_THREADS / 32;
-    reduce_finalize_kernel<WHAT, 32>
-        <<<(unsigned)((channels + kPer - 1) / kPer), QSB_THREADS, 0, stream>>>(
-            P, out, channels, pl.fin_count, pl.fin_q);
+    QSB_CUDA_TRY(launch_k(reduce_finalize_kernel<WHAT, 32>, dim3((unsigned)((channels + kPer - 1) / kPer)),
+                          dim3(QSB_THREADS), 0, stream, P, out, channels, pl.fin_count, pl.fin_q));
   }
   QSB_LAUNCH_CHECK();
   return 0;
