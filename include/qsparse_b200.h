@@ -226,6 +226,27 @@ int qsb_magnitude_ema_full(float *magnitude, const float *x,
  *      (values = sort(flat); threshold = values[idx + 1])
  * ---------------------------------------------------------------------- */
 int64_t qsb_kth_workspace_bytes(int64_t n);
+/* The same select over values SHARDED across GPUs (one monolithic
+ * weight tensor split by element range): rank k_global is global, every GPU passes
+ * its n_local values.  Protocol, identical on every rank, same workspace throughout:
+ *   qsb_kth_dist_begin(ws)
+ *   for pass in 0, 1, 2:
+ *     qsb_kth_dist_pass(v, n_local, k_global, pass, ..., &hist, &count)
+ *     all-reduce(SUM) the `count` 64-bit counters at `hist` over the ranks
+ *     (e.g. ncclAllReduce ncclUint64 / torch.distributed on an int64 view)
+ *   qsb_kth_dist_final(k_global, ws, thr_out)   -> the same threshold everywhere
+ * Exact (integer histograms); 3 all-reduces of <= 32 KB.  The workspace is
+ * qsb_kth_workspace_bytes(n_local) bytes.  replaces: the reference has no multi-GPU
+ * path; equals calculate_mask_given_importance (qsparse/util.py:103-117) on the
+ * concatenated tensor. */
+int qsb_kth_dist_begin(void *workspace, int64_t workspace_bytes, void *stream);
+int qsb_kth_dist_pass(const float *v, int64_t n_local, int64_t k_global,
+                      int pass, int take_abs, void *workspace,
+                      int64_t workspace_bytes, void **hist_out,
+                      int64_t *hist_counters_out, void *stream);
+int qsb_kth_dist_final(int64_t k_global, void *workspace, float *thr_out_dev,
+                       void *stream);
+
 /* take_abs != 0 selects on |v| (importance = x.abs() without materialising it,
  * running_average=False, qsparse/sparse.py:63-64). */
 int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,

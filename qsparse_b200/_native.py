@@ -43,6 +43,10 @@ _SIGNATURES = {
     "qsb_magnitude_ema_full": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P]),
     "qsb_kth_workspace_bytes": (c_int64, [c_int64]),
     "qsb_kth_value": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),
+    "qsb_kth_dist_begin": (c_int, [_P, c_int64, _P]),
+    "qsb_kth_dist_pass": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, ctypes.POINTER(c_void_p),
+                                  ctypes.POINTER(c_int64), _P]),
+    "qsb_kth_dist_final": (c_int, [c_int64, _P, _P, _P]),
     "qsb_mask_from_threshold": (c_int, [_P, c_int, _P, _P, c_int64, _P]),
     "qsb_mask_build_apply": (c_int, [_P, c_int, _P, _P, _P, _P, c_int64, _P]),
     "qsb_prune_quant_params": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_double, c_int64, c_int,

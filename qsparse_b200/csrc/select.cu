@@ -468,9 +468,21 @@ __global__ void __launch_bounds__(QSB_THREADS)
       find_bin<kBins0>(ws.hist0, kk, &b0, &k1);
       find_bin<kBins1>(ws.hist1, k1, &b1, &k1);
       find_bin<kBins2>(ws.hist2, k1, &b2, &k1);
-      if (tid == 0) *thr_out = key_to_float((b0 << 24) | (b1 << 12) | b2);
+      if (tid == 0 && thr_out) *thr_out = key_to_float((b0 << 24) | (b1 << 12) | b2);
     }
   }
+}
+
+// the answer from three (globally complete) histograms: the last step of a select whose
+// histograms were summed over several GPUs between the passes
+__global__ void __launch_bounds__(QSB_THREADS)
+    select_final_kernel(SelectWs ws, int64_t k, float *thr_out) {
+  unsigned long long k1;
+  uint32_t b0, b1, b2;
+  find_bin<kBins0>(ws.hist0, (unsigned long long)k, &b0, &k1);
+  find_bin<kBins1>(ws.hist1, k1, &b1, &k1);
+  find_bin<kBins2>(ws.hist2, k1, &b2, &k1);
+  if (threadIdx.x == 0) *thr_out = key_to_float((b0 << 24) | (b1 << 12) | b2);
 }
 
 // ---------------------------------------------------------------------------
@@ -941,4 +953,62 @@ extern "C" int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
                     : run_passes<8, false>(v, n, k, ws, fb, st, thr_out_dev, stream);
   return take_abs ? run_passes<1, true>(v, n, k, ws, fb, st, thr_out_dev, stream)
                   : run_passes<1, false>(v, n, k, ws, fb, st, thr_out_dev, stream);
+}
+
+// ---------------------------------------------------------------------------
+// sharded select: the values live on several GPUs (each holds n_local of them); the rank k is
+// global.  Per pass every GPU histograms its shard with the prefix derived from the
+// (already summed) earlier histograms, the caller sums the new histogram over the GPUs
+// (an all-reduce of <= 32 KB of 64-bit counters: exact), and after the third pass
+// qsb_kth_dist_final reads the answer — identical on every GPU.  SURVEY 8(e), weights.
+// ---------------------------------------------------------------------------
+static SelectWs dist_ws(void *workspace) {
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
+  SelectWs ws;
+  ws.hist0 = reinterpret_cast<unsigned long long *>(base);
+  ws.hist1 = ws.hist0 + kBins0;
+  ws.hist2 = ws.hist1 + kBins1;
+  return ws;
+}
+
+extern "C" int qsb_kth_dist_begin(void *workspace, int64_t workspace_bytes, void *stream) {
+  if (!workspace || workspace_bytes < qsb_kth_workspace_bytes(0)) return QSB_E_WORKSPACE;
+  QSB_CUDA_TRY(cudaMemsetAsync(dist_ws(workspace).hist0, 0, kSelectHeaderBytes, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int qsb_kth_dist_pass(const float *v, int64_t n_local, int64_t k_global, int pass,
+                                 int take_abs, void *workspace, int64_t workspace_bytes,
+                                 void **hist_out, int64_t *hist_counters_out, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_local < 0 || k_global < 0 || pass < 0 || pass > 2) return QSB_E_BADARG;
+  if (!workspace || workspace_bytes < qsb_kth_workspace_bytes(0)) return QSB_E_WORKSPACE;
+  if (n_local > 0 && (!v || !aligned_to(v, 4))) return QSB_E_ALIGN;
+  const SelectWs ws = dist_ws(workspace);
+  unsigned long long *h = pass == 0 ? ws.hist0 : pass == 1 ? ws.hist1 : ws.hist2;
+  if (hist_out) *hist_out = h;
+  if (hist_counters_out) *hist_counters_out = pass == 0 ? kBins0 : kBins1;
+  if (n_local == 0) return 0;  // an empty shard still takes part in the all-reduce
+  SelState *st = reinterpret_cast<SelState *>(
+      reinterpret_cast<unsigned char *>(ws.hist0) + kHistBytes + kFastHistBytes + kSegCtrBytes);
+  const FastBufs fb{nullptr, nullptr, nullptr, nullptr, 0};
+  const bool v32 = aligned_to(v, 32);
+#define QSB_DIST_PASS(P)                                                                         \
+  (v32 ? (take_abs ? launch_pass<P, 8, true>(v, n_local, k_global, ws, fb, st, nullptr, stream, false)  \
+                   : launch_pass<P, 8, false>(v, n_local, k_global, ws, fb, st, nullptr, stream, false)) \
+       : (take_abs ? launch_pass<P, 1, true>(v, n_local, k_global, ws, fb, st, nullptr, stream, false)  \
+                   : launch_pass<P, 1, false>(v, n_local, k_global, ws, fb, st, nullptr, stream, false)))
+  if (pass == 0) return QSB_DIST_PASS(0);
+  if (pass == 1) return QSB_DIST_PASS(1);
+  return QSB_DIST_PASS(2);
+#undef QSB_DIST_PASS
+}
+
+extern "C" int qsb_kth_dist_final(int64_t k_global, void *workspace, float *thr_out_dev,
+                                  void *stream) {
+  if (!workspace || !thr_out_dev || k_global < 0) return QSB_E_BADARG;
+  select_final_kernel<<<1, QSB_THREADS, 0, (cudaStream_t)stream>>>(dist_ws(workspace), k_global,
+                                                                   thr_out_dev);
+  QSB_LAUNCH_CHECK();
+  return 0;
 }

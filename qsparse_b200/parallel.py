@@ -152,3 +152,93 @@ def combine_rows_host(gathered: torch.Tensor, n_rows: int, row_bytes: int, chann
         total = total + row[: 8 * channels].view(torch.float64)
         amax = torch.maximum(amax, row[8 * channels: 12 * channels].view(torch.float32).abs())
     return total, amax
+
+
+# ----------------------------------------------------------------------------- weights
+def layer_owner(layer_index: int, world: int) -> int:
+    """Round-robin assignment of prune layers to ranks: the thresholds of different layers are
+    independent, so the expensive part of an unstructured prune step (the k-th value of every
+    layer's importance) shards by layer."""
+    return layer_index % world
+
+
+def combine_thresholds(local: torch.Tensor, group=None) -> torch.Tensor:
+    """``local[i]`` holds the threshold of layer i on its owner and 0 elsewhere; one all-reduce
+    (SUM of one non-zero term: exact) leaves every threshold on every rank."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(local, op=dist.ReduceOp.SUM, group=group)
+    return local
+
+
+def sharded_layer_thresholds(importances, ks, group=None, take_abs=False) -> torch.Tensor:
+    """Thresholds ``sorted(importances[i])[ks[i]]`` for a set of (replicated) layers: every rank
+    selects only on the layers it owns, then one all-reduce of L floats.  Returns a float32
+    tensor [L] on the importances' device, identical on every rank (and equal to the
+    single-process thresholds: the select is exact)."""
+    from . import ops
+
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else 0
+    dev = importances[0].device
+    thr = torch.zeros(len(importances), dtype=torch.float32, device=dev)
+    for i, (imp, k) in enumerate(zip(importances, ks)):
+        if layer_owner(i, world) == rank:
+            thr[i:i + 1] = ops.kth_value(imp.reshape(-1), int(k), take_abs=take_abs)
+    return combine_thresholds(thr, group)
+
+
+def sharded_kth_value(v_local: torch.Tensor, k_global: int, group=None, take_abs=False) -> torch.Tensor:
+    """k-th smallest value (0-based, global rank) of a tensor SHARDED over the ranks of ``group``
+    by element range: three local histogram passes, each followed by an all-reduce (SUM) of the
+    integer histogram (<= 32 KB) — exact, identical on every rank, and the bulk tensor never
+    leaves its GPU.  ``qsb_kth_dist_*`` in include/qsparse_b200.h."""
+    import ctypes
+    from ctypes import byref, c_int, c_int64, c_void_p
+
+    from . import _native as N
+
+    lib = N.load_library()
+    N.require_cuda(v_local, "v_local")
+    v = N.as_f32_contiguous(v_local.detach()).reshape(-1)
+    n = v.numel()
+    dev = v.device
+    nbytes = lib.qsb_kth_workspace_bytes(c_int64(n))
+    ws = N.workspace(dev, nbytes)
+    stream = N.stream_ptr(dev)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    N.check(lib.qsb_kth_dist_begin(N.ptr(ws), c_int64(ws.numel()), stream), "qsb_kth_dist_begin")
+    for p in range(3):
+        hist, count = c_void_p(), c_int64()
+        N.check(lib.qsb_kth_dist_pass(N.ptr(v) if n else c_void_p(0), c_int64(n), c_int64(int(k_global)), c_int(p),
+                                      c_int(1 if take_abs else 0), N.ptr(ws), c_int64(ws.numel()), byref(hist),
+                                      byref(count), stream), "qsb_kth_dist_pass")
+        if multi:
+            off = hist.value - ws.data_ptr()
+            h = ws[off: off + 8 * count.value].view(torch.int64)   # 64-bit counters (< 2^63)
+            dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+    thr = torch.empty(1, dtype=torch.float32, device=dev)
+    N.check(lib.qsb_kth_dist_final(c_int64(int(k_global)), N.ptr(ws), N.ptr(thr), stream), "qsb_kth_dist_final")
+    return thr
+
+
+def prune_weight_set_step(weights, magnitudes, masks, outs, t: int, sparsity: float, group=None):
+    """One unstructured, running-average prune step over a set of replicated weight tensors
+    (BASELINE config 4) on every rank of ``group``:
+
+        magnitude EMA (replicated, 12 B/elem)  ref sparse.py:82-89
+        k-th value per layer, sharded by layer + one all-reduce of L floats  ref util.py:103-117
+        mask = magnitude >= thr, out = w * mask (replicated, 13 B/elem)       ref sparse.py:65-66,116
+
+    ``t`` is the callback's step counter.  Results equal ``MagnitudePruningCallback`` run on one
+    GPU, bit for bit."""
+    from . import ops
+    from .util import kth_rank
+
+    for w, mag in zip(weights, magnitudes):
+        ops.magnitude_ema_full_(mag, w, t)
+    ks = [kth_rank(sparsity, m.numel()) for m in magnitudes]
+    thr = sharded_layer_thresholds(magnitudes, ks, group)
+    for i, (w, mag, mask, out) in enumerate(zip(weights, magnitudes, masks, outs)):
+        ops.mask_build_apply(mag, thr[i:i + 1], w, mask, out=out)
+    return thr

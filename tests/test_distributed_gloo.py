@@ -68,3 +68,36 @@ def test_two_rank_stat_exchange_gloo():
         p.join(150)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert out.get(timeout=5) == "ok"
+
+
+def _thr_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qsparse_b200.parallel import combine_thresholds, layer_owner
+    L = 7
+    truth = torch.tensor([0.5, -0.0, 3e-7, float("inf"), 1.25, 0.0, 9.0])
+    local = torch.zeros(L)
+    owned = [i for i in range(L) if layer_owner(i, world) == rank]
+    for i in owned:
+        local[i] = truth[i]
+    got = combine_thresholds(local)
+    assert torch.equal(got, truth), (rank, got)           # (-0.0 == 0.0: the mask compare is unaffected)
+    assert sorted(owned) == list(range(rank, L, world))
+    if rank == 0:
+        out.put("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_layer_sharded_thresholds_gloo():
+    """host logic of the layer-sharded prune step: round-robin ownership, one all-reduce"""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_thr_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert out.get(timeout=5) == "ok"

@@ -74,3 +74,107 @@ def test_two_gpu_peer_memory_exchange_equals_single_process():
             lo, hi = r["rank"] * per_rank, (r["rank"] + 1) * per_rank
             assert np.array_equal(r["y"][t], ys[t][lo:hi]), t
     assert results[0]["p2p"] == results[1]["p2p"]
+
+
+# ----------------------------------------------------------------------------- weights
+def _weight_set(seed=4):
+    rng = np.random.default_rng(seed)
+    shapes = [(64, 32, 3, 3), (128, 64, 3, 3), (40, 1000), (7, 13, 5), (256, 256, 3, 3)]
+    return [(rng.standard_normal(s) * 0.02).astype(np.float32) for s in shapes]
+
+
+def _weights_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from qsparse_b200 import parallel
+    # (a) one monolithic tensor sharded by element range (uneven shards, one with ties)
+    rng = np.random.default_rng(11)
+    full = (rng.standard_normal(3_000_017) * 0.02).astype(np.float32)
+    full[::7] = 0.0
+    cut = 1_200_003
+    shard = torch.from_numpy(full[:cut] if rank == 0 else full[cut:]).cuda()
+    ks = [0, 5, full.size // 2, (3 * full.size) // 4, full.size - 1]
+    got = [parallel.sharded_kth_value(shard, k, take_abs=True).item() for k in ks]
+    got_signed = [parallel.sharded_kth_value(shard, k).item() for k in ks]
+    # (b) a replicated weight set: layer-sharded thresholds, replicated EMA and apply
+    ws = [torch.from_numpy(w).cuda() for w in _weight_set()]
+    mags = [torch.zeros_like(w) for w in ws]
+    masks = [torch.ones(w.shape, dtype=torch.bool, device=w.device) for w in ws]
+    outs = [torch.empty_like(w) for w in ws]
+    thr_hist = []
+    for t in range(3):
+        for w in ws:
+            w.mul_(1.0 + 0.05 * t)
+        thr = parallel.prune_weight_set_step(ws, mags, masks, outs, t, 0.75)
+        thr_hist.append(thr.cpu().numpy())
+    out.put(dict(rank=rank, kth=got, kth_signed=got_signed, thr=thr_hist,
+                 masks=[m.cpu().numpy() for m in masks], outs=[o.cpu().numpy() for o in outs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_select_and_layer_sharded_prune():
+    import torch.multiprocessing as mp
+    from qsparse_b200 import parallel
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_weights_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out.get(timeout=240) for _ in range(world)], key=lambda r: r["rank"])
+    for p in procs:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    rng = np.random.default_rng(11)
+    full = (rng.standard_normal(3_000_017) * 0.02).astype(np.float32)
+    full[::7] = 0.0
+    ks = [0, 5, full.size // 2, (3 * full.size) // 4, full.size - 1]
+    ref_abs, ref = np.sort(np.abs(full)), np.sort(full)
+    for r in results:
+        assert [np.float32(v) for v in r["kth"]] == [ref_abs[k] for k in ks]
+        assert [np.float32(v) for v in r["kth_signed"]] == [ref[k] for k in ks]
+    # single process, same steps
+    ws = [torch.from_numpy(w).cuda() for w in _weight_set()]
+    mags = [torch.zeros_like(w) for w in ws]
+    masks = [torch.ones(w.shape, dtype=torch.bool, device=w.device) for w in ws]
+    outs = [torch.empty_like(w) for w in ws]
+    for t in range(3):
+        for w in ws:
+            w.mul_(1.0 + 0.05 * t)
+        thr = parallel.prune_weight_set_step(ws, mags, masks, outs, t, 0.75)
+        for r in results:
+            assert np.array_equal(r["thr"][t], thr.cpu().numpy()), t
+    for r in results:
+        for i in range(len(ws)):
+            assert np.array_equal(r["masks"][i], masks[i].cpu().numpy())
+            assert np.array_equal(r["outs"][i].view(np.int32), outs[i].cpu().numpy().view(np.int32))
+
+
+def test_weight_set_step_equals_magnitude_callback():
+    """prune_weight_set_step (one process) == MagnitudePruningCallback(running_average=True) per layer,
+    and sharded_kth_value == ops.kth_value == sort."""
+    from qsparse_b200 import ops, parallel
+    from qsparse_b200.sparse import MagnitudePruningCallback
+    ws = [torch.from_numpy(w).cuda() for w in _weight_set(5)]
+    mags = [torch.zeros_like(w) for w in ws]
+    masks = [torch.ones(w.shape, dtype=torch.bool, device=w.device) for w in ws]
+    outs = [torch.empty_like(w) for w in ws]
+    cbs = [MagnitudePruningCallback(running_average=True) for _ in ws]
+    cb_masks = [torch.ones(w.shape, dtype=torch.bool, device=w.device) for w in ws]
+    for cb in cbs:
+        cb.train()
+    for t in range(3):
+        parallel.prune_weight_set_step(ws, mags, masks, outs, t, 0.5)
+        for w, cb, m, mine, o in zip(ws, cbs, cb_masks, masks, outs):
+            y = cb(w, 0.5, m)
+            if t > 0:      # the callback does not refresh the mask at t == 0 with a running average
+                assert torch.equal(m, mine) and torch.equal(y, o), t
+    v = ws[1].reshape(-1)
+    for k in (0, v.numel() // 3, v.numel() - 1):
+        assert torch.equal(parallel.sharded_kth_value(v, k), ops.kth_value(v, k))
+        assert parallel.sharded_kth_value(v, k).item() == torch.sort(v).values[k].item()
