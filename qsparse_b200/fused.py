@@ -116,3 +116,147 @@ class PruneQuantize(nn.Module):
     def forward(self, x):
         N.require_cuda(x, "x")
         return _PruneQuantizeFn.apply(x, self)
+
+
+# ----------------------------------------------------------------------------- fusion pass
+class _FusedLayersFn(torch.autograd.Function):
+    """forward value and backward of ``QuantizeLayer(PruneLayer(x))`` in its steady state, on the two
+    layers' own state tensors: y = Q(x * mask), gx = clamp(g) * mask (grad_output clamped in place, like
+    DecimalQuantization.backward does, ref quantize.py:65-77, sparse.py backward of x * mask)."""
+
+    @staticmethod
+    def forward(ctx, x, xs, layout, mask, decimal, bits, notch):
+        ctx.layout, ctx.mask, ctx.decimal, ctx.bits, ctx.notch = layout, mask, decimal, bits, notch
+        return ops.fq_pow2_fwd(xs, decimal, layout, mask=mask).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        g = grad_output
+        if g.dtype != torch.float32:
+            g = g.float()
+        if not g.is_contiguous():
+            g = g.contiguous()
+        _, gx = ops.ste_bwd(g, ctx.decimal, True, ctx.bits, ctx.notch, ctx.layout, mask=ctx.mask,
+                            clamp_in_place=True, want_gx=True)
+        return (gx,) + (None,) * 6
+
+
+class FusedPruneQuantSequential(nn.Sequential):
+    """``Sequential(Sequential(act, PruneLayer), QuantizeLayer)`` (what two ``convert()`` calls build around
+    an activation, ref qsparse/convert.py:214-217) or ``Sequential(PruneLayer, QuantizeLayer)``, with the
+    SAME children — module tree and ``state_dict`` keys are untouched — whose forward sends every
+    steady-state training step through the fused kernels (reduce -> one parameter kernel -> quantize with
+    the mask folded in: 20 B/elem with the backward, instead of ~60 + 16).
+
+    A step is fused only when it is provably the plain case: both layers initialised, training, structured
+    channel prune (``dimensions={1}``) by the stock ``MagnitudePruningCallback`` (no gradient / l0 / hook
+    variants), pruning started and the sparsity not changing at this step, per-tensor stock
+    ``DecimalQuantizer`` past its timeout.  Every other step (warm-up, ramp steps, eval, other callbacks,
+    non-contiguous inputs) runs the two layers one after the other, exactly as before.  Counters and
+    parameters advance identically either way, so the two routes can alternate freely."""
+
+    fused_steps = 0  # how many forwards took the fused route (per instance once incremented)
+
+    def _layers(self):
+        first, q = self[0], self[1]
+        if isinstance(first, nn.Sequential):
+            return first[0], first[1], q
+        return None, first, q
+
+    def _fusable(self, p, q, x):
+        from .quantize import DecimalQuantizer, QuantizeLayer
+        from .sparse import MagnitudePruningCallback, PruneLayer
+
+        if not (isinstance(p, PruneLayer) and isinstance(q, QuantizeLayer) and self.training and p.training
+                and q.training):
+            return False
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() >= 2 and x.is_contiguous()):
+            return False
+        cb, qcb = p.callback, q.callback
+        if type(cb) is not MagnitudePruningCallback or type(qcb) is not DecimalQuantizer:
+            return False
+        if cb.use_gradient or cb.l0 or cb.forward_hook is not None or not cb.training or not qcb.training:
+            return False
+        if p.dimensions != {1} or not p.initted or not q.initted or p.mask.numel() == 1:
+            return False
+        if p.mask.numel() != x.shape[1] or p.mask.numel() > 2048:
+            return False
+        n = p._n_mirror.get(p._n_updates)
+        if n < p.start or n in p.schedules:
+            return False
+        if not cb.initted or cb._t() >= cb.stop_mask_refresh or cb.mask_refresh_interval <= 0:
+            return False
+        if cb.running_average and not hasattr(cb, "magnitude"):
+            return False
+        if q.channelwise >= 0 or q.timeout <= 0 or q._t_mirror.get(q._n_updates) < q.timeout:
+            return False
+        if qcb.backward_passthrough or qcb.use_float_scaler or qcb.group_num > 0:
+            return False
+        if tuple(q.weight.shape) != (1, 1) or p._s_mirror.get(p._cur_sparsity) < 0:
+            return False
+        return True
+
+    def _fused_step(self, p, q, x):
+        cb, qcb = p.callback, q.callback
+        layout = N.channel_layout(x.shape, 1)
+        outer, ch, inner = layout
+        xs = N.as_f32_contiguous(x.detach())
+        sparsity = p._s_mirror.get(p._cur_sparsity)
+        t = cb._t()
+        refresh = (t % cb.mask_refresh_interval == 0 and t <= cb.stop_mask_refresh) and \
+            (t > 0 or not cb.running_average)
+        k = kth_rank(sparsity, ch)
+        if k >= ch:
+            raise IndexError(f"index {k} is out of bounds for dimension 0 with size {ch}")
+        decimal = torch.empty(1, dtype=torch.float32, device=x.device)
+        with torch.no_grad():
+            if cb.running_average:
+                magnitude, mode = cb.magnitude.data.view(-1), 1
+            else:
+                magnitude, mode = torch.empty(ch, dtype=torch.float32, device=x.device), 2
+            ws = ops.reduce_partials(xs, layout)
+            ops.prune_quant_step_params(magnitude, p.mask.data.view(-1), q.weight.data.view(-1), decimal, ws, layout,
+                                        float(outer * inner), t, mode, refresh, k, q.bits, qcb.t, True)
+            # the counters of the two layers and their callbacks, as their own forwards advance them
+            cb.t += 1
+            cb._t_mirror.wrote(cb.t, t + 1)
+            n = p._n_mirror.get(p._n_updates)
+            p._n_updates += 1
+            p._n_mirror.wrote(p._n_updates, n + 1)
+            qcb.t += 1
+            q._quantized = True
+            tq = q._t_mirror.get(q._n_updates)
+            q._n_updates += 1
+            q._t_mirror.wrote(q._n_updates, tq + 1)
+        self.fused_steps += 1
+        return _FusedLayersFn.apply(x, xs, layout, p.mask.data.view(-1), decimal, q.bits,
+                                    1 if qcb.flip_axis else 0)
+
+    def forward(self, x):
+        pre, p, q = self._layers()
+        if pre is not None:
+            x = pre(x)
+        if self._fusable(p, q, x):
+            return self._fused_step(p, q, x)
+        return q(p(x))
+
+
+def fuse_prune_quantize(model: nn.Module) -> nn.Module:
+    """Fusion pass over a converted model (in place): every ``Sequential(Sequential(m, PruneLayer),
+    QuantizeLayer)`` / ``Sequential(PruneLayer, QuantizeLayer)`` becomes a ``FusedPruneQuantSequential``
+    (same children, same ``state_dict``).  Returns the model."""
+    from .quantize import QuantizeLayer
+    from .sparse import PruneLayer
+
+    def is_site(m):
+        if type(m) is not nn.Sequential or len(m) != 2 or not isinstance(m[1], QuantizeLayer):
+            return False
+        first = m[0]
+        if isinstance(first, PruneLayer):
+            return True
+        return type(first) is nn.Sequential and len(first) == 2 and isinstance(first[1], PruneLayer)
+
+    for mod in list(model.modules()):
+        if is_site(mod):
+            mod.__class__ = FusedPruneQuantSequential
+    return model

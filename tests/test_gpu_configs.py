@@ -201,3 +201,58 @@ def test_preload_state_dict_roundtrip():
     conv3.quantize._quantized = True                          # not part of state_dict
     assert np.allclose(npy(conv(x)), npy(conv3(x)), atol=1e-5)
     assert int((~conv3.prune.mask).sum().item()) > 0
+
+
+# ----------------------------------------------------------------------------- fusion pass
+def _converted_net(fuse: bool):
+    import qsparse_b200 as q
+    torch.manual_seed(7)
+    net = torch.nn.Sequential(
+        torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.ReLU(),
+        torch.nn.Conv2d(16, 24, 3, padding=1), torch.nn.ReLU(),
+        torch.nn.Flatten(), torch.nn.Linear(24 * 8 * 8, 10)).cuda()
+    net = q.convert(net, q.prune(sparsity=0.5, dimensions={1}, start=2, interval=3, repetition=2),
+                    activation_layers=[torch.nn.ReLU], log=False)
+    net = q.convert(net, q.quantize(bits=8, channelwise=-1, timeout=4, callback=q.DecimalQuantizer()),
+                    activation_layers=[torch.nn.ReLU], log=False)
+    if fuse:
+        net = q.fuse_prune_quantize(net)
+    return net
+
+
+def test_fusion_pass_equals_unfused_layers():
+    """fuse_prune_quantize keeps the module tree / state_dict keys and gives bit-identical outputs, gradients
+    and layer state over warm-up, ramp, steady-state and eval steps; the fused route is actually taken."""
+    from qsparse_b200.fused import FusedPruneQuantSequential
+    torch.backends.cudnn.deterministic = True      # the two nets must see identical conv arithmetic
+    torch.backends.cudnn.benchmark = False
+    a, b = _converted_net(False), _converted_net(True)
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    sites = [m for m in b.modules() if isinstance(m, FusedPruneQuantSequential)]
+    assert len(sites) == 2
+    a.train()
+    b.train()
+    for step in range(14):
+        x = torch.randn(8, 3, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(100 + step))
+        if step == 11:            # an eval step in between
+            a.eval()
+            b.eval()
+        ya, yb = a(x), b(x)
+        assert torch.equal(ya, yb), step
+        if step != 11:
+            ya.square().mean().backward()
+            yb.square().mean().backward()
+            for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+                if pa.grad is not None:
+                    assert torch.equal(pa.grad, pb.grad), (step, na)
+                    pa.grad = pb.grad = None
+        sa, sb = a.state_dict(), b.state_dict()
+        assert sa.keys() == sb.keys()
+        for key in sa:
+            assert torch.equal(sa[key], sb[key]), (step, key)
+        a.train()
+        b.train()
+    assert all(s.fused_steps >= 6 for s in sites), [s.fused_steps for s in sites]
+    # checkpoint interchange: the unfused model loads the fused model's state and vice versa
+    a.load_state_dict(b.state_dict())
+    b.load_state_dict(a.state_dict())
