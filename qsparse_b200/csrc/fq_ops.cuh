@@ -15,6 +15,17 @@ __device__ __forceinline__ float mask_mul(float x, bool keep) {
   return __fmul_rn(x, keep ? 1.0f : 0.0f);
 }
 
+// min(max(v, lo), hi) with NaN-PROPAGATING FMNMX (one instruction each instead of compare +
+// select): the same value as clamp_torch for finite bounds — a NaN v stays NaN (canonical
+// payload), and the one sign-of-zero difference (v = -0, lo = +0 gives +0) cannot reach the
+// output of the line quantizer (q * step + lo rounds both to the same value).
+__device__ __forceinline__ float clamp_fmnmx_nan(float v, float lo, float hi) {
+  float t, r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(t) : "f"(v), "f"(lo));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(t), "f"(hi));
+  return r;
+}
+
 // torch.clamp(v, min=Tensor, max=Tensor): a NaN bound makes the result NaN.
 __device__ __forceinline__ float clamp_torch_tensor(float v, float lo,
                                                     float hi) {
@@ -214,17 +225,23 @@ struct LineOp {
     float t = a;
     if constexpr (MASK == QSB_MASK_CHANNEL) t = __fmul_rn(a, p.m);
     if constexpr (MASK == QSB_MASK_ELEMENT) t = mask_mul(a, mb != 0);
-    const float kMagic = 12582912.0f;             // 1.5 * 2^23
-    const float xc = clamp_torch(t, p.lo, p.hi);  // (:158) bounds are finite here
+    const float kMagic = 12582912.0f;                  // 1.5 * 2^23
+    const float xc = clamp_fmnmx_nan(t, p.lo, p.hi);   // (:158) bounds are finite here
     if constexpr (FZP) {
-      float q = div_rn_by_unchecked(__fsub_rn(xc, p.lo), p.step, p.rstep);  // (:176-177)
+      // xc - lo >= +0: the zero-sign fix-up of the exact division is dead here
+      const float d = __fsub_rn(xc, p.lo);
+      const float q0 = __fmul_rn(d, p.rstep);                                 // (:176-177)
+      float e = __fmaf_rn(-p.step, q0, d);
+      float q = __fmaf_rn(e, p.rstep, q0);
+      e = __fmaf_rn(-p.step, q, d);
+      q = __fmaf_rn(e, p.rstep, q);
       q = __fsub_rn(__fadd_rn(q, kMagic), kMagic);                            // round_ (:178)
-      q = clamp_torch(q, 0.0f, q_max);
+      q = clamp_fmnmx_nan(q, 0.0f, q_max);
       o0 = __fadd_rn(__fmul_rn(q, p.step), p.lo);                             // (:179-180)
     } else {
       float q = div_rn_by_unchecked(xc, p.step, p.rstep);
       q = __fsub_rn(__fadd_rn(q, kMagic), kMagic);                            // (:162)
-      q = clamp_torch(__fsub_rn(q, p.qstart), 0.0f, q_max);                   // (:164)
+      q = clamp_fmnmx_nan(__fsub_rn(q, p.qstart), 0.0f, q_max);               // (:164)
       o0 = __fmul_rn(__fadd_rn(q, p.qstart), p.step);                         // (:165)
     }
   }
