@@ -186,11 +186,15 @@ def main():
     del wt, magf, yb, mk, x, g, y
 
     # ---------------- config 5: flat sweep, fused prune(element mask) + pow2 quant fwd, bwd
-    for p in ([22, 26] if args.quick else [20, 22, 24, 26, 28, 30]):
+    for p in ([22, 26] if args.quick else [20, 22, 24, 26, 28, 30, 32]):
         n5 = 1 << p
-        x5 = torch.randn(n5, device=dev)
+        x5 = torch.empty(n5, device=dev)
+        m5 = torch.empty(n5, dtype=torch.bool, device=dev)
+        for lo in range(0, n5, 1 << 28):              # fill in 1 GiB pieces: no 16 GB temporaries at 2^32
+            hi = min(lo + (1 << 28), n5)
+            x5[lo:hi].normal_()
+            m5[lo:hi] = torch.rand(hi - lo, device=dev) > 0.5
         y5 = torch.empty_like(x5)
-        m5 = torch.rand(n5, device=dev) > 0.5
         report("c5_fused_fwd", 9 * n5, lambda: ops.fq_pow2_fwd(x5, dec1, (1, 1, n5), mask=m5, out=y5), log2n=p)
         report("c5_fused_bwd", 9 * n5, lambda: ops.ste_bwd(x5, dec1, True, 8, 0, (1, 1, n5), mask=m5,
                                                            clamp_in_place=False, want_gx=True), log2n=p)

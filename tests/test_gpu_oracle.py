@@ -517,3 +517,63 @@ def test_weight_layer_fused_equals_unfused(cb_name):
         assert torch.equal(sa[k], sb[k]), k
     for (ya, ga), (yb, gb) in zip(ra, rb):
         assert torch.equal(ya, yb) and torch.equal(ga, gb)
+
+
+def test_int64_indexing_4G_elements():
+    """BASELINE config 5's largest size: 2^32 + 24 elements (element indices do not fit 32 bits).  The
+    per-tensor and element-mask kernels, the STE backward, the per-channel window kernel and the
+    reductions must address the whole tensor: checked on slices around 2^31, 2^32 and the end against
+    the plain torch formula (bit-exact), plus an untouched-canary check past the end."""
+    from qsparse_b200 import ops
+    free, _ = torch.cuda.mem_get_info()
+    n = (1 << 32) + 24
+    if free < 60 * (1 << 30):
+        pytest.skip("needs ~45 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    buf = torch.empty(n + 64, device="cuda")
+    x = buf[:n]
+    for lo in range(0, n, 1 << 28):                       # fill in 1 GiB pieces (no 16 GB temporary)
+        hi = min(lo + (1 << 28), n)
+        x[lo:hi].normal_(generator=g)
+    x[(1 << 32) + 3] = 77.25                              # the tensor's abs-max lives beyond 2^32
+    ybuf = torch.full((n + 64,), -123.0, device="cuda")
+    y = ybuf[:n]
+    ops.fq_pow2_fwd(x, 4.0, (1, 1, n), out=y)
+    spots = [0, (1 << 31) - 4096, (1 << 31), (1 << 32) - 4096, (1 << 32), n - 4096]
+
+    def ref_q(v):
+        return (v * 16.0).int().float() * 0.0625
+    for s in spots:
+        sl = slice(s, min(s + 4096, n))
+        assert torch.equal(y[sl], ref_q(x[sl])), s
+    assert torch.all(ybuf[n:] == -123.0)                  # nothing written past the end
+    # element mask fused forward + backward
+    mask = torch.empty(n, dtype=torch.bool, device="cuda")
+    for lo in range(0, n, 1 << 28):
+        hi = min(lo + (1 << 28), n)
+        mask[lo:hi] = x[lo:hi] > -0.3
+    ops.fq_pow2_fwd(x, 4.0, (1, 1, n), mask=mask, out=y)
+    for s in spots:
+        sl = slice(s, min(s + 4096, n))
+        assert torch.equal(y[sl], ref_q(x[sl] * mask[sl])), s
+    _, gx = ops.ste_bwd(x, 4.0, True, 8, 0, (1, 1, n), mask=mask, clamp_in_place=False, want_gx=True)
+    for s in spots:
+        sl = slice(s, min(s + 4096, n))
+        want = torch.clamp(x[sl], -128 / 16.0, 127 / 16.0) * mask[sl]
+        assert torch.equal(gx[sl], want), s
+    del gx, mask
+    # reductions: per tensor and per channel ([4, C = 8, inner]) over the whole 4G range
+    st = ops.reduce_stats(x, (1, 1, n), absmax=True)
+    assert st["absmax"].item() == 77.25
+    inner = n // 32
+    st = ops.reduce_stats(x[: 32 * inner], (4, 8, inner), absmax=True, minmax=True)
+    view = x[: 32 * inner].view(4, 8, inner)
+    assert torch.equal(st["max"], view.amax(dim=(0, 2))) and torch.equal(st["min"], view.amin(dim=(0, 2)))
+    # per-channel decimals through the window kernel
+    dec = torch.arange(8, device="cuda", dtype=torch.float32)
+    ops.fq_pow2_fwd(x[: 32 * inner], dec, (4, 8, inner), out=y[: 32 * inner])
+    yv = y[: 32 * inner].view(4, 8, inner)
+    for o, c in ((0, 0), (1, 7), (3, 7), (2, 3)):
+        d = float(c)
+        seg = view[o, c, -2048:]
+        assert torch.equal(yv[o, c, -2048:], (seg * 2.0 ** d).int().float() * 2.0 ** -d), (o, c)
