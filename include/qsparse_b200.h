@@ -253,6 +253,17 @@ int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
                   float *thr_out_dev, void *workspace, int64_t workspace_bytes,
                   void *stream);
 
+/* `count` independent selects (the layers of a weight set) in one
+ * launch sequence: v[i] has n[i] values, thr_out_dev[i] = its k[i]-th smallest.  The
+ * pointer / size arrays are HOST arrays (read during the call).  Segments of >= 2^17
+ * values take the sampled-pivot route together (blockIdx.y = segment), so 29 layers of
+ * 2.4 M values cost about as much as one select over their total. */
+int64_t qsb_kth_batched_workspace_bytes(const int64_t *n, int count);
+int qsb_kth_value_batched(const float *const *v, const int64_t *n,
+                          const int64_t *k, int count, int take_abs,
+                          float *thr_out_dev, void *workspace,
+                          int64_t workspace_bytes, void *stream);
+
 /* ref: calculate_mask_given_importance qsparse/util.py:117  mask = imp >= thr */
 int qsb_mask_from_threshold(const float *importance, int take_abs,
                             const float *thr_dev, uint8_t *mask_out, int64_t n,

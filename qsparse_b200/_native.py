@@ -43,6 +43,9 @@ _SIGNATURES = {
     "qsb_magnitude_ema_full": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P]),
     "qsb_kth_workspace_bytes": (c_int64, [c_int64]),
     "qsb_kth_value": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),
+    "qsb_kth_batched_workspace_bytes": (c_int64, [ctypes.POINTER(c_int64), c_int]),
+    "qsb_kth_value_batched": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int,
+                                      c_int, _P, _P, c_int64, _P]),
     "qsb_kth_dist_begin": (c_int, [_P, c_int64, _P]),
     "qsb_kth_dist_pass": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, ctypes.POINTER(c_void_p),
                                   ctypes.POINTER(c_int64), _P]),

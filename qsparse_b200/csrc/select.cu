@@ -377,9 +377,9 @@ __device__ void fast_pass(const FastBufs &fb, unsigned long long kc, SelState *s
 // one radix pass; route chosen on the device
 // ---------------------------------------------------------------------------
 template <int PASS, int V, bool ABS>
-__global__ void __launch_bounds__(QSB_THREADS)
-    select_pass_kernel(const float *__restrict__ v, int64_t n, int64_t k, SelectWs ws,
-                       FastBufs fb, SelState *st_rw, float *thr_out) {
+__device__ __forceinline__ void select_pass_body(const float *__restrict__ v, int64_t n, int64_t k,
+                                                 SelectWs ws, FastBufs fb, SelState *st_rw,
+                                                 float *thr_out) {
   constexpr int kSmemWords = (PASS == 0) ? kBins0 * 32 : kBins1;
   static_assert(kSmemWords >= kFastBins, "the fast passes reuse the histogram");
   __shared__ uint32_t s_hist[kSmemWords];
@@ -553,9 +553,9 @@ __device__ __forceinline__ void cluster_sum_hist(cg::cluster_group &cluster, uin
 }
 
 template <int PER>
-__global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThreads)
-    select_sample_kernel(const float *__restrict__ v, int64_t n, int take_abs, int r_lo,
-                         int r_hi, SelState *st, uint4 *zero_base, int zero_vecs) {
+__device__ __forceinline__ void select_sample_body(const float *__restrict__ v, int64_t n,
+                                                   int take_abs, int r_lo, int r_hi, SelState *st,
+                                                   uint4 *zero_base, int zero_vecs) {
   static_assert(kFastBins == 2 * kSampleThreads, "two bins per thread");
   constexpr int kSampleSize = kSampleThreads * kSampleCtas * PER;
   constexpr int kTieMinCount = kSampleSize / 50;  // >= 2 % of the sample in lo's bucket: ties at lo
@@ -687,10 +687,9 @@ __device__ __forceinline__ uint32_t classify8(const VecF<8> &x, float lo, float 
 }
 
 template <int U, bool ABS>
-__global__ void __launch_bounds__(QSB_THREADS, U == 2 ? 8 : 5)
-    select_partition_kernel(const float *__restrict__ v, int64_t n, const SelState *st,
-                            unsigned long long *segctr, float *__restrict__ cand,
-                            uint32_t seg_cap) {
+__device__ __forceinline__ void select_partition_body(const float *__restrict__ v, int64_t n,
+                                                      const SelState *st, unsigned long long *segctr,
+                                                      float *__restrict__ cand, uint32_t seg_cap) {
   constexpr int V = 8;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
   // every thread parks its own elements here so that the (rare) candidates can be picked
@@ -811,36 +810,117 @@ __global__ void __launch_bounds__(QSB_THREADS, U == 2 ? 8 : 5)
 }
 
 // ---------------------------------------------------------------------------
-// host side
+// several independent selects ("segments": the layers of a weight set) in the same launches:
+// blockIdx.y picks the segment, every kernel reads its segment's arguments from a table in
+// the kernel parameters.  One select is the table with one entry.
 // ---------------------------------------------------------------------------
 constexpr int64_t kHistBytes = (int64_t)(kBins0 + kBins1 + kBins2) * sizeof(unsigned long long);
 constexpr int64_t kFastHistBytes = 3 * (int64_t)kFastBins * sizeof(uint32_t);
 constexpr int64_t kSegCtrBytes = (int64_t)kSegs * kSegStride * sizeof(unsigned long long);
-// [hist x3 | fast hist x3 | segment counters | SelState | pad] | candidate segments
+// per segment: [hist x3 | fast hist x3 | segment counters | SelState | pad] | candidate segments
 constexpr int64_t kSelectHeaderBytes = kHistBytes + kFastHistBytes + kSegCtrBytes + 1024;
-static_assert(kSelectHeaderBytes % 16 == 0, "the sampler zeroes the header with 128-bit stores");
+static_assert(kSelectHeaderBytes % 256 == 0, "headers of consecutive segments stay 256-byte aligned");
 static_assert(sizeof(SelState) <= 128, "SelState must fit the header pad (timing slots follow it)");
+
+struct SegDesc {
+  const float *v;
+  int64_t n, k;
+  float *thr_out;
+  unsigned char *hdr;  // kSelectHeaderBytes, 256-byte aligned
+  float *cand;         // [kSegs][seg_cap]
+  uint32_t seg_cap;
+  int r_lo, r_hi;      // sample ranks of the pivots
+  int fast;            // 0: generic passes only (small or unaligned input)
+};
+constexpr int kMaxSegs = 40;  // 40 x 64 B of kernel parameters
+struct SegTable {
+  SegDesc d[kMaxSegs];
+};
+
+__host__ __device__ inline SelectWs ws_of(unsigned char *hdr) {
+  SelectWs ws;
+  ws.hist0 = reinterpret_cast<unsigned long long *>(hdr);
+  ws.hist1 = ws.hist0 + kBins0;
+  ws.hist2 = ws.hist1 + kBins1;
+  return ws;
+}
+__host__ __device__ inline uint32_t *fh_of(unsigned char *hdr) {
+  return reinterpret_cast<uint32_t *>(hdr + kHistBytes);
+}
+__host__ __device__ inline unsigned long long *segctr_of(unsigned char *hdr) {
+  return reinterpret_cast<unsigned long long *>(hdr + kHistBytes + kFastHistBytes);
+}
+__host__ __device__ inline SelState *st_of(unsigned char *hdr) {
+  return reinterpret_cast<SelState *>(hdr + kHistBytes + kFastHistBytes + kSegCtrBytes);
+}
+
+template <int PER>
+__global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThreads)
+    select_sample_kernel(const __grid_constant__ SegTable tab, int take_abs) {
+  const SegDesc &d = tab.d[blockIdx.y];
+  uint4 *zb = reinterpret_cast<uint4 *>(d.hdr);
+  constexpr int zv = (int)(kSelectHeaderBytes / 16);
+  if (!d.fast) {  // generic passes only: this launch just zeroes the segment's header
+    for (int j = blockIdx.x * kSampleThreads + threadIdx.x; j < zv; j += kSampleThreads * kSampleCtas)
+      zb[j] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  select_sample_body<PER>(d.v, d.n, take_abs, d.r_lo, d.r_hi, st_of(d.hdr), zb, zv);
+}
+
+template <int U, bool ABS>
+__global__ void __launch_bounds__(QSB_THREADS, U == 2 ? 8 : 5)
+    select_partition_kernel(const __grid_constant__ SegTable tab) {
+  const SegDesc &d = tab.d[blockIdx.y];
+  if (!d.fast || (int64_t)blockIdx.x * (QSB_THREADS * 8 * U) >= d.n) return;
+  select_partition_body<U, ABS>(d.v, d.n, st_of(d.hdr), segctr_of(d.hdr), d.cand, d.seg_cap);
+}
+
+template <int PASS, int V, bool ABS>
+__global__ void __launch_bounds__(QSB_THREADS)
+    select_pass_kernel(const __grid_constant__ SegTable tab) {
+  const SegDesc &d = tab.d[blockIdx.y];
+  FastBufs fb{nullptr, nullptr, nullptr, nullptr, 0};
+  if (d.fast) fb = FastBufs{st_of(d.hdr), d.cand, segctr_of(d.hdr), fh_of(d.hdr), d.seg_cap};
+  select_pass_body<PASS, V, ABS>(d.v, d.n, d.k, ws_of(d.hdr), fb, st_of(d.hdr), d.thr_out);
+}
+
 static int g_select_fast = 1;  // tuning key 4
 static int g_select_pdl = 1;   // tuning key 8: programmatic dependent launch inside a select
 static int g_partition_u = 4;  // tuning key 6: 256-bit loads in flight per thread (2 or 4)
 static int g_sample_per = 2;   // tuning key 7: samples per sampler thread (1, 2, 4 -> 8K, 16K, 32K samples)
-
-// slots per segment: n/8 in total, a multiple of 8 per segment, < 2^32
-static int64_t seg_slots(int64_t n) {
-  if (n < kFastMinN) return 0;
-  int64_t c = ((n >> kCandShift) / kSegs) & ~(int64_t)7;
-  return c > 0xfffffff8ll ? 0xfffffff8ll : c;
-}
+constexpr int64_t kFastMinNBatched = 1 << 17;  // segments of a batch share the launches' fixed costs
 
 void set_select_fast(int v) { g_select_fast = v; }
 void set_select_pdl(int v) { g_select_pdl = v != 0; }
 void set_select_partition_u(int v) { g_partition_u = (v == 2) ? 2 : 4; }
 void set_select_sample_per(int v) { g_sample_per = (v == 1 || v == 4) ? v : 2; }
 
+// slots per candidate segment: n/8 in total, a multiple of 8 per segment, < 2^32
+static int64_t seg_slots(int64_t n) {
+  int64_t c = ((n >> kCandShift) / kSegs) & ~(int64_t)7;
+  return c > 0xfffffff8ll ? 0xfffffff8ll : c;
+}
+// workspace of one segment: header + candidates (reserved whenever the fast route could be taken)
+static int64_t seg_workspace_bytes(int64_t n) {
+  const int64_t cand = n >= kFastMinNBatched ? kSegs * seg_slots(n) * (int64_t)sizeof(float) : 0;
+  return kSelectHeaderBytes + (cand + 255) / 256 * 256;
+}
+
+template <class K>
+static int launch_seg(K kernel, dim3 grid, dim3 block, cudaStream_t stream, bool pdl, const SegTable &tab) {
+  if (pdl && g_select_pdl) {  // the previous kernel of this select is the dependency
+    QSB_CUDA_TRY(launch_pdl(kernel, grid, block, 0, stream, tab));
+    return 0;
+  }
+  kernel<<<grid, block, 0, stream>>>(tab);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int PASS, int V, bool ABS>
-static int launch_pass(const float *v, int64_t n, int64_t k, const SelectWs &ws,
-                       const FastBufs &fb, SelState *st, float *thr_out,
-                       cudaStream_t stream, bool after_kernel) {
+static int launch_pass(const SegTable &tab, int L, int64_t max_n, bool any_fast, cudaStream_t stream,
+                       bool pdl) {
   static int occ = 0;
   if (occ == 0) {
     int o = 0;
@@ -850,109 +930,140 @@ static int launch_pass(const float *v, int64_t n, int64_t k, const SelectWs &ws,
   }
   constexpr int U = (V == 8) ? 2 : 4;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
-  int64_t grid = (int64_t)device_props().sm_count * occ;
-  const int64_t tiles = (n + kTile - 1) / kTile;
+  int64_t grid = (int64_t)device_props().sm_count * occ / L;  // the chip is shared by the L segments
+  const int64_t tiles = (max_n + kTile - 1) / kTile;
   if (grid > tiles) grid = tiles;
+  if (any_fast && grid < kSegs) grid = kSegs;  // the candidate passes work in multiples of kSegs CTAs
   if (grid < 1) grid = 1;
-  if (g_select_pdl && after_kernel) {  // the previous kernel of this select is the dependency
-    QSB_CUDA_TRY(launch_pdl(select_pass_kernel<PASS, V, ABS>, dim3((unsigned)grid), dim3(QSB_THREADS), 0,
-                            stream, v, n, k, ws, fb, st, thr_out));
-    return 0;
-  }
-  select_pass_kernel<PASS, V, ABS>
-      <<<(unsigned)grid, QSB_THREADS, 0, stream>>>(v, n, k, ws, fb, st, thr_out);
-  QSB_LAUNCH_CHECK();
-  return 0;
+  return launch_seg(select_pass_kernel<PASS, V, ABS>, dim3((unsigned)grid, (unsigned)L), dim3(QSB_THREADS),
+                    stream, pdl, tab);
 }
 
-template <int V, bool ABS>
-static int run_passes(const float *v, int64_t n, int64_t k, const SelectWs &ws,
-                      const FastBufs &fb, SelState *st, float *thr_out,
-                      cudaStream_t stream) {
+// descs[0..L): one launch sequence.  v8: every segment is 32-byte aligned (256-bit loads).
+template <bool ABS>
+static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, cudaStream_t stream) {
+  SegTable tab;
+  int64_t max_n = 0, max_fast_n = 0;
+  for (int i = 0; i < L; ++i) {
+    tab.d[i] = descs[i];
+    if (descs[i].n > max_n) max_n = descs[i].n;
+    if (descs[i].fast && descs[i].n > max_fast_n) max_fast_n = descs[i].n;
+  }
+  const bool any_fast = max_fast_n > 0;
   int rc;
-  // without the fast route the first pass follows a memset, not a kernel of ours
-  if ((rc = launch_pass<0, V, ABS>(v, n, k, ws, fb, st, thr_out, stream, fb.st != nullptr))) return rc;
-  if ((rc = launch_pass<1, V, ABS>(v, n, k, ws, fb, st, thr_out, stream, true))) return rc;
-  return launch_pass<2, V, ABS>(v, n, k, ws, fb, st, thr_out, stream, true);
+  if (first_after_kernel) {
+    // pivots for the fast segments; zeroes every segment's header (no memset node)
+    const dim3 sg(kSampleCtas, (unsigned)L);
+    if (g_sample_per == 1)
+      select_sample_kernel<1><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
+    else if (g_sample_per == 4)
+      select_sample_kernel<4><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
+    else
+      select_sample_kernel<2><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
+    QSB_LAUNCH_CHECK();
+  }
+  if (any_fast) {
+    const int u = g_partition_u;
+    const int64_t tile = (int64_t)QSB_THREADS * 8 * u;
+    const dim3 pg((unsigned)((max_fast_n + tile - 1) / tile), (unsigned)L);
+    rc = u == 4 ? launch_seg(select_partition_kernel<4, ABS>, pg, dim3(QSB_THREADS), stream, true, tab)
+                : launch_seg(select_partition_kernel<2, ABS>, pg, dim3(QSB_THREADS), stream, true, tab);
+    if (rc) return rc;
+  }
+  if (v8) {
+    if ((rc = launch_pass<0, 8, ABS>(tab, L, max_n, any_fast, stream, first_after_kernel))) return rc;
+    if ((rc = launch_pass<1, 8, ABS>(tab, L, max_n, any_fast, stream, true))) return rc;
+    return launch_pass<2, 8, ABS>(tab, L, max_n, any_fast, stream, true);
+  }
+  if ((rc = launch_pass<0, 1, ABS>(tab, L, max_n, any_fast, stream, first_after_kernel))) return rc;
+  if ((rc = launch_pass<1, 1, ABS>(tab, L, max_n, any_fast, stream, true))) return rc;
+  return launch_pass<2, 1, ABS>(tab, L, max_n, any_fast, stream, true);
 }
 
-template <int U, bool ABS>
-static int launch_partition(const float *v, int64_t n, const SelState *st,
-                            unsigned long long *segctr, float *cand, uint32_t seg_cap,
-                            cudaStream_t stream) {
-  constexpr int64_t kTile = (int64_t)QSB_THREADS * 8 * U;
-  const int64_t tiles = (n + kTile - 1) / kTile;
-  if (g_select_pdl) {
-    QSB_CUDA_TRY(launch_pdl(select_partition_kernel<U, ABS>, dim3((unsigned)tiles), dim3(QSB_THREADS), 0,
-                            stream, v, n, st, segctr, cand, seg_cap));
-    return 0;
-  }
-  select_partition_kernel<U, ABS>
-      <<<(unsigned)tiles, QSB_THREADS, 0, stream>>>(v, n, st, segctr, cand, seg_cap);
-  QSB_LAUNCH_CHECK();
-  return 0;
+// fill one descriptor; returns the bytes of workspace it uses
+static int64_t make_desc(SegDesc &d, const float *v, int64_t n, int64_t k, float *thr_out,
+                         unsigned char *hdr, bool batched) {
+  d.v = v;
+  d.n = n;
+  d.k = k;
+  d.thr_out = thr_out;
+  d.hdr = hdr;
+  d.cand = reinterpret_cast<float *>(hdr + kSelectHeaderBytes);
+  d.seg_cap = (uint32_t)seg_slots(n);
+  d.fast = g_select_fast && aligned_to(v, 32) && n >= (batched ? kFastMinNBatched : kFastMinN);
+  // sample ranks bracketing k: +-4.5 sigma of the binomial rank error, +3
+  const double m = (double)(kSampleThreads * kSampleCtas * g_sample_per), p = (double)k / (double)n;
+  const double delta = 4.5 * sqrt(m * p * (1.0 - p)) + 3.0;
+  d.r_lo = (int)floor(p * m - delta);
+  d.r_hi = (int)ceil(p * m + delta);
+  return seg_workspace_bytes(n);
 }
 
 }  // namespace qsb
 
 using namespace qsb;
 
-extern "C" int64_t qsb_kth_workspace_bytes(int64_t n) {
-  return 256 + kSelectHeaderBytes + 32 + kSegs * seg_slots(n) * (int64_t)sizeof(float) + 32;
+extern "C" int64_t qsb_kth_workspace_bytes(int64_t n) { return 256 + seg_workspace_bytes(n); }
+
+extern "C" int64_t qsb_kth_batched_workspace_bytes(const int64_t *n, int count) {
+  int64_t total = 256;
+  for (int i = 0; i < count; ++i) total += seg_workspace_bytes(n[i]);
+  return total;
+}
+
+extern "C" int qsb_kth_value_batched(const float *const *v, const int64_t *n, const int64_t *k,
+                                     int count, int take_abs, float *thr_out_dev, void *workspace,
+                                     int64_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (count < 0 || !v || !n || !k || !thr_out_dev || !workspace) return QSB_E_BADARG;
+  if (count == 0) return 0;
+  for (int i = 0; i < count; ++i) {
+    if (n[i] <= 0 || k[i] < 0 || k[i] >= n[i] || !v[i]) return QSB_E_BADARG;
+    if (!aligned_to(v[i], 4)) return QSB_E_ALIGN;
+  }
+  if (workspace_bytes < qsb_kth_batched_workspace_bytes(n, count)) return QSB_E_WORKSPACE;
+  unsigned char *hdr =
+      reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  const bool batched = count > 1;
+  SegDesc group[kMaxSegs];
+  int L = 0;
+  auto flush = [&](bool v8) -> int {
+    if (L == 0) return 0;
+    const int rc = take_abs ? run_group<true>(group, L, v8, true, stream)
+                            : run_group<false>(group, L, v8, true, stream);
+    L = 0;
+    return rc;
+  };
+  int rc;
+  // 32-byte aligned segments share launches (up to kMaxSegs per sequence) ...
+  for (int i = 0; i < count; ++i) {
+    SegDesc d;
+    const int64_t used = make_desc(d, v[i], n[i], k[i], thr_out_dev + i, hdr, batched);
+    hdr += used;
+    if (!aligned_to(v[i], 32)) continue;
+    group[L++] = d;
+    if (L == kMaxSegs && (rc = flush(true))) return rc;
+  }
+  if ((rc = flush(true))) return rc;
+  // ... the others go one by one through the scalar-load kernels
+  hdr = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  for (int i = 0; i < count; ++i) {
+    SegDesc d;
+    const int64_t used = make_desc(d, v[i], n[i], k[i], thr_out_dev + i, hdr, batched);
+    hdr += used;
+    if (aligned_to(v[i], 32)) continue;
+    group[L++] = d;
+    if ((rc = flush(false))) return rc;
+  }
+  return 0;
 }
 
 extern "C" int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
                              float *thr_out_dev, void *workspace,
-                             int64_t workspace_bytes, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+                             int64_t workspace_bytes, void *stream) {
   if (n <= 0 || k < 0 || k >= n) return QSB_E_BADARG;
   if (!v || !thr_out_dev || !workspace) return QSB_E_BADARG;
-  if (!aligned_to(v, 4)) return QSB_E_ALIGN;
-  if (workspace_bytes < qsb_kth_workspace_bytes(n)) return QSB_E_WORKSPACE;
-  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
-  SelectWs ws;
-  ws.hist0 = reinterpret_cast<unsigned long long *>(base);
-  ws.hist1 = ws.hist0 + kBins0;
-  ws.hist2 = ws.hist1 + kBins1;
-  uint32_t *fh = reinterpret_cast<uint32_t *>(ws.hist2 + kBins2);
-  unsigned long long *segctr = reinterpret_cast<unsigned long long *>(fh + 3 * kFastBins);
-  SelState *st = reinterpret_cast<SelState *>(segctr + kSegs * kSegStride);
-
-  const bool v32 = aligned_to(v, 32);
-  FastBufs fb{nullptr, nullptr, nullptr, nullptr, 0};
-  if (g_select_fast && n >= kFastMinN && v32) {
-    float *cand = reinterpret_cast<float *>((base + kSelectHeaderBytes + 31) / 32 * 32);
-    const uint32_t cap = (uint32_t)seg_slots(n);
-    // sample ranks bracketing k: +-4.5 sigma of the binomial rank error, +3
-    const double m = (double)(kSampleThreads * kSampleCtas * g_sample_per), p = (double)k / (double)n;
-    const double delta = 4.5 * sqrt(m * p * (1.0 - p)) + 3.0;
-    const int r_lo = (int)floor(p * m - delta), r_hi = (int)ceil(p * m + delta);
-    uint4 *zb = reinterpret_cast<uint4 *>(base);
-    const int zv = (int)(kSelectHeaderBytes / 16);
-    if (g_sample_per == 1)
-      select_sample_kernel<1><<<kSampleCtas, kSampleThreads, 0, stream>>>(v, n, take_abs, r_lo, r_hi, st, zb, zv);
-    else if (g_sample_per == 4)
-      select_sample_kernel<4><<<kSampleCtas, kSampleThreads, 0, stream>>>(v, n, take_abs, r_lo, r_hi, st, zb, zv);
-    else
-      select_sample_kernel<2><<<kSampleCtas, kSampleThreads, 0, stream>>>(v, n, take_abs, r_lo, r_hi, st, zb, zv);
-    QSB_LAUNCH_CHECK();
-    int rc;
-    if (g_partition_u == 4)
-      rc = take_abs ? launch_partition<4, true>(v, n, st, segctr, cand, cap, stream)
-                    : launch_partition<4, false>(v, n, st, segctr, cand, cap, stream);
-    else
-      rc = take_abs ? launch_partition<2, true>(v, n, st, segctr, cand, cap, stream)
-                    : launch_partition<2, false>(v, n, st, segctr, cand, cap, stream);
-    if (rc) return rc;
-    fb = FastBufs{st, cand, segctr, fh, cap};
-  } else {
-    QSB_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<void *>(base), 0, kSelectHeaderBytes, stream));
-  }
-  if (v32)
-    return take_abs ? run_passes<8, true>(v, n, k, ws, fb, st, thr_out_dev, stream)
-                    : run_passes<8, false>(v, n, k, ws, fb, st, thr_out_dev, stream);
-  return take_abs ? run_passes<1, true>(v, n, k, ws, fb, st, thr_out_dev, stream)
-                  : run_passes<1, false>(v, n, k, ws, fb, st, thr_out_dev, stream);
+  return qsb_kth_value_batched(&v, &n, &k, 1, take_abs, thr_out_dev, workspace, workspace_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -962,14 +1073,10 @@ extern "C" int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
 // (an all-reduce of <= 32 KB of 64-bit counters: exact), and after the third pass
 // qsb_kth_dist_final reads the answer — identical on every GPU.  SURVEY 8(e), weights.
 // ---------------------------------------------------------------------------
-static SelectWs dist_ws(void *workspace) {
-  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256;
-  SelectWs ws;
-  ws.hist0 = reinterpret_cast<unsigned long long *>(base);
-  ws.hist1 = ws.hist0 + kBins0;
-  ws.hist2 = ws.hist1 + kBins1;
-  return ws;
+static unsigned char *dist_hdr(void *workspace) {
+  return reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
 }
+static SelectWs dist_ws(void *workspace) { return ws_of(dist_hdr(workspace)); }
 
 extern "C" int qsb_kth_dist_begin(void *workspace, int64_t workspace_bytes, void *stream) {
   if (!workspace || workspace_bytes < qsb_kth_workspace_bytes(0)) return QSB_E_WORKSPACE;
@@ -989,15 +1096,17 @@ extern "C" int qsb_kth_dist_pass(const float *v, int64_t n_local, int64_t k_glob
   if (hist_out) *hist_out = h;
   if (hist_counters_out) *hist_counters_out = pass == 0 ? kBins0 : kBins1;
   if (n_local == 0) return 0;  // an empty shard still takes part in the all-reduce
-  SelState *st = reinterpret_cast<SelState *>(
-      reinterpret_cast<unsigned char *>(ws.hist0) + kHistBytes + kFastHistBytes + kSegCtrBytes);
-  const FastBufs fb{nullptr, nullptr, nullptr, nullptr, 0};
-  const bool v32 = aligned_to(v, 32);
-#define QSB_DIST_PASS(P)                                                                         \
-  (v32 ? (take_abs ? launch_pass<P, 8, true>(v, n_local, k_global, ws, fb, st, nullptr, stream, false)  \
-                   : launch_pass<P, 8, false>(v, n_local, k_global, ws, fb, st, nullptr, stream, false)) \
-       : (take_abs ? launch_pass<P, 1, true>(v, n_local, k_global, ws, fb, st, nullptr, stream, false)  \
-                   : launch_pass<P, 1, false>(v, n_local, k_global, ws, fb, st, nullptr, stream, false)))
+  SegDesc d;
+  make_desc(d, v, n_local, k_global, nullptr, dist_hdr(workspace), false);
+  d.fast = 0;  // histograms only; the answer is read by qsb_kth_dist_final after the last all-reduce
+  SegTable tab;
+  tab.d[0] = d;
+  const bool v8 = aligned_to(v, 32);
+#define QSB_DIST_PASS(P)                                                                        \
+  (v8 ? (take_abs ? launch_pass<P, 8, true>(tab, 1, n_local, false, stream, false)               \
+                  : launch_pass<P, 8, false>(tab, 1, n_local, false, stream, false))             \
+      : (take_abs ? launch_pass<P, 1, true>(tab, 1, n_local, false, stream, false)               \
+                  : launch_pass<P, 1, false>(tab, 1, n_local, false, stream, false)))
   if (pass == 0) return QSB_DIST_PASS(0);
   if (pass == 1) return QSB_DIST_PASS(1);
   return QSB_DIST_PASS(2);

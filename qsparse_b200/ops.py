@@ -284,6 +284,28 @@ def kth_value(v, k: int, take_abs=False):
     return thr
 
 
+def kth_value_batched(vs, ks, take_abs=False):
+    """thresholds ``sorted(vs[i])[ks[i]]`` of several tensors (the layers of a weight set) in ONE launch
+    sequence: float32 device tensor [len(vs)].  Same kernels as ``kth_value``; blockIdx.y is the tensor."""
+    import ctypes
+    lib = N.load_library()
+    count = len(vs)
+    dev = vs[0].device
+    flat = []
+    for v in vs:
+        N.require_cuda(v, "importance")
+        flat.append(N.as_f32_contiguous(v.detach()).reshape(-1))
+    ptrs = (ctypes.c_void_p * count)(*[t.data_ptr() for t in flat])
+    ns = (c_int64 * count)(*[t.numel() for t in flat])
+    kk = (c_int64 * count)(*[int(k) for k in ks])
+    thr = torch.empty(count, dtype=torch.float32, device=dev)
+    nbytes = lib.qsb_kth_batched_workspace_bytes(ns, c_int(count))
+    ws = N.workspace(dev, nbytes)
+    N.check(lib.qsb_kth_value_batched(ptrs, ns, kk, c_int(count), c_int(1 if take_abs else 0), N.ptr(thr), N.ptr(ws),
+                                      c_int64(ws.numel()), N.stream_ptr(dev)), "qsb_kth_value_batched")
+    return thr
+
+
 def mask_from_threshold(importance, thr, mask_out, take_abs=False):
     lib = N.load_library()
     N.check(lib.qsb_mask_from_threshold(N.ptr(importance), c_int(1 if take_abs else 0), N.ptr(thr), N.ptr(mask_out),

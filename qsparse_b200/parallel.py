@@ -182,9 +182,13 @@ def sharded_layer_thresholds(importances, ks, group=None, take_abs=False) -> tor
     rank = dist.get_rank(group) if multi else 0
     dev = importances[0].device
     thr = torch.zeros(len(importances), dtype=torch.float32, device=dev)
-    for i, (imp, k) in enumerate(zip(importances, ks)):
-        if layer_owner(i, world) == rank:
-            thr[i:i + 1] = ops.kth_value(imp.reshape(-1), int(k), take_abs=take_abs)
+    owned = [i for i in range(len(importances)) if layer_owner(i, world) == rank]
+    if owned:   # every owned layer in the same launches (blockIdx.y = layer)
+        got = ops.kth_value_batched([importances[i] for i in owned], [ks[i] for i in owned], take_abs=take_abs)
+        if len(owned) == len(importances):
+            return got                                  # a single rank owns everything
+        for j, i in enumerate(owned):                   # device-to-device, capturable
+            thr[i:i + 1] = got[j:j + 1]
     return combine_thresholds(thr, group)
 
 

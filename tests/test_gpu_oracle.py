@@ -577,3 +577,29 @@ def test_int64_indexing_4G_elements():
         d = float(c)
         seg = view[o, c, -2048:]
         assert torch.equal(yv[o, c, -2048:], (seg * 2.0 ** d).int().float() * 2.0 ** -d), (o, c)
+
+
+def test_kth_value_batched_matches_single_and_sort():
+    """several selects in one launch sequence (weight-set layers): mixed sizes (generic and sampled routes),
+    an unaligned view, heavy ties, k at both ends."""
+    from qsparse_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(8)
+    sizes = [2_359_296, 131_072, 100, 4097, 1 << 20, 300_001, 2_359_296, 65_536 * 3]
+    vs = [torch.randn(s, device="cuda", generator=g) * 0.02 for s in sizes]
+    vs[4] = torch.relu(vs[4])                       # half zeros
+    vs[5] = torch.randn(300_002, device="cuda", generator=g)[1:]   # 4-byte aligned only
+    vs[6] = torch.round(vs[6] * 512) / 512          # a coarse grid: heavy ties everywhere
+    for frac in (0.5, 0.0, 0.999999, 0.75):
+        ks = [min(int(frac * v.numel()), v.numel() - 1) for v in vs]
+        for take_abs in (False, True):
+            thr = ops.kth_value_batched(vs, ks, take_abs=take_abs)
+            for i, (v, k) in enumerate(zip(vs, ks)):
+                ref = torch.sort(v.abs() if take_abs else v).values[k]
+                assert thr[i].item() == ref.item(), (frac, take_abs, i)
+                assert ops.kth_value(v, k, take_abs=take_abs).item() == ref.item(), (frac, take_abs, i, "single")
+    # more segments than one launch sequence holds
+    many = [torch.randn(150_000 + 1000 * i, device="cuda", generator=g) for i in range(45)]
+    ks = [m.numel() // 3 for m in many]
+    thr = ops.kth_value_batched(many, ks)
+    for i, (m, k) in enumerate(zip(many, ks)):
+        assert thr[i].item() == torch.sort(m).values[k].item(), i
