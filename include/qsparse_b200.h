@@ -219,6 +219,19 @@ int qsb_magnitude_ema_full(float *magnitude, const float *x,
                            const float *tensor_min, int use_l0, int64_t n,
                            int64_t t, void *stream);
 
+/* Multi-tensor forms for a weight SET (BASELINE config 4): the same arithmetic as
+ * qsb_magnitude_ema_full (without l0) / qsb_mask_build_apply on `count` separate
+ * tensors in ONE launch; tensor i has n[i] elements, thr_dev[i] is its threshold.
+ * The pointer / size arrays are HOST arrays.  Returns QSB_E_UNSUPPORTED when a
+ * tensor is not 32-byte aligned (use the single-tensor calls then). */
+int qsb_magnitude_ema_full_multi(float *const *magnitude, const float *const *x,
+                                 const int64_t *n, int count, int64_t t,
+                                 void *stream);
+int qsb_mask_build_apply_multi(const float *const *importance, int take_abs,
+                               const float *thr_dev, const float *const *x,
+                               float *const *y, uint8_t *const *mask_out,
+                               const int64_t *n, int count, void *stream);
+
 /* ------------------------------------------------------------------------
  * K5  exact k-th value (ascending, 0-based rank k) by radix select on the
  * order-preserving uint32 key; NaNs order last (like torch.sort).

@@ -41,6 +41,11 @@ _SIGNATURES = {
     "qsb_row_quant_fused": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, _P]),
     "qsb_magnitude_ema_reduced": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_double, c_int64, _P]),
     "qsb_magnitude_ema_full": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P]),
+    "qsb_magnitude_ema_full_multi": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                             ctypes.POINTER(c_int64), c_int, c_int64, _P]),
+    "qsb_mask_build_apply_multi": (c_int, [ctypes.POINTER(c_void_p), c_int, _P, ctypes.POINTER(c_void_p),
+                                           ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                           ctypes.POINTER(c_int64), c_int, _P]),
     "qsb_kth_workspace_bytes": (c_int64, [c_int64]),
     "qsb_kth_value": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),
     "qsb_kth_batched_workspace_bytes": (c_int64, [ctypes.POINTER(c_int64), c_int]),

@@ -5,6 +5,8 @@
 // FMA contraction can happen (the reference rounds after every ATen op).
 #include <math.h>
 
+#include <vector>
+
 #include "fq_ops.cuh"
 #include "map_kernel.cuh"
 #include "reduce_internal.cuh"
@@ -109,6 +111,7 @@ struct MaskBuildOp {
                         kHasFast = false;
   const float *thr;
   bool take_abs;
+  __device__ __forceinline__ void bind(const float *aux) { thr = aux; }  // multi-tensor: per layer
   struct P {
     float thr;
   };
@@ -136,6 +139,7 @@ struct EmaFullOp {
   const float *tensor_min;  // device scalar, only read when use_l0
   bool use_l0;
   float t_f, t_plus_1_f, r_t_plus_1;  // r = RN(1 / (t + 1)), host computed
+  __device__ __forceinline__ void bind(const float *) {}
   struct P {
     bool indicator;
   };
@@ -497,6 +501,55 @@ extern "C" int qsb_mask_build_apply(const float *importance, int take_abs,
   MaskBuildOp<true> op{thr_dev, take_abs != 0};
   return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
       op, io, Layout{1, 1, n}, (cudaStream_t)stream);
+}
+
+// ---- multi-tensor forms (the layers of a weight set in one launch) ----------------------
+static bool all_aligned32(const void *const *p, int count) {
+  for (int i = 0; i < count; ++i)
+    if (!aligned_to(p[i], 32)) return false;
+  return true;
+}
+
+extern "C" int qsb_mask_build_apply_multi(const float *const *importance, int take_abs,
+                                          const float *thr_dev, const float *const *x,
+                                          float *const *y, uint8_t *const *mask_out,
+                                          const int64_t *n, int count, void *stream) {
+  if (count < 0) return QSB_E_BADARG;
+  if (count == 0) return 0;
+  if (!importance || !thr_dev || !x || !y || !mask_out || !n) return QSB_E_BADARG;
+  if (!all_aligned32((const void *const *)importance, count) ||
+      !all_aligned32((const void *const *)x, count) || !all_aligned32((const void *const *)y, count))
+    return QSB_E_UNSUPPORTED;
+  std::vector<MultiEntry> ent((size_t)count);
+  for (int i = 0; i < count; ++i) {
+    if (n[i] < 0 || !importance[i] || !x[i] || !y[i] || !mask_out[i]) return QSB_E_BADARG;
+    if (!aligned_to(mask_out[i], 8)) return QSB_E_UNSUPPORTED;
+    ent[i] = MultiEntry{importance[i], x[i], y[i], mask_out[i], thr_dev + i, n[i], 0};
+  }
+  MaskBuildOp<true> op{thr_dev, take_abs != 0};
+  return launch_map_multi<decltype(op), Hint::STREAM, Hint::KEEP>(op, ent.data(), count,
+                                                                   (cudaStream_t)stream);
+}
+
+extern "C" int qsb_magnitude_ema_full_multi(float *const *magnitude, const float *const *x,
+                                            const int64_t *n, int count, int64_t t,
+                                            void *stream) {
+  if (count < 0 || t < 0) return QSB_E_BADARG;
+  if (count == 0) return 0;
+  if (!magnitude || !x || !n) return QSB_E_BADARG;
+  if (!all_aligned32((const void *const *)magnitude, count) ||
+      !all_aligned32((const void *const *)x, count))
+    return QSB_E_UNSUPPORTED;
+  std::vector<MultiEntry> ent((size_t)count);
+  for (int i = 0; i < count; ++i) {
+    if (n[i] < 0 || !magnitude[i] || !x[i]) return QSB_E_BADARG;
+    ent[i] = MultiEntry{x[i], magnitude[i], magnitude[i], nullptr, nullptr, n[i], 0};
+  }
+  const float tp1 = (float)(t + 1);
+  volatile float rcp = 1.0f / tp1;  // IEEE round-to-nearest on the host
+  EmaFullOp op{nullptr, false, (float)t, tp1, rcp};
+  return launch_map_multi<decltype(op), Hint::STREAM, Hint::KEEP>(op, ent.data(), count,
+                                                                   (cudaStream_t)stream);
 }
 
 extern "C" int qsb_magnitude_ema_full(float *magnitude, const float *x,

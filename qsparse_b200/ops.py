@@ -284,6 +284,51 @@ def kth_value(v, k: int, take_abs=False):
     return thr
 
 
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _multi_ok(*lists) -> bool:
+    """the multi-tensor kernels need fp32 contiguous, 32-byte aligned tensors"""
+    for ts in lists:
+        for t in ts:
+            if t.dtype not in (torch.float32, torch.bool, torch.uint8) or not t.is_contiguous() \
+                    or t.data_ptr() % 32:
+                return False
+    return True
+
+
+def magnitude_ema_full_multi_(magnitudes, xs, t: int):
+    """``magnitude_ema_full_`` for every (magnitude, x) pair in ONE launch (falls back to one launch per
+    tensor when a tensor is not 32-byte aligned)."""
+    if not _multi_ok(magnitudes, xs):
+        for m, x in zip(magnitudes, xs):
+            magnitude_ema_full_(m, N.as_f32_contiguous(x.detach()), t)
+        return magnitudes
+    lib = N.load_library()
+    count = len(magnitudes)
+    ns = (c_int64 * count)(*[m.numel() for m in magnitudes])
+    N.check(lib.qsb_magnitude_ema_full_multi(_ptr_array(magnitudes), _ptr_array(xs), ns, c_int(count), c_int64(t),
+                                             N.stream_ptr(magnitudes[0].device)), "qsb_magnitude_ema_full_multi")
+    return magnitudes
+
+
+def mask_build_apply_multi(importances, thr, xs, masks, outs, take_abs=False):
+    """``mask_build_apply`` for every layer in ONE launch; ``thr`` is the float32 [L] threshold tensor."""
+    if not _multi_ok(importances, xs, outs, masks) or not thr.is_contiguous():
+        for i, (imp, x, m, o) in enumerate(zip(importances, xs, masks, outs)):
+            mask_build_apply(imp, thr[i:i + 1], x, m, take_abs, out=o)
+        return outs
+    lib = N.load_library()
+    count = len(importances)
+    ns = (c_int64 * count)(*[x.numel() for x in xs])
+    N.check(lib.qsb_mask_build_apply_multi(_ptr_array(importances), c_int(1 if take_abs else 0), N.ptr(thr),
+                                           _ptr_array(xs), _ptr_array(outs), _ptr_array(masks), ns, c_int(count),
+                                           N.stream_ptr(xs[0].device)), "qsb_mask_build_apply_multi")
+    return outs
+
+
 def kth_value_batched(vs, ks, take_abs=False):
     """thresholds ``sorted(vs[i])[ks[i]]`` of several tensors (the layers of a weight set) in ONE launch
     sequence: float32 device tensor [len(vs)].  Same kernels as ``kth_value``; blockIdx.y is the tensor."""

@@ -239,10 +239,8 @@ def prune_weight_set_step(weights, magnitudes, masks, outs, t: int, sparsity: fl
     from . import ops
     from .util import kth_rank
 
-    for w, mag in zip(weights, magnitudes):
-        ops.magnitude_ema_full_(mag, w, t)
+    ops.magnitude_ema_full_multi_(magnitudes, weights, t)            # one launch for the whole set
     ks = [kth_rank(sparsity, m.numel()) for m in magnitudes]
-    thr = sharded_layer_thresholds(magnitudes, ks, group)
-    for i, (w, mag, mask, out) in enumerate(zip(weights, magnitudes, masks, outs)):
-        ops.mask_build_apply(mag, thr[i:i + 1], w, mask, out=out)
+    thr = sharded_layer_thresholds(magnitudes, ks, group)            # one launch sequence per rank
+    ops.mask_build_apply_multi(magnitudes, thr, weights, masks, outs)  # one launch
     return thr

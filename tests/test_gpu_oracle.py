@@ -603,3 +603,31 @@ def test_kth_value_batched_matches_single_and_sort():
     thr = ops.kth_value_batched(many, ks)
     for i, (m, k) in enumerate(zip(many, ks)):
         assert thr[i].item() == torch.sort(m).values[k].item(), i
+
+
+def test_multi_tensor_ema_and_mask_equal_single_tensor_calls():
+    """one launch over a weight set == one launch per tensor (sizes with vector tails, a tile-multiple size,
+    more tensors than one table holds; an unaligned tensor sends the whole call down the per-tensor path)."""
+    from qsparse_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(21)
+    sizes = [455, 4096, 8192 + 3, 100_000, 7] + [1000 + 37 * i for i in range(50)]
+    for unaligned in (False, True):
+        xs = [torch.randn(s, device="cuda", generator=g) for s in sizes]
+        if unaligned:
+            xs[2] = torch.randn(sizes[2] + 1, device="cuda", generator=g)[1:]
+        mags_a = [torch.rand(s, device="cuda", generator=g) for s in sizes]
+        mags_b = [m.clone() for m in mags_a]
+        ops.magnitude_ema_full_multi_(mags_a, xs, 3)
+        for m, x in zip(mags_b, xs):
+            ops.magnitude_ema_full_(m, x.contiguous(), 3)
+        for a, b in zip(mags_a, mags_b):
+            assert torch.equal(a, b)
+        thr = torch.rand(len(sizes), device="cuda", generator=g) * 0.5
+        masks_a = [torch.ones(s, dtype=torch.bool, device="cuda") for s in sizes]
+        masks_b = [torch.ones(s, dtype=torch.bool, device="cuda") for s in sizes]
+        outs_a = [torch.full((s,), 9.0, device="cuda") for s in sizes]
+        ops.mask_build_apply_multi(mags_a, thr, xs, masks_a, outs_a)
+        for i, (m, x, mk) in enumerate(zip(mags_b, xs, masks_b)):
+            y = ops.mask_build_apply(m, thr[i:i + 1], x.contiguous(), mk)
+            assert torch.equal(mk, masks_a[i]) and torch.equal(y, outs_a[i]), i
+            assert torch.equal(mk, m >= thr[i])
