@@ -67,7 +67,7 @@ def _is_channelwise(param) -> bool:
 def _broadcast_result(y: torch.Tensor, x_shape, param) -> torch.Tensor:
     """A one-element tensor parameter of higher rank than x broadcasts the result
     shape in the reference (`input * toi` with toi of shape [1, 1])."""
-    if isinstance(param, torch.Tensor) and param.dim() > len(x_shape):
+    if isinstance(param, torch.Tensor) and param.numel() == 1 and param.dim() > len(x_shape):
         return y.reshape(torch.broadcast_shapes(tuple(x_shape), tuple(param.shape)))
     return y
 

@@ -193,7 +193,7 @@ class UniformPruningCallback(MagnitudePruningCallback):
         budget = int(round((sparsity - cur_sparsity) * np.prod(mask.shape)))
         slots = mask.nonzero(as_tuple=True)
         chosen = np.random.choice(range(len(slots[0])), size=budget, replace=False)
-        mask.data[[slot[chosen] for slot in slots]] = False
+        mask.data[tuple(slot[chosen] for slot in slots)] = False
         return apply_mask(x, mask)
 
 
