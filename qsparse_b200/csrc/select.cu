@@ -940,8 +940,13 @@ static int launch_pass(const SegTable &tab, int L, int64_t max_n, bool any_fast,
 }
 
 // descs[0..L): one launch sequence.  v8: every segment is 32-byte aligned (256-bit loads).
+// samples per sampler thread: the tuning value for one select; 8 Ki samples per segment for a batch
+// (its segments are small: 16 Ki samples of a 2.4 M-element layer would touch a fifth of its lines)
+static int sample_per(bool batched) { return batched ? 1 : g_sample_per; }
+
 template <bool ABS>
-static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, cudaStream_t stream) {
+static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, bool batched,
+                     cudaStream_t stream) {
   SegTable tab;
   int64_t max_n = 0, max_fast_n = 0;
   for (int i = 0; i < L; ++i) {
@@ -954,9 +959,10 @@ static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, cu
   if (first_after_kernel) {
     // pivots for the fast segments; zeroes every segment's header (no memset node)
     const dim3 sg(kSampleCtas, (unsigned)L);
-    if (g_sample_per == 1)
+    const int per = sample_per(batched);
+    if (per == 1)
       select_sample_kernel<1><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
-    else if (g_sample_per == 4)
+    else if (per == 4)
       select_sample_kernel<4><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
     else
       select_sample_kernel<2><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
@@ -992,7 +998,7 @@ static int64_t make_desc(SegDesc &d, const float *v, int64_t n, int64_t k, float
   d.seg_cap = (uint32_t)seg_slots(n);
   d.fast = g_select_fast && aligned_to(v, 32) && n >= (batched ? kFastMinNBatched : kFastMinN);
   // sample ranks bracketing k: +-4.5 sigma of the binomial rank error, +3
-  const double m = (double)(kSampleThreads * kSampleCtas * g_sample_per), p = (double)k / (double)n;
+  const double m = (double)(kSampleThreads * kSampleCtas * sample_per(batched)), p = (double)k / (double)n;
   const double delta = 4.5 * sqrt(m * p * (1.0 - p)) + 3.0;
   d.r_lo = (int)floor(p * m - delta);
   d.r_hi = (int)ceil(p * m + delta);
@@ -1029,8 +1035,8 @@ extern "C" int qsb_kth_value_batched(const float *const *v, const int64_t *n, co
   int L = 0;
   auto flush = [&](bool v8) -> int {
     if (L == 0) return 0;
-    const int rc = take_abs ? run_group<true>(group, L, v8, true, stream)
-                            : run_group<false>(group, L, v8, true, stream);
+    const int rc = take_abs ? run_group<true>(group, L, v8, true, batched, stream)
+                            : run_group<false>(group, L, v8, true, batched, stream);
     L = 0;
     return rc;
   };
