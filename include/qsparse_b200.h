@@ -113,6 +113,25 @@ int qsb_fq_line_fwd(const float *x, float *y, const float *lines_dev,
                     int mask_kind, int64_t outer, int64_t channels,
                     int64_t inner, void *stream);
 
+/* Integer export: the integer CODE of a fake-quantizer, one byte per
+ * element (5 B/elem instead of 8), for deployment after quantization-aware training.
+ *   kind 0 (decimal): q = clamp(int32_rz(x * 2^d), -2^(b-1), 2^(b-1)-1)   as int8
+ *                     param = decimal; dequantised value  q * 2^-d
+ *   kind 1 (scaler) : q = clamp(int32(rint(x / s)), -2^(b-1), 2^(b-1)-1)  as int8
+ *                     param = scale;   dequantised value  q * s
+ *   kind 2 (line)   : q = clamp(rint((clamp(x, lo, hi) - lo) / step), 0, 2^b - 1) as uint8
+ *                     param = (lo, hi) rows; step = (hi - lo) / 2^b; value q * step + lo
+ * param_dev: per tensor (n_param == 1) or per channel (n_param == channels), or NULL to
+ * use param_host (and param_host2 = hi for kind 2).  bits <= 8.  Inside the clamp range
+ * the dequantised value equals qsb_fq_*_fwd's output bit for bit.
+ * ref: the integer-arithmetic property qsparse proves in tests/test_quantize.py:73-101;
+ *      qsparse/quantize.py:55-63, :107-117, :168-181 for the codes. */
+int qsb_quant_export_int8(const float *x, uint8_t *q_out, int kind,
+                          const float *param_dev, int64_t n_param,
+                          double param_host, double param_host2, int bits,
+                          int64_t outer, int64_t channels, int64_t inner,
+                          void *stream);
+
 /* ------------------------------------------------------------------------
  * K2  straight-through-estimator backward (and the fused prune backward).
  * ref: DecimalQuantization.backward qsparse/quantize.py:65-77,

@@ -30,6 +30,8 @@ _SIGNATURES = {
     "qsb_fq_scaler_fwd": (c_int, [_P, _P, _P, c_int64, c_float, _P, c_int, c_int64, c_int64, c_int64, _P]),
     "qsb_fq_line_fwd": (c_int, [_P, _P, _P, c_int64, c_float, c_float, c_int, c_int, _P, c_int,
                                 c_int64, c_int64, c_int64, _P]),
+    "qsb_quant_export_int8": (c_int, [_P, _P, c_int, _P, c_int64, c_double, c_double, c_int, c_int64, c_int64,
+                                      c_int64, _P]),
     "qsb_ste_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_int, c_int, c_int, _P, c_int,
                             c_int64, c_int64, c_int64, _P]),
     "qsb_mask_apply": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, c_int64, _P]),

@@ -156,6 +156,47 @@ struct EmaFullOp {
   }
 };
 
+// ---------------------------------------------------------------------------
+// integer export: the integer CODE of the fake-quantizers, one byte per
+// element instead of a float — 5 B/elem instead of 8.  Inside the representable range
+// dequantising the code (q * 2^-d, q * s, q * step + lo) reproduces the fake-quant output
+// bit for bit (the property tests/test_quantize.py:73-101 of the reference relies on).
+// The parameter derivation is the fake-quant ops' own (Op::params).
+// ---------------------------------------------------------------------------
+struct ExportPow2Op : Pow2Op<QSB_MASK_NONE> {
+  static constexpr bool kOut0 = false, kOutB = true, kCanSkip = false;
+  int q_min, q_max;
+  __device__ __forceinline__ void apply(float a, float, uint8_t, const P &p, float &, float &,
+                                        uint8_t &ob) const {
+    int q = __float2int_rz(__fmul_rn(a, p.toi));
+    q = q < q_min ? q_min : (q > q_max ? q_max : q);
+    ob = (uint8_t)(int8_t)q;
+  }
+};
+
+struct ExportScalerOp : ScalerOp<QSB_MASK_NONE> {
+  static constexpr bool kOut0 = false, kOutB = true, kCanSkip = false, kHasFast = false;
+  int q_min, q_max;
+  __device__ __forceinline__ void apply(float a, float, uint8_t, const P &p, float &, float &,
+                                        uint8_t &ob) const {
+    int q = __float2int_rn(div_rn_by_q(a, p.s, p.r, p.ok));
+    q = q < q_min ? q_min : (q > q_max ? q_max : q);
+    ob = (uint8_t)(int8_t)q;
+  }
+};
+
+struct ExportLineOp : LineOp<QSB_MASK_NONE, true> {
+  static constexpr bool kOut0 = false, kOutB = true, kCanSkip = false, kHasFast = false;
+  __device__ __forceinline__ void apply(float a, float, uint8_t, const P &p, float &, float &,
+                                        uint8_t &ob) const {
+    const float xc = clamp_torch_tensor(a, p.lo, p.hi);
+    const float d = __fsub_rn(xc, p.lo);
+    float q = p.fast ? div_rn_by_unchecked(d, p.step, p.rstep) : __fdiv_rn(d, p.step);
+    q = clamp_torch(rintf(q), 0.0f, q_max);
+    ob = (uint8_t)__float2int_rn(q);  // NaN -> 0
+  }
+};
+
 }  // namespace qsb
 
 // ===========================================================================
@@ -300,6 +341,46 @@ extern "C" int qsb_fq_line_fwd(const float *x, float *y, const float *lines_dev,
           op, io, L, (cudaStream_t)stream);
     }
   });
+}
+
+/* integer codes of the three fake-quantizers */
+extern "C" int qsb_quant_export_int8(const float *x, uint8_t *q_out, int kind,
+                                     const float *param_dev, int64_t n_param,
+                                     double param_host, double param_host2, int bits,
+                                     int64_t outer, int64_t channels, int64_t inner,
+                                     void *stream) {
+  if (int e = check_layout(outer, channels, inner)) return e;
+  if (kind < 0 || kind > 2 || bits < 1 || bits > 8) return QSB_E_BADARG;
+  if (outer * channels * inner == 0) return 0;
+  if (!x || !q_out) return QSB_E_BADARG;
+  int stride = 0;
+  if (param_dev) {
+    stride = param_stride(n_param, channels);
+    if (stride < 0) return QSB_E_BADARG;
+    if (kind == 2 && !aligned_to(param_dev, 8)) return QSB_E_ALIGN;
+  }
+  const Layout L = effective_layout(outer, channels, inner, stride == 1);
+  MapIO io{x, nullptr, nullptr, nullptr, nullptr, q_out};
+  const int q_min = -(1 << (bits - 1)), q_max = (1 << (bits - 1)) - 1;
+  if (kind == 0) {
+    ExportPow2Op op;
+    op.dec = param_dev, op.dec_stride = stride;
+    op.toi_host = (float)pow(2.0, param_host), op.tof_host = (float)pow(2.0, -param_host);
+    op.cmask = nullptr, op.q_min = q_min, op.q_max = q_max;
+    return launch_map<ExportPow2Op, Hint::STREAM, Hint::KEEP>(op, io, L, (cudaStream_t)stream);
+  }
+  if (kind == 1) {
+    ExportScalerOp op;
+    op.scale = param_dev, op.scale_stride = stride, op.scale_host = (float)param_host;
+    op.cmask = nullptr, op.q_min = q_min, op.q_max = q_max;
+    return launch_map<ExportScalerOp, Hint::STREAM, Hint::KEEP>(op, io, L, (cudaStream_t)stream);
+  }
+  ExportLineOp op;
+  op.lines = param_dev, op.lines_stride = stride;
+  op.lo_host = (float)param_host, op.hi_host = (float)param_host2;
+  const double N = ldexp(1.0, bits);
+  op.n_levels = (float)N, op.q_max = (float)(N - 1.0), op.cmask = nullptr;
+  return launch_map<ExportLineOp, Hint::STREAM, Hint::KEEP>(op, io, L, (cudaStream_t)stream);
 }
 
 extern "C" int qsb_ste_bwd(const float *g, float *g_clamped_out, float *gx_out,

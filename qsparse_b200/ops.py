@@ -150,6 +150,31 @@ def ste_bwd(g, scale, is_decimal: bool, bits: int, notch: int, layout: Layout, m
     return gc, gx
 
 
+EXPORT_DECIMAL, EXPORT_SCALER, EXPORT_LINE = 0, 1, 2
+
+
+def quant_export_int8(x, kind: int, param, bits: int, layout: Layout):
+    """integer codes of a fake-quantizer: int8 (decimal / scaler) or uint8 (line) tensor of x's shape.
+    ``param``: decimal / scale (float or tensor [1] / [C]) or lines ((lo, hi) or tensor [1|C, 2])."""
+    lib = N.load_library()
+    N.require_cuda(x, "input")
+    xs = N.as_f32_contiguous(x.detach())
+    q = torch.empty(xs.shape, dtype=torch.uint8 if kind == EXPORT_LINE else torch.int8, device=x.device)
+    dev, n, h1, h2 = None, 1, 0.0, 0.0
+    if isinstance(param, torch.Tensor):
+        N.require_cuda(param, "param")
+        dev = param.detach().float().contiguous()
+        n = dev.numel() // (2 if kind == EXPORT_LINE else 1)
+    elif kind == EXPORT_LINE:
+        h1, h2 = float(param[0]), float(param[1])
+    else:
+        h1 = float(param)
+    N.check(lib.qsb_quant_export_int8(N.ptr(xs), N.ptr(q), c_int(kind), N.ptr(dev), c_int64(n), c_double(h1),
+                                      c_double(h2), c_int(bits), c_int64(layout[0]), c_int64(layout[1]),
+                                      c_int64(layout[2]), N.stream_ptr(x.device)), "qsb_quant_export_int8")
+    return q
+
+
 # ----------------------------------------------------------------------------- K6
 def mask_apply(x, mask, layout: Layout, out=None):
     N.require_cuda(x, "input")

@@ -508,6 +508,33 @@ class QuantizeLayer(nn.Module):
         return out
 
 
+def export_integer(layer: "QuantizeLayer", x: torch.Tensor):
+    """Integer deployment form of what ``layer`` computes for ``x``: the int8 / uint8 codes plus
+    the parameters that turn them back into the fake-quantized values,
+
+        DecimalQuantizer   q int8,  value = q * 2^-decimal          (decimal per tensor or per channel)
+        ScalerQuantizer    q int8,  value = q * scale
+        AdaptiveQuantizer  q uint8, value = q * step + lo,  step = (hi - lo) / 2^bits   (float zero-point form)
+
+    one kernel, 5 B/elem (``qsb_quant_export_int8``).  Values outside the ``bits``-bit range saturate (the
+    fake-quantizers themselves do not clamp in the forward).  Returns a dict."""
+    assert isinstance(layer, QuantizeLayer) and layer.initted and layer.bits <= 8
+    cb, ci = layer.callback, layer.channelwise
+    xs = N.as_f32_contiguous(x.detach())
+    layout = N.channel_layout(xs.shape, ci)
+    w = layer.weight.data
+    if isinstance(cb, AdaptiveQuantizer):
+        lines = w.reshape(-1, 2)
+        q = ops.quant_export_int8(xs, ops.EXPORT_LINE, lines, layer.bits, layout)
+        return dict(q=q, kind="line", bits=layer.bits, lines=lines.clone(), channel_index=ci)
+    if cb.use_float_scaler:
+        q = ops.quant_export_int8(xs, ops.EXPORT_SCALER, w.reshape(-1), layer.bits, layout)
+        return dict(q=q, kind="scaler", bits=layer.bits, scale=w.reshape(-1).clone(), channel_index=ci)
+    dec = ops.scale_to_decimal(w).reshape(-1)
+    q = ops.quant_export_int8(xs, ops.EXPORT_DECIMAL, dec, layer.bits, layout)
+    return dict(q=q, kind="decimal", bits=layer.bits, decimal=dec, channel_index=ci)
+
+
 def quantize(inp: nn.Module = None, bits: int = 8, channelwise: int = 1, timeout: int = 1000,
              callback: BaseQuantizer = None, bias_bits: int = -1, name: str = "") -> nn.Module:
     """Create a ``QuantizeLayer`` (no input module) or wrap the weight / bias of ``inp``

@@ -631,3 +631,68 @@ def test_multi_tensor_ema_and_mask_equal_single_tensor_calls():
             y = ops.mask_build_apply(m, thr[i:i + 1], x.contiguous(), mk)
             assert torch.equal(mk, masks_a[i]) and torch.equal(y, outs_a[i]), i
             assert torch.equal(mk, m >= thr[i])
+
+
+# ----------------------------------------------------------------------------- integer export
+@pytest.mark.parametrize("shape,ci", [((4, 6, 7, 7), 1), ((16, 40), 0), ((3, 5, 33), 2), ((2, 3, 1000), -1)])
+def test_quant_export_int8_codes_and_dequant(shape, ci):
+    """codes == the numpy restatement of the reference's integer step; dequantised codes == the fake-quant
+    output wherever the value is inside the bits-bit range; saturation outside."""
+    from qsparse_b200 import ops
+    from qsparse_b200.quantize import quantize_with_decimal, quantize_with_scaler, quantize_with_line
+    bits = 6
+    x = rnd(shape, 31, 1.5)
+    C = shape[ci] if ci >= 0 else 1
+    rng = np.random.default_rng(7)
+    dec = rng.integers(2, 5, C).astype(np.float32)
+    sc = rng.uniform(0.02, 0.2, C).astype(np.float32)
+    lines = np.stack([rng.uniform(-2, -0.1, C), rng.uniform(0.1, 2, C)], 1).astype(np.float32)
+    layout = (1, 1, x.size) if ci < 0 else tuple(orc.layout(shape, ci))
+    bshape = [1] * len(shape)
+    if ci >= 0:
+        bshape[ci] = C
+    xc = cu(x)
+    lo_q, hi_q = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    # decimal
+    q = npy(ops.quant_export_int8(xc, ops.EXPORT_DECIMAL, cu(dec), bits, layout))
+    raw = np.trunc(x * np.float32(2.0) ** dec.reshape(bshape)).astype(np.int64)
+    assert q.dtype == np.int8 and np.array_equal(q, np.clip(raw, lo_q, hi_q))
+    inside = (raw >= lo_q) & (raw <= hi_q)
+    fq = npy(quantize_with_decimal(xc, bits, cu(dec) if ci >= 0 else float(dec[0]), ci))
+    deq = q.astype(np.float32) * np.float32(2.0) ** -dec.reshape(bshape)
+    assert bits_equal(np.where(inside, deq, 0), np.where(inside, fq + np.float32(0), 0))
+    assert inside.mean() < 1.0                                   # the saturation branch is exercised
+    # scaler
+    q = npy(ops.quant_export_int8(xc, ops.EXPORT_SCALER, cu(sc), bits, layout))
+    raw = np.rint(x / sc.reshape(bshape)).astype(np.int64)
+    assert np.array_equal(q, np.clip(raw, lo_q, hi_q))
+    inside = (raw >= lo_q) & (raw <= hi_q)
+    fq = npy(quantize_with_scaler(xc, bits, cu(sc) if ci >= 0 else float(sc[0]), ci))
+    deq = q.astype(np.float32) * sc.reshape(bshape)
+    assert bits_equal(np.where(inside, deq, 0), np.where(inside, fq + np.float32(0), 0))
+    # line (float zero point): every code is in range by construction
+    q = npy(ops.quant_export_int8(xc, ops.EXPORT_LINE, cu(lines), bits, layout))
+    assert q.dtype == np.uint8 and q.max() <= (1 << bits) - 1
+    lo, hi = lines[:, 0].reshape(bshape), lines[:, 1].reshape(bshape)
+    step = (hi - lo) / np.float32(1 << bits)
+    fq = npy(quantize_with_line(xc, bits, cu(lines), ci if ci >= 0 else -1, False, True))
+    assert bits_equal(q.astype(np.float32) * step + lo, fq)
+
+
+def test_export_integer_from_layers():
+    import qsparse_b200 as q
+    from qsparse_b200.quantize import export_integer
+    x = cu(rnd((4, 10, 12, 12), 5, 0.5))
+    for cb, key in ((q.DecimalQuantizer(), "decimal"), (q.ScalerQuantizer(), "scale"), (q.AdaptiveQuantizer(), "lines")):
+        layer = q.quantize(bits=8, timeout=2, channelwise=1 if key == "lines" else -1, callback=cb)
+        for _ in range(4):
+            y = layer(x)
+        out = export_integer(layer, x)
+        if key == "decimal":
+            deq = out["q"].float() * 2.0 ** -out["decimal"]
+        elif key == "scale":
+            deq = out["q"].float() * out["scale"]
+        else:
+            lo, hi = out["lines"][:, 0].view(1, -1, 1, 1), out["lines"][:, 1].view(1, -1, 1, 1)
+            deq = out["q"].float() * ((hi - lo) / 256.0) + lo
+        assert torch.equal(deq + 0.0, y + 0.0), key
