@@ -339,7 +339,7 @@ def run_ours(args):
         hb[1].copy_(g)
     hx, hg, hy, hgx = hbuf[0]
     ctx = c_void_p()
-    N.check(lib.qsb_host_ctx_create(byref(ctx), c_int64(n), c_int64(C), c_int(8)), "qsb_host_ctx_create")
+    N.check(lib.qsb_host_ctx_create(byref(ctx), c_int64(n), c_int64(C), c_int(args.e2e_chunks)), "qsb_host_ctx_create")
     e_state = dict(mag=torch.zeros(C, device=dev), mask=torch.ones(C, dtype=torch.bool, device=dev),
                    scale=torch.zeros(1, device=dev), dec=torch.zeros(1, device=dev), t=0)
 
@@ -445,7 +445,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4 * world,
                 "d2h_bytes_per_step": 2 * n * 4 * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
                 "api": "qsb_host_prune_quant_step_submit / qsb_host_ctx_wait (C-ABI, pinned host buffers, 8 chunks, "
-                       "3 streams, two steps in flight)",
+                       "3 streams, two steps in flight)".replace("8 chunks", f"{args.e2e_chunks} chunks"),
                 "pcie_h2d_gbs": round(pcie_h2d, 1), "pcie_d2h_gbs": round(pcie_d2h, 1),
                 "bound": "PCIe, full duplex: per step 2 x 205.5 MB up (x, g) and 2 x 205.5 MB down (y, gx); step t+1's "
                          "upload overlaps step t's download",
@@ -469,6 +469,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="batch chunks of the host-buffer pipeline")
     ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
                     help="1: launch the step's kernels with programmatic stream serialization (tuning key 12)")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
