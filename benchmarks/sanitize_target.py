@@ -37,6 +37,15 @@ masks = [torch.ones(w.shape, dtype=torch.bool, device=dev) for w in ws]
 outs = [torch.empty_like(w) for w in ws]
 for t in range(2):
     parallel.prune_weight_set_step(ws, mags, masks, outs, t, 0.5)
+# K9 fused prune step: sampled route (ties, NaN), generic route for the small tensors
+xs9 = [torch.randn(s, device=dev, generator=g) * 0.02 for s in (300_000, 131_072 + 5, 999)]
+xs9[0] = torch.relu(xs9[0])
+xs9[1][::1009] = float("nan")
+mg9 = [torch.zeros_like(x) for x in xs9]
+mk9 = [torch.ones(x.shape, dtype=torch.bool, device=dev) for x in xs9]
+ot9 = [torch.empty_like(x) for x in xs9]
+for t in range(2):
+    ops.prune_unstructured_step_batched_(mg9, xs9, mk9, ot9, [x.numel() // 2 for x in xs9], t)
 # fused training step pieces + maps + export
 x = torch.relu(torch.randn(8, 16, 14, 14, device=dev, generator=g))
 layout = (8, 16, 196)

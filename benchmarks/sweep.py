@@ -185,6 +185,17 @@ def main():
     thr = ops.kth_value(magf, n4 // 2)
     report("c4_mask_build_apply", 13 * n4, lambda: ops.mask_build_apply(magf, thr, wt, mk, out=yb))
     report("c4_torch_sort", 4 * n4, lambda: torch.sort(magf))
+    # the whole step (EMA + select + mask/apply) as three kernels' worth of calls, and in one pass (K9)
+    state = {"t": 3}
+
+    def c4_three_stage():
+        ops.magnitude_ema_full_(magf, wt, state["t"])
+        th = ops.kth_value(magf, n4 // 2)
+        ops.mask_build_apply(magf, th, wt, mk, out=yb)
+    report("c4_prune_step_3stage", 29 * n4, c4_three_stage, note="EMA 12 + select 4 + mask/apply 13 B/elem")
+    report("c4_prune_step_fused", 29 * n4,
+           lambda: ops.prune_unstructured_step_batched_([magf], [wt], [mk], [yb], [n4 // 2], state["t"]),
+           note="K9: one streaming pass, ~17.5 B/elem of traffic; GB/s on the reference's 29 B/elem")
     del wt, magf, yb, mk, x, g, y
 
     # ---------------- config 5: flat sweep, fused prune(element mask) + pow2 quant fwd, bwd

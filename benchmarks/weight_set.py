@@ -49,6 +49,14 @@ def timed(fn, iters=8):
     return ts[len(ts) // 2]
 
 
+if "--tune" in sys.argv:
+    for per in (1, 2, 4):
+        for sig in (30, 35, 45):
+            ops.set_tuning(13, per)
+            ops.set_tuning(14, sig)
+            print(json.dumps(dict(kernel="c4_weight_set_step", samples_k=8 * per, sigma=sig / 10, us=round(timed(step), 1))))
+    ops.set_tuning(13, 2)
+    ops.set_tuning(14, 35)
 t_eager = timed(step)
 side = torch.cuda.Stream()
 side.wait_stream(torch.cuda.current_stream())

@@ -73,7 +73,9 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *   key 10 / 11: persistent CTAs per SM (0 = up to 3) / ring stages (0 = auto) of the latter;
  *   key 12: 1 = the streaming, reduction and fused-parameter kernels are launched with
  *          programmatic stream serialization (each begins with griddepcontrol.wait, so
- *          stream order is unchanged; launch latency overlaps the predecessor's tail). */
+ *          stream order is unchanged; launch latency overlaps the predecessor's tail);
+ *   key 13 / 14: fused prune step: samples per sampler thread (1, 2 = default, 4) / distance
+ *          of the pivots from the estimated rank in tenths of a sigma (default 35). */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and
@@ -250,6 +252,27 @@ int qsb_mask_build_apply_multi(const float *const *importance, int take_abs,
                                const float *thr_dev, const float *const *x,
                                float *const *y, uint8_t *const *mask_out,
                                const int64_t *n, int count, void *stream);
+
+/* One unstructured, running-average prune step of `count` tensors in ONE streaming pass
+ * (17 B/elem instead of 12 + 4 + 13 = 29 for the three calls above), per tensor i:
+ *   magnitude[i] = (t*magnitude[i] + |x[i]|) / (t+1)        ref qsparse/sparse.py:82-89
+ *   thr[i]       = sort(magnitude[i])[k[i]]                 ref qsparse/util.py:113-116
+ *   mask_out[i]  = magnitude[i] >= thr[i];  y[i] = x[i] * mask_out[i]   ref sparse.py:65-66
+ * How: the sampler estimates, from 8 Ki of the magnitudes the EMA is about to produce, two
+ * pivots that bracket the threshold and their midpoint; the streaming pass computes the
+ * EMA, writes mask / y provisionally (>= midpoint), and records the ~4 % of elements
+ * between the pivots with their positions; the select runs on those; a fix-up kernel
+ * patches the few records whose provisional decision differs from the final one.  When
+ * the pivots miss (decided on the device) the masks are rebuilt by a gated full pass.
+ * Results are bit-identical to the three separate calls.  Host arrays of pointers /
+ * sizes; QSB_E_UNSUPPORTED when a tensor is not 32-byte aligned. */
+int64_t qsb_prune_step_workspace_bytes(const int64_t *n, int count);
+int qsb_prune_unstructured_step_batched(float *const *magnitude,
+                                        const float *const *x, float *const *y,
+                                        uint8_t *const *mask_out, const int64_t *n,
+                                        const int64_t *k, int count, int64_t t,
+                                        float *thr_out_dev, void *workspace,
+                                        int64_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * K5  exact k-th value (ascending, 0-based rank k) by radix select on the

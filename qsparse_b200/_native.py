@@ -48,6 +48,11 @@ _SIGNATURES = {
     "qsb_mask_build_apply_multi": (c_int, [ctypes.POINTER(c_void_p), c_int, _P, ctypes.POINTER(c_void_p),
                                            ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
                                            ctypes.POINTER(c_int64), c_int, _P]),
+    "qsb_prune_step_workspace_bytes": (c_int64, [ctypes.POINTER(c_int64), c_int]),
+    "qsb_prune_unstructured_step_batched": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                                    ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                                    ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int, c_int64,
+                                                    _P, _P, c_int64, _P]),
     "qsb_kth_workspace_bytes": (c_int64, [c_int64]),
     "qsb_kth_value": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int64, _P]),
     "qsb_kth_batched_workspace_bytes": (c_int64, [ctypes.POINTER(c_int64), c_int]),

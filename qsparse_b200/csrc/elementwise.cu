@@ -18,6 +18,8 @@ void set_select_pdl(int v);
 void set_row_tma(int v);
 void set_row_ctas_per_sm(int v);
 void set_row_stages(int v);
+void set_step_sample_per(int v);
+void set_step_sigma10(int v);
 }
 
 namespace qsb {
@@ -500,6 +502,14 @@ extern "C" int qsb_set_tuning(int key, int value) {
   }
   if (key == 12) {
     set_pdl_enabled(value);
+    return 0;
+  }
+  if (key == 13) {
+    set_step_sample_per(value);
+    return 0;
+  }
+  if (key == 14) {
+    set_step_sigma10(value);
     return 0;
   }
   return QSB_E_BADARG;

@@ -33,6 +33,12 @@ __device__ __forceinline__ float magnitude_ema_step(float mag, float m,
   return __fdiv_rn(__fadd_rn(__fmul_rn((float)t, mag), m), (float)(t + 1));
 }
 
+// full-size magnitude EMA  mag = (t * mag + |x|) / (t + 1)   ref qsparse/sparse.py:85-89
+// (t_f = float(t), tp1 = float(t + 1), rcp = RN(1 / tp1) computed on the host)
+__device__ __forceinline__ float ema_full_step(float mag, float x, float t_f, float tp1, float rcp) {
+  return div_rn_by(__fadd_rn(__fmul_rn(t_f, mag), fabsf(x)), tp1, rcp, true);
+}
+
 // lines = (w * (t - 1) + new) / t     ref qsparse/quantize.py:428-430
 __device__ __forceinline__ float lines_ema_step(float w, float nw, float tm1, float t) {
   return __fdiv_rn(__fadd_rn(__fmul_rn(w, tm1), nw), t);

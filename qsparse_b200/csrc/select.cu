@@ -38,6 +38,7 @@
 #include <math.h>
 #include <stddef.h>
 
+#include "param_math.cuh"
 #include "qsb_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -80,6 +81,14 @@ struct SelState {
   unsigned long long count_below;  // values < lo plus (ties) values == lo   (written by the first pass)
   uint32_t done;                // generic pass 2 ticket
   uint32_t done_b, done_c;      // fast pass tickets
+  float mid;                    // fused prune step: provisional threshold (key midpoint of [lo, hi])
+  uint32_t need_full;           // fused prune step: the provisional masks cannot be patched, redo them all
+};
+
+// Fused unstructured prune step (EMA -> threshold -> mask -> apply in ONE streaming pass, see
+// qsb_prune_unstructured_step_batched): extra per-call constants of the magnitude EMA.
+struct EmaC {
+  float t_f, tp1, rcp;
 };
 static_assert(offsetof(SelState, lo) == 0 && offsetof(SelState, hi) == 4, "the partition kernel loads both pivots at once");
 
@@ -143,6 +152,8 @@ __device__ uint32_t fast_route(const FastBufs &fb, SelState *st_rw, int pass,
       if (blockIdx.x == 0) {
         st_rw->count_below = lt + eq;
         st_rw->route = route;
+        // (fused prune step) ties at lo were provisionally pruned and are not in the candidate list
+        st_rw->need_full = (route == 2) || (route == 3 && fb.st->width > 0);
         if (route == 3) *thr_out = fb.st->lo;
       }
     }
@@ -552,10 +563,11 @@ __device__ __forceinline__ void cluster_sum_hist(cg::cluster_group &cluster, uin
   reinterpret_cast<uint2 *>(h)[threadIdx.x] = acc;
 }
 
-template <int PER>
+template <int PER, bool STEP>
 __device__ __forceinline__ void select_sample_body(const float *__restrict__ v, int64_t n,
                                                    int take_abs, int r_lo, int r_hi, SelState *st,
-                                                   uint4 *zero_base, int zero_vecs) {
+                                                   uint4 *zero_base, int zero_vecs,
+                                                   const float *__restrict__ w, EmaC ec) {
   static_assert(kFastBins == 2 * kSampleThreads, "two bins per thread");
   constexpr int kSampleSize = kSampleThreads * kSampleCtas * PER;
   constexpr int kTieMinCount = kSampleSize / 50;  // >= 2 % of the sample in lo's bucket: ties at lo
@@ -575,8 +587,12 @@ __device__ __forceinline__ void select_sample_body(const float *__restrict__ v, 
   pdl_trigger();  // the partition kernel may start loading v on the other SMs right away
   float f[PER];
 #pragma unroll
-  for (int q = 0; q < PER; ++q)
-    f[q] = v[(int64_t)(q * kSampleThreads * kSampleCtas + i) * stride + (stride >> 1)];
+  for (int q = 0; q < PER; ++q) {
+    const int64_t at = (int64_t)(q * kSampleThreads * kSampleCtas + i) * stride + (stride >> 1);
+    f[q] = v[at];
+    // fused prune step: sample the magnitudes the EMA is ABOUT to produce
+    if constexpr (STEP) f[q] = ema_full_step(f[q], w[at], ec.t_f, ec.tp1, ec.rcp);
+  }
   for (int j = i; j < zero_vecs; j += kSampleThreads * kSampleCtas) zero_base[j] = make_uint4(0, 0, 0, 0);
   reinterpret_cast<uint2 *>(h0)[tid] = make_uint2(0, 0);
   reinterpret_cast<uint2 *>(ha)[tid] = make_uint2(0, 0);
@@ -636,6 +652,7 @@ __device__ __forceinline__ void select_sample_body(const float *__restrict__ v, 
       // many samples in lo's 22-bit bucket (zeros of a ReLU output, a value of a quantisation
       // grid): count the values == lo instead of storing them.  Also when lo == hi.
       st->tie_lo = (span == 0u) || lo_tie;
+      st->mid = key_to_float(lo_key + (span >> 1) + (span & 1u));  // > lo whenever lo < hi
     }
   }
   cluster.sync();  // the other CTAs' shared memory must outlive CTA 0's reads
@@ -686,10 +703,20 @@ __device__ __forceinline__ uint32_t classify8(const VecF<8> &x, float lo, float 
   return (uint32_t)__float2int_rz(acc);
 }
 
-template <int U, bool ABS>
+struct StepPtrs {  // fused prune step only
+  const float *w;       // the tensor behind the magnitudes; the mask is applied to it
+  float *mag;           // == v, writable
+  float *y;
+  uint8_t *mask;
+  uint32_t *cand_idx;   // element index of every stored candidate (parallel to cand)
+};
+
+template <int U, bool ABS, bool STEP>
 __device__ __forceinline__ void select_partition_body(const float *__restrict__ v, int64_t n,
                                                       const SelState *st, unsigned long long *segctr,
-                                                      float *__restrict__ cand, uint32_t seg_cap) {
+                                                      float *__restrict__ cand, uint32_t seg_cap,
+                                                      StepPtrs sp, EmaC ec) {
+  static_assert(!STEP || !ABS, "magnitudes are non-negative");
   constexpr int V = 8;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * V * U;
   // every thread parks its own elements here so that the (rare) candidates can be picked
@@ -702,17 +729,40 @@ __device__ __forceinline__ void select_partition_body(const float *__restrict__ 
   const int64_t t0 = (int64_t)blockIdx.x * kTile;
   const int64_t base = t0 + (int64_t)tid * V;
   VecF<V> x[U];
+  VecF<V> wv[STEP ? U : 1];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int64_t e = base + (int64_t)u * QSB_THREADS * V;
-    if (e < n_main) x[u] = ld_vec<V, Hint::KEEP>(v + e);
+    if (e < n_main) {
+      x[u] = ld_vec<V, Hint::KEEP>(v + e);
+      if constexpr (STEP) wv[u] = ld_vec<V, Hint::KEEP>(sp.w + e);
+    }
   }
   const bool tail_owner = (t0 <= n_main && n_main < t0 + kTile);
-  float tail_val = 0.f;
+  float tail_val = 0.f, tail_w = 0.f;
   const bool has_tail = tail_owner && (n_main + tid < n);
-  if (has_tail) tail_val = v[n_main + tid];
+  if (has_tail) {
+    tail_val = v[n_main + tid];
+    if constexpr (STEP) tail_w = sp.w[n_main + tid];
+  }
   pdl_wait();     // the loads above are in flight; the pivots come from the sampler
   pdl_trigger();
+  if constexpr (STEP) {
+    // the magnitude EMA itself: x becomes the NEW magnitude, written back in place
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = base + (int64_t)u * QSB_THREADS * V;
+      if (e < n_main) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) x[u].v[j] = ema_full_step(x[u].v[j], wv[u].v[j], ec.t_f, ec.tp1, ec.rcp);
+        st_vec<V, Hint::KEEP>(sp.mag + e, x[u]);
+      }
+    }
+    if (has_tail) {
+      tail_val = ema_full_step(tail_val, tail_w, ec.t_f, ec.tp1, ec.rcp);
+      sp.mag[n_main + tid] = tail_val;
+    }
+  }
   const float2 piv = *reinterpret_cast<const float2 *>(st);
   const float lo = piv.x, hi = piv.y;
   const bool tie = st->tie_lo != 0;
@@ -751,6 +801,32 @@ __device__ __forceinline__ void select_partition_body(const float *__restrict__ 
     if (tail_val < lo) ++lt;
     else if (tie && tail_val == lo) ++eq;
     else if (tail_val <= hi) tail_c = true, ++nc;
+  }
+  if constexpr (STEP) {
+    // provisional mask and output: keep what is >= mid.  Everything outside [lo, hi] is final;
+    // the candidates on the wrong side of the true threshold are patched by the fix-up kernel.
+    const float mid = st->mid;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = base + (int64_t)u * QSB_THREADS * V;
+      if (e < n_main) {
+        VecF<V> yv;
+        VecB<V> mb;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const bool keep = x[u].v[j] >= mid;  // false for NaN, like importance >= threshold
+          mb.b[j] = keep ? 1 : 0;
+          yv.v[j] = __fmul_rn(wv[u].v[j], keep ? 1.0f : 0.0f);
+        }
+        st_vec<V, Hint::KEEP>(sp.y + e, yv);
+        st_bytes<V>(sp.mask + e, mb);
+      }
+    }
+    if (has_tail) {
+      const bool keep = tail_val >= mid;
+      sp.mask[n_main + tid] = keep ? 1 : 0;
+      sp.y[n_main + tid] = __fmul_rn(tail_w, keep ? 1.0f : 0.0f);
+    }
   }
   if (nc) {
 #pragma unroll
@@ -793,6 +869,7 @@ __device__ __forceinline__ void select_partition_body(const float *__restrict__ 
   const long long g = s_gbase;
   if (nc == 0 || g < 0) return;  // nothing to store, or the segment is full
   float *out = cand + (size_t)seg * seg_cap + (uint32_t)g;
+  uint32_t *out_idx = STEP ? sp.cand_idx + (size_t)seg * seg_cap + (uint32_t)g : nullptr;
   uint32_t pos = wbase + (incl - nc);
   const float *sx = reinterpret_cast<const float *>(s_x);
 #pragma unroll
@@ -803,10 +880,93 @@ __device__ __forceinline__ void select_partition_body(const float *__restrict__ 
       m &= m - 1;
       const int q = 4 * w + (b >> 3);  // float4 row of s_x: u * 2 + j / 4
       const float a = sx[((q * QSB_THREADS) + tid) * 4 + ((b >> 1) & 3)];
+      if constexpr (STEP)  // where the candidate lives, for the fix-up of its mask / output
+        out_idx[pos] = (uint32_t)(base + (int64_t)(2 * w + (b >> 4)) * QSB_THREADS * V + ((b & 15) >> 1));
       out[pos++] = (ABS ? fabsf(a) : a) + 0.0f;  // -0 -> +0
     }
   }
-  if (tail_c) out[pos] = tail_val + 0.0f;
+  if (tail_c) {
+    if constexpr (STEP) out_idx[pos] = (uint32_t)(n_main + tid);
+    out[pos] = tail_val + 0.0f;
+  }
+}
+
+// fused prune step, after the threshold is known: patch the candidates whose provisional
+// decision (>= mid) differs from the final one (>= thr) — a few 0.1 % of the elements.
+__device__ __forceinline__ void step_fixup_body(const SelState *st, const unsigned long long *segctr,
+                                                const float *__restrict__ cand,
+                                                const uint32_t *__restrict__ cand_idx, uint32_t seg_cap,
+                                                const float *__restrict__ thr_dev, StepPtrs sp) {
+  pdl_wait();
+  pdl_trigger();
+  if (st->need_full) return;  // the gated full pass rebuilds everything instead
+  const unsigned nctas = gridDim.x / kSegs * kSegs;
+  if (blockIdx.x >= nctas) return;
+  const float thr = *thr_dev, mid = st->mid;
+  const int seg = blockIdx.x % kSegs, part = blockIdx.x / kSegs, parts = nctas / kSegs;
+  const uint32_t nc = (uint32_t)__ldcg(segctr + seg * kSegStride);
+  const float *cv = cand + (size_t)seg * seg_cap;
+  const uint32_t *ci = cand_idx + (size_t)seg * seg_cap;
+  auto patch = [&](float val, uint32_t i) {
+    const bool prov = val >= mid, fin = val >= thr;
+    if (prov != fin) {
+      const uint32_t e = ci[i];
+      sp.mask[e] = fin ? 1 : 0;
+      sp.y[e] = __fmul_rn(sp.w[e], fin ? 1.0f : 0.0f);
+    }
+  };
+  // four 128-bit loads of candidate values in flight per thread; positions are only read for a patch
+  const uint32_t n4 = nc >> 2, step = (uint32_t)parts * QSB_THREADS;
+  const float4 *c4 = reinterpret_cast<const float4 *>(cv);
+  for (uint32_t i = (uint32_t)part * QSB_THREADS + threadIdx.x; i < n4; i += 4 * step) {
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * step < n4) q[u] = c4[i + u * step];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * step < n4) {
+        const uint32_t b = (i + u * step) << 2;
+        patch(q[u].x, b);
+        patch(q[u].y, b + 1);
+        patch(q[u].z, b + 2);
+        patch(q[u].w, b + 3);
+      }
+  }
+  if (part == 0 && threadIdx.x < (nc & 3u)) patch(cv[(n4 << 2) + threadIdx.x], (n4 << 2) + threadIdx.x);
+}
+
+// fused prune step, the rare complete redo (generic route, or rank k inside a block of ties at
+// lo): mask = magnitude >= thr, y = w * mask over the whole segment.  Always launched, gated
+// on the device; `force`: the segment never had provisional outputs (too small for the fast route).
+__device__ __forceinline__ void step_full_mask_body(const SelState *st, bool force, int64_t n,
+                                                    const float *__restrict__ thr_dev, StepPtrs sp) {
+  pdl_wait();
+  pdl_trigger();
+  if (!force && !st->need_full) return;
+  const float thr = *thr_dev;
+  constexpr int V = 8;
+  const int64_t n_main = (n / V) * V;
+  for (int64_t e = ((int64_t)blockIdx.x * QSB_THREADS + threadIdx.x) * V; e < n_main;
+       e += (int64_t)gridDim.x * QSB_THREADS * V) {
+    const VecF<V> m = ld_vec<V, Hint::KEEP>(sp.mag + e), wv = ld_vec<V, Hint::KEEP>(sp.w + e);
+    VecF<V> yv;
+    VecB<V> mb;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const bool keep = m.v[j] >= thr;
+      mb.b[j] = keep ? 1 : 0;
+      yv.v[j] = __fmul_rn(wv.v[j], keep ? 1.0f : 0.0f);
+    }
+    st_vec<V, Hint::KEEP>(sp.y + e, yv);
+    st_bytes<V>(sp.mask + e, mb);
+  }
+  if (blockIdx.x == 0 && n_main + threadIdx.x < n) {
+    const int64_t e = n_main + threadIdx.x;
+    const bool keep = sp.mag[e] >= thr;
+    sp.mask[e] = keep ? 1 : 0;
+    sp.y[e] = __fmul_rn(sp.w[e], keep ? 1.0f : 0.0f);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -831,8 +991,13 @@ struct SegDesc {
   uint32_t seg_cap;
   int r_lo, r_hi;      // sample ranks of the pivots
   int fast;            // 0: generic passes only (small or unaligned input)
+  // fused prune step only (v is then the magnitude tensor, updated in place)
+  const float *w;
+  float *y;
+  uint8_t *mask;
+  uint32_t *cand_idx;
 };
-constexpr int kMaxSegs = 40;  // 40 x 64 B of kernel parameters
+constexpr int kMaxSegs = 32;  // 32 x 96 B of kernel parameters
 struct SegTable {
   SegDesc d[kMaxSegs];
 };
@@ -854,9 +1019,13 @@ __host__ __device__ inline SelState *st_of(unsigned char *hdr) {
   return reinterpret_cast<SelState *>(hdr + kHistBytes + kFastHistBytes + kSegCtrBytes);
 }
 
-template <int PER>
+__device__ __forceinline__ StepPtrs step_ptrs(const SegDesc &d) {
+  return StepPtrs{d.w, const_cast<float *>(d.v), d.y, d.mask, d.cand_idx};
+}
+
+template <int PER, bool STEP>
 __global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThreads)
-    select_sample_kernel(const __grid_constant__ SegTable tab, int take_abs) {
+    select_sample_kernel(const __grid_constant__ SegTable tab, int take_abs, EmaC ec) {
   const SegDesc &d = tab.d[blockIdx.y];
   uint4 *zb = reinterpret_cast<uint4 *>(d.hdr);
   constexpr int zv = (int)(kSelectHeaderBytes / 16);
@@ -865,7 +1034,7 @@ __global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThr
       zb[j] = make_uint4(0, 0, 0, 0);
     return;
   }
-  select_sample_body<PER>(d.v, d.n, take_abs, d.r_lo, d.r_hi, st_of(d.hdr), zb, zv);
+  select_sample_body<PER, STEP>(d.v, d.n, take_abs, d.r_lo, d.r_hi, st_of(d.hdr), zb, zv, d.w, ec);
 }
 
 template <int U, bool ABS>
@@ -873,7 +1042,43 @@ __global__ void __launch_bounds__(QSB_THREADS, U == 2 ? 8 : 5)
     select_partition_kernel(const __grid_constant__ SegTable tab) {
   const SegDesc &d = tab.d[blockIdx.y];
   if (!d.fast || (int64_t)blockIdx.x * (QSB_THREADS * 8 * U) >= d.n) return;
-  select_partition_body<U, ABS>(d.v, d.n, st_of(d.hdr), segctr_of(d.hdr), d.cand, d.seg_cap);
+  select_partition_body<U, ABS, false>(d.v, d.n, st_of(d.hdr), segctr_of(d.hdr), d.cand, d.seg_cap,
+                                       StepPtrs{}, EmaC{});
+}
+
+// fused prune step: EMA + partition + provisional mask / output in one streaming pass
+__global__ void __launch_bounds__(QSB_THREADS, 4)
+    step_partition_kernel(const __grid_constant__ SegTable tab, EmaC ec) {
+  constexpr int U = 2;
+  constexpr int64_t kTile = (int64_t)QSB_THREADS * 8 * U;
+  const SegDesc &d = tab.d[blockIdx.y];
+  const int64_t t0 = (int64_t)blockIdx.x * kTile;
+  if (t0 >= d.n) return;
+  if (d.fast) {
+    select_partition_body<U, false, true>(d.v, d.n, st_of(d.hdr), segctr_of(d.hdr), d.cand, d.seg_cap,
+                                          step_ptrs(d), ec);
+    return;
+  }
+  // a segment too small for the sampled route: just the EMA (its mask comes from the full pass)
+  pdl_wait();
+  pdl_trigger();
+  float *mag = const_cast<float *>(d.v);
+  const int64_t end = t0 + kTile < d.n ? t0 + kTile : d.n;
+  for (int64_t e = t0 + threadIdx.x; e < end; e += QSB_THREADS)
+    mag[e] = ema_full_step(mag[e], d.w[e], ec.t_f, ec.tp1, ec.rcp);
+}
+
+__global__ void __launch_bounds__(QSB_THREADS)
+    step_fixup_kernel(const __grid_constant__ SegTable tab) {
+  const SegDesc &d = tab.d[blockIdx.y];
+  if (!d.fast) return;
+  step_fixup_body(st_of(d.hdr), segctr_of(d.hdr), d.cand, d.cand_idx, d.seg_cap, d.thr_out, step_ptrs(d));
+}
+
+__global__ void __launch_bounds__(QSB_THREADS)
+    step_full_mask_kernel(const __grid_constant__ SegTable tab) {
+  const SegDesc &d = tab.d[blockIdx.y];
+  step_full_mask_body(st_of(d.hdr), !d.fast, d.n, d.thr_out, step_ptrs(d));
 }
 
 template <int PASS, int V, bool ABS>
@@ -907,13 +1112,14 @@ static int64_t seg_workspace_bytes(int64_t n) {
   return kSelectHeaderBytes + (cand + 255) / 256 * 256;
 }
 
-template <class K>
-static int launch_seg(K kernel, dim3 grid, dim3 block, cudaStream_t stream, bool pdl, const SegTable &tab) {
+template <class K, class... A>
+static int launch_seg(K kernel, dim3 grid, dim3 block, cudaStream_t stream, bool pdl, const SegTable &tab,
+                      A... extra) {
   if (pdl && g_select_pdl) {  // the previous kernel of this select is the dependency
-    QSB_CUDA_TRY(launch_pdl(kernel, grid, block, 0, stream, tab));
+    QSB_CUDA_TRY(launch_pdl(kernel, grid, block, 0, stream, tab, extra...));
     return 0;
   }
-  kernel<<<grid, block, 0, stream>>>(tab);
+  kernel<<<grid, block, 0, stream>>>(tab, extra...);
   QSB_LAUNCH_CHECK();
   return 0;
 }
@@ -942,11 +1148,17 @@ static int launch_pass(const SegTable &tab, int L, int64_t max_n, bool any_fast,
 // descs[0..L): one launch sequence.  v8: every segment is 32-byte aligned (256-bit loads).
 // samples per sampler thread: the tuning value for one select; 8 Ki samples per segment for a batch
 // (its segments are small: 16 Ki samples of a 2.4 M-element layer would touch a fifth of its lines)
-static int sample_per(bool batched) { return batched ? 1 : g_sample_per; }
+static int g_step_sample_per = 2;   // tuning key 13: samples per sampler thread in the fused prune step
+static int g_step_sigma10 = 35;     // tuning key 14: pivot distance in 0.1 sigma in the fused prune step
+void set_step_sample_per(int v) { g_step_sample_per = (v == 1 || v == 4) ? v : 2; }
+void set_step_sigma10(int v) { g_step_sigma10 = v < 20 ? 20 : (v > 60 ? 60 : v); }
+static int sample_per(bool batched, bool step = false) {
+  return step ? g_step_sample_per : (batched ? 1 : g_sample_per);
+}
 
-template <bool ABS>
+template <bool ABS, bool STEP = false>
 static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, bool batched,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, EmaC ec = EmaC{}) {
   SegTable tab;
   int64_t max_n = 0, max_fast_n = 0;
   for (int i = 0; i < L; ++i) {
@@ -959,16 +1171,21 @@ static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, bo
   if (first_after_kernel) {
     // pivots for the fast segments; zeroes every segment's header (no memset node)
     const dim3 sg(kSampleCtas, (unsigned)L);
-    const int per = sample_per(batched);
+    const int per = sample_per(batched, STEP);
     if (per == 1)
-      select_sample_kernel<1><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
+      select_sample_kernel<1, STEP><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0, ec);
     else if (per == 4)
-      select_sample_kernel<4><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
+      select_sample_kernel<4, STEP><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0, ec);
     else
-      select_sample_kernel<2><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0);
+      select_sample_kernel<2, STEP><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0, ec);
     QSB_LAUNCH_CHECK();
   }
-  if (any_fast) {
+  if constexpr (STEP) {
+    // EMA for every segment, partition + provisional outputs for the fast ones: one streaming pass
+    const int64_t tile = (int64_t)QSB_THREADS * 8 * 2;
+    const dim3 pg((unsigned)((max_n + tile - 1) / tile), (unsigned)L);
+    if ((rc = launch_seg(step_partition_kernel, pg, dim3(QSB_THREADS), stream, true, tab, ec))) return rc;
+  } else if (any_fast) {
     const int u = g_partition_u;
     const int64_t tile = (int64_t)QSB_THREADS * 8 * u;
     const dim3 pg((unsigned)((max_fast_n + tile - 1) / tile), (unsigned)L);
@@ -979,7 +1196,26 @@ static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, bo
   if (v8) {
     if ((rc = launch_pass<0, 8, ABS>(tab, L, max_n, any_fast, stream, first_after_kernel))) return rc;
     if ((rc = launch_pass<1, 8, ABS>(tab, L, max_n, any_fast, stream, true))) return rc;
-    return launch_pass<2, 8, ABS>(tab, L, max_n, any_fast, stream, true);
+    if ((rc = launch_pass<2, 8, ABS>(tab, L, max_n, any_fast, stream, true))) return rc;
+    if constexpr (STEP) {
+      // patch the few candidates on the wrong side of the threshold; redo whole segments only where
+      // the sampled route was not taken (both decide on the device and mostly exit at once)
+      if (any_fast) {
+        int parts = 16 * device_props().sm_count / (kSegs * L);  // ~16 CTAs per SM over all segments
+        if (parts < 1) parts = 1;
+        if (parts > 16) parts = 16;
+        if ((rc = launch_seg(step_fixup_kernel, dim3((unsigned)(kSegs * parts), (unsigned)L),
+                             dim3(QSB_THREADS), stream, true, tab)))
+          return rc;
+      }
+      int64_t fg = 4 * (int64_t)device_props().sm_count / L;
+      const int64_t vt = (max_n + QSB_THREADS * 8 - 1) / (QSB_THREADS * 8);
+      if (fg > vt) fg = vt;
+      if (fg < 1) fg = 1;
+      return launch_seg(step_full_mask_kernel, dim3((unsigned)fg, (unsigned)L), dim3(QSB_THREADS), stream,
+                        true, tab);
+    }
+    return 0;
   }
   if ((rc = launch_pass<0, 1, ABS>(tab, L, max_n, any_fast, stream, first_after_kernel))) return rc;
   if ((rc = launch_pass<1, 1, ABS>(tab, L, max_n, any_fast, stream, true))) return rc;
@@ -988,7 +1224,7 @@ static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, bo
 
 // fill one descriptor; returns the bytes of workspace it uses
 static int64_t make_desc(SegDesc &d, const float *v, int64_t n, int64_t k, float *thr_out,
-                         unsigned char *hdr, bool batched) {
+                         unsigned char *hdr, bool batched, bool step = false) {
   d.v = v;
   d.n = n;
   d.k = k;
@@ -996,10 +1232,17 @@ static int64_t make_desc(SegDesc &d, const float *v, int64_t n, int64_t k, float
   d.hdr = hdr;
   d.cand = reinterpret_cast<float *>(hdr + kSelectHeaderBytes);
   d.seg_cap = (uint32_t)seg_slots(n);
+  d.w = nullptr;
+  d.y = nullptr;
+  d.mask = nullptr;
+  d.cand_idx = nullptr;
   d.fast = g_select_fast && aligned_to(v, 32) && n >= (batched ? kFastMinNBatched : kFastMinN);
   // sample ranks bracketing k: +-4.5 sigma of the binomial rank error, +3
-  const double m = (double)(kSampleThreads * kSampleCtas * sample_per(batched)), p = (double)k / (double)n;
-  const double delta = 4.5 * sqrt(m * p * (1.0 - p)) + 3.0;
+  const double m = (double)(kSampleThreads * kSampleCtas * sample_per(batched, step)), p = (double)k / (double)n;
+  // a miss of the pivots costs one full redo of the step's masks (~the price of the step), so the fused
+  // step brackets tighter than a select whose miss costs three full passes
+  const double sigmas = step ? g_step_sigma10 / 10.0 : 4.5;
+  const double delta = sigmas * sqrt(m * p * (1.0 - p)) + 3.0;
   d.r_lo = (int)floor(p * m - delta);
   d.r_hi = (int)ceil(p * m + delta);
   return seg_workspace_bytes(n);
@@ -1060,6 +1303,64 @@ extern "C" int qsb_kth_value_batched(const float *const *v, const int64_t *n, co
     if (aligned_to(v[i], 32)) continue;
     group[L++] = d;
     if ((rc = flush(false))) return rc;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// fused unstructured prune step over a set of tensors
+// ---------------------------------------------------------------------------
+static int64_t step_seg_workspace_bytes(int64_t n) {
+  const int64_t cand = n >= kFastMinNBatched ? kSegs * seg_slots(n) * (int64_t)sizeof(float) : 0;
+  return kSelectHeaderBytes + 2 * ((cand + 255) / 256 * 256);  // values + element indices
+}
+
+extern "C" int64_t qsb_prune_step_workspace_bytes(const int64_t *n, int count) {
+  int64_t total = 256;
+  for (int i = 0; i < count; ++i) total += step_seg_workspace_bytes(n[i]);
+  return total;
+}
+
+extern "C" int qsb_prune_unstructured_step_batched(float *const *magnitude, const float *const *x,
+                                                   float *const *y, uint8_t *const *mask_out,
+                                                   const int64_t *n, const int64_t *k, int count,
+                                                   int64_t t, float *thr_out_dev, void *workspace,
+                                                   int64_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (count < 0 || t < 0 || !magnitude || !x || !y || !mask_out || !n || !k || !thr_out_dev || !workspace)
+    return QSB_E_BADARG;
+  if (count == 0) return 0;
+  for (int i = 0; i < count; ++i) {
+    if (n[i] <= 0 || k[i] < 0 || k[i] >= n[i] || !magnitude[i] || !x[i] || !y[i] || !mask_out[i])
+      return QSB_E_BADARG;
+    // whole 256-bit vectors everywhere: anything else takes the separate kernels
+    if (!aligned_to(magnitude[i], 32) || !aligned_to(x[i], 32) || !aligned_to(y[i], 32) ||
+        !aligned_to(mask_out[i], 8))
+      return QSB_E_UNSUPPORTED;
+  }
+  if (workspace_bytes < qsb_prune_step_workspace_bytes(n, count)) return QSB_E_WORKSPACE;
+  const float tp1 = (float)(t + 1);
+  volatile float rcp = 1.0f / tp1;  // IEEE round-to-nearest on the host, as in qsb_magnitude_ema_full
+  const EmaC ec{(float)t, tp1, rcp};
+  unsigned char *hdr =
+      reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  SegDesc group[kMaxSegs];
+  int L = 0, rc;
+  for (int i = 0; i < count; ++i) {
+    SegDesc d;
+    make_desc(d, magnitude[i], n[i], k[i], thr_out_dev + i, hdr, true, true);
+    const int64_t cand_bytes = (step_seg_workspace_bytes(n[i]) - kSelectHeaderBytes) / 2;
+    d.cand_idx = reinterpret_cast<uint32_t *>(hdr + kSelectHeaderBytes + cand_bytes);
+    d.w = x[i];
+    d.y = y[i];
+    d.mask = mask_out[i];
+    if (n[i] >= (1ll << 32)) d.fast = 0;  // candidate positions are 32-bit
+    hdr += step_seg_workspace_bytes(n[i]);
+    group[L++] = d;
+    if (L == kMaxSegs || i == count - 1) {
+      if ((rc = run_group<false, true>(group, L, true, true, true, stream, ec))) return rc;
+      L = 0;
+    }
   }
   return 0;
 }

@@ -354,6 +354,31 @@ def mask_build_apply_multi(importances, thr, xs, masks, outs, take_abs=False):
     return outs
 
 
+def prune_step_supported(magnitudes, xs, masks, outs) -> bool:
+    """can ``prune_unstructured_step_batched_`` take these tensors? (fp32 / bool, contiguous, 32-byte aligned)"""
+    return _multi_ok(magnitudes, xs, outs, masks) and all(x.dtype == torch.float32 for x in xs)
+
+
+def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int):
+    """K9: the whole unstructured running-average prune step of a set of tensors — magnitude EMA (in place),
+    exact k-th value threshold, mask, ``out = x * mask`` — in ONE streaming pass plus a few small launches
+    (17 B/elem instead of 29).  Returns the thresholds (float32 [L]).  Same results as
+    ``magnitude_ema_full_`` + ``kth_value`` + ``mask_build_apply`` per tensor."""
+    lib = N.load_library()
+    count = len(magnitudes)
+    dev = magnitudes[0].device
+    ns = (c_int64 * count)(*[m.numel() for m in magnitudes])
+    kk = (c_int64 * count)(*[int(k) for k in ks])
+    thr = torch.empty(count, dtype=torch.float32, device=dev)
+    nbytes = lib.qsb_prune_step_workspace_bytes(ns, c_int(count))
+    ws = N.workspace(dev, nbytes)
+    N.check(lib.qsb_prune_unstructured_step_batched(_ptr_array(magnitudes), _ptr_array(xs), _ptr_array(outs),
+                                                    _ptr_array(masks), ns, kk, c_int(count), c_int64(t), N.ptr(thr),
+                                                    N.ptr(ws), c_int64(ws.numel()), N.stream_ptr(dev)),
+            "qsb_prune_unstructured_step_batched")
+    return thr
+
+
 def kth_value_batched(vs, ks, take_abs=False):
     """thresholds ``sorted(vs[i])[ks[i]]`` of several tensors (the layers of a weight set) in ONE launch
     sequence: float32 device tensor [len(vs)].  Same kernels as ``kth_value``; blockIdx.y is the tensor."""

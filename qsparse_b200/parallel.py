@@ -226,6 +226,9 @@ def sharded_kth_value(v_local: torch.Tensor, k_global: int, group=None, take_abs
     return thr
 
 
+FUSE_PRUNE_STEP = True   # False: EMA / select / mask as three (multi-tensor) stages — same results
+
+
 def prune_weight_set_step(weights, magnitudes, masks, outs, t: int, sparsity: float, group=None):
     """One unstructured, running-average prune step over a set of replicated weight tensors
     (BASELINE config 4) on every rank of ``group``:
@@ -239,8 +242,12 @@ def prune_weight_set_step(weights, magnitudes, masks, outs, t: int, sparsity: fl
     from . import ops
     from .util import kth_rank
 
-    ops.magnitude_ema_full_multi_(magnitudes, weights, t)            # one launch for the whole set
     ks = [kth_rank(sparsity, m.numel()) for m in magnitudes]
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi and FUSE_PRUNE_STEP and ops.prune_step_supported(magnitudes, weights, masks, outs):
+        # one rank: EMA, select and mask/apply of every layer in ONE streaming pass (K9, 17 B/elem)
+        return ops.prune_unstructured_step_batched_(magnitudes, weights, masks, outs, ks, t)
+    ops.magnitude_ema_full_multi_(magnitudes, weights, t)            # one launch for the whole set
     thr = sharded_layer_thresholds(magnitudes, ks, group)            # one launch sequence per rank
     ops.mask_build_apply_multi(magnitudes, thr, weights, masks, outs)  # one launch
     return thr

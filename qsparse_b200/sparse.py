@@ -31,6 +31,11 @@ from .imitation import imitate
 from .util import HostMirror, get_option, kth_rank, logging
 
 
+# Route the stock unstructured running-average prune step through the one-pass kernel (K9).  False keeps
+# update_magnitude -> k-th value -> mask build + apply (same results; the tests compare the two).
+FUSE_PRUNE_STEP = True
+
+
 class _MaskApply(torch.autograd.Function):
     """``x * mask`` (ref qsparse/sparse.py:66,116,122,263) and its gradient ``g * mask``.
 
@@ -154,6 +159,29 @@ class MagnitudePruningCallback(nn.Module):
                 out = None
         return _MaskApply.apply(x, mask, out)
 
+    def _fused_unstructured_step(self, x, sparsity, mask, t):
+        """update_magnitude + prune_and_update_mask of the stock unstructured running-average case in ONE
+        streaming pass (K9, ``qsb_prune_unstructured_step_batched``: 17 B/elem instead of 29); None when
+        the case is not the stock one (a subclass, gradient / l0 importance, a structured mask, ...)."""
+        if not FUSE_PRUNE_STEP or type(self) is not MagnitudePruningCallback:
+            return None
+        if not self.running_average or self.use_gradient or self.l0 or not hasattr(self, "magnitude"):
+            return None
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and tuple(mask.shape) == tuple(x.shape)):
+            return None
+        with torch.no_grad():
+            xs = N.as_f32_contiguous(x.detach())
+            mag = self.magnitude.data
+            out = torch.empty_like(xs)
+            if not ops.prune_step_supported([mag], [xs], [mask.data], [out]):
+                return None
+            n = mask.numel()
+            k = kth_rank(sparsity, n)
+            if k >= n:
+                raise IndexError(f"index {k} is out of bounds for dimension 0 with size {n}")
+            ops.prune_unstructured_step_batched_([mag], [xs], [mask.data], [out], [k], t)
+        return _MaskApply.apply(x, mask, out)
+
     def forward(self, x: torch.Tensor, sparsity: float, mask: torch.Tensor, name=""):
         if not self.training:
             return apply_mask(x, mask)
@@ -163,11 +191,14 @@ class MagnitudePruningCallback(nn.Module):
             if self.mask_refresh_interval <= 0:
                 self.mask_refresh_interval = 1
         t = self._t()
-        if t < self.stop_mask_refresh:
-            self.receive_input(x)
         refresh = (sparsity >= 0 and (t % self.mask_refresh_interval == 0 and t <= self.stop_mask_refresh)
                    and (t > 0 or not self.running_average))
-        out = self.prune_and_update_mask(x, sparsity, mask) if refresh else apply_mask(x, mask)
+        out = self._fused_unstructured_step(x, sparsity, mask, t) if (refresh and t < self.stop_mask_refresh) \
+            else None
+        if out is None:
+            if t < self.stop_mask_refresh:
+                self.receive_input(x)
+            out = self.prune_and_update_mask(x, sparsity, mask) if refresh else apply_mask(x, mask)
         self.t += 1
         self._t_mirror.wrote(self.t, t + 1)
         if self.forward_hook is not None:

@@ -256,3 +256,33 @@ def test_fusion_pass_equals_unfused_layers():
     # checkpoint interchange: the unfused model loads the fused model's state and vice versa
     a.load_state_dict(b.state_dict())
     b.load_state_dict(a.state_dict())
+
+
+def test_unstructured_callback_fused_step_equals_unfused():
+    """MagnitudePruningCallback on a weight-shaped mask: the K9 route (one streaming pass) and the
+    update_magnitude -> kth_value -> mask_build_apply route give identical magnitudes, masks, outputs and
+    gradients, step after step (incl. the step-0 no-refresh rule and a non-contiguous input)."""
+    import importlib
+    sp = importlib.import_module("qsparse_b200.sparse")
+    res = {}
+    for fuse in (True, False):
+        sp.FUSE_PRUNE_STEP = fuse
+        try:
+            g = torch.Generator(device="cuda").manual_seed(3)
+            cb = sp.MagnitudePruningCallback(running_average=True)
+            cb.train()
+            mask = torch.nn.Parameter(torch.ones(96, 64, 3, 3, dtype=torch.bool, device="cuda"), requires_grad=False)
+            rec = []
+            for t in range(5):
+                w = (torch.randn(96, 64, 3, 3, device="cuda", generator=g) * 0.05).requires_grad_(True)
+                x = w.transpose(2, 3) if t == 3 else w          # a non-contiguous view once
+                y = cb(x, 0.6, mask)
+                y.sum().backward()
+                rec.append((y.detach().clone(), w.grad.clone(), mask.data.clone(), cb.magnitude.data.clone()))
+            res[fuse] = rec
+        finally:
+            sp.FUSE_PRUNE_STEP = True
+    for t, (a, b) in enumerate(zip(res[True], res[False])):
+        for i, (u, v) in enumerate(zip(a, b)):
+            assert torch.equal(u, v), (t, i)
+    assert abs(1 - res[True][-1][2].float().mean().item() - 0.6) < 1e-3

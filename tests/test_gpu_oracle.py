@@ -696,3 +696,55 @@ def test_export_integer_from_layers():
             lo, hi = out["lines"][:, 0].view(1, -1, 1, 1), out["lines"][:, 1].view(1, -1, 1, 1)
             deq = out["q"].float() * ((hi - lo) / 256.0) + lo
         assert torch.equal(deq + 0.0, y + 0.0), key
+
+
+# ----------------------------------------------------------------------------- K9 fused unstructured prune step
+def _step_reference(mags, xs, ks, t):
+    """EMA -> k-th value -> mask -> apply with the separate kernels (each pinned to the oracle elsewhere)"""
+    from qsparse_b200 import ops
+    thr, masks, outs = [], [], []
+    for m, x, k in zip(mags, xs, ks):
+        ops.magnitude_ema_full_(m, x, t)
+        th = ops.kth_value(m, k)
+        mk = torch.empty(x.shape, dtype=torch.bool, device=x.device)
+        outs.append(ops.mask_build_apply(m, th, x, mk))
+        masks.append(mk)
+        thr.append(th)
+    return torch.cat(thr), masks, outs
+
+
+@pytest.mark.parametrize("kind", ["normal", "half_zero_weights", "grid", "sorted", "with_nan", "constant"])
+def test_prune_step_fused_equals_separate_kernels(kind):
+    """K9 == magnitude_ema_full + kth_value + mask_build_apply, bit for bit (magnitudes, thresholds, masks,
+    outputs) over several steps, for sizes on both routes (sampled / generic), vector tails, heavy ties at the
+    threshold (zeros, a value grid, a constant tensor), adversarial order and NaNs."""
+    from qsparse_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    sizes = [2_359_296, 131_072 + 5, 300_007, 999, 1 << 20]
+    xs = [torch.randn(s, device="cuda", generator=g) * 0.02 for s in sizes]
+    if kind == "half_zero_weights":
+        xs = [torch.relu(x) for x in xs]
+    elif kind == "grid":
+        xs = [torch.round(x * 256) / 256 for x in xs]
+    elif kind == "sorted":
+        xs = [torch.sort(x).values for x in xs]
+    elif kind == "with_nan":
+        for x in xs:
+            x[::1009] = float("nan")
+    elif kind == "constant":
+        xs = [torch.full_like(x, 0.125) for x in xs]
+    mags_a = [torch.rand(s, device="cuda", generator=g) * 0.01 for s in sizes]
+    mags_b = [m.clone() for m in mags_a]
+    masks_a = [torch.ones(s, dtype=torch.bool, device="cuda") for s in sizes]
+    outs_a = [torch.full((s,), 7.0, device="cuda") for s in sizes]
+    for step, frac in enumerate((0.5, 0.75, 0.001, 0.98)):
+        ks = [min(max(int(frac * s), 0), s - 1) for s in sizes]
+        assert ops.prune_step_supported(mags_a, xs, masks_a, outs_a)
+        thr_a = ops.prune_unstructured_step_batched_(mags_a, xs, masks_a, outs_a, ks, step)
+        thr_b, masks_b, outs_b = _step_reference(mags_b, xs, ks, step)
+        for i in range(len(sizes)):
+            assert torch.equal(mags_a[i].view(torch.int32), mags_b[i].view(torch.int32)), (kind, step, i, "mag")
+            ta, tb = thr_a[i], thr_b[i]
+            assert (ta == tb).item() or (torch.isnan(ta) and torch.isnan(tb)).item(), (kind, step, i, ta, tb)
+            assert torch.equal(masks_a[i], masks_b[i]), (kind, step, i, "mask")
+            assert torch.equal(outs_a[i].view(torch.int32), outs_b[i].view(torch.int32)), (kind, step, i, "out")
