@@ -55,7 +55,7 @@ if "--tune" in sys.argv:
             ops.set_tuning(13, per)
             ops.set_tuning(14, sig)
             print(json.dumps(dict(kernel="c4_weight_set_step", samples_k=8 * per, sigma=sig / 10, us=round(timed(step), 1))))
-    ops.set_tuning(13, 2)
+    ops.set_tuning(13, 4)
     ops.set_tuning(14, 35)
 t_eager = timed(step)
 side = torch.cuda.Stream()

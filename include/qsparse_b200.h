@@ -65,7 +65,7 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *   key 6: 256-bit loads in flight per thread in the select's partition pass
  *          (2, 4 = default);
  *   key 7: samples per sampler thread of the select (1, 2 = default, 4 ->
- *          8 Ki, 16 Ki, 32 Ki samples);
+ *          8 Ki, 16 Ki, 32 Ki samples; 4 reads four neighbours per location);
  *   key 8: 1 = the kernels of one select are chained by programmatic dependent
  *          launch (default), 0 = ordinary stream order;
  *   key 9: qsb_row_quant_fused on rows of 1 Ki .. 16 Ki elements: 0 = register-
@@ -74,7 +74,7 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *   key 12: 1 = the streaming, reduction and fused-parameter kernels are launched with
  *          programmatic stream serialization (each begins with griddepcontrol.wait, so
  *          stream order is unchanged; launch latency overlaps the predecessor's tail);
- *   key 13 / 14: fused prune step: samples per sampler thread (1, 2 = default, 4) / distance
+ *   key 13 / 14: fused prune step: samples per sampler thread (1, 2, 4 = default) / distance
  *          of the pivots from the estimated rank in tenths of a sigma (default 35). */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with

@@ -586,12 +586,27 @@ __device__ __forceinline__ void select_sample_body(const float *__restrict__ v, 
 #endif
   pdl_trigger();  // the partition kernel may start loading v on the other SMs right away
   float f[PER];
+  if constexpr (PER == 4) {
+    // four neighbours per location (one 128-bit load): 32 Ki samples for the lines 8 Ki would touch —
+    // what matters for the layers of a weight set, where the sample is a visible fraction of the tensor
+    const int64_t stride4 = n / (kSampleThreads * kSampleCtas);
+    const int64_t at = ((int64_t)i * stride4 + (stride4 >> 1)) & ~(int64_t)3;
+    const float4 q4 = *reinterpret_cast<const float4 *>(v + at);
+    f[0] = q4.x, f[1] = q4.y, f[2] = q4.z, f[3] = q4.w;
+    if constexpr (STEP) {  // fused prune step: sample the magnitudes the EMA is ABOUT to produce
+      const float4 w4 = *reinterpret_cast<const float4 *>(w + at);
+      f[0] = ema_full_step(f[0], w4.x, ec.t_f, ec.tp1, ec.rcp);
+      f[1] = ema_full_step(f[1], w4.y, ec.t_f, ec.tp1, ec.rcp);
+      f[2] = ema_full_step(f[2], w4.z, ec.t_f, ec.tp1, ec.rcp);
+      f[3] = ema_full_step(f[3], w4.w, ec.t_f, ec.tp1, ec.rcp);
+    }
+  } else {
 #pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const int64_t at = (int64_t)(q * kSampleThreads * kSampleCtas + i) * stride + (stride >> 1);
-    f[q] = v[at];
-    // fused prune step: sample the magnitudes the EMA is ABOUT to produce
-    if constexpr (STEP) f[q] = ema_full_step(f[q], w[at], ec.t_f, ec.tp1, ec.rcp);
+    for (int q = 0; q < PER; ++q) {
+      const int64_t at = (int64_t)(q * kSampleThreads * kSampleCtas + i) * stride + (stride >> 1);
+      f[q] = v[at];
+      if constexpr (STEP) f[q] = ema_full_step(f[q], w[at], ec.t_f, ec.tp1, ec.rcp);
+    }
   }
   for (int j = i; j < zero_vecs; j += kSampleThreads * kSampleCtas) zero_base[j] = make_uint4(0, 0, 0, 0);
   reinterpret_cast<uint2 *>(h0)[tid] = make_uint2(0, 0);
@@ -1146,14 +1161,14 @@ static int launch_pass(const SegTable &tab, int L, int64_t max_n, bool any_fast,
 }
 
 // descs[0..L): one launch sequence.  v8: every segment is 32-byte aligned (256-bit loads).
-// samples per sampler thread: the tuning value for one select; 8 Ki samples per segment for a batch
-// (its segments are small: 16 Ki samples of a 2.4 M-element layer would touch a fifth of its lines)
-static int g_step_sample_per = 2;   // tuning key 13: samples per sampler thread in the fused prune step
+// samples per sampler thread: the tuning value for one select; for a batch (small segments: 16 Ki
+// scattered samples of a 2.4 M-element layer would touch a fifth of its lines) 8 Ki locations x 4 neighbours
+static int g_step_sample_per = 4;   // tuning key 13: samples per sampler thread in the fused prune step
 static int g_step_sigma10 = 35;     // tuning key 14: pivot distance in 0.1 sigma in the fused prune step
-void set_step_sample_per(int v) { g_step_sample_per = (v == 1 || v == 4) ? v : 2; }
+void set_step_sample_per(int v) { g_step_sample_per = (v == 1 || v == 2) ? v : 4; }
 void set_step_sigma10(int v) { g_step_sigma10 = v < 20 ? 20 : (v > 60 ? 60 : v); }
 static int sample_per(bool batched, bool step = false) {
-  return step ? g_step_sample_per : (batched ? 1 : g_sample_per);
+  return step ? g_step_sample_per : (batched ? 4 : g_sample_per);
 }
 
 template <bool ABS, bool STEP = false>
