@@ -107,7 +107,8 @@ def _weights_worker(rank, world, port, out):
     for t in range(3):
         for w in ws:
             w.mul_(1.0 + 0.05 * t)
-        thr = parallel.prune_weight_set_step(ws, mags, masks, outs, t, 0.75)
+        # alternate the two multi-GPU routes: layer-sharded select + all-reduce / replicated one-pass K9
+        thr = parallel.prune_weight_set_step(ws, mags, masks, outs, t, 0.75, shard_by_layer=(t != 1))
         thr_hist.append(thr.cpu().numpy())
     out.put(dict(rank=rank, kth=got, kth_signed=got_signed, thr=thr_hist,
                  masks=[m.cpu().numpy() for m in masks], outs=[o.cpu().numpy() for o in outs]))
