@@ -130,6 +130,19 @@ def main():
         state["t"] += 1
     report("fused_train_step", 20 * n, step)
 
+    # the reference-API route of config 2 (iii): MagnitudePruningCallback with a channel mask, refresh every step
+    import importlib
+    sp = importlib.import_module("qsparse_b200.sparse")
+    for fuse in (True, False):
+        sp.FUSE_PRUNE_STEP = fuse
+        cb = sp.MagnitudePruningCallback(running_average=True)
+        cb.train()
+        pmask = torch.nn.Parameter(torch.ones(1, 64, 1, 1, dtype=torch.bool, device=dev), requires_grad=False)
+        with torch.no_grad():
+            cb(x, 0.75, pmask)
+            report("prune_callback_structured_step", 12 * n, lambda: cb(x, 0.75, pmask),
+                   route="3 launches (partials, parameter kernel, apply)" if fuse else "9 launches")
+    sp.FUSE_PRUNE_STEP = True
     del emask
     # ---------------- config 3: [4096, 4096] channelwise=0
     w = torch.randn(4096, 4096, device=dev) * 0.02

@@ -182,6 +182,38 @@ class MagnitudePruningCallback(nn.Module):
             ops.prune_unstructured_step_batched_([mag], [xs], [mask.data], [out], [k], t)
         return _MaskApply.apply(x, mask, out)
 
+    def _fused_structured_step(self, x, sparsity, mask, t, refresh):
+        """update_magnitude [+ prune_and_update_mask] of the stock structured (channel-mask) case in three
+        launches — reduction partials, ONE parameter kernel (finalize, magnitude EMA, k-th value by rank
+        counting, mask), mask apply — instead of nine (reduce + finalize, EMA, a 4-launch select over C values,
+        mask build, apply).  None when the case is not the stock one."""
+        if not FUSE_PRUNE_STEP or type(self) is not MagnitudePruningCallback:
+            return None
+        if self.use_gradient or self.l0 or (self.running_average and not hasattr(self, "magnitude")):
+            return None
+        if not (self.running_average or refresh):
+            return None                                   # nothing to update: plain mask apply
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == mask.dim()):
+            return None
+        kind, layout = ops.mask_layout(x.shape, mask.shape)
+        outer, ch, inner = layout
+        if kind != "channel" or ch != mask.numel() or ch < 2 or ch > 2048 or outer * inner < 64:
+            return None
+        with torch.no_grad():
+            xs = N.as_f32_contiguous(x.detach())
+            k = kth_rank(sparsity, ch) if refresh else 0
+            if refresh and k >= ch:
+                raise IndexError(f"index {k} is out of bounds for dimension 0 with size {ch}")
+            if self.running_average:
+                magnitude, mode = self.magnitude.data.view(-1), 1
+            else:
+                magnitude, mode = torch.empty(ch, dtype=torch.float32, device=x.device), 2
+            dummy = torch.zeros(1, dtype=torch.float32, device=x.device)
+            ws = ops.reduce_partials(xs, layout)
+            ops.prune_quant_step_params(magnitude, mask.data.view(-1), dummy, None, ws, layout,
+                                        float(outer * inner), t, mode, refresh, k, 8, 0, False)
+        return apply_mask(x, mask)
+
     def forward(self, x: torch.Tensor, sparsity: float, mask: torch.Tensor, name=""):
         if not self.training:
             return apply_mask(x, mask)
@@ -193,8 +225,12 @@ class MagnitudePruningCallback(nn.Module):
         t = self._t()
         refresh = (sparsity >= 0 and (t % self.mask_refresh_interval == 0 and t <= self.stop_mask_refresh)
                    and (t > 0 or not self.running_average))
-        out = self._fused_unstructured_step(x, sparsity, mask, t) if (refresh and t < self.stop_mask_refresh) \
-            else None
+        out = None
+        if t < self.stop_mask_refresh:
+            if refresh:
+                out = self._fused_unstructured_step(x, sparsity, mask, t)
+            if out is None:
+                out = self._fused_structured_step(x, sparsity, mask, t, refresh)
         if out is None:
             if t < self.stop_mask_refresh:
                 self.receive_input(x)

@@ -286,3 +286,36 @@ def test_unstructured_callback_fused_step_equals_unfused():
         for i, (u, v) in enumerate(zip(a, b)):
             assert torch.equal(u, v), (t, i)
     assert abs(1 - res[True][-1][2].float().mean().item() - 0.6) < 1e-3
+
+
+@pytest.mark.parametrize("running_average", [True, False])
+def test_structured_callback_fused_step_equals_unfused(running_average):
+    """MagnitudePruningCallback with a channel mask: the 3-launch route (partials, one parameter kernel, apply)
+    equals the 9-launch route — magnitudes, masks, outputs, gradients — incl. steps without a mask refresh."""
+    import importlib
+    sp = importlib.import_module("qsparse_b200.sparse")
+    res = {}
+    for fuse in (True, False):
+        sp.FUSE_PRUNE_STEP = fuse
+        try:
+            g = torch.Generator(device="cuda").manual_seed(5)
+            cb = sp.MagnitudePruningCallback(running_average=running_average, mask_refresh_interval=2)
+            cb.train()
+            mask = torch.nn.Parameter(torch.ones(1, 48, 1, 1, dtype=torch.bool, device="cuda"), requires_grad=False)
+            scale = torch.linspace(0.2, 2.0, 48, device="cuda").view(1, 48, 1, 1)
+            rec = []
+            for t in range(6):
+                x = (torch.randn(6, 48, 9, 11, device="cuda", generator=g) * scale * (1 + 0.3 * t)).requires_grad_(True)
+                y = cb(x, 0.5, mask)
+                y.sum().backward()
+                item = [y.detach().clone(), x.grad.clone(), mask.data.clone()]
+                if running_average:
+                    item.append(cb.magnitude.data.clone())
+                rec.append(item)
+            res[fuse] = rec
+        finally:
+            sp.FUSE_PRUNE_STEP = True
+    for t, (a, b) in enumerate(zip(res[True], res[False])):
+        for i, (u, v) in enumerate(zip(a, b)):
+            assert torch.equal(u, v), (t, i)
+    assert res[True][-1][2].sum().item() == 24
