@@ -143,6 +143,19 @@ def main():
             report("prune_callback_structured_step", 12 * n, lambda: cb(x, 0.75, pmask),
                    route="3 launches (partials, parameter kernel, apply)" if fuse else "9 launches")
     sp.FUSE_PRUNE_STEP = True
+    # config 2 (ii): QuantizeLayer(bits=8, channelwise=-1, DecimalQuantizer) training forward, 12 B/elem
+    import qsparse_b200 as q
+    qz = importlib.import_module("qsparse_b200.quantize")
+    for fuse in (True, False):
+        qz.FUSE_ROW_QUANTIZE = fuse
+        ql = q.quantize(bits=8, channelwise=-1, timeout=1, callback=q.DecimalQuantizer())
+        ql.train()
+        with torch.no_grad():
+            ql(x)
+            ql(x)
+            report("quantize_layer_tensor_step", 12 * n, lambda: ql(x),
+                   route="3 launches (partials, parameter kernel, quantize)" if fuse else "5 launches")
+    qz.FUSE_ROW_QUANTIZE = True
     del emask
     # ---------------- config 3: [4096, 4096] channelwise=0
     w = torch.randn(4096, 4096, device=dev) * 0.02

@@ -265,10 +265,27 @@ __global__ void __launch_bounds__(1024)
         }
       }
     }
-    for (int o = group >> 1; o > 0; o >>= 1) {
+    for (int o = (group < 32 ? group : 32) >> 1; o > 0; o >>= 1) {
       sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const uint32_t other = __shfl_xor_sync(0xffffffffu, mx, o);
       mx = other > mx ? other : mx;
+    }
+    if (group > 32) {
+      // one channel, the whole CTA (per-tensor statistics: thousands of partials for ONE value):
+      // combine the warps of the group through shared memory, in warp order
+      __shared__ double s_psum[32];
+      __shared__ uint32_t s_pmax[32];
+      if (lane == 0) {
+        s_psum[warp] = sum;
+        s_pmax[warp] = mx;
+      }
+      __syncthreads();
+      if (gl == 0)
+        for (int w = 1; w < group / 32; ++w) {
+          sum += s_psum[warp + w];
+          mx = s_pmax[warp + w] > mx ? s_pmax[warp + w] : mx;
+        }
+      __syncthreads();
     }
     if (act && gl == 0) {
       s_sum[c] = sum;
@@ -529,6 +546,7 @@ extern "C" int qsb_prune_quant_step_params(
   if (pl.fin_count > 0x7fffffffLL || pl.fin_q > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
   int tpc = 32;  // threads per channel: largest power of two <= min(32, 1024 / channels)
   while (tpc > 1 && (int64_t)tpc * channels > 1024) tpc >>= 1;
+  if (channels == 1) tpc = 1024;  // per-tensor statistics: the whole CTA finalizes the one channel
   QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, magnitude, mask,
                         scale, decimal_out, P, (int)pl.fin_count, (int)pl.fin_q, (int)channels, tpc, px,
                         (unsigned long long)step_stamp, count, t_prune, update_magnitude, refresh_mask, k,

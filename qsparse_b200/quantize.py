@@ -223,6 +223,45 @@ class _RowFusedSte(torch.autograd.Function):
         return (_ste_backward(ctx, grad_output),) + (None,) * 4
 
 
+class _TensorFusedSte(torch.autograd.Function):
+    """Per-tensor Decimal / Scaler layer step in three launches instead of five: reduction partials ->
+    ONE parameter kernel (finalize abs-max, scale EMA into ``weight``, decimal) -> fake-quantize; the
+    backward is the ordinary STE kernel.  Same results as ``optimize`` + ``forward``
+    (ref quantize.py:327-349, :24-131)."""
+
+    @staticmethod
+    def forward(ctx, input, quantizer, bits, weight, xs):
+        is_decimal = not quantizer.use_float_scaler
+        n = xs.numel()
+        layout = (1, 1, n)
+        dev = xs.device
+        decimal = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = ops.reduce_partials(xs, layout)
+        ops.prune_quant_step_params(torch.zeros(1, device=dev), torch.ones(1, dtype=torch.bool, device=dev),
+                                    weight.data.view(-1), decimal, ws, layout, float(n), 0, 0, False, 0, bits,
+                                    quantizer.t, True)
+        quantizer.t += 1
+        if is_decimal:
+            y = ops.fq_pow2_fwd(xs, decimal, layout)
+        else:
+            y = ops.fq_scaler_fwd(xs, weight.data.view(-1), layout)
+        ctx.backward_passthrough = quantizer.backward_passthrough
+        ctx.notch = 1 if quantizer.flip_axis else 0
+        ctx.bits = bits
+        ctx.is_decimal = is_decimal
+        ctx.channelwise = False
+        ctx.channel_index = -1
+        ctx.param_is_tensor = True
+        ctx.param_host = None
+        ctx.save_for_backward(decimal if is_decimal else weight.data.view(-1))
+        # a [1, 1] parameter broadcasts a lower-rank input's result, like the unfused functions
+        return _broadcast_result(y.view(input.shape), input.shape, weight)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return (_ste_backward(ctx, grad_output),) + (None,) * 4
+
+
 class _RowFusedLine(torch.autograd.Function):
     """K8 for the asymmetric quantizer: per-row min / max -> lines EMA (in place) -> line fake-quantize in
     ONE launch; identity backward (ref quantize.py:393-430, :134-185)."""
@@ -339,8 +378,17 @@ class DecimalQuantizer(BaseQuantizer):
 
     def optimize_and_forward(self, x, bits, weight, channel_index=-1, **kwargs):
         """optimize() followed by forward() as one kernel when the tensor allows it (K8); None otherwise."""
-        xs = _row_fusable(self, ScalerQuantizer if self.use_float_scaler else DecimalQuantizer, x, weight,
-                          channel_index)
+        exact = ScalerQuantizer if self.use_float_scaler else DecimalQuantizer
+        if channel_index < 0:
+            # per tensor: partials -> one parameter kernel -> quantize
+            if type(self) is not exact or self.group_num > 0 or not isinstance(weight, nn.Parameter):
+                return None
+            if not (isinstance(x, torch.Tensor) and x.is_cuda and x.numel() >= 4096 and x.is_contiguous()):
+                return None
+            if tuple(weight.shape) != (1, 1):
+                return None
+            return _TensorFusedSte.apply(x, self, bits, weight, N.as_f32_contiguous(x.detach()))
+        xs = _row_fusable(self, exact, x, weight, channel_index)
         if xs is None:
             return None
         return _RowFusedSte.apply(x, self, bits, weight, xs)
@@ -486,10 +534,13 @@ class QuantizeLayer(nn.Module):
                 if t == self.timeout:
                     logging.warn(f"quantizing {self.name} with {self.bits} bits")
                 fused = None
-                if self.channelwise == 0 and self.batch_dimension != 0 and FUSE_ROW_QUANTIZE:
-                    # weights quantized along their leading axis: estimate + quantize in one launch (K8)
+                if FUSE_ROW_QUANTIZE and ((self.channelwise == 0 and self.batch_dimension != 0)
+                                          or self.channelwise < 0):
+                    # weights quantized along their leading axis: estimate + quantize in one launch (K8);
+                    # per-tensor layers: partials -> one parameter kernel -> quantize
                     fuse = getattr(self.callback, "optimize_and_forward", None)
-                    fused = fuse(x, self.bits, self.weight, channel_index=0) if fuse is not None else None
+                    fused = fuse(x, self.bits, self.weight, channel_index=self.channelwise) \
+                        if fuse is not None else None
                 if fused is None:
                     new_weight = self.callback.optimize(x, self.bits, self.weight,
                                                         batched=self.batch_dimension == 0,

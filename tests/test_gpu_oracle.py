@@ -748,3 +748,35 @@ def test_prune_step_fused_equals_separate_kernels(kind):
             assert (ta == tb).item() or (torch.isnan(ta) and torch.isnan(tb)).item(), (kind, step, i, ta, tb)
             assert torch.equal(masks_a[i], masks_b[i]), (kind, step, i, "mask")
             assert torch.equal(outs_a[i].view(torch.int32), outs_b[i].view(torch.int32)), (kind, step, i, "out")
+
+
+@pytest.mark.parametrize("cb_name", ["DecimalQuantizer", "ScalerQuantizer"])
+def test_per_tensor_layer_fused_equals_unfused(cb_name):
+    """QuantizeLayer(channelwise=-1): the 3-launch step (partials, one parameter kernel, quantize) gives the same
+    outputs, scale, counters and input gradients as reduce -> EMA -> [decimal] -> quantize (5 launches)."""
+    import importlib
+    import qsparse_b200 as q
+    qz = importlib.import_module("qsparse_b200.quantize")
+    outs = {}
+    for fuse in (True, False):
+        qz.FUSE_ROW_QUANTIZE = fuse
+        try:
+            layer = q.quantize(bits=8, channelwise=-1, timeout=2, callback=getattr(qz, cb_name)())
+            layer.train()
+            rec = []
+            for step in range(6):
+                g = torch.Generator("cuda").manual_seed(step)
+                x = (torch.randn(16, 24, 20, 20, device="cuda", generator=g) * (0.3 + 0.2 * step)).requires_grad_(True)
+                y = layer(x)
+                (y * torch.randn(y.shape, device="cuda", generator=g) * 40).sum().backward()
+                rec.append((y.detach().clone(), x.grad.clone()))
+            sd = {k: v.detach().clone() for k, v in layer.state_dict().items()}
+            outs[fuse] = (rec, sd, layer.callback.t)
+        finally:
+            qz.FUSE_ROW_QUANTIZE = True
+    (ra, sa, ta), (rb, sb, tb) = outs[True], outs[False]
+    assert ta == tb and sa.keys() == sb.keys()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    for i, ((ya, ga), (yb, gb)) in enumerate(zip(ra, rb)):
+        assert torch.equal(ya, yb) and torch.equal(ga, gb), i
