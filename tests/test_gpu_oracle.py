@@ -780,3 +780,24 @@ def test_per_tensor_layer_fused_equals_unfused(cb_name):
         assert torch.equal(sa[k], sb[k]), k
     for i, ((ya, ga), (yb, gb)) in enumerate(zip(ra, rb)):
         assert torch.equal(ya, yb) and torch.equal(ga, gb), i
+
+
+def test_prune_step_fused_many_small_tensors_and_repeat():
+    """more tensors than one launch sequence holds (all on the generic route: too small to sample), plus the
+    same call repeated on the same workspace (no stale state between calls)."""
+    from qsparse_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(77)
+    sizes = [1000 + 257 * i for i in range(40)] + [200_000]
+    xs = [torch.randn(s, device="cuda", generator=g) for s in sizes]
+    mags_a = [torch.zeros(s, device="cuda") for s in sizes]
+    mags_b = [torch.zeros(s, device="cuda") for s in sizes]
+    masks_a = [torch.ones(s, dtype=torch.bool, device="cuda") for s in sizes]
+    outs_a = [torch.empty(s, device="cuda") for s in sizes]
+    for step in range(3):
+        ks = [s // 2 for s in sizes]
+        thr_a = ops.prune_unstructured_step_batched_(mags_a, xs, masks_a, outs_a, ks, step)
+        thr_b, masks_b, outs_b = _step_reference(mags_b, xs, ks, step)
+        assert torch.equal(thr_a, thr_b), step
+        for i in range(len(sizes)):
+            assert torch.equal(mags_a[i], mags_b[i]) and torch.equal(masks_a[i], masks_b[i]), (step, i)
+            assert torch.equal(outs_a[i].view(torch.int32), outs_b[i].view(torch.int32)), (step, i)
