@@ -64,7 +64,7 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *          (default), 0 = always the 3-pass radix select;
  *   key 6: 256-bit loads in flight per thread in the select's partition pass
  *          (2, 4 = default);
- *   key 7: samples per sampler thread of the select (1, 2 = default, 4 ->
+ *   key 7: samples per sampler thread of the select (1, 2, 4 = default ->
  *          8 Ki, 16 Ki, 32 Ki samples; 4 reads four neighbours per location);
  *   key 8: 1 = the kernels of one select are chained by programmatic dependent
  *          launch (default), 0 = ordinary stream order;

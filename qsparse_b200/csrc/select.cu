@@ -584,6 +584,7 @@ __device__ __forceinline__ void select_sample_body(const float *__restrict__ v, 
 #ifdef QSB_SELECT_TIMING
   const long long t_start = clock64();
 #endif
+  pdl_wait();     // v may come from the kernel launched just before (e.g. the magnitude EMA)
   pdl_trigger();  // the partition kernel may start loading v on the other SMs right away
   float f[PER];
   if constexpr (PER == 4) {
@@ -1045,6 +1046,7 @@ __global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThr
   uint4 *zb = reinterpret_cast<uint4 *>(d.hdr);
   constexpr int zv = (int)(kSelectHeaderBytes / 16);
   if (!d.fast) {  // generic passes only: this launch just zeroes the segment's header
+    pdl_wait();   // ... which the previous select on this workspace may still be reading
     for (int j = blockIdx.x * kSampleThreads + threadIdx.x; j < zv; j += kSampleThreads * kSampleCtas)
       zb[j] = make_uint4(0, 0, 0, 0);
     return;
@@ -1108,13 +1110,13 @@ __global__ void __launch_bounds__(QSB_THREADS)
 static int g_select_fast = 1;  // tuning key 4
 static int g_select_pdl = 1;   // tuning key 8: programmatic dependent launch inside a select
 static int g_partition_u = 4;  // tuning key 6: 256-bit loads in flight per thread (2 or 4)
-static int g_sample_per = 2;   // tuning key 7: samples per sampler thread (1, 2, 4 -> 8K, 16K, 32K samples)
+static int g_sample_per = 4;   // tuning key 7: samples per sampler thread (1, 2, 4 -> 8K, 16K, 32K samples)
 constexpr int64_t kFastMinNBatched = 1 << 17;  // segments of a batch share the launches' fixed costs
 
 void set_select_fast(int v) { g_select_fast = v; }
 void set_select_pdl(int v) { g_select_pdl = v != 0; }
 void set_select_partition_u(int v) { g_partition_u = (v == 2) ? 2 : 4; }
-void set_select_sample_per(int v) { g_sample_per = (v == 1 || v == 4) ? v : 2; }
+void set_select_sample_per(int v) { g_sample_per = (v == 1 || v == 2) ? v : 4; }
 
 // slots per candidate segment: n/8 in total, a multiple of 8 per segment, < 2^32
 static int64_t seg_slots(int64_t n) {
@@ -1187,13 +1189,16 @@ static int run_group(SegDesc *descs, int L, bool v8, bool first_after_kernel, bo
     // pivots for the fast segments; zeroes every segment's header (no memset node)
     const dim3 sg(kSampleCtas, (unsigned)L);
     const int per = sample_per(batched, STEP);
+    // (PDL: the sampler starts with griddepcontrol.wait, so it is ordered after whatever precedes it
+    // in the stream, but its launch latency overlaps that kernel's tail)
+    const int abs_i = ABS ? 1 : 0;
     if (per == 1)
-      select_sample_kernel<1, STEP><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0, ec);
+      rc = launch_seg(select_sample_kernel<1, STEP>, sg, dim3(kSampleThreads), stream, true, tab, abs_i, ec);
     else if (per == 4)
-      select_sample_kernel<4, STEP><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0, ec);
+      rc = launch_seg(select_sample_kernel<4, STEP>, sg, dim3(kSampleThreads), stream, true, tab, abs_i, ec);
     else
-      select_sample_kernel<2, STEP><<<sg, kSampleThreads, 0, stream>>>(tab, ABS ? 1 : 0, ec);
-    QSB_LAUNCH_CHECK();
+      rc = launch_seg(select_sample_kernel<2, STEP>, sg, dim3(kSampleThreads), stream, true, tab, abs_i, ec);
+    if (rc) return rc;
   }
   if constexpr (STEP) {
     // EMA for every segment, partition + provisional outputs for the fast ones: one streaming pass
