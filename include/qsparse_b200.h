@@ -75,7 +75,9 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *          programmatic stream serialization (each begins with griddepcontrol.wait, so
  *          stream order is unchanged; launch latency overlaps the predecessor's tail);
  *   key 13 / 14: fused prune step: samples per sampler thread (1, 2, 4 = default) / distance
- *          of the pivots from the estimated rank in tenths of a sigma (default 35). */
+ *          of the pivots from the estimated rank in tenths of a sigma (default 35);
+ *   key 15: per-channel kernels on channel-last layouts (inner == 1, channels % 8 == 0):
+ *          1 = a thread keeps one group of 8 channels in registers (default), 0 = table walk. */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and

@@ -25,7 +25,7 @@ void set_step_sigma10(int v);
 namespace qsb {
 
 MapTuning &map_tuning() {
-  static MapTuning t{0, 0, 1};
+  static MapTuning t{0, 0, 1, 1};
   return t;
 }
 
@@ -502,6 +502,10 @@ extern "C" int qsb_set_tuning(int key, int value) {
   }
   if (key == 12) {
     set_pdl_enabled(value);
+    return 0;
+  }
+  if (key == 15) {
+    map_tuning().lastdim = value;
     return 0;
   }
   if (key == 13) {

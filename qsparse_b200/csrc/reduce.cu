@@ -164,36 +164,83 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
 }
 
 // ---------------------------------------------------------------------------
-// stage 1, column mode.  partial index = chunk * ncols + col
+// stage 1, column mode.  partial index = chunk * ncols + col.
+// A CTA owns a band of rows (blockIdx.y) and `tpr` column-vectors of it (blockIdx.x); when
+// the tensor has fewer than 256 column-vectors ([N, 64] activations: 16 of them) the CTA's
+// 256 / tpr "row lanes" walk interleaved rows of the band, so every thread is busy and a
+// warp still reads consecutive memory; the row lanes are then combined through shared
+// memory in lane order (deterministic) and row lane 0 writes the partial.
 // ---------------------------------------------------------------------------
 template <int WHAT, int V>
 __global__ void __launch_bounds__(QSB_THREADS)
     reduce_cols_kernel(const float *__restrict__ x, int64_t nrows, int64_t ncols,
-                       int64_t rows_per_chunk, Partials P) {
+                       int64_t rows_per_chunk, int tpr, Partials P) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t vcols = ncols / V;  // V == 4 requires ncols % 4 == 0
-  const int64_t vc = (int64_t)blockIdx.x * QSB_THREADS + threadIdx.x;
-  if (vc >= vcols) return;
+  const int rpb = QSB_THREADS / tpr;  // row lanes
+  const int cl = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const int64_t vc = (int64_t)blockIdx.x * tpr + cl;
+  const bool live = vc < vcols;
   const int64_t chunk = blockIdx.y;
   const int64_t r0 = chunk * rows_per_chunk;
   const int64_t r1 = (r0 + rows_per_chunk < nrows) ? r0 + rows_per_chunk : nrows;
   Acc<WHAT> acc[V];
-  const float *p = x + vc * V;
-  int64_t r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    VecF<V> v[4];
+  if (live) {
+    const float *p = x + vc * V;
+    int64_t r = r0 + rl;
+    for (; r + 3 * (int64_t)rpb < r1; r += 4 * (int64_t)rpb) {
+      VecF<V> v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = ld_vec<V, Hint::KEEP>(p + (r + k) * ncols);
+      for (int k = 0; k < 4; ++k) v[k] = ld_vec<V, Hint::KEEP>(p + (r + (int64_t)k * rpb) * ncols);
 #pragma unroll
-    for (int q = 0; q < V; ++q) {
-      const float col4[4] = {v[0].v[q], v[1].v[q], v[2].v[q], v[3].v[q]};
-      acc[q].template add_n<4>(col4);
+      for (int q = 0; q < V; ++q) {
+        const float col4[4] = {v[0].v[q], v[1].v[q], v[2].v[q], v[3].v[q]};
+        acc[q].template add_n<4>(col4);
+      }
+    }
+    for (; r < r1; r += rpb) {
+      VecF<V> v = ld_vec<V, Hint::KEEP>(p + r * ncols);
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q].add(v.v[q]);
     }
   }
-  for (; r < r1; ++r) {
-    VecF<V> v = ld_vec<V, Hint::KEEP>(p + r * ncols);
+  if (rpb > 1) {
+    // combine the row lanes: [field][q][thread] in shared memory, summed by row lane 0 in order
+    __shared__ uint32_t s_amax[V][QSB_THREADS];
+    __shared__ float s_mn[V][QSB_THREADS], s_mx[V][QSB_THREADS];
+    __shared__ double s_asum[V][QSB_THREADS];
+    __shared__ uint32_t s_nnz[V][QSB_THREADS];
+    __shared__ uint8_t s_nan[V][QSB_THREADS];
 #pragma unroll
-    for (int q = 0; q < V; ++q) acc[q].add(v.v[q]);
+    for (int q = 0; q < V; ++q) {
+      if constexpr (WHAT & QSB_STAT_ABSMAX) s_amax[q][threadIdx.x] = acc[q].amax;
+      if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+        s_mn[q][threadIdx.x] = acc[q].mn;
+        s_nan[q][threadIdx.x] = acc[q].nan ? 1 : 0;
+      }
+      if constexpr (WHAT & QSB_STAT_MINMAX) s_mx[q][threadIdx.x] = acc[q].mx;
+      if constexpr (WHAT & QSB_STAT_ABSSUM) s_asum[q][threadIdx.x] = acc[q].asum;
+      if constexpr (WHAT & QSB_STAT_NNZ) s_nnz[q][threadIdx.x] = acc[q].nnz;
+    }
+    __syncthreads();
+    if (rl != 0) return;
+    for (int l = 1; l < rpb; ++l) {
+      const int t = l * tpr + cl;
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if constexpr (WHAT & QSB_STAT_ABSMAX) acc[q].amax = s_amax[q][t] > acc[q].amax ? s_amax[q][t] : acc[q].amax;
+        if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+          acc[q].mn = fminf(acc[q].mn, s_mn[q][t]);
+          acc[q].nan |= s_nan[q][t] != 0;
+        }
+        if constexpr (WHAT & QSB_STAT_MINMAX) acc[q].mx = fmaxf(acc[q].mx, s_mx[q][t]);
+        if constexpr (WHAT & QSB_STAT_ABSSUM) acc[q].asum += s_asum[q][t];
+        if constexpr (WHAT & QSB_STAT_NNZ) acc[q].nnz += s_nnz[q][t];
+      }
+    }
   }
+  if (!live) return;
 #pragma unroll
   for (int q = 0; q < V; ++q) {
     const int64_t idx = chunk * ncols + vc * V + q;
@@ -411,7 +458,13 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
     p.ncols = channels * inner;
     p.vcol = (p.ncols % 4 == 0 && (x == nullptr || aligned_to(x, 16))) ? 4 : 1;
     const int64_t threads = p.ncols / p.vcol;
-    int64_t chunks = (target + threads - 1) / (threads > 0 ? threads : 1);
+    // threads of one row that a CTA covers: a power of two <= 256; the other 256 / tpr "row lanes"
+    // of the CTA walk interleaved rows of the chunk
+    int64_t tpr = 1;
+    while (tpr < threads && tpr < QSB_THREADS) tpr <<= 1;
+    p.tpr = (int)tpr;
+    const int64_t ctas_x = (threads + tpr - 1) / tpr;
+    int64_t chunks = (target / QSB_THREADS + ctas_x - 1) / ctas_x;
     // at least 8 rows per chunk so the partial array stays small
     const int64_t max_chunks = (outer + 7) / 8;
     if (chunks > max_chunks) chunks = max_chunks;
@@ -458,14 +511,13 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
                           pl.rows, inner, pl.seg, pl.segs_per_row, pl.vwarps, P));
   } else {
     const int64_t threads = pl.ncols / pl.vcol;
-    dim3 grid((unsigned)((threads + QSB_THREADS - 1) / QSB_THREADS),
-              (unsigned)pl.chunks);
+    dim3 grid((unsigned)((threads + pl.tpr - 1) / pl.tpr), (unsigned)pl.chunks);
     if (pl.vcol == 4)
-      reduce_cols_kernel<WHAT, 4><<<grid, QSB_THREADS, 0, stream>>>(
-          x, pl.nrows, pl.ncols, pl.rows_per_chunk, P);
+      QSB_CUDA_TRY(launch_k(reduce_cols_kernel<WHAT, 4>, grid, dim3(QSB_THREADS), 0, stream, x, pl.nrows,
+                            pl.ncols, pl.rows_per_chunk, pl.tpr, P));
     else
-      reduce_cols_kernel<WHAT, 1><<<grid, QSB_THREADS, 0, stream>>>(
-          x, pl.nrows, pl.ncols, pl.rows_per_chunk, P);
+      QSB_CUDA_TRY(launch_k(reduce_cols_kernel<WHAT, 1>, grid, dim3(QSB_THREADS), 0, stream, x, pl.nrows,
+                            pl.ncols, pl.rows_per_chunk, pl.tpr, P));
   }
   QSB_LAUNCH_CHECK();
   if (!finalize) return 0;

@@ -18,6 +18,7 @@ struct ReducePlan {
   int64_t rows, seg, segs_per_row, vwarps;       // row mode
   int64_t nrows, ncols, chunks, rows_per_chunk;  // column mode
   int vcol;
+  int tpr;  // column mode: threads of a CTA along a row (the CTA's other 256 / tpr row lanes interleave rows)
   // channel c combines entries j = 0..fin_count-1 at
   //   idx(j) = (j / fin_q) * (channels * fin_q) + c * fin_q + (j % fin_q)
   int64_t n_partials, fin_count, fin_q;

@@ -37,6 +37,10 @@ SHAPES = [
     ((5, 3, 33), 2),        # channel = last axis
     ((2, 3, 1000), 1),      # inner 1000
     ((1, 2, 70001), 1),     # long rows, odd length
+    ((64, 128), 1),         # channel-last, C % 8 == 0: group-resident kernel, row-lane column reduce
+    ((33, 4096), 1),        # channel-last, more groups than one CTA covers
+    ((1000, 8), 1),         # channel-last, one group
+    ((5, 7, 24), 2),        # channel = last axis of a 3-D tensor
 ]
 
 
