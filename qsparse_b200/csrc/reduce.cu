@@ -128,6 +128,51 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
   for (int64_t vw = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
        vw < vwarps; vw += warps_phys) {
     Acc<WHAT> acc;
+    if (seg <= 256) {
+      // short rows (7x7 .. 16x16 feature maps): one item is a single vector per lane, i.e. one DRAM
+      // round trip for < 1 KB per warp.  Keep FOUR items in flight; the accumulation order (item by
+      // item, head -> body -> tail) is the one of the loop below, so the results are identical.
+      for (int64_t item0 = vw; item0 < items; item0 += 4 * vwarps) {
+        float hv[4], tv[4];
+        VecF<8> bv[4];
+        int head[4], nv[4];
+        bool ok[4], has_tail[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t item = item0 + (int64_t)k * vwarps;
+          ok[k] = item < items;
+          head[k] = nv[k] = 0;
+          has_tail[k] = false;
+          if (ok[k]) {
+            const int64_t row = item / segs_per_row;
+            const int64_t s = item - row * segs_per_row;
+            const int64_t c0 = s * seg;
+            const int64_t c1 = (c0 + seg < inner) ? c0 + seg : inner;
+            const float *p = x + row * inner + c0;
+            const int len = (int)(c1 - c0);
+            int h = (int)(((32 - (reinterpret_cast<uintptr_t>(p) & 31)) & 31) >> 2);
+            if (h > len) h = len;
+            head[k] = h;
+            nv[k] = (len - h) >> 3;
+            if (lane < h) hv[k] = p[lane];
+            if (lane < nv[k]) bv[k] = ld_vec<8, Hint::KEEP>(p + h + (lane << 3));
+            const int done = h + (nv[k] << 3);
+            has_tail[k] = done + lane < len;
+            if (has_tail[k]) tv[k] = p[done + lane];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (ok[k]) {
+            if (lane < head[k]) acc.add(hv[k]);
+            if (lane < nv[k]) acc.template add_n<8>(bv[k].v);
+            if (has_tail[k]) acc.add(tv[k]);
+          }
+        }
+      }
+      warp_store<WHAT>(acc, lane, P, vw);
+      continue;
+    }
     for (int64_t item = vw; item < items; item += vwarps) {
       const int64_t row = item / segs_per_row;
       const int64_t s = item - row * segs_per_row;

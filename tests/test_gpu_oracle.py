@@ -41,6 +41,10 @@ SHAPES = [
     ((33, 4096), 1),        # channel-last, more groups than one CTA covers
     ((1000, 8), 1),         # channel-last, one group
     ((5, 7, 24), 2),        # channel = last axis of a 3-D tensor
+    ((64, 96, 7, 7), 1),    # 7x7 maps at scale: straddling vectors on the fast path, 4 short rows in flight
+    ((8, 64, 14, 14), 1),   # inner 196
+    ((6, 5, 16, 16), 1),    # inner 256: the short-row boundary
+    ((3, 5, 257), 1),       # inner 257: just past it
 ]
 
 
