@@ -76,7 +76,9 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         for _, _, log in results:
             if log:
                 print(log)
-    if rebuilt or not LIB_PATH.exists() or force:
+    # relink also when an earlier run compiled objects but died before linking (e.g. a closed pipe)
+    stale = LIB_PATH.exists() and any(r[0].stat().st_mtime > LIB_PATH.stat().st_mtime for r in results)
+    if rebuilt or stale or not LIB_PATH.exists() or force:
         cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *[str(r[0]) for r in results],
                "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -11,10 +11,14 @@
 //                partial at the end (W partials in total instead of one per item).
 //                256-bit loads, 4 in flight per lane, scalar head/tail peel for
 //                pieces that do not start on a 32-byte boundary;
+//   tile mode   (64 <= inner <= 256, short rows): same partial layout as row mode, but a
+//                CTA stages 32 consecutive rows per visit in shared memory with aligned,
+//                coalesced loads and a warp reduces a row from there (reduce_tile_kernel);
 //   column mode (inner  < 64): the tensor is [outer, channels*inner]; one
 //                thread per column (or 4 columns) walks a chunk of rows, so a
 //                warp still reads contiguous 128/512-byte lines.
-// Stage 2 (finalize) combines the partials of each channel in a fixed order.
+// Stage 2 (finalize) combines the partials of each channel in a fixed order (a transposed
+// variant when the entries of one channel are `channels` apart).
 //
 // sum|x|: the 8 values of one 256-bit vector are first added pairwise in fp32
 // (3 levels, |x| >= 0 so there is no cancellation), the vector sum is then
@@ -128,51 +132,6 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
   for (int64_t vw = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
        vw < vwarps; vw += warps_phys) {
     Acc<WHAT> acc;
-    if (seg <= 256) {
-      // short rows (7x7 .. 16x16 feature maps): one item is a single vector per lane, i.e. one DRAM
-      // round trip for < 1 KB per warp.  Keep FOUR items in flight; the accumulation order (item by
-      // item, head -> body -> tail) is the one of the loop below, so the results are identical.
-      for (int64_t item0 = vw; item0 < items; item0 += 4 * vwarps) {
-        float hv[4], tv[4];
-        VecF<8> bv[4];
-        int head[4], nv[4];
-        bool ok[4], has_tail[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int64_t item = item0 + (int64_t)k * vwarps;
-          ok[k] = item < items;
-          head[k] = nv[k] = 0;
-          has_tail[k] = false;
-          if (ok[k]) {
-            const int64_t row = item / segs_per_row;
-            const int64_t s = item - row * segs_per_row;
-            const int64_t c0 = s * seg;
-            const int64_t c1 = (c0 + seg < inner) ? c0 + seg : inner;
-            const float *p = x + row * inner + c0;
-            const int len = (int)(c1 - c0);
-            int h = (int)(((32 - (reinterpret_cast<uintptr_t>(p) & 31)) & 31) >> 2);
-            if (h > len) h = len;
-            head[k] = h;
-            nv[k] = (len - h) >> 3;
-            if (lane < h) hv[k] = p[lane];
-            if (lane < nv[k]) bv[k] = ld_vec<8, Hint::KEEP>(p + h + (lane << 3));
-            const int done = h + (nv[k] << 3);
-            has_tail[k] = done + lane < len;
-            if (has_tail[k]) tv[k] = p[done + lane];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (ok[k]) {
-            if (lane < head[k]) acc.add(hv[k]);
-            if (lane < nv[k]) acc.template add_n<8>(bv[k].v);
-            if (has_tail[k]) acc.add(tv[k]);
-          }
-        }
-      }
-      warp_store<WHAT>(acc, lane, P, vw);
-      continue;
-    }
     for (int64_t item = vw; item < items; item += vwarps) {
       const int64_t row = item / segs_per_row;
       const int64_t s = item - row * segs_per_row;
@@ -206,6 +165,118 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
     }
     warp_store<WHAT>(acc, lane, P, vw);
   }
+}
+
+// ---------------------------------------------------------------------------
+// stage 1, short rows (kTileMinInner <= inner <= kTileMaxInner: 8x8 .. 16x16 feature maps).
+// A warp per row is one sub-KB request per DRAM round trip with rows that start mid-sector
+// (measured 0.21 of the copy peak on [256, 256, 14, 14]).  Here a CTA owns `tile_rows`
+// consecutive virtual warps ("slots"), i.e. tile_rows consecutive ROWS of every tile it visits
+// — one contiguous span of memory: it is read with aligned, fully coalesced 256-bit loads into
+// shared memory (the next tile's loads are already in flight in registers), then warp w reduces
+// rows w, w + 8, ... from shared memory, lane-strided, into one accumulator per slot.  The
+// partial layout (one entry per virtual warp, slot % channels == channel) is the row kernel's.
+// ---------------------------------------------------------------------------
+constexpr int kTileMinInner = 64;  // below: column mode (a warp per 7x7 row wastes lanes and issue slots: measured 2-3x slower)
+constexpr int kTileMaxInner = 256;
+constexpr int kTileFloats = 8192;  // 32 KB of shared memory; 4 vectors per thread
+constexpr int kTileRowsMax = 32;   // 4 slots per warp
+constexpr int kTileVpt = kTileFloats / 8 / QSB_THREADS;
+
+template <int WHAT>
+__global__ void __launch_bounds__(QSB_THREADS, 4)
+    reduce_tile_kernel(const float *__restrict__ x, int64_t rows, int inner, int tile_rows, int spans,
+                       int span_stride, int64_t vwarps, Partials P) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ __align__(32) float tile[kTileFloats];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t slot0 = (int64_t)blockIdx.x * tile_rows;
+  const int nslots = (int)((vwarps - slot0 < tile_rows) ? vwarps - slot0 : tile_rows);
+  const int vps = span_stride >> 3;  // vectors per span
+  Acc<WHAT> acc[kTileRowsMax / 8];
+  VecF<8> r[kTileVpt];
+  unsigned have_next = 0;  // which r[i] hold data of the visit being fetched
+
+  // rows [base + g * vwarps, +nslots) for g < spans: `spans` contiguous pieces of memory, each
+  // copied to tile[g * span_stride ...] keeping its position inside a 32-byte sector
+  auto fetch = [&](int64_t base) {
+    have_next = 0;
+#pragma unroll
+    for (int i = 0; i < kTileVpt; ++i) {
+      const int v = threadIdx.x + i * QSB_THREADS;
+      const int g = v / vps, vi = v - g * vps;
+      if (g >= spans) continue;
+      const int64_t base_g = base + (int64_t)g * vwarps;
+      if (base_g >= rows) continue;
+      const int nr = (int)((rows - base_g < nslots) ? rows - base_g : nslots);
+      const float *S = x + base_g * inner;
+      const int a = (int)((reinterpret_cast<uintptr_t>(S) >> 2) & 7);
+      const float *A = S - a;  // 32-byte aligned
+      const int end = a + nr * inner;
+      if ((vi << 3) >= end) continue;
+      have_next |= 1u << i;
+      if ((vi > 0 || a == 0) && (vi << 3) + 8 <= end) {
+        r[i] = ld_vec<8, Hint::KEEP>(A + (vi << 3));
+      } else {  // first / last vector of a span: never touch memory outside it
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = (vi << 3) + j;
+          r[i].v[j] = (e >= a && e < end) ? A[e] : 0.f;
+        }
+      }
+    }
+  };
+
+  const int64_t visit = (int64_t)spans * vwarps;
+  fetch(slot0);
+  for (int64_t base = slot0; base < rows; base += visit) {
+    const unsigned have = have_next;
+#pragma unroll
+    for (int i = 0; i < kTileVpt; ++i) {
+      if (have & (1u << i)) {
+        float4 *d = reinterpret_cast<float4 *>(tile + ((threadIdx.x + i * QSB_THREADS) << 3));
+        d[0] = make_float4(r[i].v[0], r[i].v[1], r[i].v[2], r[i].v[3]);
+        d[1] = make_float4(r[i].v[4], r[i].v[5], r[i].v[6], r[i].v[7]);
+      }
+    }
+    __syncthreads();
+    have_next = 0;
+    if (base + visit < rows) fetch(base + visit);
+    for (int g = 0; g < spans; ++g) {
+      const int64_t base_g = base + (int64_t)g * vwarps;
+      if (base_g >= rows) break;
+      const int nr = (int)((rows - base_g < nslots) ? rows - base_g : nslots);
+      const int a = (int)((reinterpret_cast<uintptr_t>(x + base_g * inner) >> 2) & 7);
+#pragma unroll
+      for (int q = 0; q < kTileRowsMax / 8; ++q) {
+        const int rr = w + 8 * q;
+        if (rr < nr) {
+          const float *rowp = tile + g * span_stride + a + rr * inner;
+          float s = 0.f;  // <= 8 terms per lane in fp32, then fp64 (see the header note)
+          for (int j = lane; j < inner; j += 32) {
+            const float v = rowp[j];
+            if constexpr (WHAT & QSB_STAT_ABSMAX) {
+              const uint32_t b = __float_as_uint(v) & 0x7fffffffu;
+              acc[q].amax = b > acc[q].amax ? b : acc[q].amax;
+            }
+            if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+              acc[q].mn = fminf(acc[q].mn, v);
+              acc[q].nan |= (v != v);
+            }
+            if constexpr (WHAT & QSB_STAT_MINMAX) acc[q].mx = fmaxf(acc[q].mx, v);
+            if constexpr (WHAT & QSB_STAT_ABSSUM) s = __fadd_rn(s, fabsf(v));
+            if constexpr (WHAT & QSB_STAT_NNZ) acc[q].nnz += (v != 0.0f) ? 1u : 0u;
+          }
+          if constexpr (WHAT & QSB_STAT_ABSSUM) acc[q].asum += (double)s;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < kTileRowsMax / 8; ++q)
+    if (w + 8 * q < nslots) warp_store<WHAT>(acc[q], lane, P, slot0 + w + 8 * q);
 }
 
 // ---------------------------------------------------------------------------
@@ -425,6 +496,118 @@ __global__ void __launch_bounds__(QSB_THREADS)
   }
 }
 
+// stage 2 when fin_q == 1 (channel-last column mode, the tile kernel): entry j of channel c sits
+// at j * channels + c, so a warp that walks j touches 32 sectors for 32 values (the finalize took
+// 12 us behind a 16 us stage 1 on [16384, 1000]).  Here a CTA owns 8 ADJACENT channels: thread t
+// reads channel (t & 7) of entries (t >> 3), (t >> 3) + 32, ... — each 8-lane group reads whole
+// sectors — and the 32 entry lanes are combined by shuffles, then across warps in warp order.
+template <int WHAT>
+__global__ void __launch_bounds__(QSB_THREADS)
+    reduce_finalize_t_kernel(Partials P, FinalOut out, int64_t channels, int64_t count) {
+  pdl_wait();
+  pdl_trigger();
+  const int cl = threadIdx.x & 7, jl = threadIdx.x >> 3;
+  const int64_t c = (int64_t)blockIdx.x * 8 + cl;
+  const bool active = c < channels;
+  uint32_t amax = 0;
+  float mn = INFINITY, mx = -INFINITY;
+  bool nan = false;
+  double asum = 0.0, nnz = 0.0;
+  if (active) {
+    for (int64_t j0 = jl; j0 < count; j0 += 4 * 32) {
+      int64_t idx[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ok[u] = j0 + 32 * u < count;
+        idx[u] = ok[u] ? (j0 + 32 * u) * channels + c : 0;
+      }
+      if constexpr (WHAT & QSB_STAT_ABSMAX) {
+        uint32_t b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) b[u] = ok[u] ? P.amax[idx[u]] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) amax = b[u] > amax ? b[u] : amax;
+      }
+      if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.mn[idx[u]] : INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          nan |= (v[u] != v[u]);
+          mn = fminf(mn, v[u]);
+        }
+      }
+      if constexpr (WHAT & QSB_STAT_MINMAX) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.mx[idx[u]] : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          nan |= (v[u] != v[u]);
+          mx = fmaxf(mx, v[u]);
+        }
+      }
+      if constexpr (WHAT & QSB_STAT_ABSSUM) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.asum[idx[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) asum += v[u];
+      }
+      if constexpr (WHAT & QSB_STAT_NNZ) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.nnz[idx[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nnz += v[u];
+      }
+    }
+  }
+  // the 4 entry lanes of a warp that share a channel
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    const uint32_t a2 = __shfl_xor_sync(0xffffffffu, amax, o);
+    amax = a2 > amax ? a2 : amax;
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    nan = (__shfl_xor_sync(0xffffffffu, (int)nan, o) != 0) || nan;
+    asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    nnz += __shfl_xor_sync(0xffffffffu, nnz, o);
+  }
+  __shared__ uint32_t s_amax[QSB_THREADS / 32][8];
+  __shared__ float s_mn[QSB_THREADS / 32][8], s_mx[QSB_THREADS / 32][8];
+  __shared__ int s_nan[QSB_THREADS / 32][8];
+  __shared__ double s_asum[QSB_THREADS / 32][8], s_nnz[QSB_THREADS / 32][8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) < 8) {
+    s_amax[w][cl] = amax; s_mn[w][cl] = mn; s_mx[w][cl] = mx; s_nan[w][cl] = nan;
+    s_asum[w][cl] = asum; s_nnz[w][cl] = nnz;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && active) {
+    for (int k = 1; k < QSB_THREADS / 32; ++k) {
+      amax = s_amax[k][cl] > amax ? s_amax[k][cl] : amax;
+      mn = fminf(mn, s_mn[k][cl]);
+      mx = fmaxf(mx, s_mx[k][cl]);
+      nan = nan || s_nan[k][cl];
+      asum += s_asum[k][cl];
+      nnz += s_nnz[k][cl];
+    }
+    if constexpr (WHAT & QSB_STAT_ABSMAX)
+      if (out.absmax) out.absmax[c] = __uint_as_float(amax);
+    if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ))
+      if (out.mn) out.mn[c] = nan ? nan_f() : mn;
+    if constexpr (WHAT & QSB_STAT_MINMAX)
+      if (out.mx) out.mx[c] = nan ? nan_f() : mx;
+    if constexpr (WHAT & QSB_STAT_ABSSUM)
+      if (out.abssum) out.abssum[c] = asum;
+    if constexpr (WHAT & QSB_STAT_NNZ)
+      if (out.nnz) out.nnz[c] = nnz;
+  }
+}
+
 // min over the per-channel minima (l0 gate, qsparse/sparse.py:85)
 __global__ void tensor_min_kernel(const float *mn, int64_t channels, float *out) {
   float m = INFINITY;
@@ -454,7 +637,32 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
   ReducePlan p{};
   const int64_t warps_phys =
       (int64_t)device_props().sm_count * kRowCtasPerSm * (QSB_THREADS / 32);
-  if (inner >= kRowModeMinInner) {
+  if (inner >= kTileMinInner && inner <= kTileMaxInner) {
+    // short rows: the tile kernel.  One slot (virtual warp) per row of a tile, 4 CTAs of 32 slots
+    // per SM; slots = m * channels so that a slot only ever sees one channel.
+    p.row_mode = true;
+    p.rows = outer * channels;
+    p.seg = (inner + 7) / 8 * 8;
+    p.segs_per_row = 1;
+    p.tile_rows = (int)((kTileFloats - 7) / inner < kTileRowsMax ? (kTileFloats - 7) / inner : kTileRowsMax);
+    // one CTA visit covers `tile_spans` pieces of tile_rows rows (vwarps rows apart), each kept at its
+    // own offset inside a 32-byte sector: ~32 KB in flight per CTA whatever the row length
+    p.tile_span_stride = (int)((p.tile_rows * inner + 7 + 7) / 8 * 8);
+    p.tile_spans = kTileFloats / p.tile_span_stride;
+    const int64_t target = (int64_t)device_props().sm_count * kRowCtasPerSm * kTileRowsMax;
+    if (channels == 1) {
+      p.vwarps = p.rows < target ? p.rows : target;
+      p.fin_count = p.vwarps;
+    } else {
+      int64_t m = target / channels;
+      if (m > outer) m = outer;
+      if (m < 1) m = 1;
+      p.vwarps = m * channels;
+      p.fin_count = m;
+    }
+    p.fin_q = 1;
+    p.n_partials = p.vwarps;
+  } else if (inner >= kRowModeMinInner) {
     p.row_mode = true;
     p.rows = outer * channels;
     // balanced segments: aim for >= 6 work items per physical warp, but keep every
@@ -547,7 +755,11 @@ template <int WHAT>
 static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
                       int64_t inner, const Partials &P, const FinalOut &out,
                       cudaStream_t stream, bool finalize = true) {
-  if (pl.row_mode) {
+  if (pl.row_mode && pl.tile_rows > 0) {
+    const int64_t grid = (pl.vwarps + pl.tile_rows - 1) / pl.tile_rows;
+    QSB_CUDA_TRY(launch_k(reduce_tile_kernel<WHAT>, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, x,
+                          pl.rows, (int)inner, pl.tile_rows, pl.tile_spans, pl.tile_span_stride, pl.vwarps, P));
+  } else if (pl.row_mode) {
     constexpr int kWarps = QSB_THREADS / 32;
     int64_t grid = (int64_t)device_props().sm_count * kRowCtasPerSm;
     const int64_t need = (pl.vwarps + kWarps - 1) / kWarps;
@@ -567,7 +779,10 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
   QSB_LAUNCH_CHECK();
   if (!finalize) return 0;
   // few channels: a whole CTA per channel; many: a warp per channel
-  if (pl.fin_count > 1024) {
+  if (pl.fin_q == 1 && channels >= 8 && pl.fin_count >= 16 && pl.fin_count <= 1024) {
+    QSB_CUDA_TRY(launch_k(reduce_finalize_t_kernel<WHAT>, dim3((unsigned)((channels + 7) / 8)), dim3(QSB_THREADS),
+                          0, stream, P, out, channels, pl.fin_count));
+  } else if (pl.fin_count > 1024) {
     QSB_CUDA_TRY(launch_k(reduce_finalize_kernel<WHAT, QSB_THREADS>, dim3((unsigned)channels),
                           dim3(QSB_THREADS), 0, stream, P, out, channels, pl.fin_count, pl.fin_q));
   } else {

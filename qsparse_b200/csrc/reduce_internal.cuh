@@ -16,6 +16,8 @@ struct Partials {
 struct ReducePlan {
   bool row_mode;
   int64_t rows, seg, segs_per_row, vwarps;       // row mode
+  int tile_spans, tile_span_stride;  // tile kernel: pieces per CTA visit, floats between them in shared memory
+  int tile_rows;  // > 0: short rows, the tile kernel (tile_rows consecutive rows per CTA visit)
   int64_t nrows, ncols, chunks, rows_per_chunk;  // column mode
   int vcol;
   int tpr;  // column mode: threads of a CTA along a row (the CTA's other 256 / tpr row lanes interleave rows)

@@ -131,6 +131,28 @@ def test_reductions_vs_oracle(shape, ci):
     assert bits_equal(npy(st["absmax"]), orc.absmax(x, ci))
 
 
+@pytest.mark.parametrize("outer,C,inner,off", [(600, 96, 49, 0), (64, 300, 196, 3), (9, 20000, 16, 1),
+                                               (4100, 8, 255, 5), (70, 1, 100, 2), (40000, 24, 1, 0)])
+def test_short_row_reductions(outer, C, inner, off):
+    """The tile kernel (16 <= inner <= 256): several tiles per CTA, ragged last tile, rows that start anywhere in a
+    32-byte sector (a 4-byte-aligned view), more channels than slots; and the transposed finalize."""
+    from qsparse_b200 import ops
+    n = outer * C * inner
+    base = rnd((n + off,), 31, 1.5)
+    base[::1013] = 0.0
+    x = base[off:].reshape(outer, C, inner)
+    xc = cu(base)[off:].view(outer, C, inner)
+    st = ops.reduce_stats(xc, (outer, C, inner), absmax=True, minmax=True, abssum=True, nnz=True)
+    assert bits_equal(npy(st["absmax"]), np.abs(x).max(axis=(0, 2)))
+    assert np.array_equal(npy(st["min"]), x.min(axis=(0, 2))) and np.array_equal(npy(st["max"]), x.max(axis=(0, 2)))
+    xr = np.abs(x.astype(np.float64))
+    assert np.allclose(npy(st["abssum"]), xr.sum(axis=(0, 2)), rtol=3e-7, atol=0)
+    assert np.array_equal(npy(st["nnz"]), (xr != 0).sum(axis=(0, 2)).astype(np.float64))
+    again = ops.reduce_stats(xc, (outer, C, inner), abssum=True, absmax=True)
+    third = ops.reduce_stats(xc, (outer, C, inner), abssum=True, absmax=True)
+    assert bits_equal(npy(again["abssum"]), npy(third["abssum"]))     # deterministic
+
+
 def test_reduction_nan_propagates():
     from qsparse_b200 import ops
     x = rnd((4, 8, 100), 2)
