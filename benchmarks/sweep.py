@@ -107,6 +107,9 @@ def main():
     ops.set_tuning(1, 0)
     report("export_int8_pow2_ch", 5 * n, lambda: ops.quant_export_int8(x, ops.EXPORT_DECIMAL, decC, 8, layout),
            note="4 B read + 1 B written per element")
+    report("export_int4_pow2_ch", 4.5 * n,
+           lambda: ops.quant_export_int8(x, ops.EXPORT_DECIMAL, decC, 4, layout, pack4=True),
+           note="4 B read + half a byte written per element")
     report("mask_apply_ch", 8 * n, lambda: ops.mask_apply(x, mask75, layout, out=y))
     report("reduce_abssum_absmax_ch", 4 * n, lambda: ops.reduce_stats(x, layout, abssum=True, absmax=True))
     report("reduce_absmax_tensor", 4 * n, lambda: ops.reduce_stats(x, (1, 1, n), absmax=True))

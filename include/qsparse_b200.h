@@ -136,6 +136,16 @@ int qsb_quant_export_int8(const float *x, uint8_t *q_out, int kind,
                           int64_t outer, int64_t channels, int64_t inner,
                           void *stream);
 
+/* The same codes for bits <= 4, packed two per byte in flat element order: byte i holds
+ * element 2i in its low nibble and element 2i+1 in its high nibble (kinds 0/1: 4-bit two's
+ * complement; kind 2: unsigned); q_out has (n + 1) / 2 bytes, an odd n leaves the last high
+ * nibble 0.  4.5 B/elem.  ref: as qsb_quant_export_int8 (SURVEY 8f-3 "int4-packed"). */
+int qsb_quant_export_int4(const float *x, uint8_t *q_out, int kind,
+                          const float *param_dev, int64_t n_param,
+                          double param_host, double param_host2, int bits,
+                          int64_t outer, int64_t channels, int64_t inner,
+                          void *stream);
+
 /* ------------------------------------------------------------------------
  * K2  straight-through-estimator backward (and the fused prune backward).
  * ref: DecimalQuantization.backward qsparse/quantize.py:65-77,

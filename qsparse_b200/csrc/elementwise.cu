@@ -201,6 +201,83 @@ struct ExportLineOp : LineOp<QSB_MASK_NONE, true> {
   }
 };
 
+// Packed 4-bit export: two codes per byte (even element in the low nibble), 4.5 B/elem.  A
+// thread owns 8 consecutive elements = one 32-bit store; it walks the channel of its elements
+// itself (one 64-bit division per thread), so every [outer, C, inner] layout takes this one
+// kernel.  The per-element arithmetic is the int8 export ops' own apply().
+template <class Op>
+__global__ void __launch_bounds__(QSB_THREADS)
+    export_pack4_kernel(Op op, const float *__restrict__ x, uint8_t *__restrict__ out, int64_t n,
+                        int64_t inner, int64_t channels, int vec_ok) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int U = 2;  // vectors per thread, QSB_THREADS * 8 elements apart: both loads in flight
+  const int64_t t0 = (int64_t)blockIdx.x * (QSB_THREADS * 8 * U) + threadIdx.x * 8;
+  float v[U][8];
+  int cnt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t e0 = t0 + (int64_t)u * (QSB_THREADS * 8);
+    cnt[u] = e0 >= n ? 0 : ((n - e0 < 8) ? (int)(n - e0) : 8);
+    if (cnt[u] == 8 && vec_ok) {
+      const VecF<8> a = ld_vec<8, Hint::STREAM>(x + e0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[u][j] = a.v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[u][j] = j < cnt[u] ? x[e0 + j] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (cnt[u] == 0) continue;
+    const int64_t e0 = t0 + (int64_t)u * (QSB_THREADS * 8);
+    int64_t col, c;
+    if (n <= 0xffffffffLL) {  // 32-bit divisions when they are enough
+      const uint32_t row = (uint32_t)e0 / (uint32_t)inner;
+      col = (uint32_t)e0 - row * (uint32_t)inner;
+      c = row % (uint32_t)channels;
+    } else {
+      const int64_t row = e0 / inner;
+      col = e0 - row * inner;
+      c = row % channels;
+    }
+    typename Op::P p = op.params((int32_t)c);
+    uint32_t word = 0;
+    if (inner - col >= 8) {  // the whole vector in one row: one set of parameters
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float o0, o1;
+        uint8_t ob = 0;
+        if (j < cnt[u]) op.apply(v[u][j], 0.f, (uint8_t)1, p, o0, o1, ob);
+        word |= (uint32_t)(ob & 0xF) << (4 * j);
+      }
+    } else {  // walk the rows (kept rolled: the parameter derivation must not be replicated 8 times)
+#pragma unroll 1
+      for (int j = 0; j < cnt[u]; ++j) {
+        float o0, o1;
+        uint8_t ob = 0;
+        float vj = v[u][0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) vj = (j == k) ? v[u][k] : vj;
+        op.apply(vj, 0.f, (uint8_t)1, p, o0, o1, ob);
+        word |= (uint32_t)(ob & 0xF) << (4 * j);
+        if (++col == inner) {
+          col = 0;
+          c = (c + 1 == channels) ? 0 : c + 1;
+          p = op.params((int32_t)c);
+        }
+      }
+    }
+    uint8_t *o = out + (e0 >> 1);
+    if (cnt[u] == 8 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+      *reinterpret_cast<uint32_t *>(o) = word;
+    } else {
+      for (int b2 = 0; b2 < (cnt[u] + 1) / 2; ++b2) o[b2] = (uint8_t)(word >> (8 * b2));
+    }
+  }
+}
+
 }  // namespace qsb
 
 // ===========================================================================
@@ -385,6 +462,57 @@ extern "C" int qsb_quant_export_int8(const float *x, uint8_t *q_out, int kind,
   const double N = ldexp(1.0, bits);
   op.n_levels = (float)N, op.q_max = (float)(N - 1.0), op.cmask = nullptr;
   return launch_map<ExportLineOp, Hint::STREAM, Hint::KEEP>(op, io, L, (cudaStream_t)stream);
+}
+
+/* the same codes, two per byte */
+extern "C" int qsb_quant_export_int4(const float *x, uint8_t *q_out, int kind,
+                                     const float *param_dev, int64_t n_param,
+                                     double param_host, double param_host2, int bits,
+                                     int64_t outer, int64_t channels, int64_t inner,
+                                     void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_layout(outer, channels, inner)) return e;
+  if (kind < 0 || kind > 2 || bits < 1 || bits > 4) return QSB_E_BADARG;
+  const int64_t n = outer * channels * inner;
+  if (n == 0) return 0;
+  if (!x || !q_out) return QSB_E_BADARG;
+  if (!aligned_to(x, 4)) return QSB_E_ALIGN;
+  int stride = 0;
+  if (param_dev) {
+    stride = param_stride(n_param, channels);
+    if (stride < 0) return QSB_E_BADARG;
+    if (kind == 2 && !aligned_to(param_dev, 8)) return QSB_E_ALIGN;
+  }
+  const int q_min = -(1 << (bits - 1)), q_max = (1 << (bits - 1)) - 1;
+  const int64_t per_cta = (int64_t)QSB_THREADS * 8 * 2;  // two vectors per thread
+  const dim3 grid((unsigned)((n + per_cta - 1) / per_cta));
+  const int vec_ok = aligned_to(x, 32) ? 1 : 0;
+  // per-tensor parameters: one channel of n elements, so the walk never reloads them
+  const int64_t k_inner = stride ? inner : n, k_ch = stride ? channels : 1;
+  if (kind == 0) {
+    ExportPow2Op op;
+    op.dec = param_dev, op.dec_stride = stride;
+    op.toi_host = (float)pow(2.0, param_host), op.tof_host = (float)pow(2.0, -param_host);
+    op.cmask = nullptr, op.q_min = q_min, op.q_max = q_max;
+    QSB_CUDA_TRY(launch_k(export_pack4_kernel<ExportPow2Op>, grid, dim3(QSB_THREADS), 0, stream, op, x, q_out, n,
+                          k_inner, k_ch, vec_ok));
+  } else if (kind == 1) {
+    ExportScalerOp op;
+    op.scale = param_dev, op.scale_stride = stride, op.scale_host = (float)param_host;
+    op.cmask = nullptr, op.q_min = q_min, op.q_max = q_max;
+    QSB_CUDA_TRY(launch_k(export_pack4_kernel<ExportScalerOp>, grid, dim3(QSB_THREADS), 0, stream, op, x, q_out, n,
+                          k_inner, k_ch, vec_ok));
+  } else {
+    ExportLineOp op;
+    op.lines = param_dev, op.lines_stride = stride;
+    op.lo_host = (float)param_host, op.hi_host = (float)param_host2;
+    const double N = ldexp(1.0, bits);
+    op.n_levels = (float)N, op.q_max = (float)(N - 1.0), op.cmask = nullptr;
+    QSB_CUDA_TRY(launch_k(export_pack4_kernel<ExportLineOp>, grid, dim3(QSB_THREADS), 0, stream, op, x, q_out, n,
+                          k_inner, k_ch, vec_ok));
+  }
+  QSB_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int qsb_ste_bwd(const float *g, float *g_clamped_out, float *gx_out,

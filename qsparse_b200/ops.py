@@ -153,13 +153,17 @@ def ste_bwd(g, scale, is_decimal: bool, bits: int, notch: int, layout: Layout, m
 EXPORT_DECIMAL, EXPORT_SCALER, EXPORT_LINE = 0, 1, 2
 
 
-def quant_export_int8(x, kind: int, param, bits: int, layout: Layout):
+def quant_export_int8(x, kind: int, param, bits: int, layout: Layout, pack4: bool = False):
     """integer codes of a fake-quantizer: int8 (decimal / scaler) or uint8 (line) tensor of x's shape.
-    ``param``: decimal / scale (float or tensor [1] / [C]) or lines ((lo, hi) or tensor [1|C, 2])."""
+    ``param``: decimal / scale (float or tensor [1] / [C]) or lines ((lo, hi) or tensor [1|C, 2]).
+    ``pack4`` (bits <= 4): a flat uint8 tensor of (n + 1) // 2 bytes, element 2i in the low nibble of byte i."""
     lib = N.load_library()
     N.require_cuda(x, "input")
     xs = N.as_f32_contiguous(x.detach())
-    q = torch.empty(xs.shape, dtype=torch.uint8 if kind == EXPORT_LINE else torch.int8, device=x.device)
+    if pack4:
+        q = torch.empty((xs.numel() + 1) // 2, dtype=torch.uint8, device=x.device)
+    else:
+        q = torch.empty(xs.shape, dtype=torch.uint8 if kind == EXPORT_LINE else torch.int8, device=x.device)
     dev, n, h1, h2 = None, 1, 0.0, 0.0
     if isinstance(param, torch.Tensor):
         N.require_cuda(param, "param")
@@ -169,9 +173,10 @@ def quant_export_int8(x, kind: int, param, bits: int, layout: Layout):
         h1, h2 = float(param[0]), float(param[1])
     else:
         h1 = float(param)
-    N.check(lib.qsb_quant_export_int8(N.ptr(xs), N.ptr(q), c_int(kind), N.ptr(dev), c_int64(n), c_double(h1),
-                                      c_double(h2), c_int(bits), c_int64(layout[0]), c_int64(layout[1]),
-                                      c_int64(layout[2]), N.stream_ptr(x.device)), "qsb_quant_export_int8")
+    fn, what = (lib.qsb_quant_export_int4, "qsb_quant_export_int4") if pack4 else \
+        (lib.qsb_quant_export_int8, "qsb_quant_export_int8")
+    N.check(fn(N.ptr(xs), N.ptr(q), c_int(kind), N.ptr(dev), c_int64(n), c_double(h1), c_double(h2), c_int(bits),
+               c_int64(layout[0]), c_int64(layout[1]), c_int64(layout[2]), N.stream_ptr(x.device)), what)
     return q
 
 

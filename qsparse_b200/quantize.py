@@ -559,7 +559,7 @@ class QuantizeLayer(nn.Module):
         return out
 
 
-def export_integer(layer: "QuantizeLayer", x: torch.Tensor):
+def export_integer(layer: "QuantizeLayer", x: torch.Tensor, pack4: bool = False):
     """Integer deployment form of what ``layer`` computes for ``x``: the int8 / uint8 codes plus
     the parameters that turn them back into the fake-quantized values,
 
@@ -568,22 +568,40 @@ def export_integer(layer: "QuantizeLayer", x: torch.Tensor):
         AdaptiveQuantizer  q uint8, value = q * step + lo,  step = (hi - lo) / 2^bits   (float zero-point form)
 
     one kernel, 5 B/elem (``qsb_quant_export_int8``).  Values outside the ``bits``-bit range saturate (the
-    fake-quantizers themselves do not clamp in the forward).  Returns a dict."""
+    fake-quantizers themselves do not clamp in the forward).  ``pack4`` (layers of <= 4 bits): ``q`` is
+    a flat uint8 tensor with two codes per byte, element 2i in the low nibble (4.5 B/elem,
+    ``qsb_quant_export_int4``); ``unpack_int4`` turns it back into the int8 form.  Returns a dict."""
     assert isinstance(layer, QuantizeLayer) and layer.initted and layer.bits <= 8
+    assert not pack4 or layer.bits <= 4, "pack4 needs a layer of at most 4 bits"
     cb, ci = layer.callback, layer.channelwise
     xs = N.as_f32_contiguous(x.detach())
     layout = N.channel_layout(xs.shape, ci)
     w = layer.weight.data
     if isinstance(cb, AdaptiveQuantizer):
         lines = w.reshape(-1, 2)
-        q = ops.quant_export_int8(xs, ops.EXPORT_LINE, lines, layer.bits, layout)
-        return dict(q=q, kind="line", bits=layer.bits, lines=lines.clone(), channel_index=ci)
+        q = ops.quant_export_int8(xs, ops.EXPORT_LINE, lines, layer.bits, layout, pack4)
+        return dict(q=q, kind="line", bits=layer.bits, lines=lines.clone(), channel_index=ci, packed=pack4,
+                    shape=tuple(xs.shape))
     if cb.use_float_scaler:
-        q = ops.quant_export_int8(xs, ops.EXPORT_SCALER, w.reshape(-1), layer.bits, layout)
-        return dict(q=q, kind="scaler", bits=layer.bits, scale=w.reshape(-1).clone(), channel_index=ci)
+        q = ops.quant_export_int8(xs, ops.EXPORT_SCALER, w.reshape(-1), layer.bits, layout, pack4)
+        return dict(q=q, kind="scaler", bits=layer.bits, scale=w.reshape(-1).clone(), channel_index=ci, packed=pack4,
+                    shape=tuple(xs.shape))
     dec = ops.scale_to_decimal(w).reshape(-1)
-    q = ops.quant_export_int8(xs, ops.EXPORT_DECIMAL, dec, layer.bits, layout)
-    return dict(q=q, kind="decimal", bits=layer.bits, decimal=dec, channel_index=ci)
+    q = ops.quant_export_int8(xs, ops.EXPORT_DECIMAL, dec, layer.bits, layout, pack4)
+    return dict(q=q, kind="decimal", bits=layer.bits, decimal=dec, channel_index=ci, packed=pack4,
+                shape=tuple(xs.shape))
+
+
+def unpack_int4(exported: dict) -> torch.Tensor:
+    """The int8 / uint8 code tensor of a ``pack4`` export (plain torch ops; a reader-side helper, not a hot path)."""
+    q, shape = exported["q"], exported["shape"]
+    n = 1
+    for s_ in shape:
+        n *= int(s_)
+    nib = torch.stack([q & 0xF, q >> 4], dim=1).reshape(-1)[:n]
+    if exported["kind"] == "line":
+        return nib.reshape(shape)
+    return ((nib.to(torch.int16) ^ 8) - 8).to(torch.int8).reshape(shape)   # sign-extend the 4-bit code
 
 
 def quantize(inp: nn.Module = None, bits: int = 8, channelwise: int = 1, timeout: int = 1000,

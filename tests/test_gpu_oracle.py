@@ -728,6 +728,53 @@ def test_export_integer_from_layers():
         assert torch.equal(deq + 0.0, y + 0.0), key
 
 
+@pytest.mark.parametrize("shape,ci,off", [((4, 6, 7, 7), 1, 0), ((16, 40), 0, 0), ((3, 5, 33), 2, 1), ((2, 3, 1001), -1, 0),
+                                          ((7, 11, 1), 1, 3), ((64, 96, 14, 14), 1, 0)])
+def test_quant_export_int4_packed(shape, ci, off):
+    """two codes per byte == the low 4 bits of the int8 export of the same tensor at bits=4 (every layout incl.
+    odd element counts, unaligned input, channel-last), and the layer-level pack / unpack round trip."""
+    from qsparse_b200 import ops
+    bits = 4
+    n = int(np.prod(shape))
+    base = rnd((n + off,), 33, 1.5)
+    x = base[off:].reshape(shape)
+    xc = cu(base)[off:].view(shape)
+    C = shape[ci] if ci >= 0 else 1
+    rng = np.random.default_rng(9)
+    dec = rng.integers(0, 3, C).astype(np.float32)
+    sc = rng.uniform(0.1, 0.5, C).astype(np.float32)
+    lines = np.stack([rng.uniform(-2, -0.1, C), rng.uniform(0.1, 2, C)], 1).astype(np.float32)
+    layout = (1, 1, x.size) if ci < 0 else tuple(orc.layout(shape, ci))
+    for kind, param in ((ops.EXPORT_DECIMAL, dec), (ops.EXPORT_SCALER, sc), (ops.EXPORT_LINE, lines)):
+        q8 = npy(ops.quant_export_int8(xc, kind, cu(param), bits, layout)).reshape(-1)
+        q4 = npy(ops.quant_export_int8(xc, kind, cu(param), bits, layout, pack4=True))
+        assert q4.dtype == np.uint8 and q4.shape == ((n + 1) // 2,)
+        nib = np.stack([q4 & 0xF, q4 >> 4], 1).reshape(-1)
+        assert np.array_equal(nib[:n], q8.view(np.uint8) & 0xF), kind
+        assert n % 2 == 0 or nib[n] == 0
+    # host scalars instead of device parameters
+    q8 = npy(ops.quant_export_int8(xc, ops.EXPORT_SCALER, 0.3, bits, (1, 1, n))).reshape(-1)
+    q4 = npy(ops.quant_export_int8(xc, ops.EXPORT_SCALER, 0.3, bits, (1, 1, n), pack4=True))
+    assert np.array_equal(np.stack([q4 & 0xF, q4 >> 4], 1).reshape(-1)[:n], q8.view(np.uint8) & 0xF)
+
+
+def test_export_integer_pack4_round_trip():
+    import qsparse_b200 as q
+    from qsparse_b200.quantize import export_integer, unpack_int4
+    x = cu(rnd((4, 10, 12, 12), 5, 0.5))
+    for cb in (q.DecimalQuantizer(), q.ScalerQuantizer(), q.AdaptiveQuantizer()):
+        # channel-wise Decimal / Scaler estimation on a batch is the reference's crash domain (SURVEY Q10)
+        layer = q.quantize(bits=4, timeout=2, channelwise=1 if isinstance(cb, q.AdaptiveQuantizer) else -1,
+                           callback=cb)
+        for _ in range(4):
+            layer(x)
+        plain, packed = export_integer(layer, x), export_integer(layer, x, pack4=True)
+        assert packed["packed"] and packed["q"].numel() == x.numel() // 2
+        assert torch.equal(unpack_int4(packed), plain["q"]), type(cb).__name__
+    with pytest.raises(AssertionError):
+        export_integer(q.quantize(bits=8, timeout=0, callback=q.ScalerQuantizer()), x, pack4=True)
+
+
 # ----------------------------------------------------------------------------- K9 fused unstructured prune step
 def _step_reference(mags, xs, ks, t):
     """EMA -> k-th value -> mask -> apply with the separate kernels (each pinned to the oracle elsewhere)"""
