@@ -182,9 +182,10 @@ constexpr int kTileMaxInner = 256;
 constexpr int kTileFloats = 8192;  // 32 KB of shared memory; 4 vectors per thread
 constexpr int kTileRowsMax = 32;   // 4 slots per warp
 constexpr int kTileVpt = kTileFloats / 8 / QSB_THREADS;
+constexpr int kTileCtasPerSm = 3;  // 80 registers: 4 accumulators + a prefetched visit + a row in flight
 
-template <int WHAT>
-__global__ void __launch_bounds__(QSB_THREADS, 4)
+template <int WHAT, int KI>  // KI = loads per lane per row: inner <= 32 * KI
+__global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
     reduce_tile_kernel(const float *__restrict__ x, int64_t rows, int inner, int tile_rows, int spans,
                        int span_stride, int64_t vwarps, Partials P) {
   pdl_wait();
@@ -200,12 +201,19 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
 
   // rows [base + g * vwarps, +nslots) for g < spans: `spans` contiguous pieces of memory, each
   // copied to tile[g * span_stride ...] keeping its position inside a 32-byte sector
+  // which piece / vector of the piece this thread's i-th register vector is: the same for every visit
+  int gi[kTileVpt], vii[kTileVpt];
+#pragma unroll
+  for (int i = 0; i < kTileVpt; ++i) {
+    const int v = threadIdx.x + i * QSB_THREADS;
+    gi[i] = v / vps;
+    vii[i] = v - gi[i] * vps;
+  }
   auto fetch = [&](int64_t base) {
     have_next = 0;
 #pragma unroll
     for (int i = 0; i < kTileVpt; ++i) {
-      const int v = threadIdx.x + i * QSB_THREADS;
-      const int g = v / vps, vi = v - g * vps;
+      const int g = gi[i], vi = vii[i];
       if (g >= spans) continue;
       const int64_t base_g = base + (int64_t)g * vwarps;
       if (base_g >= rows) continue;
@@ -254,19 +262,26 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
         if (rr < nr) {
           const float *rowp = tile + g * span_stride + a + rr * inner;
           float s = 0.f;  // <= 8 terms per lane in fp32, then fp64 (see the header note)
-          for (int j = lane; j < inner; j += 32) {
-            const float v = rowp[j];
-            if constexpr (WHAT & QSB_STAT_ABSMAX) {
-              const uint32_t b = __float_as_uint(v) & 0x7fffffffu;
-              acc[q].amax = b > acc[q].amax ? b : acc[q].amax;
+          float vals[KI];
+#pragma unroll
+          for (int k = 0; k < KI; ++k)  // all the row's loads first, no loop overhead
+            if (lane + 32 * k < inner) vals[k] = rowp[lane + 32 * k];
+#pragma unroll
+          for (int k = 0; k < KI; ++k) {
+            if (lane + 32 * k < inner) {
+              const float v = vals[k];
+              if constexpr (WHAT & QSB_STAT_ABSMAX) {
+                const uint32_t b = __float_as_uint(v) & 0x7fffffffu;
+                acc[q].amax = b > acc[q].amax ? b : acc[q].amax;
+              }
+              if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+                acc[q].mn = fminf(acc[q].mn, v);
+                acc[q].nan |= (v != v);
+              }
+              if constexpr (WHAT & QSB_STAT_MINMAX) acc[q].mx = fmaxf(acc[q].mx, v);
+              if constexpr (WHAT & QSB_STAT_ABSSUM) s = __fadd_rn(s, fabsf(v));
+              if constexpr (WHAT & QSB_STAT_NNZ) acc[q].nnz += (v != 0.0f) ? 1u : 0u;
             }
-            if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
-              acc[q].mn = fminf(acc[q].mn, v);
-              acc[q].nan |= (v != v);
-            }
-            if constexpr (WHAT & QSB_STAT_MINMAX) acc[q].mx = fmaxf(acc[q].mx, v);
-            if constexpr (WHAT & QSB_STAT_ABSSUM) s = __fadd_rn(s, fabsf(v));
-            if constexpr (WHAT & QSB_STAT_NNZ) acc[q].nnz += (v != 0.0f) ? 1u : 0u;
           }
           if constexpr (WHAT & QSB_STAT_ABSSUM) acc[q].asum += (double)s;
         }
@@ -288,9 +303,8 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
 // memory in lane order (deterministic) and row lane 0 writes the partial.
 // ---------------------------------------------------------------------------
 template <int WHAT, int V>
-__global__ void __launch_bounds__(QSB_THREADS)
-    reduce_cols_kernel(const float *__restrict__ x, int64_t nrows, int64_t ncols,
-                       int64_t rows_per_chunk, int tpr, Partials P) {
+__device__ __forceinline__ void reduce_cols_body(const float *__restrict__ x, int64_t nrows, int64_t ncols,
+                                                 int64_t rows_per_chunk, int tpr, Partials P) {
   pdl_wait();
   pdl_trigger();
   const int64_t vcols = ncols / V;  // V == 4 requires ncols % 4 == 0
@@ -321,42 +335,50 @@ __global__ void __launch_bounds__(QSB_THREADS)
       for (int q = 0; q < V; ++q) acc[q].add(v.v[q]);
     }
   }
-  if (rpb > 1) {
-    // combine the row lanes: [field][q][thread] in shared memory, summed by row lane 0 in order
-    __shared__ uint32_t s_amax[V][QSB_THREADS];
-    __shared__ float s_mn[V][QSB_THREADS], s_mx[V][QSB_THREADS];
-    __shared__ double s_asum[V][QSB_THREADS];
-    __shared__ uint32_t s_nnz[V][QSB_THREADS];
-    __shared__ uint8_t s_nan[V][QSB_THREADS];
+  // staging for the two in-kernel combines: [field][q][thread]
+  __shared__ uint32_t s_amax[V][QSB_THREADS];
+  __shared__ float s_mn[V][QSB_THREADS], s_mx[V][QSB_THREADS];
+  __shared__ double s_asum[V][QSB_THREADS];
+  __shared__ uint32_t s_nnz[V][QSB_THREADS];
+  __shared__ uint8_t s_nan[V][QSB_THREADS];
+  auto stage = [&](int t) {
 #pragma unroll
     for (int q = 0; q < V; ++q) {
-      if constexpr (WHAT & QSB_STAT_ABSMAX) s_amax[q][threadIdx.x] = acc[q].amax;
+      if constexpr (WHAT & QSB_STAT_ABSMAX) s_amax[q][t] = acc[q].amax;
       if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
-        s_mn[q][threadIdx.x] = acc[q].mn;
-        s_nan[q][threadIdx.x] = acc[q].nan ? 1 : 0;
+        s_mn[q][t] = acc[q].mn;
+        s_nan[q][t] = acc[q].nan ? 1 : 0;
       }
-      if constexpr (WHAT & QSB_STAT_MINMAX) s_mx[q][threadIdx.x] = acc[q].mx;
-      if constexpr (WHAT & QSB_STAT_ABSSUM) s_asum[q][threadIdx.x] = acc[q].asum;
-      if constexpr (WHAT & QSB_STAT_NNZ) s_nnz[q][threadIdx.x] = acc[q].nnz;
+      if constexpr (WHAT & QSB_STAT_MINMAX) s_mx[q][t] = acc[q].mx;
+      if constexpr (WHAT & QSB_STAT_ABSSUM) s_asum[q][t] = acc[q].asum;
+      if constexpr (WHAT & QSB_STAT_NNZ) s_nnz[q][t] = acc[q].nnz;
     }
+  };
+  if (rpb > 1) {
+    // combine the row lanes in shared memory, summed by row lane 0 in lane order (deterministic)
+    stage(threadIdx.x);
     __syncthreads();
-    if (rl != 0) return;
-    for (int l = 1; l < rpb; ++l) {
-      const int t = l * tpr + cl;
+    if (rl == 0) {
+      for (int l = 1; l < rpb; ++l) {
+        const int t = l * tpr + cl;
 #pragma unroll
-      for (int q = 0; q < V; ++q) {
-        if constexpr (WHAT & QSB_STAT_ABSMAX) acc[q].amax = s_amax[q][t] > acc[q].amax ? s_amax[q][t] : acc[q].amax;
-        if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
-          acc[q].mn = fminf(acc[q].mn, s_mn[q][t]);
-          acc[q].nan |= s_nan[q][t] != 0;
+        for (int q = 0; q < V; ++q) {
+          if constexpr (WHAT & QSB_STAT_ABSMAX) acc[q].amax = s_amax[q][t] > acc[q].amax ? s_amax[q][t] : acc[q].amax;
+          if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+            acc[q].mn = fminf(acc[q].mn, s_mn[q][t]);
+            acc[q].nan |= s_nan[q][t] != 0;
+          }
+          if constexpr (WHAT & QSB_STAT_MINMAX) acc[q].mx = fmaxf(acc[q].mx, s_mx[q][t]);
+          if constexpr (WHAT & QSB_STAT_ABSSUM) acc[q].asum += s_asum[q][t];
+          if constexpr (WHAT & QSB_STAT_NNZ) acc[q].nnz += s_nnz[q][t];
         }
-        if constexpr (WHAT & QSB_STAT_MINMAX) acc[q].mx = fmaxf(acc[q].mx, s_mx[q][t]);
-        if constexpr (WHAT & QSB_STAT_ABSSUM) acc[q].asum += s_asum[q][t];
-        if constexpr (WHAT & QSB_STAT_NNZ) acc[q].nnz += s_nnz[q][t];
       }
     }
   }
-  if (!live) return;
+  // (Combining the row bands of 8 CTAs through a thread-block cluster's distributed shared memory before
+  // writing — 8x fewer partials — was measured and dropped: the finalize went 10 -> 5 us but this kernel
+  // 16 -> 28 us on [16384, 1000], with every cluster resident.)
+  if (!live || rl != 0) return;
 #pragma unroll
   for (int q = 0; q < V; ++q) {
     const int64_t idx = chunk * ncols + vc * V + q;
@@ -368,6 +390,13 @@ __global__ void __launch_bounds__(QSB_THREADS)
     if constexpr (WHAT & QSB_STAT_ABSSUM) P.asum[idx] = acc[q].asum;
     if constexpr (WHAT & QSB_STAT_NNZ) P.nnz[idx] = (double)acc[q].nnz;
   }
+}
+
+template <int WHAT, int V>
+__global__ void __launch_bounds__(QSB_THREADS)
+    reduce_cols_kernel(const float *__restrict__ x, int64_t nrows, int64_t ncols,
+                       int64_t rows_per_chunk, int tpr, Partials P) {
+  reduce_cols_body<WHAT, V>(x, nrows, ncols, rows_per_chunk, tpr, P);
 }
 
 // ---------------------------------------------------------------------------
@@ -506,6 +535,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
     reduce_finalize_t_kernel(Partials P, FinalOut out, int64_t channels, int64_t count) {
   pdl_wait();
   pdl_trigger();
+  constexpr int kU = 8;  // independent loads in flight per statistic
   const int cl = threadIdx.x & 7, jl = threadIdx.x >> 3;
   const int64_t c = (int64_t)blockIdx.x * 8 + cl;
   const bool active = c < channels;
@@ -514,54 +544,54 @@ __global__ void __launch_bounds__(QSB_THREADS)
   bool nan = false;
   double asum = 0.0, nnz = 0.0;
   if (active) {
-    for (int64_t j0 = jl; j0 < count; j0 += 4 * 32) {
-      int64_t idx[4];
-      bool ok[4];
+    for (int64_t j0 = jl; j0 < count; j0 += kU * 32) {
+      int64_t idx[kU];
+      bool ok[kU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         ok[u] = j0 + 32 * u < count;
         idx[u] = ok[u] ? (j0 + 32 * u) * channels + c : 0;
       }
       if constexpr (WHAT & QSB_STAT_ABSMAX) {
-        uint32_t b[4];
+        uint32_t b[kU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) b[u] = ok[u] ? P.amax[idx[u]] : 0u;
+        for (int u = 0; u < kU; ++u) b[u] = ok[u] ? P.amax[idx[u]] : 0u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) amax = b[u] > amax ? b[u] : amax;
+        for (int u = 0; u < kU; ++u) amax = b[u] > amax ? b[u] : amax;
       }
       if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
-        float v[4];
+        float v[kU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.mn[idx[u]] : INFINITY;
+        for (int u = 0; u < kU; ++u) v[u] = ok[u] ? P.mn[idx[u]] : INFINITY;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kU; ++u) {
           nan |= (v[u] != v[u]);
           mn = fminf(mn, v[u]);
         }
       }
       if constexpr (WHAT & QSB_STAT_MINMAX) {
-        float v[4];
+        float v[kU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.mx[idx[u]] : -INFINITY;
+        for (int u = 0; u < kU; ++u) v[u] = ok[u] ? P.mx[idx[u]] : -INFINITY;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kU; ++u) {
           nan |= (v[u] != v[u]);
           mx = fmaxf(mx, v[u]);
         }
       }
       if constexpr (WHAT & QSB_STAT_ABSSUM) {
-        double v[4];
+        double v[kU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.asum[idx[u]] : 0.0;
+        for (int u = 0; u < kU; ++u) v[u] = ok[u] ? P.asum[idx[u]] : 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) asum += v[u];
+        for (int u = 0; u < kU; ++u) asum += v[u];
       }
       if constexpr (WHAT & QSB_STAT_NNZ) {
-        double v[4];
+        double v[kU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? P.nnz[idx[u]] : 0.0;
+        for (int u = 0; u < kU; ++u) v[u] = ok[u] ? P.nnz[idx[u]] : 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) nnz += v[u];
+        for (int u = 0; u < kU; ++u) nnz += v[u];
       }
     }
   }
@@ -638,7 +668,7 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
   const int64_t warps_phys =
       (int64_t)device_props().sm_count * kRowCtasPerSm * (QSB_THREADS / 32);
   if (inner >= kTileMinInner && inner <= kTileMaxInner) {
-    // short rows: the tile kernel.  One slot (virtual warp) per row of a tile, 4 CTAs of 32 slots
+    // short rows: the tile kernel.  One slot (virtual warp) per row of a tile, 3 CTAs of 32 slots
     // per SM; slots = m * channels so that a slot only ever sees one channel.
     p.row_mode = true;
     p.rows = outer * channels;
@@ -649,7 +679,7 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
     // own offset inside a 32-byte sector: ~32 KB in flight per CTA whatever the row length
     p.tile_span_stride = (int)((p.tile_rows * inner + 7 + 7) / 8 * 8);
     p.tile_spans = kTileFloats / p.tile_span_stride;
-    const int64_t target = (int64_t)device_props().sm_count * kRowCtasPerSm * kTileRowsMax;
+    const int64_t target = (int64_t)device_props().sm_count * kTileCtasPerSm * kTileRowsMax;
     if (channels == 1) {
       p.vwarps = p.rows < target ? p.rows : target;
       p.fin_count = p.vwarps;
@@ -757,8 +787,13 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
                       cudaStream_t stream, bool finalize = true) {
   if (pl.row_mode && pl.tile_rows > 0) {
     const int64_t grid = (pl.vwarps + pl.tile_rows - 1) / pl.tile_rows;
-    QSB_CUDA_TRY(launch_k(reduce_tile_kernel<WHAT>, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, x,
-                          pl.rows, (int)inner, pl.tile_rows, pl.tile_spans, pl.tile_span_stride, pl.vwarps, P));
+    auto go = [&](auto kernel) {
+      return launch_k(kernel, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, x, pl.rows, (int)inner,
+                      pl.tile_rows, pl.tile_spans, pl.tile_span_stride, pl.vwarps, P);
+    };
+    if (inner <= 64) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 2>));
+    else if (inner <= 128) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 4>));
+    else QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8>));
   } else if (pl.row_mode) {
     constexpr int kWarps = QSB_THREADS / 32;
     int64_t grid = (int64_t)device_props().sm_count * kRowCtasPerSm;

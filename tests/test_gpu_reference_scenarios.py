@@ -161,6 +161,19 @@ def test_activation_pruning_structured_uniform_and_shape_rules():
     assert torch.equal(y == 0, layer.mask == 0)
     with pytest.raises(RuntimeError):
         layer(x2)                                         # an unstructured mask fixes the input shape
+    # the device-RNG extension keeps the invariants: exact budget per refresh, pruned positions stay pruned
+    torch.manual_seed(4)
+    layer = q.prune(sparsity=0.5, start=start, interval=interval, repetition=rep, dimensions={0, 1, 2, 3},
+                    callback=q.UniformPruningCallback(device_rng=True))
+    layer.train()
+    prev_dead = torch.zeros_like(x, dtype=torch.bool)
+    for i in range(steps):
+        y = layer(x)
+        if i >= start:
+            dead = layer.mask == 0
+            assert torch.equal(dead & prev_dead, prev_dead)
+            prev_dead = dead
+    assert abs(zero_fraction(y) - 0.5) <= 1 / y.numel() and torch.equal(y == 0, layer.mask == 0)
     # a channel mask lets the spatial size change in eval mode
     layer = q.prune(sparsity=0.5, start=start, interval=interval, repetition=rep, dimensions={1})
     for _ in range(start + interval * (rep + 1)):
