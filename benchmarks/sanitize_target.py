@@ -62,5 +62,21 @@ ops.fq_line_fwd(x, torch.tensor([[-0.1, 0.9]] * 16, device=dev), 8, True, layout
 ops.fq_scaler_fwd(x, 0.037, (1, 1, x.numel()))
 ops.quant_export_int8(x, ops.EXPORT_DECIMAL, 4.0, 8, (1, 1, x.numel()))
 ops.quant_export_int8(x, ops.EXPORT_LINE, torch.tensor([[-0.1, 0.9]] * 16, device=dev), 8, layout)
+# short-row / channel-last layouts: tile reduction (several visits, ragged tiles, 4-byte-aligned view), transposed
+# finalize, row-lane column reduction, group-resident channel-last maps, straddling vectors, packed int4 export
+for lay, off in (((300, 24, 196), 0), ((40, 96, 64), 3), ((9, 700, 100), 1), ((2100, 8, 255), 5), ((5000, 24, 1), 0),
+                 ((600, 1000, 1), 0), ((64, 96, 49), 0)):
+    n_ = lay[0] * lay[1] * lay[2]
+    xb = torch.randn(n_ + off, device=dev, generator=g)
+    xl = xb[off:].view(lay)
+    ops.reduce_stats(xl, lay, abssum=True, absmax=True, minmax=True, nnz=True)
+    ops.reduce_stats(xl, lay, minmax=True)
+    decl = torch.full((lay[1],), 4.0, device=dev)
+    lin = torch.tensor([[-0.5, 0.5]] * lay[1], device=dev)
+    ops.fq_pow2_fwd(xl, decl, lay)
+    ops.fq_line_fwd(xl, lin, 8, True, lay)
+    ops.ste_bwd(xl.clone(), decl, True, 8, 0, lay)
+    ops.quant_export_int8(xl, ops.EXPORT_LINE, lin, 4, lay, pack4=True)
+    ops.quant_export_int8(xl, ops.EXPORT_SCALER, 0.3, 4, (1, 1, n_), pack4=True)
 torch.cuda.synchronize()
 print("sanitize target done")
