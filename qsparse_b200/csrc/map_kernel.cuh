@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
 // ---------------------------------------------------------------------------
 // per-channel, one CTA per tile, window table (inner >= V)
 // ---------------------------------------------------------------------------
+constexpr uint32_t kUnifyInner = 512;  // P(a warp holds a straddling vector) > ~0.35 below this row length
 template <class Op, int V, int U, int MODE, Hint LH, Hint SH>
 __global__ void __launch_bounds__(QSB_THREADS)
     map_chan_win_kernel(Op op, MapIO io, int64_t n, uint32_t inner,
@@ -467,10 +468,14 @@ __global__ void __launch_bounds__(QSB_THREADS)
       VecF<V> o0, o1;
       VecB<V> ob;
       const P p0 = tab[ru[u]];
-      if (MODE == 0 || leftu[u] >= (uint32_t)V) {
+      // Short rows: almost every warp holds a lane whose vector straddles two rows (one vector in six with 7x7
+      // maps), so the two branches below would BOTH be issued for nearly every warp.  Below kUnifyInner the
+      // per-element parameter select is therefore the only path (a few SELs per element, no divergence).
+      const bool unify = MODE == 1 && inner < kUnifyInner;  // uniform across the grid
+      if (MODE == 0 || (!unify && leftu[u] >= (uint32_t)V)) {
         apply_vec<Op, V>(op, a[u], b[u], mb[u], skipv[u], p0, o0, o1, ob);
       } else {
-        const P p1 = tab[ru[u] + 1];
+        const P p1 = tab[ru[u] + (leftu[u] < (uint32_t)V ? 1 : 0)];
         bool fast2 = Op::kHasFast;  // see map_chan_win_kernel: straddling vectors stay on the cheap path
         if constexpr (Op::kHasFast)
           fast2 = op.template fast<V>(p0, a[u].v) && op.template fast<V>(p1, a[u].v);
