@@ -154,3 +154,26 @@ def test_devise_layerwise_schedule_keeps_reference_behaviour():
     assert [l.start for l in layers] == sorted(l.start for l in layers) == [10, 111]
     assert all(l.repetition == 1 and l.schedules == [l.start] for l in layers)
     assert all(l.rampup_interval == 1000 for l in layers)     # left untouched, as in the reference
+
+
+def test_unpack_int4_reader_side():
+    """unpack_int4 inverts the nibble packing of qsb_quant_export_int4 (low nibble = even element; kinds decimal /
+    scaler are 4-bit two's complement, line is unsigned), for even and odd element counts."""
+    from qsparse_b200.quantize import unpack_int4
+    rng = np.random.default_rng(0)
+    for shape in ((3, 5, 7), (4, 6)):
+        n = int(np.prod(shape))
+        for kind, lo, hi in (("decimal", -8, 8), ("scaler", -8, 8), ("line", 0, 16)):
+            codes = rng.integers(lo, hi, n)
+            nib = np.concatenate([codes & 0xF, [0] * (n % 2)]).astype(np.uint8)
+            packed = torch.from_numpy((nib[0::2] | (nib[1::2] << 4)).astype(np.uint8))
+            got = unpack_int4(dict(q=packed, kind=kind, shape=shape))
+            assert got.dtype == (torch.uint8 if kind == "line" else torch.int8)
+            assert np.array_equal(got.numpy().reshape(-1), codes)
+
+
+def test_uniform_callback_device_rng_flag():
+    import qsparse_b200 as q
+    assert q.UniformPruningCallback().device_rng is False
+    cb = q.UniformPruningCallback(mask_refresh_interval=3, device_rng=True)
+    assert cb.device_rng is True and cb.mask_refresh_interval == 3
