@@ -77,7 +77,10 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *   key 13 / 14: fused prune step: samples per sampler thread (1, 2, 4 = default) / distance
  *          of the pivots from the estimated rank in tenths of a sigma (default 35);
  *   key 15: per-channel kernels on channel-last layouts (inner == 1, channels % 8 == 0):
- *          1 = a thread keeps one group of 8 channels in registers (default), 0 = table walk. */
+ *          1 = a thread keeps one group of 8 channels in registers (default), 0 = table walk;
+ *   key 16: column-mode reductions: most threads of a CTA along one row (32, 64 = default, 128, 256);
+ *          the CTA's other threads walk interleaved rows and are combined in shared memory, so
+ *          256 / value times fewer partials reach the finalize. */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and

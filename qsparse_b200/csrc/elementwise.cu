@@ -638,6 +638,10 @@ extern "C" int qsb_set_tuning(int key, int value) {
     map_tuning().lastdim = value;
     return 0;
   }
+  if (key == 16) {
+    set_reduce_col_tpr_wide(value);
+    return 0;
+  }
   if (key == 13) {
     set_step_sample_per(value);
     return 0;

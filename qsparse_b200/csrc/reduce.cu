@@ -660,6 +660,11 @@ __global__ void tensor_min_kernel(const float *mn, int64_t channels, float *out)
 // summation order — only depends on the device, never on which statistics run.
 static int g_reduce_seg_min = 1024;
 int64_t reduce_seg_min() { return g_reduce_seg_min; }
+// column mode on wide tensors (more column vectors than this): threads of a CTA along a row; the other
+// 256 / tpr threads are row lanes whose results are combined in shared memory before the partial
+// is written, so the partial array (and the finalize's read) shrinks by that factor
+static int g_col_tpr_wide = 64;  // measured: [16384,1000] 14.7 + 6.3 -> 14.2 + 3.7 us, [512,512,7,7] 15.4 + 7.5 -> 11.4 + 6.4 us vs 256
+void set_reduce_col_tpr_wide(int v) { g_col_tpr_wide = (v == 32 || v == 64 || v == 128) ? v : 256; }
 void set_reduce_seg_min(int v) { g_reduce_seg_min = v >= 256 ? v : 256; }
 
 ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
@@ -740,19 +745,39 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
     p.nrows = outer;
     p.ncols = channels * inner;
     p.vcol = (p.ncols % 4 == 0 && (x == nullptr || aligned_to(x, 16))) ? 4 : 1;
-    const int64_t threads = p.ncols / p.vcol;
+    // The grid is planned for the vector width the SHAPE allows, whatever the alignment of x: the row
+    // bands (and with them the partial layout that qsb_prune_quant_step_params re-derives without x)
+    // must not depend on the pointer; an unaligned x only gets 4x more CTAs along the row.
+    const int64_t threads = p.ncols / (p.ncols % 4 == 0 ? 4 : 1);
     // threads of one row that a CTA covers: a power of two <= 256; the other 256 / tpr "row lanes"
     // of the CTA walk interleaved rows of the chunk
-    int64_t tpr = 1;
-    while (tpr < threads && tpr < QSB_THREADS) tpr <<= 1;
-    p.tpr = (int)tpr;
-    const int64_t ctas_x = (threads + tpr - 1) / tpr;
-    int64_t chunks = (target / QSB_THREADS + ctas_x - 1) / ctas_x;
+    int64_t tpr_max = 1;
+    while (tpr_max < threads && tpr_max < QSB_THREADS) tpr_max <<= 1;
     // at least 8 rows per chunk so the partial array stays small
     const int64_t max_chunks = (outer + 7) / 8;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
-    if (chunks > 65535) chunks = 65535;
+    const int64_t want = target / QSB_THREADS;  // resident CTAs
+    auto chunks_for = [&](int64_t tpr_) {
+      const int64_t ctas_x_ = (threads + tpr_ - 1) / tpr_;
+      int64_t c = (want + ctas_x_ / 2) / ctas_x_;  // nearest: do not spill into a second wave
+      if (c > max_chunks) c = max_chunks;
+      if (c < 1) c = 1;
+      if (c > 65535) c = 65535;
+      return c;
+    };
+    // wide tensors: from g_col_tpr_wide threads along the row upwards, the first width whose grid fills
+    // one wave best ([1024, 2048, 7, 7] at 64: 392 x 2 CTAs = 1.3 waves, 83 us instead of 71)
+    int64_t tpr = tpr_max;
+    if (tpr_max > g_col_tpr_wide) {
+      double best = -1.0;
+      for (int64_t t = g_col_tpr_wide; t <= tpr_max; t <<= 1) {
+        const int64_t total = (threads + t - 1) / t * chunks_for(t);
+        const int64_t waves = (total + want - 1) / want;
+        const double eff = (double)total / (double)(waves * want);
+        if (eff > best + 0.02) best = eff, tpr = t;
+      }
+    }
+    p.tpr = (int)tpr;
+    const int64_t chunks = chunks_for(tpr);
     p.rows_per_chunk = (outer + chunks - 1) / chunks;
     p.chunks = (outer + p.rows_per_chunk - 1) / p.rows_per_chunk;
     if (p.chunks < 1) p.chunks = 1;
@@ -837,7 +862,7 @@ extern "C" int64_t qsb_reduce_workspace_bytes(int64_t outer, int64_t channels,
                                               int64_t inner) {
   if (outer <= 0 || channels <= 0 || inner <= 0) return 256;
   const ReducePlan pl = make_plan(outer, channels, inner, nullptr);
-  // column mode may fall back to scalar columns for an unaligned x: same size.
+  // column mode falls back to scalar columns for an unaligned x: same row bands, same size.
   return partial_bytes(pl.n_partials) + 256;
 }
 

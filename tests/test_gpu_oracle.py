@@ -397,6 +397,36 @@ def test_fused_step_kernel_equals_separate_kernels(shape, C):
             assert torch.equal(st_a[key], st_c[key]), (key, t, "graph mode")
 
 
+@pytest.mark.parametrize("shape", [(4000, 48), (300, 24, 5), (700, 1000)])
+def test_fused_step_kernel_unaligned_column_mode(shape):
+    """A 4-byte-aligned x makes the column reduction fall back to scalar columns; the partial layout that the
+    parameter kernel re-derives (without seeing x) must still be the one the reduction wrote."""
+    from qsparse_b200 import ops
+    from qsparse_b200._native import channel_layout
+    C = shape[1]
+    layout = channel_layout(shape, 1)
+    count = float(layout[0] * layout[2])
+    n = int(np.prod(shape))
+    base = cu(np.abs(rnd((n + 1,), 77)))
+    k = orc.kth_index(0.5, C)
+    res = []
+    for x in (base[1:].view(shape), base[1:].clone().view(shape)):          # unaligned view, aligned copy
+        st = dict(mag=torch.zeros(C, device="cuda"), mask=torch.ones(C, dtype=torch.bool, device="cuda"),
+                  scale=torch.zeros(1, device="cuda"), dec=torch.zeros(1, device="cuda"))
+        asum = torch.empty(C, dtype=torch.float64, device="cuda")
+        amax = torch.empty(C, dtype=torch.float32, device="cuda")
+        ws = ops.reduce_partials(x, layout)
+        ops.prune_quant_step_params(st["mag"], st["mask"], st["scale"], st["dec"], ws, layout, count, 0, 1, True, k, 8,
+                                    0, True, abssum_out=asum, absmax_out=amax)
+        ref = ops.reduce_stats(x, layout, abssum=True, absmax=True)
+        assert torch.equal(amax, ref["absmax"]) and torch.allclose(asum, ref["abssum"], rtol=1e-14, atol=0)
+        assert torch.equal(amax, x.abs().amax(dim=tuple(i for i in range(len(shape)) if i != 1)))
+        res.append((st, asum, amax))
+    for key in res[0][0]:
+        assert torch.equal(res[0][0][key], res[1][0][key]), key
+    assert torch.equal(res[0][2], res[1][2])
+
+
 @pytest.mark.parametrize("kind", ["normal", "all_equal", "half_zeros", "two_values", "with_nan"])
 def test_kth_value_fast_route_and_fallback(kind):
     """n >= 2^22 takes the sampled-pivot route; data with heavy ties overflows the candidate buffer and
