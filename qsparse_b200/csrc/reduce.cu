@@ -123,15 +123,13 @@ template <int WHAT>
 __global__ void __launch_bounds__(QSB_THREADS, 4)
     reduce_rows_kernel(const float *__restrict__ x, int64_t rows, int64_t inner,
                        int64_t seg, int64_t segs_per_row, int64_t vwarps,
-                       Partials P) {
+                       Partials P, int cta_combine) {
   pdl_wait();
   pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps_phys = (int64_t)gridDim.x * (QSB_THREADS / 32);
   const int64_t items = rows * segs_per_row;
-  for (int64_t vw = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
-       vw < vwarps; vw += warps_phys) {
-    Acc<WHAT> acc;
+  auto run_vw = [&](Acc<WHAT> &acc, int64_t vw) {
     for (int64_t item = vw; item < items; item += vwarps) {
       const int64_t row = item / segs_per_row;
       const int64_t s = item - row * segs_per_row;
@@ -163,6 +161,53 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
       const int64_t done = head + (nv << 3);
       if (done + lane < len) acc.add(p[done + lane]);
     }
+  };
+  if (cta_combine) {
+    // one channel (per-tensor statistics): every warp of the CTA — one virtual warp each — feeds the same
+    // result, so the CTA combines its 8 warps in warp order and writes ONE partial; the finalize (or the
+    // fused parameter kernel) then reads gridDim.x entries instead of 8x as many
+    constexpr int kW = QSB_THREADS / 32;
+    __shared__ uint32_t s_amax[kW];
+    __shared__ float s_mn[kW], s_mx[kW];
+    __shared__ double s_asum[kW], s_nnz[kW];
+    const Partials Ps{s_amax, s_mn, s_mx, s_asum, s_nnz};
+    const int w = threadIdx.x >> 5;
+    const int64_t vw = (int64_t)blockIdx.x * kW + w;
+    Acc<WHAT> acc;
+    if (vw < vwarps) run_vw(acc, vw);
+    warp_store<WHAT>(acc, lane, Ps, w);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t amax = 0;
+      float mn = INFINITY, mx = -INFINITY;
+      bool nan = false;
+      double asum = 0.0, nnz = 0.0;
+      for (int k = 0; k < kW; ++k) {
+        if constexpr (WHAT & QSB_STAT_ABSMAX) amax = s_amax[k] > amax ? s_amax[k] : amax;
+        if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+          nan |= (s_mn[k] != s_mn[k]);
+          mn = fminf(mn, s_mn[k]);
+        }
+        if constexpr (WHAT & QSB_STAT_MINMAX) {
+          nan |= (s_mx[k] != s_mx[k]);
+          mx = fmaxf(mx, s_mx[k]);
+        }
+        if constexpr (WHAT & QSB_STAT_ABSSUM) asum += s_asum[k];
+        if constexpr (WHAT & QSB_STAT_NNZ) nnz += s_nnz[k];
+      }
+      const int64_t o = blockIdx.x;
+      if constexpr (WHAT & QSB_STAT_ABSMAX) P.amax[o] = amax;
+      if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) P.mn[o] = nan ? nan_f() : mn;
+      if constexpr (WHAT & QSB_STAT_MINMAX) P.mx[o] = nan ? nan_f() : mx;
+      if constexpr (WHAT & QSB_STAT_ABSSUM) P.asum[o] = asum;
+      if constexpr (WHAT & QSB_STAT_NNZ) P.nnz[o] = nnz;
+    }
+    return;
+  }
+  for (int64_t vw = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
+       vw < vwarps; vw += warps_phys) {
+    Acc<WHAT> acc;
+    run_vw(acc, vw);
     warp_store<WHAT>(acc, lane, P, vw);
   }
 }
@@ -427,8 +472,10 @@ __global__ void __launch_bounds__(QSB_THREADS)
   bool nan = false;
   double asum = 0.0, nnz = 0.0;
   if (active) {
+    // 32-bit division whenever the entry index fits (a 64-bit one is ~100 instructions per entry)
+    const bool small = count < 0x7fffffffLL && q < 0x7fffffffLL;
     auto index_of = [&](int64_t j) {
-      const int64_t hi = j / q;
+      const int64_t hi = small ? (int64_t)((uint32_t)j / (uint32_t)q) : j / q;
       return hi * (channels * q) + c * q + (j - hi * q);
     };
     for (int64_t j0 = tg; j0 < count; j0 += 4 * G) {
@@ -722,9 +769,10 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
     const int64_t period = channels * spr;  // items with the same (channel, segment)
     int64_t m;                              // virtual warps = m * period
     if (channels == 1) {
-      // one channel: any assignment works; one virtual warp per physical warp
+      // one channel: any assignment works; one virtual warp per physical warp, one partial per CTA
       p.vwarps = items < warps_phys ? items : warps_phys;
-      p.fin_count = p.vwarps;
+      p.cta_combine = 1;
+      p.fin_count = (p.vwarps + QSB_THREADS / 32 - 1) / (QSB_THREADS / 32);
       p.fin_q = 1;
     } else {
       const int64_t m_max = outer;
@@ -825,7 +873,7 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
     const int64_t need = (pl.vwarps + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
     QSB_CUDA_TRY(launch_k(reduce_rows_kernel<WHAT>, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, x,
-                          pl.rows, inner, pl.seg, pl.segs_per_row, pl.vwarps, P));
+                          pl.rows, inner, pl.seg, pl.segs_per_row, pl.vwarps, P, pl.cta_combine));
   } else {
     const int64_t threads = pl.ncols / pl.vcol;
     dim3 grid((unsigned)((threads + pl.tpr - 1) / pl.tpr), (unsigned)pl.chunks);
@@ -842,7 +890,8 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
   if (pl.fin_q == 1 && channels >= 8 && pl.fin_count >= 16 && pl.fin_count <= 1024) {
     QSB_CUDA_TRY(launch_k(reduce_finalize_t_kernel<WHAT>, dim3((unsigned)((channels + 7) / 8)), dim3(QSB_THREADS),
                           0, stream, P, out, channels, pl.fin_count));
-  } else if (pl.fin_count > 1024) {
+  } else if (pl.fin_count > 1024 || (pl.fin_count >= 128 && channels <= 4 * device_props().sm_count)) {
+    // a CTA per channel: many entries, or few channels (a warp per channel would leave the GPU empty)
     QSB_CUDA_TRY(launch_k(reduce_finalize_kernel<WHAT, QSB_THREADS>, dim3((unsigned)channels),
                           dim3(QSB_THREADS), 0, stream, P, out, channels, pl.fin_count, pl.fin_q));
   } else {
