@@ -116,6 +116,39 @@ __device__ __forceinline__ void warp_store(const Acc<WHAT> &a_in, int lane,
   }
 }
 
+// the same over groups of LPR consecutive lanes (each group owns one partial; `item` and `live` are the group's)
+template <int WHAT, int LPR>
+__device__ __forceinline__ void group_store(const Acc<WHAT> &a_in, int lane, const Partials &P, int64_t item,
+                                            bool live) {
+  if constexpr (LPR == 32) {
+    if (live) warp_store<WHAT>(a_in, lane, P, item);  // live is warp-uniform here
+    return;
+  }
+  Acc<WHAT> a = a_in;
+  int nan = a.nan ? 1 : 0;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    if constexpr (WHAT & QSB_STAT_ABSMAX) {
+      const uint32_t t = __shfl_xor_sync(0xffffffffu, a.amax, o);
+      a.amax = t > a.amax ? t : a.amax;
+    }
+    if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+      nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+      a.mn = fminf(a.mn, __shfl_xor_sync(0xffffffffu, a.mn, o));
+    }
+    if constexpr (WHAT & QSB_STAT_MINMAX) a.mx = fmaxf(a.mx, __shfl_xor_sync(0xffffffffu, a.mx, o));
+    if constexpr (WHAT & QSB_STAT_ABSSUM) a.asum += __shfl_xor_sync(0xffffffffu, a.asum, o);
+    if constexpr (WHAT & QSB_STAT_NNZ) a.nnz += __shfl_xor_sync(0xffffffffu, a.nnz, o);
+  }
+  if (live && (lane & (LPR - 1)) == 0) {
+    if constexpr (WHAT & QSB_STAT_ABSMAX) P.amax[item] = a.amax;
+    if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) P.mn[item] = nan ? nan_f() : a.mn;
+    if constexpr (WHAT & QSB_STAT_MINMAX) P.mx[item] = nan ? nan_f() : a.mx;
+    if constexpr (WHAT & QSB_STAT_ABSSUM) P.asum[item] = a.asum;
+    if constexpr (WHAT & QSB_STAT_NNZ) P.nnz[item] = (double)a.nnz;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // stage 1, row mode
 // ---------------------------------------------------------------------------
@@ -229,7 +262,9 @@ constexpr int kTileRowsMax = 32;   // 4 slots per warp
 constexpr int kTileVpt = kTileFloats / 8 / QSB_THREADS;
 constexpr int kTileCtasPerSm = 3;  // 80 registers: 4 accumulators + a prefetched visit + a row in flight
 
-template <int WHAT, int KI>  // KI = loads per lane per row: inner <= 32 * KI
+// LPR lanes share a row (32: a warp per row; 16: two rows per warp pass, for rows of <= 128 elements, where a
+// whole warp per 64-element row spent ~60 instructions of overhead per row); KI = loads per lane per row.
+template <int WHAT, int KI, int LPR>
 __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
     reduce_tile_kernel(const float *__restrict__ x, int64_t rows, int inner, int tile_rows, int spans,
                        int span_stride, int64_t vwarps, Partials P) {
@@ -240,7 +275,10 @@ __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
   const int64_t slot0 = (int64_t)blockIdx.x * tile_rows;
   const int nslots = (int)((vwarps - slot0 < tile_rows) ? vwarps - slot0 : tile_rows);
   const int vps = span_stride >> 3;  // vectors per span
-  Acc<WHAT> acc[kTileRowsMax / 8];
+  constexpr int G = 32 / LPR;                    // rows per warp pass
+  constexpr int kQ = kTileRowsMax / (8 * G);     // passes = accumulators per lane
+  const int gid = lane / LPR, gl = lane % LPR;
+  Acc<WHAT> acc[kQ];
   VecF<8> r[kTileVpt];
   unsigned have_next = 0;  // which r[i] hold data of the visit being fetched
 
@@ -302,18 +340,18 @@ __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
       const int nr = (int)((rows - base_g < nslots) ? rows - base_g : nslots);
       const int a = (int)((reinterpret_cast<uintptr_t>(x + base_g * inner) >> 2) & 7);
 #pragma unroll
-      for (int q = 0; q < kTileRowsMax / 8; ++q) {
-        const int rr = w + 8 * q;
+      for (int q = 0; q < kQ; ++q) {
+        const int rr = q * (8 * G) + w * G + gid;
         if (rr < nr) {
           const float *rowp = tile + g * span_stride + a + rr * inner;
           float s = 0.f;  // <= 8 terms per lane in fp32, then fp64 (see the header note)
           float vals[KI];
 #pragma unroll
           for (int k = 0; k < KI; ++k)  // all the row's loads first, no loop overhead
-            if (lane + 32 * k < inner) vals[k] = rowp[lane + 32 * k];
+            if (gl + LPR * k < inner) vals[k] = rowp[gl + LPR * k];
 #pragma unroll
           for (int k = 0; k < KI; ++k) {
-            if (lane + 32 * k < inner) {
+            if (gl + LPR * k < inner) {
               const float v = vals[k];
               if constexpr (WHAT & QSB_STAT_ABSMAX) {
                 const uint32_t b = __float_as_uint(v) & 0x7fffffffu;
@@ -335,8 +373,10 @@ __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
     __syncthreads();
   }
 #pragma unroll
-  for (int q = 0; q < kTileRowsMax / 8; ++q)
-    if (w + 8 * q < nslots) warp_store<WHAT>(acc[q], lane, P, slot0 + w + 8 * q);
+  for (int q = 0; q < kQ; ++q) {
+    const int rr = q * (8 * G) + w * G + gid;
+    group_store<WHAT, LPR>(acc[q], lane, P, slot0 + rr, rr < nslots);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -864,9 +904,9 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
       return launch_k(kernel, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, x, pl.rows, (int)inner,
                       pl.tile_rows, pl.tile_spans, pl.tile_span_stride, pl.vwarps, P);
     };
-    if (inner <= 64) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 2>));
-    else if (inner <= 128) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 4>));
-    else QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8>));
+    if (inner <= 64) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 4, 16>));
+    else if (inner <= 128) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8, 16>));
+    else QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8, 32>));
   } else if (pl.row_mode) {
     constexpr int kWarps = QSB_THREADS / 32;
     int64_t grid = (int64_t)device_props().sm_count * kRowCtasPerSm;
