@@ -292,11 +292,12 @@ int check_layout(int64_t outer, int64_t channels, int64_t inner) {
   return 0;
 }
 
-int check_mask(const uint8_t *mask, int kind) {
+// n: elements of the tensor — an empty tensor (and its empty mask) has no storage, a null pointer is fine
+int check_mask(const uint8_t *mask, int kind, int64_t n) {
   if (kind != QSB_MASK_NONE && kind != QSB_MASK_CHANNEL &&
       kind != QSB_MASK_ELEMENT)
     return QSB_E_BADARG;
-  if (kind != QSB_MASK_NONE && !mask) return QSB_E_BADARG;
+  if (kind != QSB_MASK_NONE && !mask && n != 0) return QSB_E_BADARG;
   return 0;
 }
 
@@ -337,7 +338,7 @@ extern "C" int qsb_fq_pow2_fwd(const float *x, float *y,
                                int mask_kind, int64_t outer, int64_t channels,
                                int64_t inner, void *stream) {
   if (int e = check_layout(outer, channels, inner)) return e;
-  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (int e = check_mask(mask_dev, mask_kind, outer * channels * inner)) return e;
   if (outer * channels * inner == 0) return 0;
   if (!x || !y) return QSB_E_BADARG;
   int stride = 0;
@@ -365,7 +366,7 @@ extern "C" int qsb_fq_scaler_fwd(const float *x, float *y,
                                  int mask_kind, int64_t outer, int64_t channels,
                                  int64_t inner, void *stream) {
   if (int e = check_layout(outer, channels, inner)) return e;
-  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (int e = check_mask(mask_dev, mask_kind, outer * channels * inner)) return e;
   if (outer * channels * inner == 0) return 0;
   if (!x || !y) return QSB_E_BADARG;
   int stride = 0;
@@ -391,7 +392,7 @@ extern "C" int qsb_fq_line_fwd(const float *x, float *y, const float *lines_dev,
                                int64_t outer, int64_t channels, int64_t inner,
                                void *stream) {
   if (int e = check_layout(outer, channels, inner)) return e;
-  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (int e = check_mask(mask_dev, mask_kind, outer * channels * inner)) return e;
   if (bits < 0 || bits > 62) return QSB_E_BADARG;
   if (outer * channels * inner == 0) return 0;
   if (!x || !y) return QSB_E_BADARG;
@@ -522,7 +523,7 @@ extern "C" int qsb_ste_bwd(const float *g, float *g_clamped_out, float *gx_out,
                            int64_t outer, int64_t channels, int64_t inner,
                            void *stream) {
   if (int e = check_layout(outer, channels, inner)) return e;
-  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (int e = check_mask(mask_dev, mask_kind, outer * channels * inner)) return e;
   if (outer * channels * inner == 0) return 0;
   if (!g) return QSB_E_BADARG;
   if (!g_clamped_out && !gx_out) return QSB_E_BADARG;
@@ -567,7 +568,7 @@ extern "C" int qsb_mask_apply(const float *x, float *y, const uint8_t *mask_dev,
                               int mask_kind, int64_t outer, int64_t channels,
                               int64_t inner, void *stream) {
   if (int e = check_layout(outer, channels, inner)) return e;
-  if (int e = check_mask(mask_dev, mask_kind)) return e;
+  if (int e = check_mask(mask_dev, mask_kind, outer * channels * inner)) return e;
   if (mask_kind == QSB_MASK_NONE) return QSB_E_BADARG;
   if (outer * channels * inner == 0) return 0;
   if (!x || !y) return QSB_E_BADARG;

@@ -153,6 +153,31 @@ def test_short_row_reductions(outer, C, inner, off):
     assert bits_equal(npy(again["abssum"]), npy(third["abssum"]))     # deterministic
 
 
+def test_empty_and_single_element_inputs():
+    """Degenerate sizes: an empty tensor passes through every functional entry point (the reference returns an empty
+    tensor: all its ops are elementwise); one element goes through the scalar tail of every kernel."""
+    from qsparse_b200 import ops
+    from qsparse_b200.quantize import quantize_with_decimal, quantize_with_scaler, quantize_with_line
+    e = torch.empty(0, device="cuda")
+    for y in (quantize_with_decimal(e, 8, 4), quantize_with_scaler(e, 8, 0.1), quantize_with_line(e, 8, (-0.1, 0.9))):
+        assert y.shape == (0,) and y.dtype == torch.float32
+    e4 = torch.empty(0, 3, 5, 5, device="cuda")
+    assert quantize_with_decimal(e4, 8, cu(np.array([1, 2, 3], np.float32)), 1).shape == (0, 3, 5, 5)
+    assert ops.mask_apply(e, torch.empty(0, dtype=torch.bool, device="cuda"), (1, 1, 0)).shape == (0,)
+    x1 = np.array([0.7391], np.float32)
+    assert bits_equal(npy(quantize_with_decimal(cu(x1), 8, 4)), orc.fq_pow2_fwd(x1, 4))
+    assert bits_equal(npy(quantize_with_scaler(cu(x1), 8, 0.013)), orc.fq_scaler_fwd(x1, np.float32(0.013)))
+    lines = np.array([[-0.2, 0.9]], np.float32)
+    assert bits_equal(npy(quantize_with_line(cu(x1), 8, (-0.2, 0.9))), orc.fq_line_fwd(x1, lines, 8, -1, True))
+    st = ops.reduce_stats(cu(x1), (1, 1, 1), absmax=True, minmax=True, abssum=True, nnz=True)
+    assert npy(st["absmax"])[0] == x1[0] and npy(st["min"])[0] == x1[0] and npy(st["max"])[0] == x1[0]
+    assert npy(st["abssum"])[0] == np.float64(x1[0]) and npy(st["nnz"])[0] == 1.0
+    assert npy(ops.kth_value(cu(x1), 0))[0] == x1[0]
+    g = cu(np.array([500.0], np.float32))
+    ops.ste_bwd(g, 0.0, True, 8, 0, (1, 1, 1))            # decimal 0, 8 bits: clamp to [-128, 127]
+    assert npy(g)[0] == 127.0
+
+
 def test_reduction_nan_propagates():
     from qsparse_b200 import ops
     x = rnd((4, 8, 100), 2)
