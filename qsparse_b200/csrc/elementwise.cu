@@ -46,6 +46,7 @@ struct SteOp {
   const uint8_t *cmask;
   struct P {
     float lo, hi, m;
+    bool zero_bound;  // a bound is +-0 (1-bit layers, a zero scale): the sign of a zero result matters
   };
   __device__ __forceinline__ P params(int32_t c) const {
     float s = scale_host;
@@ -56,6 +57,7 @@ struct SteOp {
     P p;
     p.lo = __fmul_rn(n_lo, s);
     p.hi = __fmul_rn(n_hi, s);
+    p.zero_bound = p.lo == 0.0f || p.hi == 0.0f;
     p.m = 1.0f;
     if constexpr (MASK == QSB_MASK_CHANNEL) p.m = __ldg(cmask + c) ? 1.0f : 0.0f;
     return p;
@@ -64,8 +66,9 @@ struct SteOp {
   __device__ __forceinline__ void apply(float g, float, uint8_t mb, const P &p,
                                         float &o0, float &o1, uint8_t &) const {
     // (:72-75) clamp with tensor bounds: NaN in g or in a bound gives NaN — exactly what the
-    // NaN-propagating FMNMX pair computes, in 2 instructions instead of 7
-    float v = clamp_fmnmx_nan(g, p.lo, p.hi);
+    // NaN-propagating FMNMX pair computes, in 2 instructions instead of 7.  FMNMX orders -0 < +0
+    // while torch's clamp keeps g when g == bound, so a zero bound takes the compare/select form.
+    float v = p.zero_bound ? clamp_torch_tensor(g, p.lo, p.hi) : clamp_fmnmx_nan(g, p.lo, p.hi);
     if (v != v) v = 0.0f;                         // (:76) fires only for NaN
     o0 = v;
     if constexpr (MASK == QSB_MASK_CHANNEL)

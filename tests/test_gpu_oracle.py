@@ -178,6 +178,33 @@ def test_empty_and_single_element_inputs():
     assert npy(g)[0] == 127.0
 
 
+@pytest.mark.parametrize("bits", [1, 2, 3, 12, 16, 24, 32])
+def test_bit_width_extremes(bits):
+    """The reference takes any bit width (its tests use 8 and 4): 2^bits - 1 is not representable in fp32 from 25
+    bits on, the line quantizer's step underflows the fast-division range, the STE bounds reach 2^31."""
+    from qsparse_b200 import ops
+    from qsparse_b200.quantize import quantize_with_line
+    x = rnd((3, 5, 41), 90 + bits, 2.0)
+    x.reshape(-1)[::53] *= 1e6
+    C = 5
+    rng = np.random.default_rng(bits)
+    lines = np.stack([rng.uniform(-2, -0.1, C), rng.uniform(0.1, 2, C)], 1).astype(np.float32)
+    for fzp in (True, False):
+        assert bits_equal(npy(quantize_with_line(cu(x), bits, cu(lines), 1, False, fzp)),
+                          orc.fq_line_fwd(x, lines, bits, 1, fzp)), fzp
+        assert bits_equal(npy(quantize_with_line(cu(x), bits, (-0.3, 1.1), -1, False, fzp)),
+                          orc.fq_line_fwd(x, np.array([[-0.3, 1.1]], np.float32), bits, -1, fzp)), fzp
+    g = rnd((3, 5, 41), 70 + bits, 3.0)
+    g.reshape(-1)[::31] *= 1e9
+    dec = rng.integers(-2, 7, C).astype(np.float32)
+    sc = rng.uniform(0.001, 0.05, C).astype(np.float32)
+    for scale, is_dec in ((dec, True), (sc, False)):
+        gc = cu(g).clone()
+        ops.ste_bwd(gc, cu(scale), is_dec, bits, 1, (3, 5, 41))
+        ref, _ = orc.ste_bwd(g, scale, bits, 1, is_dec, True)
+        assert bits_equal(npy(gc), ref), is_dec
+
+
 def test_reduction_nan_propagates():
     from qsparse_b200 import ops
     x = rnd((4, 8, 100), 2)
