@@ -205,6 +205,54 @@ def test_bit_width_extremes(bits):
         assert bits_equal(npy(gc), ref), is_dec
 
 
+def test_extreme_parameters_and_inputs():
+    """Decimals / scales / lines far outside the useful range (overflowing 2^d, zero / negative / infinite / NaN
+    scales, empty and inverted ranges) over inputs with +-0, +-inf, NaN, subnormals and huge values.  The oracle
+    equals the unmodified reference (CPU) on all of these; the kernels must equal the oracle, per tensor (host
+    parameter) and per channel (device parameters) — for the int32-based quantizers inside the documented parity
+    domain |x * 2^d| < 2^31 (outside it `.int()` is INT_MIN on x86 and saturates on CUDA, in the
+    reference as well)."""
+    from qsparse_b200.quantize import quantize_with_decimal, quantize_with_scaler, quantize_with_line
+    rng = np.random.default_rng(0)
+    decs = [-40.0, -1.0, 0.0, 30.0, 100.0, 126.0, 130.0]
+    scs = [1e-30, 3e37, -0.5, 0.0, float("inf"), float("nan"), 1e-42]
+    lns = [(0.0, 0.0), (1.0, 1.0), (0.5, -0.5), (0.0, 1e-30), (-1e30, 1e30), (0.0, float("inf")), (-0.3, 0.7)]
+    C = 7
+    x = (rng.standard_normal((3, C, 330)) * 2).astype(np.float32)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e38, -1e38, 1e-40, -1e-40, 3e9, -3e9, 0.5], np.float32)
+    x[:, :, :12] = special
+    x[:, :, 12:40] *= np.float32(1e-12)                   # something inside the domain for the large decimals
+    xc = cu(x)
+
+    def in_domain(q):
+        with np.errstate(all="ignore"):
+            return np.isfinite(q) & (np.abs(q) < 2.0 ** 31)
+
+    def check(got, exp, ok, what):
+        assert bits_equal(np.where(ok, npy(got), 0), np.where(ok, exp, 0)), what
+
+    with np.errstate(all="ignore"):
+        dv, sv = np.array(decs, np.float32), np.array(scs, np.float32)
+        check(quantize_with_decimal(xc, 8, cu(dv), 1), orc.fq_pow2_fwd(x, dv, 1),
+              in_domain(x * (np.float32(2.0) ** dv).reshape(1, C, 1)), "decimal per channel")
+        ok_s = in_domain(x / sv.reshape(1, C, 1))
+        ok_s[:, [5], :] = False                           # a NaN scale: nothing is in the domain
+        check(quantize_with_scaler(xc, 8, cu(sv), 1), orc.fq_scaler_fwd(x, sv, 1), ok_s, "scaler per channel")
+        for d in decs:
+            check(quantize_with_decimal(xc, 8, d), orc.fq_pow2_fwd(x, d), in_domain(x * np.float32(2.0) ** np.float32(d)),
+                  ("decimal", d))
+        for sc in scs[:5] + scs[6:]:
+            check(quantize_with_scaler(xc, 8, sc), orc.fq_scaler_fwd(x, np.float32(sc)), in_domain(x / np.float32(sc)),
+                  ("scaler", sc))
+    lines = np.array(lns, np.float32)
+    for fzp in (True, False):                             # no int32 in the line quantizer: the whole input range
+        assert bits_equal(npy(quantize_with_line(xc, 8, cu(lines), 1, False, fzp)),
+                          orc.fq_line_fwd(x, lines, 8, 1, fzp)), fzp
+        for ln in lns:
+            assert bits_equal(npy(quantize_with_line(xc, 8, ln, -1, False, fzp)),
+                              orc.fq_line_fwd(x, np.array([ln], np.float32), 8, -1, fzp)), (ln, fzp)
+
+
 def test_reduction_nan_propagates():
     from qsparse_b200 import ops
     x = rnd((4, 8, 100), 2)
