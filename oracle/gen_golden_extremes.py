@@ -1,0 +1,83 @@
+"""oracle/gen_golden_extremes.py — TEST INFRASTRUCTURE.
+
+Golden vectors for the corners the reference's own tests never visit, produced by the UNMODIFIED reference
+(mlzxy/qsparse v2.0.1, imported from /root/reference) on CPU tensors:
+
+  * decimals / scales / line ranges far outside the useful range (2^d overflowing, zero / negative / infinite /
+    NaN scales, empty and inverted ranges) over inputs with +-0, +-inf, NaN, subnormals and huge values;
+  * bit widths 1 ... 32 for the line quantizer and the straight-through backward (2^bits - 1 is not
+    representable in fp32 from 25 bits on; at 1 bit a clamp bound is +0.0 and the sign of a zero gradient shows).
+
+    python oracle/gen_golden_extremes.py        # rewrites tests/golden/extremes_v1.npz  (< 1 MB)
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from gen_golden import import_reference, OUT  # noqa: E402
+
+DECS = [-40.0, -1.0, 0.0, 30.0, 100.0, 126.0, 130.0]
+SCALES = [1e-30, 3e37, -0.5, 0.0, float("inf"), float("nan"), 1e-42]
+LINES = [(0.0, 0.0), (1.0, 1.0), (0.5, -0.5), (0.0, 1e-30), (-1e30, 1e30), (0.0, float("inf")), (-0.3, 0.7)]
+BITS = [1, 2, 3, 12, 16, 24, 32]
+SPECIAL = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e38, -1e38, 1e-40, -1e-40, 3e9, -3e9, 0.5], np.float32)
+
+
+def main():
+    qsparse = import_reference()
+    from qsparse.quantize import quantize_with_decimal, quantize_with_scaler, quantize_with_line
+    qsparse.set_qsparse_options(log_on_created=False)
+    rng = np.random.default_rng(20261018)
+    g = {}
+    C = len(DECS)
+    x = (rng.standard_normal((3, C, 330)) * 2).astype(np.float32)
+    x[:, :, :12] = SPECIAL
+    x[:, :, 12:40] *= np.float32(1e-12)
+    g["x"] = x
+    xt = torch.from_numpy(x)
+    g["decs"], g["scales"], g["lines"] = (np.array(DECS, np.float32), np.array(SCALES, np.float32),
+                                          np.array(LINES, np.float32))
+    g["pow2/ch"] = quantize_with_decimal(xt.clone(), 8, torch.tensor(DECS), 1).numpy()
+    g["scaler/ch"] = quantize_with_scaler(xt.clone(), 8, torch.tensor(SCALES), 1).numpy()
+    for i, d in enumerate(DECS):
+        g[f"pow2/t{i}"] = quantize_with_decimal(xt.clone(), 8, d).numpy()
+    for i, s in enumerate(SCALES):
+        g[f"scaler/t{i}"] = quantize_with_scaler(xt.clone(), 8, s).numpy()
+    for fzp in (True, False):
+        g[f"line/ch_fzp{int(fzp)}"] = quantize_with_line(xt.clone(), 8, torch.tensor(LINES), 1, False, fzp).numpy()
+        for i, ln in enumerate(LINES):
+            g[f"line/t{i}_fzp{int(fzp)}"] = quantize_with_line(xt.clone(), 8, ln, -1, False, fzp).numpy()
+
+    # bit widths
+    xb = (rng.standard_normal((3, 5, 41)) * 2).astype(np.float32)
+    xb.reshape(-1)[::53] *= 1e6
+    xb.reshape(-1)[[1, 2, 3, 4]] = [0.0, -0.0, 0.5, -0.5]
+    gb = (rng.standard_normal((3, 5, 41)) * 3).astype(np.float32)
+    gb.reshape(-1)[::31] *= 1e9
+    gb.reshape(-1)[[1, 2, 3, 4, 5]] = [0.0, -0.0, np.nan, np.inf, -np.inf]
+    g["bits/x"], g["bits/g"] = xb, gb
+    lines5 = np.stack([rng.uniform(-2, -0.1, 5), rng.uniform(0.1, 2, 5)], 1).astype(np.float32)
+    dec5 = rng.integers(-2, 7, 5).astype(np.float32)
+    sc5 = rng.uniform(0.001, 0.05, 5).astype(np.float32)
+    g["bits/lines"], g["bits/dec"], g["bits/scale"] = lines5, dec5, sc5
+    for b in BITS:
+        for fzp in (True, False):
+            g[f"bits/line_b{b}_fzp{int(fzp)}"] = quantize_with_line(
+                torch.from_numpy(xb), b, torch.from_numpy(lines5), 1, False, fzp).numpy()
+        for name, fn, par in (("dec", quantize_with_decimal, dec5), ("scale", quantize_with_scaler, sc5)):
+            for flip in (False, True):
+                xin = torch.from_numpy(xb).clone().requires_grad_(True)
+                go = torch.from_numpy(gb).clone()
+                fn(xin, b, torch.from_numpy(par), 1, False, False, flip).backward(go)
+                g[f"bits/bwd_{name}_b{b}_f{int(flip)}"] = go.numpy().copy()       # grad_output after the in-place clamp
+    np.savez_compressed(OUT / "extremes_v1.npz", **g)
+    print("wrote", OUT / "extremes_v1.npz", len(g), "arrays")
+
+
+if __name__ == "__main__":
+    main()

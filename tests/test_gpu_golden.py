@@ -245,3 +245,63 @@ def test_layer_flows(golden):
         assert np.array_equal(npy(qp.prune.mask), g["layer/qp_mask"])
         assert bits_equal(npy(qp.quantize.weight), g["layer/qp_scale"])
         assert not bits_equal(npy(qp._parameters["weight"]), npy(qp.weight))  # raw parameter untouched
+
+
+# ----------------------------------------------------------------------------- corners (oracle/gen_golden_extremes.py)
+@pytest.fixture(scope="module")
+def extremes():
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / "golden" / "extremes_v1.npz")
+
+
+def test_extreme_parameters_against_reference_goldens(extremes, q):
+    """The kernels against what the reference itself returned for overflowing decimals, degenerate scales and line
+    ranges over non-finite inputs.  The line quantizer has no int32 step: compared everywhere.  Decimal / scaler go
+    through `.int()`, which is INT_MIN on the reference's x86 run and saturating on CUDA (for the reference as
+    well): compared inside the documented domain |q| < 2^31."""
+    g = extremes
+    x = g["x"]
+    xc = cu(x)
+    C = x.shape[1]
+    for fzp in (True, False):
+        assert bits_equal(npy(q.quantize_with_line(xc, 8, cu(g["lines"]), 1, False, fzp)), g[f"line/ch_fzp{int(fzp)}"])
+        for i, ln in enumerate(g["lines"]):
+            got = q.quantize_with_line(xc, 8, (float(ln[0]), float(ln[1])), -1, False, fzp)
+            assert bits_equal(npy(got), g[f"line/t{i}_fzp{int(fzp)}"]), (i, fzp)
+
+    def inside(qv):
+        return np.isfinite(qv) & (np.abs(qv) < 2.0 ** 31)
+
+    with np.errstate(all="ignore"):
+        ok = inside(x * (np.float32(2.0) ** g["decs"]).reshape(1, C, 1))
+        got = npy(q.quantize_with_decimal(xc, 8, cu(g["decs"]), 1))
+        assert ok.mean() > 0.3 and bits_equal(np.where(ok, got, 0), np.where(ok, g["pow2/ch"], 0))
+        ok = inside(x / g["scales"].reshape(1, C, 1))
+        got = npy(q.quantize_with_scaler(xc, 8, cu(g["scales"]), 1))
+        assert ok.mean() > 0.3 and bits_equal(np.where(ok, got, 0), np.where(ok, g["scaler/ch"], 0))
+        for i, d in enumerate(g["decs"]):
+            ok = inside(x * np.float32(2.0) ** d)
+            got = npy(q.quantize_with_decimal(xc, 8, float(d)))
+            assert bits_equal(np.where(ok, got, 0), np.where(ok, g[f"pow2/t{i}"], 0)), d
+        for i, s in enumerate(g["scales"]):
+            if np.isnan(s):
+                continue
+            ok = inside(x / s)
+            got = npy(q.quantize_with_scaler(xc, 8, float(s)))
+            assert bits_equal(np.where(ok, got, 0), np.where(ok, g[f"scaler/t{i}"], 0)), s
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 12, 16, 24, 32])
+def test_bit_width_extremes_against_reference_goldens(extremes, q, bits):
+    """1 ... 32 bits through the public functions: line forward, and the in-place clamp of grad_output by the
+    straight-through backward (at 1 bit a bound is +0.0: the reference keeps a -0.0 gradient, FMNMX would not)."""
+    g = extremes
+    x, gr = g["bits/x"], g["bits/g"]
+    for fzp in (True, False):
+        got = q.quantize_with_line(cu(x), bits, cu(g["bits/lines"]), 1, False, fzp)
+        assert bits_equal(npy(got), g[f"bits/line_b{bits}_fzp{int(fzp)}"]), fzp
+    for name, fn, par in (("dec", q.quantize_with_decimal, g["bits/dec"]),
+                          ("scale", q.quantize_with_scaler, g["bits/scale"])):
+        for flip in (False, True):
+            _, go = _run_bwd(fn, x, gr, bits, cu(par), 1, False, False, flip)
+            assert bits_equal(go, g[f"bits/bwd_{name}_b{bits}_f{int(flip)}"]), (name, flip)

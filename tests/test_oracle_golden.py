@@ -167,3 +167,40 @@ def test_oracle_layer_emulators_match_reference_layers(golden):
         out = em.forward(g["layer/px"])
         assert bits_equal(out, g["layer/p_out"][t]), t
         assert np.array_equal(em.mask, g["layer/p_mask"][t]), t
+
+
+# ----------------------------------------------------------------------------- corners (oracle/gen_golden_extremes.py)
+@pytest.fixture(scope="module")
+def extremes():
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / "golden" / "extremes_v1.npz")
+
+
+def test_extreme_parameters_forward(extremes):
+    """Overflowing decimals, zero / negative / infinite / NaN scales, empty and inverted line ranges over +-0, +-inf,
+    NaN, subnormal and huge inputs: the oracle equals the reference everywhere, including where `.int()` is out of
+    range (x86 semantics: INT_MIN)."""
+    g = extremes
+    x = g["x"]
+    assert bits_equal(orc.fq_pow2_fwd(x, g["decs"], 1), g["pow2/ch"])
+    assert bits_equal(orc.fq_scaler_fwd(x, g["scales"], 1), g["scaler/ch"])
+    for i, d in enumerate(g["decs"]):
+        assert bits_equal(orc.fq_pow2_fwd(x, float(d)), g[f"pow2/t{i}"]), d
+    for i, s in enumerate(g["scales"]):
+        assert bits_equal(orc.fq_scaler_fwd(x, np.float32(s)), g[f"scaler/t{i}"]), s
+    for fzp in (True, False):
+        assert bits_equal(orc.fq_line_fwd(x, g["lines"], 8, 1, fzp), g[f"line/ch_fzp{int(fzp)}"]), fzp
+        for i, ln in enumerate(g["lines"]):
+            assert bits_equal(orc.fq_line_fwd(x, ln.reshape(1, 2), 8, -1, fzp), g[f"line/t{i}_fzp{int(fzp)}"]), (i, fzp)
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 12, 16, 24, 32])
+def test_bit_width_extremes(extremes, bits):
+    g = extremes
+    for fzp in (True, False):
+        assert bits_equal(orc.fq_line_fwd(g["bits/x"], g["bits/lines"], bits, 1, fzp),
+                          g[f"bits/line_b{bits}_fzp{int(fzp)}"]), fzp
+    for name, par, is_dec in (("dec", g["bits/dec"], True), ("scale", g["bits/scale"], False)):
+        for flip in (False, True):
+            got, _ = orc.ste_bwd(g["bits/g"], par, bits, 1, is_dec, flip)
+            assert bits_equal(got, g[f"bits/bwd_{name}_b{bits}_f{int(flip)}"]), (name, flip)
