@@ -6,7 +6,8 @@ Golden vectors for the corners the reference's own tests never visit, produced b
   * decimals / scales / line ranges far outside the useful range (2^d overflowing, zero / negative / infinite /
     NaN scales, empty and inverted ranges) over inputs with +-0, +-inf, NaN, subnormals and huge values;
   * bit widths 1 ... 32 for the line quantizer and the straight-through backward (2^bits - 1 is not
-    representable in fp32 from 25 bits on; at 1 bit a clamp bound is +0.0 and the sign of a zero gradient shows).
+    representable in fp32 from 25 bits on; at 1 bit a clamp bound is +0.0 and the sign of a zero gradient shows);
+  * calculate_mask_given_importance on NaN / inf / constant / one- and two-element importances at sparsity 0 ... 1.
 
     python oracle/gen_golden_extremes.py        # rewrites tests/golden/extremes_v1.npz  (< 1 MB)
 """
@@ -25,6 +26,7 @@ DECS = [-40.0, -1.0, 0.0, 30.0, 100.0, 126.0, 130.0]
 SCALES = [1e-30, 3e37, -0.5, 0.0, float("inf"), float("nan"), 1e-42]
 LINES = [(0.0, 0.0), (1.0, 1.0), (0.5, -0.5), (0.0, 1e-30), (-1e30, 1e30), (0.0, float("inf")), (-0.3, 0.7)]
 BITS = [1, 2, 3, 12, 16, 24, 32]
+MASK_SPARSITIES = [0.0, 0.3, 0.5, 0.75, 0.999, 1.0]
 SPECIAL = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e38, -1e38, 1e-40, -1e-40, 3e9, -3e9, 0.5], np.float32)
 
 
@@ -75,6 +77,25 @@ def main():
                 go = torch.from_numpy(gb).clone()
                 fn(xin, b, torch.from_numpy(par), 1, False, False, flip).backward(go)
                 g[f"bits/bwd_{name}_b{b}_f{int(flip)}"] = go.numpy().copy()       # grad_output after the in-place clamp
+    # masks from importances with NaN / inf / constant / tiny tensors at the ends of the sparsity range
+    from qsparse.util import calculate_mask_given_importance
+    base = rng.standard_normal(1000).astype(np.float32)
+    nan7 = base.copy()
+    nan7[::7] = np.nan
+    infs = base.copy()
+    infs[:5] = [np.inf, -np.inf, np.inf, 0.0, -0.0]
+    mask_cases = {"normal": base, "nan": nan7, "inf": infs, "allnan": np.full(64, np.nan, np.float32),
+                  "const": np.full(100, 0.25, np.float32), "two": np.array([3.0, 1.0], np.float32),
+                  "one": np.array([3.0], np.float32)}
+    g["mask/names"] = np.array(list(mask_cases))
+    g["mask/sparsities"] = np.array(MASK_SPARSITIES)
+    for name, v in mask_cases.items():
+        g[f"mask/{name}/imp"] = v
+        for i, sp in enumerate(MASK_SPARSITIES):
+            try:
+                g[f"mask/{name}/s{i}"] = calculate_mask_given_importance(torch.from_numpy(v), sp).numpy()
+            except IndexError:
+                g[f"mask/{name}/s{i}"] = np.array([-1], np.int8)          # the reference raises IndexError
     np.savez_compressed(OUT / "extremes_v1.npz", **g)
     print("wrote", OUT / "extremes_v1.npz", len(g), "arrays")
 

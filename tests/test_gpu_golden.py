@@ -305,3 +305,17 @@ def test_bit_width_extremes_against_reference_goldens(extremes, q, bits):
         for flip in (False, True):
             _, go = _run_bwd(fn, x, gr, bits, cu(par), 1, False, False, flip)
             assert bits_equal(go, g[f"bits/bwd_{name}_b{bits}_f{int(flip)}"]), (name, flip)
+
+
+def test_mask_corner_cases_against_reference_goldens(extremes):
+    from qsparse_b200.util import calculate_mask_given_importance
+    g = extremes
+    for name in g["mask/names"]:
+        imp = cu(g[f"mask/{name}/imp"])
+        for i, sp in enumerate(g["mask/sparsities"]):
+            exp = g[f"mask/{name}/s{i}"]
+            if exp.dtype == np.int8:
+                with pytest.raises(IndexError):
+                    calculate_mask_given_importance(imp, float(sp))
+            else:
+                assert np.array_equal(npy(calculate_mask_given_importance(imp, float(sp))), exp), (name, sp)

@@ -204,3 +204,18 @@ def test_bit_width_extremes(extremes, bits):
         for flip in (False, True):
             got, _ = orc.ste_bwd(g["bits/g"], par, bits, 1, is_dec, flip)
             assert bits_equal(got, g[f"bits/bwd_{name}_b{bits}_f{int(flip)}"]), (name, flip)
+
+
+def test_mask_corner_cases(extremes):
+    """NaN / inf / constant / tiny importances at sparsity 0 ... 1: same mask, or IndexError where the reference
+    raises it."""
+    g = extremes
+    for name in g["mask/names"]:
+        imp = g[f"mask/{name}/imp"]
+        for i, sp in enumerate(g["mask/sparsities"]):
+            exp = g[f"mask/{name}/s{i}"]
+            if exp.dtype == np.int8:
+                with pytest.raises(IndexError):
+                    orc.mask_given_importance(imp, float(sp))
+            else:
+                assert np.array_equal(orc.mask_given_importance(imp, float(sp))[0], exp), (name, sp)
