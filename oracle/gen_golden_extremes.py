@@ -96,6 +96,11 @@ def main():
                 g[f"mask/{name}/s{i}"] = calculate_mask_given_importance(torch.from_numpy(v), sp).numpy()
             except IndexError:
                 g[f"mask/{name}/s{i}"] = np.array([-1], np.int8)          # the reference raises IndexError
+    # scale -> decimal on degenerate scales: round(log2(nan_to_num(1/s, posinf=1, neginf=1)))  (quantize.py:316)
+    sd = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 1e-40, -0.5, -1e-30, 3e38, 1.0, 0.7071068, 1.4142135,
+                   2.0 ** -126, 2.0 ** 127, 2.0 ** -149, 1.1754942e-38, 0.1, 3.0], np.float32)
+    g["s2d/scales"] = sd
+    g["s2d/decimals"] = (1 / torch.from_numpy(sd.copy())).nan_to_num(posinf=1, neginf=1).log2().round().numpy()
     np.savez_compressed(OUT / "extremes_v1.npz", **g)
     print("wrote", OUT / "extremes_v1.npz", len(g), "arrays")
 

@@ -319,3 +319,9 @@ def test_mask_corner_cases_against_reference_goldens(extremes):
                     calculate_mask_given_importance(imp, float(sp))
             else:
                 assert np.array_equal(npy(calculate_mask_given_importance(imp, float(sp))), exp), (name, sp)
+
+
+def test_scale_to_decimal_degenerate_scales_against_reference_goldens(extremes):
+    from qsparse_b200 import ops
+    got = ops.scale_to_decimal(cu(extremes["s2d/scales"]))
+    assert bits_equal(npy(got).reshape(-1), extremes["s2d/decimals"])

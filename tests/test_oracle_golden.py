@@ -219,3 +219,8 @@ def test_mask_corner_cases(extremes):
                     orc.mask_given_importance(imp, float(sp))
             else:
                 assert np.array_equal(orc.mask_given_importance(imp, float(sp))[0], exp), (name, sp)
+
+
+def test_scale_to_decimal_degenerate_scales(extremes):
+    """zero / infinite / NaN / negative / subnormal scales: 1/s overflows to the nan_to_num replacement values."""
+    assert bits_equal(orc.scale_to_decimal(extremes["s2d/scales"]), extremes["s2d/decimals"])
