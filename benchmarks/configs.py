@@ -1,0 +1,673 @@
+"""BASELINE.json configurations 3, 4 and 5 for bench.py (`python bench.py --config N`), same JSON schema
+as the headline configuration (roofline, cpu_baseline, e2e, clocks, gpu_launches).
+
+  3  channel-wise 4-bit weight quantization of a [4096, 4096] linear weight, adaptive (min/max) scale
+     estimation: one training access of the weight = estimate -> EMA -> line fake-quant
+     (ref qsparse/quantize.py:140-185, 393-430).  Weights are replicated under data parallelism: at
+     N > 1 every rank runs the same access ("replicas only", no collective).
+  4  unstructured magnitude prune (running-average statistics, exact k-th value mask) of a 64 Mi
+     element conv weight set (28 x [512,512,3,3] + remainder), one step = EMA + threshold + mask + apply
+     per layer (ref qsparse/sparse.py:58-66,82-89, util.py:103-117).  N > 1: replicated one-pass step
+     (no communication) and, reported beside it, the layer-sharded select + one all-reduce of thresholds.
+  5  element-wise fused prune(mask) + pow2 fake-quant forward and backward over flat tensors of
+     2^20 .. 2^32 elements (ref qsparse/quantize.py:43-77 + sparse.py:116); N GPUs each on its own
+     shard (weak: n per GPU fixed; --strong: n / N per GPU), no collective.
+
+Timing: CUDA events on the launching stream around every step, a clean-line L2 flush (512 MB write +
+384 MB read) between steps whenever the step's tensors fit the 126 MB L2, max over ranks.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+L2_BYTES = 126 * 1024 * 1024
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class Flusher:
+    def __init__(self, torch, dev):
+        self.w = torch.zeros(128 * 1024 * 1024, device=dev)   # 512 MB written ...
+        self.r = torch.zeros(96 * 1024 * 1024, device=dev)    # ... then 384 MB read: L2 holds clean lines
+
+    def __call__(self):
+        self.w.add_(1.0)
+        self.r.max()
+
+
+def timed(torch, fn, steps, warmup, flush=None, world=1, dev=None):
+    """ms per step (sum of per-step CUDA-event intervals; the flush sits outside them), max over ranks"""
+    dist = _dist()
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s, e in ev:
+        if flush is not None:
+            flush()
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    ms = sum(s.elapsed_time(e) for s, e in ev) / steps
+    if dist:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        dist.barrier()
+    return ms
+
+
+def back_to_back(torch, fn, steps, warmup, world=1, dev=None):
+    """ms per step of `steps` calls issued back to back (one event pair around all of them)"""
+    dist = _dist()
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    if dist:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        dist.barrier()
+    return ms
+
+
+def _prof():
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return {}
+
+
+def _base(metric, value, world, args, ms, cfg, n_units, clocks, scaling="weak"):
+    return {"metric": metric, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "elems_per_s": round(n_units / (ms * 1e-3), 1), "clocks": clocks}
+
+
+# ============================================================================= config 3
+C3_SHAPE = (4096, 4096)
+C3_BITS = 4
+C3_METRIC = "channelwise 4-bit weight quantize (adaptive estimate + line fake-quant) HBM GB/s"
+
+
+def c3_config():
+    return {"workload": "config[2]: [4096,4096] fp32 linear weight, bits=4, channelwise=0, AdaptiveQuantizer: one training "
+                        "access = per-row min/max -> EMA -> line fake-quant, fused in ONE row-resident launch "
+                        "(8 B/elem: one read + one write; the reference's algorithm re-reads the tensor: 12 B/elem)",
+            "shape_per_gpu": list(C3_SHAPE), "bits": C3_BITS, "parallelism": "replicas only (weights are replicated under "
+            "data parallelism; no collective)", "l2": "67 MB tensor fits the 126 MB L2: clean-line flush (512 MB write + "
+            "384 MB read) between timed steps; the L2-warm figure is reported beside it"}
+
+
+def run_c3(args, env):
+    import torch
+    import qsparse_b200 as q
+    from qsparse_b200 import ops
+    world, rank, dev = env["world"], env["rank"], env["dev"]
+    peak, peak_src = env["peak"]
+    n = C3_SHAPE[0] * C3_SHAPE[1]
+    torch.manual_seed(3)
+    w = torch.randn(C3_SHAPE, device=dev) * 0.02
+    lines = torch.zeros(C3_SHAPE[0], 2, device=dev)
+    state = {"t": 1}
+
+    def step():
+        ops.row_quant_fused_(w, lines, ops.ROW_LINE, C3_BITS, state["t"], True)
+        state["t"] += 1
+
+    flush = Flusher(torch, dev)
+    sampler = env["sampler_cls"](dev.index)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    steps = min(args.steps, 400)
+    ms = timed(torch, step, steps, args.warmup, flush, world, dev)
+    ms_warm = back_to_back(torch, step, steps, args.warmup, world, dev)
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < 0.6:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    # the three-launch route of the same access (what the un-fused path costs)
+    lines3 = torch.zeros_like(lines)
+    wy = torch.empty_like(w)
+
+    def step3():
+        st_ = ops.reduce_stats(w, (1, C3_SHAPE[0], C3_SHAPE[1]), minmax=True)
+        ops.lines_ema_(lines3, st_["min"], st_["max"], 2)
+        ops.fq_line_fwd(w, lines3, C3_BITS, True, (1, C3_SHAPE[0], C3_SHAPE[1]), out=wy)
+    ms3 = timed(torch, step3, min(steps, 100), 3, flush, world, dev)
+
+    # module API: quantize(nn.Linear, bits=4, channelwise=0, timeout=1, AdaptiveQuantizer()).weight in training
+    q.set_qsparse_options(log_on_created=False)
+    lin = torch.nn.Linear(C3_SHAPE[1], C3_SHAPE[0], bias=False).to(dev)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    ql = q.quantize(lin, bits=C3_BITS, channelwise=0, timeout=1, callback=q.AdaptiveQuantizer()).train()
+    with torch.no_grad():
+        _ = ql.weight
+        _ = ql.weight
+
+        def mod_step():
+            return ql.weight
+        ms_mod = timed(torch, mod_step, min(steps, 100), 3, flush, world, dev)
+        yq = ql.weight
+    # parity against the raw kernel on the same EMA state is covered by tests; here: same shape, finite
+    assert yq.shape == w.shape and bool(torch.isfinite(yq).all().item())
+
+    # e2e: pinned host weight in, quantized weight out, through the module API
+    hw = torch.empty(C3_SHAPE, dtype=torch.float32).pin_memory()
+    hw.copy_(w)
+    hy = torch.empty(C3_SHAPE, dtype=torch.float32).pin_memory()
+    e2e_steps = max(4, min(args.steps, 20))
+
+    def e2e_step():
+        with torch.no_grad():
+            lin.weight.copy_(hw, non_blocking=True)
+            hy.copy_(ql.weight, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    dist = _dist()
+    if dist:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+
+    gpu_eager = cpu = None
+    if world == 1 and not args.no_gpu_eager:
+        from oracle.torch_eager import WeightLineQuantEager
+        eg = WeightLineQuantEager(C3_BITS)
+        ms_e = timed(torch, lambda: eg.forward(w), 20, 3, flush, 1, dev)
+        gpu_eager = {"what": "the reference's eager ATen sequence (min, max, cat, EMA, clamp, sub, div, round, clamp_, mul, add)",
+                     "ms_per_step": round(ms_e, 4), "value": round(8 * n / (ms_e * 1e-3) / 1e9, 2), "unit": "GB/s",
+                     "speedup_of_this_repo": round(ms_e / ms, 2)}
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_c3(env["host_threads"], 5)
+    prof = _prof()
+    value = world * 8 * n / (ms * 1e-3) / 1e9
+    line = _base(C3_METRIC, value, world, args, ms, c3_config(), world * n, clocks)
+    line["steps"] = steps
+    line.update({
+        "frac_of_measured_hbm_peak": round(value / world / peak, 4),
+        "value_actual": round(value, 2),
+        "value_on_reference_algorithm_bytes": round(world * 12 * n / (ms * 1e-3) / 1e9, 2),
+        "bytes_per_elem": {"algorithmic": 8, "actual": 8, "reference_algorithm": 12},
+        "l2_warm": {"ms_per_step": round(ms_warm, 5), "value": round(world * 8 * n / (ms_warm * 1e-3) / 1e9, 2)},
+        "three_launch_route": {"ms_per_step": round(ms3, 5), "what": "reduce_stats(minmax) + lines_ema + fq_line_fwd (12 B/elem)"},
+        "module_api": {"api": "quantize(nn.Linear, bits=4, channelwise=0, timeout=1, AdaptiveQuantizer()).weight",
+                       "ms_per_step": round(ms_mod, 5), "value": round(world * 8 * n / (ms_mod * 1e-3) / 1e9, 2)},
+        "launch_mode": "eager, one launch per step (row_quant_kernel)",
+        "gpu_launches": steps,
+        "e2e": {"value": round(world * 8 * n / e2e_s / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": 4 * n * world,
+                "d2h_bytes_per_step": 4 * n * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
+                "api": "pinned host weight -> layer.weight.copy_ -> quantize(...).weight (module API) -> pinned host"},
+        "roofline": {"bound": "hbm", "kernel": "row_quant_kernel<LINE> (row-resident estimate + EMA + line fake-quant)",
+                     "achieved": round(8 * n / (ms * 1e-3) / 1e9, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": round(8 * n / (ms * 1e-3) / 1e9 / peak, 4), "traffic": prof.get("row_quant_line_dram_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": 8 * n, "avg_launch_us": round(ms * 1e3, 2)},
+        "gpu_eager_baseline": gpu_eager, "cpu_baseline": cpu,
+    })
+    return line
+
+
+def cpu_c3(threads, steps):
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    w = (rng.standard_normal(C3_SHAPE, dtype=np.float32) * np.float32(0.02))
+    rows = C3_SHAPE[0]
+    threads = max(1, min(threads, rows))
+    sl = [slice(i * rows // threads, (i + 1) * rows // threads) for i in range(threads)]
+    pool = ThreadPoolExecutor(threads)
+    lines = np.zeros((rows, 2), np.float32)
+    st = {"t": 1}
+
+    def part(s):
+        mn, mx = orc.minmax(w[s], 0)
+        lines[s] = orc.lines_ema(lines[s], mn, mx, st["t"])
+        return orc.fq_line_fwd(w[s], lines[s], C3_BITS, 0, True)
+
+    def step():
+        list(pool.map(part, sl))
+        st["t"] += 1
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    n = w.size
+    return {"value": round(8 * n / dt / 1e9, 3), "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} accesses of the full [4096,4096] weight, row-sliced over the threads, {dt*1e3:.1f} ms/step",
+            "elems_per_s": round(n / dt, 1), "ms_per_step": round(dt * 1e3, 3)}
+
+
+# ============================================================================= config 4
+C4_TOTAL = 1 << 26
+C4_METRIC = "unstructured magnitude prune step (EMA + k-th value mask + apply) HBM GB/s"
+
+
+def c4_shapes():
+    shapes = [(512, 512, 3, 3)] * 28
+    rest = C4_TOTAL - sum(512 * 512 * 9 for _ in shapes)
+    shapes.append((rest // 4096, 4096))
+    return shapes
+
+
+def c4_config(sparsity):
+    return {"workload": f"config[3]: 64 Mi-element conv weight set (28 x [512,512,3,3] + [256,4096]), unstructured magnitude "
+                        f"prune at sparsity {sparsity:g}, running-average statistics, exact k-th value threshold per layer: "
+                        "EMA 12 + select 4 + mask/apply 13 = 29 B/elem in the reference's algorithm; here ONE streaming "
+                        "pass (~17.5 B/elem of traffic) + candidate passes + fix-up",
+            "elements": C4_TOTAL, "layers": 29, "sparsity": sparsity,
+            "parallelism": "weights are replicated under data parallelism: every rank runs the one-pass step on all "
+                           "layers (no communication; thresholds are exact, so ranks agree bit for bit); the layer-sharded "
+                           "select + all-reduce route is timed beside it",
+            "l2": "268 MB per tensor kind exceeds the 126 MB L2; no flush"}
+
+
+def run_c4(args, env):
+    import torch
+    from qsparse_b200 import ops, parallel
+    from qsparse_b200.util import kth_rank
+    world, rank, dev = env["world"], env["rank"], env["dev"]
+    peak, peak_src = env["peak"]
+    sparsity = 0.5 if args.sparsity is None else args.sparsity
+    torch.manual_seed(4)
+    ws = [torch.randn(s, device=dev) * 0.02 for s in c4_shapes()]
+    mags = [w.abs() * 0.9 for w in ws]
+    masks = [torch.ones(w.shape, dtype=torch.bool, device=dev) for w in ws]
+    outs = [torch.empty_like(w) for w in ws]
+    n = sum(w.numel() for w in ws)
+    state = {"t": 3}
+
+    def step():
+        parallel.prune_weight_set_step(ws, mags, masks, outs, state["t"], sparsity)
+        state["t"] += 1
+
+    def step_sharded():
+        parallel.prune_weight_set_step(ws, mags, masks, outs, state["t"], sparsity, shard_by_layer=True)
+        state["t"] += 1
+
+    sampler = env["sampler_cls"](dev.index)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    steps = min(args.steps, 200)
+    ms = back_to_back(torch, step, steps, args.warmup, world, dev)
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < 0.6:
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_sh = back_to_back(torch, step_sharded, min(steps, 50), 3, world, dev)
+    # graph: the whole step as one captured CUDA graph (launch-gap free)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        parallel.prune_weight_set_step(ws, mags, masks, outs, 3, sparsity)
+    torch.cuda.current_stream().wait_stream(side)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        parallel.prune_weight_set_step(ws, mags, masks, outs, 3, sparsity)
+    ms_graph = back_to_back(torch, gr.replay, min(steps, 100), 3, world, dev)
+
+    # correctness inside the bench: masks equal torch.sort's threshold on two layers; ranks agree bit for bit
+    ok = True
+    for i in (0, 28):
+        kk = kth_rank(sparsity, mags[i].numel())
+        thr = torch.sort(mags[i].reshape(-1)).values[kk]
+        ok = ok and bool(torch.equal(masks[i], mags[i] >= thr)) and bool(torch.equal(outs[i], ws[i] * masks[i]))
+    dist = _dist()
+    ranks_equal = None
+    if dist:
+        digest = torch.stack([m.view(torch.uint8).sum(dtype=torch.int64) for m in masks])
+        got = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(got, digest)
+        ranks_equal = all(torch.equal(got[0], g_) for g_ in got)
+        ok = ok and ranks_equal
+
+    # module API: MagnitudePruningCallback per layer (the reference's own call)
+    from qsparse_b200.sparse import MagnitudePruningCallback
+    cbs = [MagnitudePruningCallback(running_average=True).train() for _ in ws]
+    cmasks = [torch.nn.Parameter(torch.ones(w.shape, dtype=torch.bool, device=dev), requires_grad=False) for w in ws]
+
+    def mod_step():
+        with torch.no_grad():
+            for cb, w, m in zip(cbs, ws, cmasks):
+                cb(w, sparsity, m)
+    ms_mod = back_to_back(torch, mod_step, min(steps, 20), 3, world, dev)
+    del cbs, cmasks
+
+    # e2e: pinned host weights in, pruned weights + masks out
+    hws = [torch.empty(w.shape, dtype=torch.float32).pin_memory() for w in ws]
+    hos = [torch.empty(w.shape, dtype=torch.float32).pin_memory() for w in ws]
+    for h, w in zip(hws, ws):
+        h.copy_(w)
+    e2e_steps = max(2, min(args.steps, 6))
+
+    def e2e_step():
+        for w, h in zip(ws, hws):
+            w.copy_(h, non_blocking=True)
+        step()
+        for h, o in zip(hos, outs):
+            h.copy_(o, non_blocking=True)
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    del hws, hos
+
+    gpu_eager = cpu = None
+    if world == 1 and not args.no_gpu_eager:
+        from oracle.torch_eager import UnstructuredPruneEager
+        egs = [UnstructuredPruneEager(w, sparsity) for w in ws]
+        for e_ in egs:
+            e_.t = 3
+
+        def eager_step():
+            for e_, w in zip(egs, ws):
+                e_.forward(w)
+        ms_e = back_to_back(torch, eager_step, 5, 2, 1, dev)
+        gpu_eager = {"what": "the reference's eager ATen sequence per layer (abs, mul, add, div, copy, flatten, sort, ge, copy, mul)",
+                     "ms_per_step": round(ms_e, 4), "value": round(29 * n / (ms_e * 1e-3) / 1e9, 2), "unit": "GB/s",
+                     "speedup_of_this_repo": round(ms_e / ms, 2)}
+        del egs
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_c4(env["host_threads"], sparsity)
+    prof = _prof()
+    value = world * 29 * n / (ms * 1e-3) / 1e9
+    traffic_bpe = 17.5
+    line = _base(C4_METRIC, value, world, args, ms, c4_config(sparsity), world * n, clocks)
+    line["steps"] = steps
+    line.update({
+        "frac_of_measured_hbm_peak": round(value / world / peak, 4),
+        "value_actual": round(world * traffic_bpe * n / (ms * 1e-3) / 1e9, 2),
+        "frac_actual": round(traffic_bpe * n / (ms * 1e-3) / 1e9 / peak, 4),
+        "bytes_per_elem": {"algorithmic": 29, "actual": traffic_bpe,
+                           "note": "value is quoted on the reference algorithm's 29 B/elem (SURVEY 8d); the one-pass step "
+                                   "really moves ~17.5 B/elem (R w, R mag, W mag, W y, 1 B W mask + candidates): value_actual"},
+        "masks_equal_sort_threshold": ok, "ranks_bit_equal": ranks_equal,
+        "cuda_graph": {"ms_per_step": round(ms_graph, 5), "value": round(world * 29 * n / (ms_graph * 1e-3) / 1e9, 2)},
+        "layer_sharded_select": {"ms_per_step": round(ms_sh, 5), "value": round(world * 29 * n / (ms_sh * 1e-3) / 1e9, 2),
+                                 "what": "replicated multi-tensor EMA + per-rank batched select on owned layers + all-reduce "
+                                         "of 29 thresholds + replicated multi-tensor mask/apply"},
+        "module_api": {"api": "MagnitudePruningCallback(running_average=True)(w, sparsity, mask) per layer",
+                       "ms_per_step": round(ms_mod, 5), "value": round(world * 29 * n / (ms_mod * 1e-3) / 1e9, 2)},
+        "launch_mode": "eager (sampler, streaming pass, 3 candidate passes, fix-up, gated full pass)",
+        "gpu_launches": 7 * steps,
+        "e2e": {"value": round(world * 29 * n / e2e_s / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": 4 * n * world,
+                "d2h_bytes_per_step": 4 * n * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
+                "api": "pinned host weights -> device -> parallel.prune_weight_set_step -> pruned weights to pinned host"},
+        "roofline": {"bound": "hbm", "kernel": "step_partition_kernel (EMA + provisional mask + apply + candidate append, one pass)",
+                     "achieved": round(traffic_bpe * n / (ms * 1e-3) / 1e9, 1), "peak": peak, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(traffic_bpe * n / (ms * 1e-3) / 1e9 / peak, 4),
+                     "traffic": prof.get("step_partition_dram_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": int(traffic_bpe * n), "avg_launch_us": round(ms * 1e3, 2),
+                     "note": "whole-step time over the streaming pass's bytes: the sampler, candidate passes and fix-up "
+                             "(~25 % of the step) are charged to it"},
+        "gpu_eager_baseline": gpu_eager, "cpu_baseline": cpu,
+    })
+    return line
+
+
+def cpu_c4(threads, sparsity):
+    """bounded sample: `threads` layers of [512,512,3,3] (one per thread): EMA + sort-based mask + apply"""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    layers = max(1, min(threads, 8))
+    rng = np.random.default_rng(4)
+    ws = [(rng.standard_normal((512, 512, 3, 3), dtype=np.float32) * np.float32(0.02)) for _ in range(layers)]
+    mags = [np.abs(w) * np.float32(0.9) for w in ws]
+    pool = ThreadPoolExecutor(layers)
+
+    def one(i):
+        mags[i] = orc.magnitude_ema(mags[i].reshape(-1), np.abs(ws[i]).reshape(-1), 3).reshape(ws[i].shape)
+        mask, _ = orc.mask_given_importance(mags[i].reshape(-1), sparsity)
+        return orc.mask_apply(ws[i].reshape(-1), mask.reshape(-1), -1)
+
+    t0 = time.perf_counter()
+    list(pool.map(one, range(layers)))
+    dt = time.perf_counter() - t0
+    n = sum(w.size for w in ws)
+    return {"value": round(29 * n / dt / 1e9, 3), "unit": "GB/s", "cores": layers, "kind": "port",
+            "sample": f"one step over {layers} of the 29 layers ([512,512,3,3] each, one per thread; qsort-based threshold), "
+                      f"{dt:.1f} s", "elems_per_s": round(n / dt, 1)}
+
+
+# ============================================================================= config 5
+C5_METRIC = "elementwise fake-quant+prune fwd/bwd HBM GB/s"
+
+
+def c5_config(strong, sizes):
+    return {"workload": "config[4]: flat fp32 tensors, fused prune (element mask given) + 8-bit pow2 fake-quant forward "
+                        "(R x, R mask, W y = 9 B/elem) and backward (R g, R mask, W gx = 9 B/elem), 2^20 .. 2^32 elements",
+            "log2_sizes": sizes, "headline_size": "2^30 elements per GPU" if not strong else "2^32 elements over all GPUs",
+            "parallelism": "independent shards, no collective (" + ("strong: total fixed" if strong else "weak: n per GPU fixed") + ")",
+            "l2": "clean-line flush between timed launches for tensors that fit the 126 MB L2 (n <= 2^24)"}
+
+
+def run_c5(args, env):
+    import torch
+    from qsparse_b200 import ops
+    world, rank, dev = env["world"], env["rank"], env["dev"]
+    peak, peak_src = env["peak"]
+    sizes = [20, 22, 24, 26, 28, 30, 32]
+    headline = 32 if args.strong else 30
+    dec = torch.tensor([5.0], device=dev)
+    flush = Flusher(torch, dev)
+    sampler = env["sampler_cls"](dev.index)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    sweep = []
+    head = None
+    for p in sizes:
+        n_total = 1 << p
+        n5 = n_total // world if args.strong else n_total
+        if n5 < 1024:
+            continue
+        x5 = torch.empty(n5, device=dev)
+        m5 = torch.empty(n5, dtype=torch.bool, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(5 + rank)
+        for lo in range(0, n5, 1 << 28):              # fill in 1 GiB pieces: no 16 GB temporaries at 2^32
+            hi = min(lo + (1 << 28), n5)
+            x5[lo:hi].normal_(generator=gen)
+            m5[lo:hi] = torch.rand(hi - lo, device=dev, generator=gen) > 0.5
+        y5 = torch.empty_like(x5)
+        lay = (1, 1, n5)
+        fl = flush if n5 * 4 <= L2_BYTES * 2 else None
+        steps = max(5, min(args.steps, 200 if p <= 26 else (40 if p <= 30 else 10)))
+
+        def fwd():
+            ops.fq_pow2_fwd(x5, dec, lay, mask=m5, out=y5)
+
+        def bwd():
+            ops.ste_bwd(x5, dec, True, 8, 0, lay, mask=m5, clamp_in_place=False, want_gx=True)
+
+        def both():
+            fwd()
+            bwd()
+        ms_f = timed(torch, fwd, steps, 3, fl, world, dev)
+        ms_b = timed(torch, bwd, steps, 3, fl, world, dev)
+        rec = {"log2n": p, "n_per_gpu": n5, "fwd_us": round(ms_f * 1e3, 2), "bwd_us": round(ms_b * 1e3, 2),
+               "fwd_gbs": round(world * 9 * n5 / (ms_f * 1e-3) / 1e9, 1), "bwd_gbs": round(world * 9 * n5 / (ms_b * 1e-3) / 1e9, 1),
+               "fwd_frac": round(9 * n5 / (ms_f * 1e-3) / 1e9 / peak, 4), "bwd_frac": round(9 * n5 / (ms_b * 1e-3) / 1e9 / peak, 4)}
+        if p == headline:
+            ms_h = back_to_back(torch, both, steps, 3, world, dev)
+            # property at full size: idempotence of the fake-quantizer on its own output, masked zeros are +0
+            fwd()
+            y_again = ops.fq_pow2_fwd(y5, dec, lay, mask=m5)
+            head_n = min(n5, 1 << 22)
+            prop = bool(torch.equal(y_again, y5)) and bool((y5[:head_n][~m5[:head_n]] == 0).all().item())
+            head = dict(n5=n5, ms=ms_h, steps=steps, prop=prop, ms_f=ms_f, ms_b=ms_b)
+            del y_again
+        sweep.append(rec)
+        del x5, y5, m5
+        torch.cuda.empty_cache()
+    clocks = sampler.stop() if rank == 0 else None
+    n5, ms = head["n5"], head["ms"]
+
+    # e2e at 2^26 per GPU: pinned host x, g, mask in; y, gx out, through the autograd functional API
+    from qsparse_b200.quantize import quantize_with_decimal
+    ne = 1 << 26
+    hx = torch.randn(ne).pin_memory()
+    hg = torch.randn(ne).pin_memory()
+    hm = (torch.rand(ne) > 0.5).pin_memory()
+    hy = torch.empty(ne).pin_memory()
+    hgx = torch.empty(ne).pin_memory()
+    e2e_steps = max(4, min(args.steps, 10))
+
+    def e2e_step():
+        xd = hx.to(dev, non_blocking=True).requires_grad_(True)
+        md = hm.to(dev, non_blocking=True)
+        gd = hg.to(dev, non_blocking=True)
+        yd = quantize_with_decimal(xd * md, 8, 5)
+        yd.backward(gd)
+        hy.copy_(yd.detach(), non_blocking=True)
+        hgx.copy_(xd.grad, non_blocking=True)
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    dist = _dist()
+    if dist:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    del hx, hg, hm, hy, hgx
+
+    gpu_eager = cpu = None
+    if world == 1 and not args.no_gpu_eager:
+        from oracle.torch_eager import masked_pow2_fwd_bwd
+        n_e = 1 << 28
+        xe = torch.randn(n_e, device=dev)
+        ge = torch.randn(n_e, device=dev)
+        me = torch.rand(n_e, device=dev) > 0.5
+        ms_e = back_to_back(torch, lambda: masked_pow2_fwd_bwd(xe, ge, me, dec), 5, 2, 1, dev)
+        ours_e = next(r for r in sweep if r["log2n"] == 28)
+        ours_ms = (ours_e["fwd_us"] + ours_e["bwd_us"]) / 1e3
+        gpu_eager = {"what": "the reference's eager ATen sequence (mul, pow, mul, int, float, clamp_, float, mul | clamp_, ne, "
+                             "index_put_, mul) at 2^28 elements",
+                     "ms_per_step": round(ms_e, 4), "value": round(18 * n_e / (ms_e * 1e-3) / 1e9, 2), "unit": "GB/s",
+                     "speedup_of_this_repo": round(ms_e / ours_ms, 2)}
+        del xe, ge, me
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_c5(env["host_threads"])
+    value = world * 18 * n5 / (ms * 1e-3) / 1e9
+    line = _base(C5_METRIC, value, world, args, ms, c5_config(args.strong, sizes), world * n5, clocks,
+                 scaling="strong" if args.strong else "weak")
+    line["steps"] = head["steps"]
+    best = head["ms_f"]
+    line.update({
+        "frac_of_measured_hbm_peak": round(value / world / peak, 4),
+        "value_actual": round(value, 2), "bytes_per_elem": {"algorithmic": 18, "actual": 18},
+        "sweep": sweep, "full_size_property_ok": head["prop"],
+        "launch_mode": "eager, forward + backward kernel per step",
+        "gpu_launches": 2 * head["steps"],
+        "e2e": {"value": round(world * 18 * ne / e2e_s / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": 9 * ne * world,
+                "d2h_bytes_per_step": 8 * ne * world, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
+                "api": "pinned host x, g, mask -> device -> quantize_with_decimal(x * mask, 8, 5) + autograd backward "
+                       "(functional API) -> y, gx to pinned host; 2^26 elements per GPU"},
+        "roofline": {"bound": "hbm", "kernel": "map_kernel<Pow2Op<ELEMENT mask>> (y = Q(x*mask), 9 B/elem)",
+                     "achieved": round(9 * n5 / (best * 1e-3) / 1e9, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": round(9 * n5 / (best * 1e-3) / 1e9 / peak, 4), "traffic": _prof().get("c5_fwd_dram_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": 9 * n5, "avg_launch_us": round(best * 1e3, 2)},
+        "gpu_eager_baseline": gpu_eager, "cpu_baseline": cpu,
+    })
+    return line
+
+
+def cpu_c5(threads):
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    n = 1 << 26
+    threads = max(1, threads)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(n, dtype=np.float32)
+    g = rng.standard_normal(n, dtype=np.float32)
+    m = rng.random(n, dtype=np.float32) > 0.5
+    sl = [slice(i * n // threads, (i + 1) * n // threads) for i in range(threads)]
+    pool = ThreadPoolExecutor(threads)
+    dec = np.array([5.0], np.float32)
+
+    def part(s):
+        orc.fq_pow2_fwd(x[s], dec, -1, mask=m[s])
+        orc.ste_bwd(g[s], dec, 8, -1, True, False, mask=m[s])
+
+    list(pool.map(part, sl))
+    steps = 5
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        list(pool.map(part, sl))
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(18 * n / dt / 1e9, 3), "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} forward+backward passes over 2^26 elements, sliced over the threads, {dt*1e3:.0f} ms/step",
+            "elems_per_s": round(n / dt, 1)}
+
+
+# ============================================================================= dispatch
+def run_ours(args, env):
+    return {3: run_c3, 4: run_c4, 5: run_c5}[args.config](args, env)
+
+
+def run_reference(args):
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if args.config == 3:
+        cpu = cpu_c3(threads, max(1, min(args.steps, 10)))
+        metric, cfg = C3_METRIC, c3_config()
+    elif args.config == 4:
+        sp = 0.5 if args.sparsity is None else args.sparsity
+        cpu = cpu_c4(threads, sp)
+        metric, cfg = C4_METRIC, c4_config(sp)
+    else:
+        cpu = cpu_c5(threads)
+        metric, cfg = C5_METRIC, c5_config(args.strong, [20, 22, 24, 26, 28, 30, 32])
+    v = cpu["value"]
+    return {"impl": "reference", "metric": metric, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cpu.get("ms_per_step"), "higher_is_better": True,
+            "scaling": "strong" if (args.config == 5 and args.strong) else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg, "cpu_baseline": cpu,
+            "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "oracle/ (plain-C restatement of the reference, pinned to its golden vectors) on the host cores"}

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QSB_ABI_VERSION 1
+#define QSB_ABI_VERSION 2
 
 /* argument errors */
 #define QSB_E_BADARG (-1)     /* null pointer / negative size / bad enum        */
@@ -80,7 +80,13 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *          1 = a thread keeps one group of 8 channels in registers (default), 0 = table walk;
  *   key 16: column-mode reductions: most threads of a CTA along one row (32, 64 = default, 128, 256);
  *          the CTA's other threads walk interleaved rows and are combined in shared memory, so
- *          256 / value times fewer partials reach the finalize. */
+ *          256 / value times fewer partials reach the finalize;
+ *   key 17: row-mode statistics kernel of the training step (sum|x| + max|x|): 0 = 4 x 256-bit
+ *          loads in flight per lane, 4 CTAs / SM (default); 1 = 6 loads, 3 CTAs / SM; 2 = 8 loads,
+ *          2 CTAs / SM (the reduction plan — and with it the summation order — follows);
+ *   key 18: 1 = qsb_reduce_prune_quant_step reads the channels the previous mask keeps with
+ *          L2::evict_last (the forward pass re-reads exactly those next) and the rest with
+ *          L2::evict_first (default), 0 = default policy for everything. */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and
@@ -409,8 +415,15 @@ int qsb_p2p_free(void *dev_ptr);
 /* bufs[r] = rank r's exchange buffer as mapped in THIS process (bufs[rank] local) */
 int qsb_p2p_group_create(qsb_p2p_group **out, int rank, int world,
                          int64_t channels, void *const *bufs);
-/* *error_out != 0 if a peer's stamp did not arrive within 4 s (synchronises) */
+/* *error_out != 0 if a peer's statistics did not arrive within the timeout (synchronises).
+ * A step that timed out does NOT continue on stale data: it writes NaN into scale / decimal /
+ * magnitude (every later output of the layer is NaN) and raises this flag. */
 int qsb_p2p_group_error(qsb_p2p_group *group, int *error_out);
+/* the same without synchronising: the copy into *error_out_pinned (pinned host memory) is
+ * ordered after the work already queued on `stream`. */
+int qsb_p2p_group_error_async(qsb_p2p_group *group, int *error_out_pinned, void *stream);
+/* how long a step waits for its peers before it poisons itself (default 30 000 ms) */
+int qsb_p2p_group_set_timeout_ms(qsb_p2p_group *group, int64_t timeout_ms);
 int qsb_p2p_group_destroy(qsb_p2p_group *group);
 
 int qsb_prune_quant_step_params(float *magnitude, uint8_t *mask, float *scale,
@@ -423,6 +436,47 @@ int qsb_prune_quant_step_params(float *magnitude, uint8_t *mask, float *scale,
                                 int64_t k, int bits, int64_t t_quant,
                                 int update_scale, double *abssum_out,
                                 float *absmax_out, int64_t *step_counter_dev,
+                                void *stream);
+
+/* The same parameter step on FINALIZED statistics rows (as qsb_prune_quant_params takes
+ * them: one row per staged chunk, combined in row order) with the peer exchange of
+ * qsb_prune_quant_step_params — what the host-buffer pipeline runs at N > 1 GPUs.
+ * `count` is the number of elements per channel over ALL ranks. */
+int qsb_prune_quant_rows_step_params(float *magnitude, uint8_t *mask, float *scale,
+                                     float *decimal_out, const double *abssum,
+                                     const float *absmax, int64_t n_stat_rows,
+                                     int64_t stat_row_stride_bytes, int64_t channels,
+                                     qsb_p2p_group *group, int64_t step_stamp,
+                                     double count, int64_t t_prune,
+                                     int update_magnitude, int refresh_mask,
+                                     int64_t k, int bits, int64_t t_quant,
+                                     int update_scale, void *stream);
+
+/* ------------------------------------------------------------------------
+ * The training step's "everything before apply" as ONE launch (the default route):
+ * the stage-1 reduction of sum|x| / max|x| over x [outer, channels, inner] whose
+ * LAST-ARRIVING CTA runs the parameter step of qsb_prune_quant_step_params as the
+ * kernel's tail (finalize -> peer exchange -> magnitude EMA -> threshold -> mask ->
+ * scale EMA -> decimal).  No single-CTA launch, no host sync; across GPUs the peer
+ * exchange starts the moment this GPU's statistics are complete.
+ * ref: sparse.py:58-66,82-89 + util.py:79-117 + quantize.py:316,329-348 in one launch.
+ * workspace: qsb_reduce_workspace_bytes(outer, channels, inner).
+ * arrival_counter_dev: one device uint32 owned by the caller, ZERO before the first use;
+ * the kernel leaves it zero (one counter per stream that may run this concurrently).
+ * stats_local != 0: abssum_out / absmax_out receive THIS rank's statistics row (before
+ * the exchange) instead of the combined one.  Other arguments as in
+ * qsb_prune_quant_step_params.  Requires channels <= 1024. */
+int qsb_reduce_prune_quant_step(const float *x, int64_t outer, int64_t channels,
+                                int64_t inner, void *workspace,
+                                int64_t workspace_bytes,
+                                unsigned int *arrival_counter_dev,
+                                float *magnitude, uint8_t *mask, float *scale,
+                                float *decimal_out, qsb_p2p_group *group,
+                                int64_t step_stamp, double count, int64_t t_prune,
+                                int update_magnitude, int refresh_mask, int64_t k,
+                                int bits, int64_t t_quant, int update_scale,
+                                double *abssum_out, float *absmax_out,
+                                int stats_local, int64_t *step_counter_dev,
                                 void *stream);
 
 /* ------------------------------------------------------------------------
@@ -446,6 +500,9 @@ int qsb_host_ctx_destroy(qsb_host_ctx *ctx);
  * decimal[1]) lives on the device in caller-provided buffers.  Host buffers
  * should be pinned.  Work is ordered after caller_stream; the call returns when
  * y_host and gx_host are complete.
+ * group (optional, NULL = one GPU): the batch is sharded over the ranks of the group; the
+ * chunk statistics are exchanged with the peers (step_stamp as in
+ * qsb_prune_quant_step_params) so every rank derives the parameters of the concatenated batch.
  * ref: PruneLayer.forward sparse.py:215-273 -> QuantizeLayer.forward
  * quantize.py:473-518 and their backward passes. */
 int qsb_host_prune_quant_step(qsb_host_ctx *ctx, const float *x_host,
@@ -455,6 +512,7 @@ int qsb_host_prune_quant_step(qsb_host_ctx *ctx, const float *x_host,
                               float *decimal_dev, int64_t outer,
                               int64_t channels, int64_t inner, int64_t t_prune,
                               int64_t k, int bits, int64_t t_quant,
+                              qsb_p2p_group *group, int64_t step_stamp,
                               void *caller_stream);
 
 /* The same step, asynchronous: enqueue everything for `slot` (0 or 1) and return.
@@ -472,6 +530,7 @@ int qsb_host_prune_quant_step_submit(qsb_host_ctx *ctx, int slot,
                                      int64_t outer, int64_t channels,
                                      int64_t inner, int64_t t_prune, int64_t k,
                                      int bits, int64_t t_quant,
+                                     qsb_p2p_group *group, int64_t step_stamp,
                                      void *caller_stream);
 int qsb_host_ctx_wait(qsb_host_ctx *ctx, int slot);
 

@@ -1,0 +1,155 @@
+"""TEST / BENCH INFRASTRUCTURE — not part of the product (only tests/ and bench.py's baseline legs import it).
+
+The reference's own ATen op sequence for the hot path, restated as plain eager torch ops in the
+same order, so it can run on CUDA tensors on the GPU box (where /root/reference does not exist)
+as the "PyTorch-eager on the same B200" baseline BASELINE.md asks for.  Every function cites the
+reference lines whose ops it repeats.  No qsparse_b200 kernel is involved: this is what a user of
+mlzxy/qsparse gets on a B200 today, and the bar the hand-written kernels have to beat.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def squeeze_tensor_to_shape(x, shape):
+    """ref qsparse/util.py:92-98: one `mean(i, keepdim=True)` per squeezed axis, in axis order"""
+    for i, (sx, sm) in enumerate(zip(x.shape, shape)):
+        if sx != sm:
+            x = x.mean(i, keepdim=True)
+    return x
+
+
+def calculate_mask_given_importance(importance, sparsity):
+    """ref qsparse/util.py:113-117: full sort, threshold = values[idx + 1], mask = importance >= thr"""
+    values = importance.flatten().sort()[0]
+    n = len(values)
+    idx = max(int(sparsity * n - 1), 0)
+    return importance >= values[idx + 1]
+
+
+class PruneQuantizeEager:
+    """`Sequential(PruneLayer(dimensions={1}, MagnitudePruningCallback()), QuantizeLayer(bits,
+    channelwise=-1, DecimalQuantizer()))` in its steady state (pruning started, quantizer past its
+    timeout), forward + backward, as the reference executes it (ref qsparse/sparse.py:82-122,
+    qsparse/quantize.py:30-77,312-349,501-508).  Host synchronisations (`.item()`) are kept where
+    the reference has them."""
+
+    def __init__(self, channels, device, sparsity=0.75, bits=8):
+        self.sparsity, self.bits = sparsity, bits
+        self.t = torch.zeros(1, dtype=torch.int64, device=device)          # callback.t (nn.Parameter)
+        self.magnitude = torch.zeros(1, channels, 1, 1, device=device)
+        self.mask = torch.ones(1, channels, 1, 1, dtype=torch.bool, device=device)
+        self.weight = torch.zeros(1, 1, device=device)                     # QuantizeLayer.weight
+        self.tq = 0                                                        # DecimalQuantizer.t (python int)
+        self.n_updates = torch.zeros(1, dtype=torch.int32, device=device)  # QuantizeLayer._n_updates
+
+    @torch.no_grad()
+    def forward(self, x):
+        # ---- MagnitudePruningCallback.forward (sparse.py:100-122) ----
+        t_item = self.t.item()                                             # sparse.py:108 (host sync)
+        # update_magnitude (sparse.py:82-89)
+        xa = squeeze_tensor_to_shape(x.abs(), self.magnitude.shape)        # abs + 3 means
+        t = self.t.item()                                                  # sparse.py:88 (host sync)
+        self.magnitude[:] = (t * self.magnitude + xa) / (t + 1)
+        if t_item > 0:
+            # prune_and_update_mask (sparse.py:58-66)
+            self.mask[:] = calculate_mask_given_importance(self.magnitude, self.sparsity)
+        out = x * self.mask                                                # sparse.py:66 / :116
+        self.t += 1
+        # ---- QuantizeLayer.forward (quantize.py:495-518): t = _n_updates.item(), optimize, callback ----
+        _ = self.n_updates.item()                                          # quantize.py:496 (host sync)
+        # DecimalQuantizer.optimize (quantize.py:327-349), channel_index == -1
+        a = out.abs().view(1, -1)
+        new_weight = (a.max(dim=1).values / (2 ** (self.bits - 1))).view(1, 1)
+        if self.tq == 0:
+            self.weight = new_weight
+        else:
+            self.weight[:] = (self.tq * self.weight + new_weight) / (self.tq + 1)
+        self.tq += 1
+        # DecimalQuantizer.quantize (quantize.py:312-325)
+        decimal = (1 / self.weight).nan_to_num(posinf=1, neginf=1).log2().round()
+        # DecimalQuantization.forward (quantize.py:43-63)
+        limit = 2.0 ** (self.bits - 1)
+        tof = 2.0 ** -decimal
+        toi = 2.0 ** decimal
+        q = (out * toi).int()
+        q.float().clamp_(-limit, limit - 1)                                # quantize.py:59-62 (result discarded)
+        y = q.float() * tof
+        self.n_updates += 1
+        self._saved = (limit, tof)
+        return y
+
+    @torch.no_grad()
+    def backward(self, grad_output):
+        limit, tof = self._saved
+        # DecimalQuantization.backward (quantize.py:67-77)
+        v = grad_output.clamp_((-limit) * tof, (limit - 1) * tof)
+        v[v != grad_output] = 0
+        # backward of `x * mask` (sparse.py:66)
+        return v * self.mask
+
+
+class WeightLineQuantEager:
+    """config 3: `quantize(nn.Linear(4096, 4096), bits=4, channelwise=0, timeout=1,
+    callback=AdaptiveQuantizer())`, the training access of `.weight`
+    (ref qsparse/quantize.py:140-185 LineQuantization, :393-430 AdaptiveQuantizer.optimize)."""
+
+    def __init__(self, bits=4):
+        self.bits = bits
+        self.lines = None
+        self.t = 0
+
+    @torch.no_grad()
+    def forward(self, w):
+        x = w.contiguous().view(-1, w[0].numel())                           # channel_index == 0, not batched
+        lb = x.min(dim=1).values
+        ub = x.max(dim=1).values
+        sample = torch.cat([lb.view(-1, 1), ub.view(-1, 1)], dim=1)
+        self.t += 1
+        self.lines = sample if self.lines is None else (self.lines * (self.t - 1) + sample) / self.t
+        # LineQuantization.forward, training (float zero point), quantize.py:148-181
+        lines = self.lines
+        shape = [1] * w.dim()
+        shape[0] = -1
+        lo, hi = lines[:, 0].view(shape), lines[:, 1].view(shape)
+        xc = torch.clamp(w, lo, hi)
+        step = (hi - lo) / (2 ** self.bits)
+        step[step == 0] = 0.0001
+        qa = ((xc - lo) / step).round()
+        qa.clamp_(0, 2 ** self.bits - 1)
+        return qa * step + lo
+
+
+class UnstructuredPruneEager:
+    """config 4: `MagnitudePruningCallback(running_average=True)` with a full-size mask on one weight tensor
+    (ref qsparse/sparse.py:58-66,82-89, qsparse/util.py:103-117)."""
+
+    def __init__(self, like, sparsity):
+        self.sparsity = sparsity
+        self.magnitude = torch.zeros_like(like)
+        self.mask = torch.ones(like.shape, dtype=torch.bool, device=like.device)
+        self.t = 0
+
+    @torch.no_grad()
+    def forward(self, w):
+        xa = w.abs()
+        self.magnitude[:] = (self.t * self.magnitude + xa) / (self.t + 1)
+        if self.t > 0:
+            self.mask[:] = calculate_mask_given_importance(self.magnitude, self.sparsity)
+        self.t += 1
+        return w * self.mask
+
+
+@torch.no_grad()
+def masked_pow2_fwd_bwd(x, g, mask, decimal, bits=8):
+    """config 5: `quantize_with_decimal(x * mask, bits, decimal)` forward and its backward
+    (ref qsparse/quantize.py:43-77 and the `x * mask` of sparse.py:116)."""
+    limit = 2.0 ** (bits - 1)
+    tof, toi = 2.0 ** -decimal, 2.0 ** decimal
+    out = x * mask
+    q = (out * toi).int()
+    q.float().clamp_(-limit, limit - 1)
+    y = q.float() * tof
+    v = g.clamp_((-limit) * tof, (limit - 1) * tof)
+    v[v != g] = 0
+    return y, v * mask

@@ -76,16 +76,24 @@ _SIGNATURES = {
     "qsb_p2p_free": (c_int, [_P]),
     "qsb_p2p_group_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int64, ctypes.POINTER(c_void_p)]),
     "qsb_p2p_group_error": (c_int, [_P, ctypes.POINTER(c_int)]),
+    "qsb_p2p_group_error_async": (c_int, [_P, _P, _P]),
+    "qsb_p2p_group_set_timeout_ms": (c_int, [_P, c_int64]),
     "qsb_p2p_group_destroy": (c_int, [_P]),
+    "qsb_prune_quant_rows_step_params": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64,
+                                                 c_double, c_int64, c_int, c_int, c_int64, c_int, c_int64, c_int,
+                                                 _P]),
+    "qsb_reduce_prune_quant_step": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P,
+                                            c_int64, c_double, c_int64, c_int, c_int, c_int64, c_int, c_int64,
+                                            c_int, _P, _P, c_int, _P, _P]),
     "qsb_prune_quant_step_params": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64,
                                             c_double, c_int64, c_int, c_int, c_int64, c_int, c_int64, c_int, _P, _P,
                                             _P, _P]),
     "qsb_host_ctx_create": (c_int, [ctypes.POINTER(c_void_p), c_int64, c_int64, c_int]),
     "qsb_host_ctx_destroy": (c_int, [_P]),
     "qsb_host_prune_quant_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,
-                                          c_int64, c_int, c_int64, _P]),
+                                          c_int64, c_int, c_int64, _P, c_int64, _P]),
     "qsb_host_prune_quant_step_submit": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64,
-                                                 c_int64, c_int64, c_int, c_int64, _P]),
+                                                 c_int64, c_int64, c_int, c_int64, _P, c_int64, _P]),
     "qsb_host_ctx_wait": (c_int, [_P, c_int]),
     "qsb_set_tuning": (c_int, [c_int, c_int]),
     "qsb_selftest_fastdiv": (c_int, [c_int64, c_int64, ctypes.c_uint64, _P, _P]),
@@ -114,7 +122,7 @@ def load_library() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.qsb_abi_version() != 1:
+    if lib.qsb_abi_version() != 2:
         raise NativeLibraryError("libqsparse_b200.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

@@ -646,6 +646,14 @@ extern "C" int qsb_set_tuning(int key, int value) {
     set_reduce_col_tpr_wide(value);
     return 0;
   }
+  if (key == 17) {
+    set_reduce_row_variant(value);
+    return 0;
+  }
+  if (key == 18) {
+    set_reduce_keep_hint(value);
+    return 0;
+  }
   if (key == 13) {
     set_step_sample_per(value);
     return 0;

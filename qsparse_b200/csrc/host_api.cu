@@ -21,6 +21,7 @@
 
 #include <vector>
 
+#include "p2p_internal.cuh"
 #include "qsb_common.cuh"
 
 constexpr int kHostSlots = 2;  // steps in flight: step t+1 uploads while step t downloads
@@ -125,7 +126,8 @@ extern "C" int qsb_host_prune_quant_step_submit(
     qsb_host_ctx *c, int slot, const float *x_host, const float *g_host, float *y_host,
     float *gx_host, float *magnitude_dev, uint8_t *mask_dev, float *scale_dev,
     float *decimal_dev, int64_t outer, int64_t channels, int64_t inner,
-    int64_t t_prune, int64_t k, int bits, int64_t t_quant, void *caller_stream) {
+    int64_t t_prune, int64_t k, int bits, int64_t t_quant, qsb_p2p_group *group,
+    int64_t step_stamp, void *caller_stream) {
   if (!c || slot < 0 || slot >= kHostSlots) return QSB_E_BADARG;
   if (!x_host || !g_host || !y_host || !gx_host) return QSB_E_BADARG;
   if (outer <= 0 || channels <= 0 || inner <= 0) return QSB_E_BADARG;
@@ -202,10 +204,21 @@ extern "C" int qsb_host_prune_quant_step_submit(
     const double *abssum0 = reinterpret_cast<const double *>(c->d_stats);
     const float *absmax0 =
         reinterpret_cast<const float *>(c->d_stats + channels * sizeof(double));
-    rc = qsb_prune_quant_params(magnitude_dev, mask_dev, scale_dev, decimal_dev,
-                                abssum0, absmax0, n_chunks, c->stats_row_bytes,
-                                channels, (double)outer * (double)inner, t_prune,
-                                1, t_prune > 0, k, bits, t_quant, 1, c->s_comp);
+    if (group) {
+      // N > 1 GPUs: the chunk rows are summed in chunk order, exchanged with the peers over
+      // NVLink inside the same kernel and combined in rank order — the same computation as the
+      // resident path's fused step
+      rc = qsb_prune_quant_rows_step_params(
+          magnitude_dev, mask_dev, scale_dev, decimal_dev, abssum0, absmax0, n_chunks,
+          c->stats_row_bytes, channels, group, step_stamp,
+          (double)outer * (double)inner * (double)group->dev.world, t_prune, 1, t_prune > 0, k, bits,
+          t_quant, 1, c->s_comp);
+    } else {
+      rc = qsb_prune_quant_params(magnitude_dev, mask_dev, scale_dev, decimal_dev,
+                                  abssum0, absmax0, n_chunks, c->stats_row_bytes,
+                                  channels, (double)outer * (double)inner, t_prune,
+                                  1, t_prune > 0, k, bits, t_quant, 1, c->s_comp);
+    }
     if (rc) return rc;
   }
   // ---- forward apply per chunk, download y ---------------------------------
@@ -246,11 +259,13 @@ extern "C" int qsb_host_prune_quant_step(
     qsb_host_ctx *c, const float *x_host, const float *g_host, float *y_host,
     float *gx_host, float *magnitude_dev, uint8_t *mask_dev, float *scale_dev,
     float *decimal_dev, int64_t outer, int64_t channels, int64_t inner,
-    int64_t t_prune, int64_t k, int bits, int64_t t_quant, void *caller_stream) {
+    int64_t t_prune, int64_t k, int bits, int64_t t_quant, qsb_p2p_group *group,
+    int64_t step_stamp, void *caller_stream) {
   // results are in the host buffers when this returns
   int rc = qsb_host_prune_quant_step_submit(c, 0, x_host, g_host, y_host, gx_host, magnitude_dev,
                                             mask_dev, scale_dev, decimal_dev, outer, channels,
-                                            inner, t_prune, k, bits, t_quant, caller_stream);
+                                            inner, t_prune, k, bits, t_quant, group, step_stamp,
+                                            caller_stream);
   if (rc) return rc;
   return qsb_host_ctx_wait(c, 0);
 }

@@ -1,13 +1,13 @@
 // Peer-memory plumbing for the fused statistics exchange.
 //
 // Every rank owns one small exchange buffer in its own HBM:
-//     slots [2 parities][world][row_bytes]   row = [C x fp64 sum|x| | C x u32 bits of max|x|]
-//     flags [2 parities][world] x u64        step stamps
+//     slots [2 parities][world][row_bytes]   row = 3 * C packets of 8 bytes {data word, stamp}
 // and maps every peer's buffer through CUDA IPC (same node, NVLink / NVSwitch).
-// qsb_prune_quant_step_params' kernel then WRITES its row into slot [parity][rank]
-// of every peer with plain stores over NVLink, publishes a stamp, waits for the
-// stamps of all peers in its own buffer and combines the rows in rank order — the
-// collective is part of the parameter kernel, there is no NCCL launch.
+// The parameter step (step_epilogue.cuh: the tail of the fused reduction, or the stand-alone
+// kernel) WRITES its row into slot [parity][rank] of every peer with 64-bit stores over
+// NVLink — data and "ready" stamp in the same store, no fence — polls its own buffer until
+// every peer's packets carry the current stamp and combines the rows in rank order: the
+// collective is part of the kernel, there is no NCCL launch.
 #include <string.h>
 
 #include "p2p_internal.cuh"
@@ -17,7 +17,7 @@ using namespace qsb;
 extern "C" int64_t qsb_p2p_group_bytes(int world, int64_t channels) {
   if (world < 1 || world > kMaxRanks || channels < 1) return 0;
   const int64_t row = p2p_row_bytes(channels);
-  return 2 * world * row + 2 * kMaxRanks * (int64_t)sizeof(unsigned long long) + 256;
+  return 2 * world * row + 256;
 }
 
 // cudaMalloc (not the torch caching allocator: IPC handles need a whole allocation),
@@ -62,6 +62,7 @@ extern "C" int qsb_p2p_group_create(qsb_p2p_group **out, int rank, int world,
   g->dev.rank = rank;
   g->dev.world = world;
   g->dev.row_bytes = p2p_row_bytes(channels);
+  g->dev.timeout_ns = 30ull * 1000000000ull;  // qsb_p2p_group_set_timeout_ms
   g->channels = channels;
   for (int r = 0; r < world; ++r) {
     if (!bufs[r]) {
@@ -82,6 +83,22 @@ extern "C" int qsb_p2p_group_create(qsb_p2p_group **out, int rank, int world,
 extern "C" int qsb_p2p_group_error(qsb_p2p_group *g, int *error_out) {
   if (!g || !error_out) return QSB_E_BADARG;
   QSB_CUDA_TRY(cudaMemcpy(error_out, g->dev.error, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int qsb_p2p_group_set_timeout_ms(qsb_p2p_group *g, int64_t timeout_ms) {
+  if (!g || timeout_ms <= 0) return QSB_E_BADARG;
+  g->dev.timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
+  return 0;
+}
+
+// asynchronous form of qsb_p2p_group_error: the copy is ordered after everything queued on
+// `stream` so far; *error_out_pinned is valid once the stream (or an event after this call)
+// has completed.  Lets a training loop poll the flag without a synchronisation per step.
+extern "C" int qsb_p2p_group_error_async(qsb_p2p_group *g, int *error_out_pinned, void *stream) {
+  if (!g || !error_out_pinned) return QSB_E_BADARG;
+  QSB_CUDA_TRY(cudaMemcpyAsync(error_out_pinned, g->dev.error, sizeof(int), cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
   return 0;
 }
 

@@ -14,6 +14,7 @@
 #include "param_math.cuh"
 #include "qsb_common.cuh"
 #include "reduce_internal.cuh"
+#include "step_epilogue.cuh"
 
 namespace qsb {
 
@@ -179,233 +180,25 @@ __global__ void __launch_bounds__(1024)
 
 
 // ---------------------------------------------------------------------------
-// ONE kernel between "stage-1 partials are written" and "apply":
-//   finalize the reduction  ->  exchange the statistics row with every peer GPU
-//   over NVLink (peer stores + stamp, no NCCL launch)  ->  combine in rank order
-//   ->  magnitude EMA, k-th threshold, mask, abs-max of kept, scale EMA, decimal.
-// One CTA of 1024 threads.
+// The parameter step as a stand-alone one-CTA launch (step_epilogue.cuh): used when the
+// statistics come as finalized rows (chunks of a host tensor), for > 1024 channels, or when
+// the caller ran qsb_reduce_partials itself.  The training step proper uses the fused form,
+// qsb_reduce_prune_quant_step (reduce.cu), where the last CTA of the reduction does this.
 // ---------------------------------------------------------------------------
-constexpr int kStepMaxChannels = 2048;
-
-__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 __global__ void __launch_bounds__(1024)
-    prune_quant_step_kernel(float *magnitude, uint8_t *mask, float *scale,
-                            float *decimal_out, Partials P, int fin_count,
-                            int fin_q, int channels, int group, P2PDev px,
-                            unsigned long long stamp, double count,
-                            int64_t t_prune, int update_magnitude,
-                            int refresh_mask, int64_t k, float limit,
-                            int64_t t_quant, int update_scale,
-                            double *abssum_out, float *absmax_out,
-                            long long *step_counter) {
-  // graph mode: the step index lives on the device (the launch arguments of a captured
-  // CUDA graph are frozen), the kernel reads it, derives t / stamp / refresh itself
-  // and increments it at the end.  `refresh_mask` then carries the refresh interval.
+    prune_quant_step_kernel(const __grid_constant__ StepArgs a) {
   pdl_wait();     // the partials come from the reduction launched just before
   pdl_trigger();  // the forward kernel's CTAs may queue up behind this single CTA
-  if (step_counter) {
-    const long long t = *step_counter;
-    t_prune = t;
-    t_quant = t;
-    stamp = (unsigned long long)(t + 1);
-    const int interval = refresh_mask > 0 ? refresh_mask : 1;
-    refresh_mask = (t % interval == 0) && (t > 0 || update_magnitude == 2);
-  }
   __shared__ double s_sum[kStepMaxChannels];
   __shared__ uint32_t s_max[kStepMaxChannels];
   __shared__ float s_imp[kStepMaxChannels];
   __shared__ uint32_t s_key[kStepMaxChannels];
+  __shared__ double s_psum[32];
+  __shared__ uint32_t s_pmax[32], s_amax[32];
   __shared__ float s_thr;
-  __shared__ uint32_t s_amax[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // `group` threads (a power of two <= 32, inside one warp) share a channel, so the few
-  // thousand partials are fetched with independent loads by all 1024 threads; the
-  // kernel is a chain of dependent round trips, everything is laid out to keep it short.
-  const int gl = tid % group, gc = tid / group, cpp = 1024 / group;
-  const float scale_old = (tid == 0) ? scale[0] : 0.0f;  // prefetch
-
-  // ---- 1. finalize this GPU's partials (fixed order: strided per thread, xor tree) ----
-  for (int base = 0; base < channels; base += cpp) {
-    const int c = base + gc;
-    const bool act = c < channels;
-    float mag_old = 0.0f;
-    if (act && gl == 0 && update_magnitude != 2) mag_old = magnitude[c];  // prefetch
-    double sum = 0.0;
-    uint32_t mx = 0;
-    if (act) {
-      for (int j0 = gl; j0 < fin_count; j0 += 4 * group) {
-        double v[4];
-        uint32_t b[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + u * group;
-          const bool ok = j < fin_count;
-          const int hi = ok ? j / fin_q : 0;
-          const int64_t idx = (int64_t)hi * ((int64_t)channels * fin_q) + (int64_t)c * fin_q + (ok ? j - hi * fin_q : 0);
-          v[u] = ok ? P.asum[idx] : 0.0;
-          b[u] = ok ? P.amax[idx] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          sum += v[u];
-          mx = b[u] > mx ? b[u] : mx;
-        }
-      }
-    }
-    for (int o = (group < 32 ? group : 32) >> 1; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const uint32_t other = __shfl_xor_sync(0xffffffffu, mx, o);
-      mx = other > mx ? other : mx;
-    }
-    if (group > 32) {
-      // one channel, the whole CTA (per-tensor statistics: thousands of partials for ONE value):
-      // combine the warps of the group through shared memory, in warp order
-      __shared__ double s_psum[32];
-      __shared__ uint32_t s_pmax[32];
-      if (lane == 0) {
-        s_psum[warp] = sum;
-        s_pmax[warp] = mx;
-      }
-      __syncthreads();
-      if (gl == 0)
-        for (int w = 1; w < group / 32; ++w) {
-          sum += s_psum[warp + w];
-          mx = s_pmax[warp + w] > mx ? s_pmax[warp + w] : mx;
-        }
-      __syncthreads();
-    }
-    if (act && gl == 0) {
-      s_sum[c] = sum;
-      s_max[c] = mx;
-      s_imp[c] = mag_old;
-    }
-  }
-  __syncthreads();
-
-  // ---- 2. exchange with the peers (weak scaling over the batch) ----------------
-  if (px.world > 1) {
-    const int parity = (int)(stamp & 1ull);
-    // push my row into slot [parity][rank] of EVERY rank's buffer (mine included)
-    for (int i = tid; i < channels * px.world; i += blockDim.x) {
-      const int r = i / channels, c = i - r * channels;
-      unsigned char *slot = px.bufs[r] + p2p_slot_offset(px, parity, px.rank);
-      reinterpret_cast<double *>(slot)[c] = s_sum[c];
-      reinterpret_cast<uint32_t *>(slot + (int64_t)channels * 8)[c] = s_max[c];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < px.world) {
-      st_flag(reinterpret_cast<unsigned long long *>(px.bufs[tid] +
-                                                    p2p_flag_offset(px, parity, px.rank)),
-              stamp);
-      // wait for rank `tid`'s stamp in MY buffer (bounded: never hang the GPU)
-      const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(
-          px.bufs[px.rank] + p2p_flag_offset(px, parity, tid));
-      const unsigned long long t0 = global_ns();
-      while (ld_flag(flag) != stamp) {
-        __nanosleep(100);
-        if (global_ns() - t0 > 4000000000ull) {  // 4 s
-          *px.error = 1;
-          break;
-        }
-      }
-    }
-    __syncthreads();
-    // combine in rank order (SUM of sums, MAX of maxima): identical on every rank
-    for (int c = tid; c < channels; c += blockDim.x) {
-      double sum = 0.0;
-      uint32_t mx = 0;
-      for (int r = 0; r < px.world; ++r) {
-        const unsigned char *slot = px.bufs[px.rank] + p2p_slot_offset(px, parity, r);
-        sum += __ldcg(reinterpret_cast<const double *>(slot) + c);
-        const uint32_t b = __ldcg(reinterpret_cast<const uint32_t *>(slot + (int64_t)channels * 8) + c);
-        mx = b > mx ? b : mx;
-      }
-      s_sum[c] = sum;
-      s_max[c] = mx;
-    }
-    __syncthreads();
-  }
-
-  // ---- 3. importance (magnitude EMA) --------------------------------------------
-  for (int c = tid; c < channels; c += blockDim.x) {
-    if (abssum_out) {
-      abssum_out[c] = s_sum[c];
-      absmax_out[c] = __uint_as_float(s_max[c]);
-    }
-    const float m = (float)(s_sum[c] / count);
-    float imp;
-    if (update_magnitude == 2) {
-      imp = m;
-    } else {
-      imp = s_imp[c];  // the prefetched old magnitude
-      if (update_magnitude == 1) {
-        imp = magnitude_ema_step(imp, m, t_prune);
-        magnitude[c] = imp;
-      }
-    }
-    s_imp[c] = imp;
-    s_key[c] = float_to_key(imp);
-  }
-  __syncthreads();
-
-  // ---- 4. threshold = sorted(importance)[k] by rank counting, `group` threads/channel --
-  if (refresh_mask) {
-    for (int base = 0; base < channels; base += cpp) {
-      const int c = base + gc;
-      const bool act = c < channels;
-      const uint32_t kc = act ? s_key[c] : 0u;
-      int cnt = 0;
-      if (act)
-        for (int j = gl; j < channels; j += group) {
-          const uint32_t kj = s_key[j];
-          cnt += (kj < kc) || (kj == kc && j < c);
-        }
-      for (int o = group >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (act && gl == 0 && cnt == k) s_thr = s_imp[c];
-    }
-    __syncthreads();
-  }
-
-  // ---- 5. mask, abs-max of the kept channels, scale EMA, decimal ------------------
-  const float thr = refresh_mask ? s_thr : 0.0f;
-  uint32_t am = 0;
-  for (int c = tid; c < channels; c += blockDim.x) {
-    bool keep;
-    if (refresh_mask) {
-      keep = s_imp[c] >= thr;
-      mask[c] = keep ? 1 : 0;
-    } else {
-      keep = mask[c] != 0;
-    }
-    if (keep && update_scale) am = s_max[c] > am ? s_max[c] : am;
-  }
-  am = warp_reduce(am, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
-  if (lane == 0) s_amax[warp] = am;
-  __syncthreads();
-  if (tid == 0) {
-    float s = scale_old;
-    if (update_scale) {
-      for (int w = 1; w < 32; ++w) am = s_amax[w] > am ? s_amax[w] : am;
-      s = scale_ema_step(s, __uint_as_float(am), limit, t_quant);
-      scale[0] = s;
-    }
-    if (decimal_out) decimal_out[0] = scale_to_decimal(s);
-    if (step_counter) *step_counter = t_prune + 1;
-  }
+  __shared__ int s_flag;
+  const StepSmem sm{s_sum, s_max, s_imp, s_key, s_psum, s_pmax, s_amax, &s_thr, &s_flag};
+  step_epilogue(a, sm);
 }
 
 }  // namespace qsb
@@ -519,6 +312,50 @@ extern "C" int qsb_prune_quant_params(float *magnitude, uint8_t *mask,
   return 0;
 }
 
+// shared argument checks + StepArgs assembly of the three parameter-step entry points
+namespace qsb {
+int fill_step_args(qsb::StepArgs &a, float *magnitude, uint8_t *mask, float *scale, float *decimal_out,
+                   int64_t channels, qsb_p2p_group *group, int64_t step_stamp, double count, int64_t t_prune,
+                   int update_magnitude, int refresh_mask, int64_t k, int bits, int64_t t_quant,
+                   int update_scale, double *abssum_out, float *absmax_out, int stats_local,
+                   int64_t *step_counter_dev, int threads) {
+  if (!mask || !scale) return QSB_E_BADARG;
+  if (update_magnitude < 0 || update_magnitude > 2) return QSB_E_BADARG;
+  if (update_magnitude != 2 && !magnitude) return QSB_E_BADARG;
+  if (!(count > 0)) return QSB_E_BADARG;
+  if (refresh_mask && (k < 0 || k >= channels)) return QSB_E_BADARG;
+  if ((abssum_out == nullptr) != (absmax_out == nullptr)) return QSB_E_BADARG;
+  if (group && (group->channels != channels || (!step_counter_dev && step_stamp <= 0)))
+    return QSB_E_BADARG;
+  a = qsb::StepArgs{};
+  a.magnitude = magnitude;
+  a.mask = mask;
+  a.scale = scale;
+  a.decimal_out = decimal_out;
+  a.channels = (int)channels;
+  // the summation order of a channel depends on `group` only: derive it for the 256-thread CTA of the
+  // fused reduction whatever the launch, so every route produces the same bits
+  (void)threads;
+  a.group = qsb::step_group_for(channels, 256);
+  a.px.world = 1;
+  if (group) a.px = group->dev;
+  a.stamp = (unsigned long long)step_stamp;
+  a.count = count;
+  a.t_prune = t_prune;
+  a.update_magnitude = update_magnitude;
+  a.refresh_mask = refresh_mask;
+  a.k = k;
+  a.limit = (float)pow(2.0, (double)bits - 1.0);
+  a.t_quant = t_quant;
+  a.update_scale = update_scale;
+  a.abssum_out = abssum_out;
+  a.absmax_out = absmax_out;
+  a.stats_local = stats_local;
+  a.step_counter = reinterpret_cast<long long *>(step_counter_dev);
+  return 0;
+}
+}  // namespace qsb
+
 extern "C" int qsb_prune_quant_step_params(
     float *magnitude, uint8_t *mask, float *scale, float *decimal_out,
     void *reduce_workspace, int64_t workspace_bytes, int64_t outer,
@@ -528,29 +365,39 @@ extern "C" int qsb_prune_quant_step_params(
     float *absmax_out, int64_t *step_counter_dev, void *stream) {
   if (channels <= 0 || channels > kStepMaxChannels) return QSB_E_UNSUPPORTED;
   if (outer <= 0 || inner <= 0 || !reduce_workspace) return QSB_E_BADARG;
-  if (!mask || !scale) return QSB_E_BADARG;
-  if (update_magnitude < 0 || update_magnitude > 2) return QSB_E_BADARG;
-  if (update_magnitude != 2 && !magnitude) return QSB_E_BADARG;
-  if (!(count > 0)) return QSB_E_BADARG;
-  if (refresh_mask && (k < 0 || k >= channels)) return QSB_E_BADARG;
-  if ((abssum_out == nullptr) != (absmax_out == nullptr)) return QSB_E_BADARG;
-  if (group && (group->channels != channels || (!step_counter_dev && step_stamp <= 0)))
-    return QSB_E_BADARG;
+  StepArgs a;
+  const int rc = fill_step_args(a, magnitude, mask, scale, decimal_out, channels, group, step_stamp, count,
+                                t_prune, update_magnitude, refresh_mask, k, bits, t_quant, update_scale,
+                                abssum_out, absmax_out, 0, step_counter_dev, 1024);
+  if (rc) return rc;
   const ReducePlan pl = make_plan(outer, channels, inner, nullptr);
   if (workspace_bytes < partial_bytes(pl.n_partials) + 256) return QSB_E_WORKSPACE;
-  const Partials P = partials_from_workspace(reduce_workspace, pl.n_partials);
-  P2PDev px{};
-  px.world = 1;
-  if (group) px = group->dev;
-  const float limit = (float)pow(2.0, (double)bits - 1.0);
   if (pl.fin_count > 0x7fffffffLL || pl.fin_q > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
-  int tpc = 32;  // threads per channel: largest power of two <= min(32, 1024 / channels)
-  while (tpc > 1 && (int64_t)tpc * channels > 1024) tpc >>= 1;
-  if (channels == 1) tpc = 1024;  // per-tensor statistics: the whole CTA finalizes the one channel
-  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, magnitude, mask,
-                        scale, decimal_out, P, (int)pl.fin_count, (int)pl.fin_q, (int)channels, tpc, px,
-                        (unsigned long long)step_stamp, count, t_prune, update_magnitude, refresh_mask, k,
-                        limit, t_quant, update_scale, abssum_out, absmax_out,
-                        reinterpret_cast<long long *>(step_counter_dev)));
+  a.P = partials_from_workspace(reduce_workspace, pl.n_partials);
+  a.fin_count = (int)pl.fin_count;
+  a.fin_q = (int)pl.fin_q;
+  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, a));
+  return 0;
+}
+
+// The same parameter step on FINALIZED statistics rows (one per staged chunk of a host
+// tensor), with the peer exchange: what the host-buffer pipeline uses at N > 1 GPUs.
+extern "C" int qsb_prune_quant_rows_step_params(
+    float *magnitude, uint8_t *mask, float *scale, float *decimal_out, const double *abssum,
+    const float *absmax, int64_t n_stat_rows, int64_t stat_row_stride_bytes, int64_t channels,
+    qsb_p2p_group *group, int64_t step_stamp, double count, int64_t t_prune, int update_magnitude,
+    int refresh_mask, int64_t k, int bits, int64_t t_quant, int update_scale, void *stream) {
+  if (channels <= 0 || channels > kStepMaxChannels) return QSB_E_UNSUPPORTED;
+  if (!abssum || !absmax || n_stat_rows < 1 || n_stat_rows > 4096) return QSB_E_BADARG;
+  StepArgs a;
+  const int rc = fill_step_args(a, magnitude, mask, scale, decimal_out, channels, group, step_stamp, count,
+                                t_prune, update_magnitude, refresh_mask, k, bits, t_quant, update_scale,
+                                nullptr, nullptr, 0, nullptr, 1024);
+  if (rc) return rc;
+  a.row_sum = abssum;
+  a.row_max = absmax;
+  a.n_rows = (int)n_stat_rows;
+  a.row_stride = stat_row_stride_bytes;
+  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, a));
   return 0;
 }

@@ -31,11 +31,20 @@
 
 #include "qsb_common.cuh"
 #include "reduce_internal.cuh"
+#include "step_epilogue.cuh"
 
 namespace qsb {
 
 constexpr int kRowModeMinInner = 64;
-constexpr int kRowCtasPerSm = 4;  // matches __launch_bounds__ of reduce_rows_kernel
+constexpr int kRowCtasPerSm = 4;  // column mode / default row variant
+// row-kernel variant (tuning key 17): 0 = 4 x 256-bit loads per lane in flight, 4 CTAs / SM;
+// 1 = 6 loads, 3 CTAs / SM; 2 = 8 loads, 2 CTAs / SM.  The plan's warp count follows.
+static int g_row_variant = 0;
+void set_reduce_row_variant(int v) { g_row_variant = (v >= 0 && v <= 2) ? v : 0; }
+static inline int row_ctas_per_sm() { return g_row_variant == 0 ? 4 : (g_row_variant == 1 ? 3 : 2); }
+// tuning key 18: the fused step reads the previous mask's kept channels with L2::evict_last
+static int g_keep_hint = 1;
+void set_reduce_keep_hint(int v) { g_keep_hint = v != 0; }
 
 template <int WHAT>
 struct Acc {
@@ -150,19 +159,80 @@ __device__ __forceinline__ void group_store(const Acc<WHAT> &a_in, int lane, con
 }
 
 // ---------------------------------------------------------------------------
-// stage 1, row mode
+// Fused tail: a stage-1 kernel instantiated with StepTail ends with the parameter step of the
+// structured prune -> quantize training step (step_epilogue.cuh), run by whichever CTA arrives
+// LAST at a device-wide counter — no separate finalize / parameter launch, and across GPUs
+// the peer exchange starts the moment this GPU's statistics are complete.  NoTail: plain stage 1.
 // ---------------------------------------------------------------------------
-template <int WHAT>
-__global__ void __launch_bounds__(QSB_THREADS, 4)
+struct NoTail {
+  static constexpr bool kFused = false;
+};
+struct StepTail {
+  static constexpr bool kFused = true;
+  StepArgs a;
+  unsigned int *arrival;     // zero before the first launch; the last CTA resets it
+  const uint8_t *keep_hint;  // optional channel mask of the previous step (L2 residency hint)
+};
+
+__device__ __forceinline__ void fused_step_tail(const StepTail &t, unsigned char *smem) {
+  __shared__ int s_last;
+  __threadfence();  // this thread's partials are visible device-wide before the CTA checks in
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    s_last = atomicAdd(t.arrival, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *t.arrival = 0;  // ready for the next launch
+  step_epilogue(t.a, carve_step_smem(smem, t.a.channels));
+}
+
+// 256-bit load with a run-time L2 eviction policy (createpolicy): kept channels of the previous
+// mask are read evict_last — the forward pass re-reads exactly those a few microseconds later,
+// 51 MB of the bench tensor — everything else evict_first.
+__device__ __forceinline__ uint64_t l2_policy(bool keep) {
+  uint64_t pol;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ VecF<8> ld_vec8_policy(const float *p, uint64_t pol) {
+  VecF<8> r;
+  asm volatile(
+      "ld.global.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+      : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+        "=f"(r.v[7])
+      : "l"(p), "l"(pol));
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// stage 1, row mode.  U = 256-bit loads in flight per lane and round, MINB = resident CTAs
+// per SM the register budget is set for (the plan's warp count follows, row_ctas_per_sm()).
+// ---------------------------------------------------------------------------
+template <int WHAT, int U, int MINB, class Tail>
+__global__ void __launch_bounds__(QSB_THREADS, MINB)
     reduce_rows_kernel(const float *__restrict__ x, int64_t rows, int64_t inner,
                        int64_t seg, int64_t segs_per_row, int64_t vwarps,
-                       Partials P, int cta_combine) {
+                       Partials P, int cta_combine, int channels, const __grid_constant__ Tail tail) {
   pdl_wait();
   pdl_trigger();
+  extern __shared__ __align__(16) unsigned char qsb_dyn_smem[];
   const int lane = threadIdx.x & 31;
   const int64_t warps_phys = (int64_t)gridDim.x * (QSB_THREADS / 32);
   const int64_t items = rows * segs_per_row;
   auto run_vw = [&](Acc<WHAT> &acc, int64_t vw) {
+    // every item of a virtual warp belongs to ONE channel
+    uint64_t pol = 0;
+    bool use_pol = false;
+    if constexpr (Tail::kFused) {
+      if (tail.keep_hint) {
+        use_pol = true;
+        pol = l2_policy(tail.keep_hint[(vw / segs_per_row) % channels] != 0);
+      }
+    }
     for (int64_t item = vw; item < items; item += vwarps) {
       const int64_t row = item / segs_per_row;
       const int64_t s = item - row * segs_per_row;
@@ -176,19 +246,19 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
       if (lane < head) acc.add(p[lane]);
       const float *pv = p + head;
       const int64_t nv = (len - head) >> 3;
-      // body: 256-bit loads, up to 4 in flight per lane (predicated, so short
-      // pieces do not fall back to one load per round trip)
-      for (int64_t j = lane; j < nv; j += 128) {
-        const bool b1 = j + 32 < nv, b2 = j + 64 < nv, b3 = j + 96 < nv;
-        VecF<8> v0, v1, v2, v3;
-        v0 = ld_vec<8, Hint::KEEP>(pv + (j << 3));
-        if (b1) v1 = ld_vec<8, Hint::KEEP>(pv + ((j + 32) << 3));
-        if (b2) v2 = ld_vec<8, Hint::KEEP>(pv + ((j + 64) << 3));
-        if (b3) v3 = ld_vec<8, Hint::KEEP>(pv + ((j + 96) << 3));
-        acc.template add_n<8>(v0.v);
-        if (b1) acc.template add_n<8>(v1.v);
-        if (b2) acc.template add_n<8>(v2.v);
-        if (b3) acc.template add_n<8>(v3.v);
+      // body: 256-bit loads, up to U in flight per lane (predicated, so short pieces do not
+      // fall back to one load per round trip); vector order per lane is the same for every U
+      for (int64_t j = lane; j < nv; j += 32 * U) {
+        VecF<8> v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (j + 32 * u < nv) {
+            if (Tail::kFused && use_pol) v[u] = ld_vec8_policy(pv + ((j + 32 * u) << 3), pol);
+            else v[u] = ld_vec<8, Hint::KEEP>(pv + ((j + 32 * u) << 3));
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (j + 32 * u < nv) acc.template add_n<8>(v[u].v);
       }
       // tail
       const int64_t done = head + (nv << 3);
@@ -198,7 +268,7 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
   if (cta_combine) {
     // one channel (per-tensor statistics): every warp of the CTA — one virtual warp each — feeds the same
     // result, so the CTA combines its 8 warps in warp order and writes ONE partial; the finalize (or the
-    // fused parameter kernel) then reads gridDim.x entries instead of 8x as many
+    // fused parameter step) then reads gridDim.x entries instead of 8x as many
     constexpr int kW = QSB_THREADS / 32;
     __shared__ uint32_t s_amax[kW];
     __shared__ float s_mn[kW], s_mx[kW];
@@ -235,14 +305,15 @@ __global__ void __launch_bounds__(QSB_THREADS, 4)
       if constexpr (WHAT & QSB_STAT_ABSSUM) P.asum[o] = asum;
       if constexpr (WHAT & QSB_STAT_NNZ) P.nnz[o] = nnz;
     }
-    return;
+  } else {
+    for (int64_t vw = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
+         vw < vwarps; vw += warps_phys) {
+      Acc<WHAT> acc;
+      run_vw(acc, vw);
+      warp_store<WHAT>(acc, lane, P, vw);
+    }
   }
-  for (int64_t vw = (int64_t)blockIdx.x * (QSB_THREADS / 32) + (threadIdx.x >> 5);
-       vw < vwarps; vw += warps_phys) {
-    Acc<WHAT> acc;
-    run_vw(acc, vw);
-    warp_store<WHAT>(acc, lane, P, vw);
-  }
+  if constexpr (Tail::kFused) fused_step_tail(tail, qsb_dyn_smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -264,10 +335,10 @@ constexpr int kTileCtasPerSm = 3;  // 80 registers: 4 accumulators + a prefetche
 
 // LPR lanes share a row (32: a warp per row; 16: two rows per warp pass, for rows of <= 128 elements, where a
 // whole warp per 64-element row spent ~60 instructions of overhead per row); KI = loads per lane per row.
-template <int WHAT, int KI, int LPR>
+template <int WHAT, int KI, int LPR, class Tail>
 __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
     reduce_tile_kernel(const float *__restrict__ x, int64_t rows, int inner, int tile_rows, int spans,
-                       int span_stride, int64_t vwarps, Partials P) {
+                       int span_stride, int64_t vwarps, Partials P, const __grid_constant__ Tail tail) {
   pdl_wait();
   pdl_trigger();
   __shared__ __align__(32) float tile[kTileFloats];
@@ -377,6 +448,8 @@ __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
     const int rr = q * (8 * G) + w * G + gid;
     group_store<WHAT, LPR>(acc[q], lane, P, slot0 + rr, rr < nslots);
   }
+  // the tile buffer (32 KB) is free now: the parameter step's shared memory (<= 20.5 KB) lives there
+  if constexpr (Tail::kFused) fused_step_tail(tail, reinterpret_cast<unsigned char *>(tile));
 }
 
 // ---------------------------------------------------------------------------
@@ -477,11 +550,13 @@ __device__ __forceinline__ void reduce_cols_body(const float *__restrict__ x, in
   }
 }
 
-template <int WHAT, int V>
+template <int WHAT, int V, class Tail>
 __global__ void __launch_bounds__(QSB_THREADS)
     reduce_cols_kernel(const float *__restrict__ x, int64_t nrows, int64_t ncols,
-                       int64_t rows_per_chunk, int tpr, Partials P) {
+                       int64_t rows_per_chunk, int tpr, Partials P, const __grid_constant__ Tail tail) {
+  extern __shared__ __align__(16) unsigned char qsb_dyn_smem[];
   reduce_cols_body<WHAT, V>(x, nrows, ncols, rows_per_chunk, tpr, P);
+  if constexpr (Tail::kFused) fused_step_tail(tail, qsb_dyn_smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -758,7 +833,7 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
                             const float *x) {
   ReducePlan p{};
   const int64_t warps_phys =
-      (int64_t)device_props().sm_count * kRowCtasPerSm * (QSB_THREADS / 32);
+      (int64_t)device_props().sm_count * row_ctas_per_sm() * (QSB_THREADS / 32);
   if (inner >= kTileMinInner && inner <= kTileMaxInner) {
     // short rows: the tile kernel.  One slot (virtual warp) per row of a tile, 3 CTAs of 32 slots
     // per SM; slots = m * channels so that a slot only ever sees one channel.
@@ -828,7 +903,7 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
     }
     p.n_partials = p.vwarps;
   } else {
-    const int64_t target = warps_phys * 32;
+    const int64_t target = (int64_t)device_props().sm_count * kRowCtasPerSm * QSB_THREADS;
     p.row_mode = false;
     p.nrows = outer;
     p.ncols = channels * inner;
@@ -894,35 +969,52 @@ Partials partials_from_workspace(void *workspace, int64_t n_partials) {
   return P;
 }
 
-template <int WHAT>
+template <int WHAT, class Tail = NoTail>
 static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
                       int64_t inner, const Partials &P, const FinalOut &out,
-                      cudaStream_t stream, bool finalize = true) {
+                      cudaStream_t stream, bool finalize = true, const Tail &tail = Tail{}) {
+  // dynamic shared memory of the fused parameter step (the tile kernel re-uses its tile buffer)
+  const size_t dyn = Tail::kFused ? step_smem_bytes((int)channels) : 0;
   if (pl.row_mode && pl.tile_rows > 0) {
     const int64_t grid = (pl.vwarps + pl.tile_rows - 1) / pl.tile_rows;
     auto go = [&](auto kernel) {
       return launch_k(kernel, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, x, pl.rows, (int)inner,
-                      pl.tile_rows, pl.tile_spans, pl.tile_span_stride, pl.vwarps, P);
+                      pl.tile_rows, pl.tile_spans, pl.tile_span_stride, pl.vwarps, P, tail);
     };
-    if (inner <= 64) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 4, 16>));
-    else if (inner <= 128) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8, 16>));
-    else QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8, 32>));
+    if (inner <= 64) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 4, 16, Tail>));
+    else if (inner <= 128) QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8, 16, Tail>));
+    else QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8, 32, Tail>));
   } else if (pl.row_mode) {
     constexpr int kWarps = QSB_THREADS / 32;
-    int64_t grid = (int64_t)device_props().sm_count * kRowCtasPerSm;
+    int64_t grid = (int64_t)device_props().sm_count * row_ctas_per_sm();
     const int64_t need = (pl.vwarps + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
-    QSB_CUDA_TRY(launch_k(reduce_rows_kernel<WHAT>, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, x,
-                          pl.rows, inner, pl.seg, pl.segs_per_row, pl.vwarps, P, pl.cta_combine));
+    auto go = [&](auto kernel) {
+      return launch_k(kernel, dim3((unsigned)grid), dim3(QSB_THREADS), dyn, stream, x, pl.rows, inner, pl.seg,
+                      pl.segs_per_row, pl.vwarps, P, pl.cta_combine, (int)channels, tail);
+    };
+    // the wider variants exist for the statistics of the training step (sum|x| + max|x|)
+    constexpr bool kVariants = WHAT == (QSB_STAT_ABSSUM | QSB_STAT_ABSMAX);
+    bool launched = false;
+    if constexpr (kVariants) {
+      if (g_row_variant == 1) {
+        QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 6, 3, Tail>));
+        launched = true;
+      } else if (g_row_variant == 2) {
+        QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 8, 2, Tail>));
+        launched = true;
+      }
+    }
+    if (!launched) QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 4, 4, Tail>));
   } else {
     const int64_t threads = pl.ncols / pl.vcol;
     dim3 grid((unsigned)((threads + pl.tpr - 1) / pl.tpr), (unsigned)pl.chunks);
     if (pl.vcol == 4)
-      QSB_CUDA_TRY(launch_k(reduce_cols_kernel<WHAT, 4>, grid, dim3(QSB_THREADS), 0, stream, x, pl.nrows,
-                            pl.ncols, pl.rows_per_chunk, pl.tpr, P));
+      QSB_CUDA_TRY(launch_k(reduce_cols_kernel<WHAT, 4, Tail>, grid, dim3(QSB_THREADS), dyn, stream, x, pl.nrows,
+                            pl.ncols, pl.rows_per_chunk, pl.tpr, P, tail));
     else
-      QSB_CUDA_TRY(launch_k(reduce_cols_kernel<WHAT, 1>, grid, dim3(QSB_THREADS), 0, stream, x, pl.nrows,
-                            pl.ncols, pl.rows_per_chunk, pl.tpr, P));
+      QSB_CUDA_TRY(launch_k(reduce_cols_kernel<WHAT, 1, Tail>, grid, dim3(QSB_THREADS), dyn, stream, x, pl.nrows,
+                            pl.ncols, pl.rows_per_chunk, pl.tpr, P, tail));
   }
   QSB_LAUNCH_CHECK();
   if (!finalize) return 0;
@@ -1016,4 +1108,41 @@ extern "C" int qsb_reduce_partials(const float *x, int64_t outer, int64_t channe
   FinalOut out{nullptr, nullptr, nullptr, nullptr, nullptr};
   return run_reduce<QSB_STAT_ABSSUM | QSB_STAT_ABSMAX>(x, pl, channels, inner, P, out,
                                                       stream, /*finalize=*/false);
+}
+
+// ONE launch for everything between "x is in HBM" and "apply" of the fused structured
+// prune -> pow2 quantize training step: the stage-1 reduction of sum|x| / max|x| whose
+// last-arriving CTA finalizes, exchanges the statistics row with the peer GPUs and derives
+// magnitude EMA / threshold / mask / scale / decimal (step_epilogue.cuh).
+extern "C" int qsb_reduce_prune_quant_step(
+    const float *x, int64_t outer, int64_t channels, int64_t inner, void *workspace,
+    int64_t workspace_bytes, unsigned int *arrival_counter_dev, float *magnitude, uint8_t *mask,
+    float *scale, float *decimal_out, qsb_p2p_group *group, int64_t step_stamp, double count,
+    int64_t t_prune, int update_magnitude, int refresh_mask, int64_t k, int bits, int64_t t_quant,
+    int update_scale, double *abssum_out, float *absmax_out, int stats_local,
+    int64_t *step_counter_dev, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (outer <= 0 || channels <= 0 || inner <= 0) return QSB_E_BADARG;
+  if (channels > kStepFusedMaxChannels) return QSB_E_UNSUPPORTED;
+  if (!x || !workspace || !arrival_counter_dev) return QSB_E_BADARG;
+  if (!aligned_to(x, 4) || !aligned_to(arrival_counter_dev, 4)) return QSB_E_ALIGN;
+  StepTail tail;
+  const int rc = fill_step_args(tail.a, magnitude, mask, scale, decimal_out, channels, group, step_stamp, count,
+                                t_prune, update_magnitude, refresh_mask, k, bits, t_quant, update_scale,
+                                abssum_out, absmax_out, stats_local, step_counter_dev, QSB_THREADS);
+  if (rc) return rc;
+  const ReducePlan pl = make_plan(outer, channels, inner, x);
+  if (workspace_bytes < partial_bytes(pl.n_partials) + 256) return QSB_E_WORKSPACE;
+  if (pl.fin_count > 0x7fffffffLL || pl.fin_q > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
+  const Partials P = partials_from_workspace(workspace, pl.n_partials);
+  tail.a.P = P;
+  tail.a.fin_count = (int)pl.fin_count;
+  tail.a.fin_q = (int)pl.fin_q;
+  tail.arrival = arrival_counter_dev;
+  // the previous step's mask as an L2 residency hint: channels it keeps are about to be re-read by
+  // the forward pass (only meaningful for a per-channel mask in row mode)
+  tail.keep_hint = (g_keep_hint && pl.row_mode && pl.tile_rows == 0 && channels > 1) ? mask : nullptr;
+  FinalOut out{nullptr, nullptr, nullptr, nullptr, nullptr};
+  return run_reduce<QSB_STAT_ABSSUM | QSB_STAT_ABSMAX, StepTail>(x, pl, channels, inner, P, out, stream,
+                                                                 /*finalize=*/false, tail);
 }

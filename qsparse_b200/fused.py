@@ -1,18 +1,21 @@
 """Fused structured prune -> pow2 quantize (K7): the training step of
 ``Sequential(PruneLayer(dimensions={channel}), QuantizeLayer(channelwise=-1,
 callback=DecimalQuantizer()))`` (the adjacency ``convert()`` creates,
-ref qsparse/convert.py:214-217) in four launches and 20 B/elem:
+ref qsparse/convert.py:214-217) in three launches and 20 B/elem:
 
-    forward   reduce_stats(x)            4 B/elem   per-channel sum|x| and max|x|, one read
-              prune_quant_params         ~0         magnitude EMA, k-th threshold, mask,
+    forward   reduce_prune_quant_step(x) 4 B/elem   per-channel sum|x| and max|x| in one read; the
+                                                    kernel's last-arriving CTA finalizes, exchanges the
+                                                    statistics row with the peer GPUs (NVLink packets)
+                                                    and derives magnitude EMA, k-th threshold, mask,
                                                     abs-max of kept channels, scale EMA, decimal
               fq_pow2_fwd(x, mask)       8 B/elem   y = Q(x * mask); pruned channels are not read
     backward  ste_bwd(g, mask)           8 B/elem   gx = clamp(g) * mask
 
 against the reference's ~60 B/elem forward.  No host synchronisation:
 step counters are host integers, every derived scalar stays on the device.  With a
-process group the statistics row is all-gathered (parallel.StatExchange) and combined
-in rank order inside the parameter kernel.
+process group the statistics row is exchanged over peer memory inside that kernel
+(parallel.P2PExchange; NCCL all-gather + a parameter kernel when peer mapping is
+unavailable) and combined in rank order, so every rank derives identical parameters.
 """
 from __future__ import annotations
 
@@ -44,7 +47,8 @@ class PruneQuantize(nn.Module):
     PruneLayer.mask, shape [C]) and ``scale`` (QuantizeLayer.weight, shape [1, 1])."""
 
     def __init__(self, sparsity: float = 0.5, bits: int = 8, channel_index: int = 1, running_average: bool = True,
-                 mask_refresh_interval: int = 1, group=None, mutate_grad_output: bool = False):
+                 mask_refresh_interval: int = 1, group=None, mutate_grad_output: bool = False,
+                 exchange_timeout_ms: int = 30000, check_every: int = 16):
         super().__init__()
         self.sparsity = sparsity
         self.bits = bits
@@ -53,6 +57,8 @@ class PruneQuantize(nn.Module):
         self.mask_refresh_interval = max(int(mask_refresh_interval), 1)
         self.group = group
         self.mutate_grad_output = mutate_grad_output  # also clamp grad_output in place (quantize.py:72)
+        self.exchange_timeout_ms = exchange_timeout_ms
+        self.check_every = max(int(check_every), 1)   # steps between polls of the exchange's error flag
         self.t_prune = 0   # MagnitudePruningCallback.t
         self.t_quant = 0   # DecimalQuantizer.t
         self._exchange: Optional[StatExchange] = None
@@ -66,9 +72,13 @@ class PruneQuantize(nn.Module):
         self.mask = nn.Parameter(torch.ones(channels, dtype=torch.bool, device=dev), requires_grad=False)
         self.scale = nn.Parameter(torch.zeros(1, 1, device=dev), requires_grad=False)
         self.decimal = torch.zeros(1, device=dev)
-        self._p2p = make_exchange(channels, dev, self.group) if channels <= 2048 else None
         import torch.distributed as dist
+        from .parallel import assert_equal_shards
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if multi:
+            assert_equal_shards(x.numel() // channels, self.group)
+        self._p2p = make_exchange(channels, dev, self.group, timeout_ms=self.exchange_timeout_ms) \
+            if channels <= 2048 else None
         # NCCL all-gather path only when peer memory is unavailable (or > 2048 channels)
         self._exchange = StatExchange(channels, dev, self.group) if (multi and self._p2p is None) or channels > 2048 \
             else True
@@ -95,14 +105,21 @@ class PruneQuantize(nn.Module):
                                        mode, refresh, k, self.bits, self.t_quant, True, n_rows=n_rows,
                                        row_stride_bytes=stride)
             else:
-                # one kernel: finalize + peer-memory exchange + parameters
-                ws = ops.reduce_partials(xs, layout)
                 world = self._p2p.world if self._p2p is not None else 1
-                ops.prune_quant_step_params(self.magnitude.data, self.mask.data, self.scale.data, self.decimal, ws,
-                                            layout, float(outer * inner * world), t, mode, refresh, k, self.bits,
-                                            self.t_quant, True,
-                                            group=self._p2p.handle if self._p2p is not None else None,
-                                            step_stamp=self._p2p.next_stamp() if self._p2p is not None else 1)
+                grp = self._p2p.handle if self._p2p is not None else None
+                stamp = self._p2p.next_stamp() if self._p2p is not None else 1
+                if ch <= ops.FUSED_STEP_MAX_CHANNELS:
+                    # ONE kernel: reduction whose last CTA finalizes, exchanges and derives the parameters
+                    ops.reduce_prune_quant_step(xs, layout, self.magnitude.data, self.mask.data, self.scale.data,
+                                                self.decimal, float(outer * inner * world), t, mode, refresh, k,
+                                                self.bits, self.t_quant, True, group=grp, step_stamp=stamp)
+                else:
+                    ws = ops.reduce_partials(xs, layout)
+                    ops.prune_quant_step_params(self.magnitude.data, self.mask.data, self.scale.data, self.decimal,
+                                                ws, layout, float(outer * inner * world), t, mode, refresh, k,
+                                                self.bits, self.t_quant, True, group=grp, step_stamp=stamp)
+                if self._p2p is not None and t % self.check_every == 0:
+                    self._p2p.check()     # raises when an earlier step timed out waiting for a peer
             self.t_prune += 1
             self.t_quant += 1
         return ops.fq_pow2_fwd(xs, self.decimal, layout, mask=self.mask.data)
@@ -206,17 +223,23 @@ class FusedPruneQuantSequential(nn.Sequential):
         refresh = (t % cb.mask_refresh_interval == 0 and t <= cb.stop_mask_refresh) and \
             (t > 0 or not cb.running_average)
         k = kth_rank(sparsity, ch)
-        if k >= ch:
+        if refresh and k >= ch:    # the un-fused route only indexes sorted()[k] on a refresh step
             raise IndexError(f"index {k} is out of bounds for dimension 0 with size {ch}")
+        if not refresh:
+            k = min(k, ch - 1)
         decimal = torch.empty(1, dtype=torch.float32, device=x.device)
         with torch.no_grad():
             if cb.running_average:
                 magnitude, mode = cb.magnitude.data.view(-1), 1
             else:
                 magnitude, mode = torch.empty(ch, dtype=torch.float32, device=x.device), 2
-            ws = ops.reduce_partials(xs, layout)
-            ops.prune_quant_step_params(magnitude, p.mask.data.view(-1), q.weight.data.view(-1), decimal, ws, layout,
-                                        float(outer * inner), t, mode, refresh, k, q.bits, qcb.t, True)
+            if ch <= ops.FUSED_STEP_MAX_CHANNELS:
+                ops.reduce_prune_quant_step(xs, layout, magnitude, p.mask.data.view(-1), q.weight.data.view(-1),
+                                            decimal, float(outer * inner), t, mode, refresh, k, q.bits, qcb.t, True)
+            else:
+                ws = ops.reduce_partials(xs, layout)
+                ops.prune_quant_step_params(magnitude, p.mask.data.view(-1), q.weight.data.view(-1), decimal, ws,
+                                            layout, float(outer * inner), t, mode, refresh, k, q.bits, qcb.t, True)
             # the counters of the two layers and their callbacks, as their own forwards advance them
             cb.t += 1
             cb._t_mirror.wrote(cb.t, t + 1)

@@ -467,5 +467,56 @@ def prune_quant_step_params(magnitude, mask, scale, decimal_out, workspace, layo
         N.ptr(step_counter), N.stream_ptr(mask.device)), "qsb_prune_quant_step_params")
 
 
+FUSED_STEP_MAX_CHANNELS = 1024
+
+_arrival_counters = {}
+
+
+def arrival_counter(device: torch.device) -> torch.Tensor:
+    """the zero-initialised uint32 the fused step's last-arriving CTA is elected with: one per
+    (device, stream); the kernel leaves it zero"""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    c = _arrival_counters.get(key)
+    if c is None:
+        c = torch.zeros(64, dtype=torch.int32, device=device)   # a 256-byte line of its own
+        _arrival_counters[key] = c
+    return c
+
+
+def reduce_prune_quant_step(x, layout: Layout, magnitude, mask, scale, decimal_out, count: float, t_prune: int,
+                            update_magnitude: int, refresh_mask, k: int, bits: int, t_quant: int,
+                            update_scale: bool, group=None, step_stamp: int = 1, abssum_out=None, absmax_out=None,
+                            stats_local: bool = False, step_counter=None):
+    """ONE launch: sum|x| / max|x| reduction of x whose last-arriving CTA finalizes, exchanges with the
+    peer GPUs (``group`` = parallel.P2PExchange handle) and updates magnitude / mask / scale / decimal."""
+    N.require_cuda(x, "input")
+    lib = N.load_library()
+    outer, ch, inner = layout
+    nbytes = lib.qsb_reduce_workspace_bytes(c_int64(outer), c_int64(ch), c_int64(inner))
+    ws = N.workspace(x.device, nbytes)
+    N.check(lib.qsb_reduce_prune_quant_step(
+        N.ptr(x), c_int64(outer), c_int64(ch), c_int64(inner), N.ptr(ws), c_int64(ws.numel()),
+        N.ptr(arrival_counter(x.device)), N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out), group,
+        c_int64(step_stamp), c_double(count), c_int64(t_prune), c_int(update_magnitude), c_int(int(refresh_mask)),
+        c_int64(k), c_int(bits), c_int64(t_quant), c_int(1 if update_scale else 0), N.ptr(abssum_out),
+        N.ptr(absmax_out), c_int(1 if stats_local else 0), N.ptr(step_counter), N.stream_ptr(x.device)),
+        "qsb_reduce_prune_quant_step")
+
+
+def prune_quant_rows_step_params(magnitude, mask, scale, decimal_out, stats: dict, count: float, t_prune: int,
+                                 update_magnitude: int, refresh_mask: bool, k: int, bits: int, t_quant: int,
+                                 update_scale: bool, n_rows: int = 1, row_stride_bytes: int = 0, group=None,
+                                 step_stamp: int = 1):
+    """``prune_quant_params`` (finalized statistics rows, combined in row order) plus the peer-memory
+    exchange of the training step."""
+    lib = N.load_library()
+    N.check(lib.qsb_prune_quant_rows_step_params(
+        N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out), N.ptr(stats["abssum"]),
+        N.ptr(stats["absmax"]), c_int64(n_rows), c_int64(row_stride_bytes), c_int64(mask.numel()), group,
+        c_int64(step_stamp), c_double(count), c_int64(t_prune), c_int(update_magnitude),
+        c_int(1 if refresh_mask else 0), c_int64(k), c_int(bits), c_int64(t_quant),
+        c_int(1 if update_scale else 0), N.stream_ptr(mask.device)), "qsb_prune_quant_rows_step_params")
+
+
 def set_tuning(key: int, value: int):
     N.check(N.load_library().qsb_set_tuning(c_int(key), c_int(value)), "qsb_set_tuning")

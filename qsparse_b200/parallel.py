@@ -62,12 +62,22 @@ class StatExchange:
 
 class P2PExchange:
     """Peer-memory statistics exchange: every rank maps every other rank's small exchange
-    buffer through CUDA IPC (same node, NVLink / NVSwitch); the parameter kernel then
-    pushes its row to all peers, publishes a step stamp and combines the rows in rank
-    order — no collective launch on the critical path.  ``handle`` is what
-    ``ops.prune_quant_step_params(group=...)`` takes."""
+    buffer through CUDA IPC (same node, NVLink / NVSwitch); the parameter step (the tail of
+    the fused reduction kernel) pushes its row to all peers as 8-byte {data, stamp} packets,
+    polls its own buffer for theirs and combines the rows in rank order — no collective launch
+    on the critical path.  ``handle`` is what ``ops.reduce_prune_quant_step(group=...)`` takes.
 
-    def __init__(self, channels: int, device, group: Optional[dist.ProcessGroup] = None):
+    The constructor is collective.  Every local CUDA step is followed by a vote (all-reduce of
+    an ok flag), so a failure on ONE rank makes every rank raise at the same point instead of
+    leaving the others inside a mismatched collective.
+
+    A step whose peers do not show up within ``timeout_ms`` does not continue on stale data: the
+    kernel writes NaN into the layer's scale / decimal / magnitude and raises the group's error
+    flag; ``check()`` (called by ``PruneQuantize`` every ``check_every`` steps) turns that into a
+    ``RuntimeError``."""
+
+    def __init__(self, channels: int, device, group: Optional[dist.ProcessGroup] = None,
+                 timeout_ms: int = 30000):
         import ctypes
         from ctypes import byref, c_int, c_int64, c_void_p
 
@@ -75,70 +85,132 @@ class P2PExchange:
 
         self._N = N
         self.lib = N.load_library()
+        self.group = group
+        self.device = torch.device(device)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.local = c_void_p()
+        self.peers = []
+        self.handle = None
+        self.stamp = 0
+        self._err_host = None
+        self._err_event = None
         if self.world > 16:
             raise RuntimeError("P2PExchange supports up to 16 ranks of one node")
+        # the vote travels on the group's own backend: CPU tensor for gloo, device tensor for NCCL
+        vote_dev = self.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+        def vote(err: Optional[BaseException], what: str):
+            ok = torch.tensor([0.0 if err is not None else 1.0], device=vote_dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if ok.item() == 0:
+                self.close()
+                raise RuntimeError(f"peer-memory exchange: {what} failed on "
+                                   f"{'this rank: ' + repr(err) if err is not None else 'another rank'}")
+
         nbytes = self.lib.qsb_p2p_group_bytes(c_int(self.world), c_int64(channels))
-        self.local = c_void_p()
         handle = ctypes.create_string_buffer(64)
-        with torch.cuda.device(device):
-            N.check(self.lib.qsb_p2p_alloc(c_int64(nbytes), byref(self.local), handle), "qsb_p2p_alloc")
+        err = None
+        with torch.cuda.device(self.device):
+            try:
+                N.check(self.lib.qsb_p2p_alloc(c_int64(nbytes), byref(self.local), handle), "qsb_p2p_alloc")
+            except Exception as exc:
+                err = exc
+            vote(err, "qsb_p2p_alloc")
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self.peers = []
             bufs = (c_void_p * self.world)()
-            for r in range(self.world):
-                if r == self.rank:
-                    bufs[r] = self.local
-                    continue
-                p = c_void_p()
-                N.check(self.lib.qsb_p2p_open(ctypes.create_string_buffer(handles[r], 64), byref(p)), "qsb_p2p_open")
-                self.peers.append(p)
-                bufs[r] = p
-            self.handle = c_void_p()
-            N.check(self.lib.qsb_p2p_group_create(byref(self.handle), c_int(self.rank), c_int(self.world),
-                                                  c_int64(channels), bufs), "qsb_p2p_group_create")
-        dist.barrier(group=group)      # every peer has mapped every buffer before the first kernel
-        self.stamp = 0
+            try:
+                for r in range(self.world):
+                    if r == self.rank:
+                        bufs[r] = self.local
+                        continue
+                    p = c_void_p()
+                    N.check(self.lib.qsb_p2p_open(ctypes.create_string_buffer(handles[r], 64), byref(p)),
+                            "qsb_p2p_open")
+                    self.peers.append(p)
+                    bufs[r] = p
+                h = c_void_p()
+                N.check(self.lib.qsb_p2p_group_create(byref(h), c_int(self.rank), c_int(self.world),
+                                                      c_int64(channels), bufs), "qsb_p2p_group_create")
+                self.handle = h
+                N.check(self.lib.qsb_p2p_group_set_timeout_ms(self.handle, c_int64(int(timeout_ms))),
+                        "qsb_p2p_group_set_timeout_ms")
+            except Exception as exc:
+                err = exc
+            # every peer has mapped every buffer before the first kernel (the vote is the barrier)
+            vote(err, "qsb_p2p_open / qsb_p2p_group_create")
 
     def next_stamp(self) -> int:
         self.stamp += 1
         return self.stamp
 
     def error(self) -> int:
+        """the group's error flag (synchronises with the device)"""
         from ctypes import byref, c_int
         e = c_int(0)
         self._N.check(self.lib.qsb_p2p_group_error(self.handle, byref(e)), "qsb_p2p_group_error")
         return e.value
 
+    def check(self):
+        """Raise if a PREVIOUS poll saw the error flag, then queue the next asynchronous read of
+        the flag behind the work already on the current stream — no synchronisation per step;
+        a timed-out step is reported one poll later (and its outputs are NaN in the meantime)."""
+        from ctypes import c_void_p
+        if self._err_host is None:
+            self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._err_event = torch.cuda.Event()
+        elif self._err_event.query() and int(self._err_host[0]) != 0:
+            raise RuntimeError(
+                "qsparse_b200: a peer GPU's statistics did not arrive within the exchange timeout; the step was "
+                "poisoned (scale / decimal / magnitude are NaN) instead of continuing on stale data")
+        self._N.check(self.lib.qsb_p2p_group_error_async(self.handle, c_void_p(self._err_host.data_ptr()),
+                                                         self._N.stream_ptr(self.device)),
+                      "qsb_p2p_group_error_async")
+        self._err_event.record(torch.cuda.current_stream(self.device))
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.qsb_p2p_group_destroy(self.handle)
-            self.handle = None
-            for p in self.peers:
-                self.lib.qsb_p2p_close(p)
+        self.handle = None
+        for p in getattr(self, "peers", []):
+            self.lib.qsb_p2p_close(p)
+        self.peers = []
+        if getattr(self, "local", None):
             self.lib.qsb_p2p_free(self.local)
+            self.local = None
+
+    def __del__(self):   # the cudaMalloc'ed buffer and the IPC mappings do not belong to torch's allocator
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
-def make_exchange(channels: int, device, group=None):
-    """P2PExchange when a multi-rank group is initialised and peer mapping works, else None
-    (single process, or the caller falls back to StatExchange / NCCL)."""
+def make_exchange(channels: int, device, group=None, timeout_ms: int = 30000):
+    """P2PExchange when a multi-rank group is initialised and peer mapping works on EVERY rank, else
+    None (single process, or the caller falls back to StatExchange / NCCL).  Collective: every rank
+    returns the same kind of object (P2PExchange's constructor votes after each phase)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
-    ok = torch.ones(1, device=device)
-    ex = None
     try:
-        ex = P2PExchange(channels, device, group)
-    except Exception as exc:  # pragma: no cover - depends on the box
+        return P2PExchange(channels, device, group, timeout_ms=timeout_ms)
+    except RuntimeError as exc:  # pragma: no cover - depends on the box
         print(f"[qsparse_b200] peer-memory exchange unavailable ({exc}); using NCCL all-gather")
-        ok.zero_()
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # all ranks take the same path
-    if ok.item() == 0:
-        if ex is not None:
-            ex.close()
         return None
-    return ex
+
+
+def assert_equal_shards(n_local: int, group=None):
+    """The exchange combines per-channel SUMS and divides by ``count = n_local * world``: every rank
+    must hold the same number of elements per channel (the reference's mean over the concatenated
+    batch).  One all-gather of an integer at layer initialisation."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    sizes = [None] * dist.get_world_size(group)
+    dist.all_gather_object(sizes, int(n_local), group=group)
+    if len(set(sizes)) != 1:
+        raise RuntimeError(f"qsparse_b200: ranks hold different shard sizes per channel {sizes}; the batch-sharded "
+                           "prune/quantize step needs equal per-rank batches")
 
 
 def combine_rows_host(gathered: torch.Tensor, n_rows: int, row_bytes: int, channels: int):

@@ -76,6 +76,60 @@ def test_two_gpu_peer_memory_exchange_equals_single_process():
     assert results[0]["p2p"] == results[1]["p2p"]
 
 
+def _straggler_worker(rank, world, port, out):
+    """rank 1 shows up 1.5 s late for step 1 while rank 0 only waits 300 ms: rank 0 must NOT continue on the
+    stale rows of its buffer — its parameters are poisoned (NaN) and the error flag is raised."""
+    import time
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from qsparse_b200.fused import PruneQuantize
+    C, per_rank = 48, 6
+    full = _make_batch(world, per_rank, C)
+    layer = PruneQuantize(sparsity=0.5, bits=8, exchange_timeout_ms=300, check_every=1)
+    layer.train()
+    x = torch.from_numpy(full[rank * per_rank:(rank + 1) * per_rank]).cuda()
+    layer(x)                               # step 0: both ranks on time
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 1:
+        time.sleep(1.5)
+    y = layer(x)                           # step 1
+    torch.cuda.synchronize()
+    raised = False
+    try:
+        layer(x)                           # step 2: polls the flag queued behind step 1
+        torch.cuda.synchronize()
+    except RuntimeError as exc:
+        raised = "did not arrive" in str(exc)
+    out.put(dict(rank=rank, err=layer._p2p.error() if layer._p2p else -1, raised=raised,
+                 scale_nan=bool(torch.isnan(layer.scale).any().item()), y_nan=bool(torch.isnan(y).any().item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_straggler_poisons_instead_of_using_stale_rows():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_straggler_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out.get(timeout=180) for _ in range(world)], key=lambda r: r["rank"])
+    for p in procs:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    if results[0]["err"] == -1:
+        pytest.skip("peer memory unavailable on this box (NCCL all-gather path has no device-side timeout)")
+    assert results[0]["err"] == 1 and results[0]["scale_nan"] and results[0]["y_nan"] and results[0]["raised"]
+    # the late rank found rank 0's packets waiting and finished its own step normally
+    assert results[1]["err"] == 0 and not results[1]["scale_nan"]
+
+
 # ----------------------------------------------------------------------------- weights (SURVEY 8e)
 def _weight_set(seed=4):
     rng = np.random.default_rng(seed)

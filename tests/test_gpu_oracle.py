@@ -497,6 +497,91 @@ def test_fused_step_kernel_equals_separate_kernels(shape, C):
             assert torch.equal(st_a[key], st_c[key]), (key, t, "graph mode")
 
 
+@pytest.mark.parametrize("shape,C", [((8, 64, 56, 56), 64), ((8, 64, 14, 14), 64), ((4, 200, 9, 9), 200),
+                                     ((16, 7, 70), 7), ((32, 48), 48), ((64, 1000), 1000), ((3, 1, 5000), 1),
+                                     ((2, 1024, 300), 1024), ((5, 3, 1031), 3)])
+def test_one_launch_step_equals_two_launch_step(shape, C):
+    """qsb_reduce_prune_quant_step (the reduction's last-arriving CTA runs the parameter step) must be
+    bit-identical to qsb_reduce_partials + qsb_prune_quant_step_params in every stage-1 mode (rows, tile,
+    columns, one channel), with the row-kernel variants and with / without the L2 keep hint; the arrival
+    counter must be left at zero after every launch."""
+    from qsparse_b200 import ops
+    from qsparse_b200._native import channel_layout
+    layout = channel_layout(shape, 1)
+    count = float(layout[0] * layout[2])
+    k = orc.kth_index(0.5, C)
+
+    def fresh():
+        return dict(mag=torch.zeros(C, device="cuda"), mask=torch.ones(C, dtype=torch.bool, device="cuda"),
+                    scale=torch.zeros(1, device="cuda"), dec=torch.zeros(1, device="cuda"))
+
+    xs = [cu(np.maximum(rnd(shape, 900 + t), 0) * np.linspace(0.3, 1.7, C, dtype=np.float32).reshape(
+        (1, C) + (1,) * (len(shape) - 2))) for t in range(4)]
+    try:
+        for variant in (0, 1, 2):
+            ops.set_tuning(17, variant)
+            ref = fresh()
+            ref_stats = []
+            for t, x in enumerate(xs):
+                ws = ops.reduce_partials(x, layout)
+                asum = torch.empty(C, dtype=torch.float64, device="cuda")
+                amax = torch.empty(C, dtype=torch.float32, device="cuda")
+                ops.prune_quant_step_params(ref["mag"], ref["mask"], ref["scale"], ref["dec"], ws, layout, count, t,
+                                            1, t > 0, k, 8, t, True, abssum_out=asum, absmax_out=amax)
+                ref_stats.append((asum, amax, {key: v.clone() for key, v in ref.items()}))
+            for hint in (1, 0):
+                ops.set_tuning(18, hint)
+                st = fresh()
+                stg = fresh()
+                counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+                for t, x in enumerate(xs):
+                    asum = torch.empty(C, dtype=torch.float64, device="cuda")
+                    amax = torch.empty(C, dtype=torch.float32, device="cuda")
+                    ops.reduce_prune_quant_step(x, layout, st["mag"], st["mask"], st["scale"], st["dec"], count, t, 1,
+                                                t > 0, k, 8, t, True, abssum_out=asum, absmax_out=amax)
+                    assert int(ops.arrival_counter(x.device)[0].item()) == 0
+                    assert torch.equal(asum, ref_stats[t][0]) and torch.equal(amax, ref_stats[t][1]), (variant, t)
+                    # local statistics row == the combined one on a single GPU
+                    asum_l = torch.empty_like(asum)
+                    amax_l = torch.empty_like(amax)
+                    ops.reduce_prune_quant_step(x, layout, stg["mag"], stg["mask"], stg["scale"], stg["dec"], count, 0,
+                                                1, 1, k, 8, 0, True, abssum_out=asum_l, absmax_out=amax_l,
+                                                stats_local=True, step_counter=counter)
+                    assert counter.item() == t + 1
+                    assert torch.equal(asum_l, asum) and torch.equal(amax_l, amax)
+                    for key in st:
+                        assert torch.equal(st[key], ref_stats[t][2][key]), (key, t, variant, hint)
+                        assert torch.equal(stg[key], ref_stats[t][2][key]), (key, t, variant, hint, "graph mode")
+    finally:
+        ops.set_tuning(17, 0)
+        ops.set_tuning(18, 1)
+
+
+def test_one_launch_step_oracle_three_steps():
+    """the one-launch step against the plain-C oracle on the smoke shape (magnitude within the documented
+    mean tolerance, mask / decimal exact)"""
+    from qsparse_b200 import ops
+    C, shape, layout = 16, (4, 16, 14, 14), (4, 16, 196)
+    x = np.maximum(rnd(shape, 41), 0) * np.linspace(0.1, 2, C, dtype=np.float32).reshape(1, C, 1, 1)
+    xd = cu(x)
+    mag = torch.zeros(C, device="cuda")
+    mask = torch.ones(C, dtype=torch.bool, device="cuda")
+    scale = torch.zeros(1, device="cuda")
+    dec = torch.zeros(1, device="cuda")
+    mag_ref, mask_ref, scale_ref = np.zeros(C, np.float32), np.ones(C, bool), np.zeros(1, np.float32)
+    k = orc.kth_index(0.75, C)
+    for t in range(3):
+        ops.reduce_prune_quant_step(xd, layout, mag, mask, scale, dec, 4 * 196.0, t, 1, t > 0, k, 8, t, True)
+        mag_ref = orc.magnitude_ema(mag_ref, orc.squeeze_mean_abs(x, (1, C, 1, 1)).reshape(-1), t)
+        if t > 0:
+            mask_ref, _ = orc.mask_given_importance(mag_ref, 0.75)
+        scale_ref = orc.scale_ema(scale_ref, np.array([np.max(orc.absmax(x, 1) * mask_ref)], np.float32), 8, t)
+        assert np.array_equal(npy(mask), mask_ref)
+        assert bits_equal(npy(scale), scale_ref)
+        assert bits_equal(npy(dec), orc.scale_to_decimal(scale_ref))
+        assert ulp_diff(npy(mag), mag_ref).max() <= 8
+
+
 @pytest.mark.parametrize("shape", [(4000, 48), (300, 24, 5), (700, 1000)])
 def test_fused_step_kernel_unaligned_column_mode(shape):
     """A 4-byte-aligned x makes the column reduction fall back to scalar columns; the partial layout that the
