@@ -276,6 +276,7 @@ def run_ours(args):
     counter = torch.zeros(1, dtype=torch.int64, device=dev)      # device-side step index (graph mode)
     stream = N.stream_ptr(dev)
     count_all = float(LAYOUT[0] * LAYOUT[2] * world)
+    arrival = torch.zeros(64, dtype=torch.int32, device=dev)     # the fused step's CTA arrival counter (stays zero)
 
     def bwd(s=st):
         # gx = clamp(g) * mask, dense read of g, dense write of gx (8 B/elem)
@@ -287,10 +288,10 @@ def run_ours(args):
         # ONE launch: reduction + (last CTA) finalize, peer exchange, parameters
         if counter_ is not None:
             ops.reduce_prune_quant_step(x, LAYOUT, s["mag"], s["mask"], s["scale"], s["dec"], count_all, 0, 1, 1, k,
-                                        BITS, 0, True, group=grp, step_counter=counter_, **kw)
+                                        BITS, 0, True, group=grp, step_counter=counter_, arrival=arrival, **kw)
         else:
             ops.reduce_prune_quant_step(x, LAYOUT, s["mag"], s["mask"], s["scale"], s["dec"], count_all, t, 1, t > 0,
-                                        k, BITS, t, True, group=grp, step_stamp=stamp, **kw)
+                                        k, BITS, t, True, group=grp, step_stamp=stamp, arrival=arrival, **kw)
 
     def params_nccl(s, t):
         ops.reduce_stats(x, LAYOUT, abssum=True, absmax=True, out={"abssum": ex.row.abssum, "absmax": ex.row.absmax})
@@ -338,8 +339,6 @@ def run_ours(args):
     use_graph = args.mode == "graph" and ex is None
     if use_graph:
         counter.fill_(state["t"])
-        if p2p:
-            p2p.stamp = 1 << 40     # graph mode derives the stamps from the device-side step counter
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -413,6 +412,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         seg = [sum(e[j].elapsed_time(e[j + 1]) for e in evs[10:]) / (reps - 10) * 1e3 for j in range(3)]
         kern = seg
+    if p2p:
+        p2p.stamp = state["t"]      # graph mode derived the stamps from the device-side step counter (stamp = t + 1)
     barrier()
 
     # ---- module API: the same step through fused.PruneQuantize (autograd forward + backward) ----

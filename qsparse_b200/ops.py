@@ -486,9 +486,11 @@ def arrival_counter(device: torch.device) -> torch.Tensor:
 def reduce_prune_quant_step(x, layout: Layout, magnitude, mask, scale, decimal_out, count: float, t_prune: int,
                             update_magnitude: int, refresh_mask, k: int, bits: int, t_quant: int,
                             update_scale: bool, group=None, step_stamp: int = 1, abssum_out=None, absmax_out=None,
-                            stats_local: bool = False, step_counter=None):
+                            stats_local: bool = False, step_counter=None, arrival=None):
     """ONE launch: sum|x| / max|x| reduction of x whose last-arriving CTA finalizes, exchanges with the
-    peer GPUs (``group`` = parallel.P2PExchange handle) and updates magnitude / mask / scale / decimal."""
+    peer GPUs (``group`` = parallel.P2PExchange handle) and updates magnitude / mask / scale / decimal.
+    ``arrival``: a caller-owned zeroed int32 tensor (default: one per device and stream, created on first
+    use — pass your own when capturing a CUDA graph so that no fill is captured)."""
     N.require_cuda(x, "input")
     lib = N.load_library()
     outer, ch, inner = layout
@@ -496,7 +498,7 @@ def reduce_prune_quant_step(x, layout: Layout, magnitude, mask, scale, decimal_o
     ws = N.workspace(x.device, nbytes)
     N.check(lib.qsb_reduce_prune_quant_step(
         N.ptr(x), c_int64(outer), c_int64(ch), c_int64(inner), N.ptr(ws), c_int64(ws.numel()),
-        N.ptr(arrival_counter(x.device)), N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out), group,
+        N.ptr(arrival if arrival is not None else arrival_counter(x.device)), N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out), group,
         c_int64(step_stamp), c_double(count), c_int64(t_prune), c_int(update_magnitude), c_int(int(refresh_mask)),
         c_int64(k), c_int(bits), c_int64(t_quant), c_int(1 if update_scale else 0), N.ptr(abssum_out),
         N.ptr(absmax_out), c_int(1 if stats_local else 0), N.ptr(step_counter), N.stream_ptr(x.device)),
