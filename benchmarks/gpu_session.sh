@@ -12,7 +12,7 @@ for stage in "$@"; do
     smoke)
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.txt 2>&1 ;;
     variants)
-      for v in 0 1 2; do for h in 1 0; do
+      for v in 2 0; do for h in 1 0; do
         timeout 300 python bench.py --steps 500 --warmup 10 --no-cpu-baseline --no-gpu-eager --row-variant $v --keep-hint $h \
           > $out/${tag}_bench_v${v}_h${h}.json 2> $out/${tag}_bench_v${v}_h${h}.err
       done; done ;;
@@ -21,6 +21,15 @@ for stage in "$@"; do
       timeout 600 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_s20.json 2>> $out/${tag}_bench.err
       timeout 600 python bench.py --sparsity 0 --no-cpu-baseline > $out/${tag}_bench_dense.json 2>> $out/${tag}_bench.err
       timeout 600 python bench.py --mode eager --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_eager.json 2>> $out/${tag}_bench.err ;;
+    probe)
+      timeout 300 python benchmarks/bw_probe.py > $out/${tag}_bw_probe.jsonl 2>&1 ;;
+    multi)
+      timeout 900 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -25 > $out/${tag}_tests_multi.txt
+      for n in 2; do
+        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+          bench.py --gpus $n --steps 500 --warmup 10 > $out/${tag}_bench_n${n}.json 2> $out/${tag}_bench_n${n}.err
+        echo "rc=$?" >> $out/${tag}_bench_n${n}.err
+      done ;;
     ref)
       timeout 600 python bench.py --impl reference --steps 10 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err ;;
     configs)

@@ -60,8 +60,14 @@ def convert(  # noqa: C901
     include: Optional[Union[str, List[str]]] = None,
     exclude: Optional[Union[str, List[str]]] = None,
     order: str = "post",
+    fuse: bool = False,
 ) -> nn.Module:
-    """ref qsparse/convert.py:21-245 (argument meaning identical)."""
+    """ref qsparse/convert.py:21-245 (argument meaning identical).
+
+    ``fuse`` (extension, off by default): after the conversion, run the fusion pass
+    ``fused.fuse_prune_quantize`` over the model, so every ``Sequential(Sequential(act, PruneLayer),
+    QuantizeLayer)`` site that this and earlier ``convert()`` calls created sends its steady-state training
+    steps through the fused kernels.  Module tree, ``state_dict`` keys and results are unchanged."""
     assert isinstance(operator, (PruneLayer, QuantizeLayer)), \
         "`operator` does not belong to (PruneLayer, QuantizeLayer)"
     assert order in ["pre", "post"], "`order` must be either 'pre' or 'post'"
@@ -181,4 +187,7 @@ def convert(  # noqa: C901
     else:  # nn.DataParallel-style wrapper
         model.module = convert_tree(model.module)
     auto_name_prune_quantize_layers(nn_module(model))
+    if fuse:
+        from .fused import fuse_prune_quantize
+        fuse_prune_quantize(nn_module(model))
     return model

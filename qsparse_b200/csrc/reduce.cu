@@ -38,10 +38,11 @@ namespace qsb {
 constexpr int kRowModeMinInner = 64;
 constexpr int kRowCtasPerSm = 4;  // column mode / default row variant
 // row-kernel variant (tuning key 17): 0 = 4 x 256-bit loads per lane in flight, 4 CTAs / SM;
-// 1 = 6 loads, 3 CTAs / SM; 2 = 8 loads, 2 CTAs / SM.  The plan's warp count follows.
-static int g_row_variant = 0;
-void set_reduce_row_variant(int v) { g_row_variant = (v >= 0 && v <= 2) ? v : 0; }
-static inline int row_ctas_per_sm() { return g_row_variant == 0 ? 4 : (g_row_variant == 1 ? 3 : 2); }
+// 2 = 8 loads, 2 CTAs / SM (default: half as many partials for the finalize / the fused tail).
+// The plan's warp count follows.
+static int g_row_variant = 2;  // measured on the bench step: 158.7 (0) / 159.2 (1) / 156.8 us (2)
+void set_reduce_row_variant(int v) { g_row_variant = (v == 0) ? 0 : 2; }
+static inline int row_ctas_per_sm() { return g_row_variant == 0 ? 4 : 2; }
 // tuning key 18: the fused step reads the previous mask's kept channels with L2::evict_last
 static int g_keep_hint = 1;
 void set_reduce_keep_hint(int v) { g_keep_hint = v != 0; }
@@ -993,19 +994,8 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
       return launch_k(kernel, dim3((unsigned)grid), dim3(QSB_THREADS), dyn, stream, x, pl.rows, inner, pl.seg,
                       pl.segs_per_row, pl.vwarps, P, pl.cta_combine, (int)channels, tail);
     };
-    // the wider variants exist for the statistics of the training step (sum|x| + max|x|)
-    constexpr bool kVariants = WHAT == (QSB_STAT_ABSSUM | QSB_STAT_ABSMAX);
-    bool launched = false;
-    if constexpr (kVariants) {
-      if (g_row_variant == 1) {
-        QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 6, 3, Tail>));
-        launched = true;
-      } else if (g_row_variant == 2) {
-        QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 8, 2, Tail>));
-        launched = true;
-      }
-    }
-    if (!launched) QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 4, 4, Tail>));
+    if (g_row_variant == 2) QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 8, 2, Tail>));
+    else QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 4, 4, Tail>));
   } else {
     const int64_t threads = pl.ncols / pl.vcol;
     dim3 grid((unsigned)((threads + pl.tpr - 1) / pl.tpr), (unsigned)pl.chunks);

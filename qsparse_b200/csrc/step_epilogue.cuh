@@ -160,11 +160,14 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
       double sum = 0.0;
       uint32_t mx = 0;
       if (act) {
-        for (int j0 = gl; j0 < a.fin_count; j0 += 4 * group) {
-          double v[4];
-          uint32_t b[4];
+        // kFinBatch independent loads per thread in flight (L2 hits): the C2 plan has 9 entries per
+        // thread, i.e. ONE round trip; the additions run in ascending j whatever the batch size
+        constexpr int kFinBatch = 12;
+        for (int j0 = gl; j0 < a.fin_count; j0 += kFinBatch * group) {
+          double v[kFinBatch];
+          uint32_t b[kFinBatch];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < kFinBatch; ++u) {
             const int j = j0 + u * group;
             const bool ok = j < a.fin_count;
             const int hi = ok ? j / a.fin_q : 0;
@@ -174,7 +177,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
             b[u] = ok ? __ldcg(a.P.amax + idx) : 0u;
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < kFinBatch; ++u) {
             sum += v[u];
             mx = b[u] > mx ? b[u] : mx;
           }

@@ -142,9 +142,13 @@ class _FusedLayersFn(torch.autograd.Function):
     DecimalQuantization.backward does, ref quantize.py:65-77, sparse.py backward of x * mask)."""
 
     @staticmethod
-    def forward(ctx, x, xs, layout, mask, decimal, bits, notch):
-        ctx.layout, ctx.mask, ctx.decimal, ctx.bits, ctx.notch = layout, mask, decimal, bits, notch
-        return ops.fq_pow2_fwd(xs, decimal, layout, mask=mask).view(x.shape)
+    def forward(ctx, x, xs, layout, mask, param, bits, notch, is_decimal):
+        # param: the step's decimal (DecimalQuantizer) or the layer's scale itself (ScalerQuantizer)
+        ctx.layout, ctx.mask, ctx.param, ctx.bits, ctx.notch = layout, mask, param, bits, notch
+        ctx.is_decimal = is_decimal
+        if is_decimal:
+            return ops.fq_pow2_fwd(xs, param, layout, mask=mask).view(x.shape)
+        return ops.fq_scaler_fwd(xs, param, layout, mask=mask).view(x.shape)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -153,9 +157,9 @@ class _FusedLayersFn(torch.autograd.Function):
             g = g.float()
         if not g.is_contiguous():
             g = g.contiguous()
-        _, gx = ops.ste_bwd(g, ctx.decimal, True, ctx.bits, ctx.notch, ctx.layout, mask=ctx.mask,
+        _, gx = ops.ste_bwd(g, ctx.param, ctx.is_decimal, ctx.bits, ctx.notch, ctx.layout, mask=ctx.mask,
                             clamp_in_place=True, want_gx=True)
-        return (gx,) + (None,) * 6
+        return (gx,) + (None,) * 7
 
 
 class FusedPruneQuantSequential(nn.Sequential):
@@ -168,7 +172,7 @@ class FusedPruneQuantSequential(nn.Sequential):
     A step is fused only when it is provably the plain case: both layers initialised, training, structured
     channel prune (``dimensions={1}``) by the stock ``MagnitudePruningCallback`` (no gradient / l0 / hook
     variants), pruning started and the sparsity not changing at this step, per-tensor stock
-    ``DecimalQuantizer`` past its timeout.  Every other step (warm-up, ramp steps, eval, other callbacks,
+    ``DecimalQuantizer`` or ``ScalerQuantizer`` (``quantize()``'s default callback) past its timeout.  Every other step (warm-up, ramp steps, eval, other callbacks,
     non-contiguous inputs) runs the two layers one after the other, exactly as before.  Counters and
     parameters advance identically either way, so the two routes can alternate freely."""
 
@@ -181,7 +185,7 @@ class FusedPruneQuantSequential(nn.Sequential):
         return None, first, q
 
     def _fusable(self, p, q, x):
-        from .quantize import DecimalQuantizer, QuantizeLayer
+        from .quantize import DecimalQuantizer, QuantizeLayer, ScalerQuantizer
         from .sparse import MagnitudePruningCallback, PruneLayer
 
         if not (isinstance(p, PruneLayer) and isinstance(q, QuantizeLayer) and self.training and p.training
@@ -190,7 +194,7 @@ class FusedPruneQuantSequential(nn.Sequential):
         if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() >= 2 and x.is_contiguous()):
             return False
         cb, qcb = p.callback, q.callback
-        if type(cb) is not MagnitudePruningCallback or type(qcb) is not DecimalQuantizer:
+        if type(cb) is not MagnitudePruningCallback or type(qcb) not in (DecimalQuantizer, ScalerQuantizer):
             return False
         if cb.use_gradient or cb.l0 or cb.forward_hook is not None or not cb.training or not qcb.training:
             return False
@@ -207,7 +211,9 @@ class FusedPruneQuantSequential(nn.Sequential):
             return False
         if q.channelwise >= 0 or q.timeout <= 0 or q._t_mirror.get(q._n_updates) < q.timeout:
             return False
-        if qcb.backward_passthrough or qcb.use_float_scaler or qcb.group_num > 0:
+        if qcb.backward_passthrough or qcb.use_uint or qcb.group_num > 0:
+            return False
+        if qcb.use_float_scaler != (type(qcb) is ScalerQuantizer):
             return False
         if tuple(q.weight.shape) != (1, 1) or p._s_mirror.get(p._cur_sparsity) < 0:
             return False
@@ -227,7 +233,10 @@ class FusedPruneQuantSequential(nn.Sequential):
             raise IndexError(f"index {k} is out of bounds for dimension 0 with size {ch}")
         if not refresh:
             k = min(k, ch - 1)
-        decimal = torch.empty(1, dtype=torch.float32, device=x.device)
+        is_decimal = not qcb.use_float_scaler
+        # DecimalQuantizer: this step's decimal (a fresh tensor: the backward must see THIS step's value);
+        # ScalerQuantizer: the quantize kernels read the layer's scale itself, like the reference's saved tensor
+        decimal = torch.empty(1, dtype=torch.float32, device=x.device) if is_decimal else None
         with torch.no_grad():
             if cb.running_average:
                 magnitude, mode = cb.magnitude.data.view(-1), 1
@@ -252,8 +261,9 @@ class FusedPruneQuantSequential(nn.Sequential):
             q._n_updates += 1
             q._t_mirror.wrote(q._n_updates, tq + 1)
         self.fused_steps += 1
-        return _FusedLayersFn.apply(x, xs, layout, p.mask.data.view(-1), decimal, q.bits,
-                                    1 if qcb.flip_axis else 0)
+        return _FusedLayersFn.apply(x, xs, layout, p.mask.data.view(-1),
+                                    decimal if is_decimal else q.weight.data.view(-1), q.bits,
+                                    1 if qcb.flip_axis else 0, is_decimal)
 
     def forward(self, x):
         pre, p, q = self._layers()

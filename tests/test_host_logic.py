@@ -36,6 +36,33 @@ def test_api_surface_matches_reference_exports():
         assert hasattr(u, name), name
 
 
+def test_every_reference_export_is_importable_and_alias_works():
+    """qsparse/__init__.py:2-8 of the reference, name by name (fuse_bn included), and the `qsparse` alias"""
+    import importlib
+    import sys
+    for name in ("convert", "fuse_bn", "quantize", "DecimalQuantizer", "ScalerQuantizer", "AdaptiveQuantizer",
+                 "MagnitudePruningCallback", "UniformPruningCallback", "prune", "devise_layerwise_pruning_schedule",
+                 "auto_name_prune_quantize_layers", "calculate_mask_given_importance", "get_qsparse_option",
+                 "set_qsparse_options"):
+        assert getattr(qs, name) is not None, name
+    saved = {k: v for k, v in sys.modules.items() if k == "qsparse" or k.startswith("qsparse.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        from qsparse_b200 import compat
+        compat.install_as_qsparse()
+        qsparse = importlib.import_module("qsparse")
+        assert qsparse is qs and qsparse.fuse_bn is qs.fuse_bn
+        from qsparse.quantize import QuantizeLayer, quantize_with_decimal   # noqa: F401
+        from qsparse.sparse import PruneLayer                               # noqa: F401
+        from qsparse.util import squeeze_tensor_to_shape                    # noqa: F401
+        from qsparse.fuse import fuse_bn                                    # noqa: F401
+    finally:
+        for k in [k for k in sys.modules if k == "qsparse" or k.startswith("qsparse.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
 def test_channel_layout():
     assert channel_layout((256, 64, 56, 56), 1) == (256, 64, 3136)
     assert channel_layout((4096, 4096), 0) == (1, 4096, 4096)
