@@ -249,6 +249,15 @@ int qsb_row_quant_fused(const float *x, float *y, float *param,
 /* ref: MagnitudePruningCallback.update_magnitude qsparse/sparse.py:82-89 with a
  * reduced (structured) magnitude:  m = abssum / count  (or nnz / count when
  * use_l0 and *tensor_min == 0);  mag = (t*mag + m) / (t+1) */
+/* The same with an element prune mask applied first — the weight chain quantize(prune(layer))
+ * (ref qsparse/imitation.py:61-71) with a frozen mask: y = Q(x * mask), the row's parameter is
+ * estimated on x * mask.  9 B/elem in one launch.  mask_dev: uint8 [rows * inner], 8-byte aligned. */
+int qsb_row_quant_fused_masked(const float *x, float *y, float *param,
+                               float *decimal_out, const uint8_t *mask_dev,
+                               int kind, int bits, int float_zero_point,
+                               int64_t rows, int64_t inner, int64_t t,
+                               void *stream);
+
 int qsb_magnitude_ema_reduced(float *magnitude, const double *abssum,
                               const double *nnz, const float *tensor_min,
                               int use_l0, int64_t channels, double count,

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "qsb_scale_to_decimal": (c_int, [_P, _P, c_int64, _P]),
     "qsb_lines_ema": (c_int, [_P, _P, _P, c_int64, c_int64, _P]),
     "qsb_row_quant_fused": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, _P]),
+    "qsb_row_quant_fused_masked": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, _P]),
     "qsb_magnitude_ema_reduced": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_double, c_int64, _P]),
     "qsb_magnitude_ema_full": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P]),
     "qsb_magnitude_ema_full_multi": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),

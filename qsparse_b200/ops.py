@@ -264,10 +264,11 @@ def row_quant_supported(x, rows: int) -> bool:
     return inner % 8 == 0 and inner <= 16384 and x.data_ptr() % 32 == 0
 
 
-def row_quant_fused_(x, param, kind: int, bits: int, t: int, float_zero_point=True):
+def row_quant_fused_(x, param, kind: int, bits: int, t: int, float_zero_point=True, mask=None):
     """K8: per-row estimate (abs-max or min/max) -> EMA into ``param`` (in place) -> fake-quantize, one launch.
     x: [rows, ...] fp32 contiguous; param: [rows, 1] (scale) or [rows, 2] (lines).
-    Returns (y, decimal or None)."""
+    ``mask``: optional element prune mask of x's shape: estimate and quantize ``x * mask`` (the weight chain
+    ``quantize(prune(layer))`` with a frozen mask).  Returns (y, decimal or None)."""
     lib = N.load_library()
     N.require_cuda(x, "x")
     N.require_cuda(param, "weight")
@@ -275,6 +276,15 @@ def row_quant_fused_(x, param, kind: int, bits: int, t: int, float_zero_point=Tr
     inner = x.numel() // rows
     y = torch.empty_like(x)
     dec = torch.empty(rows, dtype=torch.float32, device=x.device) if kind == ROW_DECIMAL else None
+    if mask is not None:
+        N.require_cuda(mask, "mask")
+        if mask.numel() != x.numel() or mask.dtype not in (torch.bool, torch.uint8) or not mask.is_contiguous():
+            raise ValueError("mask must be a contiguous bool / uint8 tensor with x's number of elements")
+        N.check(lib.qsb_row_quant_fused_masked(N.ptr(x), N.ptr(y), N.ptr(param), N.ptr(dec), N.ptr(mask), c_int(kind),
+                                               c_int(bits), c_int(1 if float_zero_point else 0), c_int64(rows),
+                                               c_int64(inner), c_int64(t), N.stream_ptr(x.device)),
+                "qsb_row_quant_fused_masked")
+        return y, dec
     N.check(lib.qsb_row_quant_fused(N.ptr(x), N.ptr(y), N.ptr(param), N.ptr(dec), c_int(kind), c_int(bits),
                                     c_int(1 if float_zero_point else 0), c_int64(rows), c_int64(inner), c_int64(t),
                                     N.stream_ptr(x.device)), "qsb_row_quant_fused")
