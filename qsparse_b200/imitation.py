@@ -38,6 +38,7 @@ def imitate(human: nn.Module, name: str, thing: Callable, bias_thing: Optional[C
         def bias(self):
             return getattr(self, name + "_bias")(read(self, "bias"))
 
+    Imitation._qsb_imitates = name      # which operator this level of the chain applies (fusion pass)
     Imitation.__name__ = base.__name__
     Imitation.__qualname__ = base.__qualname__
     human.__class__ = Imitation

@@ -224,9 +224,9 @@ class _RowFusedSte(torch.autograd.Function):
 
 
 class _TensorFusedSte(torch.autograd.Function):
-    """Per-tensor Decimal / Scaler layer step in three launches instead of five: reduction partials ->
-    ONE parameter kernel (finalize abs-max, scale EMA into ``weight``, decimal) -> fake-quantize; the
-    backward is the ordinary STE kernel.  Same results as ``optimize`` + ``forward``
+    """Per-tensor Decimal / Scaler layer step in two launches instead of five: the abs-max reduction,
+    whose last-arriving CTA finalizes it and updates scale EMA (into ``weight``) and decimal ->
+    fake-quantize; the backward is the ordinary STE kernel.  Same results as ``optimize`` + ``forward``
     (ref quantize.py:327-349, :24-131)."""
 
     @staticmethod
@@ -236,10 +236,10 @@ class _TensorFusedSte(torch.autograd.Function):
         layout = (1, 1, n)
         dev = xs.device
         decimal = torch.empty(1, dtype=torch.float32, device=dev)
-        ws = ops.reduce_partials(xs, layout)
-        ops.prune_quant_step_params(torch.zeros(1, device=dev), torch.ones(1, dtype=torch.bool, device=dev),
-                                    weight.data.view(-1), decimal, ws, layout, float(n), 0, 0, False, 0, bits,
-                                    quantizer.t, True)
+        # ONE launch: abs-max reduction whose last-arriving CTA finalizes and updates scale / decimal
+        ops.reduce_prune_quant_step(xs, layout, torch.zeros(1, device=dev),
+                                    torch.ones(1, dtype=torch.bool, device=dev), weight.data.view(-1), decimal,
+                                    float(n), 0, 0, False, 0, bits, quantizer.t, True)
         quantizer.t += 1
         if is_decimal:
             y = ops.fq_pow2_fwd(xs, decimal, layout)

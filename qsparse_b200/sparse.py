@@ -183,9 +183,9 @@ class MagnitudePruningCallback(nn.Module):
         return _MaskApply.apply(x, mask, out)
 
     def _fused_structured_step(self, x, sparsity, mask, t, refresh):
-        """update_magnitude [+ prune_and_update_mask] of the stock structured (channel-mask) case in three
-        launches — reduction partials, ONE parameter kernel (finalize, magnitude EMA, k-th value by rank
-        counting, mask), mask apply — instead of nine (reduce + finalize, EMA, a 4-launch select over C values,
+        """update_magnitude [+ prune_and_update_mask] of the stock structured (channel-mask) case in two
+        launches — the reduction, whose last-arriving CTA finalizes and does magnitude EMA, k-th value by rank
+        counting and the mask; then mask apply — instead of nine (reduce + finalize, EMA, a 4-launch select over C values,
         mask build, apply).  None when the case is not the stock one."""
         if not FUSE_PRUNE_STEP or type(self) is not MagnitudePruningCallback:
             return None
@@ -209,9 +209,13 @@ class MagnitudePruningCallback(nn.Module):
             else:
                 magnitude, mode = torch.empty(ch, dtype=torch.float32, device=x.device), 2
             dummy = torch.zeros(1, dtype=torch.float32, device=x.device)
-            ws = ops.reduce_partials(xs, layout)
-            ops.prune_quant_step_params(magnitude, mask.data.view(-1), dummy, None, ws, layout,
-                                        float(outer * inner), t, mode, refresh, k, 8, 0, False)
+            if ch <= ops.FUSED_STEP_MAX_CHANNELS:
+                ops.reduce_prune_quant_step(xs, layout, magnitude, mask.data.view(-1), dummy, None,
+                                            float(outer * inner), t, mode, refresh, k, 8, 0, False)
+            else:
+                ws = ops.reduce_partials(xs, layout)
+                ops.prune_quant_step_params(magnitude, mask.data.view(-1), dummy, None, ws, layout,
+                                            float(outer * inner), t, mode, refresh, k, 8, 0, False)
         return apply_mask(x, mask)
 
     def forward(self, x: torch.Tensor, sparsity: float, mask: torch.Tensor, name=""):

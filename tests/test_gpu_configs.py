@@ -23,9 +23,11 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
-@pytest.mark.parametrize("tag", ["scaler", "decimal"])
-def test_config1_mnist_end_to_end(tag):
-    """BASELINE config 1: 60 training steps of the converted MNIST net on the GPU.
+@pytest.mark.parametrize("tag,fuse", [("scaler", False), ("decimal", False), ("scaler", True), ("decimal", True)])
+def test_config1_mnist_end_to_end(tag, fuse):
+    """BASELINE config 1: 60 training steps of the converted MNIST net on the GPU (``fuse``: with the fusion
+    pass applied — the steady-state steps of the two prune->quantize activation sites then run through the
+    fused kernels, with the DEFAULT ScalerQuantizer callback as well as with DecimalQuantizer).
 
     (a) Teacher-forced parity: EVERY Prune/Quantize layer call of the run (2 + 8 layers x 60 steps)
         is checked against the oracle's restatement of the reference's layer logic on the identical
@@ -72,13 +74,43 @@ def test_config1_mnist_end_to_end(tag):
             assert bits_equal(npy(module.weight).reshape(-1), em.weight), ("scale", module.name, em.n)
             checked["quant"] += 1
 
+    from qsparse_b200.fused import FusedPruneQuantSequential
+    captured, seen, fused_sites = {}, {}, []
+
+    def capture(module, inputs, output):          # the activation in front of a fused site
+        captured[id(module)] = npy(output)
+
+    def site_hook(site, inputs, output):
+        """a fused step bypasses the two layers' own forwards (and their hooks): check it here against the
+        chained emulators — same state objects as the un-fused steps of the same layers use"""
+        if site.fused_steps == seen.get(id(site), 0):
+            return
+        seen[id(site)] = site.fused_steps
+        pre, p, qz = site._layers()
+        x = captured[id(pre)]
+        emp = emulators.setdefault(id(p), OraclePrune(0.5, 20, 10, 4))
+        emq = emulators.setdefault(id(qz), OracleQuantize(8, 10, tag))
+        exp = emq.forward(emp.forward(x), True)
+        assert bits_equal(npy(output), exp), ("fused site", p.name, emp.n)
+        assert np.array_equal(npy(p.mask), emp.mask), ("mask", p.name, emp.n)
+        assert ulp_diff(npy(p.callback.magnitude), emp.mag).max() <= 8, ("mag", p.name, emp.n)
+        assert bits_equal(npy(qz.weight).reshape(-1), emq.weight), ("scale", qz.name, emq.n)
+        checked["prune"] += 1
+        checked["quant"] += 1
+
     orig_build = build
 
     def build_hooked(qs_, cb):
         model = orig_build(qs_, cb)
+        if fuse:
+            qs_.fuse_prune_quantize(model)
         for m in model.modules():
             if isinstance(m, (sp.PruneLayer, q.QuantizeLayer)):
                 m.register_forward_hook(hook)
+            if isinstance(m, FusedPruneQuantSequential):
+                fused_sites.append(m)
+                m.register_forward_hook(site_hook)
+                m._layers()[0].register_forward_hook(capture)
         return model
 
     import oracle.gen_golden_config1 as cfg1
@@ -88,6 +120,9 @@ def test_config1_mnist_end_to_end(tag):
     finally:
         cfg1.build = orig_build
     assert checked == {"prune": 2 * 60, "quant": 8 * 60}
+    if fuse:   # steps 21-29, 31-39, 41-49, 51-59 of both sites are steady-state steps
+        assert len(fused_sites) == 2 and all(s_.fused_steps == 36 for s_ in fused_sites), \
+            [s_.fused_steps for s_ in fused_sites]
 
     # ---- (b) against the reference's CPU run --------------------------------------------------
     assert np.array_equal(out["sparsity"], ref[f"{tag}/sparsity"])
@@ -208,7 +243,7 @@ def test_preload_state_dict_roundtrip():
 
 
 # ----------------------------------------------------------------------------- fusion pass
-def _converted_net(fuse: bool):
+def _converted_net(fuse: bool, callback="decimal", via_convert=False):
     import qsparse_b200 as q
     torch.manual_seed(7)
     net = torch.nn.Sequential(
@@ -217,20 +252,22 @@ def _converted_net(fuse: bool):
         torch.nn.Flatten(), torch.nn.Linear(24 * 8 * 8, 10)).cuda()
     net = q.convert(net, q.prune(sparsity=0.5, dimensions={1}, start=2, interval=3, repetition=2),
                     activation_layers=[torch.nn.ReLU], log=False)
-    net = q.convert(net, q.quantize(bits=8, channelwise=-1, timeout=4, callback=q.DecimalQuantizer()),
-                    activation_layers=[torch.nn.ReLU], log=False)
-    if fuse:
+    cb = {"decimal": q.DecimalQuantizer, "scaler": q.ScalerQuantizer, "default": lambda: None}[callback]()
+    net = q.convert(net, q.quantize(bits=8, channelwise=-1, timeout=4, callback=cb),
+                    activation_layers=[torch.nn.ReLU], log=False, fuse=fuse and via_convert)
+    if fuse and not via_convert:
         net = q.fuse_prune_quantize(net)
     return net
 
 
-def test_fusion_pass_equals_unfused_layers():
+@pytest.mark.parametrize("callback,via_convert", [("decimal", False), ("scaler", False), ("default", True)])
+def test_fusion_pass_equals_unfused_layers(callback, via_convert):
     """fuse_prune_quantize keeps the module tree / state_dict keys and gives bit-identical outputs, gradients
     and layer state over warm-up, ramp, steady-state and eval steps; the fused route is actually taken."""
     from qsparse_b200.fused import FusedPruneQuantSequential
     torch.backends.cudnn.deterministic = True      # the two nets must see identical conv arithmetic
     torch.backends.cudnn.benchmark = False
-    a, b = _converted_net(False), _converted_net(True)
+    a, b = _converted_net(False, callback), _converted_net(True, callback, via_convert)
     assert list(a.state_dict().keys()) == list(b.state_dict().keys())
     sites = [m for m in b.modules() if isinstance(m, FusedPruneQuantSequential)]
     assert len(sites) == 2
@@ -260,6 +297,55 @@ def test_fusion_pass_equals_unfused_layers():
     # checkpoint interchange: the unfused model loads the fused model's state and vice versa
     a.load_state_dict(b.state_dict())
     b.load_state_dict(a.state_dict())
+
+
+def test_weight_chain_fusion_equals_unfused():
+    """quantize(prune(conv)) with an unstructured mask that freezes after `stop_mask_refresh`: the fusion pass
+    sends the frozen-mask training steps through K8 with the element mask; outputs, weight gradients and all
+    layer state stay bit-identical to the un-fused chain over warm-up, refresh, frozen and eval steps."""
+    import qsparse_b200 as q
+    q.set_qsparse_options(log_on_created=False)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+
+    def make(cb_name, fuse):
+        torch.manual_seed(11)
+        conv = torch.nn.Conv2d(16, 32, 3, padding=1).cuda()
+        cb = {"decimal": q.DecimalQuantizer, "scaler": q.ScalerQuantizer, "adaptive": q.AdaptiveQuantizer}[cb_name]()
+        pcb = q.MagnitudePruningCallback(mask_refresh_interval=1, stop_mask_refresh=4)
+        conv = q.prune(conv, sparsity=0.6, dimensions={0, 1, 2, 3}, start=1, interval=1, repetition=1, callback=pcb)
+        conv = q.quantize(conv, bits=6, channelwise=0, timeout=2, callback=cb)
+        net = torch.nn.Sequential(conv).cuda()
+        if fuse:
+            q.fuse_prune_quantize(net)
+        return net
+
+    for cb_name in ("decimal", "scaler", "adaptive"):
+        a, b = make(cb_name, False), make(cb_name, True)
+        a.train(), b.train()
+        for step in range(12):
+            x = torch.randn(4, 16, 10, 10, device="cuda", generator=torch.Generator("cuda").manual_seed(50 + step))
+            if step == 9:
+                a.eval(), b.eval()
+            ya, yb = a(x), b(x)
+            assert torch.equal(ya, yb), (cb_name, step)
+            if step != 9:
+                ya.square().mean().backward()
+                yb.square().mean().backward()
+                for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+                    if pa.grad is not None:
+                        assert torch.equal(pa.grad, pb.grad), (cb_name, step, na)
+                        # a tiny SGD step so that the weights (and with them the statistics) move
+                        with torch.no_grad():
+                            pa.sub_(0.05 * pa.grad)
+                            pb.sub_(0.05 * pb.grad)
+                        pa.grad = pb.grad = None
+            sa, sb = a.state_dict(), b.state_dict()
+            assert sa.keys() == sb.keys()
+            for key in sa:
+                assert torch.equal(sa[key], sb[key]), (cb_name, step, key)
+            a.train(), b.train()
+        assert b[0].fused_weight_steps >= 5, (cb_name, b[0].fused_weight_steps)
 
 
 def test_unstructured_callback_fused_step_equals_unfused():

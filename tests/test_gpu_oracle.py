@@ -713,6 +713,28 @@ def test_row_quant_fused_vs_oracle_and_unfused(shape, kind, row_variant):
         assert torch.equal(y.view(torch.int32), y_unf.view(torch.int32)), (kind, step, "y vs unfused")
 
 
+@pytest.mark.parametrize("shape", [(64, 4608), (300, 1152), (37, 256), (16, 16384)])
+@pytest.mark.parametrize("kind", ["decimal", "scaler", "line"])
+def test_row_quant_fused_masked_equals_mask_apply_then_row_quant(shape, kind):
+    """K8 with an element mask == mask_apply followed by K8, bit for bit (values, parameters, decimals)"""
+    from qsparse_b200 import ops
+    code = {"decimal": ops.ROW_DECIMAL, "scaler": ops.ROW_SCALER, "line": ops.ROW_LINE}[kind]
+    x = cu(rnd(shape, 21) * 0.05)
+    mask = cu(np.random.default_rng(22).random(shape) > 0.6)
+    wsz = 2 if kind == "line" else 1
+    pa = torch.zeros(shape[0], wsz, device="cuda")
+    pb = torch.zeros(shape[0], wsz, device="cuda")
+    for t in range(3):
+        tt = t + 1 if kind == "line" else t
+        xm = ops.mask_apply(x, mask, (1, 1, x.numel()))
+        ya, da = ops.row_quant_fused_(xm, pa, code, 4, tt)
+        yb, db = ops.row_quant_fused_(x, pb, code, 4, tt, mask=mask)
+        assert bits_equal(npy(ya), npy(yb)) and bits_equal(npy(pa), npy(pb)), (kind, t)
+        if da is not None:
+            assert bits_equal(npy(da), npy(db))
+        x = x * 1.1
+
+
 def test_row_quant_fused_nan_and_unsupported():
     from qsparse_b200 import ops
     x = rnd((4, 512), 3)
