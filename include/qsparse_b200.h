@@ -361,6 +361,14 @@ int qsb_mask_build_apply(const float *importance, int take_abs,
                          const float *thr_dev, const float *x, float *y,
                          uint8_t *mask_out, int64_t n, void *stream);
 
+/* ref: DecimalQuantizer.forward group-wise sharing  qsparse/quantize.py:361-366
+ *   out[c, :] = mean over {c' : labels[c'] == labels[c]} of values[c', :]
+ * values / out: float [channels, weight_size] (may alias), labels: int64 [channels] in [0, groups).
+ * One launch instead of a host loop over the groups; the mean is the correctly rounded one. */
+int qsb_group_mean(const float *values, const int64_t *labels, float *out,
+                   int64_t channels, int64_t weight_size, int64_t groups,
+                   void *stream);
+
 /* ------------------------------------------------------------------------
  * Fused structured prune -> pow2 quantize parameter step: everything the
  * reference does between "statistics are reduced" and "apply" for

@@ -5,7 +5,7 @@ sm_100a CUDA kernels, behind qsparse's own Python API (export list of
 from .convert import convert
 from .fuse import fuse_bn
 from .fused import fuse_prune_quantize
-from .quantize import quantize, DecimalQuantizer, ScalerQuantizer, AdaptiveQuantizer
+from .quantize import quantize, DecimalQuantizer, ScalerQuantizer, AdaptiveQuantizer, PercentileQuantizer
 from .sparse import MagnitudePruningCallback, UniformPruningCallback, prune, devise_layerwise_pruning_schedule
 from .util import auto_name_prune_quantize_layers, calculate_mask_given_importance
 from .util import get_option as get_qsparse_option

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "qsb_kth_dist_final": (c_int, [c_int64, _P, _P, _P]),
     "qsb_mask_from_threshold": (c_int, [_P, c_int, _P, _P, c_int64, _P]),
     "qsb_mask_build_apply": (c_int, [_P, c_int, _P, _P, _P, _P, c_int64, _P]),
+    "qsb_group_mean": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P]),
     "qsb_prune_quant_params": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_double, c_int64, c_int,
                                        c_int, c_int64, c_int, c_int64, c_int, _P]),
     "qsb_reduce_partials": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, _P]),

@@ -76,6 +76,34 @@ __global__ void magnitude_ema_reduced_kernel(float *mag, const double *abssum,
   mag[i] = magnitude_ema_step(mag[i], m, t);
 }
 
+// group-wise scale sharing (ref qsparse/quantize.py:361-366): every channel's parameter row is replaced
+// by the mean of its group's rows.  One CTA; thread (g, col) sums the group's members in ascending
+// channel order in fp64 and rounds once (the correctly rounded mean: within 1 ulp of torch's fp32 mean
+// whatever its summation order), then every channel picks up its group's mean.  Replaces a Python loop
+// of `group_num` boolean-index + mean + scatter launches (each with a host sync for the index count).
+__global__ void __launch_bounds__(1024)
+    group_mean_kernel(const float *values, const long long *labels, float *out, int channels, int wsz,
+                      int groups) {
+  extern __shared__ float s_mean[];  // [groups * wsz]
+  for (int i = threadIdx.x; i < groups * wsz; i += blockDim.x) {
+    const int g = i / wsz, col = i - g * wsz;
+    double acc = 0.0;
+    int cnt = 0;
+    for (int c = 0; c < channels; ++c)
+      if (labels[c] == g) {
+        acc += (double)values[(int64_t)c * wsz + col];
+        ++cnt;
+      }
+    s_mean[i] = cnt ? (float)(acc / (double)cnt) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < channels * wsz; i += blockDim.x) {
+    const int c = i / wsz, col = i - c * wsz;
+    const long long g = labels[c];
+    out[i] = (g >= 0 && g < groups) ? s_mean[(int)g * wsz + col] : values[i];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // fused structured prune -> pow2 quantize parameter step (one CTA)
 // ---------------------------------------------------------------------------
@@ -279,6 +307,18 @@ extern "C" int qsb_magnitude_ema_reduced(float *magnitude, const double *abssum,
   magnitude_ema_reduced_kernel<<<blocks_for(channels, 256), 256, 0,
                                  (cudaStream_t)stream>>>(
       magnitude, abssum, nnz, tensor_min, use_l0, channels, count, t);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qsb_group_mean(const float *values, const int64_t *labels, float *out, int64_t channels,
+                              int64_t weight_size, int64_t groups, void *stream) {
+  if (channels < 0 || weight_size < 1 || groups < 1) return QSB_E_BADARG;
+  if (channels == 0) return 0;
+  if (!values || !labels || !out) return QSB_E_BADARG;
+  if (groups * weight_size > 8192 || channels > (1 << 24)) return QSB_E_UNSUPPORTED;
+  group_mean_kernel<<<1, 1024, (size_t)(groups * weight_size) * sizeof(float), (cudaStream_t)stream>>>(
+      values, reinterpret_cast<const long long *>(labels), out, (int)channels, (int)weight_size, (int)groups);
   QSB_LAUNCH_CHECK();
   return 0;
 }

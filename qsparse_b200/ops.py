@@ -244,6 +244,22 @@ def scale_to_decimal(scale):
     return d
 
 
+def group_mean(values, labels, groups: int):
+    """every row of ``values`` [C, weight_size] replaced by the mean of its group's rows (``labels`` int64 [C]);
+    one launch, result in a new tensor"""
+    lib = N.load_library()
+    N.require_cuda(values, "values")
+    v = values.detach()
+    if v.dtype != torch.float32 or not v.is_contiguous():
+        v = v.float().contiguous()
+    lab = labels.detach().to(device=v.device, dtype=torch.int64).contiguous()
+    out = torch.empty_like(v)
+    c = v.shape[0] if v.dim() > 0 else 1
+    N.check(lib.qsb_group_mean(N.ptr(v), N.ptr(lab), N.ptr(out), c_int64(c), c_int64(max(v.numel() // max(c, 1), 1)),
+                               c_int64(int(groups)), N.stream_ptr(v.device)), "qsb_group_mean")
+    return out
+
+
 def lines_ema_(lines, mn, mx, t: int):
     lib = N.load_library()
     N.require_cuda(lines, "lines")

@@ -401,16 +401,67 @@ class DecimalQuantizer(BaseQuantizer):
             clustering = AgglomerativeClustering(n_clusters=self.group_num)
             clustering.fit(scaler.detach().cpu().numpy())
             self.groups = nn.Parameter(torch.from_numpy(clustering.labels_).to(scaler.device), requires_grad=False)
-        grouped = torch.clone(scaler)
-        for gi in range(self.group_num):  # tiny [C, weight_size] tensors (quantize.py:361-366)
-            member = self.groups == gi
-            grouped[member] = grouped[member].mean(dim=0)
-        return grouped
+        # per-group mean of the [C, weight_size] parameter rows (quantize.py:361-366) in ONE launch on the
+        # device: the reference's loop does `group_num` boolean-index + mean + scatter steps, each with a host
+        # sync.  The mean is the correctly rounded one (<= 1 ulp from torch's fp32 mean).
+        return ops.group_mean(scaler, self.groups, self.group_num).view(scaler.shape)
 
     def forward(self, tensor, bits, scaler, channel_index=-1, **kwargs):
         if self.t >= self.group_timeout and self.group_num > 0 and scaler.numel() > self.group_num:
             scaler = self._group(scaler)
         return self.quantize(tensor, bits, scaler, channel_index, **kwargs)
+
+
+class PercentileQuantizer(DecimalQuantizer):
+    """EXTENSION (not in qsparse 2.0.1; BASELINE.json's north_star asks for "abs-max and percentile statistics"):
+    the scale statistic is the ``percentile``-th percentile of ``|x|`` instead of its maximum,
+
+        new = sorted(|x|)[k] / 2^(bits-1),   k = clamp(ceil(percentile / 100 * n) - 1, 0, n - 1)
+
+    per tensor (``channel_index=-1``) or per leading-axis channel (``channel_index=0``), with the same running
+    mean as ``DecimalQuantizer`` (ref qsparse/quantize.py:344-348).  The k-th value comes from the exact
+    one-pass select of the prune path (``qsb_kth_value(take_abs)``, 4 B/elem, no sort, no host sync).
+    ``use_float_scaler=True`` quantizes with the scale itself (like ``ScalerQuantizer``), otherwise with the
+    nearest power of two (like ``DecimalQuantizer``).  ``percentile=100`` reproduces the abs-max estimators bit
+    for bit.  The forward does not saturate outliers (the reference's fake-quant functions never clamp in the
+    forward); the integer export does."""
+
+    def __init__(self, percentile: float = 99.9, use_float_scaler: bool = False, **kwargs):
+        super().__init__(**kwargs)
+        if not 0.0 < percentile <= 100.0:
+            raise ValueError("percentile must be in (0, 100]")
+        self.percentile = float(percentile)
+        self.use_float_scaler = bool(use_float_scaler)
+        self.function = ScalerQuantization.apply if use_float_scaler else DecimalQuantization.apply
+
+    @staticmethod
+    def rank(percentile: float, n: int) -> int:
+        return min(max(int(math.ceil(percentile / 100.0 * n)) - 1, 0), n - 1)
+
+    def optimize(self, x, bits, weight=None, batched=False, channel_index=-1, **kwargs):
+        N.require_cuda(x, "x")
+        if channel_index not in (-1, 0) or (batched and channel_index == 0):
+            raise NotImplementedError("PercentileQuantizer estimates per tensor or per leading-axis channel")
+        wshape = self.get_weight_shape(x, channel_index)
+        with torch.no_grad():
+            xs = N.as_f32_contiguous(x.detach())
+            if channel_index < 0:
+                stat = ops.kth_value(xs.reshape(-1), self.rank(self.percentile, xs.numel()), take_abs=True)
+            else:
+                rows = xs.reshape(xs.shape[0], -1)
+                k = self.rank(self.percentile, rows.shape[1])
+                stat = torch.cat([ops.kth_value_batched(list(rows[i:i + 32]), [k] * len(rows[i:i + 32]),
+                                                        take_abs=True) for i in range(0, rows.shape[0], 32)])
+            if weight is None:
+                weight = torch.zeros(wshape, dtype=torch.float32, device=x.device)
+            target = weight.data if isinstance(weight, nn.Parameter) else weight
+            assert tuple(target.shape) == tuple(wshape) and target.is_contiguous()
+            ops.scale_ema_(target, stat.contiguous(), bits, self.t)
+        self.t += 1
+        return weight
+
+    def optimize_and_forward(self, *args, **kwargs):
+        return None          # the fused abs-max routes do not apply
 
 
 class ScalerQuantizer(DecimalQuantizer):

@@ -325,6 +325,15 @@ class PruneLayer(nn.Module):
         assert len(x.shape) > 1
         N.require_cuda(x, "x")
         mask_shape = [s if i in self.dimensions else 1 for i, s in enumerate(x.shape)]
+        # the kernels address a mask as one contiguous run of kept axes ([1,C,1,1], [1,C,H,W], [Cout,1,1,1], the
+        # full shape ...): say so now, with the layer's name, rather than at the first pruning step
+        try:
+            ops.mask_layout(list(x.shape), mask_shape)
+        except NotImplementedError as exc:
+            raise NotImplementedError(
+                f"PruneLayer{' @ ' + self.name if self.name else ''}: dimensions={sorted(self.dimensions)} on an input of "
+                f"shape {tuple(x.shape)} keeps non-adjacent axes; qsparse_b200 supports prune masks whose kept axes "
+                f"form one contiguous run (e.g. {{1}}, {{1, 2, 3}}, {{0}}, all axes)") from exc
         self.mask = nn.Parameter(torch.ones(*mask_shape, dtype=torch.bool, device=x.device), requires_grad=False)
         if self.mask.numel() == 1:
             logging.warn(f"the mask shape of {self.name} is {tuple(self.mask.shape)}, which is not prunable")
@@ -376,11 +385,16 @@ def prune(inp: nn.Module = None, sparsity: float = 0.5, dimensions: Iterable[int
 
 
 def devise_layerwise_pruning_schedule(net: nn.Module, start: int = 1, interval: int = 10,
-                                      mask_refresh_interval: int = 1, inplace=False):
+                                      mask_refresh_interval: int = 1, inplace=False, fix_ramp: bool = False):
     """Stagger the start of every PruneLayer, attribute for attribute as the reference
     does (ref qsparse/sparse.py:343-359).  Note that the reference leaves
-    ``rampup_interval`` untouched, which makes the ramp formula overshoot afterwards
-    (SURVEY Q15); that behaviour is kept, not fixed."""
+    ``rampup_interval`` untouched, which makes the ramp formula of ``PruneLayer.forward``
+    (sparse.py:252-257) evaluate ``(1 - old_interval / new_interval)^3`` at the layer's single
+    schedule point — a target sparsity far outside [0, 1] whenever the layer was created with a
+    different interval.  Default: that behaviour is kept, not fixed.
+
+    ``fix_ramp=True`` (extension, opt-in): also set ``rampup_interval = interval`` on every layer, so
+    the one-shot schedule reaches exactly the layer's configured ``sparsity``."""
     if not inplace:
         net = copy.deepcopy(net)
     layers = [m for m in net.modules() if isinstance(m, PruneLayer)]
@@ -392,6 +406,8 @@ def devise_layerwise_pruning_schedule(net: nn.Module, start: int = 1, interval: 
         layer.schedules = [start]
         layer.callback.mask_refresh_interval = mask_refresh_interval
         layer.callback.stop_mask_refresh = interval
+        if fix_ramp:
+            layer.rampup_interval = interval
         if weight_only:
             layer.callback.running_average = False
         start += interval + 1

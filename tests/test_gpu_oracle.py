@@ -416,6 +416,47 @@ def test_full_size_properties_config2():
     assert torch.equal(again["abssum"], st["abssum"])        # deterministic: fixed summation order
 
 
+def test_full_size_config2_step_vs_oracle_every_element():
+    """The WHOLE [256,64,56,56] tensor of BASELINE config 2 through two fused training steps (one-launch
+    statistics + parameter step, forward, backward) against the plain-C oracle on the identical tensor: all
+    51,380,224 outputs and gradients bit for bit, mask / scale / decimal exact, magnitude within the documented
+    mean tolerance."""
+    from concurrent.futures import ThreadPoolExecutor
+    from qsparse_b200 import ops
+    torch.manual_seed(2)
+    shape, layout, C = (256, 64, 56, 56), (256, 64, 3136), 64
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.relu(torch.randn(shape, device="cuda", generator=gen)) * torch.linspace(0.5, 1.5, C, device="cuda").view(
+        1, C, 1, 1)
+    g = torch.randn(shape, device="cuda", generator=gen) * 3
+    xh, gh = npy(x), npy(g)
+    mag = torch.zeros(C, device="cuda")
+    mask = torch.ones(C, dtype=torch.bool, device="cuda")
+    scale = torch.zeros(1, device="cuda")
+    dec = torch.zeros(1, device="cuda")
+    mag_ref, mask_ref, scale_ref = np.zeros(C, np.float32), np.ones(C, bool), np.zeros(1, np.float32)
+    k = orc.kth_index(0.75, C)
+    pool = ThreadPoolExecutor(8)
+    parts = [slice(i * 32, (i + 1) * 32) for i in range(8)]
+    for t in range(2):
+        ops.reduce_prune_quant_step(x, layout, mag, mask, scale, dec, 256 * 3136.0, t, 1, t > 0, k, 8, t, True)
+        y = ops.fq_pow2_fwd(x, dec, layout, mask=mask)
+        _, gx = ops.ste_bwd(g, dec, True, 8, 0, layout, mask=mask, clamp_in_place=False, want_gx=True)
+        mag_ref = orc.magnitude_ema(mag_ref, orc.squeeze_mean_abs(xh, (1, C, 1, 1)).reshape(-1), t)
+        if t > 0:
+            mask_ref, _ = orc.mask_given_importance(mag_ref, 0.75)
+        scale_ref = orc.scale_ema(scale_ref, np.array([np.max(orc.absmax(xh, 1) * mask_ref)], np.float32), 8, t)
+        dec_ref = orc.scale_to_decimal(scale_ref)
+        assert np.array_equal(npy(mask), mask_ref) and bits_equal(npy(scale), scale_ref) and bits_equal(npy(dec), dec_ref)
+        assert ulp_diff(npy(mag), mag_ref).max() <= 8
+        yh, gxh = npy(y), npy(gx)
+        y_ref = list(pool.map(lambda sl: orc.fq_pow2_fwd(xh[sl], dec_ref, 1, mask=mask_ref), parts))
+        g_ref = list(pool.map(lambda sl: orc.ste_bwd(gh[sl].copy(), dec_ref, 8, 1, True, False, mask=mask_ref)[1], parts))
+        for sl, yr, gr in zip(parts, y_ref, g_ref):
+            assert np.array_equal(yh[sl].view(np.uint32), yr.view(np.uint32)), t
+            assert np.array_equal(gxh[sl].view(np.uint32), gr.view(np.uint32)), t
+
+
 def test_full_size_select_64M():
     """64 Mi-element importance (BASELINE config 4): exact threshold == torch.sort's, mask count."""
     from qsparse_b200 import calculate_mask_given_importance, ops
@@ -1116,3 +1157,76 @@ def test_prune_step_fused_many_small_tensors_and_repeat():
         for i in range(len(sizes)):
             assert torch.equal(mags_a[i], mags_b[i]) and torch.equal(masks_a[i], masks_b[i]), (step, i)
             assert torch.equal(outs_a[i].view(torch.int32), outs_b[i].view(torch.int32)), (step, i)
+
+
+# ----------------------------------------------------------------------------- extensions (north_star "percentile")
+@pytest.mark.parametrize("shape,ci", [((64, 3, 7, 7), -1), ((1 << 22,), -1), ((48, 1152), 0), ((5, 4096), 0)])
+@pytest.mark.parametrize("pct", [99.9, 50.0, 100.0])
+def test_percentile_quantizer_statistic_vs_numpy(shape, ci, pct):
+    """PercentileQuantizer.optimize: scale = sorted(|x|)[k] / 2^(bits-1) with the running mean of the abs-max
+    estimators, against a numpy restatement; percentile = 100 equals DecimalQuantizer bit for bit."""
+    import qsparse_b200 as q
+    bits = 6
+    est = q.PercentileQuantizer(percentile=pct)
+    ref_w = None
+    dq = q.DecimalQuantizer()
+    w = wd = None
+    for t in range(3):
+        x = rnd(shape, 700 + t) * (1 + 0.3 * t)
+        w = est.optimize(cu(x), bits, w, channel_index=ci)
+        rows = np.abs(x).reshape(1, -1) if ci < 0 else np.abs(x).reshape(shape[0], -1)
+        k = q.PercentileQuantizer.rank(pct, rows.shape[1])
+        stat = np.sort(rows, axis=1)[:, k].astype(np.float32)
+        ref_w = orc.scale_ema(np.zeros_like(stat) if ref_w is None else ref_w, stat, bits, t)
+        assert bits_equal(npy(w).reshape(-1), ref_w), (pct, t)
+        if pct == 100.0:
+            wd = dq.optimize(cu(x), bits, wd, channel_index=ci)
+            assert bits_equal(npy(w), npy(wd))
+    # through a layer: forward + backward run, scale is what the estimator produced
+    layer = q.quantize(bits=bits, channelwise=ci, timeout=1, callback=q.PercentileQuantizer(percentile=pct,
+                                                                                           use_float_scaler=True))
+    layer.batch_dimension = -1
+    layer.train()
+    xt = cu(rnd(shape, 710)).requires_grad_(True)
+    layer(xt)
+    y = layer(xt)
+    y.sum().backward()
+    assert y.shape == xt.shape and bool(torch.isfinite(y).all()) and xt.grad is not None
+
+
+@pytest.mark.parametrize("C,wsz,groups", [(64, 1, 4), (1000, 1, 7), (96, 2, 5), (8, 1, 8)])
+def test_group_mean_equals_reference_loop(C, wsz, groups):
+    """qsb_group_mean == the reference's per-group `grouped[member] = grouped[member].mean(dim=0)` loop
+    (quantize.py:361-366) to <= 1 ulp (it is the correctly rounded mean), exact for groups of equal values"""
+    from qsparse_b200 import ops
+    rng = np.random.default_rng(C)
+    vals = (np.abs(rng.standard_normal((C, wsz))) * 0.05 + 1e-3).astype(np.float32)
+    labels = rng.integers(0, groups, C)
+    labels[:groups] = np.arange(groups)
+    got = npy(ops.group_mean(cu(vals), torch.from_numpy(labels).cuda(), groups))
+    ref = vals.copy()
+    ref64 = vals.astype(np.float64)
+    for g in range(groups):
+        m = labels == g
+        ref[m] = torch.from_numpy(vals[m]).mean(dim=0).numpy()
+        exact = ref64[m].mean(axis=0).astype(np.float32)
+        assert bits_equal(got[m], np.broadcast_to(exact, got[m].shape))
+    assert ulp_diff(got, ref).max() <= 1
+    same = np.full((C, wsz), 0.125, np.float32)
+    assert bits_equal(npy(ops.group_mean(cu(same), torch.from_numpy(labels).cuda(), groups)), same)
+
+
+def test_groupwise_quantizer_uses_device_group_mean():
+    """DecimalQuantizer(group_num=...) after its group timeout: decimals equal the reference loop's"""
+    import qsparse_b200 as q
+    cb = q.DecimalQuantizer(group_num=3, group_timeout=0)
+    cb.t = 1
+    x = cu(rnd((24, 40), 31))
+    scaler = cu((np.abs(rnd((24, 1), 32)) * 0.02 + 1e-3))
+    y = cb(x, 8, scaler, channel_index=0)
+    labels = cb.groups.cpu().numpy()
+    grouped = npy(scaler).copy()
+    for g in range(3):
+        grouped[labels == g] = grouped[labels == g].mean(axis=0)
+    exp = orc.fq_pow2_fwd(npy(x), orc.scale_to_decimal(grouped.reshape(-1)), 0)
+    assert bits_equal(npy(y), exp)

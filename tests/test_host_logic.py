@@ -204,3 +204,27 @@ def test_uniform_callback_device_rng_flag():
     assert q.UniformPruningCallback().device_rng is False
     cb = q.UniformPruningCallback(mask_refresh_interval=3, device_rng=True)
     assert cb.device_rng is True and cb.mask_refresh_interval == 3
+
+
+def test_layerwise_schedule_reference_behaviour_and_fixed_variant():
+    """devise_layerwise_pruning_schedule replicates the reference (rampup_interval untouched: the ramp formula
+    overshoots); fix_ramp=True makes the single schedule point reach exactly `sparsity`."""
+    def net():
+        return nn.Sequential(qs.prune(sparsity=0.5, start=100, interval=100, repetition=4),
+                             qs.prune(sparsity=0.75, start=100, interval=100, repetition=4))
+
+    def target(layer):
+        n = layer.schedules[0]
+        ratio = (1.0 - (n - layer.start + layer.rampup_interval) / (layer.interval * layer.repetition)) ** 3
+        return layer.sparsity * (1 - ratio)
+
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        kept = qs.devise_layerwise_pruning_schedule(net(), start=1, interval=10)
+        fixed = qs.devise_layerwise_pruning_schedule(net(), start=1, interval=10, fix_ramp=True)
+    assert [l.start for l in kept] == [1, 12] and [l.schedules for l in kept] == [[1], [12]]
+    assert [l.rampup_interval for l in kept] == [100, 100]            # untouched, like the reference
+    assert target(kept[0]) == 0.5 * (1 - (1.0 - 100 / 10) ** 3)       # = 365: the reference's overshoot
+    assert [l.rampup_interval for l in fixed] == [10, 10]
+    assert target(fixed[0]) == 0.5 and target(fixed[1]) == 0.75
+    for a, b in zip(kept, fixed):
+        assert (a.start, a.interval, a.repetition, a.schedules) == (b.start, b.interval, b.repetition, b.schedules)
