@@ -756,7 +756,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json configuration (1-based index into `configs`; 2 = the metric's headline, default)")
     ap.add_argument("--sparsity", type=float, default=None,
                     help="config 2: channel sparsity, default 0.75 (0 = the dense line: 63 of 64 channels kept, no "
@@ -770,6 +770,7 @@ def main():
                     help="graph: the forward half of the step is one captured CUDA graph (default)")
     ap.add_argument("--row-variant", type=int, default=None, choices=[0, 2], help="development: tuning key 17")
     ap.add_argument("--keep-hint", type=int, default=None, choices=[0, 1], help="development: tuning key 18")
+    ap.add_argument("--c1-decimal", action="store_true", help="config 1: DecimalQuantizer instead of the default ScalerQuantizer")
     ap.add_argument("--strong", action="store_true", help="config 5: strong scaling (total size fixed as N grows)")
     args = ap.parse_args()
     if args.config == 2 and args.sparsity is None:

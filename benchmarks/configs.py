@@ -647,14 +647,213 @@ def cpu_c5(threads):
             "elems_per_s": round(n / dt, 1)}
 
 
+# ============================================================================= config 1
+C1_METRIC = "MNIST-net training steps/s (8-bit quantize + 50% channel prune, batch 64)"
+C1_BATCH = 64
+
+
+def c1_config(kind):
+    return {"workload": "config[0]: the CNN of examples/mnist.py (conv 1-32-64, fc 9216-128-10, BatchNorm), batch 64 of "
+                        "synthetic MNIST-shaped data, converted with prune(sparsity=0.5, dimensions={1}, start=20, "
+                        "interval=10, repetition=4) on the first two ReLU outputs and quantize(bits=8, channelwise=-1, "
+                        f"timeout=10, callback={kind}) on the input, 4 weights and 3 activations; one step = forward + "
+                        "nll_loss + backward + Adadelta step, in the steady state (after step 60)",
+            "batch": C1_BATCH, "quantizer": kind,
+            "parallelism": "replicas only (launch-bound: every tensor is < 6 MB)",
+            "l2": "every tensor fits the L2: this configuration measures launch / host overhead, not bandwidth"}
+
+
+def _c1_net(torch):
+    nn, F = torch.nn, torch.nn.functional
+
+    class Net(nn.Module):
+        """topology of examples/mnist.py:17-44"""
+
+        def __init__(self):
+            super().__init__()
+            self.conv_part = nn.Sequential(
+                nn.Conv2d(1, 32, 3, 1), nn.BatchNorm2d(32), nn.ReLU(),
+                nn.Conv2d(32, 64, 3, 1), nn.BatchNorm2d(64), nn.ReLU(),
+                nn.MaxPool2d(2), nn.Dropout(0.0))
+            self.linear_part = nn.Sequential(
+                nn.Flatten(), nn.Linear(9216, 128), nn.BatchNorm1d(128), nn.ReLU(), nn.Dropout(0.0), nn.Linear(128, 10))
+
+        def forward(self, x):
+            return F.log_softmax(self.linear_part(self.conv_part(x)), dim=1)
+
+    torch.manual_seed(1)
+    return Net()
+
+
+def _c1_convert(torch, q, net, kind, fuse):
+    nn = torch.nn
+    cb = {"ScalerQuantizer": q.ScalerQuantizer, "DecimalQuantizer": q.DecimalQuantizer}[kind]
+    net = q.convert(net, q.prune(sparsity=0.5, dimensions={1}, start=20, interval=10, repetition=4),
+                    activation_layers=[nn.ReLU], excluded_activation_layer_indexes=[(nn.ReLU, [-1])], log=False)
+    return q.convert(net, q.quantize(bits=8, channelwise=-1, timeout=10, callback=cb()),
+                     activation_layers=[nn.ReLU], weight_layers=[nn.Conv2d, nn.Linear], input=True, log=False,
+                     fuse=fuse)
+
+
+def _c1_time(torch, model, dev, steps, warm, host_batches=None):
+    """(wall ms/step, CUDA-event ms/step, losses) of `steps` training steps after `warm` warm-up steps"""
+    F = torch.nn.functional
+    model.train()
+    opt = torch.optim.Adadelta([p for p in model.parameters() if p.requires_grad], lr=1.0)
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = torch.randn(C1_BATCH, 1, 28, 28, device=dev, generator=g)
+    y = torch.randint(0, 10, (C1_BATCH,), device=dev, generator=g)
+
+    def step(i):
+        if host_batches is not None:
+            hx, hy = host_batches[i % len(host_batches)]
+            xb, yb = hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)
+        else:
+            xb, yb = x, y
+        opt.zero_grad(set_to_none=True)
+        loss = F.nll_loss(model(xb), yb)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    last = None
+    for i in range(steps):
+        last = step(i)
+        if host_batches is not None:
+            last = last.item()         # the step's result is read back every step on the e2e path
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps * 1e3
+    return wall, e0.elapsed_time(e1) / steps, float(last)
+
+
+def run_c1(args, env):
+    import io
+    import contextlib
+    import torch
+    import qsparse_b200 as q
+    world, rank, dev = env["world"], env["rank"], env["dev"]
+    peak, peak_src = env["peak"]
+    q.set_qsparse_options(log_on_created=False)
+    torch.backends.cudnn.benchmark = False
+    kind = "DecimalQuantizer" if getattr(args, "c1_decimal", False) else "ScalerQuantizer"
+    steps = max(50, min(args.steps, 300))
+    warm = 70
+    sampler = env["sampler_cls"](dev.index)
+    if rank == 0:
+        sampler.start()
+    res = {}
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        res["plain_net_no_qsparse"] = _c1_time(torch, _c1_net(torch).to(dev), dev, steps, warm)
+        fused = _c1_convert(torch, q, _c1_net(torch), kind, True).to(dev)
+        res["fused"] = _c1_time(torch, fused, dev, steps, warm)
+        res["unfused"] = _c1_time(torch, _c1_convert(torch, q, _c1_net(torch), kind, False).to(dev), dev, steps, warm)
+        hb = [(torch.randn(C1_BATCH, 1, 28, 28).pin_memory(), torch.randint(0, 10, (C1_BATCH,)).pin_memory())
+              for _ in range(8)]
+        e2e_model = _c1_convert(torch, q, _c1_net(torch), kind, True).to(dev)
+        res["e2e"] = _c1_time(torch, e2e_model, dev, steps, warm, host_batches=hb)
+    clocks = sampler.stop() if rank == 0 else None
+    from qsparse_b200.fused import FusedPruneQuantSequential
+    fused_steps = [m.fused_steps for m in fused.modules() if isinstance(m, FusedPruneQuantSequential)]
+    gpu_eager = cpu = None
+    if world == 1 and not args.no_gpu_eager:
+        from oracle.torch_eager import build_mnist_eager
+        eg = build_mnist_eager("decimal" if kind == "DecimalQuantizer" else "scaler").to(dev)
+        w_e, ev_e, _ = _c1_time(torch, eg, dev, steps, warm)
+        gpu_eager = {"what": "the same converted net with the reference's layers restated as eager torch modules "
+                             "(oracle/torch_eager.py::build_mnist_eager, equal to the reference step for step on CPU)",
+                     "ms_per_step": round(w_e, 4), "cuda_event_ms_per_step": round(ev_e, 4),
+                     "value": round(1e3 / w_e, 2), "unit": "steps/s",
+                     "speedup_of_this_repo": round(w_e / res["fused"][0], 2)}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.torch_eager import build_mnist_eager
+        cpu_dev = torch.device("cpu")
+        torch.set_num_threads(env["host_threads"])
+        egc = build_mnist_eager("decimal" if kind == "DecimalQuantizer" else "scaler")
+        F = torch.nn.functional
+        opt = torch.optim.Adadelta([p for p in egc.parameters() if p.requires_grad], lr=1.0)
+        xc, yc = torch.randn(C1_BATCH, 1, 28, 28), torch.randint(0, 10, (C1_BATCH,))
+        egc.train()
+
+        def cstep():
+            opt.zero_grad()
+            F.nll_loss(egc(xc), yc).backward()
+            opt.step()
+        for _ in range(62):
+            cstep()
+        t0 = time.perf_counter()
+        for _ in range(40):
+            cstep()
+        dt = (time.perf_counter() - t0) / 40
+        cpu = {"value": round(1 / dt, 2), "unit": "steps/s", "cores": env["host_threads"], "kind": "port",
+               "sample": f"40 steady-state training steps of the eager restatement on CPU tensors, {dt*1e3:.1f} ms/step",
+               "ms_per_step": round(dt * 1e3, 3)}
+    wall, evms, loss = res["fused"]
+    hot_elems = C1_BATCH * (28 * 28 + 32 * 26 * 26 + 64 * 24 * 24 + 128) + 32 * 9 + 64 * 32 * 9 + 128 * 9216 + 1280
+    hot_bytes = 20 * hot_elems
+    line = _base(C1_METRIC, world * 1e3 / wall, world, args, wall, c1_config(kind), world * C1_BATCH, clocks)
+    line["unit"] = "steps/s"
+    line["steps"] = steps
+    line.update({
+        "loss_after_timed_steps": loss, "fused_steps_per_site": fused_steps,
+        "variants_ms_per_step": {k: {"wall": round(v[0], 4), "cuda_events": round(v[1], 4)} for k, v in res.items()},
+        "qsparse_overhead_ms_per_step": {"fused": round(res["fused"][0] - res["plain_net_no_qsparse"][0], 4),
+                                         "unfused": round(res["unfused"][0] - res["plain_net_no_qsparse"][0], 4)},
+        "launch_mode": "eager module API (10 prune / quantize layers per step; fusion pass applied to the two "
+                       "prune->quantize activation sites)",
+        "gpu_launches": None,
+        "e2e": {"value": round(world * 1e3 / res["e2e"][0], 2), "unit": "steps/s", "h2d_bytes_per_step": C1_BATCH * (784 * 4 + 8),
+                "d2h_bytes_per_step": 4, "ms_per_step": round(res["e2e"][0], 4), "steps": steps,
+                "api": "pinned host batch -> device -> converted model forward / backward / optimizer step -> loss.item()"},
+        "roofline": {"bound": "hbm", "kernel": "(launch-bound configuration) all prune / quantize tensors of one step",
+                     "achieved": round(hot_bytes / (wall * 1e-3) / 1e9, 2), "peak": peak, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(hot_bytes / (wall * 1e-3) / 1e9 / peak, 5), "traffic": None,
+                     "algorithmic_bytes_per_launch": hot_bytes,
+                     "note": "20 B/elem over the 1.5 M activation + 1.2 M weight elements the operators touch per step, "
+                             "divided by the WHOLE training step's wall time: this configuration is bound by kernel-launch "
+                             "and Python overhead, the roofline fraction is reported for completeness"},
+        "gpu_eager_baseline": gpu_eager, "cpu_baseline": cpu,
+    })
+    return line
+
+
 # ============================================================================= dispatch
 def run_ours(args, env):
-    return {3: run_c3, 4: run_c4, 5: run_c5}[args.config](args, env)
+    return {1: run_c1, 3: run_c3, 4: run_c4, 5: run_c5}[args.config](args, env)
 
 
 def run_reference(args):
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    if args.config == 3:
+    if args.config == 1:
+        import torch
+        from oracle.torch_eager import build_mnist_eager
+        F = torch.nn.functional
+        torch.set_num_threads(threads)
+        net = build_mnist_eager("scaler").train()
+        opt = torch.optim.Adadelta([p for p in net.parameters() if p.requires_grad], lr=1.0)
+        xc, yc = torch.randn(C1_BATCH, 1, 28, 28), torch.randint(0, 10, (C1_BATCH,))
+
+        def cstep():
+            opt.zero_grad()
+            F.nll_loss(net(xc), yc).backward()
+            opt.step()
+        for _ in range(62):
+            cstep()
+        n = max(5, min(args.steps, 40))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            cstep()
+        dt = (time.perf_counter() - t0) / n
+        cpu = {"value": round(1 / dt, 2), "unit": "steps/s", "cores": threads, "kind": "port", "ms_per_step": round(dt * 1e3, 3),
+               "sample": f"{n} steady-state training steps of the eager restatement of the reference's layers on CPU tensors"}
+        metric, cfg = C1_METRIC, c1_config("ScalerQuantizer")
+    elif args.config == 3:
         cpu = cpu_c3(threads, max(1, min(args.steps, 10)))
         metric, cfg = C3_METRIC, c3_config()
     elif args.config == 4:
@@ -665,9 +864,9 @@ def run_reference(args):
         cpu = cpu_c5(threads)
         metric, cfg = C5_METRIC, c5_config(args.strong, [20, 22, 24, 26, 28, 30, 32])
     v = cpu["value"]
-    return {"impl": "reference", "metric": metric, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+    return {"impl": "reference", "metric": metric, "value": v, "unit": cpu["unit"], "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cpu.get("ms_per_step"), "higher_is_better": True,
             "scaling": "strong" if (args.config == 5 and args.strong) else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg, "cpu_baseline": cpu,
-            "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": v, "unit": cpu["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "oracle/ (plain-C restatement of the reference, pinned to its golden vectors) on the host cores"}

@@ -33,7 +33,7 @@ for stage in "$@"; do
     ref)
       timeout 600 python bench.py --impl reference --steps 10 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err ;;
     configs)
-      for c in 3 4 5; do
+      for c in ${CONFIGS:-1 3 4 5}; do
         timeout 900 python bench.py --config $c --steps 200 > $out/${tag}_bench_c${c}.json 2> $out/${tag}_bench_c${c}.err
       done ;;
     launches)

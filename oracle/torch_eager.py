@@ -153,3 +153,179 @@ def masked_pow2_fwd_bwd(x, g, mask, decimal, bits=8):
     v = g.clamp_((-limit) * tof, (limit - 1) * tof)
     v[v != g] = 0
     return y, v * mask
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 1: the reference's LAYERS as eager nn.Modules (control flow of qsparse/quantize.py:473-518 and
+# qsparse/sparse.py:99-122,215-273 incl. their `.item()` host syncs), so that the converted MNIST net of
+# examples/mnist.py can be timed on the GPU box without the reference tree.  Checked step for step against the
+# imported reference in tests/test_torch_eager_vs_reference.py.
+# ---------------------------------------------------------------------------------------------------------
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class _DecimalFn(torch.autograd.Function):
+    """ref qsparse/quantize.py:30-77"""
+
+    @staticmethod
+    def forward(ctx, input, bits, decimal):
+        limit = 2.0 ** (bits - 1)
+        tof = 2.0 ** -decimal
+        toi = 2.0 ** decimal
+        ctx.save_for_backward(torch.tensor(limit), tof)
+        q = (input * toi).int()
+        q.float().clamp_(-limit, limit - 1)
+        return q.float() * tof
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        limit, tof = ctx.saved_tensors
+        v = grad_output.clamp_((-limit) * tof, (limit - 1) * tof)
+        v[v != grad_output] = 0
+        return v, None, None
+
+
+class _ScalerFn(torch.autograd.Function):
+    """ref qsparse/quantize.py:86-131"""
+
+    @staticmethod
+    def forward(ctx, input, bits, scaler):
+        limit = 2.0 ** (bits - 1)
+        ctx.save_for_backward(torch.tensor(limit), scaler)
+        q = (input / scaler).round().int()
+        q.float().clamp_(-limit, limit - 1)
+        return q.float() * scaler
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        limit, scaler = ctx.saved_tensors
+        v = grad_output.clamp_((-limit) * scaler, (limit - 1) * scaler)
+        v[v != grad_output] = 0
+        return v, None, None
+
+
+class EagerQuantizeLayer(nn.Module):
+    """per-tensor (channelwise = -1) QuantizeLayer with a Decimal / Scaler quantizer"""
+
+    def __init__(self, bits=8, timeout=10, kind="scaler"):
+        super().__init__()
+        self.bits, self.timeout, self.kind = bits, timeout, kind
+        self.cb_t = 0
+        self._quantized = False
+
+    def forward(self, x):
+        if not hasattr(self, "_n_updates"):
+            self.weight = nn.Parameter(torch.zeros(1, 1).to(x.device), requires_grad=False)
+            self._n_updates = nn.Parameter(torch.zeros(1, dtype=torch.int).to(x.device), requires_grad=False)
+        t = self._n_updates.item()
+        out = x
+        if self.timeout > 0:
+            if t >= self.timeout:
+                if self.training:
+                    with torch.no_grad():
+                        a = x.abs().view(1, -1)
+                        new_weight = (a.max(dim=1).values / (2 ** (self.bits - 1))).view(1, 1)
+                    if self.cb_t == 0:
+                        self.weight.data[:] = new_weight
+                    else:
+                        self.weight.data[:] = (self.cb_t * self.weight + new_weight) / (self.cb_t + 1)
+                    self.cb_t += 1
+                    self._quantized = True
+                if self._quantized:
+                    if self.kind == "decimal":
+                        d = (1 / self.weight).nan_to_num(posinf=1, neginf=1).log2().round()
+                        out = _DecimalFn.apply(x, self.bits, d)
+                    else:
+                        out = _ScalerFn.apply(x, self.bits, self.weight)
+            if self.training:
+                self._n_updates += 1
+        return out
+
+
+class EagerPruneLayer(nn.Module):
+    """structured channel prune (dimensions = {1}), MagnitudePruningCallback(running_average=True)"""
+
+    def __init__(self, sparsity=0.5, start=20, interval=10, repetition=4):
+        super().__init__()
+        self.sparsity, self.start, self.interval, self.repetition = sparsity, start, interval, repetition
+        self.schedules = [start + interval * i for i in range(repetition)]
+        self.rampup_interval = interval
+        self._n = nn.Parameter(torch.tensor(-1, dtype=torch.int), requires_grad=False)
+        self.t = nn.Parameter(torch.full((1,), -1), requires_grad=False)
+
+    def forward(self, x):
+        if self._n.dim() == 0:
+            shape = [1 if i != 1 else s for i, s in enumerate(x.shape)]
+            self.mask = nn.Parameter(torch.ones(*shape, dtype=torch.bool).to(x.device), requires_grad=False)
+            self._n = nn.Parameter(torch.zeros(1, dtype=torch.int).to(x.device), requires_grad=False)
+            self._cur = nn.Parameter(torch.zeros(1).to(x.device), requires_grad=False)
+            self.t = nn.Parameter(self.t.data.to(x.device), requires_grad=False)
+        if (self._n.item() in self.schedules) and self.training:
+            ratio = (1.0 - (self._n.item() - self.start + self.rampup_interval) / (self.interval * self.repetition)) ** 3
+            self._cur[0] = self.sparsity * (1 - ratio)
+            _ = self._cur.item()                                          # the reference logs it (sparse.py:258)
+        if not self.training:
+            return x * self.mask
+        n_updates = self._n.item()
+        if n_updates >= self.start:
+            sparsity = self._cur.item()
+            if self.t.item() == -1:                                        # callback.initted
+                self.magnitude = nn.Parameter(torch.zeros(*self.mask.shape, device=x.device), requires_grad=False)
+                self.t.data[:] = 0
+            t_item = self.t.item()
+            with torch.no_grad():
+                xa = squeeze_tensor_to_shape(x.abs(), self.magnitude.shape)
+                t = self.t.item()
+                self.magnitude.data[:] = (t * self.magnitude + xa) / (t + 1)
+            if sparsity >= 0 and t_item > 0:
+                self.mask.data[:] = calculate_mask_given_importance(self.magnitude, sparsity)
+            out = x * self.mask
+            self.t += 1
+        else:
+            out = x
+        self._n += 1
+        return out
+
+
+class _QuantizedWeightLayer(nn.Module):
+    """`quantize(layer)`: the layer runs with quantize_layer(weight) (ref qsparse/imitation.py)"""
+
+    def __init__(self, layer, kind):
+        super().__init__()
+        self.layer = layer
+        self.q = EagerQuantizeLayer(8, 10, kind)
+
+    def forward(self, x):
+        w = self.q(self.layer.weight)
+        if isinstance(self.layer, nn.Conv2d):
+            return F.conv2d(x, w, self.layer.bias, self.layer.stride, self.layer.padding)
+        return F.linear(x, w, self.layer.bias)
+
+
+def build_mnist_eager(kind="scaler"):
+    """the converted Net of BASELINE config 1 (oracle/gen_golden_config1.py::build) with eager reference layers:
+    input quantize; conv/linear weights quantized; ReLU -> prune -> quantize after the first two ReLUs, ReLU ->
+    quantize after the third."""
+    torch.manual_seed(1)
+    conv1, bn1 = nn.Conv2d(1, 32, 3, 1), nn.BatchNorm2d(32)
+    conv2, bn2 = nn.Conv2d(32, 64, 3, 1), nn.BatchNorm2d(64)
+    fc1, bn3, fc2 = nn.Linear(9216, 128), nn.BatchNorm1d(128), nn.Linear(128, 10)
+
+    def site(prune):
+        mods = [nn.ReLU()] + ([EagerPruneLayer()] if prune else []) + [EagerQuantizeLayer(8, 10, kind)]
+        return nn.Sequential(*mods)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inq = EagerQuantizeLayer(8, 10, kind)
+            self.conv_part = nn.Sequential(_QuantizedWeightLayer(conv1, kind), bn1, site(True),
+                                           _QuantizedWeightLayer(conv2, kind), bn2, site(True), nn.MaxPool2d(2))
+            self.linear_part = nn.Sequential(nn.Flatten(), _QuantizedWeightLayer(fc1, kind), bn3, site(False),
+                                             _QuantizedWeightLayer(fc2, kind))
+
+        def forward(self, x):
+            return F.log_softmax(self.linear_part(self.conv_part(self.inq(x))), dim=1)
+
+    return Net()

@@ -79,3 +79,28 @@ def test_unstructured_prune_matches_reference_callback():
         yr = cb(wt, 0.5, mask)
         ye = eager.forward(wt)
         assert torch.equal(yr, ye) and torch.equal(mask, eager.mask), t
+
+
+def test_mnist_eager_net_matches_reference_converted_net():
+    """build_mnist_eager (the config-1 GPU-eager baseline of bench.py) trains step for step like the
+    reference's convert()'ed net on CPU: identical losses for 35 steps (warm-up, quantization start at 10,
+    pruning start at 20 and two ramp points)."""
+    import torch.nn.functional as F
+    from oracle.gen_golden_config1 import build, data
+    from oracle.torch_eager import build_mnist_eager
+    qsparse, DecimalQuantizer, _, _ = _ref()
+    from qsparse.quantize import ScalerQuantizer
+    for kind, factory in (("scaler", ScalerQuantizer), ("decimal", DecimalQuantizer)):
+        ref = build(qsparse, factory)
+        mine = build_mnist_eager(kind)
+        ref.train(), mine.train()
+        o1 = torch.optim.Adadelta(ref.parameters(), lr=1.0)
+        o2 = torch.optim.Adadelta([p for p in mine.parameters() if p.requires_grad], lr=1.0)
+        for step in range(35):
+            x, y = data(step)
+            o1.zero_grad(), o2.zero_grad()
+            l1 = F.nll_loss(ref(x), y)
+            l2 = F.nll_loss(mine(x), y)
+            l1.backward(), l2.backward()
+            o1.step(), o2.step()
+            assert l1.item() == l2.item(), (kind, step, l1.item(), l2.item())
