@@ -153,12 +153,28 @@ def require_cuda(t: torch.Tensor, name: str = "tensor") -> None:
         )
 
 
-def ptr(t: Optional[torch.Tensor]) -> c_void_p:
-    return c_void_p(0 if t is None else t.data_ptr())
+def ptr(t: Optional[torch.Tensor]):
+    """device address as a plain int (None -> NULL): ctypes converts it through the declared argtypes,
+    without building a c_void_p object per argument"""
+    return None if t is None else t.data_ptr()
 
 
-def stream_ptr(device: torch.device) -> c_void_p:
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def stream_key(device: torch.device) -> Tuple[int, int]:
+    """(device index, raw cudaStream_t of torch's current stream) — one C call, not the
+    ``torch.cuda.current_stream()`` object round trip (8 us each; a small layer makes a dozen)."""
+    idx = device.index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if _raw_stream is not None:
+        return idx, _raw_stream(idx)
+    return idx, torch.cuda.current_stream(device).cuda_stream
+
+
+def stream_ptr(device: torch.device):
+    return stream_key(device)[1] or None
 
 
 _workspaces = {}
@@ -166,7 +182,7 @@ _workspaces = {}
 
 def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     """Per (device, stream) scratch buffer, grown on demand, never shrunk."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = stream_key(device)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

@@ -250,15 +250,15 @@ class FusedPruneQuantSequential(nn.Sequential):
                 ops.prune_quant_step_params(magnitude, p.mask.data.view(-1), q.weight.data.view(-1), decimal, ws,
                                             layout, float(outer * inner), t, mode, refresh, k, q.bits, qcb.t, True)
             # the counters of the two layers and their callbacks, as their own forwards advance them
-            cb.t += 1
+            cb.t.data.add_(1)
             cb._t_mirror.wrote(cb.t, t + 1)
             n = p._n_mirror.get(p._n_updates)
-            p._n_updates += 1
+            p._n_updates.data.add_(1)
             p._n_mirror.wrote(p._n_updates, n + 1)
             qcb.t += 1
             q._quantized = True
             tq = q._t_mirror.get(q._n_updates)
-            q._n_updates += 1
+            q._n_updates.data.add_(1)
             q._t_mirror.wrote(q._n_updates, tq + 1)
         self.fused_steps += 1
         return _FusedLayersFn.apply(x, xs, layout, p.mask.data.view(-1),
@@ -348,13 +348,13 @@ def _fused_weight_step(p, q, raw):
     with torch.no_grad():
         # the counters of the two layers and their callbacks, as their own forwards advance them
         t = cb._t()
-        cb.t += 1
+        cb.t.data.add_(1)
         cb._t_mirror.wrote(cb.t, t + 1)
-        p._n_updates += 1
+        p._n_updates.data.add_(1)
         p._n_mirror.wrote(p._n_updates, n + 1)
         t_line = qcb._next_t() if type(qcb) is AdaptiveQuantizer else 0
         q._quantized = True
-        q._n_updates += 1
+        q._n_updates.data.add_(1)
         q._t_mirror.wrote(q._n_updates, tq + 1)
     return _FusedWeightFn.apply(raw, ws, p.mask.data, q, t_line)
 

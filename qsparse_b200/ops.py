@@ -501,7 +501,7 @@ _arrival_counters = {}
 def arrival_counter(device: torch.device) -> torch.Tensor:
     """the zero-initialised uint32 the fused step's last-arriving CTA is elected with: one per
     (device, stream); the kernel leaves it zero"""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = N.stream_key(device)
     c = _arrival_counters.get(key)
     if c is None:
         c = torch.zeros(64, dtype=torch.int32, device=device)   # a 256-byte line of its own

@@ -223,6 +223,18 @@ class _RowFusedSte(torch.autograd.Function):
         return (_ste_backward(ctx, grad_output),) + (None,) * 4
 
 
+_dummies = {}
+
+
+def _dummy_state(dev):
+    """(magnitude, mask) placeholders of the parameter step for layers that only quantize (never written)"""
+    d = _dummies.get(dev)
+    if d is None:
+        d = (torch.zeros(1, device=dev), torch.ones(1, dtype=torch.bool, device=dev))
+        _dummies[dev] = d
+    return d
+
+
 class _TensorFusedSte(torch.autograd.Function):
     """Per-tensor Decimal / Scaler layer step in two launches instead of five: the abs-max reduction,
     whose last-arriving CTA finalizes it and updates scale EMA (into ``weight``) and decimal ->
@@ -235,10 +247,10 @@ class _TensorFusedSte(torch.autograd.Function):
         n = xs.numel()
         layout = (1, 1, n)
         dev = xs.device
-        decimal = torch.empty(1, dtype=torch.float32, device=dev)
+        decimal = torch.empty(1, dtype=torch.float32, device=dev) if is_decimal else None
         # ONE launch: abs-max reduction whose last-arriving CTA finalizes and updates scale / decimal
-        ops.reduce_prune_quant_step(xs, layout, torch.zeros(1, device=dev),
-                                    torch.ones(1, dtype=torch.bool, device=dev), weight.data.view(-1), decimal,
+        mag0, mask1 = _dummy_state(dev)
+        ops.reduce_prune_quant_step(xs, layout, mag0, mask1, weight.data.view(-1), decimal if is_decimal else None,
                                     float(n), 0, 0, False, 0, bits, quantizer.t, True)
         quantizer.t += 1
         if is_decimal:
@@ -383,7 +395,7 @@ class DecimalQuantizer(BaseQuantizer):
             # per tensor: partials -> one parameter kernel -> quantize
             if type(self) is not exact or self.group_num > 0 or not isinstance(weight, nn.Parameter):
                 return None
-            if not (isinstance(x, torch.Tensor) and x.is_cuda and x.numel() >= 4096 and x.is_contiguous()):
+            if not (isinstance(x, torch.Tensor) and x.is_cuda and x.numel() >= 1 and x.is_contiguous()):
                 return None
             if tuple(weight.shape) != (1, 1):
                 return None
@@ -605,7 +617,7 @@ class QuantizeLayer(nn.Module):
                 out = self.callback(x, self.bits, self.weight, channel_index=self.channelwise,
                                     inplace=self.batch_dimension == 0)
         if self.training:
-            self._n_updates += 1
+            self._n_updates.data.add_(1)      # in place: no Module.__setattr__ round trip
             self._t_mirror.wrote(self._n_updates, t + 1)
         return out
 

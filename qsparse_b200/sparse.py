@@ -239,7 +239,7 @@ class MagnitudePruningCallback(nn.Module):
             if t < self.stop_mask_refresh:
                 self.receive_input(x)
             out = self.prune_and_update_mask(x, sparsity, mask) if refresh else apply_mask(x, mask)
-        self.t += 1
+        self.t.data.add_(1)
         self._t_mirror.wrote(self.t, t + 1)
         if self.forward_hook is not None:
             self.forward_hook(mask, name)
@@ -362,7 +362,7 @@ class PruneLayer(nn.Module):
             out = self.callback(x, self._s_mirror.get(self._cur_sparsity), mask=self.mask, name=self.name)
         else:
             out = x
-        self._n_updates += 1
+        self._n_updates.data.add_(1)
         self._n_mirror.wrote(self._n_updates, n + 1)
         return out
 

@@ -540,7 +540,7 @@ def test_fused_step_kernel_equals_separate_kernels(shape, C):
 
 @pytest.mark.parametrize("shape,C", [((8, 64, 56, 56), 64), ((8, 64, 14, 14), 64), ((4, 200, 9, 9), 200),
                                      ((16, 7, 70), 7), ((32, 48), 48), ((64, 1000), 1000), ((3, 1, 5000), 1),
-                                     ((2, 1024, 300), 1024), ((5, 3, 1031), 3)])
+                                     ((2, 1024, 300), 1024), ((5, 3, 1031), 3), ((2, 1, 9), 1), ((1, 1, 288), 1)])
 def test_one_launch_step_equals_two_launch_step(shape, C):
     """qsb_reduce_prune_quant_step (the reduction's last-arriving CTA runs the parameter step) must be
     bit-identical to qsb_reduce_partials + qsb_prune_quant_step_params in every stage-1 mode (rows, tile,
