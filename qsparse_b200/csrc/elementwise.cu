@@ -204,6 +204,19 @@ struct ExportLineOp : LineOp<QSB_MASK_NONE, true> {
   }
 };
 
+// The same codes packed two per byte on the streaming-map skeleton (window parameter tables, one CTA per
+// tile, 256-bit loads, one 32-bit store per 8 codes): what qsb_quant_export_int4 launches for 32-byte
+// aligned tensors whose size is a multiple of 8.
+struct ExportPow2Op4 : ExportPow2Op {
+  static constexpr bool kPack4 = true;
+};
+struct ExportScalerOp4 : ExportScalerOp {
+  static constexpr bool kPack4 = true;
+};
+struct ExportLineOp4 : ExportLineOp {
+  static constexpr bool kPack4 = true;
+};
+
 // Packed 4-bit export: two codes per byte (even element in the low nibble), 4.5 B/elem.  A
 // thread owns 8 consecutive elements = one 32-bit store; it walks the channel of its elements
 // itself (one 64-bit division per thread), so every [outer, C, inner] layout takes this one
@@ -488,6 +501,30 @@ extern "C" int qsb_quant_export_int4(const float *x, uint8_t *q_out, int kind,
     if (kind == 2 && !aligned_to(param_dev, 8)) return QSB_E_ALIGN;
   }
   const int q_min = -(1 << (bits - 1)), q_max = (1 << (bits - 1)) - 1;
+  if (n % 8 == 0 && aligned_to(x, 32) && aligned_to(q_out, 4)) {
+    // the streaming-map skeleton (0.67 -> see profiles/ of the copy peak with the generic kernel below)
+    const Layout L = effective_layout(outer, channels, inner, stride == 1);
+    MapIO io{x, nullptr, nullptr, nullptr, nullptr, q_out};
+    if (kind == 0) {
+      ExportPow2Op4 op;
+      op.dec = param_dev, op.dec_stride = stride;
+      op.toi_host = (float)pow(2.0, param_host), op.tof_host = (float)pow(2.0, -param_host);
+      op.cmask = nullptr, op.q_min = q_min, op.q_max = q_max;
+      return launch_map<ExportPow2Op4, Hint::STREAM, Hint::KEEP>(op, io, L, stream);
+    }
+    if (kind == 1) {
+      ExportScalerOp4 op;
+      op.scale = param_dev, op.scale_stride = stride, op.scale_host = (float)param_host;
+      op.cmask = nullptr, op.q_min = q_min, op.q_max = q_max;
+      return launch_map<ExportScalerOp4, Hint::STREAM, Hint::KEEP>(op, io, L, stream);
+    }
+    ExportLineOp4 op;
+    op.lines = param_dev, op.lines_stride = stride;
+    op.lo_host = (float)param_host, op.hi_host = (float)param_host2;
+    const double N = ldexp(1.0, bits);
+    op.n_levels = (float)N, op.q_max = (float)(N - 1.0), op.cmask = nullptr;
+    return launch_map<ExportLineOp4, Hint::STREAM, Hint::KEEP>(op, io, L, stream);
+  }
   const int64_t per_cta = (int64_t)QSB_THREADS * 8 * 2;  // two vectors per thread
   const dim3 grid((unsigned)((n + per_cta - 1) / per_cta));
   const int vec_ok = aligned_to(x, 32) ? 1 : 0;

@@ -23,6 +23,8 @@
 //                    when it fits, 32-bit (column, channel) bookkeeping advanced
 //                    by constants — no division in the loop.
 #pragma once
+#include <type_traits>
+
 #include "qsb_common.cuh"
 
 namespace qsb {
@@ -66,6 +68,34 @@ __device__ __forceinline__ void apply_vec(const Op &op, const VecF<V> &a,
   for (int j = 0; j < V; ++j)
     op.apply(skip ? 0.f : a.v[j], Op::kIn1 ? b.v[j] : 0.f,
              Op::kInB ? mb.b[j] : (uint8_t)1, p, o0.v[j], o1.v[j], ob.b[j]);
+}
+
+// Byte outputs are one byte per element (masks, int8 codes) or, for ops that declare
+// `static constexpr bool kPack4 = true`, one NIBBLE per element (packed 4-bit codes, element 2i in the
+// low nibble of byte i): a vector of 8 codes is then ONE 32-bit store.
+template <class Op, class = void>
+struct is_pack4 : std::false_type {};
+template <class Op>
+struct is_pack4<Op, std::void_t<decltype(Op::kPack4)>> : std::bool_constant<Op::kPack4> {};
+
+template <class Op, int V>
+__device__ __forceinline__ void store_outb(uint8_t *outb, int64_t e, const VecB<V> &ob) {
+  if constexpr (is_pack4<Op>::value) {
+    if constexpr (V == 8) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w |= (uint32_t)(ob.b[j] & 0xF) << (4 * j);
+      *reinterpret_cast<uint32_t *>(outb + (e >> 1)) = w;
+    } else if constexpr (V == 4) {
+      uint16_t w = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w |= (uint16_t)((ob.b[j] & 0xF) << (4 * j));
+      *reinterpret_cast<uint16_t *>(outb + (e >> 1)) = w;
+    }
+    // V == 1 would make two threads share a byte: the launcher never picks it for a packed output
+  } else {
+    st_bytes<V>(outb + e, ob);
+  }
 }
 
 struct MapTuning {
@@ -118,7 +148,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
         apply_vec<Op, V>(op, a[u], b[u], mb[u], false, p, o0, o1, ob);
         if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
         if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
-        if constexpr (Op::kOutB) st_bytes<V>(io.outb + e, ob);
+        if constexpr (Op::kOutB) store_outb<Op, V>(io.outb, e, ob);
       }
     }
   }
@@ -213,7 +243,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
       VecB<V> mb, ob;
       apply_vec<Op, V>(op, a[u], b[u], mb, false, p, o0, o1, ob);
       if constexpr (Op::kOut0) st_vec<V, SH>(t.out0 + e, o0);
-      if constexpr (Op::kOutB) st_bytes<V>(t.outb + e, ob);
+      if constexpr (Op::kOutB) store_outb<Op, V>(t.outb, e, ob);
     }
   }
   // the last n % V elements of the tensor, scalar, by the CTA that owns that position
@@ -387,7 +417,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
         }
         if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
         if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
-        if constexpr (Op::kOutB) st_bytes<V>(io.outb + e, ob);
+        if constexpr (Op::kOutB) store_outb<Op, V>(io.outb, e, ob);
       }
     }
     advance32(col0, c0, G.si_cols, G.si_ch, G);
@@ -497,7 +527,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
       }
       if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
       if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
-      if constexpr (Op::kOutB) st_bytes<V>(io.outb + e, ob);
+      if constexpr (Op::kOutB) store_outb<Op, V>(io.outb, e, ob);
     }
   }
   // tail: the last n % V elements, scalar, by the CTA that owns them
@@ -629,7 +659,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
         }
         if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
         if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
-        if constexpr (Op::kOutB) st_bytes<V>(io.outb + e, ob);
+        if constexpr (Op::kOutB) store_outb<Op, V>(io.outb, e, ob);
       }
     }
   }
@@ -676,7 +706,7 @@ int launch_map(const Op &op, const MapIO &io, const Layout &L,
   if (Op::kOut0) acc(io.out0, 1);
   if (Op::kOut1) acc(io.out1, 1);
   if (Op::kInB) acc(io.inb, 4);
-  if (Op::kOutB) acc(io.outb, 4);
+  if (Op::kOutB) acc(io.outb, is_pack4<Op>::value ? 8 : 4);  // packed nibbles: V / 2 bytes per vector
   if (bits & 3) return QSB_E_ALIGN;
   if (L.channels <= 1) {
     if ((bits & 31) == 0) return launch_map_tensor<Op, 8, 2, LH, SH>(op, io, n, stream);

@@ -177,16 +177,22 @@ struct StepTail {
 
 __device__ __forceinline__ void fused_step_tail(const StepTail &t, unsigned char *smem) {
   __shared__ int s_last;
-  __threadfence();  // this thread's partials are visible device-wide before the CTA checks in
+  // The CTA barrier orders every thread's partial stores before thread 0's fence + atomic (the grid-sync
+  // pattern of cooperative groups): ONE device-scope fence per CTA instead of one per thread — each is a
+  // MEMBAR.SC.GPU + CCTL.IVALL on the last CTA's critical path.
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned total = gridDim.x * gridDim.y;
-    s_last = atomicAdd(t.arrival, 1u) == total - 1;
+    __threadfence();
+    const int last = atomicAdd(t.arrival, 1u) == total - 1;
+    if (last) {
+      __threadfence();   // the other CTAs' partials are visible to the loads below (they go to L2: __ldcg)
+      *t.arrival = 0;    // ready for the next launch
+    }
+    s_last = last;
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x == 0) *t.arrival = 0;  // ready for the next launch
   step_epilogue(t.a, carve_step_smem(smem, t.a.channels));
 }
 
