@@ -420,6 +420,37 @@ def run_ours(args):
         p2p.stamp = state["t"]      # graph mode derived the stamps from the device-side step counter (stamp = t + 1)
     barrier()
 
+    # ---- phases INSIDE the statistics + parameter kernel, from %globaltimer stamps the kernel writes itself:
+    # how long the streaming part takes and how long the serial tail of the last-arriving CTA is ----
+    phases = None
+    if ex is None:
+        stamps = torch.empty(8, dtype=torch.int64, device=dev)
+        acc = []
+        for i in range(40):
+            t = state["t"]
+            stamps.fill_(torch.iinfo(torch.int64).max)
+            bwd()                                   # the usual predecessor of the kernel in the step
+            if graph is not None:
+                params_fused(st, 0, 0, counter_=counter, timing=stamps)
+            else:
+                params_fused(st, t, p2p.next_stamp() if p2p else 1, timing=stamps)
+            ops.fq_pow2_fwd(x, st["dec"], LAYOUT, mask=st["mask"], out=y)
+            state["t"] += 1
+            acc.append(stamps.clone())
+        torch.cuda.synchronize()
+        tt = torch.stack(acc[5:]).double().cpu()
+        d = lambda a, b: float((tt[:, b] - tt[:, a]).mean()) / 1e3
+        phases = {"source": "%globaltimer stamps written by the kernel (mean of 35 launches, us)",
+                  "streaming_reduction_first_cta_start_to_last_arrival": round(d(0, 1), 2),
+                  "serial_tail_last_arrival_to_parameters_written": round(d(1, 6), 2),
+                  "tail_finalize": round(d(1, 2), 2), "tail_peer_exchange": round(d(2, 3), 2),
+                  "tail_magnitude_ema": round(d(3, 4), 2), "tail_rank_count": round(d(4, 5), 2),
+                  "tail_mask_scale_decimal": round(d(5, 6), 2),
+                  "streaming_part_gbs": round(n * 4 / d(0, 1) / 1e3, 1)}
+        if p2p:
+            p2p.stamp = state["t"]
+    barrier()
+
     # ---- module API: the same step through fused.PruneQuantize (autograd forward + backward) ----
     module_api = None
     if world == 1:
@@ -617,7 +648,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": n * 8, "avg_launch_us": round(bwd_ms * 1e3, 2),
                      "how": "CUDA events around every launch of the step, live in this run, over "
                             f"{max(60, min(args.steps, 400)) - 10} steps right after the timed region (same state, same buffers)",
-                     "kernels": kernels,
+                     "kernels": kernels, "statistics_kernel_phases": phases,
                      "step": {"algorithmic_bytes": n * BYTES_PER_ELEM, "actual_bytes": int(n * actual_bytes_per_elem),
                               "us": round(ms_per_step * 1e3, 2), "frac": round(value / world / peak, 4),
                               "frac_actual": round(value_actual / world / peak, 4)}},

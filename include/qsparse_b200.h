@@ -482,7 +482,11 @@ int qsb_prune_quant_rows_step_params(float *magnitude, uint8_t *mask, float *sca
  * the kernel leaves it zero (one counter per stream that may run this concurrently).
  * stats_local != 0: abssum_out / absmax_out receive THIS rank's statistics row (before
  * the exchange) instead of the combined one.  Other arguments as in
- * qsb_prune_quant_step_params.  Requires channels <= 1024. */
+ * qsb_prune_quant_step_params.  Requires channels <= 1024.
+ * timing_out_dev (optional, 8 x uint64): %globaltimer stamps in ns — [0] earliest CTA start
+ * (atomicMin: set it to UINT64_MAX before the launch), [1] the last-arriving CTA enters the
+ * parameter step, [2] statistics finalized, [3] peer exchange done, [4] magnitude EMA done,
+ * [5] threshold found, [6] scale / decimal written.  bench.py reports the phases from it. */
 int qsb_reduce_prune_quant_step(const float *x, int64_t outer, int64_t channels,
                                 int64_t inner, void *workspace,
                                 int64_t workspace_bytes,
@@ -494,7 +498,7 @@ int qsb_reduce_prune_quant_step(const float *x, int64_t outer, int64_t channels,
                                 int bits, int64_t t_quant, int update_scale,
                                 double *abssum_out, float *absmax_out,
                                 int stats_local, int64_t *step_counter_dev,
-                                void *stream);
+                                uint64_t *timing_out_dev, void *stream);
 
 /* ------------------------------------------------------------------------
  * Host-buffer entry points (what a host-side caller that keeps its tensors in

@@ -86,7 +86,7 @@ _SIGNATURES = {
                                                  _P]),
     "qsb_reduce_prune_quant_step": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P,
                                             c_int64, c_double, c_int64, c_int, c_int, c_int64, c_int, c_int64,
-                                            c_int, _P, _P, c_int, _P, _P]),
+                                            c_int, _P, _P, c_int, _P, _P, _P]),
     "qsb_prune_quant_step_params": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64,
                                             c_double, c_int64, c_int, c_int, c_int64, c_int, c_int64, c_int, _P, _P,
                                             _P, _P]),

@@ -175,7 +175,7 @@ struct StepTail {
   const uint8_t *keep_hint;  // optional channel mask of the previous step (L2 residency hint)
 };
 
-__device__ __forceinline__ void fused_step_tail(const StepTail &t, unsigned char *smem) {
+__device__ __forceinline__ void fused_step_tail(const StepTail &t, unsigned char *smem, const StepPrefetch &pre) {
   __shared__ int s_last;
   // The CTA barrier orders every thread's partial stores before thread 0's fence + atomic (the grid-sync
   // pattern of cooperative groups): ONE device-scope fence per CTA instead of one per thread — each is a
@@ -193,7 +193,19 @@ __device__ __forceinline__ void fused_step_tail(const StepTail &t, unsigned char
   }
   __syncthreads();
   if (!s_last) return;
-  step_epilogue(t.a, carve_step_smem(smem, t.a.channels));
+  step_epilogue(t.a, carve_step_smem(smem, t.a.channels), pre);
+}
+
+// kernel start: the old state into registers (StepPrefetch) and, for the bench's evidence, the earliest
+// start time of any CTA
+template <class Tail>
+__device__ __forceinline__ StepPrefetch fused_step_begin(const Tail &tail) {
+  if constexpr (Tail::kFused) {
+    if (tail.a.timing && threadIdx.x == 0) atomicMin(tail.a.timing, global_ns());
+    return step_prefetch(tail.a);
+  } else {
+    return StepPrefetch{false, 0.f, 0.f, 0};
+  }
 }
 
 // 256-bit load with a run-time L2 eviction policy (createpolicy): kept channels of the previous
@@ -227,6 +239,7 @@ __global__ void __launch_bounds__(QSB_THREADS, MINB)
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(16) unsigned char qsb_dyn_smem[];
+  const StepPrefetch pre = fused_step_begin(tail);
   const int lane = threadIdx.x & 31;
   const int64_t warps_phys = (int64_t)gridDim.x * (QSB_THREADS / 32);
   const int64_t items = rows * segs_per_row;
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(QSB_THREADS, MINB)
       warp_store<WHAT>(acc, lane, P, vw);
     }
   }
-  if constexpr (Tail::kFused) fused_step_tail(tail, qsb_dyn_smem);
+  if constexpr (Tail::kFused) fused_step_tail(tail, qsb_dyn_smem, pre);
 }
 
 // ---------------------------------------------------------------------------
@@ -348,6 +361,7 @@ __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
                        int span_stride, int64_t vwarps, Partials P, const __grid_constant__ Tail tail) {
   pdl_wait();
   pdl_trigger();
+  const StepPrefetch pre = fused_step_begin(tail);
   __shared__ __align__(32) float tile[kTileFloats];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t slot0 = (int64_t)blockIdx.x * tile_rows;
@@ -456,7 +470,7 @@ __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
     group_store<WHAT, LPR>(acc[q], lane, P, slot0 + rr, rr < nslots);
   }
   // the tile buffer (32 KB) is free now: the parameter step's shared memory (<= 20.5 KB) lives there
-  if constexpr (Tail::kFused) fused_step_tail(tail, reinterpret_cast<unsigned char *>(tile));
+  if constexpr (Tail::kFused) fused_step_tail(tail, reinterpret_cast<unsigned char *>(tile), pre);
 }
 
 // ---------------------------------------------------------------------------
@@ -562,8 +576,10 @@ __global__ void __launch_bounds__(QSB_THREADS)
     reduce_cols_kernel(const float *__restrict__ x, int64_t nrows, int64_t ncols,
                        int64_t rows_per_chunk, int tpr, Partials P, const __grid_constant__ Tail tail) {
   extern __shared__ __align__(16) unsigned char qsb_dyn_smem[];
+  if constexpr (Tail::kFused) pdl_wait();  // the old state may have been written by the kernel just before
+  const StepPrefetch pre = fused_step_begin(tail);
   reduce_cols_body<WHAT, V>(x, nrows, ncols, rows_per_chunk, tpr, P);
-  if constexpr (Tail::kFused) fused_step_tail(tail, qsb_dyn_smem);
+  if constexpr (Tail::kFused) fused_step_tail(tail, qsb_dyn_smem, pre);
 }
 
 // ---------------------------------------------------------------------------
@@ -1116,7 +1132,7 @@ extern "C" int qsb_reduce_prune_quant_step(
     float *scale, float *decimal_out, qsb_p2p_group *group, int64_t step_stamp, double count,
     int64_t t_prune, int update_magnitude, int refresh_mask, int64_t k, int bits, int64_t t_quant,
     int update_scale, double *abssum_out, float *absmax_out, int stats_local,
-    int64_t *step_counter_dev, void *stream_) {
+    int64_t *step_counter_dev, uint64_t *timing_out_dev, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (outer <= 0 || channels <= 0 || inner <= 0) return QSB_E_BADARG;
   if (channels > kStepFusedMaxChannels) return QSB_E_UNSUPPORTED;
@@ -1135,6 +1151,7 @@ extern "C" int qsb_reduce_prune_quant_step(
   tail.a.fin_count = (int)pl.fin_count;
   tail.a.fin_q = (int)pl.fin_q;
   tail.arrival = arrival_counter_dev;
+  tail.a.timing = reinterpret_cast<unsigned long long *>(timing_out_dev);
   // the previous step's mask as an L2 residency hint: channels it keeps are about to be re-read by
   // the forward pass (only meaningful for a per-channel mask in row mode)
   tail.keep_hint = (g_keep_hint && pl.row_mode && pl.tile_rows == 0 && channels > 1) ? mask : nullptr;

@@ -64,6 +64,7 @@ struct StepArgs {
   float *absmax_out;   // row when stats_local != 0)
   int stats_local;
   long long *step_counter;  // optional device step index (CUDA graphs)
+  unsigned long long *timing;  // optional: %globaltimer stamps of the phases (development / bench evidence)
 };
 
 struct StepSmem {
@@ -110,15 +111,45 @@ __device__ __forceinline__ uint2 ld_packet(const void *p) {
 }
 __device__ __forceinline__ float nan_poison() { return __uint_as_float(0x7fc00000u); }
 
+// What a CTA may already hold when it enters the parameter step: the fused kernels load the layer's
+// old state at KERNEL START (a few hundred bytes that the streaming traffic of the previous step has
+// long evicted from L2, i.e. DRAM-latency loads), so that the tail does not wait for them.
+struct StepPrefetch {
+  bool valid;
+  float mag_old;        // magnitude[tid / group] for the threads with tid % group == 0
+  float scale_old;      // scale[0] (thread 0)
+  long long t;          // *step_counter (every thread)
+};
+
+__device__ __forceinline__ StepPrefetch step_prefetch(const StepArgs &a) {
+  StepPrefetch p;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  p.valid = a.channels * a.group <= nthr;   // one finalize pass: thread (c * group) owns channel c
+  p.mag_old = 0.0f;
+  p.scale_old = 0.0f;
+  p.t = 0;
+  if (!p.valid) return p;
+  const int c = tid / a.group;
+  if (tid % a.group == 0 && c < a.channels && a.update_magnitude != 2) p.mag_old = a.magnitude[c];
+  if (tid == 0) p.scale_old = a.scale[0];
+  if (a.step_counter) p.t = *a.step_counter;
+  return p;
+}
+
+__device__ __forceinline__ void step_stamp_time(const StepArgs &a, int slot) {
+  if (a.timing && threadIdx.x == 0) a.timing[slot] = global_ns();
+}
+
 // Runs on every thread of ONE CTA (blockDim.x a multiple of 32).  sm: shared memory of that CTA.
-__device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem &sm) {
+__device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem &sm,
+                                              const StepPrefetch pre = StepPrefetch{false, 0.f, 0.f, 0}) {
   int64_t t_prune = a.t_prune, t_quant = a.t_quant;
   unsigned long long stamp = a.stamp;
   int refresh_mask = a.refresh_mask;
   if (a.step_counter) {
     // graph mode: the step index lives on the device (the launch arguments of a captured
     // CUDA graph are frozen); `refresh_mask` then carries the refresh interval.
-    const long long t = *a.step_counter;
+    const long long t = pre.valid ? pre.t : *a.step_counter;
     t_prune = t;
     t_quant = t;
     stamp = (unsigned long long)(t + 1);
@@ -128,8 +159,9 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
   const int channels = a.channels, group = a.group;
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int gl = tid % group, gc = tid / group, cpp = nthr / group;
-  const float scale_old = (tid == 0) ? a.scale[0] : 0.0f;  // prefetch
+  const float scale_old = pre.valid ? pre.scale_old : ((tid == 0) ? a.scale[0] : 0.0f);  // prefetch
   if (tid == 0) *sm.flag = 0;
+  step_stamp_time(a, 1);
 
   // ---- 1. this GPU's statistics, fixed order ------------------------------------------
   if (a.row_sum) {
@@ -155,8 +187,8 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
     for (int base = 0; base < channels; base += cpp) {
       const int c = base + gc;
       const bool act = c < channels;
-      float mag_old = 0.0f;
-      if (act && gl == 0 && a.update_magnitude != 2) mag_old = a.magnitude[c];  // prefetch
+      float mag_old = pre.mag_old;
+      if (!pre.valid && act && gl == 0 && a.update_magnitude != 2) mag_old = a.magnitude[c];  // prefetch
       double sum = 0.0;
       uint32_t mx = 0;
       if (act) {
@@ -211,6 +243,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
     }
   }
   __syncthreads();
+  step_stamp_time(a, 2);
   if (a.abssum_out && a.stats_local) {
     for (int c = tid; c < channels; c += nthr) {
       a.abssum_out[c] = sm.sum[c];
@@ -296,6 +329,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
   }
 
   // ---- 3. importance (magnitude EMA) -----------------------------------------------------
+  step_stamp_time(a, 3);
   for (int c = tid; c < channels; c += nthr) {
     if (a.abssum_out && !a.stats_local) {
       a.abssum_out[c] = sm.sum[c];
@@ -318,6 +352,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
   __syncthreads();
 
   // ---- 4. threshold = sorted(importance)[k] by rank counting, `group` threads per channel ----
+  step_stamp_time(a, 4);
   if (refresh_mask) {
     for (int base = 0; base < channels; base += cpp) {
       const int c = base + gc;
@@ -339,6 +374,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
   }
 
   // ---- 5. mask, abs-max of the kept channels, scale EMA, decimal ---------------------------
+  step_stamp_time(a, 5);
   const float thr = refresh_mask ? *sm.thr : 0.0f;
   uint32_t am = 0;
   for (int c = tid; c < channels; c += nthr) {
@@ -363,6 +399,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
     }
     if (a.decimal_out) a.decimal_out[0] = scale_to_decimal(s);
     if (a.step_counter) *a.step_counter = t_prune + 1;
+    if (a.timing) a.timing[6] = global_ns();
   }
 }
 

@@ -512,7 +512,7 @@ def arrival_counter(device: torch.device) -> torch.Tensor:
 def reduce_prune_quant_step(x, layout: Layout, magnitude, mask, scale, decimal_out, count: float, t_prune: int,
                             update_magnitude: int, refresh_mask, k: int, bits: int, t_quant: int,
                             update_scale: bool, group=None, step_stamp: int = 1, abssum_out=None, absmax_out=None,
-                            stats_local: bool = False, step_counter=None, arrival=None):
+                            stats_local: bool = False, step_counter=None, arrival=None, timing=None):
     """ONE launch: sum|x| / max|x| reduction of x whose last-arriving CTA finalizes, exchanges with the
     peer GPUs (``group`` = parallel.P2PExchange handle) and updates magnitude / mask / scale / decimal.
     ``arrival``: a caller-owned zeroed int32 tensor (default: one per device and stream, created on first
@@ -527,8 +527,8 @@ def reduce_prune_quant_step(x, layout: Layout, magnitude, mask, scale, decimal_o
         N.ptr(arrival if arrival is not None else arrival_counter(x.device)), N.ptr(magnitude), N.ptr(mask), N.ptr(scale), N.ptr(decimal_out), group,
         c_int64(step_stamp), c_double(count), c_int64(t_prune), c_int(update_magnitude), c_int(int(refresh_mask)),
         c_int64(k), c_int(bits), c_int64(t_quant), c_int(1 if update_scale else 0), N.ptr(abssum_out),
-        N.ptr(absmax_out), c_int(1 if stats_local else 0), N.ptr(step_counter), N.stream_ptr(x.device)),
-        "qsb_reduce_prune_quant_step")
+        N.ptr(absmax_out), c_int(1 if stats_local else 0), N.ptr(step_counter), N.ptr(timing),
+        N.stream_ptr(x.device)), "qsb_reduce_prune_quant_step")
 
 
 def prune_quant_rows_step_params(magnitude, mask, scale, decimal_out, stats: dict, count: float, t_prune: int,
