@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(1024)
 // the caller ran qsb_reduce_partials itself.  The training step proper uses the fused form,
 // qsb_reduce_prune_quant_step (reduce.cu), where the last CTA of the reduction does this.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+constexpr int kStepKernelThreads = 512;  // 128 registers per thread: the batched peer poll keeps 24 packets in flight
+__global__ void __launch_bounds__(kStepKernelThreads)
     prune_quant_step_kernel(const __grid_constant__ StepArgs a) {
   pdl_wait();     // the partials come from the reduction launched just before
   pdl_trigger();  // the forward kernel's CTAs may queue up behind this single CTA
@@ -416,7 +417,7 @@ extern "C" int qsb_prune_quant_step_params(
   a.P = partials_from_workspace(reduce_workspace, pl.n_partials);
   a.fin_count = (int)pl.fin_count;
   a.fin_q = (int)pl.fin_q;
-  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, a));
+  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(kStepKernelThreads), 0, (cudaStream_t)stream, a));
   return 0;
 }
 
@@ -438,6 +439,6 @@ extern "C" int qsb_prune_quant_rows_step_params(
   a.row_max = absmax;
   a.n_rows = (int)n_stat_rows;
   a.row_stride = stat_row_stride_bytes;
-  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, a));
+  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(kStepKernelThreads), 0, (cudaStream_t)stream, a));
   return 0;
 }
