@@ -208,6 +208,9 @@ def main():
     mk = torch.empty(n4, dtype=torch.bool, device=dev)
     report("c4_ema_full", 12 * n4, lambda: ops.magnitude_ema_full_(magf, wt, 3))
     report("c4_kth_value", 4 * n4, lambda: ops.kth_value(magf, n4 // 2), route="sampled pivots, ~1 pass")
+    hint = ops.new_select_hints(1, dev)
+    report("c4_kth_value_hinted", 4 * n4, lambda: ops.kth_value(magf, n4 // 2, hint=hint),
+           route="pivots from the previous answer (warm start), ~1 pass")
     ops.set_tuning(4, 0)
     report("c4_kth_value_3pass", 4 * n4, lambda: ops.kth_value(magf, n4 // 2), route="3-pass radix select")
     ops.set_tuning(4, 1)
@@ -225,6 +228,10 @@ def main():
     report("c4_prune_step_fused", 29 * n4,
            lambda: ops.prune_unstructured_step_batched_([magf], [wt], [mk], [yb], [n4 // 2], state["t"]),
            note="K9: one streaming pass, ~17.5 B/elem of traffic; GB/s on the reference's 29 B/elem")
+    hint9 = ops.new_select_hints(1, dev)
+    report("c4_prune_step_fused_hinted", 29 * n4,
+           lambda: ops.prune_unstructured_step_batched_([magf], [wt], [mk], [yb], [n4 // 2], state["t"], hints=hint9),
+           note="K9 with warm-started pivots")
     del wt, magf, yb, mk, x, g, y
 
     # ---------------- config 5: flat sweep, fused prune(element mask) + pow2 quant fwd, bwd

@@ -350,6 +350,24 @@ int qsb_kth_value_batched(const float *const *v, const int64_t *n,
                           int64_t workspace_bytes, void *stream);
 
 /* ref: calculate_mask_given_importance qsparse/util.py:117  mask = imp >= thr */
+/* Warm-started forms for training loops, which ask for the same order statistic of a slowly drifting
+ * tensor every step.  hints_dev: count x 8 uint32 words owned by the caller, ZERO before the first
+ * call and left alone between calls on the same tensors (reset them when a tensor or its rank k
+ * changes abruptly, e.g. at a sparsity ramp point).  From the third call on the pivots are the previous
+ * answer -/+ an adaptive delta instead of a 32 Ki-element sample: no sampler pass, a few thousand
+ * candidates instead of ~2 % of n.  Results are exact whatever the hints contain (a bracket that misses
+ * rank k takes the generic route on the device and widens). */
+int qsb_kth_value_batched_hinted(const float *const *v, const int64_t *n,
+                                 const int64_t *k, int count, int take_abs,
+                                 float *thr_out_dev, uint32_t *hints_dev,
+                                 void *workspace, int64_t workspace_bytes,
+                                 void *stream);
+int qsb_prune_unstructured_step_batched_hinted(
+    float *const *magnitude, const float *const *x, float *const *y,
+    uint8_t *const *mask_out, const int64_t *n, const int64_t *k, int count,
+    int64_t t, float *thr_out_dev, uint32_t *hints_dev, void *workspace,
+    int64_t workspace_bytes, void *stream);
+
 int qsb_mask_from_threshold(const float *importance, int take_abs,
                             const float *thr_dev, uint8_t *mask_out, int64_t n,
                             void *stream);

@@ -83,6 +83,7 @@ struct SelState {
   uint32_t done_b, done_c;      // fast pass tickets
   float mid;                    // fused prune step: provisional threshold (key midpoint of [lo, hi])
   uint32_t need_full;           // fused prune step: the provisional masks cannot be patched, redo them all
+  uint32_t from_hint;           // the pivots came from the caller's hint, not from a sample
 };
 
 // Fused unstructured prune step (EMA -> threshold -> mask -> apply in ONE streaming pass, see
@@ -91,6 +92,47 @@ struct EmaC {
   float t_f, tp1, rcp;
 };
 static_assert(offsetof(SelState, lo) == 0 && offsetof(SelState, hi) == 4, "the partition kernel loads both pivots at once");
+
+// ---------------------------------------------------------------------------
+// Pivot hints (warm start).  A training loop asks for the SAME order statistic of a slowly drifting
+// tensor every step (the running-average magnitudes of a layer: mag_t = (t mag_{t-1} + |w|) / (t + 1)),
+// so the previous answer brackets the next one far better than 32 Ki fresh samples do.  The caller may
+// keep 8 words of state per tensor ("hint", zero-initialised) across calls:
+//   [0] state: 0 nothing, 1 one answer seen (the next call still samples), 2 pivots available
+//   [1] key of the last answer      [2] delta: half-width of the next pivot bracket, in key steps (ulps)
+// With state 2 the sampler kernel does not sample at all — it only zeroes the header and publishes
+// lo / hi = last answer -/+ delta — and the bracket is so tight (a few thousand candidates instead of
+// 2.5 % of n) that the candidate passes and the fix-up of the fused prune step become trivial.  The
+// answer is exact whatever the hint says: if rank k is not inside [lo, hi] the device takes the generic
+// route exactly as for a missed sample bracket, and the hint widens (delta x 8) or falls back to state 1.
+// After every call: delta = max(8 x |key drift|, delta / 2, 64).
+// ---------------------------------------------------------------------------
+constexpr uint32_t kHintMinDelta = 64, kHintMaxDelta = 1u << 24;
+__device__ __forceinline__ void hint_update(uint32_t *hint, float thr, bool missed) {
+  if (!hint) return;
+  if (thr != thr) {  // a NaN threshold cannot bracket anything
+    hint[0] = 0;
+    return;
+  }
+  const uint32_t key = float_to_key(thr + 0.0f), state = hint[0], old = hint[1], delta = hint[2];
+  if (state == 0) {
+    hint[0] = 1, hint[1] = key, hint[2] = 0;
+    return;
+  }
+  const unsigned long long drift = key > old ? key - old : old - key;
+  unsigned long long nd = 8ull * drift;
+  if (state == 2) {
+    if (missed) nd += 8ull * delta;
+    else if (nd < delta / 2) nd = delta / 2;
+  }
+  if (nd < kHintMinDelta) nd = kHintMinDelta;
+  hint[1] = key;
+  if (nd > kHintMaxDelta) {  // too wide to be worth it: the next call samples again
+    hint[0] = 1, hint[2] = 0;
+    return;
+  }
+  hint[0] = 2, hint[2] = (uint32_t)nd;
+}
 
 #ifdef QSB_SELECT_TIMING
 #define QSB_TICK(st, slot)                                                      \
@@ -113,6 +155,7 @@ struct FastBufs {
   const unsigned long long *segctr;
   uint32_t *fh;                    // [3][kFastBins] histograms of the range-relative digits
   uint32_t seg_cap;                // slots per segment (multiple of 8)
+  uint32_t *hint;                  // caller's pivot hint (may be null)
 };
 
 // Totals of the packed counters -> where is rank k?  Pass 0: every CTA derives the route
@@ -154,7 +197,10 @@ __device__ uint32_t fast_route(const FastBufs &fb, SelState *st_rw, int pass,
         st_rw->route = route;
         // (fused prune step) ties at lo were provisionally pruned and are not in the candidate list
         st_rw->need_full = (route == 2) || (route == 3 && fb.st->width > 0);
-        if (route == 3) *thr_out = fb.st->lo;
+        if (route == 3) {
+          *thr_out = fb.st->lo;
+          hint_update(fb.hint, fb.st->lo, false);
+        }
       }
     }
   }
@@ -316,7 +362,10 @@ __device__ void fast_pass(const FastBufs &fb, unsigned long long kc, SelState *s
   if constexpr (STAGE >= 1) {
     find_bin<kFastBins>(fb.fh, kc, &b0, &k1);
     if (shift_a == 0) {  // the whole range fitted digit A
-      if (STAGE == 1 && blockIdx.x == 0 && tid == 0) *thr_out = key_to_float(lo_key + b0);
+      if (STAGE == 1 && blockIdx.x == 0 && tid == 0) {
+        *thr_out = key_to_float(lo_key + b0);
+        hint_update(fb.hint, *thr_out, false);
+      }
       return;
     }
   }
@@ -374,13 +423,18 @@ __device__ void fast_pass(const FastBufs &fb, unsigned long long kc, SelState *s
   if (!*s_last) return;
   if constexpr (STAGE == 1) {
     find_bin<kFastBins>(fb.fh + kFastBins, k1, &b1, &k2);
-    if (tid == 0) *thr_out = key_to_float(lo_key + (b0 << shift_a) + b1);
+    if (tid == 0) {
+      *thr_out = key_to_float(lo_key + (b0 << shift_a) + b1);
+      hint_update(fb.hint, *thr_out, false);
+    }
   } else if constexpr (STAGE == 2) {
     uint32_t b2;
     unsigned long long k3;
     find_bin<kFastBins>(fb.fh + 2 * kFastBins, k2, &b2, &k3);
-    if (tid == 0)
+    if (tid == 0) {
       *thr_out = key_to_float(lo_key + (b0 << shift_a) + (b1 << shift_b) + b2);
+      hint_update(fb.hint, *thr_out, false);
+    }
   }
 }
 
@@ -390,7 +444,7 @@ __device__ void fast_pass(const FastBufs &fb, unsigned long long kc, SelState *s
 template <int PASS, int V, bool ABS>
 __device__ __forceinline__ void select_pass_body(const float *__restrict__ v, int64_t n, int64_t k,
                                                  SelectWs ws, FastBufs fb, SelState *st_rw,
-                                                 float *thr_out) {
+                                                 float *thr_out, uint32_t *hint) {
   constexpr int kSmemWords = (PASS == 0) ? kBins0 * 32 : kBins1;
   static_assert(kSmemWords >= kFastBins, "the fast passes reuse the histogram");
   __shared__ uint32_t s_hist[kSmemWords];
@@ -479,7 +533,11 @@ __device__ __forceinline__ void select_pass_body(const float *__restrict__ v, in
       find_bin<kBins0>(ws.hist0, kk, &b0, &k1);
       find_bin<kBins1>(ws.hist1, k1, &b1, &k1);
       find_bin<kBins2>(ws.hist2, k1, &b2, &k1);
-      if (tid == 0 && thr_out) *thr_out = key_to_float((b0 << 24) | (b1 << 12) | b2);
+      if (tid == 0 && thr_out) {
+        *thr_out = key_to_float((b0 << 24) | (b1 << 12) | b2);
+        // the generic route after hinted pivots = the bracket missed rank k
+        hint_update(hint, *thr_out, fb.st != nullptr && fb.st->from_hint != 0);
+      }
     }
   }
 }
@@ -567,7 +625,8 @@ template <int PER, bool STEP>
 __device__ __forceinline__ void select_sample_body(const float *__restrict__ v, int64_t n,
                                                    int take_abs, int r_lo, int r_hi, SelState *st,
                                                    uint4 *zero_base, int zero_vecs,
-                                                   const float *__restrict__ w, EmaC ec) {
+                                                   const float *__restrict__ w, EmaC ec,
+                                                   const uint32_t *hint) {
   static_assert(kFastBins == 2 * kSampleThreads, "two bins per thread");
   constexpr int kSampleSize = kSampleThreads * kSampleCtas * PER;
   constexpr int kTieMinCount = kSampleSize / 50;  // >= 2 % of the sample in lo's bucket: ties at lo
@@ -586,6 +645,33 @@ __device__ __forceinline__ void select_sample_body(const float *__restrict__ v, 
 #endif
   pdl_wait();     // v may come from the kernel launched just before (e.g. the magnitude EMA)
   pdl_trigger();  // the partition kernel may start loading v on the other SMs right away
+  if (hint && hint[0] == 2) {
+    // warm start: no sample at all — zero the header, then publish last answer -/+ delta as the pivots
+    const uint32_t thr_key = hint[1], delta = hint[2];
+    for (int j = i; j < zero_vecs; j += kSampleThreads * kSampleCtas) zero_base[j] = make_uint4(0, 0, 0, 0);
+    cluster.sync();  // the header (SelState included) is zero before it is written
+    if (rank == 0 && tid == 0) {
+      uint32_t lo_key = thr_key > kKeyNegInf + delta ? thr_key - delta : kKeyNegInf;
+      uint32_t hi_key = thr_key < kKeyPosInf - delta ? thr_key + delta : kKeyPosInf;
+      if (lo_key < kKeyNegInf) lo_key = kKeyNegInf;
+      if (hi_key > kKeyPosInf) hi_key = kKeyPosInf;
+      if (lo_key == kKeyNegZero) lo_key = kKeyPosZero;  // stored candidates are canonical (+0)
+      if (hi_key == kKeyNegZero) hi_key = kKeyPosZero;
+      if (hi_key < lo_key) hi_key = lo_key;
+      const uint32_t span = hi_key - lo_key;
+      const uint32_t width = span ? 32u - (uint32_t)__clz(span) : 0u;
+      st->lo = key_to_float(lo_key);
+      st->hi = key_to_float(hi_key);
+      st->lo_key = lo_key;
+      st->width = width;
+      st->shift_a = width > (uint32_t)kFastBits ? width - kFastBits : 0u;
+      st->shift_b = width > 2u * kFastBits ? width - 2u * kFastBits : 0u;
+      st->tie_lo = (span == 0u);
+      st->mid = key_to_float(lo_key + (span >> 1) + (span & 1u));
+      st->from_hint = 1;
+    }
+    return;
+  }
   float f[PER];
   if constexpr (PER == 4) {
     // four neighbours per location (one 128-bit load): 32 Ki samples for the lines 8 Ki would touch —
@@ -1012,8 +1098,9 @@ struct SegDesc {
   float *y;
   uint8_t *mask;
   uint32_t *cand_idx;
+  uint32_t *hint;      // caller's pivot hint of this segment (8 words, may be null)
 };
-constexpr int kMaxSegs = 32;  // 32 x 96 B of kernel parameters
+constexpr int kMaxSegs = 32;  // 32 x 104 B of kernel parameters
 struct SegTable {
   SegDesc d[kMaxSegs];
 };
@@ -1051,7 +1138,7 @@ __global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThr
       zb[j] = make_uint4(0, 0, 0, 0);
     return;
   }
-  select_sample_body<PER, STEP>(d.v, d.n, take_abs, d.r_lo, d.r_hi, st_of(d.hdr), zb, zv, d.w, ec);
+  select_sample_body<PER, STEP>(d.v, d.n, take_abs, d.r_lo, d.r_hi, st_of(d.hdr), zb, zv, d.w, ec, d.hint);
 }
 
 template <int U, bool ABS>
@@ -1102,9 +1189,9 @@ template <int PASS, int V, bool ABS>
 __global__ void __launch_bounds__(QSB_THREADS)
     select_pass_kernel(const __grid_constant__ SegTable tab) {
   const SegDesc &d = tab.d[blockIdx.y];
-  FastBufs fb{nullptr, nullptr, nullptr, nullptr, 0};
-  if (d.fast) fb = FastBufs{st_of(d.hdr), d.cand, segctr_of(d.hdr), fh_of(d.hdr), d.seg_cap};
-  select_pass_body<PASS, V, ABS>(d.v, d.n, d.k, ws_of(d.hdr), fb, st_of(d.hdr), d.thr_out);
+  FastBufs fb{nullptr, nullptr, nullptr, nullptr, 0, nullptr};
+  if (d.fast) fb = FastBufs{st_of(d.hdr), d.cand, segctr_of(d.hdr), fh_of(d.hdr), d.seg_cap, d.hint};
+  select_pass_body<PASS, V, ABS>(d.v, d.n, d.k, ws_of(d.hdr), fb, st_of(d.hdr), d.thr_out, d.fast ? d.hint : nullptr);
 }
 
 static int g_select_fast = 1;  // tuning key 4
@@ -1256,6 +1343,7 @@ static int64_t make_desc(SegDesc &d, const float *v, int64_t n, int64_t k, float
   d.y = nullptr;
   d.mask = nullptr;
   d.cand_idx = nullptr;
+  d.hint = nullptr;
   d.fast = g_select_fast && aligned_to(v, 32) && n >= (batched ? kFastMinNBatched : kFastMinN);
   // sample ranks bracketing k: +-4.5 sigma of the binomial rank error, +3
   const double m = (double)(kSampleThreads * kSampleCtas * sample_per(batched, step)), p = (double)k / (double)n;
@@ -1280,9 +1368,9 @@ extern "C" int64_t qsb_kth_batched_workspace_bytes(const int64_t *n, int count) 
   return total;
 }
 
-extern "C" int qsb_kth_value_batched(const float *const *v, const int64_t *n, const int64_t *k,
-                                     int count, int take_abs, float *thr_out_dev, void *workspace,
-                                     int64_t workspace_bytes, void *stream_) {
+static int kth_value_batched_impl(const float *const *v, const int64_t *n, const int64_t *k, int count,
+                                  int take_abs, float *thr_out_dev, uint32_t *hints_dev, void *workspace,
+                                  int64_t workspace_bytes, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (count < 0 || !v || !n || !k || !thr_out_dev || !workspace) return QSB_E_BADARG;
   if (count == 0) return 0;
@@ -1310,6 +1398,7 @@ extern "C" int qsb_kth_value_batched(const float *const *v, const int64_t *n, co
     const int64_t used = make_desc(d, v[i], n[i], k[i], thr_out_dev + i, hdr, batched);
     hdr += used;
     if (!aligned_to(v[i], 32)) continue;
+    d.hint = hints_dev ? hints_dev + 8 * (int64_t)i : nullptr;
     group[L++] = d;
     if (L == kMaxSegs && (rc = flush(true))) return rc;
   }
@@ -1341,11 +1430,10 @@ extern "C" int64_t qsb_prune_step_workspace_bytes(const int64_t *n, int count) {
   return total;
 }
 
-extern "C" int qsb_prune_unstructured_step_batched(float *const *magnitude, const float *const *x,
-                                                   float *const *y, uint8_t *const *mask_out,
-                                                   const int64_t *n, const int64_t *k, int count,
-                                                   int64_t t, float *thr_out_dev, void *workspace,
-                                                   int64_t workspace_bytes, void *stream_) {
+static int prune_step_batched_impl(float *const *magnitude, const float *const *x, float *const *y,
+                                   uint8_t *const *mask_out, const int64_t *n, const int64_t *k, int count,
+                                   int64_t t, float *thr_out_dev, uint32_t *hints_dev, void *workspace,
+                                   int64_t workspace_bytes, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (count < 0 || t < 0 || !magnitude || !x || !y || !mask_out || !n || !k || !thr_out_dev || !workspace)
     return QSB_E_BADARG;
@@ -1374,6 +1462,7 @@ extern "C" int qsb_prune_unstructured_step_batched(float *const *magnitude, cons
     d.w = x[i];
     d.y = y[i];
     d.mask = mask_out[i];
+    d.hint = hints_dev ? hints_dev + 8 * (int64_t)i : nullptr;
     if (n[i] >= (1ll << 32)) d.fast = 0;  // candidate positions are 32-bit
     hdr += step_seg_workspace_bytes(n[i]);
     group[L++] = d;
@@ -1385,12 +1474,50 @@ extern "C" int qsb_prune_unstructured_step_batched(float *const *magnitude, cons
   return 0;
 }
 
+extern "C" int qsb_kth_value_batched(const float *const *v, const int64_t *n, const int64_t *k,
+                                     int count, int take_abs, float *thr_out_dev, void *workspace,
+                                     int64_t workspace_bytes, void *stream) {
+  return kth_value_batched_impl(v, n, k, count, take_abs, thr_out_dev, nullptr, workspace, workspace_bytes,
+                                stream);
+}
+
+// the same with pivot hints: hints_dev = count x 8 uint32 words owned by the caller, zero before the
+// first call and then left alone between calls on the same tensors (see "Pivot hints" at the top)
+extern "C" int qsb_kth_value_batched_hinted(const float *const *v, const int64_t *n, const int64_t *k,
+                                            int count, int take_abs, float *thr_out_dev,
+                                            uint32_t *hints_dev, void *workspace,
+                                            int64_t workspace_bytes, void *stream) {
+  if (hints_dev && !aligned_to(hints_dev, 4)) return QSB_E_ALIGN;
+  return kth_value_batched_impl(v, n, k, count, take_abs, thr_out_dev, hints_dev, workspace, workspace_bytes,
+                                stream);
+}
+
 extern "C" int qsb_kth_value(const float *v, int64_t n, int64_t k, int take_abs,
                              float *thr_out_dev, void *workspace,
                              int64_t workspace_bytes, void *stream) {
   if (n <= 0 || k < 0 || k >= n) return QSB_E_BADARG;
   if (!v || !thr_out_dev || !workspace) return QSB_E_BADARG;
   return qsb_kth_value_batched(&v, &n, &k, 1, take_abs, thr_out_dev, workspace, workspace_bytes, stream);
+}
+
+extern "C" int qsb_prune_unstructured_step_batched(float *const *magnitude, const float *const *x,
+                                                   float *const *y, uint8_t *const *mask_out,
+                                                   const int64_t *n, const int64_t *k, int count,
+                                                   int64_t t, float *thr_out_dev, void *workspace,
+                                                   int64_t workspace_bytes, void *stream) {
+  return prune_step_batched_impl(magnitude, x, y, mask_out, n, k, count, t, thr_out_dev, nullptr, workspace,
+                                 workspace_bytes, stream);
+}
+
+// the same with pivot hints (count x 8 uint32 words, zero before the first step of these layers): from the
+// third step on the sampler is skipped and the candidate set shrinks from ~2 % of a layer to a few thousand
+extern "C" int qsb_prune_unstructured_step_batched_hinted(
+    float *const *magnitude, const float *const *x, float *const *y, uint8_t *const *mask_out,
+    const int64_t *n, const int64_t *k, int count, int64_t t, float *thr_out_dev, uint32_t *hints_dev,
+    void *workspace, int64_t workspace_bytes, void *stream) {
+  if (hints_dev && !aligned_to(hints_dev, 4)) return QSB_E_ALIGN;
+  return prune_step_batched_impl(magnitude, x, y, mask_out, n, k, count, t, thr_out_dev, hints_dev, workspace,
+                                 workspace_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------

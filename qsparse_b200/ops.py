@@ -327,8 +327,19 @@ def magnitude_ema_full_(magnitude, x, t: int, tensor_min=None, use_l0=False):
 
 
 # ----------------------------------------------------------------------------- K5 / K6
-def kth_value(v, k: int, take_abs=False):
-    """device scalar holding sorted(v)[k] (ascending, NaNs last)."""
+def new_select_hints(count: int, device) -> torch.Tensor:
+    """zeroed pivot-hint state for ``count`` tensors (see ``kth_value(hint=...)``)"""
+    return torch.zeros(count, 8, dtype=torch.int32, device=device)
+
+
+def kth_value(v, k: int, take_abs=False, hint=None):
+    """device scalar holding sorted(v)[k] (ascending, NaNs last).
+
+    ``hint``: optional persistent state from ``new_select_hints(1, device)`` for a loop that asks for the same
+    order statistic of a slowly drifting tensor every step: from the third call on the pivots come from the
+    previous answer instead of a fresh sample (exact either way)."""
+    if hint is not None:
+        return kth_value_batched([v], [k], take_abs, hints=hint)
     lib = N.load_library()
     N.require_cuda(v, "importance")
     n = v.numel()
@@ -390,7 +401,7 @@ def prune_step_supported(magnitudes, xs, masks, outs) -> bool:
     return _multi_ok(magnitudes, xs, outs, masks) and all(x.dtype == torch.float32 for x in xs)
 
 
-def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int):
+def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int, hints=None):
     """K9: the whole unstructured running-average prune step of a set of tensors — magnitude EMA (in place),
     exact k-th value threshold, mask, ``out = x * mask`` — in ONE streaming pass plus a few small launches
     (17 B/elem instead of 29).  Returns the thresholds (float32 [L]).  Same results as
@@ -403,6 +414,13 @@ def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int):
     thr = torch.empty(count, dtype=torch.float32, device=dev)
     nbytes = lib.qsb_prune_step_workspace_bytes(ns, c_int(count))
     ws = N.workspace(dev, nbytes)
+    if hints is not None:
+        assert hints.dtype == torch.int32 and hints.numel() >= 8 * count and hints.is_contiguous()
+        N.check(lib.qsb_prune_unstructured_step_batched_hinted(
+            _ptr_array(magnitudes), _ptr_array(xs), _ptr_array(outs), _ptr_array(masks), ns, kk, c_int(count),
+            c_int64(t), N.ptr(thr), N.ptr(hints), N.ptr(ws), c_int64(ws.numel()), N.stream_ptr(dev)),
+            "qsb_prune_unstructured_step_batched_hinted")
+        return thr
     N.check(lib.qsb_prune_unstructured_step_batched(_ptr_array(magnitudes), _ptr_array(xs), _ptr_array(outs),
                                                     _ptr_array(masks), ns, kk, c_int(count), c_int64(t), N.ptr(thr),
                                                     N.ptr(ws), c_int64(ws.numel()), N.stream_ptr(dev)),
@@ -410,7 +428,7 @@ def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int):
     return thr
 
 
-def kth_value_batched(vs, ks, take_abs=False):
+def kth_value_batched(vs, ks, take_abs=False, hints=None):
     """thresholds ``sorted(vs[i])[ks[i]]`` of several tensors (the layers of a weight set) in ONE launch
     sequence: float32 device tensor [len(vs)].  Same kernels as ``kth_value``; blockIdx.y is the tensor."""
     import ctypes
@@ -427,6 +445,12 @@ def kth_value_batched(vs, ks, take_abs=False):
     thr = torch.empty(count, dtype=torch.float32, device=dev)
     nbytes = lib.qsb_kth_batched_workspace_bytes(ns, c_int(count))
     ws = N.workspace(dev, nbytes)
+    if hints is not None:
+        assert hints.dtype == torch.int32 and hints.numel() >= 8 * count and hints.is_contiguous()
+        N.check(lib.qsb_kth_value_batched_hinted(ptrs, ns, kk, c_int(count), c_int(1 if take_abs else 0), N.ptr(thr),
+                                                 N.ptr(hints), N.ptr(ws), c_int64(ws.numel()), N.stream_ptr(dev)),
+                "qsb_kth_value_batched_hinted")
+        return thr
     N.check(lib.qsb_kth_value_batched(ptrs, ns, kk, c_int(count), c_int(1 if take_abs else 0), N.ptr(thr), N.ptr(ws),
                                       c_int64(ws.numel()), N.stream_ptr(dev)), "qsb_kth_value_batched")
     return thr

@@ -302,7 +302,7 @@ FUSE_PRUNE_STEP = True   # False: EMA / select / mask as three (multi-tensor) st
 
 
 def prune_weight_set_step(weights, magnitudes, masks, outs, t: int, sparsity: float, group=None,
-                          shard_by_layer: bool = False):
+                          shard_by_layer: bool = False, hints=None):
     """One unstructured, running-average prune step over a set of replicated weight tensors
     (BASELINE config 4) on every rank of ``group``:
 
@@ -323,7 +323,9 @@ def prune_weight_set_step(weights, magnitudes, masks, outs, t: int, sparsity: fl
     ks = [kth_rank(sparsity, m.numel()) for m in magnitudes]
     if not shard_by_layer and FUSE_PRUNE_STEP and ops.prune_step_supported(magnitudes, weights, masks, outs):
         # EMA, select and mask/apply of every layer in ONE streaming pass (K9, ~17.5 B/elem)
-        return ops.prune_unstructured_step_batched_(magnitudes, weights, masks, outs, ks, t)
+        # hints (ops.new_select_hints(len(weights), device), kept by the caller across steps): warm-started
+        # pivots — from the third step on no sampler pass and a few thousand candidates per layer
+        return ops.prune_unstructured_step_batched_(magnitudes, weights, masks, outs, ks, t, hints=hints)
     ops.magnitude_ema_full_multi_(magnitudes, weights, t)            # one launch for the whole set
     thr = sharded_layer_thresholds(magnitudes, ks, group)            # one launch sequence per rank
     ops.mask_build_apply_multi(magnitudes, thr, weights, masks, outs)  # one launch

@@ -34,6 +34,8 @@ from .util import HostMirror, get_option, kth_rank, logging
 # Route the stock unstructured running-average prune step through the one-pass kernel (K9).  False keeps
 # update_magnitude -> k-th value -> mask build + apply (same results; the tests compare the two).
 FUSE_PRUNE_STEP = True
+# Warm-start the exact k-th value select of that step from the previous step's threshold (same results).
+SELECT_HINTS = True
 
 
 class _MaskApply(torch.autograd.Function):
@@ -179,7 +181,14 @@ class MagnitudePruningCallback(nn.Module):
             k = kth_rank(sparsity, n)
             if k >= n:
                 raise IndexError(f"index {k} is out of bounds for dimension 0 with size {n}")
-            ops.prune_unstructured_step_batched_([mag], [xs], [mask.data], [out], [k], t)
+            # warm-started pivots: the threshold of a running-average magnitude moves slowly from step to step
+            # (reset when the tensor or the rank changes, e.g. at a sparsity ramp point)
+            key = (mag.data_ptr(), n, k)
+            if getattr(self, "_hint_key", None) != key or self._hint.device != mag.device:
+                self._hint = ops.new_select_hints(1, mag.device)
+                self._hint_key = key
+            ops.prune_unstructured_step_batched_([mag], [xs], [mask.data], [out], [k], t,
+                                                 hints=self._hint if SELECT_HINTS else None)
         return _MaskApply.apply(x, mask, out)
 
     def _fused_structured_step(self, x, sparsity, mask, t, refresh):

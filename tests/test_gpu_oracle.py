@@ -1231,3 +1231,74 @@ def test_groupwise_quantizer_uses_device_group_mean():
         grouped[labels == g] = grouped[labels == g].mean(axis=0)
     exp = orc.fq_pow2_fwd(npy(x), orc.scale_to_decimal(grouped.reshape(-1)), 0)
     assert bits_equal(npy(y), exp)
+
+
+# ----------------------------------------------------------------------------- warm-started select (pivot hints)
+@pytest.mark.parametrize("kind", ["normal_abs", "relu", "grid", "signed"])
+def test_kth_value_with_pivot_hints_stays_exact(kind):
+    """A loop that asks for the same order statistic of a slowly drifting tensor: with a hint the pivots come from
+    the previous answer (no sampler) from the third call on.  Every answer must still equal torch.sort's, through
+    slow drift, an abrupt change of the data (the bracket misses: generic route on the device, hint widens), heavy
+    ties and a change of sign."""
+    from qsparse_b200 import ops
+    n = (1 << 22) + 40
+    g = torch.Generator(device="cuda").manual_seed(17)
+    base = torch.randn(n, device="cuda", generator=g) * 0.02
+    noise = torch.randn(n, device="cuda", generator=g) * 0.02
+    take_abs = kind == "normal_abs"
+    hint = ops.new_select_hints(1, base.device)
+    states = []
+    for t in range(12):
+        v = base + noise * (0.01 * t)                       # slow drift
+        if t in (6, 7):
+            v = v * 3.0 + 0.01                              # abrupt change: the hinted bracket misses
+        if kind == "relu":
+            v = torch.relu(v)
+        elif kind == "grid":
+            v = torch.round(v * 64) / 64                    # heavy ties on a quantisation grid
+        for k in ((n // 2,) if t else (n // 2,)):
+            got = ops.kth_value(v, k, take_abs=take_abs, hint=hint)
+            ref = torch.sort(v.abs() if take_abs else v).values[k]
+            assert got.item() == ref.item(), (kind, t, got.item(), ref.item())
+        states.append(int(hint[0, 0].item()))
+    assert states[0] == 1 and 2 in states, states            # the warm route was actually taken
+    # extreme ranks and a fresh hint per rank
+    v = base.abs()
+    for k in (0, 1, n - 2, n - 1):
+        h = ops.new_select_hints(1, base.device)
+        ref = torch.sort(v).values[k].item()
+        for _ in range(4):
+            assert ops.kth_value(v, k, hint=h).item() == ref, k
+
+
+def test_prune_step_with_pivot_hints_equals_unhinted():
+    """K9 over a set of layers for 10 steps with warm-started pivots == the same steps with sampled pivots, bit for
+    bit (magnitudes, thresholds, masks, outputs), including a step at which the weights change abruptly."""
+    from qsparse_b200 import ops
+    from qsparse_b200.util import kth_rank
+    rng = np.random.default_rng(23)
+    shapes = [(256, 256, 3, 3), (512, 1024), (300_007,), (64, 32, 3, 3)]
+    ws = [cu((rng.standard_normal(s) * 0.02).astype(np.float32)) for s in shapes]
+
+    def fresh():
+        return ([torch.zeros_like(w) for w in ws], [torch.ones(w.shape, dtype=torch.bool, device="cuda") for w in ws],
+                [torch.empty_like(w) for w in ws])
+
+    (ma, ka, oa), (mb, kb, ob) = fresh(), fresh()
+    hints = ops.new_select_hints(len(ws), ws[0].device)
+    ks = [kth_rank(0.6, w.numel()) for w in ws]
+    used = 0
+    for t in range(10):
+        if t == 6:
+            ws = [w * 1.7 for w in ws]
+        else:
+            ws = [w * 1.003 for w in ws]
+        ta = ops.prune_unstructured_step_batched_(ma, ws, ka, oa, ks, t)
+        tb = ops.prune_unstructured_step_batched_(mb, ws, kb, ob, ks, t, hints=hints)
+        assert torch.equal(ta, tb), t
+        for i in range(len(ws)):
+            assert torch.equal(ma[i], mb[i]) and torch.equal(ka[i], kb[i]) and torch.equal(oa[i], ob[i]), (t, i)
+            ref = torch.sort(ma[i].reshape(-1)).values[ks[i]]
+            assert tb[i].item() == ref.item(), (t, i)
+        used += int((hints[:, 0] == 2).sum().item())
+    assert used > 0
