@@ -373,6 +373,28 @@ def run_c4(args, env):
                 cb(w, sparsity, m)
     ms_mod = back_to_back(torch, mod_step, min(steps, 20), 3, world, dev)
     del cbs, cmasks
+    # the same through prune()-wrapped modules with the model-level batched step (WeightSetPruner)
+    import qsparse_b200 as q
+
+    class _W(torch.nn.Module):
+        def __init__(self, w):
+            super().__init__()
+            self.weight = torch.nn.Parameter(w.clone(), requires_grad=False)
+
+    q.set_qsparse_options(log_on_created=False)
+    mods = torch.nn.ModuleList([q.prune(_W(w), sparsity=sparsity, dimensions=set(range(w.dim())), start=0, interval=1,
+                                        repetition=1) for w in ws]).train()
+    pruner = q.WeightSetPruner(mods)
+
+    def batched_mod_step():
+        with torch.no_grad():
+            pruner.step()
+            for m in mods:
+                m.weight
+    for _ in range(3):
+        batched_mod_step()
+    ms_bmod = back_to_back(torch, batched_mod_step, min(steps, 50), 3, world, dev)
+    del mods, pruner
 
     # e2e: pinned host weights in, pruned weights + masks out
     hws = [torch.empty(w.shape, dtype=torch.float32).pin_memory() for w in ws]
@@ -440,6 +462,9 @@ def run_c4(args, env):
                                          "of 29 thresholds + replicated multi-tensor mask/apply"},
         "module_api": {"api": "MagnitudePruningCallback(running_average=True)(w, sparsity, mask) per layer",
                        "ms_per_step": round(ms_mod, 5), "value": round(world * 29 * n / (ms_mod * 1e-3) / 1e9, 2)},
+        "module_api_batched": {"api": "WeightSetPruner(model).step() + every prune()-wrapped module's .weight",
+                               "ms_per_step": round(ms_bmod, 5),
+                               "value": round(world * 29 * n / (ms_bmod * 1e-3) / 1e9, 2)},
         "launch_mode": "eager (sampler, streaming pass, 3 candidate passes, fix-up, gated full pass)",
         "gpu_launches": 7 * steps,
         "e2e": {"value": round(world * 29 * n / e2e_s / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": 4 * n * world,

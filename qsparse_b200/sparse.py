@@ -239,7 +239,14 @@ class MagnitudePruningCallback(nn.Module):
         refresh = (sparsity >= 0 and (t % self.mask_refresh_interval == 0 and t <= self.stop_mask_refresh)
                    and (t > 0 or not self.running_average))
         out = None
-        if t < self.stop_mask_refresh:
+        pre = getattr(self, "_precomputed", None)
+        if pre is not None:
+            # this step's magnitude / mask / output were computed for the whole weight set in one batched launch
+            # sequence (WeightSetPruner.step); valid for exactly this step of this tensor
+            self._precomputed = None
+            if pre[0] == t and pre[1] is x and refresh and t < self.stop_mask_refresh:
+                out = _MaskApply.apply(x, mask, pre[2])
+        if out is None and t < self.stop_mask_refresh:
             if refresh:
                 out = self._fused_unstructured_step(x, sparsity, mask, t)
             if out is None:
@@ -374,6 +381,92 @@ class PruneLayer(nn.Module):
         self._n_updates.data.add_(1)
         self._n_mirror.wrote(self._n_updates, n + 1)
         return out
+
+
+class WeightSetPruner:
+    """EXTENSION (SURVEY 8e "weights"): the unstructured running-average prune step of EVERY pruned
+    weight of a model in one batched launch sequence instead of one sequence per layer.
+
+    Every ``prune(layer, dimensions=all axes)`` module runs, on each access of its ``weight``, magnitude EMA +
+    exact k-th value + mask + apply for its own tensor (``MagnitudePruningCallback.forward``): 7 launches per
+    layer and step, 1.9 ms for the 29 layers of BASELINE config 4 although the work is 0.2 ms.  The weights
+    only change at ``optimizer.step()``, so the whole set can be done up front::
+
+        pruner = WeightSetPruner(model)
+        for batch in data:
+            pruner.step()            # one streaming pass over all pruned weights (K9, warm-started pivots)
+            loss = model(batch) ...  # each layer's PruneLayer picks its precomputed mask / output up
+
+    Results are bit-identical to the per-layer path: the same kernels run with the same arguments; a layer whose
+    state does not allow it this step (not started, ramp point, eval, custom callback, first step) is simply left
+    to its own forward.  ``step()`` must run after the weights were last modified and before the forward."""
+
+    def __init__(self, model: nn.Module):
+        self.layers = []
+        for mod in model.modules():
+            p = getattr(mod, "prune", None)
+            if isinstance(p, PruneLayer) and "weight" in getattr(mod, "_parameters", {}):
+                self.layers.append((mod, p))
+        self._hints = None
+        self._hint_key = None
+
+    def _eligible(self, mod, p):
+        cb = p.callback
+        w = mod._parameters["weight"]
+        if not (p.training and cb.training and type(cb) is MagnitudePruningCallback and FUSE_PRUNE_STEP):
+            return None
+        if not p.initted or not cb.initted or not cb.running_average or cb.use_gradient or cb.l0:
+            return None
+        if not hasattr(cb, "magnitude") or tuple(p.mask.shape) != tuple(w.shape):
+            return None
+        n = p._n_mirror.get(p._n_updates)
+        if n < p.start or n in p.schedules:
+            return None
+        t = cb._t()
+        sparsity = p._s_mirror.get(p._cur_sparsity)
+        refresh = (sparsity >= 0 and (t % cb.mask_refresh_interval == 0 and t <= cb.stop_mask_refresh) and t > 0)
+        if not refresh or t >= cb.stop_mask_refresh:
+            return None
+        if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
+            return None
+        k = kth_rank(sparsity, w.numel())
+        if k >= w.numel():
+            return None
+        return w, cb, t, k
+
+    @torch.no_grad()
+    def step(self) -> int:
+        """Precompute this step for every eligible layer; returns how many layers were batched."""
+        todo = []
+        for mod, p in self.layers:
+            e = self._eligible(mod, p)
+            if e is not None:
+                todo.append((p,) + e)
+        if not todo:
+            return 0
+        # all layers of one batch share the callback step index only if they started together: group by t
+        done = 0
+        by_t = {}
+        for item in todo:
+            by_t.setdefault(item[3], []).append(item)
+        for t, items in by_t.items():
+            ws = [it[1].detach() for it in items]
+            mags = [it[2].magnitude.data for it in items]
+            masks = [it[0].mask.data for it in items]
+            outs = [torch.empty_like(w) for w in ws]
+            ks = [it[4] for it in items]
+            if not ops.prune_step_supported(mags, ws, masks, outs):
+                continue
+            key = tuple((m.data_ptr(), k) for m, k in zip(mags, ks))
+            if self._hint_key != key:
+                self._hints = ops.new_select_hints(len(items), ws[0].device)
+                self._hint_key = key
+            ops.prune_unstructured_step_batched_(mags, ws, masks, outs, ks, t,
+                                                 hints=self._hints if SELECT_HINTS and len(by_t) == 1 else None)
+            for it, o in zip(items, outs):
+                it[2]._precomputed = (t, it[1], o)
+            done += len(items)
+        return done
 
 
 def prune(inp: nn.Module = None, sparsity: float = 0.5, dimensions: Iterable[int] = {1},

@@ -348,6 +348,54 @@ def test_weight_chain_fusion_equals_unfused():
         assert b[0].fused_weight_steps >= 5, (cb_name, b[0].fused_weight_steps)
 
 
+def test_weight_set_pruner_equals_per_layer_path():
+    """WeightSetPruner.step() (one batched launch sequence for all pruned weights) followed by the forward ==
+    the per-layer path, bit for bit: outputs, weight gradients, masks, magnitudes, counters — over warm-up, the
+    ramp points (left to the layers themselves), steady state and an eval step."""
+    import qsparse_b200 as q
+    q.set_qsparse_options(log_on_created=False)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+
+    def make():
+        torch.manual_seed(3)
+        layers = [torch.nn.Conv2d(8, 64, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(64, 64, 3, padding=1),
+                  torch.nn.ReLU(), torch.nn.Flatten(), torch.nn.Linear(64 * 6 * 6, 300)]
+        net = torch.nn.Sequential(*layers).cuda()
+        for i in (0, 2, 5):
+            net[i] = q.prune(net[i], sparsity=0.5, dimensions={0, 1, 2, 3} if i != 5 else {0, 1}, start=2, interval=3,
+                             repetition=2)
+        return net
+
+    a, b = make(), make()
+    pruner = q.WeightSetPruner(b)
+    assert len(pruner.layers) == 3
+    a.train(), b.train()
+    batched = 0
+    for step in range(14):
+        x = torch.randn(4, 8, 6, 6, device="cuda", generator=torch.Generator("cuda").manual_seed(200 + step))
+        if step == 10:
+            a.eval(), b.eval()
+        batched += pruner.step()
+        ya, yb = a(x), b(x)
+        assert torch.equal(ya, yb), step
+        if step != 10:
+            ya.square().mean().backward()
+            yb.square().mean().backward()
+            for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+                if pa.grad is not None:
+                    assert torch.equal(pa.grad, pb.grad), (step, na)
+                    with torch.no_grad():
+                        pa.sub_(0.05 * pa.grad)
+                        pb.sub_(0.05 * pb.grad)
+                    pa.grad = pb.grad = None
+        sa, sb = a.state_dict(), b.state_dict()
+        for key in sa:
+            assert torch.equal(sa[key], sb[key]), (step, key)
+        a.train(), b.train()
+    assert batched >= 3 * 6, batched
+
+
 def test_unstructured_callback_fused_step_equals_unfused():
     """MagnitudePruningCallback on a weight-shaped mask: the K9 route (one streaming pass) and the
     update_magnitude -> kth_value -> mask_build_apply route give identical magnitudes, masks, outputs and
