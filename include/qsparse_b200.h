@@ -81,9 +81,9 @@ int qsb_device_info(int *sm_count, int64_t *l2_bytes);
  *   key 16: column-mode reductions: most threads of a CTA along one row (32, 64 = default, 128, 256);
  *          the CTA's other threads walk interleaved rows and are combined in shared memory, so
  *          256 / value times fewer partials reach the finalize;
- *   key 17: row-mode statistics kernels: 2 = 8 x 256-bit loads in flight per lane, 2 CTAs / SM
- *          (default), 0 = 4 loads, 4 CTAs / SM (the reduction plan — and with it the summation
- *          order — follows);
+ *   key 17: row-mode statistics kernels: 2 = 8 x 256-bit loads in flight per lane, 2 CTAs / SM,
+ *          0 = 4 loads, 4 CTAs / SM, any other value = by row length (default: 2 for rows of
+ *          >= 2048 elements, else 0); the reduction plan — and with it the summation order — follows;
  *   key 18: 1 = qsb_reduce_prune_quant_step reads the channels the previous mask keeps with
  *          L2::evict_last (the forward pass re-reads exactly those next) and the rest with
  *          L2::evict_first (default), 0 = default policy for everything. */

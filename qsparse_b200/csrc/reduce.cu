@@ -40,9 +40,17 @@ constexpr int kRowCtasPerSm = 4;  // column mode / default row variant
 // row-kernel variant (tuning key 17): 0 = 4 x 256-bit loads per lane in flight, 4 CTAs / SM;
 // 2 = 8 loads, 2 CTAs / SM (default: half as many partials for the finalize / the fused tail).
 // The plan's warp count follows.
-static int g_row_variant = 2;  // measured on the bench step: 158.7 (0) / 159.2 (1) / 156.8 us (2)
-void set_reduce_row_variant(int v) { g_row_variant = (v == 0) ? 0 : 2; }
-static inline int row_ctas_per_sm() { return g_row_variant == 0 ? 4 : 2; }
+static int g_row_variant = -1;  // -1 = by row length (default), 0 / 2 = forced
+void set_reduce_row_variant(int v) { g_row_variant = (v == 0 || v == 2) ? v : -1; }
+// Long rows (>= 2048 elements: 8 full vectors per lane and round) keep 8 loads in flight per lane at 2 CTAs / SM
+// — measured on the bench step 158.7 -> 156.8 us, and half as many partials for the tail; on shorter rows a
+// round has fewer than 8 vectors per lane, so the extra registers only cost warps ([256,128,28,28]: 0.62 -> 0.54
+// of the copy peak with the 8-load variant): those keep 4 loads at 4 CTAs / SM.
+static inline int row_variant_for(int64_t inner) {
+  if (g_row_variant >= 0) return g_row_variant;
+  return inner >= 2048 ? 2 : 0;
+}
+static inline int row_ctas_per_sm(int variant) { return variant == 0 ? 4 : 2; }
 // tuning key 18: the fused step reads the previous mask's kept channels with L2::evict_last
 static int g_keep_hint = 1;
 void set_reduce_keep_hint(int v) { g_keep_hint = v != 0; }
@@ -855,8 +863,9 @@ void set_reduce_seg_min(int v) { g_reduce_seg_min = v >= 256 ? v : 256; }
 ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
                             const float *x) {
   ReducePlan p{};
+  p.row_variant = row_variant_for(inner);
   const int64_t warps_phys =
-      (int64_t)device_props().sm_count * row_ctas_per_sm() * (QSB_THREADS / 32);
+      (int64_t)device_props().sm_count * row_ctas_per_sm(p.row_variant) * (QSB_THREADS / 32);
   if (inner >= kTileMinInner && inner <= kTileMaxInner) {
     // short rows: the tile kernel.  One slot (virtual warp) per row of a tile, 3 CTAs of 32 slots
     // per SM; slots = m * channels so that a slot only ever sees one channel.
@@ -1009,14 +1018,14 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
     else QSB_CUDA_TRY(go(reduce_tile_kernel<WHAT, 8, 32, Tail>));
   } else if (pl.row_mode) {
     constexpr int kWarps = QSB_THREADS / 32;
-    int64_t grid = (int64_t)device_props().sm_count * row_ctas_per_sm();
+    int64_t grid = (int64_t)device_props().sm_count * row_ctas_per_sm(pl.row_variant);
     const int64_t need = (pl.vwarps + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
     auto go = [&](auto kernel) {
       return launch_k(kernel, dim3((unsigned)grid), dim3(QSB_THREADS), dyn, stream, x, pl.rows, inner, pl.seg,
                       pl.segs_per_row, pl.vwarps, P, pl.cta_combine, (int)channels, tail);
     };
-    if (g_row_variant == 2) QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 8, 2, Tail>));
+    if (pl.row_variant == 2) QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 8, 2, Tail>));
     else QSB_CUDA_TRY(go(reduce_rows_kernel<WHAT, 4, 4, Tail>));
   } else {
     const int64_t threads = pl.ncols / pl.vcol;

@@ -17,6 +17,7 @@ struct ReducePlan {
   bool row_mode;
   int64_t rows, seg, segs_per_row, vwarps;       // row mode
   int tile_spans, tile_span_stride;  // tile kernel: pieces per CTA visit, floats between them in shared memory
+  int row_variant;  // row mode: 0 = 4 loads in flight per lane, 4 CTAs / SM; 2 = 8 loads, 2 CTAs / SM
   int cta_combine;  // row mode, one channel: a CTA writes one partial for its 8 warps
   int tile_rows;  // > 0: short rows, the tile kernel (tile_rows consecutive rows per CTA visit)
   int64_t nrows, ncols, chunks, rows_per_chunk;  // column mode

@@ -595,7 +595,7 @@ def test_one_launch_step_equals_two_launch_step(shape, C):
                         assert torch.equal(st[key], ref_stats[t][2][key]), (key, t, variant, hint)
                         assert torch.equal(stg[key], ref_stats[t][2][key]), (key, t, variant, hint, "graph mode")
     finally:
-        ops.set_tuning(17, 2)
+        ops.set_tuning(17, -1)
         ops.set_tuning(18, 1)
 
 
