@@ -30,6 +30,11 @@ for stage in "$@"; do
           bench.py --gpus $n --steps 500 --warmup 10 > $out/${tag}_bench_n${n}.json 2> $out/${tag}_bench_n${n}.err
         echo "rc=$?" >> $out/${tag}_bench_n${n}.err
       done ;;
+    sanitize)
+      for tool in memcheck racecheck synccheck; do
+        echo "== compute-sanitizer --tool $tool" >> $out/${tag}_sanitizer.txt
+        timeout 900 compute-sanitizer --tool $tool python benchmarks/sanitize_target.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Error|error|sanitize target done" | head -30 >> $out/${tag}_sanitizer.txt
+      done ;;
     ref)
       timeout 600 python bench.py --impl reference --steps 10 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err ;;
     configs)

@@ -78,5 +78,52 @@ for lay, off in (((300, 24, 196), 0), ((40, 96, 64), 3), ((9, 700, 100), 1), ((2
     ops.ste_bwd(xl.clone(), decl, True, 8, 0, lay)
     ops.quant_export_int8(xl, ops.EXPORT_LINE, lin, 4, lay, pack4=True)
     ops.quant_export_int8(xl, ops.EXPORT_SCALER, 0.3, 4, (1, 1, n_), pack4=True)
+# ---- round 2 ----
+# one-launch training step (reduction + last-arriving CTA's parameter step) in every stage-1 mode, both row
+# variants, with / without the L2 keep hint, host step index and device step counter, local statistics output
+for lay in ((8, 16, 3136), (8, 16, 196), (4, 200, 81), (32, 48, 1), (64, 1000, 1), (3, 1, 5000), (2, 1024, 300)):
+    C = lay[1]
+    xs_ = torch.relu(torch.randn(lay, device=dev, generator=g))
+    for variant in (2, 0, -1):
+        ops.set_tuning(17, variant)
+        for hint_ in (1, 0):
+            ops.set_tuning(18, hint_)
+            mag_ = torch.zeros(C, device=dev)
+            mask_ = torch.ones(C, dtype=torch.bool, device=dev)
+            sc_, de_ = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+            ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+            asum = torch.empty(C, dtype=torch.float64, device=dev)
+            amax = torch.empty(C, dtype=torch.float32, device=dev)
+            tm = torch.full((8,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+            for t in range(3):
+                ops.reduce_prune_quant_step(xs_, lay, mag_, mask_, sc_, de_, float(lay[0] * lay[2]), t, 1,
+                                            t > 0 and C > 1, C // 2 if C > 1 else 0, 8, t, True, abssum_out=asum,
+                                            absmax_out=amax, stats_local=(t == 1), timing=tm)
+                ops.reduce_prune_quant_step(xs_, lay, mag_, mask_, sc_, de_, float(lay[0] * lay[2]), 0, 1,
+                                            1 if C > 1 else 1 << 30, C // 2 if C > 1 else 0, 8, 0, True,
+                                            step_counter=ctr)
+ops.set_tuning(17, -1)
+ops.set_tuning(18, 1)
+# the stand-alone parameter step on finalized rows (host-buffer pipeline form)
+st_ = ops.reduce_stats(x, layout, abssum=True, absmax=True)
+ops.prune_quant_rows_step_params(mag, mask, scale, dec, st_, 8 * 196.0, 2, 1, True, 8, 8, 2, True)
+# K8 with an element mask, group mean, packed int4 on the map skeleton (aligned, n % 8 == 0)
+for shape in ((64, 4608), (37, 256), (16, 16384)):
+    xr = torch.randn(shape, device=dev, generator=g) * 0.05
+    mk = torch.rand(shape, device=dev, generator=g) > 0.5
+    for kind, w in ((ops.ROW_LINE, 2), (ops.ROW_SCALER, 1), (ops.ROW_DECIMAL, 1)):
+        ops.row_quant_fused_(xr, torch.zeros(shape[0], w, device=dev), kind, 4, 1 if kind == ops.ROW_LINE else 0, mask=mk)
+ops.group_mean(torch.rand(96, 2, device=dev), torch.randint(0, 5, (96,), device=dev), 5)
+xa = torch.randn(8, 16, 196, device=dev, generator=g)
+ops.quant_export_int8(xa, ops.EXPORT_DECIMAL, torch.full((16,), 3.0, device=dev), 4, (8, 16, 196), pack4=True)
+ops.quant_export_int8(xa, ops.EXPORT_LINE, torch.tensor([[-0.5, 0.5]] * 16, device=dev), 4, (8, 16, 196), pack4=True)
+# warm-started select and fused prune step (hint states 0 -> 1 -> 2, then a miss)
+hint = ops.new_select_hints(1, dev)
+vv = torch.randn((1 << 22) + 8, device=dev, generator=g)
+for t in range(5):
+    ops.kth_value(vv * (1 + 0.001 * t) if t != 3 else vv * 4 + 1, vv.numel() // 2, hint=hint)
+hints9 = ops.new_select_hints(len(xs9), dev)
+for t in range(2, 6):
+    ops.prune_unstructured_step_batched_(mg9, xs9, mk9, ot9, [x_.numel() // 2 for x_ in xs9], t, hints=hints9)
 torch.cuda.synchronize()
 print("sanitize target done")
