@@ -459,10 +459,20 @@ __global__ void __launch_bounds__(QSB_THREADS)
   const int64_t n_main = (n / V) * V;
   const int64_t t0 =
       (int64_t)(reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * kTile;
-  // first row / column / channel of the tile (uniform across the CTA)
-  const int64_t row0 = t0 / inner;
-  const uint32_t col0 = (uint32_t)(t0 - row0 * inner);
-  const uint32_t c0 = (uint32_t)(row0 % channels);
+  // first row / column / channel of the tile (uniform across the CTA); 32-bit divisions whenever the
+  // tile starts below 2^32 (a 64-bit one is ~100 instructions, executed by every thread of every CTA:
+  // with the prune mask folded in, three quarters of the bench tensor's CTAs only store zeros and
+  // their ~300 instructions per warp made the kernel issue-bound, 61 % SM throughput in ncu)
+  uint32_t col0, c0;
+  if (t0 <= 0xffffffffLL) {
+    const uint32_t row0 = (uint32_t)t0 / inner;
+    col0 = (uint32_t)t0 - row0 * inner;
+    c0 = row0 % channels;
+  } else {
+    const int64_t row0 = t0 / inner;
+    col0 = (uint32_t)(t0 - row0 * inner);
+    c0 = (uint32_t)(row0 % channels);
+  }
   const uint32_t rows = (col0 + kTile - 1) / inner + 1;
   for (uint32_t k = threadIdx.x; k < rows; k += QSB_THREADS)
     tab[k] = op.params((int32_t)((c0 + k) % channels));
@@ -498,6 +508,21 @@ __global__ void __launch_bounds__(QSB_THREADS)
       VecF<V> o0, o1;
       VecB<V> ob;
       const P p0 = tab[ru[u]];
+      if constexpr (Op::kCanSkip) {
+        // a vector of a skipped (pruned) channel: its output is the op's value at 0 — the same for all 8
+        // elements — so evaluate it once instead of eight times (and never touch the unread registers)
+        if (skipv[u] && (MODE == 0 || leftu[u] >= (uint32_t)V)) {
+          float z0 = 0.f, z1 = 0.f;
+          uint8_t zb = 0;
+          op.apply(0.f, 0.f, (uint8_t)1, p0, z0, z1, zb);
+#pragma unroll
+          for (int j = 0; j < V; ++j) o0.v[j] = z0, o1.v[j] = z1, ob.b[j] = zb;
+          if constexpr (Op::kOut0) st_vec<V, SH>(io.out0 + e, o0);
+          if constexpr (Op::kOut1) st_vec<V, SH>(io.out1 + e, o1);
+          if constexpr (Op::kOutB) store_outb<Op, V>(io.outb, e, ob);
+          continue;
+        }
+      }
       // Short rows: almost every warp holds a lane whose vector straddles two rows (one vector in six with 7x7
       // maps), so the two branches below would BOTH be issued for nearly every warp.  Below kUnifyInner the
       // per-element parameter select is therefore the only path (a few SELs per element, no divergence).
