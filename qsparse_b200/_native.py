@@ -39,6 +39,8 @@ _SIGNATURES = {
     "qsb_mask_apply": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, c_int64, _P]),
     "qsb_reduce_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "qsb_reduce_stats": (c_int, [_P, c_int, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "qsb_reduce_stats_fused": (c_int, [_P, c_int, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int64, _P,
+                                       _P]),
     "qsb_scale_ema": (c_int, [_P, _P, c_int64, c_int, c_int64, _P]),
     "qsb_scale_to_decimal": (c_int, [_P, _P, c_int64, _P]),
     "qsb_lines_ema": (c_int, [_P, _P, _P, c_int64, c_int64, _P]),

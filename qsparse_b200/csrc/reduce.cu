@@ -33,6 +33,8 @@
 #include "reduce_internal.cuh"
 #include "step_epilogue.cuh"
 
+#include <type_traits>
+
 namespace qsb {
 
 constexpr int kRowModeMinInner = 64;
@@ -208,12 +210,140 @@ __device__ __forceinline__ void fused_step_tail(const StepTail &t, unsigned char
 // start time of any CTA
 template <class Tail>
 __device__ __forceinline__ StepPrefetch fused_step_begin(const Tail &tail) {
-  if constexpr (Tail::kFused) {
+  if constexpr (std::is_same<Tail, StepTail>::value) {
     if (tail.a.timing && threadIdx.x == 0) atomicMin(tail.a.timing, global_ns());
     return step_prefetch(tail.a);
   } else {
     return StepPrefetch{false, 0.f, 0.f, 0};
   }
+}
+
+// ---------------------------------------------------------------------------
+// The same idea for the stand-alone reductions (qsb_reduce_stats): when the partial array is small
+// (channels x entries <= kFinalTailMaxEntries) the last-arriving CTA of stage 1 combines the partials
+// itself — a warp per channel, fixed order — instead of a second launch that is pure latency
+// (3.5-5 us behind a 12-35 us stage 1).
+// ---------------------------------------------------------------------------
+struct FinalOut {
+  float *absmax, *mn, *mx;
+  double *abssum, *nnz;
+};
+constexpr int64_t kFinalTailMaxEntries = 16384;
+struct FinalTail {
+  static constexpr bool kFused = true;
+  FinalOut out;
+  unsigned int *arrival;
+  int64_t channels, count, q;
+};
+
+template <int WHAT>
+__device__ __forceinline__ void finalize_in_cta(const Partials &P, const FinalTail &t) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t c = warp; c < t.channels; c += nwarps) {
+    uint32_t amax = 0;
+    float mn = INFINITY, mx = -INFINITY;
+    bool nan = false;
+    double asum = 0.0, nnz = 0.0;
+    for (int64_t j0 = lane; j0 < t.count; j0 += 4 * 32) {
+      int64_t idx[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t j = j0 + 32 * u;
+        ok[u] = j < t.count;
+        const int64_t hi = ok[u] ? (int64_t)((uint32_t)j / (uint32_t)t.q) : 0;  // entries <= 16 Ki: 32-bit
+        idx[u] = ok[u] ? hi * (t.channels * t.q) + c * t.q + (j - hi * t.q) : 0;
+      }
+      if constexpr (WHAT & QSB_STAT_ABSMAX) {
+        uint32_t b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) b[u] = ok[u] ? __ldcg(P.amax + idx[u]) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) amax = b[u] > amax ? b[u] : amax;
+      }
+      if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? __ldcg(P.mn + idx[u]) : INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          nan |= (v[u] != v[u]);
+          mn = fminf(mn, v[u]);
+        }
+      }
+      if constexpr (WHAT & QSB_STAT_MINMAX) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? __ldcg(P.mx + idx[u]) : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          nan |= (v[u] != v[u]);
+          mx = fmaxf(mx, v[u]);
+        }
+      }
+      if constexpr (WHAT & QSB_STAT_ABSSUM) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? __ldcg(P.asum + idx[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) asum += v[u];
+      }
+      if constexpr (WHAT & QSB_STAT_NNZ) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? __ldcg(P.nnz + idx[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nnz += v[u];
+      }
+    }
+    amax = warp_reduce(amax, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
+    mn = warp_reduce(mn, [](float a, float b) { return fminf(a, b); });
+    mx = warp_reduce(mx, [](float a, float b) { return fmaxf(a, b); });
+    nan = __any_sync(0xffffffffu, nan);
+    asum = warp_reduce(asum, [](double a, double b) { return a + b; });
+    nnz = warp_reduce(nnz, [](double a, double b) { return a + b; });
+    if (lane == 0) {
+      const float qnan = __uint_as_float(0x7fc00000u);
+      if constexpr (WHAT & QSB_STAT_ABSMAX)
+        if (t.out.absmax) t.out.absmax[c] = __uint_as_float(amax);
+      if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ))
+        if (t.out.mn) t.out.mn[c] = nan ? qnan : mn;
+      if constexpr (WHAT & QSB_STAT_MINMAX)
+        if (t.out.mx) t.out.mx[c] = nan ? qnan : mx;
+      if constexpr (WHAT & QSB_STAT_ABSSUM)
+        if (t.out.abssum) t.out.abssum[c] = asum;
+      if constexpr (WHAT & QSB_STAT_NNZ)
+        if (t.out.nnz) t.out.nnz[c] = nnz;
+    }
+  }
+}
+
+// last-arriver election shared by the two tails
+__device__ __forceinline__ bool cta_is_last(unsigned int *arrival) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    __threadfence();
+    const int last = atomicAdd(arrival, 1u) == total - 1;
+    if (last) {
+      __threadfence();
+      *arrival = 0;
+    }
+    s_last = last;
+  }
+  __syncthreads();
+  return s_last != 0;
+}
+
+template <int WHAT>
+__device__ __forceinline__ void fused_tail(const FinalTail &t, const Partials &P, unsigned char *, const StepPrefetch &) {
+  if (cta_is_last(t.arrival)) finalize_in_cta<WHAT>(P, t);
+}
+template <int WHAT>
+__device__ __forceinline__ void fused_tail(const StepTail &t, const Partials &, unsigned char *smem,
+                                           const StepPrefetch &pre) {
+  fused_step_tail(t, smem, pre);
 }
 
 // 256-bit load with a run-time L2 eviction policy (createpolicy): kept channels of the previous
@@ -255,7 +385,7 @@ __global__ void __launch_bounds__(QSB_THREADS, MINB)
     // every item of a virtual warp belongs to ONE channel
     uint64_t pol = 0;
     bool use_pol = false;
-    if constexpr (Tail::kFused) {
+    if constexpr (std::is_same<Tail, StepTail>::value) {
       if (tail.keep_hint) {
         use_pol = true;
         pol = l2_policy(tail.keep_hint[(vw / segs_per_row) % channels] != 0);
@@ -281,7 +411,7 @@ __global__ void __launch_bounds__(QSB_THREADS, MINB)
 #pragma unroll
         for (int u = 0; u < U; ++u)
           if (j + 32 * u < nv) {
-            if (Tail::kFused && use_pol) v[u] = ld_vec8_policy(pv + ((j + 32 * u) << 3), pol);
+            if (std::is_same<Tail, StepTail>::value && use_pol) v[u] = ld_vec8_policy(pv + ((j + 32 * u) << 3), pol);
             else v[u] = ld_vec<8, Hint::KEEP>(pv + ((j + 32 * u) << 3));
           }
 #pragma unroll
@@ -341,7 +471,7 @@ __global__ void __launch_bounds__(QSB_THREADS, MINB)
       warp_store<WHAT>(acc, lane, P, vw);
     }
   }
-  if constexpr (Tail::kFused) fused_step_tail(tail, qsb_dyn_smem, pre);
+  if constexpr (Tail::kFused) fused_tail<WHAT>(tail, P, qsb_dyn_smem, pre);
 }
 
 // ---------------------------------------------------------------------------
@@ -478,7 +608,7 @@ __global__ void __launch_bounds__(QSB_THREADS, kTileCtasPerSm)
     group_store<WHAT, LPR>(acc[q], lane, P, slot0 + rr, rr < nslots);
   }
   // the tile buffer (32 KB) is free now: the parameter step's shared memory (<= 20.5 KB) lives there
-  if constexpr (Tail::kFused) fused_step_tail(tail, reinterpret_cast<unsigned char *>(tile), pre);
+  if constexpr (Tail::kFused) fused_tail<WHAT>(tail, P, reinterpret_cast<unsigned char *>(tile), pre);
 }
 
 // ---------------------------------------------------------------------------
@@ -584,10 +714,10 @@ __global__ void __launch_bounds__(QSB_THREADS)
     reduce_cols_kernel(const float *__restrict__ x, int64_t nrows, int64_t ncols,
                        int64_t rows_per_chunk, int tpr, Partials P, const __grid_constant__ Tail tail) {
   extern __shared__ __align__(16) unsigned char qsb_dyn_smem[];
-  if constexpr (Tail::kFused) pdl_wait();  // the old state may have been written by the kernel just before
+  if constexpr (std::is_same<Tail, StepTail>::value) pdl_wait();  // the old state may have been written by the kernel just before
   const StepPrefetch pre = fused_step_begin(tail);
   reduce_cols_body<WHAT, V>(x, nrows, ncols, rows_per_chunk, tpr, P);
-  if constexpr (Tail::kFused) fused_step_tail(tail, qsb_dyn_smem, pre);
+  if constexpr (Tail::kFused) fused_tail<WHAT>(tail, P, qsb_dyn_smem, pre);
 }
 
 // ---------------------------------------------------------------------------
@@ -596,11 +726,6 @@ __global__ void __launch_bounds__(QSB_THREADS)
 // (q = segments per row in row mode, `inner` in column mode).
 // G threads per channel (32: a warp; 256: a CTA), fixed order.
 // ---------------------------------------------------------------------------
-struct FinalOut {
-  float *absmax, *mn, *mx;
-  double *abssum, *nnz;
-};
-
 template <int WHAT, int G>
 __global__ void __launch_bounds__(QSB_THREADS)
     reduce_finalize_kernel(Partials P, FinalOut out, int64_t channels,
@@ -1006,7 +1131,7 @@ static int run_reduce(const float *x, const ReducePlan &pl, int64_t channels,
                       int64_t inner, const Partials &P, const FinalOut &out,
                       cudaStream_t stream, bool finalize = true, const Tail &tail = Tail{}) {
   // dynamic shared memory of the fused parameter step (the tile kernel re-uses its tile buffer)
-  const size_t dyn = Tail::kFused ? step_smem_bytes((int)channels) : 0;
+  const size_t dyn = std::is_same<Tail, StepTail>::value ? step_smem_bytes((int)channels) : 0;
   if (pl.row_mode && pl.tile_rows > 0) {
     const int64_t grid = (pl.vwarps + pl.tile_rows - 1) / pl.tile_rows;
     auto go = [&](auto kernel) {
@@ -1068,11 +1193,10 @@ extern "C" int64_t qsb_reduce_workspace_bytes(int64_t outer, int64_t channels,
   return partial_bytes(pl.n_partials) + 256;
 }
 
-extern "C" int qsb_reduce_stats(const float *x, int what, int64_t outer,
-                                int64_t channels, int64_t inner, float *absmax,
-                                float *mn, float *mx, double *abssum,
-                                double *nnz, float *tensor_min, void *workspace,
-                                int64_t workspace_bytes, void *stream_) {
+static int reduce_stats_impl(const float *x, int what, int64_t outer, int64_t channels, int64_t inner,
+                             float *absmax, float *mn, float *mx, double *abssum, double *nnz,
+                             float *tensor_min, void *workspace, int64_t workspace_bytes,
+                             unsigned int *arrival, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (outer <= 0 || channels <= 0 || inner <= 0) return QSB_E_BADARG;
   if (!x || !workspace) return QSB_E_BADARG;
@@ -1086,9 +1210,16 @@ extern "C" int qsb_reduce_stats(const float *x, int what, int64_t outer,
   const Partials P = partials_from_workspace(workspace, pl.n_partials);
   FinalOut out{absmax, mn, mx, abssum, nnz};
   int rc;
+  // small partial arrays: the last-arriving CTA of stage 1 finalizes (one launch instead of two)
+  const bool fuse_final = arrival != nullptr && channels * pl.fin_count <= kFinalTailMaxEntries &&
+                          pl.fin_count < 0x7fffffffLL && pl.fin_q < 0x7fffffffLL;
+  const FinalTail ft{out, arrival, channels, pl.fin_count, pl.fin_q};
   switch (what) {
-#define QSB_CASE(W) \
-  case W: rc = run_reduce<W>(x, pl, channels, inner, P, out, stream); break;
+#define QSB_CASE(W)                                                                                       \
+  case W:                                                                                                 \
+    rc = fuse_final ? run_reduce<W, FinalTail>(x, pl, channels, inner, P, out, stream, false, ft)         \
+                    : run_reduce<W>(x, pl, channels, inner, P, out, stream);                              \
+    break;
     QSB_CASE(QSB_STAT_ABSMAX)
     QSB_CASE(QSB_STAT_MINMAX)
     QSB_CASE(QSB_STAT_ABSSUM)
@@ -1097,10 +1228,12 @@ extern "C" int qsb_reduce_stats(const float *x, int what, int64_t outer,
     QSB_CASE(QSB_STAT_ABSSUM | QSB_STAT_NNZ | QSB_STAT_ABSMAX)
     QSB_CASE(QSB_STAT_ABSMAX | QSB_STAT_MINMAX)
 #undef QSB_CASE
-    default:
+    default: {
       // any other combination: everything in one pass
-      rc = run_reduce<QSB_STAT_ABSMAX | QSB_STAT_MINMAX | QSB_STAT_ABSSUM |
-                      QSB_STAT_NNZ>(x, pl, channels, inner, P, out, stream);
+      constexpr int kAll = QSB_STAT_ABSMAX | QSB_STAT_MINMAX | QSB_STAT_ABSSUM | QSB_STAT_NNZ;
+      rc = fuse_final ? run_reduce<kAll, FinalTail>(x, pl, channels, inner, P, out, stream, false, ft)
+                      : run_reduce<kAll>(x, pl, channels, inner, P, out, stream);
+    }
   }
   if (rc) return rc;
   if ((what & QSB_STAT_NNZ) && tensor_min) {
@@ -1112,6 +1245,26 @@ extern "C" int qsb_reduce_stats(const float *x, int what, int64_t outer,
     QSB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int qsb_reduce_stats(const float *x, int what, int64_t outer, int64_t channels, int64_t inner,
+                                float *absmax, float *mn, float *mx, double *abssum, double *nnz,
+                                float *tensor_min, void *workspace, int64_t workspace_bytes, void *stream) {
+  return reduce_stats_impl(x, what, outer, channels, inner, absmax, mn, mx, abssum, nnz, tensor_min, workspace,
+                           workspace_bytes, nullptr, stream);
+}
+
+// The same in ONE launch whenever the partial array is small (channels x entries <= 16 Ki): the
+// last-arriving CTA of stage 1 combines the partials itself.  arrival_counter_dev as in
+// qsb_reduce_prune_quant_step (one zeroed uint32 per stream, left zero).
+extern "C" int qsb_reduce_stats_fused(const float *x, int what, int64_t outer, int64_t channels,
+                                      int64_t inner, float *absmax, float *mn, float *mx, double *abssum,
+                                      double *nnz, float *tensor_min, void *workspace,
+                                      int64_t workspace_bytes, unsigned int *arrival_counter_dev,
+                                      void *stream) {
+  if (!arrival_counter_dev) return QSB_E_BADARG;
+  return reduce_stats_impl(x, what, outer, channels, inner, absmax, mn, mx, abssum, nnz, tensor_min, workspace,
+                           workspace_bytes, arrival_counter_dev, stream);
 }
 
 // Stage 1 only: leaves the per-virtual-warp partials of sum|x| and max|x| in the

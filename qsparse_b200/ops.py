@@ -192,6 +192,9 @@ def mask_apply(x, mask, layout: Layout, out=None):
 
 
 # ----------------------------------------------------------------------------- K3
+FUSE_REDUCE_FINALIZE = True   # small partial arrays: the reduction's last-arriving CTA finalizes (one launch)
+
+
 def reduce_stats(x, layout: Layout, absmax=False, minmax=False, abssum=False, nnz=False, out=None):
     """One read of x -> dict of per-channel statistics (device tensors).  ``out`` may
     supply pre-allocated result tensors (e.g. views into a statistics row that is
@@ -216,6 +219,13 @@ def reduce_stats(x, layout: Layout, absmax=False, minmax=False, abssum=False, nn
         res["tensor_min"] = torch.empty(1, dtype=torch.float32, device=dev)
     nbytes = lib.qsb_reduce_workspace_bytes(c_int64(outer), c_int64(ch), c_int64(inner))
     ws = N.workspace(dev, nbytes)
+    if FUSE_REDUCE_FINALIZE:
+        N.check(lib.qsb_reduce_stats_fused(N.ptr(x), c_int(what), c_int64(outer), c_int64(ch), c_int64(inner),
+                                           N.ptr(res.get("absmax")), N.ptr(res.get("min")), N.ptr(res.get("max")),
+                                           N.ptr(res.get("abssum")), N.ptr(res.get("nnz")),
+                                           N.ptr(res.get("tensor_min")), N.ptr(ws), c_int64(ws.numel()),
+                                           N.ptr(arrival_counter(dev)), N.stream_ptr(dev)), "qsb_reduce_stats_fused")
+        return res
     N.check(lib.qsb_reduce_stats(N.ptr(x), c_int(what), c_int64(outer), c_int64(ch), c_int64(inner),
                                  N.ptr(res.get("absmax")), N.ptr(res.get("min")), N.ptr(res.get("max")),
                                  N.ptr(res.get("abssum")), N.ptr(res.get("nnz")), N.ptr(res.get("tensor_min")),

@@ -521,7 +521,10 @@ class AdaptiveQuantizer(DecimalQuantizer):
     def optimize(self, x, bits, weight=None, channel_index=-1, batched=False, **kwargs):
         N.require_cuda(x, "x")
         if batched and channel_index == 0:
-            raise NotImplementedError("AdaptiveQuantizer: channel_index=0 on a batched activation")
+            # the reference transposes axes 1 and 0 and then calls .view() on the non-contiguous result, which
+            # raises for every input (quantize.py:399-402): same error type and message here
+            raise RuntimeError("view size is not compatible with input tensor's size and stride (at least one "
+                               "dimension spans across two contiguous subspaces). Use .reshape(...) instead.")
         with torch.no_grad():
             xs = N.as_f32_contiguous(x.detach())
             # per-(sample, channel) min/max followed by min-of-mins / max-of-maxes over the

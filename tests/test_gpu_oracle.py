@@ -1302,3 +1302,34 @@ def test_prune_step_with_pivot_hints_equals_unhinted():
             assert tb[i].item() == ref.item(), (t, i)
         used += int((hints[:, 0] == 2).sum().item())
     assert used > 0
+
+
+@pytest.mark.parametrize("lay", [(256, 64, 3136), (8, 16, 196), (4, 200, 81), (32, 48, 1), (64, 1000, 1), (3, 1, 5000),
+                                 (1, 4096, 4096), (2100, 8, 255), (1, 1, 1 << 22), (40, 3000, 7)])
+def test_reduce_stats_one_launch_equals_two_launch(lay):
+    """qsb_reduce_stats_fused (the last-arriving CTA of stage 1 finalizes) against the two-launch form: max / min /
+    nnz exact, sums to the last fp64 bits (another fixed order); large partial arrays fall back to two launches"""
+    from qsparse_b200 import ops
+    n = lay[0] * lay[1] * lay[2]
+    g = torch.Generator(device="cuda").manual_seed(n % 1000)
+    x = torch.randn(n, device="cuda", generator=g).view(lay)
+    x.view(-1)[::97] = 0.0
+    res = {}
+    for fused in (True, False):
+        ops.FUSE_REDUCE_FINALIZE = fused
+        try:
+            res[fused] = [ops.reduce_stats(x, lay, absmax=True, minmax=True, abssum=True, nnz=True),
+                          ops.reduce_stats(x, lay, minmax=True), ops.reduce_stats(x, lay, absmax=True),
+                          ops.reduce_stats(x, lay, abssum=True, absmax=True)]
+            assert int(ops.arrival_counter(x.device)[0].item()) == 0
+        finally:
+            ops.FUSE_REDUCE_FINALIZE = True
+    for a, b in zip(res[True], res[False]):
+        assert a.keys() == b.keys()
+        for key in a:
+            if key == "abssum":
+                assert torch.allclose(a[key], b[key], rtol=1e-13, atol=0), key
+            else:
+                assert torch.equal(a[key], b[key]), key
+    ref = x.abs().amax(dim=(0, 2))
+    assert torch.equal(res[True][2]["absmax"], ref)

@@ -344,3 +344,11 @@ def test_convert_scenarios():
     assert tail.index("linear") > tail.index("quantize")
     nested = str(q.convert(pre, q.prune(sparsity=0.5), activation_layers=[nn.Conv2d, nn.Linear], log=False)).lower()
     assert nested.index("quantize") < nested.index("prune")
+
+
+def test_adaptive_batched_channel0_raises_like_the_reference():
+    """AdaptiveQuantizer.optimize(batched=True, channel_index=0): the reference's transpose(1, 0).view(...) raises a
+    RuntimeError for every input (quantize.py:399-402); so does this implementation."""
+    import qsparse_b200 as q
+    with pytest.raises(RuntimeError, match="view size is not compatible"):
+        q.AdaptiveQuantizer().optimize(rand(4, 3, 5, 5, seed=1), 8, None, channel_index=0, batched=True)
