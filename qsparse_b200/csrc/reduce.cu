@@ -220,90 +220,163 @@ __device__ __forceinline__ StepPrefetch fused_step_begin(const Tail &tail) {
 
 // ---------------------------------------------------------------------------
 // The same idea for the stand-alone reductions (qsb_reduce_stats): when the partial array is small
-// (channels x entries <= kFinalTailMaxEntries) the last-arriving CTA of stage 1 combines the partials
-// itself — a warp per channel, fixed order — instead of a second launch that is pure latency
+// (final_tail_ok) the last-arriving CTA of stage 1 combines the partials itself, in a fixed order,
+// instead of a second launch that is pure latency
 // (3.5-5 us behind a 12-35 us stage 1).
 // ---------------------------------------------------------------------------
 struct FinalOut {
   float *absmax, *mn, *mx;
   double *abssum, *nnz;
 };
-constexpr int64_t kFinalTailMaxEntries = 16384;
 struct FinalTail {
   static constexpr bool kFused = true;
   FinalOut out;
   unsigned int *arrival;
   int64_t channels, count, q;
+  int group;  // threads per channel in the tail
 };
 
+// One CTA finalizes every channel: `group` threads per channel (a power of two; the whole CTA for one channel),
+// all channels of a pass and all loads of a thread in flight at once — the tail is a handful of L2 round trips,
+// not one per channel.  The host only fuses shapes for which that holds (final_tail_ok).
+constexpr int kFinalBatch = 12;
 template <int WHAT>
 __device__ __forceinline__ void finalize_in_cta(const Partials &P, const FinalTail &t) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int64_t c = warp; c < t.channels; c += nwarps) {
-    uint32_t amax = 0;
-    float mn = INFINITY, mx = -INFINITY;
-    bool nan = false;
-    double asum = 0.0, nnz = 0.0;
-    for (int64_t j0 = lane; j0 < t.count; j0 += 4 * 32) {
-      int64_t idx[4];
-      bool ok[4];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const float qnan = __uint_as_float(0x7fc00000u);
+  if (t.count == 1) {
+    // one partial per channel (e.g. 4096 weight rows): a strided copy, 8 independent loads per thread
+    for (int64_t c0 = tid; c0 < t.channels; c0 += 8 * (int64_t)nthr) {
+      uint32_t a_[8];
+      float n_[8], x_[8];
+      double s_[8], z_[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t j = j0 + 32 * u;
-        ok[u] = j < t.count;
-        const int64_t hi = ok[u] ? (int64_t)((uint32_t)j / (uint32_t)t.q) : 0;  // entries <= 16 Ki: 32-bit
-        idx[u] = ok[u] ? hi * (t.channels * t.q) + c * t.q + (j - hi * t.q) : 0;
-      }
-      if constexpr (WHAT & QSB_STAT_ABSMAX) {
-        uint32_t b[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) b[u] = ok[u] ? __ldcg(P.amax + idx[u]) : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) amax = b[u] > amax ? b[u] : amax;
-      }
-      if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? __ldcg(P.mn + idx[u]) : INFINITY;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          nan |= (v[u] != v[u]);
-          mn = fminf(mn, v[u]);
+      for (int u = 0; u < 8; ++u) {
+        const int64_t c = c0 + (int64_t)u * nthr;
+        if (c < t.channels) {
+          if constexpr (WHAT & QSB_STAT_ABSMAX) a_[u] = __ldcg(P.amax + c);
+          if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) n_[u] = __ldcg(P.mn + c);
+          if constexpr (WHAT & QSB_STAT_MINMAX) x_[u] = __ldcg(P.mx + c);
+          if constexpr (WHAT & QSB_STAT_ABSSUM) s_[u] = __ldcg(P.asum + c);
+          if constexpr (WHAT & QSB_STAT_NNZ) z_[u] = __ldcg(P.nnz + c);
         }
       }
-      if constexpr (WHAT & QSB_STAT_MINMAX) {
-        float v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? __ldcg(P.mx + idx[u]) : -INFINITY;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          nan |= (v[u] != v[u]);
-          mx = fmaxf(mx, v[u]);
+      for (int u = 0; u < 8; ++u) {
+        const int64_t c = c0 + (int64_t)u * nthr;
+        if (c < t.channels) {
+          if constexpr (WHAT & QSB_STAT_ABSMAX)
+            if (t.out.absmax) t.out.absmax[c] = __uint_as_float(a_[u]);
+          if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+            bool nan = n_[u] != n_[u];
+            if constexpr (WHAT & QSB_STAT_MINMAX) nan = nan || (x_[u] != x_[u]);
+            if (t.out.mn) t.out.mn[c] = nan ? qnan : n_[u];
+            if constexpr (WHAT & QSB_STAT_MINMAX)
+              if (t.out.mx) t.out.mx[c] = nan ? qnan : x_[u];
+          }
+          if constexpr (WHAT & QSB_STAT_ABSSUM)
+            if (t.out.abssum) t.out.abssum[c] = s_[u];
+          if constexpr (WHAT & QSB_STAT_NNZ)
+            if (t.out.nnz) t.out.nnz[c] = z_[u];
         }
-      }
-      if constexpr (WHAT & QSB_STAT_ABSSUM) {
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? __ldcg(P.asum + idx[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) asum += v[u];
-      }
-      if constexpr (WHAT & QSB_STAT_NNZ) {
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ok[u] ? __ldcg(P.nnz + idx[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) nnz += v[u];
       }
     }
-    amax = warp_reduce(amax, [](uint32_t a, uint32_t b) { return a > b ? a : b; });
-    mn = warp_reduce(mn, [](float a, float b) { return fminf(a, b); });
-    mx = warp_reduce(mx, [](float a, float b) { return fmaxf(a, b); });
-    nan = __any_sync(0xffffffffu, nan);
-    asum = warp_reduce(asum, [](double a, double b) { return a + b; });
-    nnz = warp_reduce(nnz, [](double a, double b) { return a + b; });
-    if (lane == 0) {
-      const float qnan = __uint_as_float(0x7fc00000u);
+    return;
+  }
+  const int group = t.group;
+  const int gl = tid % group, gc = tid / group, cpp = nthr / group;
+  __shared__ uint32_t s_amax[32];
+  __shared__ float s_mn[32], s_mx[32];
+  __shared__ int s_nan[32];
+  __shared__ double s_asum[32], s_nnz[32];
+  for (int64_t base = 0; base < t.channels; base += cpp) {
+    const int64_t c = base + gc;
+    const bool act = c < t.channels;
+    uint32_t amax = 0;
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    double asum = 0.0, nnz = 0.0;
+    if (act) {
+      for (int64_t j0 = gl; j0 < t.count; j0 += (int64_t)kFinalBatch * group) {
+        int64_t idx[kFinalBatch];
+        bool ok[kFinalBatch];
+#pragma unroll
+        for (int u = 0; u < kFinalBatch; ++u) {
+          const int64_t j = j0 + (int64_t)u * group;
+          ok[u] = j < t.count;
+          const int64_t hi = ok[u] ? (int64_t)((uint32_t)j / (uint32_t)t.q) : 0;
+          idx[u] = ok[u] ? hi * (t.channels * t.q) + c * t.q + (j - hi * t.q) : 0;
+        }
+        if constexpr (WHAT & QSB_STAT_ABSMAX) {
+          uint32_t b[kFinalBatch];
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) b[u] = ok[u] ? __ldcg(P.amax + idx[u]) : 0u;
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) amax = b[u] > amax ? b[u] : amax;
+        }
+        if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ)) {
+          float v[kFinalBatch];
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) v[u] = ok[u] ? __ldcg(P.mn + idx[u]) : INFINITY;
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) {
+            nan |= (v[u] != v[u]);
+            mn = fminf(mn, v[u]);
+          }
+        }
+        if constexpr (WHAT & QSB_STAT_MINMAX) {
+          float v[kFinalBatch];
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) v[u] = ok[u] ? __ldcg(P.mx + idx[u]) : -INFINITY;
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) {
+            nan |= (v[u] != v[u]);
+            mx = fmaxf(mx, v[u]);
+          }
+        }
+        if constexpr (WHAT & QSB_STAT_ABSSUM) {
+          double v[kFinalBatch];
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) v[u] = ok[u] ? __ldcg(P.asum + idx[u]) : 0.0;
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) asum += v[u];
+        }
+        if constexpr (WHAT & QSB_STAT_NNZ) {
+          double v[kFinalBatch];
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) v[u] = ok[u] ? __ldcg(P.nnz + idx[u]) : 0.0;
+#pragma unroll
+          for (int u = 0; u < kFinalBatch; ++u) nnz += v[u];
+        }
+      }
+    }
+    for (int o = (group < 32 ? group : 32) >> 1; o > 0; o >>= 1) {
+      const uint32_t a2 = __shfl_xor_sync(0xffffffffu, amax, o);
+      amax = a2 > amax ? a2 : amax;
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+      asum += __shfl_xor_sync(0xffffffffu, asum, o);
+      nnz += __shfl_xor_sync(0xffffffffu, nnz, o);
+    }
+    if (group > 32) {  // one channel, the whole CTA: combine the warps in warp order
+      if (lane == 0) {
+        s_amax[warp] = amax, s_mn[warp] = mn, s_mx[warp] = mx, s_nan[warp] = nan;
+        s_asum[warp] = asum, s_nnz[warp] = nnz;
+      }
+      __syncthreads();
+      if (gl == 0)
+        for (int w = 1; w < group / 32; ++w) {
+          amax = s_amax[warp + w] > amax ? s_amax[warp + w] : amax;
+          mn = fminf(mn, s_mn[warp + w]);
+          mx = fmaxf(mx, s_mx[warp + w]);
+          nan |= s_nan[warp + w];
+          asum += s_asum[warp + w];
+          nnz += s_nnz[warp + w];
+        }
+      __syncthreads();
+    }
+    if (act && gl == 0) {
       if constexpr (WHAT & QSB_STAT_ABSMAX)
         if (t.out.absmax) t.out.absmax[c] = __uint_as_float(amax);
       if constexpr (WHAT & (QSB_STAT_MINMAX | QSB_STAT_NNZ))
@@ -316,6 +389,15 @@ __device__ __forceinline__ void finalize_in_cta(const Partials &P, const FinalTa
         if (t.out.nnz) t.out.nnz[c] = nnz;
     }
   }
+}
+
+// which shapes the tail takes: a pure copy (one partial per channel), or ONE pass over the channels with
+// ONE batch of loads per thread
+inline bool final_tail_ok(int64_t channels, int64_t fin_count, int64_t fin_q) {
+  if (fin_count >= 0x7fffffffLL || fin_q >= 0x7fffffffLL) return false;
+  if (fin_count == 1) return channels <= 16384;
+  if (channels > QSB_THREADS) return false;
+  return fin_count <= (int64_t)kFinalBatch * step_group_for(channels, QSB_THREADS);
 }
 
 // last-arriver election shared by the two tails
@@ -1211,9 +1293,8 @@ static int reduce_stats_impl(const float *x, int what, int64_t outer, int64_t ch
   FinalOut out{absmax, mn, mx, abssum, nnz};
   int rc;
   // small partial arrays: the last-arriving CTA of stage 1 finalizes (one launch instead of two)
-  const bool fuse_final = arrival != nullptr && channels * pl.fin_count <= kFinalTailMaxEntries &&
-                          pl.fin_count < 0x7fffffffLL && pl.fin_q < 0x7fffffffLL;
-  const FinalTail ft{out, arrival, channels, pl.fin_count, pl.fin_q};
+  const bool fuse_final = arrival != nullptr && final_tail_ok(channels, pl.fin_count, pl.fin_q);
+  const FinalTail ft{out, arrival, channels, pl.fin_count, pl.fin_q, step_group_for(channels, QSB_THREADS)};
   switch (what) {
 #define QSB_CASE(W)                                                                                       \
   case W:                                                                                                 \
