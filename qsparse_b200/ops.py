@@ -192,7 +192,12 @@ def mask_apply(x, mask, layout: Layout, out=None):
 
 
 # ----------------------------------------------------------------------------- K3
-FUSE_REDUCE_FINALIZE = True   # small partial arrays: the reduction's last-arriving CTA finalizes (one launch)
+# True: small partial arrays are finalized by the reduction's last-arriving CTA (qsb_reduce_stats_fused, one launch).
+# Measured on B200 and NOT the default: the serial tail (fence, atomic, one L2 round trip, the writes; ~4-5 us) costs
+# more than a second launch whose latency programmatic dependent launch already hides — per-channel sum|x| + max|x|
+# of the bench tensor 37.9 us (two launches) vs 40.9 us (one), per-tensor abs-max 38.9 vs 38.9.  The training step's
+# fused kernel is a different trade: its tail replaces a whole dependent parameter kernel, not a 3.5 us finalize.
+FUSE_REDUCE_FINALIZE = False
 
 
 def reduce_stats(x, layout: Layout, absmax=False, minmax=False, abssum=False, nnz=False, out=None):

@@ -1323,7 +1323,7 @@ def test_reduce_stats_one_launch_equals_two_launch(lay):
                           ops.reduce_stats(x, lay, abssum=True, absmax=True)]
             assert int(ops.arrival_counter(x.device)[0].item()) == 0
         finally:
-            ops.FUSE_REDUCE_FINALIZE = True
+            ops.FUSE_REDUCE_FINALIZE = False
     for a, b in zip(res[True], res[False]):
         assert a.keys() == b.keys()
         for key in a:
