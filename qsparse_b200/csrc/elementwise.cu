@@ -691,6 +691,10 @@ extern "C" int qsb_set_tuning(int key, int value) {
     set_reduce_keep_hint(value);
     return 0;
   }
+  if (key == 20) {
+    set_reduce_col_max_inner(value);
+    return 0;
+  }
   if (key == 13) {
     set_step_sample_per(value);
     return 0;

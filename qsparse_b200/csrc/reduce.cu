@@ -53,6 +53,10 @@ static inline int row_variant_for(int64_t inner) {
   return inner >= 2048 ? 2 : 0;
 }
 static inline int row_ctas_per_sm(int variant) { return variant == 0 ? 4 : 2; }
+// tuning key 20: rows up to this many elements use the COLUMN kernel (the tensor seen as [outer, C * inner]:
+// vertical accumulation, perfectly coalesced, ~4 instructions per element) instead of the tile / row kernels
+static int g_col_max_inner = 63;
+void set_reduce_col_max_inner(int v) { g_col_max_inner = v < 1 ? 63 : v; }
 // tuning key 18: the fused step reads the previous mask's kept channels with L2::evict_last
 static int g_keep_hint = 1;
 void set_reduce_keep_hint(int v) { g_keep_hint = v != 0; }
@@ -1073,7 +1077,7 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
   p.row_variant = row_variant_for(inner);
   const int64_t warps_phys =
       (int64_t)device_props().sm_count * row_ctas_per_sm(p.row_variant) * (QSB_THREADS / 32);
-  if (inner >= kTileMinInner && inner <= kTileMaxInner) {
+  if (inner > g_col_max_inner && inner >= kTileMinInner && inner <= kTileMaxInner) {
     // short rows: the tile kernel.  One slot (virtual warp) per row of a tile, 3 CTAs of 32 slots
     // per SM; slots = m * channels so that a slot only ever sees one channel.
     p.row_mode = true;
@@ -1098,7 +1102,7 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
     }
     p.fin_q = 1;
     p.n_partials = p.vwarps;
-  } else if (inner >= kRowModeMinInner) {
+  } else if (inner > g_col_max_inner && inner >= kRowModeMinInner) {
     p.row_mode = true;
     p.rows = outer * channels;
     // balanced segments: aim for >= 6 work items per physical warp, but keep every

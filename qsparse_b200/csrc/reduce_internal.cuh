@@ -33,6 +33,7 @@ void set_reduce_seg_min(int v);
 void set_reduce_col_tpr_wide(int v);
 void set_reduce_row_variant(int v);
 void set_reduce_keep_hint(int v);
+void set_reduce_col_max_inner(int v);
 ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner, const float *x);
 int64_t partial_bytes(int64_t n);
 // carve the five partial arrays out of a caller workspace (256-byte aligned)
