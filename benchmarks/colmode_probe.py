@@ -45,7 +45,7 @@ for lay in ((256, 256, 196), (1024, 256, 64), (256, 128, 784), (512, 512, 100), 
             ref = r
         else:
             assert torch.equal(r["absmax"], ref["absmax"]) and torch.equal(r["min"], ref["min"])
-            assert torch.allclose(r["abssum"], ref["abssum"], rtol=1e-12)
+            assert torch.allclose(r["abssum"], ref["abssum"], rtol=1e-6)
         row[f"colmax{colmax}"] = [round(t1, 1), round(t2, 1), round(4 * n / t1 / 1e3 / 6457.4, 2)]
     ops.set_tuning(20, 63)
     print(json.dumps(row), flush=True)
