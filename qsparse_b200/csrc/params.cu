@@ -355,6 +355,15 @@ extern "C" int qsb_prune_quant_params(float *magnitude, uint8_t *mask,
 
 // shared argument checks + StepArgs assembly of the three parameter-step entry points
 namespace qsb {
+int launch_step_kernel_on_rows(StepArgs a, const double *row_sum, const float *row_max, cudaStream_t stream) {
+  a.row_sum = row_sum;
+  a.row_max = row_max;
+  a.n_rows = 1;
+  a.row_stride = 0;
+  QSB_CUDA_TRY(launch_k(prune_quant_step_kernel, dim3(1), dim3(kStepKernelThreads), 0, stream, a));
+  return 0;
+}
+
 int fill_step_args(qsb::StepArgs &a, float *magnitude, uint8_t *mask, float *scale, float *decimal_out,
                    int64_t channels, qsb_p2p_group *group, int64_t step_stamp, double count, int64_t t_prune,
                    int update_magnitude, int refresh_mask, int64_t k, int bits, int64_t t_quant,

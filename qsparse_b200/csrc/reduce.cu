@@ -55,8 +55,12 @@ static inline int row_variant_for(int64_t inner) {
 static inline int row_ctas_per_sm(int variant) { return variant == 0 ? 4 : 2; }
 // tuning key 20: rows up to this many elements use the COLUMN kernel (the tensor seen as [outer, C * inner]:
 // vertical accumulation, perfectly coalesced, ~4 instructions per element) instead of the tile / row kernels
-static int g_col_max_inner = 63;
-void set_reduce_col_max_inner(int v) { g_col_max_inner = v < 1 ? 63 : v; }
+// Measured (profiles/r02_colmode_probe_r2t.jsonl, sum|x| + max|x|, us): [256,256,14,14] 23.6 (tile kernel) -> 17.4,
+// [512,512,10,10] 35.8 -> 25.6, [256,512,16,16] 46.1 -> 29.7, [4096,64,14,14] 60.4 -> 39.9 (0.53 -> 0.80 of the copy
+// peak), [256,2048,8,8] 42.0 -> 27.6; rows of 784 elements and more are better off in the row kernel (23.6 vs 27.6).
+// Default: rows of up to 256 elements (what used to be the tile kernel's range); 63 restores the tile kernel.
+static int g_col_max_inner = 256;
+void set_reduce_col_max_inner(int v) { g_col_max_inner = v < 1 ? 256 : v; }
 // tuning key 18: the fused step reads the previous mask's kept channels with L2::evict_last
 static int g_keep_hint = 1;
 void set_reduce_keep_hint(int v) { g_keep_hint = v != 0; }
@@ -1194,6 +1198,11 @@ ReducePlan make_plan(int64_t outer, int64_t channels, int64_t inner,
   return p;
 }
 
+// a finalized statistics row in a workspace: fp64 sums and fp32 maxima, each 256-byte aligned
+static inline int64_t stat_row_bytes(int64_t channels) {
+  return (channels * 8 + 255) / 256 * 256 + (channels * 4 + 255) / 256 * 256;
+}
+
 int64_t partial_bytes(int64_t n) {
   // amax(4) + mn(4) + mx(4) + pad(4) + asum(8) + nnz(8), each array 256-aligned
   auto up = [](int64_t b) { return (b + 255) / 256 * 256; };
@@ -1276,7 +1285,8 @@ extern "C" int64_t qsb_reduce_workspace_bytes(int64_t outer, int64_t channels,
   if (outer <= 0 || channels <= 0 || inner <= 0) return 256;
   const ReducePlan pl = make_plan(outer, channels, inner, nullptr);
   // column mode falls back to scalar columns for an unaligned x: same row bands, same size.
-  return partial_bytes(pl.n_partials) + 256;
+  // + one finalized statistics row (fp64 sums | fp32 maxima) for the multi-launch form of the training step
+  return partial_bytes(pl.n_partials) + 256 + stat_row_bytes(channels);
 }
 
 static int reduce_stats_impl(const float *x, int what, int64_t outer, int64_t channels, int64_t inner,
@@ -1369,6 +1379,10 @@ extern "C" int qsb_reduce_partials(const float *x, int64_t outer, int64_t channe
                                                       stream, /*finalize=*/false);
 }
 
+// the last-arriving CTA finalizes channels x fin_count partials; beyond this many a second, parallel
+// finalize launch is cheaper than the serial tail (12 loads per thread and batch, 256 threads, <= 4 batches)
+constexpr int64_t kStepTailMaxEntries = 12288;
+
 // ONE launch for everything between "x is in HBM" and "apply" of the fused structured
 // prune -> pow2 quantize training step: the stage-1 reduction of sum|x| / max|x| whose
 // last-arriving CTA finalizes, exchanges the statistics row with the peer GPUs and derives
@@ -1394,6 +1408,20 @@ extern "C" int qsb_reduce_prune_quant_step(
   if (workspace_bytes < partial_bytes(pl.n_partials) + 256) return QSB_E_WORKSPACE;
   if (pl.fin_count > 0x7fffffffLL || pl.fin_q > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
   const Partials P = partials_from_workspace(workspace, pl.n_partials);
+  if (channels * pl.fin_count > kStepTailMaxEntries) {
+    // many partials per channel (column mode on wide tensors): stage 1, a parallel finalize into a statistics row
+    // in the workspace, then the parameter step as a one-CTA launch on that row — three launches
+    if (workspace_bytes < partial_bytes(pl.n_partials) + 256 + stat_row_bytes(channels)) return QSB_E_WORKSPACE;
+    unsigned char *row = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256 + (uintptr_t)partial_bytes(pl.n_partials));
+    double *row_sum = reinterpret_cast<double *>(row);
+    float *row_max = reinterpret_cast<float *>(row + (channels * 8 + 255) / 256 * 256);
+    FinalOut out{row_max, nullptr, nullptr, row_sum, nullptr};
+    const int rc2 = run_reduce<QSB_STAT_ABSSUM | QSB_STAT_ABSMAX>(x, pl, channels, inner, P, out, stream);
+    if (rc2) return rc2;
+    tail.a.timing = nullptr;
+    return launch_step_kernel_on_rows(tail.a, row_sum, row_max, stream);
+  }
   tail.a.P = P;
   tail.a.fin_count = (int)pl.fin_count;
   tail.a.fin_q = (int)pl.fin_q;

@@ -432,6 +432,9 @@ int fill_step_args(StepArgs &a, float *magnitude, uint8_t *mask, float *scale, f
                    int update_scale, double *abssum_out, float *absmax_out, int stats_local,
                    int64_t *step_counter_dev, int threads);
 
+// the stand-alone one-CTA launch of the parameter step on ONE finalized statistics row (params.cu)
+int launch_step_kernel_on_rows(StepArgs a, const double *row_sum, const float *row_max, cudaStream_t stream);
+
 // threads per channel for a CTA of `threads` threads: the largest power of two
 // <= min(32, threads / channels); one channel: the whole CTA
 inline int step_group_for(int64_t channels, int threads) {

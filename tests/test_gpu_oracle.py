@@ -581,7 +581,10 @@ def test_one_launch_step_equals_two_launch_step(shape, C):
                     ops.reduce_prune_quant_step(x, layout, st["mag"], st["mask"], st["scale"], st["dec"], count, t, 1,
                                                 t > 0 and C > 1, k, 8, t, True, abssum_out=asum, absmax_out=amax)
                     assert int(ops.arrival_counter(x.device)[0].item()) == 0
-                    assert torch.equal(asum, ref_stats[t][0]) and torch.equal(amax, ref_stats[t][1]), (variant, t)
+                    # (wide column-mode shapes take the three-launch form, whose parallel finalize adds the same
+                    # partials in another fixed order: the fp64 sums then agree to the last bits, not bit for bit)
+                    assert torch.allclose(asum, ref_stats[t][0], rtol=1e-13, atol=0), (variant, t)
+                    assert torch.equal(amax, ref_stats[t][1]), (variant, t)
                     # local statistics row == the combined one on a single GPU
                     asum_l = torch.empty_like(asum)
                     amax_l = torch.empty_like(amax)
@@ -592,8 +595,11 @@ def test_one_launch_step_equals_two_launch_step(shape, C):
                     assert counter.item() == t + 1
                     assert torch.equal(asum_l, asum) and torch.equal(amax_l, amax)
                     for key in st:
-                        assert torch.equal(st[key], ref_stats[t][2][key]), (key, t, variant, hint)
-                        assert torch.equal(stg[key], ref_stats[t][2][key]), (key, t, variant, hint, "graph mode")
+                        if key == "mag":
+                            assert ulp_diff(npy(st[key]), npy(ref_stats[t][2][key])).max() <= 1, (key, t, variant, hint)
+                        else:
+                            assert torch.equal(st[key], ref_stats[t][2][key]), (key, t, variant, hint)
+                        assert torch.equal(stg[key], st[key]), (key, t, variant, hint, "graph mode")
     finally:
         ops.set_tuning(17, -1)
         ops.set_tuning(18, 1)
