@@ -51,6 +51,10 @@ int qsb_abi_version(void);
 const char *qsb_error_string(int code);
 /* SM count and L2 size of the current device. */
 int qsb_device_info(int *sm_count, int64_t *l2_bytes);
+/* Development only (library built with -DQSB_KERNEL_TIMING, else QSB_E_UNSUPPORTED): out_host == NULL resets,
+ * otherwise reads 3 x 2 x 256 uint64 %globaltimer stamps [statistics / forward / backward kernel][first CTA
+ * start, last CTA end][SM] — the in-situ durations of a graph-replayed step without event records. */
+int qsb_debug_kernel_times(unsigned long long *out_host, void *stream);
 /* Benchmark-only knobs; defaults are what the product uses.
  *   key 0: per-tensor streaming kernels: 0 = one CTA per tile (default),
  *          n > 0 = persistent grid of n CTAs per SM;

@@ -25,6 +25,7 @@ _P = c_void_p
 _SIGNATURES = {
     "qsb_abi_version": (c_int, []),
     "qsb_error_string": (ctypes.c_char_p, [c_int]),
+    "qsb_debug_kernel_times": (c_int, [_P, _P]),
     "qsb_device_info": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int64)]),
     "qsb_fq_pow2_fwd": (c_int, [_P, _P, _P, c_int64, c_double, _P, c_int, c_int64, c_int64, c_int64, _P]),
     "qsb_fq_scaler_fwd": (c_int, [_P, _P, _P, c_int64, c_float, _P, c_int, c_int64, c_int64, c_int64, _P]),

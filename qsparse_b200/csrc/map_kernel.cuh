@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(QSB_THREADS)
                         uint32_t channels, int reverse) {
   pdl_wait();
   pdl_trigger();
+  ktime_begin(Op::kOut1 ? 2 : 1);
   using P = typename Op::P;
   static_assert(MODE == 0 || MODE == 1, "window kernel needs inner >= V");
   extern __shared__ __align__(16) unsigned char qsb_smem_raw[];
@@ -569,6 +570,9 @@ __global__ void __launch_bounds__(QSB_THREADS)
       if constexpr (Op::kOutB) io.outb[e] = ob;
     }
   }
+#ifdef QSB_KERNEL_TIMING
+  ktime_end(Op::kOut1 ? 2 : 1);
+#endif
 }
 
 template <class Op, int V, int U, int MODE, Hint LH, Hint SH>

@@ -86,6 +86,39 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 // ---------------------------------------------------------------------------
+// development only (-DQSB_KERNEL_TIMING): first-CTA-start / last-CTA-end %globaltimer stamps of the streaming
+// kernels, per SM (one atomic per CTA and SM slot), so that the in-situ duration of every kernel of a
+// graph-replayed step — and the gaps between them — can be read without event records (which undo the
+// programmatic-dependent-launch overlap).  Slots: 0 = statistics kernel, 1 = forward map, 2 = backward map.
+// ---------------------------------------------------------------------------
+#ifdef QSB_KERNEL_TIMING
+extern __device__ unsigned long long g_ktime[3][2][256];
+__device__ __forceinline__ unsigned long long ktime_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void ktime_begin(int id) {
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    atomicMin(&g_ktime[id][0][smid & 255], ktime_now());
+  }
+}
+__device__ __forceinline__ void ktime_end(int id) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    atomicMax(&g_ktime[id][1][smid & 255], ktime_now());
+  }
+}
+#else
+__device__ __forceinline__ void ktime_begin(int) {}
+__device__ __forceinline__ void ktime_end(int) {}
+#endif
+
+// ---------------------------------------------------------------------------
 // vector global-memory access.  V floats per access: 8 -> one 256-bit
 // LDG/STG (new on sm_100), 4 -> 128-bit, 1 -> scalar.
 // Loads: L1::no_allocate (every element is touched once per kernel); not .nc,

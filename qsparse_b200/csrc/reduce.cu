@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(QSB_THREADS, MINB)
   pdl_trigger();
   extern __shared__ __align__(16) unsigned char qsb_dyn_smem[];
   const StepPrefetch pre = fused_step_begin(tail);
+  if constexpr (std::is_same<Tail, StepTail>::value) ktime_begin(0);
   const int lane = threadIdx.x & 31;
   const int64_t warps_phys = (int64_t)gridDim.x * (QSB_THREADS / 32);
   const int64_t items = rows * segs_per_row;
@@ -562,6 +563,9 @@ __global__ void __launch_bounds__(QSB_THREADS, MINB)
     }
   }
   if constexpr (Tail::kFused) fused_tail<WHAT>(tail, P, qsb_dyn_smem, pre);
+#ifdef QSB_KERNEL_TIMING
+  if constexpr (std::is_same<Tail, StepTail>::value) ktime_end(0);
+#endif
 }
 
 // ---------------------------------------------------------------------------
