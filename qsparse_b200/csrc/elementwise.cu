@@ -626,6 +626,37 @@ extern "C" int qsb_mask_apply(const float *x, float *y, const uint8_t *mask_dev,
       op, io, L, (cudaStream_t)stream);
 }
 
+#ifdef QSB_KERNEL_TIMING
+namespace qsb {
+int ktime_reduce_op(unsigned long long *out, cudaStream_t stream);
+}
+#endif
+// development only: reset (out == NULL) or read (3 x 2 x 256 uint64: [kernel][start / end][SM]) the kernel stamps
+// of a -DQSB_KERNEL_TIMING build; QSB_E_UNSUPPORTED in a normal build
+extern "C" int qsb_debug_kernel_times(unsigned long long *out_host, void *stream) {
+#ifdef QSB_KERNEL_TIMING
+  if (!out_host) {
+    int rc = qsb::ktime_reduce_op(nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+    return qsb::ktime_host_op(nullptr, (cudaStream_t)stream);
+  }
+  static unsigned long long a[3][2][256], b[3][2][256];
+  int rc = qsb::ktime_reduce_op(&a[0][0][0], nullptr);
+  if (rc) return rc;
+  if ((rc = qsb::ktime_host_op(&b[0][0][0], nullptr))) return rc;
+  for (int s = 0; s < 2 * 256; ++s) {
+    out_host[s] = (&a[0][0][0])[s];                          // slot 0: the statistics kernel (reduce.cu)
+    out_host[2 * 256 + s] = (&b[1][0][0])[s];                // slots 1, 2: the map kernels (this file)
+    out_host[4 * 256 + s] = (&b[2][0][0])[s];
+  }
+  return 0;
+#else
+  (void)out_host;
+  (void)stream;
+  return QSB_E_UNSUPPORTED;
+#endif
+}
+
 extern "C" int qsb_set_tuning(int key, int value) {
   if (key == 0) {
     map_tuning().ctas_per_sm = value;

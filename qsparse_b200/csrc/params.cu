@@ -16,12 +16,6 @@
 #include "reduce_internal.cuh"
 #include "step_epilogue.cuh"
 
-#ifdef QSB_KERNEL_TIMING
-namespace qsb {
-__device__ unsigned long long g_ktime[3][2][256];
-}
-#endif
-
 namespace qsb {
 
 static int g_pdl_enabled = 1;  // tuning key 12 (default on: eager step 168.6 -> 165.1 us, = the CUDA-graph time)
@@ -253,27 +247,6 @@ extern "C" const char *qsb_error_string(int code) {
       if (code > 0) return cudaGetErrorString((cudaError_t)code);
       return "qsparse_b200: unknown error";
   }
-}
-
-// development only: reset (out == NULL) or read (3 x 2 x 256 uint64: [kernel][start / end][SM]) the kernel stamps
-// of a -DQSB_KERNEL_TIMING build; QSB_E_UNSUPPORTED in a normal build
-extern "C" int qsb_debug_kernel_times(unsigned long long *out_host, void *stream) {
-#ifdef QSB_KERNEL_TIMING
-  static unsigned long long init[3][2][256];
-  if (!out_host) {
-    for (int k = 0; k < 3; ++k)
-      for (int s = 0; s < 256; ++s) init[k][0][s] = ~0ull, init[k][1][s] = 0ull;
-    QSB_CUDA_TRY(cudaMemcpyToSymbolAsync(qsb::g_ktime, init, sizeof(init), 0, cudaMemcpyHostToDevice,
-                                         (cudaStream_t)stream));
-    return 0;
-  }
-  QSB_CUDA_TRY(cudaMemcpyFromSymbol(out_host, qsb::g_ktime, sizeof(init)));
-  return 0;
-#else
-  (void)out_host;
-  (void)stream;
-  return QSB_E_UNSUPPORTED;
-#endif
 }
 
 extern "C" int qsb_device_info(int *sm_count, int64_t *l2_bytes) {

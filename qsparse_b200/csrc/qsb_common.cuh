@@ -92,7 +92,18 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 // programmatic-dependent-launch overlap).  Slots: 0 = statistics kernel, 1 = forward map, 2 = backward map.
 // ---------------------------------------------------------------------------
 #ifdef QSB_KERNEL_TIMING
-extern __device__ unsigned long long g_ktime[3][2][256];
+// (no relocatable device code: every translation unit has its own copy; qsb_debug_kernel_times collects them)
+static __device__ unsigned long long g_ktime[3][2][256];
+// reset (out == nullptr) or read this translation unit's copy
+static inline int ktime_host_op(unsigned long long *out, cudaStream_t stream) {
+  static unsigned long long init[3][2][256];
+  if (!out) {
+    for (int k = 0; k < 3; ++k)
+      for (int s = 0; s < 256; ++s) init[k][0][s] = ~0ull, init[k][1][s] = 0ull;
+    return (int)cudaMemcpyToSymbolAsync(g_ktime, init, sizeof(init), 0, cudaMemcpyHostToDevice, stream);
+  }
+  return (int)cudaMemcpyFromSymbol(out, g_ktime, sizeof(init));
+}
 __device__ __forceinline__ unsigned long long ktime_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
