@@ -24,6 +24,10 @@ st = dict(mag=torch.zeros(C, device=dev), mask=torch.ones(C, dtype=torch.bool, d
 counter = torch.zeros(1, dtype=torch.int64, device=dev)
 arrival = torch.zeros(64, dtype=torch.int32, device=dev)
 k = 48
+if len(sys.argv) > 1:
+    ops.set_tuning(21, int(sys.argv[1]))
+if len(sys.argv) > 2:
+    ops.set_tuning(18, int(sys.argv[2]))
 
 
 def step():
@@ -77,6 +81,7 @@ for rep in range(30):
 a = np.array(rows[5:]) / 1e3
 s0, s1, s2, e0, e1, e2 = [a[:, i] for i in range(6)]
 print(json.dumps({
+    "args": sys.argv[1:],
     "what": "one graph replay of the bench step right after three others; us, mean of 25",
     "statistics_kernel": round(float((e0 - s0).mean()), 2), "gap_to_forward": round(float((s1 - e0).mean()), 2),
     "forward_kernel": round(float((e1 - s1).mean()), 2), "gap_to_backward": round(float((s2 - e1).mean()), 2),

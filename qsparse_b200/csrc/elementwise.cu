@@ -726,6 +726,18 @@ extern "C" int qsb_set_tuning(int key, int value) {
     set_reduce_col_max_inner(value);
     return 0;
   }
+  if (key == 21) {
+    // L2 set-aside for persisting accesses, in MB (device-wide, like cudaDeviceSetLimit): the keep hint of the
+    // fused training step reads the kept channels with L2::evict_last, which only has capacity of its own when a
+    // set-aside exists.  0 removes the set-aside; the value is clamped to the device maximum.
+    int dev = 0, max_bytes = 0;
+    QSB_CUDA_TRY(cudaGetDevice(&dev));
+    QSB_CUDA_TRY(cudaDeviceGetAttribute(&max_bytes, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    size_t want = (size_t)(value < 0 ? 0 : value) << 20;
+    if (want > (size_t)max_bytes) want = (size_t)max_bytes;
+    QSB_CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    return 0;
+  }
   if (key == 13) {
     set_step_sample_per(value);
     return 0;
