@@ -240,6 +240,8 @@ def run_ours(args):
         ops.set_tuning(17, args.row_variant)
     if args.keep_hint is not None:
         ops.set_tuning(18, args.keep_hint)
+    if args.reverse_tiles is not None:
+        ops.set_tuning(2, args.reverse_tiles)
     if args.l2_persist_mb is not None:
         ops.set_tuning(21, args.l2_persist_mb)
 
@@ -803,6 +805,7 @@ def main():
                     help="graph: the forward half of the step is one captured CUDA graph (default)")
     ap.add_argument("--row-variant", type=int, default=None, choices=[0, 2], help="development: tuning key 17")
     ap.add_argument("--keep-hint", type=int, default=None, choices=[0, 1], help="development: tuning key 18")
+    ap.add_argument("--reverse-tiles", type=int, default=None, choices=[0, 1, 2], help="development: tuning key 2")
     ap.add_argument("--l2-persist-mb", type=int, default=None, help="development: tuning key 21 (L2 set-aside, MB)")
     ap.add_argument("--c1-decimal", action="store_true", help="config 1: DecimalQuantizer instead of the default ScalerQuantizer")
     ap.add_argument("--strong", action="store_true", help="config 5: strong scaling (total size fixed as N grows)")

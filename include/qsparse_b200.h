@@ -60,9 +60,11 @@ int qsb_debug_kernel_times(unsigned long long *out_host, void *stream);
  *          n > 0 = persistent grid of n CTAs per SM;
  *   key 1: per-channel streaming kernels: 0 = occupancy-derived persistent
  *          grid (default), n > 0 = n CTAs per SM;
- *   key 2: tile order of the one-CTA-per-tile kernels: 1 = last tile first
- *          (default; re-reads the L2-resident tail of a just-touched tensor),
- *          0 = first tile first;
+ *   key 2: tile order of the one-CTA-per-tile kernels: 1 (default) = last tile first
+ *          (re-reads the L2-resident tail of a just-touched tensor) except in the
+ *          channel-masked kernels, which follow the fused statistics kernel and its
+ *          L2 keep tags and measured faster first tile first; 2 = always last tile
+ *          first; 0 = always first tile first;
  *   key 3: minimum segment length (elements) of the row reductions (default 1024);
  *   key 4: 1 = sampled-pivot ~1-pass route of qsb_kth_value for n >= 2^22
  *          (default), 0 = always the 3-pass radix select;
@@ -90,7 +92,12 @@ int qsb_debug_kernel_times(unsigned long long *out_host, void *stream);
  *          >= 2048 elements, else 0); the reduction plan — and with it the summation order — follows;
  *   key 18: 1 = qsb_reduce_prune_quant_step reads the channels the previous mask keeps with
  *          L2::evict_last (the forward pass re-reads exactly those next) and the rest with
- *          L2::evict_first (default), 0 = default policy for everything. */
+ *          L2::evict_first (default), 0 = default policy for everything;
+ *   key 20: statistics of rows up to this many elements use the column kernel on the
+ *          [outer, channels * inner] view instead of the tile kernel (default 256; 0 = never);
+ *   key 21: L2 set-aside for persisting accesses in MB (cudaLimitPersistingL2CacheSize, device-wide;
+ *          untouched by default).  A development probe only: every set-aside >= 32 MB HALVED the
+ *          speed of the streaming kernels on B200 (profiles/r02_l2_set_aside.jsonl). */
 int qsb_set_tuning(int key, int value);
 /* Test hook: compares the kernels' reciprocal-based exact division with
  * __fdiv_rn on n_threads * pairs_per_thread pseudo-random operand pairs and

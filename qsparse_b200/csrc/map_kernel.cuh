@@ -110,6 +110,17 @@ struct MapTuning {
 };
 MapTuning &map_tuning();
 
+// reverse_tiles: 0 never, 1 (default) every map kernel EXCEPT the channel-masked ones, 2 always.  The masked
+// forward / backward follow the fused statistics kernel, which has already tagged the kept channels
+// L2::evict_last: there the natural order measured 3 us faster on the bench step (20.7 vs 25.5 MB of DRAM reads
+// in the forward, profiles/r02_tile_order.json), while the untagged pair {statistics -> quantize} gains 4 us
+// from walking backwards at every size above ~90 MB.
+template <class Op>
+inline int reverse_for() {
+  const int v = map_tuning().reverse_tiles;
+  return (v == 2 || (v == 1 && !Op::kCanSkip)) ? 1 : 0;
+}
+
 // ---------------------------------------------------------------------------
 // per-tensor
 // ---------------------------------------------------------------------------
@@ -180,7 +191,7 @@ int launch_map_tensor(const Op &op, const MapIO &io, int64_t n,
     if (grid > tiles) grid = tiles;
   }
   if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;  // the kernel loops
-  const int reverse = (grid == tiles && map_tuning().reverse_tiles) ? 1 : 0;
+  const int reverse = (grid == tiles && reverse_for<Op>()) ? 1 : 0;
   QSB_CUDA_TRY(launch_k(kern, dim3((unsigned)grid), dim3(QSB_THREADS), 0, stream, op, io, n, reverse));
   return 0;
 }
@@ -586,7 +597,7 @@ int launch_map_chan_win(const Op &op, const MapIO &io, int64_t n,
   const size_t smem = rows_max * sizeof(P);
   if (tiles > 0x7fffffffLL) return QSB_E_UNSUPPORTED;
   QSB_CUDA_TRY(launch_k(kern, dim3((unsigned)tiles), dim3(QSB_THREADS), smem, stream, op, io, n,
-                        (uint32_t)L.inner, (uint32_t)L.channels, map_tuning().reverse_tiles ? 1 : 0));
+                        (uint32_t)L.inner, (uint32_t)L.channels, reverse_for<Op>()));
   return 0;
 }
 
