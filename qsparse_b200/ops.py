@@ -84,6 +84,33 @@ def mask_layout(x_shape: Sequence[int], mask_shape: Sequence[int]) -> Tuple[str,
     return "channel", (outer, ch, inner)
 
 
+def mask_perm(x_shape: Sequence[int], mask_shape: Sequence[int]):
+    """None when ``mask_layout`` can address the mask directly; otherwise the axis permutation that moves the
+    broadcast axes sandwiched between kept ones (``dimensions={1, 3}`` on NCHW -> mask [1,C,1,W]) in front of the
+    first kept axis, so that the kept axes form one run ([N,H,C,W] with mask [1,1,C,W]).  The reference takes any
+    dimension set through broadcasting (ref qsparse/sparse.py:66, util.py:93-101); here such a mask costs one
+    transposing copy each way around the same kernels."""
+    x_shape, mask_shape = list(x_shape), list(mask_shape)
+    if len(x_shape) != len(mask_shape):
+        return None
+    kept = [i for i, (sx, sm) in enumerate(zip(x_shape, mask_shape)) if sm != 1]
+    if not kept:
+        return None
+    lo, hi = kept[0], kept[-1] + 1
+    between = [i for i in range(lo, hi) if mask_shape[i] == 1 and x_shape[i] != 1]
+    if not between:
+        return None
+    inside = [i for i in range(lo, hi) if i not in between]
+    return list(range(lo)) + between + inside + list(range(hi, len(x_shape)))
+
+
+def invert_perm(perm):
+    inv = [0] * len(perm)
+    for i, p in enumerate(perm):
+        inv[p] = i
+    return inv
+
+
 # ----------------------------------------------------------------------------- K1
 def fq_pow2_fwd(x, decimal, layout: Layout, mask=None, out=None):
     N.require_cuda(x, "input")

@@ -45,9 +45,16 @@ class _MaskApply(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, mask, precomputed=None):
+        ctx.perm = ops.mask_perm(x.shape, mask.shape)
+        ctx.mask = mask  # read at backward time, like the reference's saved Parameter
+        if ctx.perm is not None:            # kept axes not adjacent: transpose, same kernel, transpose back
+            xs, mk = _canonical(x.detach(), mask.detach(), ctx.perm)
+            _, ctx.layout = ops.mask_layout(xs.shape, mk.shape)
+            if precomputed is not None:
+                return precomputed
+            return ops.mask_apply(xs, mk, ctx.layout).permute(ops.invert_perm(ctx.perm))
         kind, layout = ops.mask_layout(x.shape, mask.shape)
         ctx.layout = layout
-        ctx.mask = mask  # read at backward time, like the reference's saved Parameter
         if precomputed is not None:
             return precomputed
         xs = N.as_f32_contiguous(x.detach())
@@ -55,8 +62,20 @@ class _MaskApply(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
+        if ctx.perm is not None:
+            g, mk = _canonical(grad_output, ctx.mask.detach(), ctx.perm)
+            return ops.mask_apply(g, mk, ctx.layout).permute(ops.invert_perm(ctx.perm)), None, None
         g = N.as_f32_contiguous(grad_output)
         return ops.mask_apply(g, ctx.mask.detach(), ctx.layout), None, None
+
+
+def _canonical(x, like, perm):
+    """(x transposed so that the kept axes of ``like`` are adjacent — a contiguous fp32 copy, the permuted VIEW of
+    ``like``): the view shares storage with the mask / magnitude Parameter, whose non-singleton axes keep their
+    order, so the kernels' in-place updates land in the Parameter."""
+    if perm is None:
+        return N.as_f32_contiguous(x), like
+    return N.as_f32_contiguous(x.permute(perm)), like.permute(perm)
 
 
 def apply_mask(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
@@ -121,8 +140,8 @@ class MagnitudePruningCallback(nn.Module):
             return
         with torch.no_grad():
             N.require_cuda(x, "x")
-            xs = N.as_f32_contiguous(x.detach())
             mag = self.magnitude.data
+            xs, mag = _canonical(x.detach(), mag, ops.mask_perm(x.shape, mag.shape))
             t = self._t()
             kind, layout = ops.mask_layout(xs.shape, mag.shape)
             if kind == "element":
@@ -139,8 +158,9 @@ class MagnitudePruningCallback(nn.Module):
         (ref qsparse/sparse.py:58-66, qsparse/util.py:103-117)."""
         N.require_cuda(x, "x")
         with torch.no_grad():
-            xs = N.as_f32_contiguous(x.detach())
-            kind, layout = ops.mask_layout(xs.shape, mask.shape)
+            perm = ops.mask_perm(x.shape, mask.shape)
+            xs, mask_c = _canonical(x.detach(), mask.data, perm)
+            kind, layout = ops.mask_layout(xs.shape, mask_c.shape)
             n = mask.numel()
             k = kth_rank(sparsity, n)
             if k >= n:
@@ -204,6 +224,8 @@ class MagnitudePruningCallback(nn.Module):
             return None                                   # nothing to update: plain mask apply
         if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == mask.dim()):
             return None
+        if ops.mask_perm(x.shape, mask.shape) is not None:
+            return None                                   # non-adjacent kept axes: the transposing route
         kind, layout = ops.mask_layout(x.shape, mask.shape)
         outer, ch, inner = layout
         if kind != "channel" or ch != mask.numel() or ch < 2 or ch > 2048 or outer * inner < 64:
@@ -341,15 +363,6 @@ class PruneLayer(nn.Module):
         assert len(x.shape) > 1
         N.require_cuda(x, "x")
         mask_shape = [s if i in self.dimensions else 1 for i, s in enumerate(x.shape)]
-        # the kernels address a mask as one contiguous run of kept axes ([1,C,1,1], [1,C,H,W], [Cout,1,1,1], the
-        # full shape ...): say so now, with the layer's name, rather than at the first pruning step
-        try:
-            ops.mask_layout(list(x.shape), mask_shape)
-        except NotImplementedError as exc:
-            raise NotImplementedError(
-                f"PruneLayer{' @ ' + self.name if self.name else ''}: dimensions={sorted(self.dimensions)} on an input of "
-                f"shape {tuple(x.shape)} keeps non-adjacent axes; qsparse_b200 supports prune masks whose kept axes "
-                f"form one contiguous run (e.g. {{1}}, {{1, 2, 3}}, {{0}}, all axes)") from exc
         self.mask = nn.Parameter(torch.ones(*mask_shape, dtype=torch.bool, device=x.device), requires_grad=False)
         if self.mask.numel() == 1:
             logging.warn(f"the mask shape of {self.name} is {tuple(self.mask.shape)}, which is not prunable")

@@ -70,7 +70,12 @@ def squeeze_tensor_to_shape(x: torch.Tensor, shape: List[int]) -> torch.Tensor:
     # the reduction kernel sums |x|; callers pass x.abs() (non-negative), for a
     # signed x the sum of x itself is needed -> split by sign.
     xs = N.as_f32_contiguous(x.detach())
-    _, layout = ops.mask_layout(xs.shape, shape)
+    perm = ops.mask_perm(xs.shape, shape)
+    if perm is not None:      # kept axes not adjacent: transpose first; the [ch] result is in kept-axis order either way
+        xs = xs.permute(perm).contiguous()
+        _, layout = ops.mask_layout(xs.shape, [shape[p] for p in perm])
+    else:
+        _, layout = ops.mask_layout(xs.shape, shape)
     outer, ch, inner = layout
     count = float(outer * inner)
     pos = ops.reduce_stats(torch.clamp_min(xs, 0) if _maybe_negative(xs) else xs, layout, abssum=True)["abssum"]
@@ -92,7 +97,12 @@ def mean_abs_to_shape(x: torch.Tensor, shape) -> torch.Tensor:
     N.require_cuda(x, "x")
     xs = N.as_f32_contiguous(x.detach())
     shape = [int(s) for s in shape]
-    kind, layout = ops.mask_layout(xs.shape, shape)
+    perm = ops.mask_perm(xs.shape, shape)
+    if perm is not None:
+        xs = xs.permute(perm).contiguous()
+        kind, layout = ops.mask_layout(xs.shape, [shape[p] for p in perm])
+    else:
+        kind, layout = ops.mask_layout(xs.shape, shape)
     if kind == "element" and xs.numel() == _prod(shape):
         return xs.abs().view(shape)
     outer, ch, inner = layout

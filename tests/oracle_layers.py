@@ -35,9 +35,11 @@ class OracleQuantize:
 
 
 class OraclePrune:
-    """structured (channel) magnitude pruning with running average"""
+    """structured magnitude pruning with running average; ``dimensions`` = the axes the mask keeps (any set, ref
+    qsparse/sparse.py:236-241)"""
 
-    def __init__(self, sparsity, start, interval, repetition, rampup=False):
+    def __init__(self, sparsity, start, interval, repetition, rampup=False, dimensions=(1,)):
+        self.dimensions = set(dimensions)
         self.sparsity, self.start, self.interval, self.repetition = sparsity, start, interval, repetition
         self.schedules, self.rampup_interval = orc.prune_schedule(start, interval, repetition, rampup)
         self.n = 0
@@ -47,8 +49,7 @@ class OraclePrune:
         self.mag = None
 
     def forward(self, x):
-        c = x.shape[1]
-        mshape = (1, c) + (1,) * (x.ndim - 2)
+        mshape = tuple(s if i in self.dimensions else 1 for i, s in enumerate(x.shape))
         if self.mask is None:
             self.mask = np.ones(mshape, bool)
         if self.n in self.schedules:
@@ -61,7 +62,10 @@ class OraclePrune:
             self.mag = orc.magnitude_ema(self.mag, orc.squeeze_mean_abs(x, mshape), self.t)
             if orc.refresh_gate(self.t, self.cur, 1, float("inf"), True):
                 self.mask, _ = orc.mask_given_importance(self.mag, self.cur)
-            out = orc.mask_apply(x, self.mask.reshape(-1), 1)
+            if self.dimensions == {1}:
+                out = orc.mask_apply(x, self.mask.reshape(-1), 1)
+            else:                       # x * mask by broadcasting (IEEE: x * 0.0 keeps the sign of x)
+                out = x * self.mask.reshape(mshape).astype(np.float32)
             self.t += 1
         else:
             out = x

@@ -145,8 +145,10 @@ def test_squeeze_tensor_to_shape(golden):
         assert ulp_diff(got, ref).max() <= 4, tgt  # fp32 cascade sums are not restated
         got = npy(mean_abs_to_shape(x, tgt))
         assert ulp_diff(got, ref).max() <= 4, tgt
-    with pytest.raises(NotImplementedError):
-        squeeze_tensor_to_shape(x.abs(), (6, 1, 5, 1))  # kept axes 0 and 2 are not adjacent: documented limit
+    # kept axes 0 and 2 are not adjacent: the transposing route (ref: any dimension set, util.py:93-101)
+    want = npy(x.abs().mean(dim=(1, 3), keepdim=True))
+    assert ulp_diff(npy(squeeze_tensor_to_shape(x.abs(), (6, 1, 5, 1))), want).max() <= 4
+    assert ulp_diff(npy(mean_abs_to_shape(x, (6, 1, 5, 1))), want).max() <= 4
     with pytest.raises(ValueError):
         squeeze_tensor_to_shape(x.abs(), (1, 3, 1, 1))
 
@@ -245,6 +247,34 @@ def test_layer_flows(golden):
         assert np.array_equal(npy(qp.prune.mask), g["layer/qp_mask"])
         assert bits_equal(npy(qp.quantize.weight), g["layer/qp_scale"])
         assert not bits_equal(npy(qp._parameters["weight"]), npy(qp.weight))  # raw parameter untouched
+
+
+DIMS_CASES = {"nchw_13": ({1, 3}, True), "nchw_03": ({0, 3}, True), "w_02": ({0, 2}, True),
+              "w_02_instant": ({0, 2}, False), "w_013": ({0, 1, 3}, True), "nlc_02": ({0, 2}, True)}
+
+
+@pytest.mark.parametrize("name", sorted(DIMS_CASES))
+def test_non_adjacent_kept_axes(name):
+    """PruneLayer with a dimension set whose axes are not adjacent (mask [1,C,1,W], [Cout,1,kh,1] ...) against
+    what the reference returned (oracle/gen_golden_dims.py): outputs, masks, input gradients bit for bit, running
+    magnitudes to 4 ulp."""
+    import qsparse_b200 as qs
+    from qsparse_b200.sparse import MagnitudePruningCallback
+    g = np.load(Path(__file__).resolve().parent / "golden" / "dims_v1.npz")
+    dims, ra = DIMS_CASES[name]
+    with contextlib.redirect_stdout(io.StringIO()):
+        pl = qs.prune(sparsity=0.5, start=2, interval=2, repetition=2, dimensions=dims,
+                      callback=MagnitudePruningCallback(running_average=ra))
+        pl.train()
+        for t in range(g[f"{name}/x"].shape[0]):
+            x = cu(g[f"{name}/x"][t]).requires_grad_(True)
+            y = pl(x)
+            y.backward(cu(g[f"{name}/g"][t]))
+            assert np.array_equal(npy(pl.mask), g[f"{name}/mask"][t]), t
+            assert bits_equal(npy(y), g[f"{name}/out"][t]), t
+            assert bits_equal(npy(x.grad), g[f"{name}/gx"][t]), t
+            if ra and hasattr(pl.callback, "magnitude"):
+                assert ulp_diff(npy(pl.callback.magnitude).reshape(-1), g[f"{name}/mag"][t].reshape(-1)).max() <= 4, t
 
 
 # ----------------------------------------------------------------------------- corners (oracle/gen_golden_extremes.py)

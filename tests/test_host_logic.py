@@ -81,6 +81,16 @@ def test_mask_layout():
         ops.mask_layout((1, 10, 64, 64), (1, 10, 32, 32))
     with pytest.raises(NotImplementedError):
         ops.mask_layout((4, 8, 5, 5), (4, 1, 5, 1))
+    # ... which is what mask_perm() resolves: move the sandwiched broadcast axes in front of the kept run
+    assert ops.mask_perm((4, 8, 5, 5), (1, 8, 1, 1)) is None and ops.mask_perm((4, 8, 5, 5), (4, 8, 5, 5)) is None
+    perm = ops.mask_perm((4, 8, 5, 6), (4, 1, 5, 1))
+    assert perm == [1, 0, 2, 3]
+    assert ops.mask_layout([(4, 8, 5, 6)[p] for p in perm], [(4, 1, 5, 1)[p] for p in perm]) == ("channel", (8, 20, 6))
+    perm = ops.mask_perm((4, 8, 5, 6), (1, 8, 1, 6))
+    assert perm == [0, 2, 1, 3] and ops.invert_perm(perm) == [0, 2, 1, 3]
+    assert ops.mask_layout([(4, 8, 5, 6)[p] for p in perm], [(1, 8, 1, 6)[p] for p in perm]) == ("channel", (20, 48, 1))
+    perm = ops.mask_perm((2, 3, 4, 5, 6), (2, 1, 4, 1, 6))
+    assert perm == [1, 3, 0, 2, 4] and ops.invert_perm(perm) == [2, 0, 3, 1, 4]
 
 
 def test_kth_rank_matches_reference_formula():

@@ -169,6 +169,26 @@ def test_oracle_layer_emulators_match_reference_layers(golden):
         assert np.array_equal(em.mask, g["layer/p_mask"][t]), t
 
 
+DIMS_CASES = {"nchw_13": {1, 3}, "nchw_03": {0, 3}, "w_02": {0, 2}, "w_013": {0, 1, 3}, "nlc_02": {0, 2}}
+
+
+@pytest.mark.parametrize("name", sorted(DIMS_CASES))
+def test_non_adjacent_kept_axes(name):
+    """Prune masks whose kept axes are not adjacent (dimensions={1,3} on NCHW ...), recorded from the reference by
+    oracle/gen_golden_dims.py: the oracle's squeeze / EMA / mask flow reproduces magnitudes (<= 4 ulp, the fp32
+    mean chain is not restated), masks and outputs."""
+    from pathlib import Path
+    from tests.oracle_layers import OraclePrune
+    g = np.load(Path(__file__).resolve().parent / "golden" / "dims_v1.npz")
+    em = OraclePrune(0.5, 2, 2, 2, dimensions=DIMS_CASES[name])
+    for t in range(g[f"{name}/x"].shape[0]):
+        out = em.forward(g[f"{name}/x"][t])
+        assert np.array_equal(em.mask.reshape(g[f"{name}/mask"][t].shape), g[f"{name}/mask"][t]), t
+        assert bits_equal(out, g[f"{name}/out"][t]), t
+        if em.mag is not None:
+            assert ulp_diff(em.mag.reshape(-1), g[f"{name}/mag"][t].reshape(-1)).max() <= 4, t
+
+
 # ----------------------------------------------------------------------------- corners (oracle/gen_golden_extremes.py)
 @pytest.fixture(scope="module")
 def extremes():
