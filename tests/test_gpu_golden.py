@@ -3,6 +3,7 @@ against golden vectors recorded from the reference itself (tests/golden/, genera
 by oracle/gen_golden.py).  Bit-exact unless a tolerance is stated."""
 import contextlib
 import io
+from pathlib import Path
 
 import numpy as np
 import pytest
