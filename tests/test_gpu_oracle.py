@@ -1339,3 +1339,23 @@ def test_reduce_stats_one_launch_equals_two_launch(lay):
                 assert torch.equal(a[key], b[key]), key
     ref = x.abs().amax(dim=(0, 2))
     assert torch.equal(res[True][2]["absmax"], ref)
+
+
+def test_fuzz_vs_oracle():
+    """A short seeded slice of benchmarks/fuzz_vs_oracle.py: random ranks / shapes / channel axes / parameters / special
+    values / alignments through every functional entry point, plus stateful step and row-quant flows, bit for bit
+    against the oracle (12 600 cases and 1 538 flows of the full tool: profiles/r02_fuzz_vs_oracle.txt)."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_vs_oracle", Path(__file__).resolve().parent.parent / "benchmarks" / "fuzz_vs_oracle.py")
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(2026)
+    for case in range(80):
+        fz.one_case(rng, case)
+    done = 0
+    for case in range(24):
+        done += fz.step_flow_case(rng, case) is not None
+        done += fz.row_quant_case(rng, case) is not None
+    assert done >= 30
