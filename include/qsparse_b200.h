@@ -453,10 +453,14 @@ int qsb_prune_quant_params(float *magnitude, uint8_t *mask, float *scale,
  * Requires channels <= 2048 and the same (outer, channels, inner) that was
  * passed to qsb_reduce_partials.
  * step_counter_dev (optional): a device int64 step index for CUDA-graph capture
- * (launch arguments of a captured graph are frozen).  When given, the kernel uses
- * t_prune = t_quant = *step_counter_dev, step_stamp = t + 1, treats refresh_mask
- * as the refresh INTERVAL (refresh when t % interval == 0 and (t > 0 or
- * update_magnitude == 2)) and increments the counter at the end.
+ * (launch arguments of a captured graph are frozen).  When given, with t =
+ * *step_counter_dev the kernel uses t_prune = t + <the t_prune argument> and
+ * t_quant = t + <the t_quant argument> (the arguments become OFFSETS: a prune
+ * callback and a quantizer that started at different steps keep a constant
+ * distance; pass 0 for both to index everything by the counter itself),
+ * step_stamp = t + 1, treats refresh_mask as the refresh INTERVAL (refresh when
+ * t_prune % interval == 0 and (t_prune > 0 or update_magnitude == 2)) and stores
+ * t + 1 into the counter at the end.
  * ---------------------------------------------------------------------- */
 int qsb_reduce_partials(const float *x, int64_t outer, int64_t channels,
                         int64_t inner, void *workspace, int64_t workspace_bytes,

@@ -8,6 +8,7 @@ from .fused import fuse_prune_quantize
 from .quantize import quantize, DecimalQuantizer, ScalerQuantizer, AdaptiveQuantizer, PercentileQuantizer
 from .sparse import MagnitudePruningCallback, UniformPruningCallback, prune, devise_layerwise_pruning_schedule
 from .sparse import WeightSetPruner
+from .graphs import GraphedTrainStep
 from .util import auto_name_prune_quantize_layers, calculate_mask_given_importance
 from .util import get_option as get_qsparse_option
 from .util import set_options as set_qsparse_options

@@ -146,15 +146,18 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
   int64_t t_prune = a.t_prune, t_quant = a.t_quant;
   unsigned long long stamp = a.stamp;
   int refresh_mask = a.refresh_mask;
+  long long t_counter = 0;
   if (a.step_counter) {
     // graph mode: the step index lives on the device (the launch arguments of a captured
-    // CUDA graph are frozen); `refresh_mask` then carries the refresh interval.
-    const long long t = pre.valid ? pre.t : *a.step_counter;
-    t_prune = t;
-    t_quant = t;
-    stamp = (unsigned long long)(t + 1);
+    // CUDA graph are frozen).  `t_prune` / `t_quant` are then OFFSETS added to the counter (a prune
+    // callback and a quantizer started at different steps keep a constant distance) and
+    // `refresh_mask` carries the refresh interval.
+    t_counter = pre.valid ? pre.t : *a.step_counter;
+    t_prune = t_counter + a.t_prune;
+    t_quant = t_counter + a.t_quant;
+    stamp = (unsigned long long)(t_counter + 1);
     const int interval = refresh_mask > 0 ? refresh_mask : 1;
-    refresh_mask = (t % interval == 0) && (t > 0 || a.update_magnitude == 2);
+    refresh_mask = (t_prune % interval == 0) && (t_prune > 0 || a.update_magnitude == 2);
   }
   const int channels = a.channels, group = a.group;
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -344,7 +347,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
         *px.error = 1;
         a.scale[0] = nan_poison();
         if (a.decimal_out) a.decimal_out[0] = nan_poison();
-        if (a.step_counter) *a.step_counter = t_prune + 1;
+        if (a.step_counter) *a.step_counter = t_counter + 1;
       }
       return;
     }
@@ -420,7 +423,7 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &a, const StepSmem 
       a.scale[0] = s;
     }
     if (a.decimal_out) a.decimal_out[0] = scale_to_decimal(s);
-    if (a.step_counter) *a.step_counter = t_prune + 1;
+    if (a.step_counter) *a.step_counter = t_counter + 1;
     if (a.timing) a.timing[6] = global_ns();
   }
 }

@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as N
+from . import graphs
 from . import ops
 from .parallel import StatExchange, make_exchange
 from .util import kth_rank
@@ -242,15 +243,25 @@ class FusedPruneQuantSequential(nn.Sequential):
                 magnitude, mode = cb.magnitude.data.view(-1), 1
             else:
                 magnitude, mode = torch.empty(ch, dtype=torch.float32, device=x.device), 2
-            if ch <= ops.FUSED_STEP_MAX_CHANNELS:
+            if graphs.active():
+                # graph mode: the step index is the prune callback's own `t` Parameter, read and advanced by the
+                # kernel; the quantizer's EMA index keeps its constant distance to it
+                if ch > ops.FUSED_STEP_MAX_CHANNELS or cb.stop_mask_refresh != float("inf"):
+                    raise graphs.NotCapturable("a fused site with more than "
+                                               f"{ops.FUSED_STEP_MAX_CHANNELS} channels or a stopping mask refresh")
+                ops.reduce_prune_quant_step(xs, layout, magnitude, p.mask.data.view(-1), q.weight.data.view(-1),
+                                            decimal, float(outer * inner), 0, mode, cb.mask_refresh_interval,
+                                            kth_rank(sparsity, ch), q.bits, qcb.t - t, True, step_counter=cb.t.data)
+            elif ch <= ops.FUSED_STEP_MAX_CHANNELS:
                 ops.reduce_prune_quant_step(xs, layout, magnitude, p.mask.data.view(-1), q.weight.data.view(-1),
                                             decimal, float(outer * inner), t, mode, refresh, k, q.bits, qcb.t, True)
+                cb.t.data.add_(1)
             else:
                 ws = ops.reduce_partials(xs, layout)
                 ops.prune_quant_step_params(magnitude, p.mask.data.view(-1), q.weight.data.view(-1), decimal, ws,
                                             layout, float(outer * inner), t, mode, refresh, k, q.bits, qcb.t, True)
+                cb.t.data.add_(1)
             # the counters of the two layers and their callbacks, as their own forwards advance them
-            cb.t.data.add_(1)
             cb._t_mirror.wrote(cb.t, t + 1)
             n = p._n_mirror.get(p._n_updates)
             p._n_updates.data.add_(1)
@@ -287,10 +298,12 @@ class _FusedWeightFn(torch.autograd.Function):
         qcb = q.callback
         ctx.mask, ctx.rows, ctx.bits = mask, ws.shape[0], q.bits
         if type(qcb) is AdaptiveQuantizer:
+            graphs.require_eager("the fused weight chain quantize(prune(layer))")
             y, _ = ops.row_quant_fused_(ws, q.weight.data, ops.ROW_LINE, q.bits, t_line, qcb.training, mask=mask)
             ctx.kind = "line"
         else:
             is_decimal = not qcb.use_float_scaler
+            graphs.require_eager("the fused weight chain quantize(prune(layer))")
             y, dec = ops.row_quant_fused_(ws, q.weight.data, ops.ROW_DECIMAL if is_decimal else ops.ROW_SCALER,
                                           q.bits, qcb.t, mask=mask)
             qcb.t += 1

@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as N
+from . import graphs
 from . import ops
 from .common import TensorOrFloat, TensorOrInt
 from .imitation import imitate
@@ -204,6 +205,7 @@ class _RowFusedSte(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, quantizer, bits, weight, xs):
         is_decimal = not quantizer.use_float_scaler
+        graphs.require_eager("the row-resident estimate + quantize kernel (channelwise=0 weights)")
         y, dec = ops.row_quant_fused_(xs, weight.data, ops.ROW_DECIMAL if is_decimal else ops.ROW_SCALER, bits,
                                       quantizer.t)
         quantizer.t += 1
@@ -250,8 +252,14 @@ class _TensorFusedSte(torch.autograd.Function):
         decimal = torch.empty(1, dtype=torch.float32, device=dev) if is_decimal else None
         # ONE launch: abs-max reduction whose last-arriving CTA finalizes and updates scale / decimal
         mag0, mask1 = _dummy_state(dev)
-        ops.reduce_prune_quant_step(xs, layout, mag0, mask1, weight.data.view(-1), decimal if is_decimal else None,
-                                    float(n), 0, 0, False, 0, bits, quantizer.t, True)
+        if graphs.active():
+            # graph mode: the EMA index is the quantizer's device counter (read and advanced by the kernel)
+            ops.reduce_prune_quant_step(xs, layout, mag0, mask1, weight.data.view(-1), decimal if is_decimal else None,
+                                        float(n), 0, 0, graphs.NO_REFRESH_INTERVAL, 0, bits, 0, True,
+                                        step_counter=graphs.quantizer_counter(quantizer, dev))
+        else:
+            ops.reduce_prune_quant_step(xs, layout, mag0, mask1, weight.data.view(-1), decimal if is_decimal else None,
+                                        float(n), 0, 0, False, 0, bits, quantizer.t, True)
         quantizer.t += 1
         if is_decimal:
             y = ops.fq_pow2_fwd(xs, decimal, layout)
@@ -280,6 +288,7 @@ class _RowFusedLine(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, input, bits, weight, xs, t, float_zero_point):
+        graphs.require_eager("the row-resident estimate + quantize kernel (AdaptiveQuantizer)")
         y, _ = ops.row_quant_fused_(xs, weight.data, ops.ROW_LINE, bits, t, float_zero_point)
         return y.view(input.shape)
 
@@ -384,6 +393,7 @@ class DecimalQuantizer(BaseQuantizer):
                 weight = torch.zeros(wshape, dtype=torch.float32, device=x.device)
             target = weight.data if isinstance(weight, nn.Parameter) else weight
             assert tuple(target.shape) == tuple(wshape) and target.is_contiguous()
+            graphs.require_eager("DecimalQuantizer / ScalerQuantizer.optimize on this tensor layout")
             ops.scale_ema_(target, absmax, bits, self.t)
         self.t += 1
         return weight
@@ -468,6 +478,7 @@ class PercentileQuantizer(DecimalQuantizer):
                 weight = torch.zeros(wshape, dtype=torch.float32, device=x.device)
             target = weight.data if isinstance(weight, nn.Parameter) else weight
             assert tuple(target.shape) == tuple(wshape) and target.is_contiguous()
+            graphs.require_eager("PercentileQuantizer.optimize")
             ops.scale_ema_(target, stat.contiguous(), bits, self.t)
         self.t += 1
         return weight
@@ -541,6 +552,7 @@ class AdaptiveQuantizer(DecimalQuantizer):
             assert (nch, 2) == tuple(weight.shape)
             t = self._next_t()
             target = weight.data if isinstance(weight, nn.Parameter) else weight
+            graphs.require_eager("AdaptiveQuantizer.optimize")
             ops.lines_ema_(target, st["min"], st["max"], t)
         return weight
 

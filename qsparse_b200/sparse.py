@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as N
+from . import graphs
 from . import ops
 from .imitation import imitate
 from .util import HostMirror, get_option, kth_rank, logging
@@ -211,7 +212,7 @@ class MagnitudePruningCallback(nn.Module):
                                                  hints=self._hint if SELECT_HINTS else None)
         return _MaskApply.apply(x, mask, out)
 
-    def _fused_structured_step(self, x, sparsity, mask, t, refresh):
+    def _fused_structured_step(self, x, sparsity, mask, t, refresh, counter=None):
         """update_magnitude [+ prune_and_update_mask] of the stock structured (channel-mask) case in two
         launches — the reduction, whose last-arriving CTA finalizes and does magnitude EMA, k-th value by rank
         counting and the mask; then mask apply — instead of nine (reduce + finalize, EMA, a 4-launch select over C values,
@@ -240,7 +241,15 @@ class MagnitudePruningCallback(nn.Module):
             else:
                 magnitude, mode = torch.empty(ch, dtype=torch.float32, device=x.device), 2
             dummy = torch.zeros(1, dtype=torch.float32, device=x.device)
-            if ch <= ops.FUSED_STEP_MAX_CHANNELS:
+            if counter is not None:
+                # graph mode: the kernel reads the step index from `counter` (the callback's own `t` Parameter),
+                # derives the refresh gate from it and advances it
+                if ch > ops.FUSED_STEP_MAX_CHANNELS:
+                    return None
+                ops.reduce_prune_quant_step(xs, layout, magnitude, mask.data.view(-1), dummy, None,
+                                            float(outer * inner), 0, mode, self.mask_refresh_interval,
+                                            kth_rank(sparsity, ch), 8, 0, False, step_counter=counter)
+            elif ch <= ops.FUSED_STEP_MAX_CHANNELS:
                 ops.reduce_prune_quant_step(xs, layout, magnitude, mask.data.view(-1), dummy, None,
                                             float(outer * inner), t, mode, refresh, k, 8, 0, False)
             else:
@@ -260,6 +269,8 @@ class MagnitudePruningCallback(nn.Module):
         t = self._t()
         refresh = (sparsity >= 0 and (t % self.mask_refresh_interval == 0 and t <= self.stop_mask_refresh)
                    and (t > 0 or not self.running_average))
+        if graphs.active():
+            return self._graph_mode_forward(x, sparsity, mask, t, name)
         out = None
         pre = getattr(self, "_precomputed", None)
         if pre is not None:
@@ -279,6 +290,21 @@ class MagnitudePruningCallback(nn.Module):
             out = self.prune_and_update_mask(x, sparsity, mask) if refresh else apply_mask(x, mask)
         self.t.data.add_(1)
         self._t_mirror.wrote(self.t, t + 1)
+        if self.forward_hook is not None:
+            self.forward_hook(mask, name)
+        return out
+
+
+    def _graph_mode_forward(self, x, sparsity, mask, t, name):
+        """One step whose index lives on the device (qsparse_b200.graphs): only the stock structured route, with
+        the default never-stopping mask refresh."""
+        if self.stop_mask_refresh != float("inf") or sparsity < 0 or kth_rank(sparsity, mask.numel()) >= mask.numel():
+            raise graphs.NotCapturable("a prune callback with stop_mask_refresh / an out-of-range sparsity")
+        self._precomputed = None
+        out = self._fused_structured_step(x, sparsity, mask, t, True, counter=self.t.data)
+        if out is None:
+            graphs.require_eager("this prune callback (only the stock structured channel-mask step is capturable)")
+        self._t_mirror.wrote(self.t, t + 1)                 # the kernel advanced self.t itself
         if self.forward_hook is not None:
             self.forward_hook(mask, name)
         return out
@@ -450,6 +476,7 @@ class WeightSetPruner:
     @torch.no_grad()
     def step(self) -> int:
         """Precompute this step for every eligible layer; returns how many layers were batched."""
+        graphs.require_eager("WeightSetPruner.step")
         todo = []
         for mod, p in self.layers:
             e = self._eligible(mod, p)

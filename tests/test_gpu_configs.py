@@ -457,3 +457,160 @@ def test_structured_callback_fused_step_equals_unfused(running_average):
         for i, (u, v) in enumerate(zip(a, b)):
             assert torch.equal(u, v), (t, i)
     assert res[True][-1][2].sum().item() == 24
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_config1_eval_forward_in_a_cuda_graph(fuse):
+    """The converted net's inference forward enqueues kernels and never waits for the device (no `.item()`, no host
+    reads of device state), so the whole forward captures into ONE CUDA graph: replays on new inputs equal eager
+    calls bit for bit.  (The training step is host-scheduled like the reference's — step counters, schedules,
+    EMA indices are Python values — and is not capturable as a whole; its hot kernels are, see bench.py.)"""
+    import qsparse_b200 as qs
+    from benchmarks.configs import _c1_convert, _c1_net
+    qs.set_qsparse_options(log_on_created=False)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = _c1_convert(torch, qs, _c1_net(torch), "ScalerQuantizer", fuse).to(dev)
+        opt = torch.optim.SGD(model.parameters(), lr=0.01)
+        gen = torch.Generator(device=dev).manual_seed(3)
+        model.train()
+        for _ in range(64):                                  # past timeout 10 and the pruning ramp 20..50
+            x = torch.randn(64, 1, 28, 28, device=dev, generator=gen)
+            y = torch.randint(0, 10, (64,), device=dev, generator=gen)
+            opt.zero_grad()
+            torch.nn.functional.nll_loss(model(x), y).backward()
+            opt.step()
+        model.eval()
+        static_x = torch.randn(64, 1, 28, 28, device=dev, generator=gen)
+        with torch.no_grad():
+            eager0 = model(static_x).clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                model(static_x)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_y = model(static_x)
+            graph.replay()
+            assert torch.equal(static_y.view(torch.int32), eager0.view(torch.int32))
+            for _ in range(3):
+                xn = torch.randn(64, 1, 28, 28, device=dev, generator=gen)
+                static_x.copy_(xn)
+                graph.replay()
+                assert torch.equal(static_y.view(torch.int32), model(xn).view(torch.int32))
+
+
+def _c1_train_setup(kind, seed=11):
+    import qsparse_b200 as qs
+    from benchmarks.configs import _c1_convert, _c1_net
+    dev = torch.device("cuda:0")
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = _c1_convert(torch, qs, _c1_net(torch), kind, True).to(dev)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    xs = torch.randn(70, 64, 1, 28, 28, device=dev, generator=gen)
+    ys = torch.randint(0, 10, (70, 64), device=dev, generator=gen)
+    return model, opt, xs, ys
+
+
+@pytest.mark.parametrize("kind", ["ScalerQuantizer", "DecimalQuantizer"])
+def test_config1_training_step_as_one_cuda_graph(kind):
+    """qsparse_b200.GraphedTrainStep: the steady-state training step of the converted MNIST net (forward, backward,
+    optimizer step; 8 quantize and 2 fused prune->quantize sites) captured into ONE CUDA graph whose step indices
+    live on the device.  60 eager steps + 10 steps of which 6 are graph replays must leave the SAME parameters,
+    masks, scales, magnitudes and counters — device and host side — as 70 eager steps, bit for bit."""
+    import qsparse_b200 as qs
+    from qsparse_b200 import graphs
+    qs.set_qsparse_options(log_on_created=False)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    F = torch.nn.functional
+
+    def run(graph_from):
+        model, opt, xs, ys = _c1_train_setup(kind)
+        static_x, static_y = xs[0].clone(), ys[0].clone()
+        model.train()
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = F.nll_loss(model(static_x), static_y)
+            loss.backward()
+            opt.step()
+            return loss
+
+        losses = []
+        with contextlib.redirect_stdout(io.StringIO()):
+            i = 0
+            while i < 70:
+                if graph_from is not None and i == graph_from:
+                    feed = iter(range(i, i + 3))
+
+                    def warm_step():
+                        j = next(feed)
+                        static_x.copy_(xs[j]); static_y.copy_(ys[j])
+                        return step()
+
+                    # the warm-up steps are real steps on real batches; the captured function is `step`
+                    gs = _graphed(model, step, warm_step)
+                    i += 3
+                    for _ in range(6):
+                        static_x.copy_(xs[i]); static_y.copy_(ys[i])
+                        losses.append(gs.replay().clone())
+                        i += 1
+                    gs.sync_host()
+                    continue
+                static_x.copy_(xs[i]); static_y.copy_(ys[i])
+                losses.append(step().detach().clone())
+                i += 1
+        state = {k: v.clone() for k, v in model.state_dict().items()}
+        host = [int(cb.t) for cb in model.modules() if isinstance(getattr(cb, "t", None), int)]
+        fused = [m.fused_steps for m in model.modules() if hasattr(m, "fused_steps")]
+        return state, host, torch.stack(losses), fused
+
+    def _graphed(model, step, warm_step):
+        """GraphedTrainStep with distinct warm-up batches: warm up through `warm_step`, capture `step`"""
+        class _Two:
+            def __init__(self):
+                self.n = 0
+
+            def __call__(self):
+                self.n += 1
+                return warm_step() if self.n <= 3 else step()
+        return graphs.GraphedTrainStep(model, _Two(), warmup=3)
+
+    ref_state, ref_host, ref_losses, ref_fused = run(None)
+    got_state, got_host, got_losses, got_fused = run(60)
+    assert ref_host == got_host and ref_fused == got_fused
+    assert sorted(ref_state) == sorted(got_state)
+    for k in ref_state:
+        a, b = ref_state[k], got_state[k]
+        assert torch.equal(a.view(torch.uint8) if a.dtype == torch.bool else a, b.view(torch.uint8) if b.dtype == torch.bool else b), k
+    # the warm-up steps' losses are not recorded in the graphed run: compare the others
+    assert torch.equal(ref_losses[:60], got_losses[:60]) and torch.equal(ref_losses[63:69], got_losses[60:66])
+
+
+def test_graph_mode_refuses_what_it_cannot_capture():
+    """Routes that index a running mean by a HOST step counter raise NotCapturable in graph mode instead of freezing
+    the index into the graph; so does a model that is not in its steady state yet."""
+    import qsparse_b200 as qs
+    from qsparse_b200 import graphs
+    qs.set_qsparse_options(log_on_created=False)
+    dev = torch.device("cuda:0")
+    with contextlib.redirect_stdout(io.StringIO()):
+        lin = qs.quantize(nn.Linear(64, 32), bits=8, channelwise=0, timeout=1).to(dev)   # K8: host step index
+        lin.train()
+        x = torch.randn(8, 64, device=dev)
+        for _ in range(3):
+            lin(x)
+        with graphs.graph_mode(), pytest.raises(graphs.NotCapturable):
+            lin(x)
+        fresh = qs.quantize(bits=8, channelwise=-1, timeout=100).to(dev)
+        fresh.train()
+        fresh(x)
+        with pytest.raises(graphs.NotCapturable):
+            graphs.GraphedTrainStep(fresh, lambda: fresh(x))
