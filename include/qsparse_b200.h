@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QSB_ABI_VERSION 2
+#define QSB_ABI_VERSION 3
 
 /* argument errors */
 #define QSB_E_BADARG (-1)     /* null pointer / negative size / bad enum        */
@@ -245,6 +245,15 @@ int qsb_scale_to_decimal(const float *scale, float *decimal, int64_t n,
 int qsb_lines_ema(float *lines, const float *mn, const float *mx,
                   int64_t channels, int64_t t, void *stream);
 
+/* CUDA-graph forms of the two running means above (no reference counterpart: the
+ * reference's step indices are Python ints, qsparse/quantize.py:340-348,426-430):
+ * the index is *t_dev + t_offset, read by the kernel, because the launch arguments
+ * of a captured graph are frozen.  The caller advances the counter (stream-ordered). */
+int qsb_scale_ema_at(float *weight, const float *absmax, int64_t n, int bits,
+                     const int64_t *t_dev, int64_t t_offset, void *stream);
+int qsb_lines_ema_at(float *lines, const float *mn, const float *mx, int64_t channels,
+                     const int64_t *t_dev, int64_t t_offset, void *stream);
+
 /* ------------------------------------------------------------------------
  * K8  row-resident fused estimate + quantize for tensors quantized along their
  * LEADING axis (x is [rows][inner] contiguous, one parameter row per x row —
@@ -280,6 +289,13 @@ int qsb_row_quant_fused_masked(const float *x, float *y, float *param,
                                int kind, int bits, int float_zero_point,
                                int64_t rows, int64_t inner, int64_t t,
                                void *stream);
+/* CUDA-graph form of qsb_row_quant_fused[_masked]: the EMA index is *t_dev + t_offset, read by
+ * the kernel (mask_dev may be NULL); the caller advances the counter. */
+int qsb_row_quant_fused_at(const float *x, float *y, float *param,
+                           float *decimal_out, const uint8_t *mask_dev,
+                           int kind, int bits, int float_zero_point,
+                           int64_t rows, int64_t inner, const int64_t *t_dev,
+                           int64_t t_offset, void *stream);
 
 int qsb_magnitude_ema_reduced(float *magnitude, const double *abssum,
                               const double *nnz, const float *tensor_min,

@@ -45,8 +45,11 @@ _SIGNATURES = {
     "qsb_scale_ema": (c_int, [_P, _P, c_int64, c_int, c_int64, _P]),
     "qsb_scale_to_decimal": (c_int, [_P, _P, c_int64, _P]),
     "qsb_lines_ema": (c_int, [_P, _P, _P, c_int64, c_int64, _P]),
+    "qsb_scale_ema_at": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, _P]),
+    "qsb_lines_ema_at": (c_int, [_P, _P, _P, c_int64, _P, c_int64, _P]),
     "qsb_row_quant_fused": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, _P]),
     "qsb_row_quant_fused_masked": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, _P]),
+    "qsb_row_quant_fused_at": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, _P, c_int64, _P]),
     "qsb_magnitude_ema_reduced": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_double, c_int64, _P]),
     "qsb_magnitude_ema_full": (c_int, [_P, _P, _P, c_int, c_int64, c_int64, _P]),
     "qsb_magnitude_ema_full_multi": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
@@ -133,7 +136,7 @@ def load_library() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.qsb_abi_version() != 2:
+    if lib.qsb_abi_version() != 3:
         raise NativeLibraryError("libqsparse_b200.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

@@ -44,8 +44,9 @@ const DeviceProps &device_props() {
 }
 
 __global__ void scale_ema_kernel(float *w, const float *absmax, int64_t n,
-                                 float limit, int64_t t) {
+                                 float limit, int64_t t, const long long *t_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_dev) t += (int64_t)__ldg(t_dev);
   if (i < n) w[i] = scale_ema_step(w[i], absmax[i], limit, t);
 }
 
@@ -56,8 +57,14 @@ __global__ void scale_to_decimal_kernel(const float *s, float *d, int64_t n) {
 
 // lines = (w * (t - 1) + new) / t     ref qsparse/quantize.py:428-430
 __global__ void lines_ema_kernel(float *lines, const float *mn, const float *mx,
-                                 int64_t channels, float tm1, float t) {
+                                 int64_t channels, float tm1, float t, const long long *t_dev,
+                                 int64_t t_offset) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_dev) {
+    const int64_t ti = (int64_t)__ldg(t_dev) + t_offset;
+    tm1 = (float)(ti - 1);
+    t = (float)ti;
+  }
   if (i < channels) {
     lines[2 * i] = lines_ema_step(lines[2 * i], mn[i], tm1, t);
     lines[2 * i + 1] = lines_ema_step(lines[2 * i + 1], mx[i], tm1, t);
@@ -269,7 +276,31 @@ extern "C" int qsb_scale_ema(float *weight, const float *absmax, int64_t n,
   if (!weight || !absmax) return QSB_E_BADARG;
   const float limit = (float)pow(2.0, (double)bits - 1.0);
   scale_ema_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      weight, absmax, n, limit, t);
+      weight, absmax, n, limit, t, nullptr);
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+// CUDA-graph forms: the step index is *t_dev + t_offset, read by the kernel; the caller advances the counter.
+extern "C" int qsb_scale_ema_at(float *weight, const float *absmax, int64_t n, int bits,
+                                const int64_t *t_dev, int64_t t_offset, void *stream) {
+  if (n < 0 || !t_dev) return QSB_E_BADARG;
+  if (n == 0) return 0;
+  if (!weight || !absmax) return QSB_E_BADARG;
+  const float limit = (float)pow(2.0, (double)bits - 1.0);
+  scale_ema_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      weight, absmax, n, limit, t_offset, reinterpret_cast<const long long *>(t_dev));
+  QSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qsb_lines_ema_at(float *lines, const float *mn, const float *mx, int64_t channels,
+                                const int64_t *t_dev, int64_t t_offset, void *stream) {
+  if (channels < 0 || !t_dev) return QSB_E_BADARG;
+  if (channels == 0) return 0;
+  if (!lines || !mn || !mx) return QSB_E_BADARG;
+  lines_ema_kernel<<<blocks_for(channels, 256), 256, 0, (cudaStream_t)stream>>>(
+      lines, mn, mx, channels, 0.f, 1.f, reinterpret_cast<const long long *>(t_dev), t_offset);
   QSB_LAUNCH_CHECK();
   return 0;
 }
@@ -291,7 +322,7 @@ extern "C" int qsb_lines_ema(float *lines, const float *mn, const float *mx,
   if (channels == 0) return 0;
   if (!lines || !mn || !mx) return QSB_E_BADARG;
   lines_ema_kernel<<<blocks_for(channels, 256), 256, 0, (cudaStream_t)stream>>>(
-      lines, mn, mx, channels, (float)(t - 1), (float)t);
+      lines, mn, mx, channels, (float)(t - 1), (float)t, nullptr, 0);
   QSB_LAUNCH_CHECK();
   return 0;
 }

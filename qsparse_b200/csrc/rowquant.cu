@@ -45,6 +45,7 @@ struct RowConsts {
   float n_levels;  // 2^bits                          (line)
   float q_max;     // 2^bits - 1                      (line)
   int64_t t;       // scale EMA: calls so far (0-based); lines EMA: this call's number (1-based)
+  const long long *t_dev;  // optional device step counter (CUDA graphs): the index is *t_dev + t
 };
 
 struct RowStat {
@@ -100,11 +101,13 @@ __device__ __forceinline__ float2 ema_param(const RowStat &s, float2 w, const Ro
   if constexpr (KIND == kRowLine) {
     const float mn = s.nan ? __uint_as_float(0x7fc00000u) : s.mn;
     const float mx = s.nan ? __uint_as_float(0x7fc00000u) : s.mx;
-    const float tm1 = (float)(k.t - 1), tf = (float)k.t;
+    const int64_t t = k.t_dev ? (int64_t)__ldg(k.t_dev) + k.t : k.t;
+    const float tm1 = (float)(t - 1), tf = (float)t;
     r.x = lines_ema_step(w.x, mn, tm1, tf);
     r.y = lines_ema_step(w.y, mx, tm1, tf);
   } else {
-    r.x = scale_ema_step(w.x, __uint_as_float(s.amax), k.limit, k.t);
+    const int64_t t = k.t_dev ? (int64_t)__ldg(k.t_dev) + k.t : k.t;
+    r.x = scale_ema_step(w.x, __uint_as_float(s.amax), k.limit, t);
     r.y = 0.f;
   }
   return r;
@@ -425,11 +428,12 @@ using namespace qsb;
 
 static int row_quant_fused_impl(const float *x, float *y, float *param, float *decimal_out,
                                 const uint8_t *mask, int kind, int bits, int float_zero_point,
-                                int64_t rows, int64_t inner, int64_t t, void *stream_) {
+                                int64_t rows, int64_t inner, int64_t t, void *stream_,
+                                const int64_t *t_dev = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (rows < 0 || inner < 0 || bits < 0 || bits > 62) return QSB_E_BADARG;
   if (kind < kRowDecimal || kind > kRowLine) return QSB_E_BADARG;
-  if (kind == kRowLine ? t < 1 : t < 0) return QSB_E_BADARG;
+  if (!t_dev && (kind == kRowLine ? t < 1 : t < 0)) return QSB_E_BADARG;
   if (rows == 0 || inner == 0) return 0;
   if (!x || !y || !param) return QSB_E_BADARG;
   if (kind == kRowLine && !aligned_to(param, 8)) return QSB_E_ALIGN;
@@ -442,6 +446,7 @@ static int row_quant_fused_impl(const float *x, float *y, float *param, float *d
   k.n_levels = (float)N;
   k.q_max = (float)(N - 1.0);
   k.t = t;
+  k.t_dev = reinterpret_cast<const long long *>(t_dev);
   switch (kind) {
     case kRowDecimal:
       return dispatch_rows<kRowDecimal, true>(x, y, param, decimal_out, mask, rows, inner, k, stream);
@@ -472,4 +477,16 @@ extern "C" int qsb_row_quant_fused_masked(const float *x, float *y, float *param
   if (!aligned_to(mask_dev, 8)) return QSB_E_UNSUPPORTED;
   return row_quant_fused_impl(x, y, param, decimal_out, mask_dev, kind, bits, float_zero_point, rows, inner,
                               t, stream);
+}
+
+// CUDA-graph form of the two entry points above: the EMA index is *t_dev + t_offset, read by the kernel
+// (launch arguments of a captured graph are frozen); mask_dev may be NULL.  The caller advances the counter.
+extern "C" int qsb_row_quant_fused_at(const float *x, float *y, float *param, float *decimal_out,
+                                      const uint8_t *mask_dev, int kind, int bits, int float_zero_point,
+                                      int64_t rows, int64_t inner, const int64_t *t_dev, int64_t t_offset,
+                                      void *stream) {
+  if (!t_dev) return QSB_E_BADARG;
+  if (mask_dev && !aligned_to(mask_dev, 8)) return QSB_E_UNSUPPORTED;
+  return row_quant_fused_impl(x, y, param, decimal_out, mask_dev, kind, bits, float_zero_point, rows, inner,
+                              t_offset, stream, t_dev);
 }

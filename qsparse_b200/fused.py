@@ -297,15 +297,23 @@ class _FusedWeightFn(torch.autograd.Function):
         from .quantize import AdaptiveQuantizer
         qcb = q.callback
         ctx.mask, ctx.rows, ctx.bits = mask, ws.shape[0], q.bits
+        counter = graphs.quantizer_counter(qcb, ws.device) if graphs.active() else None
         if type(qcb) is AdaptiveQuantizer:
-            graphs.require_eager("the fused weight chain quantize(prune(layer))")
-            y, _ = ops.row_quant_fused_(ws, q.weight.data, ops.ROW_LINE, q.bits, t_line, qcb.training, mask=mask)
+            if counter is not None:          # graph mode: this call's number is *counter + 1
+                y, _ = ops.row_quant_fused_(ws, q.weight.data, ops.ROW_LINE, q.bits, 1, qcb.training, mask=mask,
+                                            t_dev=counter)
+                counter.add_(1)
+            else:
+                y, _ = ops.row_quant_fused_(ws, q.weight.data, ops.ROW_LINE, q.bits, t_line, qcb.training, mask=mask)
             ctx.kind = "line"
         else:
             is_decimal = not qcb.use_float_scaler
-            graphs.require_eager("the fused weight chain quantize(prune(layer))")
-            y, dec = ops.row_quant_fused_(ws, q.weight.data, ops.ROW_DECIMAL if is_decimal else ops.ROW_SCALER,
-                                          q.bits, qcb.t, mask=mask)
+            kind = ops.ROW_DECIMAL if is_decimal else ops.ROW_SCALER
+            if counter is not None:
+                y, dec = ops.row_quant_fused_(ws, q.weight.data, kind, q.bits, 0, mask=mask, t_dev=counter)
+                counter.add_(1)
+            else:
+                y, dec = ops.row_quant_fused_(ws, q.weight.data, kind, q.bits, qcb.t, mask=mask)
             qcb.t += 1
             ctx.kind = "ste"
             ctx.is_decimal = is_decimal
@@ -365,6 +373,8 @@ def _fused_weight_step(p, q, raw):
         cb._t_mirror.wrote(cb.t, t + 1)
         p._n_updates.data.add_(1)
         p._n_mirror.wrote(p._n_updates, n + 1)
+        if graphs.active():
+            graphs.quantizer_counter(qcb, raw.device)          # (its device twin exists before the count moves)
         t_line = qcb._next_t() if type(qcb) is AdaptiveQuantizer else 0
         q._quantized = True
         q._n_updates.data.add_(1)

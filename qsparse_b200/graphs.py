@@ -12,10 +12,12 @@ themselves (``step_counter_dev`` of the C-ABI), so a replay computes exactly wha
         step.replay()
     step.sync_host()                                          # host counters catch up with the device
 
-Capturable routes: per-tensor Decimal / Scaler layers (activations, weights, inputs) and fused prune -> quantize
-activation sites (``convert(..., fuse=True)``), past their timeouts and schedules, with the default mask refresh
-(every step, never stopping).  Every other stateful route raises ``NotCapturable`` while graph mode is on rather
-than silently freezing a step index."""
+Capturable routes: every stock quantizer (Decimal / Scaler / Adaptive / Percentile; per tensor, per channel, the
+row-resident weight kernel, the fused weight chain), structured (channel-mask) prune layers and fused
+prune -> quantize activation sites (``convert(..., fuse=True)``), past their timeouts and schedules, with the default
+mask refresh (every step, never stopping).  Every other stateful route (unstructured running-average pruning,
+gradient / l0 importance, group-wise scale sharing before its clustering step, ...) raises ``NotCapturable`` while
+graph mode is on rather than silently freezing a step index."""
 from __future__ import annotations
 
 import contextlib
@@ -56,13 +58,21 @@ def require_eager(what: str):
 NO_REFRESH_INTERVAL = 1 << 30   # graph-mode kernels take the refresh INTERVAL: this one never comes round
 
 
+def host_index(quantizer) -> int:
+    """how many estimation calls the quantizer has made (``t``; AdaptiveQuantizer keeps a device Parameter like the
+    reference and the host count beside it)"""
+    t = quantizer.t
+    return int(getattr(quantizer, "_t_host", 0)) if isinstance(t, torch.Tensor) else int(t)
+
+
 def quantizer_counter(quantizer, device) -> torch.Tensor:
-    """the device twin of ``quantizer.t`` (created and set OUTSIDE capture by GraphedTrainStep)"""
+    """the int64 device twin of the quantizer's call count (created and set OUTSIDE capture by GraphedTrainStep);
+    kernels index their running mean by it, the caller (or the step kernel itself) advances it"""
     c = getattr(quantizer, "_t_dev", None)
     if c is None or c.device != device:
         if torch.cuda.is_current_stream_capturing():
             raise NotCapturable("a quantizer met its first graph-mode step during capture: run warm-up steps first")
-        c = torch.full((1,), int(quantizer.t), dtype=torch.int64, device=device)
+        c = torch.full((1,), host_index(quantizer), dtype=torch.int64, device=device)
         quantizer._t_dev = c
     return c
 
@@ -104,9 +114,9 @@ class GraphedTrainStep:
         self._check_steady_state()
         self.replays = 0
         for cb in self.qcbs:                                     # device twins of the host-only EMA indices
-            if hasattr(cb, "t") and isinstance(cb.t, int):
+            if hasattr(cb, "t"):
                 dev = next((p.device for p in model.parameters() if p.is_cuda), torch.device("cuda"))
-                cb._t_dev = torch.full((1,), cb.t, dtype=torch.int64, device=dev)
+                cb._t_dev = torch.full((1,), host_index(cb), dtype=torch.int64, device=dev)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with graph_mode(), torch.cuda.stream(side):
@@ -135,7 +145,7 @@ class GraphedTrainStep:
                 raise NotCapturable(f"PruneLayer {p.name!r} is still on its sparsity schedule")
 
     def _host_state(self) -> List[int]:
-        vals = [int(cb.t) for cb in self.qcbs if isinstance(getattr(cb, "t", None), int)]
+        vals = [host_index(cb) for cb in self.qcbs if hasattr(cb, "t")]
         vals += [int(q._t_mirror.get(q._n_updates)) for q in self.qlayers if q.initted]
         vals += [int(p._n_mirror.get(p._n_updates)) for p in self.players]
         vals += [int(cb._t()) for cb in self.pcbs]
@@ -145,8 +155,12 @@ class GraphedTrainStep:
     def _restore_host_state(self, vals: List[int]):
         it = iter(vals)
         for cb in self.qcbs:
-            if isinstance(getattr(cb, "t", None), int):
-                cb.t = next(it)
+            if hasattr(cb, "t"):
+                v = next(it)
+                if isinstance(cb.t, torch.Tensor):
+                    cb._t_host = v          # the device Parameter was (or will be) advanced by the graph itself
+                else:
+                    cb.t = v
         for q in self.qlayers:
             if q.initted:
                 q._t_mirror.wrote(q._n_updates, next(it))

@@ -266,9 +266,14 @@ def reduce_stats(x, layout: Layout, absmax=False, minmax=False, abssum=False, nn
 
 
 # ----------------------------------------------------------------------------- K4
-def scale_ema_(weight, absmax, bits: int, t: int):
+def scale_ema_(weight, absmax, bits: int, t: int, t_dev=None):
+    """``t_dev`` (an int64 device counter): the index is ``*t_dev + t``, read by the kernel (CUDA graphs)."""
     lib = N.load_library()
     N.require_cuda(weight, "weight")
+    if t_dev is not None:
+        N.check(lib.qsb_scale_ema_at(N.ptr(weight), N.ptr(absmax), c_int64(weight.numel()), c_int(bits), N.ptr(t_dev),
+                                     c_int64(t), N.stream_ptr(weight.device)), "qsb_scale_ema_at")
+        return weight
     N.check(lib.qsb_scale_ema(N.ptr(weight), N.ptr(absmax), c_int64(weight.numel()), c_int(bits), c_int64(t),
                               N.stream_ptr(weight.device)), "qsb_scale_ema")
     return weight
@@ -302,9 +307,13 @@ def group_mean(values, labels, groups: int):
     return out
 
 
-def lines_ema_(lines, mn, mx, t: int):
+def lines_ema_(lines, mn, mx, t: int, t_dev=None):
     lib = N.load_library()
     N.require_cuda(lines, "lines")
+    if t_dev is not None:
+        N.check(lib.qsb_lines_ema_at(N.ptr(lines), N.ptr(mn), N.ptr(mx), c_int64(lines.numel() // 2), N.ptr(t_dev),
+                                     c_int64(t), N.stream_ptr(lines.device)), "qsb_lines_ema_at")
+        return lines
     N.check(lib.qsb_lines_ema(N.ptr(lines), N.ptr(mn), N.ptr(mx), c_int64(lines.numel() // 2), c_int64(t),
                               N.stream_ptr(lines.device)), "qsb_lines_ema")
     return lines
@@ -322,7 +331,7 @@ def row_quant_supported(x, rows: int) -> bool:
     return inner % 8 == 0 and inner <= 16384 and x.data_ptr() % 32 == 0
 
 
-def row_quant_fused_(x, param, kind: int, bits: int, t: int, float_zero_point=True, mask=None):
+def row_quant_fused_(x, param, kind: int, bits: int, t: int, float_zero_point=True, mask=None, t_dev=None):
     """K8: per-row estimate (abs-max or min/max) -> EMA into ``param`` (in place) -> fake-quantize, one launch.
     x: [rows, ...] fp32 contiguous; param: [rows, 1] (scale) or [rows, 2] (lines).
     ``mask``: optional element prune mask of x's shape: estimate and quantize ``x * mask`` (the weight chain
@@ -338,6 +347,13 @@ def row_quant_fused_(x, param, kind: int, bits: int, t: int, float_zero_point=Tr
         N.require_cuda(mask, "mask")
         if mask.numel() != x.numel() or mask.dtype not in (torch.bool, torch.uint8) or not mask.is_contiguous():
             raise ValueError("mask must be a contiguous bool / uint8 tensor with x's number of elements")
+    if t_dev is not None:       # CUDA graphs: the EMA index is *t_dev + t, read by the kernel
+        N.check(lib.qsb_row_quant_fused_at(N.ptr(x), N.ptr(y), N.ptr(param), N.ptr(dec), N.ptr(mask), c_int(kind),
+                                           c_int(bits), c_int(1 if float_zero_point else 0), c_int64(rows),
+                                           c_int64(inner), N.ptr(t_dev), c_int64(t), N.stream_ptr(x.device)),
+                "qsb_row_quant_fused_at")
+        return y, dec
+    if mask is not None:
         N.check(lib.qsb_row_quant_fused_masked(N.ptr(x), N.ptr(y), N.ptr(param), N.ptr(dec), N.ptr(mask), c_int(kind),
                                                c_int(bits), c_int(1 if float_zero_point else 0), c_int64(rows),
                                                c_int64(inner), c_int64(t), N.stream_ptr(x.device)),

@@ -192,7 +192,7 @@ class LineQuantization(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
-        return (grad_output,) + (None,) * 5
+        return (grad_output,) + (None,) * 6
 
 
 class _RowFusedSte(torch.autograd.Function):
@@ -205,9 +205,13 @@ class _RowFusedSte(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, quantizer, bits, weight, xs):
         is_decimal = not quantizer.use_float_scaler
-        graphs.require_eager("the row-resident estimate + quantize kernel (channelwise=0 weights)")
-        y, dec = ops.row_quant_fused_(xs, weight.data, ops.ROW_DECIMAL if is_decimal else ops.ROW_SCALER, bits,
-                                      quantizer.t)
+        kind = ops.ROW_DECIMAL if is_decimal else ops.ROW_SCALER
+        if graphs.active():
+            counter = graphs.quantizer_counter(quantizer, xs.device)
+            y, dec = ops.row_quant_fused_(xs, weight.data, kind, bits, 0, t_dev=counter)
+            counter.add_(1)
+        else:
+            y, dec = ops.row_quant_fused_(xs, weight.data, kind, bits, quantizer.t)
         quantizer.t += 1
         ctx.backward_passthrough = quantizer.backward_passthrough
         ctx.notch = 1 if quantizer.flip_axis else 0
@@ -287,14 +291,17 @@ class _RowFusedLine(torch.autograd.Function):
     ONE launch; identity backward (ref quantize.py:393-430, :134-185)."""
 
     @staticmethod
-    def forward(ctx, input, bits, weight, xs, t, float_zero_point):
-        graphs.require_eager("the row-resident estimate + quantize kernel (AdaptiveQuantizer)")
-        y, _ = ops.row_quant_fused_(xs, weight.data, ops.ROW_LINE, bits, t, float_zero_point)
+    def forward(ctx, input, bits, weight, xs, t, float_zero_point, counter=None):
+        if counter is not None:      # graph mode: this call's number is *counter + 1
+            y, _ = ops.row_quant_fused_(xs, weight.data, ops.ROW_LINE, bits, 1, float_zero_point, t_dev=counter)
+            counter.add_(1)
+        else:
+            y, _ = ops.row_quant_fused_(xs, weight.data, ops.ROW_LINE, bits, t, float_zero_point)
         return y.view(input.shape)
 
     @staticmethod
     def backward(ctx, grad_output):
-        return (grad_output,) + (None,) * 5
+        return (grad_output,) + (None,) * 6
 
 
 def _row_fusable(quantizer, exact_type, x, weight, channel_index):
@@ -393,8 +400,12 @@ class DecimalQuantizer(BaseQuantizer):
                 weight = torch.zeros(wshape, dtype=torch.float32, device=x.device)
             target = weight.data if isinstance(weight, nn.Parameter) else weight
             assert tuple(target.shape) == tuple(wshape) and target.is_contiguous()
-            graphs.require_eager("DecimalQuantizer / ScalerQuantizer.optimize on this tensor layout")
-            ops.scale_ema_(target, absmax, bits, self.t)
+            if graphs.active():
+                counter = graphs.quantizer_counter(self, x.device)
+                ops.scale_ema_(target, absmax, bits, 0, t_dev=counter)
+                counter.add_(1)
+            else:
+                ops.scale_ema_(target, absmax, bits, self.t)
         self.t += 1
         return weight
 
@@ -417,6 +428,7 @@ class DecimalQuantizer(BaseQuantizer):
 
     def _group(self, scaler):
         if self.groups is None:
+            graphs.require_eager("the one-shot group-wise clustering step (host-side sklearn)")
             from sklearn.cluster import AgglomerativeClustering  # one-shot, host side (quantize.py:355-359)
 
             logging.danger(f"clustering {len(scaler)} channels into {self.group_num} groups")
@@ -478,8 +490,12 @@ class PercentileQuantizer(DecimalQuantizer):
                 weight = torch.zeros(wshape, dtype=torch.float32, device=x.device)
             target = weight.data if isinstance(weight, nn.Parameter) else weight
             assert tuple(target.shape) == tuple(wshape) and target.is_contiguous()
-            graphs.require_eager("PercentileQuantizer.optimize")
-            ops.scale_ema_(target, stat.contiguous(), bits, self.t)
+            if graphs.active():
+                counter = graphs.quantizer_counter(self, x.device)
+                ops.scale_ema_(target, stat.contiguous(), bits, 0, t_dev=counter)
+                counter.add_(1)
+            else:
+                ops.scale_ema_(target, stat.contiguous(), bits, self.t)
         self.t += 1
         return weight
 
@@ -525,9 +541,10 @@ class AdaptiveQuantizer(DecimalQuantizer):
         xs = _row_fusable(self, AdaptiveQuantizer, x, weight, channel_index)
         if xs is None:
             return None
+        counter = graphs.quantizer_counter(self, xs.device) if graphs.active() else None
         with torch.no_grad():
             t = self._next_t()
-        return _RowFusedLine.apply(x, bits, weight, xs, t, self.training)
+        return _RowFusedLine.apply(x, bits, weight, xs, t, self.training, counter)
 
     def optimize(self, x, bits, weight=None, channel_index=-1, batched=False, **kwargs):
         N.require_cuda(x, "x")
@@ -550,10 +567,14 @@ class AdaptiveQuantizer(DecimalQuantizer):
                 self._t_host = 1
                 return torch.stack([st["min"], st["max"]], dim=1).view(nch, 2)
             assert (nch, 2) == tuple(weight.shape)
+            counter = graphs.quantizer_counter(self, x.device) if graphs.active() else None
             t = self._next_t()
             target = weight.data if isinstance(weight, nn.Parameter) else weight
-            graphs.require_eager("AdaptiveQuantizer.optimize")
-            ops.lines_ema_(target, st["min"], st["max"], t)
+            if counter is not None:
+                ops.lines_ema_(target, st["min"], st["max"], 1, t_dev=counter)
+                counter.add_(1)
+            else:
+                ops.lines_ema_(target, st["min"], st["max"], t)
         return weight
 
 

@@ -298,9 +298,18 @@ class MagnitudePruningCallback(nn.Module):
     def _graph_mode_forward(self, x, sparsity, mask, t, name):
         """One step whose index lives on the device (qsparse_b200.graphs): only the stock structured route, with
         the default never-stopping mask refresh."""
-        if self.stop_mask_refresh != float("inf") or sparsity < 0 or kth_rank(sparsity, mask.numel()) >= mask.numel():
-            raise graphs.NotCapturable("a prune callback with stop_mask_refresh / an out-of-range sparsity")
         self._precomputed = None
+        if t >= self.stop_mask_refresh:
+            # magnitude and mask are frozen for good (t only grows): the step is a mask apply and a counter
+            out = apply_mask(x, mask)
+            self.t.data.add_(1)
+            self._t_mirror.wrote(self.t, t + 1)
+            if self.forward_hook is not None:
+                self.forward_hook(mask, name)
+            return out
+        if self.stop_mask_refresh != float("inf") or sparsity < 0 or kth_rank(sparsity, mask.numel()) >= mask.numel():
+            raise graphs.NotCapturable("a prune callback that will stop refreshing its mask later / an out-of-range "
+                                       "sparsity")
         out = self._fused_structured_step(x, sparsity, mask, t, True, counter=self.t.data)
         if out is None:
             graphs.require_eager("this prune callback (only the stock structured channel-mask step is capturable)")

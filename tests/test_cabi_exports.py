@@ -29,7 +29,7 @@ def test_python_binding_covers_header():
     from qsparse_b200 import _native
     assert sorted(_native.exported_symbols()) == declared_symbols()
     lib = _native.load_library()
-    assert lib.qsb_abi_version() == 2
+    assert lib.qsb_abi_version() == 3
     assert b"bad argument" in lib.qsb_error_string(-1)
 
 

@@ -602,10 +602,11 @@ def test_graph_mode_refuses_what_it_cannot_capture():
     qs.set_qsparse_options(log_on_created=False)
     dev = torch.device("cuda:0")
     with contextlib.redirect_stdout(io.StringIO()):
-        lin = qs.quantize(nn.Linear(64, 32), bits=8, channelwise=0, timeout=1).to(dev)   # K8: host step index
+        # unstructured running-average pruning (the one-pass K9 step) still takes a host step index
+        lin = qs.prune(nn.Linear(64, 32), sparsity=0.5, dimensions={0, 1}, start=1, interval=1, repetition=1).to(dev)
         lin.train()
         x = torch.randn(8, 64, device=dev)
-        for _ in range(3):
+        for _ in range(4):
             lin(x)
         with graphs.graph_mode(), pytest.raises(graphs.NotCapturable):
             lin(x)
@@ -614,3 +615,107 @@ def test_graph_mode_refuses_what_it_cannot_capture():
         fresh(x)
         with pytest.raises(graphs.NotCapturable):
             graphs.GraphedTrainStep(fresh, lambda: fresh(x))
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_graphed_step_covers_the_stock_routes(fuse):
+    """GraphedTrainStep over a net that exercises every capturable route at once — generic per-channel
+    Decimal / Scaler estimation (`qsb_scale_ema_at`), the row-resident weight kernel (`qsb_row_quant_fused_at`,
+    symmetric and Adaptive), per-channel Adaptive estimation on activations (`qsb_lines_ema_at`), the percentile
+    estimator, a stand-alone structured prune layer (the one-launch step with its own `t` as the device counter), a
+    quantize(prune(layer)) weight chain whose mask is frozen (plain and fused) — 12 eager steps + 3 warm-up + 5
+    replays against 20 eager steps: every parameter, mask, scale, line, magnitude and counter bit-equal."""
+    import qsparse_b200 as qs
+    from qsparse_b200 import graphs
+    from qsparse_b200.quantize import AdaptiveQuantizer, DecimalQuantizer, PercentileQuantizer, ScalerQuantizer
+    from qsparse_b200.sparse import MagnitudePruningCallback
+    qs.set_qsparse_options(log_on_created=False)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    dev = torch.device("cuda:0")
+    F = torch.nn.functional
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.in_q = qs.quantize(bits=8, channelwise=-1, timeout=2, callback=PercentileQuantizer(99.0))
+            self.c1 = qs.quantize(nn.Conv2d(3, 16, 3, padding=1), bits=8, channelwise=0, timeout=2,
+                                  callback=DecimalQuantizer())                    # rows of 27: generic estimation
+            self.c2 = qs.quantize(nn.Conv2d(16, 16, 3, padding=1), bits=8, channelwise=0, timeout=2)   # K8, Scaler
+            self.c3 = qs.quantize(nn.Conv2d(16, 16, 3, padding=1), bits=8, channelwise=1, timeout=2,
+                                  callback=ScalerQuantizer())                     # per input channel: generic
+            self.act_q = qs.quantize(bits=8, channelwise=1, timeout=2, callback=AdaptiveQuantizer())
+            self.p = qs.prune(sparsity=0.5, dimensions={1}, start=2, interval=1, repetition=2)
+            self.t_q = qs.quantize(bits=8, channelwise=-1, timeout=3, callback=DecimalQuantizer())
+            self.fc = qs.quantize(
+                qs.prune(nn.Linear(16 * 8 * 8, 32), sparsity=0.5, dimensions={0, 1}, start=1, interval=1, repetition=1,
+                         callback=MagnitudePruningCallback(stop_mask_refresh=4)),
+                bits=4, channelwise=0, timeout=2, callback=AdaptiveQuantizer())
+            self.fc2 = qs.quantize(nn.Linear(32, 10), bits=8, channelwise=0, timeout=2, callback=AdaptiveQuantizer())
+
+        def forward(self, x):
+            x = F.relu(self.c1(self.in_q(x)))
+            x = self.act_q(F.relu(self.c2(x)))
+            x = self.t_q(self.p(F.relu(self.c3(x))))
+            return self.fc2(F.relu(self.fc(x.flatten(1))))
+
+    def run(graph_from):
+        torch.manual_seed(5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = Net().to(dev)
+            if fuse:
+                qs.fuse_prune_quantize(model)
+        opt = torch.optim.SGD(model.parameters(), lr=0.05)
+        gen = torch.Generator(device=dev).manual_seed(9)
+        xs = torch.randn(20, 16, 3, 8, 8, device=dev, generator=gen)
+        ys = torch.randint(0, 10, (20, 16), device=dev, generator=gen)
+        sx, sy = xs[0].clone(), ys[0].clone()
+        model.train()
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = F.cross_entropy(model(sx), sy)
+            loss.backward()
+            opt.step()
+            return loss
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            i = 0
+            while i < 20:
+                if graph_from is not None and i == graph_from:
+                    feed = iter(range(i, i + 3))
+
+                    class _Two:
+                        n = 0
+
+                        def __call__(self):
+                            self.n += 1
+                            if self.n <= 3:
+                                j = next(feed)
+                                sx.copy_(xs[j]); sy.copy_(ys[j])
+                            return step()
+                    gs = graphs.GraphedTrainStep(model, _Two(), warmup=3)
+                    i += 3
+                    for _ in range(5):
+                        sx.copy_(xs[i]); sy.copy_(ys[i])
+                        gs.replay()
+                        i += 1
+                    gs.sync_host()
+                    continue
+                sx.copy_(xs[i]); sy.copy_(ys[i])
+                step()
+                i += 1
+        state = {k: v.clone() for k, v in model.state_dict().items()}
+        host = [graphs.host_index(m) for m in model.modules() if hasattr(m, "optimize") and hasattr(m, "t")]
+        return state, host
+
+    ref_state, ref_host = run(None)
+    got_state, got_host = run(12)
+    assert ref_host == got_host
+    assert sorted(ref_state) == sorted(got_state)
+    for k in ref_state:
+        a, b = ref_state[k], got_state[k]
+        assert a.dtype == b.dtype and torch.equal(a.view(torch.uint8) if a.dtype == torch.bool else a,
+                                                  b.view(torch.uint8) if b.dtype == torch.bool else b), k
