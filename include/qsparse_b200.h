@@ -406,6 +406,14 @@ int qsb_prune_unstructured_step_batched_hinted(
     uint8_t *const *mask_out, const int64_t *n, const int64_t *k, int count,
     int64_t t, float *thr_out_dev, uint32_t *hints_dev, void *workspace,
     int64_t workspace_bytes, void *stream);
+/* CUDA-graph form: the EMA index is *t_dev + t_offset, read by the kernels (the launch
+ * arguments of a captured graph are frozen); hints_dev may be NULL.  The caller advances
+ * the counter. */
+int qsb_prune_unstructured_step_batched_at(
+    float *const *magnitude, const float *const *x, float *const *y,
+    uint8_t *const *mask_out, const int64_t *n, const int64_t *k, int count,
+    const int64_t *t_dev, int64_t t_offset, float *thr_out_dev,
+    uint32_t *hints_dev, void *workspace, int64_t workspace_bytes, void *stream);
 
 int qsb_mask_from_threshold(const float *importance, int take_abs,
                             const float *thr_dev, uint8_t *mask_out, int64_t n,

@@ -73,6 +73,10 @@ _SIGNATURES = {
                                                            ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
                                                            ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int,
                                                            c_int64, _P, _P, _P, c_int64, _P]),
+    "qsb_prune_unstructured_step_batched_at": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                                       ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                                       ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int,
+                                                       _P, c_int64, _P, _P, _P, c_int64, _P]),
     "qsb_kth_dist_begin": (c_int, [_P, c_int64, _P]),
     "qsb_kth_dist_pass": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, ctypes.POINTER(c_void_p),
                                   ctypes.POINTER(c_int64), _P]),

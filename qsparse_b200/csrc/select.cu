@@ -90,7 +90,19 @@ struct SelState {
 // qsb_prune_unstructured_step_batched): extra per-call constants of the magnitude EMA.
 struct EmaC {
   float t_f, tp1, rcp;
+  const long long *t_dev;  // optional device step counter (CUDA graphs): t = *t_dev + t_off, resolved by the kernel
+  long long t_off;
 };
+// rcp: the host computes RN(1 / (t + 1)) with an IEEE division; __frcp_rn is the same correctly rounded value
+__device__ __forceinline__ EmaC ema_resolve(EmaC ec) {
+  if (ec.t_dev) {
+    const long long t = __ldg(ec.t_dev) + ec.t_off;
+    ec.t_f = (float)t;
+    ec.tp1 = (float)(t + 1);
+    ec.rcp = __frcp_rn(ec.tp1);
+  }
+  return ec;
+}
 static_assert(offsetof(SelState, lo) == 0 && offsetof(SelState, hi) == 4, "the partition kernel loads both pivots at once");
 
 // ---------------------------------------------------------------------------
@@ -1129,6 +1141,7 @@ __device__ __forceinline__ StepPtrs step_ptrs(const SegDesc &d) {
 template <int PER, bool STEP>
 __global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kSampleThreads)
     select_sample_kernel(const __grid_constant__ SegTable tab, int take_abs, EmaC ec) {
+  if constexpr (STEP) ec = ema_resolve(ec);
   const SegDesc &d = tab.d[blockIdx.y];
   uint4 *zb = reinterpret_cast<uint4 *>(d.hdr);
   constexpr int zv = (int)(kSelectHeaderBytes / 16);
@@ -1153,6 +1166,7 @@ __global__ void __launch_bounds__(QSB_THREADS, U == 2 ? 8 : 5)
 // fused prune step: EMA + partition + provisional mask / output in one streaming pass
 __global__ void __launch_bounds__(QSB_THREADS, 4)
     step_partition_kernel(const __grid_constant__ SegTable tab, EmaC ec) {
+  ec = ema_resolve(ec);
   constexpr int U = 2;
   constexpr int64_t kTile = (int64_t)QSB_THREADS * 8 * U;
   const SegDesc &d = tab.d[blockIdx.y];
@@ -1433,9 +1447,9 @@ extern "C" int64_t qsb_prune_step_workspace_bytes(const int64_t *n, int count) {
 static int prune_step_batched_impl(float *const *magnitude, const float *const *x, float *const *y,
                                    uint8_t *const *mask_out, const int64_t *n, const int64_t *k, int count,
                                    int64_t t, float *thr_out_dev, uint32_t *hints_dev, void *workspace,
-                                   int64_t workspace_bytes, void *stream_) {
+                                   int64_t workspace_bytes, void *stream_, const int64_t *t_dev = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (count < 0 || t < 0 || !magnitude || !x || !y || !mask_out || !n || !k || !thr_out_dev || !workspace)
+  if (count < 0 || (!t_dev && t < 0) || !magnitude || !x || !y || !mask_out || !n || !k || !thr_out_dev || !workspace)
     return QSB_E_BADARG;
   if (count == 0) return 0;
   for (int i = 0; i < count; ++i) {
@@ -1449,7 +1463,7 @@ static int prune_step_batched_impl(float *const *magnitude, const float *const *
   if (workspace_bytes < qsb_prune_step_workspace_bytes(n, count)) return QSB_E_WORKSPACE;
   const float tp1 = (float)(t + 1);
   volatile float rcp = 1.0f / tp1;  // IEEE round-to-nearest on the host, as in qsb_magnitude_ema_full
-  const EmaC ec{(float)t, tp1, rcp};
+  const EmaC ec{(float)t, tp1, rcp, reinterpret_cast<const long long *>(t_dev), (long long)t};
   unsigned char *hdr =
       reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   SegDesc group[kMaxSegs];
@@ -1518,6 +1532,17 @@ extern "C" int qsb_prune_unstructured_step_batched_hinted(
   if (hints_dev && !aligned_to(hints_dev, 4)) return QSB_E_ALIGN;
   return prune_step_batched_impl(magnitude, x, y, mask_out, n, k, count, t, thr_out_dev, hints_dev, workspace,
                                  workspace_bytes, stream);
+}
+
+// CUDA-graph form: the EMA index is *t_dev + t_offset, read by the kernels (hints_dev may be NULL)
+extern "C" int qsb_prune_unstructured_step_batched_at(
+    float *const *magnitude, const float *const *x, float *const *y, uint8_t *const *mask_out,
+    const int64_t *n, const int64_t *k, int count, const int64_t *t_dev, int64_t t_offset, float *thr_out_dev,
+    uint32_t *hints_dev, void *workspace, int64_t workspace_bytes, void *stream) {
+  if (!t_dev) return QSB_E_BADARG;
+  if (hints_dev && !aligned_to(hints_dev, 4)) return QSB_E_ALIGN;
+  return prune_step_batched_impl(magnitude, x, y, mask_out, n, k, count, t_offset, thr_out_dev, hints_dev,
+                                 workspace, workspace_bytes, stream, t_dev);
 }
 
 // ---------------------------------------------------------------------------

@@ -459,7 +459,7 @@ def prune_step_supported(magnitudes, xs, masks, outs) -> bool:
     return _multi_ok(magnitudes, xs, outs, masks) and all(x.dtype == torch.float32 for x in xs)
 
 
-def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int, hints=None):
+def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int, hints=None, t_dev=None):
     """K9: the whole unstructured running-average prune step of a set of tensors — magnitude EMA (in place),
     exact k-th value threshold, mask, ``out = x * mask`` — in ONE streaming pass plus a few small launches
     (17 B/elem instead of 29).  Returns the thresholds (float32 [L]).  Same results as
@@ -474,6 +474,13 @@ def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int, hi
     ws = N.workspace(dev, nbytes)
     if hints is not None:
         assert hints.dtype == torch.int32 and hints.numel() >= 8 * count and hints.is_contiguous()
+    if t_dev is not None:           # CUDA graphs: the EMA index is *t_dev + t, read by the kernels
+        N.check(lib.qsb_prune_unstructured_step_batched_at(
+            _ptr_array(magnitudes), _ptr_array(xs), _ptr_array(outs), _ptr_array(masks), ns, kk, c_int(count),
+            N.ptr(t_dev), c_int64(t), N.ptr(thr), N.ptr(hints), N.ptr(ws), c_int64(ws.numel()), N.stream_ptr(dev)),
+            "qsb_prune_unstructured_step_batched_at")
+        return thr
+    if hints is not None:
         N.check(lib.qsb_prune_unstructured_step_batched_hinted(
             _ptr_array(magnitudes), _ptr_array(xs), _ptr_array(outs), _ptr_array(masks), ns, kk, c_int(count),
             c_int64(t), N.ptr(thr), N.ptr(hints), N.ptr(ws), c_int64(ws.numel()), N.stream_ptr(dev)),

@@ -182,7 +182,7 @@ class MagnitudePruningCallback(nn.Module):
                 out = None
         return _MaskApply.apply(x, mask, out)
 
-    def _fused_unstructured_step(self, x, sparsity, mask, t):
+    def _fused_unstructured_step(self, x, sparsity, mask, t, counter=None):
         """update_magnitude + prune_and_update_mask of the stock unstructured running-average case in ONE
         streaming pass (K9, ``qsb_prune_unstructured_step_batched``: 17 B/elem instead of 29); None when
         the case is not the stock one (a subclass, gradient / l0 importance, a structured mask, ...)."""
@@ -208,8 +208,9 @@ class MagnitudePruningCallback(nn.Module):
             if getattr(self, "_hint_key", None) != key or self._hint.device != mag.device:
                 self._hint = ops.new_select_hints(1, mag.device)
                 self._hint_key = key
-            ops.prune_unstructured_step_batched_([mag], [xs], [mask.data], [out], [k], t,
-                                                 hints=self._hint if SELECT_HINTS else None)
+            # graph mode (`counter`): the kernels read the step index from the callback's own `t` Parameter
+            ops.prune_unstructured_step_batched_([mag], [xs], [mask.data], [out], [k], 0 if counter is not None else t,
+                                                 hints=self._hint if SELECT_HINTS else None, t_dev=counter)
         return _MaskApply.apply(x, mask, out)
 
     def _fused_structured_step(self, x, sparsity, mask, t, refresh, counter=None):
@@ -310,9 +311,18 @@ class MagnitudePruningCallback(nn.Module):
         if self.stop_mask_refresh != float("inf") or sparsity < 0 or kth_rank(sparsity, mask.numel()) >= mask.numel():
             raise graphs.NotCapturable("a prune callback that will stop refreshing its mask later / an out-of-range "
                                        "sparsity")
+        if self.mask_refresh_interval == 1 and t > 0:
+            out = self._fused_unstructured_step(x, sparsity, mask, t, counter=self.t.data)   # full-size masks (K9)
+            if out is not None:
+                self.t.data.add_(1)
+                self._t_mirror.wrote(self.t, t + 1)
+                if self.forward_hook is not None:
+                    self.forward_hook(mask, name)
+                return out
         out = self._fused_structured_step(x, sparsity, mask, t, True, counter=self.t.data)
         if out is None:
-            graphs.require_eager("this prune callback (only the stock structured channel-mask step is capturable)")
+            graphs.require_eager("this prune callback (the stock channel-mask step and the stock full-size-mask step "
+                                 "with a refresh every step are capturable)")
         self._t_mirror.wrote(self.t, t + 1)                 # the kernel advanced self.t itself
         if self.forward_hook is not None:
             self.forward_hook(mask, name)

@@ -602,8 +602,10 @@ def test_graph_mode_refuses_what_it_cannot_capture():
     qs.set_qsparse_options(log_on_created=False)
     dev = torch.device("cuda:0")
     with contextlib.redirect_stdout(io.StringIO()):
-        # unstructured running-average pruning (the one-pass K9 step) still takes a host step index
-        lin = qs.prune(nn.Linear(64, 32), sparsity=0.5, dimensions={0, 1}, start=1, interval=1, repetition=1).to(dev)
+        # l0 importance (a data-dependent gate between two statistics) still takes a host step index
+        from qsparse_b200.sparse import MagnitudePruningCallback
+        lin = qs.prune(nn.Linear(64, 32), sparsity=0.5, dimensions={0, 1}, start=1, interval=1, repetition=1,
+                       callback=MagnitudePruningCallback(l0=True)).to(dev)
         lin.train()
         x = torch.randn(8, 64, device=dev)
         for _ in range(4):
@@ -623,7 +625,8 @@ def test_graphed_step_covers_the_stock_routes(fuse):
     Decimal / Scaler estimation (`qsb_scale_ema_at`), the row-resident weight kernel (`qsb_row_quant_fused_at`,
     symmetric and Adaptive), per-channel Adaptive estimation on activations (`qsb_lines_ema_at`), the percentile
     estimator, a stand-alone structured prune layer (the one-launch step with its own `t` as the device counter), a
-    quantize(prune(layer)) weight chain whose mask is frozen (plain and fused) — 12 eager steps + 3 warm-up + 5
+    quantize(prune(layer)) weight chain whose mask is frozen (plain and fused), an unstructured running-average prune
+    layer (the one-pass step K9 through `qsb_prune_unstructured_step_batched_at`) — 12 eager steps + 3 warm-up + 5
     replays against 20 eager steps: every parameter, mask, scale, line, magnitude and counter bit-equal."""
     import qsparse_b200 as qs
     from qsparse_b200 import graphs
@@ -649,8 +652,10 @@ def test_graphed_step_covers_the_stock_routes(fuse):
             self.act_q = qs.quantize(bits=8, channelwise=1, timeout=2, callback=AdaptiveQuantizer())
             self.p = qs.prune(sparsity=0.5, dimensions={1}, start=2, interval=1, repetition=2)
             self.t_q = qs.quantize(bits=8, channelwise=-1, timeout=3, callback=DecimalQuantizer())
+            self.fc0 = qs.prune(nn.Linear(16 * 8 * 8, 64), sparsity=0.5, dimensions={0, 1}, start=2, interval=1,
+                                repetition=2)                                     # running-average, every step: K9
             self.fc = qs.quantize(
-                qs.prune(nn.Linear(16 * 8 * 8, 32), sparsity=0.5, dimensions={0, 1}, start=1, interval=1, repetition=1,
+                qs.prune(nn.Linear(64, 32), sparsity=0.5, dimensions={0, 1}, start=1, interval=1, repetition=1,
                          callback=MagnitudePruningCallback(stop_mask_refresh=4)),
                 bits=4, channelwise=0, timeout=2, callback=AdaptiveQuantizer())
             self.fc2 = qs.quantize(nn.Linear(32, 10), bits=8, channelwise=0, timeout=2, callback=AdaptiveQuantizer())
@@ -659,7 +664,7 @@ def test_graphed_step_covers_the_stock_routes(fuse):
             x = F.relu(self.c1(self.in_q(x)))
             x = self.act_q(F.relu(self.c2(x)))
             x = self.t_q(self.p(F.relu(self.c3(x))))
-            return self.fc2(F.relu(self.fc(x.flatten(1))))
+            return self.fc2(F.relu(self.fc(F.relu(self.fc0(x.flatten(1))))))
 
     def run(graph_from):
         torch.manual_seed(5)
@@ -715,7 +720,8 @@ def test_graphed_step_covers_the_stock_routes(fuse):
     got_state, got_host = run(12)
     assert ref_host == got_host
     assert sorted(ref_state) == sorted(got_state)
-    for k in ref_state:
-        a, b = ref_state[k], got_state[k]
-        assert a.dtype == b.dtype and torch.equal(a.view(torch.uint8) if a.dtype == torch.bool else a,
-                                                  b.view(torch.uint8) if b.dtype == torch.bool else b), k
+    bad = [k for k in ref_state
+           if ref_state[k].dtype != got_state[k].dtype or not torch.equal(
+               ref_state[k].view(torch.uint8) if ref_state[k].dtype == torch.bool else ref_state[k],
+               got_state[k].view(torch.uint8) if got_state[k].dtype == torch.bool else got_state[k])]
+    assert not bad, bad

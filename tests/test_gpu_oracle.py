@@ -1359,3 +1359,64 @@ def test_fuzz_vs_oracle():
         done += fz.step_flow_case(rng, case) is not None
         done += fz.row_quant_case(rng, case) is not None
     assert done >= 30
+
+
+def test_device_step_counter_forms_equal_host_index_forms():
+    """The CUDA-graph forms of the running means — `qsb_scale_ema_at`, `qsb_lines_ema_at`, `qsb_row_quant_fused_at`
+    (plain and masked, three kinds) and `qsb_prune_unstructured_step_batched_at` (small and sampled-route tensors,
+    with pivot hints) — read their step index from device memory and must equal the host-index forms bit for bit,
+    at index 0 and later ones, with non-zero offsets as well."""
+    from qsparse_b200 import ops
+    from qsparse_b200.util import kth_rank
+    rng = np.random.default_rng(77)
+    dev = torch.device("cuda")
+    for t in (0, 1, 2, 7, 1000):
+        for off in (0, 3):
+            ctr = torch.full((1,), t - off, dtype=torch.int64, device=dev)
+            w = cu(rng.uniform(0.01, 1, 37).astype(np.float32))
+            amax = cu(rng.uniform(0, 9, 37).astype(np.float32))
+            a, b = w.clone(), w.clone()
+            ops.scale_ema_(a, amax, 8, t)
+            ops.scale_ema_(b, amax, 8, off, t_dev=ctr)
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), ("scale", t, off)
+            if t >= 1:
+                lines = cu(rng.standard_normal((37, 2)).astype(np.float32))
+                mn, mx = cu(rng.standard_normal(37).astype(np.float32)), cu(rng.standard_normal(37).astype(np.float32))
+                a, b = lines.clone(), lines.clone()
+                ops.lines_ema_(a, mn, mx, t)
+                ops.lines_ema_(b, mn, mx, off, t_dev=ctr)
+                assert torch.equal(a.view(torch.int32), b.view(torch.int32)), ("lines", t, off)
+            x = cu((rng.standard_normal((48, 256)) * 0.3).astype(np.float32))
+            m = cu(rng.random((48, 256)) > 0.4)
+            for kind, width in ((ops.ROW_DECIMAL, 1), (ops.ROW_SCALER, 1), (ops.ROW_LINE, 2)):
+                if kind == ops.ROW_LINE and t < 1:
+                    continue
+                for mask in (None, m):
+                    p0 = cu(rng.uniform(0.01, 1, (48, width)).astype(np.float32))
+                    pa, pb = p0.clone(), p0.clone()
+                    ya, da = ops.row_quant_fused_(x, pa, kind, 4, t, True, mask=mask)
+                    yb, db = ops.row_quant_fused_(x, pb, kind, 4, off, True, mask=mask, t_dev=ctr)
+                    assert torch.equal(pa.view(torch.int32), pb.view(torch.int32)), ("row param", kind, t, off)
+                    assert torch.equal(ya.view(torch.int32), yb.view(torch.int32)), ("row y", kind, t, off)
+                    if da is not None:
+                        assert torch.equal(da, db)
+    # K9 over several steps: a sampled-route tensor (>= 2^22 elements) and small ones, hints on both sides
+    shapes = [(1 << 22) + 24, (512, 1024), (64, 32, 3, 3)]
+    ws = [cu((rng.standard_normal(s) * 0.02).astype(np.float32)) for s in shapes]
+
+    def fresh():
+        return ([torch.zeros_like(w) for w in ws], [torch.ones(w.shape, dtype=torch.bool, device="cuda") for w in ws],
+                [torch.empty_like(w) for w in ws], ops.new_select_hints(len(ws), dev))
+
+    (ma, ka, oa, ha), (mb, kb, ob, hb) = fresh(), fresh()
+    ks = [kth_rank(0.6, w.numel()) for w in ws]
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    for t in range(6):
+        ws = [w * 1.002 for w in ws]
+        ta = ops.prune_unstructured_step_batched_(ma, ws, ka, oa, ks, t, hints=ha)
+        tb = ops.prune_unstructured_step_batched_(mb, ws, kb, ob, ks, 0, hints=hb, t_dev=ctr)
+        ctr.add_(1)
+        assert torch.equal(ta, tb), t
+        for i in range(len(ws)):
+            assert torch.equal(ma[i].view(torch.int32), mb[i].view(torch.int32)), (t, i, "magnitude")
+            assert torch.equal(ka[i], kb[i]) and torch.equal(oa[i].view(torch.int32), ob[i].view(torch.int32)), (t, i)
