@@ -125,5 +125,31 @@ for t in range(5):
 hints9 = ops.new_select_hints(len(xs9), dev)
 for t in range(2, 6):
     ops.prune_unstructured_step_batched_(mg9, xs9, mk9, ot9, [x_.numel() // 2 for x_ in xs9], t, hints=hints9)
+# device-step-counter (CUDA-graph) forms of the running means, with offsets, and a captured + replayed sequence
+ctr = torch.full((1,), 2, dtype=torch.int64, device=dev)
+ops.scale_ema_(torch.rand(37, device=dev), torch.rand(37, device=dev), 8, 1, t_dev=ctr)
+ops.lines_ema_(torch.rand(37, 2, device=dev), torch.rand(37, device=dev), torch.rand(37, device=dev), 1, t_dev=ctr)
+xr = torch.randn(37, 256, device=dev, generator=g) * 0.05
+mk = torch.rand(37, 256, device=dev, generator=g) > 0.5
+for kind, w in ((ops.ROW_LINE, 2), (ops.ROW_SCALER, 1), (ops.ROW_DECIMAL, 1)):
+    ops.row_quant_fused_(xr, torch.zeros(37, w, device=dev), kind, 4, 1, t_dev=ctr)
+    ops.row_quant_fused_(xr, torch.zeros(37, w, device=dev), kind, 4, 1, mask=mk, t_dev=ctr)
+for t in range(2):
+    ops.prune_unstructured_step_batched_(mg9, xs9, mk9, ot9, [x_.numel() // 2 for x_ in xs9], 0, hints=hints9, t_dev=ctr)
+    ctr.add_(1)
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+wq, pq = torch.zeros(37, 1, device=dev), torch.rand(37, device=dev)
+with torch.cuda.stream(side):
+    ops.row_quant_fused_(xr, wq, ops.ROW_SCALER, 4, 0, t_dev=ctr)
+    ops.scale_ema_(pq, torch.rand(37, device=dev), 8, 0, t_dev=ctr)
+torch.cuda.current_stream().wait_stream(side)
+gr = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gr):
+    ops.row_quant_fused_(xr, wq, ops.ROW_SCALER, 4, 0, t_dev=ctr)
+    ops.scale_ema_(pq, pq.clone(), 8, 0, t_dev=ctr)
+    ctr.add_(1)
+for _ in range(3):
+    gr.replay()
 torch.cuda.synchronize()
 print("sanitize target done")
