@@ -67,6 +67,16 @@ class PruneQuantize(nn.Module):
     def _layout(self, x):
         return N.channel_layout(x.shape, self.channel_index)
 
+    def _step_counter(self, device):
+        """device twin of ``t_prune`` for graph mode (created outside capture by ``GraphedTrainStep``)"""
+        c = getattr(self, "_t_dev", None)
+        if c is None or c.device != device:
+            if torch.cuda.is_current_stream_capturing():
+                raise graphs.NotCapturable("PruneQuantize met its first graph-mode step during capture")
+            c = torch.full((1,), int(self.t_prune), dtype=torch.int64, device=device)
+            self._t_dev = c
+        return c
+
     def _allocate(self, x, channels):
         dev = x.device
         self.magnitude = nn.Parameter(torch.zeros(channels, device=dev), requires_grad=False)
@@ -96,6 +106,7 @@ class PruneQuantize(nn.Module):
             k = kth_rank(self.sparsity, ch)
             if isinstance(self._exchange, StatExchange):
                 # NCCL fallback: finalize into the row, all-gather, combine rows in the kernel
+                graphs.require_eager("PruneQuantize over the NCCL all-gather fallback")
                 ex = self._exchange
                 ops.reduce_stats(xs, layout, abssum=True, absmax=True,
                                  out={"abssum": ex.row.abssum, "absmax": ex.row.absmax})
@@ -109,7 +120,16 @@ class PruneQuantize(nn.Module):
                 world = self._p2p.world if self._p2p is not None else 1
                 grp = self._p2p.handle if self._p2p is not None else None
                 stamp = self._p2p.next_stamp() if self._p2p is not None else 1
-                if ch <= ops.FUSED_STEP_MAX_CHANNELS:
+                if graphs.active():
+                    # graph mode: the step index (and the exchange stamp) come from a device counter that the
+                    # kernel reads and advances itself
+                    if ch > ops.FUSED_STEP_MAX_CHANNELS:
+                        raise graphs.NotCapturable(f"PruneQuantize with more than {ops.FUSED_STEP_MAX_CHANNELS} channels")
+                    ops.reduce_prune_quant_step(xs, layout, self.magnitude.data, self.mask.data, self.scale.data,
+                                                self.decimal, float(outer * inner * world), 0, mode,
+                                                self.mask_refresh_interval, k, self.bits, self.t_quant - t, True,
+                                                group=grp, step_counter=self._step_counter(xs.device))
+                elif ch <= ops.FUSED_STEP_MAX_CHANNELS:
                     # ONE kernel: reduction whose last CTA finalizes, exchanges and derives the parameters
                     ops.reduce_prune_quant_step(xs, layout, self.magnitude.data, self.mask.data, self.scale.data,
                                                 self.decimal, float(outer * inner * world), t, mode, refresh, k,
@@ -119,7 +139,7 @@ class PruneQuantize(nn.Module):
                     ops.prune_quant_step_params(self.magnitude.data, self.mask.data, self.scale.data, self.decimal,
                                                 ws, layout, float(outer * inner * world), t, mode, refresh, k,
                                                 self.bits, self.t_quant, True, group=grp, step_stamp=stamp)
-                if self._p2p is not None and t % self.check_every == 0:
+                if self._p2p is not None and t % self.check_every == 0 and not graphs.active():
                     self._p2p.check()     # raises when an earlier step timed out waiting for a peer
             self.t_prune += 1
             self.t_quant += 1

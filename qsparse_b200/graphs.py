@@ -112,6 +112,11 @@ class GraphedTrainStep:
         self.model, self.step_fn = model, step_fn
         self.qcbs, self.qlayers, self.players, self.pcbs = _stateful(model)
         self.fused_sites = [m for m in model.modules() if "fused_steps" in type(m).__dict__ or "fused_steps" in vars(m)]
+        from .fused import PruneQuantize
+        self.pq_modules = [m for m in model.modules() if isinstance(m, PruneQuantize)]
+        for m in self.pq_modules:
+            if hasattr(m, "magnitude"):
+                m._t_dev = torch.full((1,), int(m.t_prune), dtype=torch.int64, device=m.magnitude.device)
         self._check_steady_state()
         self.replays = 0
         for cb in self.qcbs:                                     # device twins of the host-only EMA indices
@@ -151,6 +156,8 @@ class GraphedTrainStep:
         vals += [int(p._n_mirror.get(p._n_updates)) for p in self.players]
         vals += [int(cb._t()) for cb in self.pcbs]
         vals += [int(m.fused_steps) for m in self.fused_sites]
+        for m in self.pq_modules:
+            vals += [int(m.t_prune), int(m.t_quant)]
         return vals
 
     def _restore_host_state(self, vals: List[int]):
@@ -171,6 +178,8 @@ class GraphedTrainStep:
             cb._t_mirror.wrote(cb.t, next(it))
         for m in self.fused_sites:
             m.fused_steps = next(it)
+        for m in self.pq_modules:
+            m.t_prune, m.t_quant = next(it), next(it)
 
     # ---- use ---------------------------------------------------------------------------------------------------
     def replay(self):

@@ -725,3 +725,70 @@ def test_graphed_step_covers_the_stock_routes(fuse):
                ref_state[k].view(torch.uint8) if ref_state[k].dtype == torch.bool else ref_state[k],
                got_state[k].view(torch.uint8) if got_state[k].dtype == torch.bool else got_state[k])]
     assert not bad, bad
+
+
+def test_prune_quantize_module_in_a_cuda_graph():
+    """fused.PruneQuantize (the module bench.py times as `module_api`): 4 eager steps + 2 warm-up + 4 replays equal
+    10 eager steps bit for bit (magnitude, mask, scale, outputs, input gradients, host counters)."""
+    from qsparse_b200 import graphs
+    from qsparse_b200.fused import PruneQuantize
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(4)
+    xs = torch.relu(torch.randn(10, 8, 32, 14, 14, device=dev, generator=gen))
+    gs_ = torch.randn(10, 8, 32, 14, 14, device=dev, generator=gen)
+
+    def run(graph):
+        layer = PruneQuantize(sparsity=0.75, bits=8).train()
+        sx = xs[0].clone().requires_grad_(True)
+        sg = gs_[0].clone()
+        outs = []
+
+        def step():
+            sx.grad = None
+            y = layer(sx)
+            y.backward(sg)
+            return y
+
+        i = 0
+        while i < 10:
+            with torch.no_grad():
+                sx.copy_(xs[i]); sg.copy_(gs_[i])
+            if graph and i == 4:
+                feed = iter((4, 5))
+
+                class _Two:
+                    n = 0
+
+                    def __call__(self):
+                        self.n += 1
+                        if self.n <= 2:
+                            j = next(feed)
+                            with torch.no_grad():
+                                sx.copy_(xs[j]); sg.copy_(gs_[j])
+                        return step()
+                g = graphs.GraphedTrainStep(layer, _Two(), warmup=2)
+                i = 6
+                for _ in range(4):
+                    with torch.no_grad():
+                        sx.copy_(xs[i]); sg.copy_(gs_[i])
+                    y = g.replay()
+                    outs.append((y.detach().clone(), sx.grad.clone()))
+                    i += 1
+                g.sync_host()
+                continue
+            y = step()
+            if i >= 6:
+                outs.append((y.detach().clone(), sx.grad.clone()))
+            i += 1
+        return layer, outs
+
+    ref, ref_outs = run(False)
+    got, got_outs = run(True)
+    assert (ref.t_prune, ref.t_quant) == (got.t_prune, got.t_quant) == (10, 10)
+    for name in ("magnitude", "mask", "scale"):
+        a, b = getattr(ref, name).data, getattr(got, name).data
+        assert torch.equal(a.view(torch.uint8) if a.dtype == torch.bool else a.view(torch.int32),
+                           b.view(torch.uint8) if b.dtype == torch.bool else b.view(torch.int32)), name
+    assert len(ref_outs) == len(got_outs) == 4
+    for (ya, ga), (yb, gb) in zip(ref_outs, got_outs):
+        assert torch.equal(ya.view(torch.int32), yb.view(torch.int32)) and torch.equal(ga.view(torch.int32), gb.view(torch.int32))
