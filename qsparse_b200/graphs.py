@@ -102,7 +102,10 @@ class GraphedTrainStep:
 
     ``warmup`` graph-mode steps run eagerly first (on a side stream, as CUDA graph capture requires): they allocate
     every workspace and put the device counters in charge.  They are REAL training steps.  The capture pass itself
-    executes nothing on the device; the host-side counters it advanced are rolled back.  ``replay()`` runs one
+    executes nothing on the device; the host-side counters it advanced are rolled back.  (As for any whole-step
+    capture in PyTorch: drop references to outputs of earlier eager steps that still carry an autograd graph — a live
+    graph pins the leaves' gradient accumulators to the stream they first ran on and invalidates the capture.)
+    ``replay()`` runs one
     step; ``sync_host()`` brings the host-side counters (``callback.t``, the counter mirrors) up to date — call it
     before going back to eager steps, ``state_dict()`` needs nothing (the device state is always current)."""
 

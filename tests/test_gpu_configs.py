@@ -776,9 +776,10 @@ def test_prune_quantize_module_in_a_cuda_graph():
                     i += 1
                 g.sync_host()
                 continue
-            y = step()
-            if i >= 6:
-                outs.append((y.detach().clone(), sx.grad.clone()))
+            y = step().detach()       # (a live autograd graph of an eager step would pin sx's AccumulateGrad node
+            if i >= 6:                # to the default stream and invalidate the capture)
+                outs.append((y.clone(), sx.grad.clone()))
+            del y
             i += 1
         return layer, outs
 
