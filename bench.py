@@ -309,6 +309,19 @@ def run_ours(args):
         ops.fq_pow2_fwd(x, st["dec"], LAYOUT, mask=st["mask"], out=y)
 
     graph = None
+    graph_many = None            # the same step captured `steps_per_graph` times back to back
+    per_graph = max(int(args.steps_per_graph), 1)
+
+    def run_steps(count):
+        """`count` steps: whole multi-step graphs first (programmatic dependent launch then also overlaps the
+        boundary between two STEPS, which a graph launch does not), single-step replays for the remainder"""
+        if graph_many is not None:
+            for _ in range(count // per_graph):
+                graph_many.replay()
+            state["t"] += (count // per_graph) * per_graph
+            count %= per_graph
+        for _ in range(count):
+            step()
 
     def step():
         if graph is not None:
@@ -350,17 +363,22 @@ def run_ours(args):
             fwd_graphable()
             bwd()
         graph = g_
+        if per_graph > 1:
+            gm_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gm_):
+                for _ in range(per_graph):
+                    fwd_graphable()
+                    bwd()
+            graph_many = gm_
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        step()
+    run_steps(warm + (-warm) % per_graph if graph_many is not None else warm)   # (whole graphs: also warms graph_many)
     barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall = time.perf_counter()
     start.record()
-    for _ in range(args.steps):
-        step()           # nothing but the step's launches between the two events (an event record between
-    end.record()         # two kernels would also undo their programmatic-dependent-launch overlap)
+    run_steps(args.steps)  # nothing but the steps' launches between the two events (an event record between
+    end.record()           # two kernels would also undo their programmatic-dependent-launch overlap)
     barrier()
     t_wall = time.perf_counter() - t_wall
     ms = start.elapsed_time(end)
@@ -393,8 +411,9 @@ def run_ours(args):
     outputs_verified = bool(torch.equal(y_chk, y) and torch.equal(gx_chk, gx))
     del y_chk, gx_chk
     launches_per_step = 3 if ex is None else 5
-    launch_mode = ("CUDA graph [reduce+finalize+exchange+params, forward, backward]" if graph is not None
-                   else "eager launches")
+    launch_mode = ("CUDA graph [reduce+finalize+exchange+params, forward, backward]"
+                   + (f" x {per_graph} steps per graph launch (the remainder of --steps as single-step graphs)"
+                      if graph_many is not None else "") if graph is not None else "eager launches")
     barrier()
 
     # ---- per-kernel pass: the same steps again, now with CUDA events around each of the three launches
@@ -634,6 +653,7 @@ def run_ours(args):
         "exchange_error": exchange_error,
         "multi_gpu_parity": parity,
         "launch_mode": launch_mode,
+        "steps_per_graph": per_graph if graph_many is not None else 1,
         "outputs_verified": outputs_verified,
         "module_api": module_api,
         "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": 2 * n * 4 * world,
@@ -801,6 +821,8 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=8, help="batch chunks of the host-buffer pipeline")
     ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
                     help="1: launch the step's kernels with programmatic stream serialization (tuning key 12)")
+    ap.add_argument("--steps-per-graph", type=int, default=4,
+                    help="steps captured back to back in one CUDA graph (1: one graph launch per step)")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: the forward half of the step is one captured CUDA graph (default)")
     ap.add_argument("--row-variant", type=int, default=None, choices=[0, 2], help="development: tuning key 17")
