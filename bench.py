@@ -371,7 +371,9 @@ def run_ours(args):
                     bwd()
             graph_many = gm_
     warm = max(args.warmup, 3)
-    run_steps(warm + (-warm) % per_graph if graph_many is not None else warm)   # (whole graphs: also warms graph_many)
+    if graph_many is not None:
+        warm += (-warm) % per_graph      # whole multi-step graphs, so that this graph is warm too (reported as run)
+    run_steps(warm)
     barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
