@@ -132,6 +132,7 @@ class GraphedTrainStep:
             for _ in range(max(int(warmup), 1)):
                 step_fn()
         torch.cuda.current_stream().wait_stream(side)
+        self._check_steady_state(after_warmup=True)
         before = self._host_state()
         self.graph = torch.cuda.CUDAGraph()
         with graph_mode(), torch.cuda.graph(self.graph):
@@ -141,7 +142,9 @@ class GraphedTrainStep:
         self._restore_host_state(before)
 
     # ---- host-side state that a captured step would have advanced -------------------------------------------
-    def _check_steady_state(self):
+    def _check_steady_state(self, after_warmup: bool = False):
+        """every layer the step uses is past its timeout / schedule (run again after the warm-up steps: a layer
+        that met its first input there is initialised by now and fails the test)"""
         for q in self.qlayers:
             if not q.initted or q.timeout <= 0:
                 continue
