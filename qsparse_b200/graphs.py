@@ -186,6 +186,8 @@ class GraphedTrainStep:
             m.fused_steps = next(it)
         for m in self.pq_modules:
             m.t_prune, m.t_quant = next(it), next(it)
+            if getattr(m, "_p2p", None) is not None:
+                m._p2p.stamp = m.t_prune      # eager steps stamp their peer packets t_prune + 1, like the kernel
 
     # ---- use ---------------------------------------------------------------------------------------------------
     def replay(self):
