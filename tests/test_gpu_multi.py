@@ -233,3 +233,82 @@ def test_weight_set_step_equals_magnitude_callback():
     for k in (0, v.numel() // 3, v.numel() - 1):
         assert torch.equal(parallel.sharded_kth_value(v, k), ops.kth_value(v, k))
         assert parallel.sharded_kth_value(v, k).item() == torch.sort(v).values[k].item()
+
+
+def _graph_worker(rank, world, port, out):
+    """2 eager steps, then GraphedTrainStep (2 warm-up steps, capture, 3 replays), sync_host, 1 more eager step:
+    the peer exchange runs from inside the captured kernel with stamps derived from the device counter."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from qsparse_b200 import graphs
+    from qsparse_b200.fused import PruneQuantize
+    C, per_rank = 48, 6
+    full = _make_batch(world, per_rank, C)
+    shard = torch.from_numpy(full[rank * per_rank:(rank + 1) * per_rank]).cuda()
+    layer = PruneQuantize(sparsity=0.5, bits=8)
+    layer.train()
+    sx = shard.clone()
+    ys = []
+    for t in range(2):
+        sx.copy_(shard * (1 + 0.1 * t))
+        ys.append(layer(sx).cpu().numpy())
+    feed = iter((2, 3))
+
+    class _Two:
+        n = 0
+
+        def __call__(self):
+            self.n += 1
+            if self.n <= 2:
+                sx.copy_(shard * (1 + 0.1 * next(feed)))
+            y = layer(sx)
+            if self.n <= 2:
+                ys.append(y.cpu().numpy())
+            return y
+    with torch.no_grad():
+        gs = graphs.GraphedTrainStep(layer, _Two(), warmup=2)
+        for t in range(4, 7):
+            sx.copy_(shard * (1 + 0.1 * t))
+            ys.append(gs.replay().cpu().numpy())
+        gs.sync_host()
+        sx.copy_(shard * 1.7)
+        ys.append(layer(sx).cpu().numpy())                  # eager again: the stamp sequence continues
+    res = dict(rank=rank, p2p=layer._p2p is not None, err=layer._p2p.error() if layer._p2p else 0,
+               mask=layer.mask.cpu().numpy(), scale=layer.scale.cpu().numpy(), mag=layer.magnitude.cpu().numpy(), y=ys,
+               t=(layer.t_prune, layer.t_quant))
+    out.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_graphed_step_equals_single_process():
+    import torch.multiprocessing as mp
+    from qsparse_b200.fused import PruneQuantize
+    world, C, per_rank = 2, 48, 6
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_graph_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out.get(timeout=180) for _ in range(world)], key=lambda r: r["rank"])
+    for p in procs:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    full = _make_batch(world, per_rank, C)
+    single = PruneQuantize(sparsity=0.5, bits=8)
+    single.train()
+    factors = [1 + 0.1 * t for t in range(7)] + [1.7]
+    ys = [single(torch.from_numpy(full * np.float32(f)).cuda()).cpu().numpy() for f in factors]
+    for r in results:
+        assert r["err"] == 0 and r["t"] == (8, 8)
+        assert np.array_equal(r["mask"], single.mask.cpu().numpy())
+        assert np.array_equal(r["scale"], single.scale.cpu().numpy())
+        assert np.allclose(r["mag"], single.magnitude.cpu().numpy(), rtol=1e-6)
+        assert len(r["y"]) == 8
+        for t in range(8):
+            lo, hi = r["rank"] * per_rank, (r["rank"] + 1) * per_rank
+            assert np.array_equal(r["y"][t], ys[t][lo:hi]), t
