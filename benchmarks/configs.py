@@ -394,7 +394,22 @@ def run_c4(args, env):
     for _ in range(3):
         batched_mod_step()
     ms_bmod = back_to_back(torch, batched_mod_step, min(steps, 50), 3, world, dev)
-    del mods, pruner
+    del pruner
+    # ... and with the per-layer module accesses of one step captured into ONE CUDA graph (GraphedTrainStep: the
+    # one-pass kernels read the step index from each callback's own `t` Parameter)
+    ms_gmod = None
+    try:
+        def access_all():
+            with torch.no_grad():
+                for m in mods:
+                    m.weight
+        gs = q.GraphedTrainStep(mods, access_all, warmup=3)
+        ms_gmod = back_to_back(torch, gs.replay, min(steps, 100), 3, world, dev)
+        gs.sync_host()
+    except Exception as exc:       # reported, not fatal: the line then carries no graphed figure
+        ms_gmod = None
+        graph_note = f"{type(exc).__name__}: {exc}"
+    del mods
 
     # e2e: pinned host weights in, pruned weights + masks out
     hws = [torch.empty(w.shape, dtype=torch.float32).pin_memory() for w in ws]
@@ -462,6 +477,10 @@ def run_c4(args, env):
                                          "of 29 thresholds + replicated multi-tensor mask/apply"},
         "module_api": {"api": "MagnitudePruningCallback(running_average=True)(w, sparsity, mask) per layer",
                        "ms_per_step": round(ms_mod, 5), "value": round(world * 29 * n / (ms_mod * 1e-3) / 1e9, 2)},
+        "module_api_one_cuda_graph": (None if ms_gmod is None else
+                                      {"api": "the 29 prune()-wrapped modules' weight accesses of one step as ONE CUDA graph "
+                                              "(qsparse_b200.GraphedTrainStep)", "ms_per_step": round(ms_gmod, 5),
+                                       "value": round(world * 29 * n / (ms_gmod * 1e-3) / 1e9, 2)}),
         "module_api_batched": {"api": "WeightSetPruner(model).step() + every prune()-wrapped module's .weight",
                                "ms_per_step": round(ms_bmod, 5),
                                "value": round(world * 29 * n / (ms_bmod * 1e-3) / 1e9, 2)},

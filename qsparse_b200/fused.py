@@ -271,7 +271,8 @@ class FusedPruneQuantSequential(nn.Sequential):
                                                f"{ops.FUSED_STEP_MAX_CHANNELS} channels or a stopping mask refresh")
                 ops.reduce_prune_quant_step(xs, layout, magnitude, p.mask.data.view(-1), q.weight.data.view(-1),
                                             decimal, float(outer * inner), 0, mode, cb.mask_refresh_interval,
-                                            kth_rank(sparsity, ch), q.bits, qcb.t - t, True, step_counter=cb.t.data)
+                                            kth_rank(sparsity, ch), q.bits, qcb.t - t, True,
+                                            step_counter=graphs.callback_counter(cb, x.device))
             elif ch <= ops.FUSED_STEP_MAX_CHANNELS:
                 ops.reduce_prune_quant_step(xs, layout, magnitude, p.mask.data.view(-1), q.weight.data.view(-1),
                                             decimal, float(outer * inner), t, mode, refresh, k, q.bits, qcb.t, True)

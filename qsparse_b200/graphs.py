@@ -78,6 +78,21 @@ def quantizer_counter(quantizer, device) -> torch.Tensor:
     return c
 
 
+def callback_counter(callback, device) -> torch.Tensor:
+    """the prune callback's own ``t`` Parameter as the device step counter.  Like the reference's, it is created on
+    the host and only follows ``model.cuda()``; a callback of a module that was never moved keeps it there (its eager
+    steps never need it on the device) — move it now, outside capture."""
+    t = callback.t
+    if t.device != device:
+        if torch.cuda.is_current_stream_capturing():
+            raise NotCapturable("a prune callback's step counter is not on the device: run warm-up steps first")
+        t.data = t.data.to(device)
+        callback._t_mirror._id = None          # re-read once (the Parameter's storage changed)
+    if t.dtype != torch.int64:
+        raise NotCapturable("the prune callback's step counter is not int64")
+    return t.data
+
+
 def _stateful(model: nn.Module):
     from .quantize import BaseQuantizer, QuantizeLayer
     from .sparse import MagnitudePruningCallback, PruneLayer

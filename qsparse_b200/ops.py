@@ -271,6 +271,7 @@ def scale_ema_(weight, absmax, bits: int, t: int, t_dev=None):
     lib = N.load_library()
     N.require_cuda(weight, "weight")
     if t_dev is not None:
+        N.require_cuda(t_dev, "t_dev")
         N.check(lib.qsb_scale_ema_at(N.ptr(weight), N.ptr(absmax), c_int64(weight.numel()), c_int(bits), N.ptr(t_dev),
                                      c_int64(t), N.stream_ptr(weight.device)), "qsb_scale_ema_at")
         return weight
@@ -311,6 +312,7 @@ def lines_ema_(lines, mn, mx, t: int, t_dev=None):
     lib = N.load_library()
     N.require_cuda(lines, "lines")
     if t_dev is not None:
+        N.require_cuda(t_dev, "t_dev")
         N.check(lib.qsb_lines_ema_at(N.ptr(lines), N.ptr(mn), N.ptr(mx), c_int64(lines.numel() // 2), N.ptr(t_dev),
                                      c_int64(t), N.stream_ptr(lines.device)), "qsb_lines_ema_at")
         return lines
@@ -348,6 +350,7 @@ def row_quant_fused_(x, param, kind: int, bits: int, t: int, float_zero_point=Tr
         if mask.numel() != x.numel() or mask.dtype not in (torch.bool, torch.uint8) or not mask.is_contiguous():
             raise ValueError("mask must be a contiguous bool / uint8 tensor with x's number of elements")
     if t_dev is not None:       # CUDA graphs: the EMA index is *t_dev + t, read by the kernel
+        N.require_cuda(t_dev, "t_dev")
         N.check(lib.qsb_row_quant_fused_at(N.ptr(x), N.ptr(y), N.ptr(param), N.ptr(dec), N.ptr(mask), c_int(kind),
                                            c_int(bits), c_int(1 if float_zero_point else 0), c_int64(rows),
                                            c_int64(inner), N.ptr(t_dev), c_int64(t), N.stream_ptr(x.device)),
@@ -475,6 +478,7 @@ def prune_unstructured_step_batched_(magnitudes, xs, masks, outs, ks, t: int, hi
     if hints is not None:
         assert hints.dtype == torch.int32 and hints.numel() >= 8 * count and hints.is_contiguous()
     if t_dev is not None:           # CUDA graphs: the EMA index is *t_dev + t, read by the kernels
+        N.require_cuda(t_dev, "t_dev")
         N.check(lib.qsb_prune_unstructured_step_batched_at(
             _ptr_array(magnitudes), _ptr_array(xs), _ptr_array(outs), _ptr_array(masks), ns, kk, c_int(count),
             N.ptr(t_dev), c_int64(t), N.ptr(thr), N.ptr(hints), N.ptr(ws), c_int64(ws.numel()), N.stream_ptr(dev)),
@@ -607,6 +611,8 @@ def reduce_prune_quant_step(x, layout: Layout, magnitude, mask, scale, decimal_o
     ``arrival``: a caller-owned zeroed int32 tensor (default: one per device and stream, created on first
     use — pass your own when capturing a CUDA graph so that no fill is captured)."""
     N.require_cuda(x, "input")
+    if step_counter is not None:
+        N.require_cuda(step_counter, "step_counter")
     lib = N.load_library()
     outer, ch, inner = layout
     nbytes = lib.qsb_reduce_workspace_bytes(c_int64(outer), c_int64(ch), c_int64(inner))

@@ -312,14 +312,15 @@ class MagnitudePruningCallback(nn.Module):
             raise graphs.NotCapturable("a prune callback that will stop refreshing its mask later / an out-of-range "
                                        "sparsity")
         if self.mask_refresh_interval == 1 and t > 0:
-            out = self._fused_unstructured_step(x, sparsity, mask, t, counter=self.t.data)   # full-size masks (K9)
+            out = self._fused_unstructured_step(x, sparsity, mask, t,
+                                                counter=graphs.callback_counter(self, x.device))   # full-size masks (K9)
             if out is not None:
                 self.t.data.add_(1)
                 self._t_mirror.wrote(self.t, t + 1)
                 if self.forward_hook is not None:
                     self.forward_hook(mask, name)
                 return out
-        out = self._fused_structured_step(x, sparsity, mask, t, True, counter=self.t.data)
+        out = self._fused_structured_step(x, sparsity, mask, t, True, counter=graphs.callback_counter(self, x.device))
         if out is None:
             graphs.require_eager("this prune callback (the stock channel-mask step and the stock full-size-mask step "
                                  "with a refresh every step are capturable)")

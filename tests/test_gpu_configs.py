@@ -793,3 +793,50 @@ def test_prune_quantize_module_in_a_cuda_graph():
     assert len(ref_outs) == len(got_outs) == 4
     for (ya, ga), (yb, gb) in zip(ref_outs, got_outs):
         assert torch.equal(ya.view(torch.int32), yb.view(torch.int32)) and torch.equal(ga.view(torch.int32), gb.view(torch.int32))
+
+
+def test_graphed_prune_modules_whose_counters_started_on_the_host():
+    """prune()-wrapped modules built around CUDA weights but never moved with `.cuda()` keep their callback's `t`
+    Parameter on the host (as in the reference); graph mode moves it to the device before it becomes a kernel
+    argument.  5 eager + 2 warm-up + 4 replays equal 11 eager steps (masks, magnitudes, counters)."""
+    import qsparse_b200 as qs
+    qs.set_qsparse_options(log_on_created=False)
+    dev = torch.device("cuda:0")
+
+    class _W(nn.Module):
+        def __init__(self, w):
+            super().__init__()
+            self.weight = nn.Parameter(w.clone(), requires_grad=False)
+
+    def run(graph):
+        gen = torch.Generator(device=dev).manual_seed(21)
+        ws = [torch.randn(s, device=dev, generator=gen) * 0.02 for s in ((64, 32, 3, 3), (128, 257), (3, 100_000))]
+        with contextlib.redirect_stdout(io.StringIO()):
+            mods = nn.ModuleList([qs.prune(_W(w), sparsity=0.6, dimensions=set(range(w.dim())), start=0, interval=1,
+                                           repetition=1) for w in ws]).train()
+
+            def access():
+                with torch.no_grad():
+                    for m in mods:
+                        m._parameters["weight"].mul_(1.001)
+                        m.weight
+            for _ in range(5):
+                access()
+            assert not mods[0].prune.callback.t.is_cuda
+            if graph:
+                gs = qs.GraphedTrainStep(mods, access, warmup=2)
+                for _ in range(4):
+                    gs.replay()
+                gs.sync_host()
+            else:
+                for _ in range(6):
+                    access()
+        return mods
+
+    a, b = run(False), run(True)
+    for ma, mb in zip(a, b):
+        assert torch.equal(ma.prune.mask, mb.prune.mask)
+        assert torch.equal(ma.prune.callback.magnitude.view(torch.int32), mb.prune.callback.magnitude.view(torch.int32))
+        assert int(ma.prune.callback.t.item()) == int(mb.prune.callback.t.item()) == 11
+        assert ma.prune.callback._t() == mb.prune.callback._t() == 11
+        assert int(ma.prune._n_updates.item()) == int(mb.prune._n_updates.item())
