@@ -152,11 +152,12 @@ struct RowOp<kRowLine, FZP> {
 // MASKED: an element prune mask is applied first (the weight chain quantize(prune(layer)),
 // ref qsparse/imitation.py:61-71): statistics and quantization both see x * mask — a real multiply by
 // 0.0 / 1.0 like the reference's — in the same single read of the row (+1 B/elem for the mask).
-// 6 CTAs / SM (<= 42 registers) for the unmasked kernels with <= 2 vectors per thread: the line quantizer otherwise
-// takes 54 registers = 4 CTAs / SM, whose load / reduce / quantize phases then overlap too little
-// ([4096,4096]: 24.4 us against 19.5 us for the scaler kind, ncu r2ar)
+// (Tried: __launch_bounds__(256, 6) for the unmasked two-vector kernels — the line kind then takes 40 registers
+// instead of 54 and ncu's cold, isolated duration on [4096,4096] drops 24.5 -> 21.8 us, but the measured launch in
+// bench.py --config 3 went 25.1 -> 26.6 us and the back-to-back rate 24.6 -> 24.8 us: with the 134 MB of reads +
+// deferred write-backs the rate is bound by DRAM, not by occupancy.  Not adopted.)
 template <int KIND, bool FZP, int U, int G, bool MASKED>
-__global__ void __launch_bounds__(QSB_THREADS, (U <= 2 && !MASKED) ? 6 : 1)
+__global__ void __launch_bounds__(QSB_THREADS)
     row_quant_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ param,
                      float *__restrict__ decimal_out, const uint8_t *__restrict__ mask, int64_t rows, int inner,
                      RowConsts k) {
