@@ -14,10 +14,11 @@ themselves (``step_counter_dev`` of the C-ABI), so a replay computes exactly wha
 
 Capturable routes: every stock quantizer (Decimal / Scaler / Adaptive / Percentile; per tensor, per channel, the
 row-resident weight kernel, the fused weight chain), the stock magnitude prune callback with a channel mask or a
-full-size mask (the one-pass step K9) or a frozen mask, and fused prune -> quantize activation sites
+full-size mask (the one-pass step K9, per layer or batched by ``WeightSetPruner``) or a frozen mask, and fused
+prune -> quantize activation sites
 (``convert(..., fuse=True)``), past their timeouts and schedules, with the default mask refresh (every step, never
 stopping).  Every other stateful route (gradient / l0 importance, sparser refresh intervals on full-size masks,
-group-wise scale sharing before its clustering step, WeightSetPruner, ...) raises ``NotCapturable`` while graph mode
+group-wise scale sharing before its clustering step, ...) raises ``NotCapturable`` while graph mode
 is on rather than silently freezing a step index."""
 from __future__ import annotations
 

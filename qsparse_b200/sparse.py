@@ -299,7 +299,15 @@ class MagnitudePruningCallback(nn.Module):
     def _graph_mode_forward(self, x, sparsity, mask, t, name):
         """One step whose index lives on the device (qsparse_b200.graphs): only the stock structured route, with
         the default never-stopping mask refresh."""
-        self._precomputed = None
+        pre, self._precomputed = getattr(self, "_precomputed", None), None
+        if pre is not None and pre[0] == t and pre[1] is x and t > 0 and t < self.stop_mask_refresh:
+            # WeightSetPruner.step() already did this step for the whole weight set (same graph, earlier node)
+            out = _MaskApply.apply(x, mask, pre[2])
+            graphs.callback_counter(self, x.device).add_(1)
+            self._t_mirror.wrote(self.t, t + 1)
+            if self.forward_hook is not None:
+                self.forward_hook(mask, name)
+            return out
         if t >= self.stop_mask_refresh:
             # magnitude and mask are frozen for good (t only grows): the step is a mask apply and a counter
             out = apply_mask(x, mask)
@@ -495,8 +503,9 @@ class WeightSetPruner:
 
     @torch.no_grad()
     def step(self) -> int:
-        """Precompute this step for every eligible layer; returns how many layers were batched."""
-        graphs.require_eager("WeightSetPruner.step")
+        """Precompute this step for every eligible layer; returns how many layers were batched.
+        In graph mode (``qsparse_b200.graphs``) the one batched launch sequence reads the step index from the first
+        layer's callback counter, so all batched layers must be at the same step."""
         todo = []
         for mod, p in self.layers:
             e = self._eligible(mod, p)
@@ -509,6 +518,8 @@ class WeightSetPruner:
         by_t = {}
         for item in todo:
             by_t.setdefault(item[3], []).append(item)
+        if graphs.active() and len(by_t) != 1:
+            raise graphs.NotCapturable("WeightSetPruner over layers at different callback steps")
         for t, items in by_t.items():
             ws = [it[1].detach() for it in items]
             mags = [it[2].magnitude.data for it in items]
@@ -521,8 +532,10 @@ class WeightSetPruner:
             if self._hint_key != key:
                 self._hints = ops.new_select_hints(len(items), ws[0].device)
                 self._hint_key = key
-            ops.prune_unstructured_step_batched_(mags, ws, masks, outs, ks, t,
-                                                 hints=self._hints if SELECT_HINTS and len(by_t) == 1 else None)
+            counter = graphs.callback_counter(items[0][2], ws[0].device) if graphs.active() else None
+            ops.prune_unstructured_step_batched_(mags, ws, masks, outs, ks, 0 if counter is not None else t,
+                                                 hints=self._hints if SELECT_HINTS and len(by_t) == 1 else None,
+                                                 t_dev=counter)
             for it, o in zip(items, outs):
                 it[2]._precomputed = (t, it[1], o)
             done += len(items)

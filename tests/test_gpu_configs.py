@@ -808,17 +808,21 @@ def test_graphed_prune_modules_whose_counters_started_on_the_host():
             super().__init__()
             self.weight = nn.Parameter(w.clone(), requires_grad=False)
 
-    def run(graph):
+    def run(graph, batched=False):
         gen = torch.Generator(device=dev).manual_seed(21)
         ws = [torch.randn(s, device=dev, generator=gen) * 0.02 for s in ((64, 32, 3, 3), (128, 257), (3, 100_000))]
         with contextlib.redirect_stdout(io.StringIO()):
             mods = nn.ModuleList([qs.prune(_W(w), sparsity=0.6, dimensions=set(range(w.dim())), start=0, interval=1,
                                            repetition=1) for w in ws]).train()
+            pruner = qs.WeightSetPruner(mods) if batched else None
 
             def access():
                 with torch.no_grad():
                     for m in mods:
                         m._parameters["weight"].mul_(1.001)
+                    if pruner is not None:
+                        pruner.step()          # the whole weight set in one batched launch sequence
+                    for m in mods:
                         m.weight
             for _ in range(5):
                 access()
@@ -834,7 +838,8 @@ def test_graphed_prune_modules_whose_counters_started_on_the_host():
         return mods
 
     a, b = run(False), run(True)
-    for ma, mb in zip(a, b):
+    c = run(True, batched=True)                # ... and with WeightSetPruner.step() inside the captured step
+    for ma, mb in list(zip(a, b)) + list(zip(a, c)):
         assert torch.equal(ma.prune.mask, mb.prune.mask)
         assert torch.equal(ma.prune.callback.magnitude.view(torch.int32), mb.prune.callback.magnitude.view(torch.int32))
         assert int(ma.prune.callback.t.item()) == int(mb.prune.callback.t.item()) == 11
