@@ -152,12 +152,16 @@ struct RowOp<kRowLine, FZP> {
 // MASKED: an element prune mask is applied first (the weight chain quantize(prune(layer)),
 // ref qsparse/imitation.py:61-71): statistics and quantization both see x * mask — a real multiply by
 // 0.0 / 1.0 like the reference's — in the same single read of the row (+1 B/elem for the mask).
-// (Tried: __launch_bounds__(256, 6) for the unmasked two-vector kernels — the line kind then takes 40 registers
-// instead of 54 and ncu's cold, isolated duration on [4096,4096] drops 24.5 -> 21.8 us, but the measured launch in
-// bench.py --config 3 went 25.1 -> 26.6 us and the back-to-back rate 24.6 -> 24.8 us: with the 134 MB of reads +
-// deferred write-backs the rate is bound by DRAM, not by occupancy.  Not adopted.)
+// 6 CTAs / SM (<= 42 registers) for the unmasked kernels with <= 2 vectors per thread: the line quantizer otherwise
+// takes 54 registers = 4 CTAs / SM, whose load / reduce / quantize phases then overlap too little.  A/B on one box
+// (benchmarks/time_c3.py, 20 launches per graph on [4096,4096]): line 26.8 -> 21.9 us, scaler 21.0 -> 20.1 us,
+// decimal 22.4 -> 21.0 us; ncu, cold and isolated: line 24.5 -> 21.8 us.  (Single event-bracketed launches vary by
+// +-1.5 us from box to box, which hid this in bench.py --config 3.)
+#ifndef QSB_K8_MIN_CTAS
+#define QSB_K8_MIN_CTAS 6
+#endif
 template <int KIND, bool FZP, int U, int G, bool MASKED>
-__global__ void __launch_bounds__(QSB_THREADS)
+__global__ void __launch_bounds__(QSB_THREADS, (U <= 2 && !MASKED) ? QSB_K8_MIN_CTAS : 1)
     row_quant_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ param,
                      float *__restrict__ decimal_out, const uint8_t *__restrict__ mask, int64_t rows, int inner,
                      RowConsts k) {
