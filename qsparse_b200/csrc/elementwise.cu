@@ -24,6 +24,18 @@ void set_step_sigma10(int v);
 
 namespace qsb {
 
+// Outputs that do not fit the L2 anyway (>= 96 MB) are stored with L2::evict_first: their dirty lines then leave the
+// cache while the kernel still runs instead of being written back under the NEXT kernel's traffic, and the lines a
+// predecessor tagged evict_last (the fused statistics kernel's keep hint) survive longer.  Bench step, A/B with two
+// library builds on one box: 142.0 -> 140.1 us (forward alone 140.8, backward alone 142.9), dense line 165.1 -> 164.0
+// (profiles/r02_store_hint_ab.json).  Smaller outputs keep the default policy: a consumer may find them in L2.
+constexpr int64_t kStreamStoreBytes = 96ll << 20;
+template <class Op>
+int launch_map_big_out(const Op &op, const MapIO &io, const Layout &L, cudaStream_t stream) {
+  if (L.numel() * 4 >= kStreamStoreBytes) return launch_map<Op, Hint::STREAM, Hint::STREAM>(op, io, L, stream);
+  return launch_map<Op, Hint::STREAM, Hint::KEEP>(op, io, L, stream);
+}
+
 MapTuning &map_tuning() {
   static MapTuning t{0, 0, 1, 1};
   return t;
@@ -371,8 +383,7 @@ extern "C" int qsb_fq_pow2_fwd(const float *x, float *y,
   const float tof = (float)pow(2.0, -decimal_host);
   return dispatch_mask(mask_kind, [&](auto mk) {
     Pow2Op<decltype(mk)::value> op{decimal_dev, stride, toi, tof, mask_dev};
-    return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
-        op, io, L, (cudaStream_t)stream);
+    return launch_map_big_out(op, io, L, (cudaStream_t)stream);
   });
 }
 
@@ -396,8 +407,7 @@ extern "C" int qsb_fq_scaler_fwd(const float *x, float *y,
            y, nullptr, nullptr};
   return dispatch_mask(mask_kind, [&](auto mk) {
     ScalerOp<decltype(mk)::value> op{scaler_dev, stride, scaler_host, mask_dev};
-    return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
-        op, io, L, (cudaStream_t)stream);
+    return launch_map_big_out(op, io, L, (cudaStream_t)stream);
   });
 }
 
@@ -587,8 +597,7 @@ extern "C" int qsb_ste_bwd(const float *g, float *g_clamped_out, float *gx_out,
   return dispatch_mask(mask_kind, [&](auto mk) {
     constexpr int MK = decltype(mk)::value;
     auto run = [&](auto op) {
-      return launch_map<decltype(op), Hint::STREAM, Hint::KEEP>(
-          op, io, L, (cudaStream_t)stream);
+      return launch_map_big_out(op, io, L, (cudaStream_t)stream);
     };
     if (gc && gx)
       return run(SteOp<MK, true, true>{scale_dev, stride, s_host,
