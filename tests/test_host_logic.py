@@ -238,3 +238,36 @@ def test_layerwise_schedule_reference_behaviour_and_fixed_variant():
     assert target(fixed[0]) == 0.5 and target(fixed[1]) == 0.75
     for a, b in zip(kept, fixed):
         assert (a.start, a.interval, a.repetition, a.schedules) == (b.start, b.interval, b.repetition, b.schedules)
+
+
+def test_graph_mode_host_logic():
+    """qsparse_b200.graphs without a GPU: the mode flag nests and restores, routes that take a host step index refuse
+    to run in graph mode, the quantizers' call count is read the same way for the int and the Parameter form."""
+    import torch
+    from qsparse_b200 import graphs
+    from qsparse_b200.quantize import AdaptiveQuantizer, DecimalQuantizer
+    assert not graphs.active()
+    graphs.require_eager("anything")                     # a no-op outside graph mode
+    with graphs.graph_mode():
+        assert graphs.active()
+        with graphs.graph_mode():
+            assert graphs.active()
+        assert graphs.active()
+        with pytest.raises(graphs.NotCapturable):
+            graphs.require_eager("a route with a host step index")
+    assert not graphs.active()
+    with pytest.raises(ZeroDivisionError):
+        with graphs.graph_mode():
+            1 / 0
+    assert not graphs.active()                           # restored on the way out of an exception too
+    assert issubclass(graphs.NotCapturable, RuntimeError)
+    d = DecimalQuantizer()
+    d.t = 7
+    assert graphs.host_index(d) == 7
+    a = AdaptiveQuantizer()
+    a.t = torch.nn.Parameter(torch.zeros(1), requires_grad=False)   # what its first optimize() creates (ref :423-425)
+    a._t_host = 3
+    assert graphs.host_index(a) == 3
+    assert graphs.NO_REFRESH_INTERVAL == 1 << 30
+    import qsparse_b200
+    assert qsparse_b200.GraphedTrainStep is graphs.GraphedTrainStep
