@@ -166,6 +166,11 @@ class GraphedTrainStep:
                 continue
             if q._t_mirror.get(q._n_updates) <= q.timeout:
                 raise NotCapturable(f"QuantizeLayer {q.name!r} has not passed its timeout yet")
+        for cb in self.qcbs:
+            # group-wise scale sharing starts at call `group_timeout` (a host-side test, quantize.py:353): a graph
+            # captured before that would never start it
+            if getattr(cb, "group_num", -1) > 0 and hasattr(cb, "t") and host_index(cb) <= cb.group_timeout:
+                raise NotCapturable("a group-wise quantizer has not reached its group_timeout yet")
         for p in self.players:
             if not p.initted:
                 raise NotCapturable(f"PruneLayer {p.name!r} has not seen an input yet")
